@@ -1,0 +1,297 @@
+"""Batched synthetic-passport generator.
+
+Replaces the reference's per-file input pipeline
+(/root/reference/test/process_passport.js:674-816 `processPassport`) for the
+benchmark and the tests: instead of parsing one real SOD/DG JSON it builds,
+from a seed, any number of passports whose DG1 / DG15 / encapsulated content /
+signed attributes have the hashes at the bit offsets the circuit parameters
+name, signs the signed attributes and emits exactly the input object
+`writeToJson` (process_passport.js:659-672) would write:
+
+    dg1, dg15, signedAttributes, encapsulatedContent : "0"/"1" strings, message
+        bytes MSB-first, SHA-padded to whole blocks (padding(), :11-91)
+    pubkey, signature : decimal strings, 64-bit little-endian chunks
+        (bigintToArrayString, :125-135)
+    skIdentity        : "0x" + first 62 hex digits of SHA-256(EC) (:630,667)
+    slaveMerkleRoot   : "0x" + Poseidon3(pkHash, pkHash, 1) (:642-654)
+    slaveMerkleInclusionBranches : 80 x "0"
+
+No reference code is imported; the layout rules are restated from SURVEY.md
+section 8(d).
+"""
+from __future__ import annotations
+
+import hashlib
+import random
+from dataclasses import dataclass
+
+from .poseidon import poseidon
+
+TREE_DEPTH = 80
+
+
+@dataclass(frozen=True)
+class CircuitParams:
+    """The 10 template parameters of RegisterIdentityBuilder
+    (/root/reference/circuits/identityManagement/registerIdentityBuilder.circom:41-52)."""
+    sig_type: int = 1
+    dg_hash: int = 256
+    doc_type: int = 3
+    ec_blocks: int = 4
+    ec_shift: int = 600
+    dg1_shift: int = 248
+    aa_algo: int = 1
+    dg15_shift: int = 1496
+    dg15_blocks: int = 3
+    aa_shift: int = 256
+
+    def as_tuple(self):
+        return (self.sig_type, self.dg_hash, self.doc_type, self.ec_blocks, self.ec_shift,
+                self.dg1_shift, self.aa_algo, self.dg15_shift, self.dg15_blocks, self.aa_shift)
+
+    @property
+    def name(self):
+        return "registerIdentity_" + "_".join(str(x) for x in self.as_tuple())
+
+    def main_source(self, include_path):
+        """The generated root file, as writeToCircom does (process_passport.js:573-588)."""
+        args = ", ".join(str(x) for x in self.as_tuple())
+        return ("pragma circom 2.1.6;\n\n"
+                f'include "{include_path}";\n\n'
+                f"component main {{ public [slaveMerkleRoot] }} = RegisterIdentityBuilder({args});\n")
+
+
+# canonical north-star circuit (/root/reference/hardhat.config.ts:29)
+C3 = CircuitParams()
+
+
+# --------------------------------------------------------------------------- primes / keys
+def _is_probable_prime(n, rng, rounds=24):
+    if n < 2:
+        return False
+    for p in (2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31, 37):
+        if n % p == 0:
+            return n == p
+    d, s = n - 1, 0
+    while d % 2 == 0:
+        d //= 2
+        s += 1
+    for _ in range(rounds):
+        a = rng.randrange(2, n - 1)
+        x = pow(a, d, n)
+        if x in (1, n - 1):
+            continue
+        for _ in range(s - 1):
+            x = x * x % n
+            if x == n - 1:
+                break
+        else:
+            return False
+    return True
+
+
+def _gen_prime(bits, rng, e=65537):
+    while True:
+        p = rng.getrandbits(bits) | (3 << (bits - 2)) | 1
+        if p % e == 1:
+            continue
+        if _is_probable_prime(p, rng):
+            return p
+
+
+class RsaKey:
+    def __init__(self, bits, rng, e=65537):
+        while True:
+            p = _gen_prime(bits // 2, rng, e)
+            q = _gen_prime(bits // 2, rng, e)
+            if p != q and (p * q).bit_length() == bits:
+                break
+        self.n, self.e, self.p, self.q = p * q, e, p, q
+        d = pow(e, -1, (p - 1) * (q - 1))
+        self.dp, self.dq, self.qinv = d % (p - 1), d % (q - 1), pow(q, -1, p)
+        self.bits = bits
+
+    def private_op(self, m):
+        m1 = pow(m % self.p, self.dp, self.p)
+        m2 = pow(m % self.q, self.dq, self.q)
+        h = (self.qinv * (m1 - m2)) % self.p
+        return m2 + h * self.q
+
+
+_DIGEST_INFO = {
+    "sha256": bytes.fromhex("3031300d060960864801650304020105000420"),
+    "sha1": bytes.fromhex("3021300906052b0e03021a05000414"),
+}
+
+
+def pkcs1v15_sign(key: RsaKey, msg: bytes, hash_name="sha256"):
+    k = key.bits // 8
+    t = _DIGEST_INFO[hash_name] + hashlib.new(hash_name, msg).digest()
+    em = b"\x00\x01" + b"\xff" * (k - len(t) - 3) + b"\x00" + t
+    return key.private_op(int.from_bytes(em, "big"))
+
+
+_KEY_CACHE = {}
+
+
+def key_pool(bits, count, seed):
+    """Deterministic pool of RSA keys (the signer certificates of the synthetic state)."""
+    k = (bits, count, seed)
+    if k not in _KEY_CACHE:
+        rng = random.Random((seed << 16) ^ bits ^ 0x5A5A)
+        _KEY_CACHE[k] = [RsaKey(bits, rng) for _ in range(count)]
+    return _KEY_CACHE[k]
+
+
+# --------------------------------------------------------------------------- padding / packing
+def sha_pad(msg: bytes, block_bits=512) -> bytes:
+    """padding() of process_passport.js:11-91 (0x80, zeros, big-endian bit length)."""
+    bb = block_bits // 8
+    lb = 8 if block_bits == 512 else 16
+    pad = (bb - ((len(msg) + 1 + lb) % bb)) % bb
+    return msg + b"\x80" + b"\x00" * pad + (len(msg) * 8).to_bytes(lb, "big")
+
+
+def bytes_to_bits(b: bytes):
+    return [(x >> (7 - i)) & 1 for x in b for i in range(8)]
+
+
+def chunks_le(x: int, n: int, k: int):
+    """bigintToArray(n, k, x) of process_passport.js:113-123."""
+    mask = (1 << n) - 1
+    return [(x >> (n * i)) & mask for i in range(k)]
+
+
+def rsa_pubkey_hash(n: int):
+    """pk_hash of getFakeIdenData (process_passport.js:642-651) ==
+    passportVerificationBuilder.circom:182-191."""
+    c = chunks_le(n, 64, 15)
+    return poseidon([(c[3 * i] << 128) + (c[3 * i + 1] << 64) + c[3 * i + 2] for i in range(5)])
+
+
+_MRZ = "ABCDEFGHIJKLMNOPQRSTUVWXYZ0123456789<"
+
+
+def _hash_name(bits):
+    return {160: "sha1", 224: "sha224", 256: "sha256", 384: "sha384", 512: "sha512"}[bits]
+
+
+@dataclass
+class Passport:
+    """One synthetic passport: raw messages + the circuit input object."""
+    dg1: bytes
+    dg15: bytes
+    ec: bytes
+    sa: bytes
+    key_index: int
+    signature: int
+    inputs: dict
+
+
+class PassportFactory:
+    """Seeded generator for one circuit parameter set (RSA PKCS#1 v1.5 families)."""
+
+    def __init__(self, params: CircuitParams = C3, seed: int = 1, n_sig_keys: int = 4,
+                 n_aa_keys: int = 4):
+        if params.sig_type not in (1, 3):
+            raise NotImplementedError("synthetic generator: RSA-2048 PKCS#1 v1.5 (SIG 1/3) only")
+        self.params = params
+        self.seed = seed
+        self.sig_hash = 160 if params.sig_type == 3 else 256
+        self.block = 512
+        self.sig_keys = key_pool(2048, n_sig_keys, seed)
+        self.aa_keys = key_pool(1024, n_aa_keys, seed + 7) if params.aa_algo else []
+        self._pkhash = [rsa_pubkey_hash(k.n) for k in self.sig_keys]
+        self._roots = [poseidon([h, h, 1]) for h in self._pkhash]
+
+    # -- message builders -------------------------------------------------
+    def _dg1(self, rng):
+        p = self.params
+        if p.doc_type == 3:
+            body = bytes([0x61, 0x5B, 0x5F, 0x1F, 0x58]) + "".join(
+                rng.choice(_MRZ) for _ in range(88)).encode()
+        else:
+            body = bytes([0x61, 0x5D, 0x5F, 0x1F, 0x5A]) + "".join(
+                rng.choice(_MRZ) for _ in range(90)).encode()
+        return body
+
+    def _dg15(self, rng):
+        p = self.params
+        if not p.aa_algo:
+            return b""
+        key = self.aa_keys[rng.randrange(len(self.aa_keys))]
+        # DER SubjectPublicKeyInfo (RSA-1024) inside tag 6F: the modulus starts at byte 32
+        hdr = bytes.fromhex("6f81a230819f300d06092a864886f70d010101050003818d0030818902818100")
+        body = hdr + key.n.to_bytes(128, "big") + bytes.fromhex("0203010001")
+        lead = p.aa_shift // 8 - 32
+        if lead < 0:
+            raise ValueError("AA_SHIFT below 256 bits is not supported by the generator")
+        body = bytes(rng.randrange(256) for _ in range(lead)) + body
+        lo, hi = self._len_range(p.dg15_blocks)
+        if not (lo <= len(body) <= hi):
+            if len(body) < lo:
+                body += bytes(rng.randrange(256) for _ in range(lo - len(body)))
+            else:
+                raise ValueError("DG15 does not fit the requested block count")
+        return body
+
+    def _len_range(self, blocks):
+        """Message lengths (bytes) whose SHA padding gives exactly `blocks` blocks; the upper
+        end keeps clear of len % 64 == 56, see SURVEY.md appendix C.4."""
+        bb = self.block // 8
+        lb = 8 if self.block == 512 else 16
+        return (blocks - 1) * bb - lb + 1, blocks * bb - lb - 1
+
+    def make(self, index: int) -> Passport:
+        p = self.params
+        rng = random.Random((self.seed << 32) ^ (index * 0x9E3779B97F4A7C15 & 0xFFFFFFFFFFFFFFFF))
+        dgh = _hash_name(p.dg_hash)
+        sgh = _hash_name(self.sig_hash)
+        dg1 = self._dg1(rng)
+        dg15 = self._dg15(rng)
+        hlen = p.dg_hash // 8
+        # encapsulated content (LDS security object)
+        lo, hi = self._len_range(p.ec_blocks)
+        need = p.dg1_shift // 8 + hlen
+        if p.aa_algo:
+            need = max(need, p.dg15_shift // 8 + hlen)
+        lo = max(lo, need)
+        if lo > hi:
+            raise ValueError("encapsulated content does not fit EC_BLOCK_NUMBER")
+        ec = bytearray(rng.randrange(256) for _ in range(rng.randint(lo, hi)))
+        ec[0] = 0x30
+        o = p.dg1_shift // 8
+        ec[o:o + hlen] = hashlib.new(dgh, dg1).digest()
+        if p.aa_algo:
+            o = p.dg15_shift // 8
+            ec[o - 3:o] = bytes([0x0F, 0x04, hlen])
+            ec[o:o + hlen] = hashlib.new(dgh, dg15).digest()
+        ec = bytes(ec)
+        # signed attributes
+        slen = self.sig_hash // 8
+        lo, hi = self._len_range(2)
+        lo = max(lo, p.ec_shift // 8 + slen)
+        sa = bytearray(rng.randrange(256) for _ in range(rng.randint(lo, hi)))
+        sa[0] = 0x31
+        o = p.ec_shift // 8
+        sa[o:o + slen] = hashlib.new(sgh, ec).digest()
+        sa = bytes(sa)
+        ki = rng.randrange(len(self.sig_keys))
+        key = self.sig_keys[ki]
+        sig = pkcs1v15_sign(key, sa, sgh)
+        sk = hashlib.sha256(ec).hexdigest()[:62]
+        inputs = {
+            "dg1": [str(b) for b in bytes_to_bits(sha_pad(dg1, self.block))],
+            "dg15": [str(b) for b in bytes_to_bits(sha_pad(dg15, self.block))] if p.aa_algo else [],
+            "signedAttributes": [str(b) for b in bytes_to_bits(sha_pad(sa, self.block))],
+            "encapsulatedContent": [str(b) for b in bytes_to_bits(sha_pad(ec, self.block))],
+            "pubkey": [str(c) for c in chunks_le(key.n, 64, 32)],
+            "signature": [str(c) for c in chunks_le(sig, 64, 32)],
+            "skIdentity": "0x" + sk,
+            "slaveMerkleRoot": "0x" + format(self._roots[ki], "x"),
+            "slaveMerkleInclusionBranches": ["0"] * TREE_DEPTH,
+        }
+        return Passport(dg1, dg15, ec, sa, ki, sig, inputs)
+
+    def batch(self, start: int, count: int):
+        return [self.make(start + i) for i in range(count)]
