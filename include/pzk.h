@@ -1,0 +1,126 @@
+/*
+ * pzk.h - C ABI of the B200-native batched witness generator / R1CS checker.
+ *
+ * Drop-in boundary for ONE hot path of fizzy74/passport-zk-circuits: the pair
+ *     wasm_tester(circuit).calculateWitness(input)  ->  checkConstraints(w)
+ * (/root/reference/test/automatisationTest.js:37-51), the documented
+ *     generate_witness.js <wasm> <input.json> <out.wtns>   (calculateWTNSBin)
+ * (/root/reference/circuits/scripts/gen-witness.sh:25, prove.sh:25) and
+ * `snarkjs wtns check` semantics.
+ * A Node N-API shim, a cgo stub or Python ctypes bind exactly these symbols
+ * (INTEGRATION.md); nothing torch-typed crosses this boundary.
+ *
+ * Conventions
+ *   - field elements cross the boundary as 32 bytes, little endian, canonical
+ *     (non-Montgomery) - the layout of a .wtns section-2 entry;
+ *   - inputs are the flattened main-component input signals in witness order
+ *     (public inputs first, then private, each in declaration order);
+ *     pzk_circuit_meta_json() names them;
+ *   - every function returns 0 on success, a negative PZK_E* code otherwise;
+ *     pzk_last_error() gives the message.  Handles are single-writer.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point
+ *     returns PZK_ENODEVICE.
+ */
+#ifndef PZK_H
+#define PZK_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PZK_OK 0
+#define PZK_EINVAL -1
+#define PZK_EIO -2
+#define PZK_ENODEVICE -3
+#define PZK_ECUDA -4
+#define PZK_ECOMPILE -5
+#define PZK_ENOMEM -6
+#define PZK_EFORMAT -7
+
+/* per-lane status bits (mirror of the circom runtime's exception codes):
+ *   0 = witness valid and every constraint satisfied                                  */
+#define PZK_STATUS_ASSERT 1u      /* runtime assert() failed            ("Assert Failed.") */
+#define PZK_STATUS_CONSTRAINT 2u  /* a `===` / R1CS row does not hold   ("Assert Failed.") */
+#define PZK_STATUS_INPUT_RANGE 4u /* input outside its declared width or >= p              */
+#define PZK_STATUS_BIGDIV 8u      /* long_div precondition violated (modulus top limb 0)   */
+
+typedef struct pzk_circuit pzk_circuit;
+
+/* ---- compiler: the role of `circom --r1cs --wasm --sym`
+ *      (/root/reference/circuits/scripts/compile-circuit.sh:34).
+ * Writes <out_prefix>.pzkp (program), .r1cs and .sym.  bits_names/bits_widths declare
+ * main inputs that are narrower than a field element (e.g. "dg1":1, "pubkey":64). */
+int pzk_compile(const char* main_circom_path, const char* out_prefix, const char* const* bits_names,
+                const int* bits_widths, int n_bits, uint32_t segment_ops, char* err, size_t err_len);
+
+/* ---- circuit handle: the role of `new WitnessCalculator(wasm)` ---------------------- */
+int pzk_circuit_open(const char* program_path, int cuda_device, pzk_circuit** out);
+void pzk_circuit_close(pzk_circuit* c);
+const char* pzk_last_error(const pzk_circuit* c);
+uint32_t pzk_witness_size(const pzk_circuit* c);    /* nWitness (wire 0 = 1)              */
+uint32_t pzk_input_size(const pzk_circuit* c);      /* flattened main inputs              */
+uint32_t pzk_public_size(const pzk_circuit* c);     /* nPubOut + nPubIn                   */
+uint32_t pzk_constraint_count(const pzk_circuit* c);
+const char* pzk_circuit_meta_json(const pzk_circuit* c); /* main IO names/dims/offsets    */
+/* algorithmic cost of one witness, for roofline accounting              */
+int pzk_circuit_stats(const pzk_circuit* c, uint64_t* op_records, uint64_t* f_mul, uint64_t* f_inv,
+                      uint64_t* rows, uint64_t* terms, uint64_t* bytes_per_lane);
+
+/* ---- calculateWitness(input)  (witness_calculator.js, external) ----------
+ * witness: n_wires x 32 bytes.  *status receives the lane status, *first_bad the first
+ * failing constraint index or -1.  The witness is written even when status != 0.       */
+int pzk_calculate_witness(pzk_circuit* c, const uint8_t* inputs_le32, uint8_t* witness_le32,
+                          uint32_t* status, int64_t* first_bad);
+
+/* ---- calculateWTNSBin(input): byte-identical iden3 .wtns v2 --------------------------
+ * needs pzk_wtns_size() bytes in `out`.                                                */
+uint64_t pzk_wtns_size(const pzk_circuit* c);
+int pzk_calculate_wtns_bin(pzk_circuit* c, const uint8_t* inputs_le32, uint8_t* out, uint32_t* status,
+                           int64_t* first_bad);
+
+/* ---- batched path (the product): B independent passports ----------------------------
+ * inputs_le32 : [B][n_inputs][32] host memory
+ * status      : [B]            first_bad : [B] (may be NULL)
+ * public_le32 : [B][n_public][32] (may be NULL) - outputs then public inputs
+ * export_lanes/n_export/witnesses_le32: optional full witnesses for selected lanes,
+ *               witnesses_le32 is [n_export][n_wires][32].
+ * Computes every signal of every lane on the device, checks every constraint
+ * (checkConstraints semantics) and copies the results back.                            */
+int pzk_witness_batch(pzk_circuit* c, const uint8_t* inputs_le32, uint64_t batch, uint32_t* status,
+                      int64_t* first_bad, uint8_t* public_le32, const uint64_t* export_lanes,
+                      uint64_t n_export, uint8_t* witnesses_le32);
+
+/* device-resident variant for measurement: upload once, run many times, download once */
+int pzk_batch_upload(pzk_circuit* c, const uint8_t* inputs_le32, uint64_t batch);
+int pzk_batch_run(pzk_circuit* c, int check_rows); /* all tiles of the uploaded batch    */
+int pzk_batch_download(pzk_circuit* c, uint32_t* status, int64_t* first_bad, uint8_t* public_le32);
+/* accumulated CUDA-event time (ms) and launch counts per kernel family since the last reset:
+ * which = 0 eval, 1 row check, 2 export/public, 3 whole run.                           */
+int pzk_profile_get(pzk_circuit* c, int which, double* ms, uint64_t* launches);
+void pzk_profile_reset(pzk_circuit* c);
+void pzk_profile_enable(pzk_circuit* c, int on);
+/* lanes processed per tile (0 = choose from free device memory)                        */
+int pzk_set_tile_lanes(pzk_circuit* c, uint64_t lanes);
+uint64_t pzk_get_tile_lanes(const pzk_circuit* c);
+
+/* ---- snarkjs `wtns check` semantics on an explicit witness -------------------------
+ * r1cs_path: iden3 .r1cs v1; wtns: iden3 .wtns v2 bytes.  *verdict = 1 when every
+ * constraint holds, else 0 and *first_bad = index of the first failing constraint.
+ * Errors: PZK_EFORMAT when the primes differ ("Curve of the witness does not match").   */
+int pzk_wtns_check(const char* r1cs_path, const uint8_t* wtns, uint64_t wtns_len, int cuda_device,
+                   int* verdict, int64_t* first_bad, char* err, size_t err_len);
+/* batched: witnesses_le32 is [batch][n_wires][32] canonical                             */
+int pzk_r1cs_check_batch(const char* r1cs_path, const uint8_t* witnesses_le32, uint64_t batch,
+                         int cuda_device, int* verdicts, int64_t* first_bad, double* kernel_ms,
+                         char* err, size_t err_len);
+
+int pzk_device_count(void);
+const char* pzk_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,197 @@
+/*
+ * pzk_program.h - on-disk / in-memory format of a compiled circuit ("program").
+ *
+ * A program is what the from-scratch compiler (csrc/compiler) lowers a circom
+ * circuit to and what the CUDA evaluator executes lane-per-witness.  It plays
+ * the role of the `<name>.wasm` that circom emits for the reference
+ * (/root/reference/circuits/scripts/compile-circuit.sh:34,
+ *  /root/reference/circuits/scripts/gen-witness.sh:25).
+ *
+ * Value classes
+ *   U : exact unsigned 64-bit integer (the signal's canonical value is < 2^64)
+ *   F : BN254 Fr element in Montgomery form, 4 x 64-bit limbs (R = 2^256)
+ *   N : canonical (non-Montgomery) 256-bit integer, lives in an F slot; only a
+ *       temporary for circom's integer operators (>> & \ % < ...) on wide values
+ *
+ * Storage: two slot planes per lane tile, slot-major / lane-minor so that a warp
+ * touches 32 consecutive words:
+ *   U plane:  u64 U[slot][lane]
+ *   F plane:  u64 F[slot][limb 0..3][lane]
+ * Slots are reused by the compiler once a value is dead (after its last op use
+ * and after the segment in which its last constraint row is checked).
+ */
+#ifndef PZK_PROGRAM_H
+#define PZK_PROGRAM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PZK_MAGIC 0x314b5a50u /* "PZK1" */
+#define PZK_VERSION 3u
+
+/* ---- opcodes ------------------------------------------------------------ */
+enum PzkOpcode {
+  PZK_NOP = 0,
+  /* U class (wrapping 64-bit ring ops, exact integer ops) */
+  PZK_U_CONST = 1, /* dst = (b << 32) | a                                  */
+  PZK_U_ADD = 2,   /* dst = a + b                                            */
+  PZK_U_SUB = 3,
+  PZK_U_MUL = 4,
+  PZK_U_DIV = 5, /* integer quotient, x / 0 = 0                            */
+  PZK_U_MOD = 6,
+  PZK_U_SHR = 7, /* shift counts >= 64 give 0                              */
+  PZK_U_SHL = 8,
+  PZK_U_AND = 9,
+  PZK_U_OR = 10,
+  PZK_U_XOR = 11,
+  PZK_U_LT = 12, /* unsigned compare -> 0/1                                */
+  PZK_U_LE = 13,
+  PZK_U_EQ = 14,
+  PZK_U_NE = 15,
+  PZK_U_SEL = 16, /* dst = a ? b : c        (ext word holds c)              */
+  PZK_U_LUT = 17, /* dst = (imm16 >> (a | b<<1 | c<<2 | d<<3)) & 1  (ext)  */
+  PZK_I_LT = 18,  /* signed 64-bit compare -> 0/1                           */
+  PZK_I_LE = 19,
+  PZK_U_LUTV = 20, /* dst = list64[e + (a | b<<1 | c<<2 | d<<3)]     (ext)  */
+  /* F class */
+  PZK_F_CONST = 24, /* dst = fpool[a]                                       */
+  PZK_F_ADD = 25,
+  PZK_F_SUB = 26,
+  PZK_F_MUL = 27,
+  PZK_F_NEG = 28,
+  PZK_F_INV = 29,    /* dst = a^-1, inv(0) = 0                                */
+  PZK_F_FROM_U = 30, /* dst = Montgomery(a), a in U plane                     */
+  PZK_F_SEL = 31,    /* dst = a(U) ? b : c  (ext)                             */
+  PZK_F_EQ = 32,     /* dst(U) = (a == b)                                     */
+  PZK_F_NE = 33,
+  PZK_F_CSEL = 34,   /* dst = fpool[b + a(U)]                                 */
+  PZK_F_FROM_I = 35, /* dst = Montgomery(a) for a signed 64-bit a             */
+  /* N class (plain 256-bit integers held in F slots) */
+  PZK_N_FROM_F = 40, /* dst(N) = canonical(a)                                */
+  PZK_F_FROM_N = 41, /* dst(F) = Montgomery(a mod p)                         */
+  PZK_N_FROM_U = 42,
+  PZK_N_BIT = 43,    /* dst(U) = (a >> b_imm) & 1                             */
+  PZK_N_LOW = 44,    /* dst(U) = a mod 2^64                                   */
+  PZK_N_SHR = 45,    /* dst(N) = a >> b(U)                                    */
+  PZK_N_AND = 46,
+  PZK_N_OR = 47,
+  PZK_N_XOR = 48,
+  PZK_N_DIV = 49, /* dst(N) = a / b (0 if b == 0)                           */
+  PZK_N_MOD = 50,
+  PZK_N_SLT = 51, /* dst(U) = signed_rep(a) < signed_rep(b)                 */
+  PZK_N_SLE = 52,
+  PZK_N_SHL = 53, /* dst(N) = ((a << b(U)) & (2^254-1)) mod p               */
+  PZK_N_FITS = 54, /* dst(U) = (a < 2^64)                                   */
+  /* macro / control */
+  PZK_BIGDIV = 60,    /* long_div intrinsic, operands in the list pool       */
+  PZK_ASSERT_NZ = 61, /* lane status |= ASSERT when a(U) == 0                */
+  PZK_IN_U = 62,      /* dst(U) = input[a], range check: value < 2^imm16      */
+  PZK_IN_F = 63,      /* dst(F) = Montgomery(input[a]); value must be < p    */
+  PZK_OPCODE_MAX = 64
+};
+
+/* flags */
+#define PZK_FLAG_B_IMM 1u  /* U ops: operand b is the 32-bit immediate in .b */
+#define PZK_FLAG_B_POOL 2u /* F ops: operand b is fpool[.b]                  */
+#define PZK_FLAG_EXT 4u    /* the following 16-byte record is an extension   */
+
+typedef struct PzkOp {
+  uint8_t opc;
+  uint8_t flags;
+  uint16_t imm16;
+  uint32_t dst;
+  uint32_t a;
+  uint32_t b;
+} PzkOp;
+
+/* extension record that follows an op with PZK_FLAG_EXT */
+typedef struct PzkOpExt {
+  uint32_t c;
+  uint32_t d;
+  uint32_t e;
+  uint32_t f;
+} PzkOpExt;
+
+/* ---- lane status bits ---------------------------------------------------- */
+#define PZK_LANE_OK 0u
+#define PZK_LANE_ASSERT 1u       /* runtime assert(...) on signals failed        */
+#define PZK_LANE_CONSTRAINT 2u   /* some R1CS row failed ("Assert Failed.")      */
+#define PZK_LANE_INPUT_RANGE 4u  /* input outside the declared range / >= p     */
+#define PZK_LANE_BIGDIV_PRE 8u   /* long_div precondition violated (top limb 0) */
+
+/* ---- constraint rows (slot addressed, per segment) ---------------------- */
+/* term.ref : bits 30..31 = class (0 = U unsigned, 1 = I signed 64, 2 = F Montgomery),
+ *            bits 0..29 = slot
+ * term.coef: index into the coefficient pool                                */
+typedef struct PzkTerm {
+  uint32_t ref;
+  uint32_t coef;
+} PzkTerm;
+
+#define PZK_REF_CLS(r) ((r) >> 30)
+#define PZK_REF_SLOT(r) ((r) & 0x3fffffffu)
+#define PZK_REF_ZERO 0xFFFFFFFFu
+#define PZK_REF_ONE 0xFFFFFFFEu
+#define PZK_OPERAND_NONE 0xFFFFFFFFu
+
+/* row kinds */
+#define PZK_ROW_FIELD 0u /* generic: Montgomery arithmetic                  */
+#define PZK_ROW_INT 1u   /* all wires U, coefficients small: exact int math */
+
+typedef struct PzkRow {
+  uint32_t term_off; /* first term (A terms, then B, then C)               */
+  uint16_t na, nb;
+  uint16_t nc;
+  uint16_t kind;
+  uint32_t index; /* constraint index in the .r1cs file                 */
+} PzkRow;
+
+typedef struct PzkSegment {
+  uint64_t op_off, n_ops;   /* in 16-byte records (ext records included)    */
+  uint64_t row_off, n_rows;
+  uint64_t exp_off, n_exp;  /* export entries defined in this segment       */
+} PzkSegment;
+
+/* witness export entry: wire <- slot */
+typedef struct PzkExport {
+  uint32_t wire;
+  uint32_t ref; /* class bits + slot; PZK_REF_ZERO / PZK_REF_ONE constants */
+} PzkExport;
+
+typedef struct PzkInput {
+  uint32_t wire;   /* witness index of this main input element             */
+  uint32_t bits;   /* declared width (0 = full field element)              */
+} PzkInput;
+
+/* file = header, then the sections in this order, each 16-byte aligned */
+typedef struct PzkHeader {
+  uint32_t magic, version;
+  uint32_t n_wires;       /* witness length (wire 0 = constant 1)           */
+  uint32_t n_pub_out, n_pub_in, n_prv_in;
+  uint32_t n_constraints;
+  uint32_t n_u_slots, n_f_slots;
+  uint32_t n_segments;
+  uint32_t n_fpool;       /* 32-byte Montgomery constants                   */
+  uint32_t n_coef;        /* coefficient pool entries (3 x 32 bytes each)   */
+  uint32_t n_inputs;      /* flattened main inputs                          */
+  uint32_t n_list;        /* u32 operand-list pool                          */
+  uint64_t n_op_records;
+  uint64_t n_rows, n_terms, n_exports;
+  uint64_t stat_u_ops, stat_f_mul, stat_f_inv, stat_f_other, stat_bigdiv;
+  uint64_t reserved[4];
+} PzkHeader;
+
+/* coefficient pool entry */
+typedef struct PzkCoef {
+  uint64_t plain[4]; /* canonical value                                     */
+  uint64_t mont[4];  /* c * R mod p    (multiplies F-class wires)            */
+  uint64_t mont2[4]; /* c * R^2 mod p  (multiplies U-class wires)            */
+} PzkCoef;
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,407 @@
+/*
+ * ORACLE (test infrastructure; never linked into or called by the product path).
+ *
+ * ssa_ref.c - plain-C, one-witness-at-a-time evaluator of a compiled program
+ * (include/pzk_program.h) plus the constraint check, with straightforward
+ * arithmetic (no Montgomery tricks beyond a textbook CIOS product, bit-serial
+ * long division).  Two jobs:
+ *   1. checker for the CUDA kernels: same program, same inputs, results must be
+ *      bit-identical (tests/, __graft_entry__.smoke());
+ *   2. the CPU baseline of bench.py ("port": the reference's own wasm calculator,
+ *      /root/reference/test/automatisationTest.js:37-51, cannot run here - no node,
+ *      no circom - see SURVEY.md section 8c/8d).
+ * Together with oracle/circom_oracle.py (which interprets the reference's .circom
+ * sources directly) it closes the loop: circom sources -> Python big-int witness
+ * == compiled program evaluated here == CUDA kernels.
+ *
+ * Semantics restated per op from the circom operators they lower
+ * (SURVEY.md section 8a footnote); long division follows
+ * /root/reference/circuits/lib/circuits/bigInt/bigIntFunc.circom:190-232
+ * (long_div: true quotient / remainder digits in base 2^n).
+ */
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "pzk_program.h"
+
+typedef unsigned __int128 u128;
+
+static const uint64_t P[4] = {0x43e1f593f0000001ull, 0x2833e84879b97091ull, 0xb85045b68181585dull,
+                              0x30644e72e131a029ull};
+static const uint64_t PINV = 0xc2e1f593efffffffull;
+static const uint64_t R2[4] = {0x1bb8e645ae216da7ull, 0x53fe3ab1e35c59e3ull, 0x8c49833d53bb8085ull,
+                               0x0216d0b17f4e44a5ull};
+static const uint64_t ONE[4] = {1, 0, 0, 0};
+
+typedef struct PzkRefProgram {
+  PzkHeader h;
+  uint8_t* blob;
+  PzkSegment* segs;
+  PzkOp* ops;
+  uint64_t* fpool;
+  PzkCoef* coefs;
+  uint32_t* list;
+  PzkInput* inputs;
+  PzkRow* rows;
+  PzkTerm* terms;
+  PzkExport* exports;
+  char* meta;
+} PzkRefProgram;
+
+static uint64_t align16(uint64_t x) { return (x + 15) & ~15ull; }
+
+PzkRefProgram* pzk_ref_load(const char* path) {
+  FILE* f = fopen(path, "rb");
+  if (!f) return NULL;
+  fseek(f, 0, SEEK_END);
+  long sz = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  uint8_t* blob = (uint8_t*)malloc((size_t)sz + 16);
+  if (!blob || fread(blob, 1, (size_t)sz, f) != (size_t)sz) { fclose(f); free(blob); return NULL; }
+  fclose(f);
+  PzkRefProgram* p = (PzkRefProgram*)calloc(1, sizeof *p);
+  memcpy(&p->h, blob, sizeof p->h);
+  if (p->h.magic != PZK_MAGIC || p->h.version != PZK_VERSION) { free(blob); free(p); return NULL; }
+  p->blob = blob;
+  uint64_t pos = align16(sizeof(PzkHeader));
+  p->segs = (PzkSegment*)(blob + pos); pos = align16(pos + p->h.n_segments * sizeof(PzkSegment));
+  p->ops = (PzkOp*)(blob + pos); pos = align16(pos + p->h.n_op_records * sizeof(PzkOp));
+  p->fpool = (uint64_t*)(blob + pos); pos = align16(pos + (uint64_t)p->h.n_fpool * 32);
+  p->coefs = (PzkCoef*)(blob + pos); pos = align16(pos + (uint64_t)p->h.n_coef * sizeof(PzkCoef));
+  p->list = (uint32_t*)(blob + pos); pos = align16(pos + (uint64_t)p->h.n_list * 4);
+  p->inputs = (PzkInput*)(blob + pos); pos = align16(pos + (uint64_t)p->h.n_inputs * sizeof(PzkInput));
+  p->rows = (PzkRow*)(blob + pos); pos = align16(pos + p->h.n_rows * sizeof(PzkRow));
+  p->terms = (PzkTerm*)(blob + pos); pos = align16(pos + p->h.n_terms * sizeof(PzkTerm));
+  p->exports = (PzkExport*)(blob + pos); pos = align16(pos + p->h.n_exports * sizeof(PzkExport));
+  p->meta = (char*)(blob + pos);
+  return p;
+}
+void pzk_ref_free(PzkRefProgram* p) { if (p) { free(p->blob); free(p); } }
+uint32_t pzk_ref_n_wires(const PzkRefProgram* p) { return p->h.n_wires; }
+uint32_t pzk_ref_n_inputs(const PzkRefProgram* p) { return p->h.n_inputs; }
+uint32_t pzk_ref_n_constraints(const PzkRefProgram* p) { return p->h.n_constraints; }
+uint32_t pzk_ref_n_outputs(const PzkRefProgram* p) { return p->h.n_pub_out; }
+const char* pzk_ref_meta(const PzkRefProgram* p, uint64_t* len) { *len = p->h.reserved[0]; return p->meta; }
+
+/* ---- 256-bit helpers ------------------------------------------------------ */
+static int cmp4(const uint64_t* a, const uint64_t* b) {
+  for (int i = 3; i >= 0; i--) { if (a[i] < b[i]) return -1; if (a[i] > b[i]) return 1; }
+  return 0;
+}
+static uint64_t add4(uint64_t* r, const uint64_t* a, const uint64_t* b) {
+  u128 c = 0;
+  for (int i = 0; i < 4; i++) { c += (u128)a[i] + b[i]; r[i] = (uint64_t)c; c >>= 64; }
+  return (uint64_t)c;
+}
+static uint64_t sub4(uint64_t* r, const uint64_t* a, const uint64_t* b) {
+  uint64_t br = 0;
+  for (int i = 0; i < 4; i++) { u128 t = (u128)a[i] - b[i] - br; r[i] = (uint64_t)t; br = (uint64_t)(t >> 64) & 1; }
+  return br;
+}
+static int is_zero4(const uint64_t* a) { return (a[0] | a[1] | a[2] | a[3]) == 0; }
+static void fadd(uint64_t* r, const uint64_t* a, const uint64_t* b) {
+  uint64_t t[4]; uint64_t c = add4(t, a, b);
+  if (c || cmp4(t, P) >= 0) sub4(t, t, P);
+  memcpy(r, t, 32);
+}
+static void fsub(uint64_t* r, const uint64_t* a, const uint64_t* b) {
+  uint64_t t[4];
+  if (sub4(t, a, b)) add4(t, t, P);
+  memcpy(r, t, 32);
+}
+static void fmul(uint64_t* r, const uint64_t* a, const uint64_t* b) { /* a*b/R mod p */
+  uint64_t t[6] = {0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < 4; i++) {
+    u128 c = 0;
+    for (int j = 0; j < 4; j++) { c += (u128)a[j] * b[i] + t[j]; t[j] = (uint64_t)c; c >>= 64; }
+    c += t[4]; t[4] = (uint64_t)c; t[5] = (uint64_t)(c >> 64);
+    uint64_t m = t[0] * PINV;
+    c = (u128)m * P[0] + t[0]; c >>= 64;
+    for (int j = 1; j < 4; j++) { c += (u128)m * P[j] + t[j]; t[j - 1] = (uint64_t)c; c >>= 64; }
+    c += t[4]; t[3] = (uint64_t)c; t[4] = t[5] + (uint64_t)(c >> 64);
+  }
+  if (t[4] || cmp4(t, P) >= 0) sub4(t, t, P);
+  memcpy(r, t, 32);
+}
+static void to_mont(uint64_t* r, const uint64_t* a) { fmul(r, a, R2); }
+static void from_mont(uint64_t* r, const uint64_t* a) { fmul(r, a, ONE); }
+static void finv(uint64_t* r, const uint64_t* a) { /* a^(p-2), Montgomery in / out; inv(0)=0 */
+  uint64_t e[4], acc[4], base[4];
+  static const uint64_t two[4] = {2, 0, 0, 0};
+  sub4(e, P, two);
+  to_mont(acc, ONE);
+  memcpy(base, a, 32);
+  for (int i = 0; i < 256; i++) {
+    if ((e[i >> 6] >> (i & 63)) & 1) fmul(acc, acc, base);
+    fmul(base, base, base);
+  }
+  memcpy(r, acc, 32);
+}
+static void shr4(uint64_t* r, const uint64_t* a, unsigned s) {
+  uint64_t t[4] = {0, 0, 0, 0};
+  if (s < 256) {
+    unsigned ws = s >> 6, bs = s & 63;
+    for (unsigned i = 0; i + ws < 4; i++) {
+      t[i] = a[i + ws] >> bs;
+      if (bs && i + ws + 1 < 4) t[i] |= a[i + ws + 1] << (64 - bs);
+    }
+  }
+  memcpy(r, t, 32);
+}
+static void shl4(uint64_t* r, const uint64_t* a, unsigned s) {
+  uint64_t t[4] = {0, 0, 0, 0};
+  if (s < 256) {
+    unsigned ws = s >> 6, bs = s & 63;
+    for (int i = 3; i >= (int)ws; i--) {
+      t[i] = a[i - ws] << bs;
+      if (bs && i - (int)ws - 1 >= 0) t[i] |= a[i - ws - 1] >> (64 - bs);
+    }
+  }
+  memcpy(r, t, 32);
+}
+static void divmod4(const uint64_t* a, const uint64_t* b, uint64_t* q, uint64_t* m) {
+  uint64_t qq[4] = {0, 0, 0, 0}, rr[4] = {0, 0, 0, 0};
+  if (!is_zero4(b))
+    for (int i = 255; i >= 0; i--) {
+      shl4(rr, rr, 1);
+      rr[0] |= (a[i >> 6] >> (i & 63)) & 1;
+      if (cmp4(rr, b) >= 0) { sub4(rr, rr, b); qq[i >> 6] |= 1ull << (i & 63); }
+    }
+  if (q) memcpy(q, qq, 32);
+  if (m) memcpy(m, rr, 32);
+}
+static void reduce_p(uint64_t* a) { while (cmp4(a, P) >= 0) sub4(a, a, P); }
+static int is_neg(const uint64_t* a) { /* a > p/2 */
+  uint64_t h[4]; shr4(h, P, 1);
+  return cmp4(a, h) > 0;
+}
+static int scmp(const uint64_t* a, const uint64_t* b) {
+  int na = is_neg(a), nb = is_neg(b);
+  if (na != nb) return na ? -1 : 1;
+  return cmp4(a, b);
+}
+
+/* ---- long division of (k+m) n-bit limbs by k n-bit limbs, bit serial ------- */
+static int bigdiv(unsigned n, unsigned k, unsigned m, const uint64_t* a, const uint64_t* b, uint64_t* q,
+                  uint64_t* r) {
+  /* pack into 64-bit words (n <= 64) */
+  enum { W = 200 };
+  uint64_t A[W] = {0}, B[W] = {0}, Q[W] = {0}, Rm[W + 1] = {0};
+  unsigned abits = n * (k + m), bbits = n * k;
+  if ((abits + 63) / 64 + 1 > W) return -1;
+  for (unsigned i = 0; i < k + m; i++)
+    for (unsigned j = 0; j < n; j++)
+      if ((a[i] >> j) & 1) { unsigned pos = i * n + j; A[pos >> 6] |= 1ull << (pos & 63); }
+  for (unsigned i = 0; i < k; i++)
+    for (unsigned j = 0; j < n; j++)
+      if ((b[i] >> j) & 1) { unsigned pos = i * n + j; B[pos >> 6] |= 1ull << (pos & 63); }
+  if (b[k - 1] == 0) return 1; /* precondition of the circom function */
+  unsigned bw = (bbits + 63) / 64 + 1;
+  for (int i = (int)abits - 1; i >= 0; i--) {
+    /* Rm = (Rm << 1) | bit */
+    uint64_t carry = (A[i >> 6] >> (i & 63)) & 1;
+    for (unsigned w = 0; w < bw; w++) { uint64_t nc = Rm[w] >> 63; Rm[w] = (Rm[w] << 1) | carry; carry = nc; }
+    int ge = 1;
+    for (int w = (int)bw - 1; w >= 0; w--) {
+      if (Rm[w] > B[w]) break;
+      if (Rm[w] < B[w]) { ge = 0; break; }
+    }
+    if (ge) {
+      uint64_t br = 0;
+      for (unsigned w = 0; w < bw; w++) { u128 t = (u128)Rm[w] - B[w] - br; Rm[w] = (uint64_t)t; br = (uint64_t)(t >> 64) & 1; }
+      Q[i >> 6] |= 1ull << (i & 63);
+    }
+  }
+  uint64_t mask = n == 64 ? ~0ull : ((1ull << n) - 1);
+  for (unsigned i = 0; i <= m; i++) {
+    uint64_t v = 0;
+    for (unsigned j = 0; j < n; j++) { unsigned pos = i * n + j; v |= ((Q[pos >> 6] >> (pos & 63)) & 1) << j; }
+    q[i] = v & mask;
+  }
+  for (unsigned i = 0; i < k; i++) {
+    uint64_t v = 0;
+    for (unsigned j = 0; j < n; j++) { unsigned pos = i * n + j; v |= ((Rm[pos >> 6] >> (pos & 63)) & 1) << j; }
+    r[i] = v & mask;
+  }
+  return 0;
+}
+
+/* ---- constraint rows -------------------------------------------------------- */
+static void term_value(const PzkRefProgram* p, const PzkTerm* t, const uint64_t* U, const uint64_t* F, uint64_t* out) {
+  const PzkCoef* c = &p->coefs[t->coef];
+  if (t->ref == PZK_REF_ONE) { memcpy(out, c->mont, 32); return; }
+  uint32_t cls = PZK_REF_CLS(t->ref), slot = PZK_REF_SLOT(t->ref);
+  if (cls == 2) { fmul(out, c->mont, F + 4 * (uint64_t)slot); return; }
+  uint64_t v = U[slot];
+  if (cls == 1 && (int64_t)v < 0) {
+    uint64_t w[4] = {(uint64_t)(-(int64_t)v), 0, 0, 0}, z[4] = {0, 0, 0, 0};
+    fmul(out, c->mont2, w);
+    fsub(out, z, out);
+    return;
+  }
+  uint64_t w[4] = {v, 0, 0, 0};
+  fmul(out, c->mont2, w);
+}
+static void lin_value(const PzkRefProgram* p, const PzkTerm* t, unsigned n, const uint64_t* U, const uint64_t* F,
+                      uint64_t* acc) {
+  memset(acc, 0, 32);
+  for (unsigned i = 0; i < n; i++) { uint64_t v[4]; term_value(p, t + i, U, F, v); fadd(acc, acc, v); }
+}
+
+/*
+ * One witness.  inputs: n_inputs x 32 bytes little endian, canonical values in main-input wire order.
+ * witness (may be NULL): n_wires x 32 bytes little endian canonical.
+ * returns the lane status bits; *first_bad = index of the first failing constraint (or -1).
+ */
+uint32_t pzk_ref_witness(const PzkRefProgram* p, const uint8_t* inputs, uint8_t* witness, int64_t* first_bad,
+                         int check_rows) {
+  uint64_t* U = (uint64_t*)calloc((size_t)p->h.n_u_slots + 1, 8);
+  uint64_t* F = (uint64_t*)calloc((size_t)p->h.n_f_slots + 1, 32);
+  uint32_t status = 0;
+  int64_t bad = -1;
+  if (witness) { memset(witness, 0, (size_t)p->h.n_wires * 32); witness[0] = 1; }
+  for (uint32_t s = 0; s < p->h.n_segments; s++) {
+    const PzkSegment* sg = &p->segs[s];
+    for (uint64_t pc = sg->op_off; pc < sg->op_off + sg->n_ops; pc++) {
+      const PzkOp* o = &p->ops[pc];
+      const PzkOpExt* x = (const PzkOpExt*)(o + 1);
+      if (o->flags & PZK_FLAG_EXT) pc++;
+#define UB ((o->flags & PZK_FLAG_B_IMM) ? (uint64_t)o->b : U[o->b])
+#define FA (F + 4 * (uint64_t)o->a)
+#define FB ((o->flags & PZK_FLAG_B_POOL) ? (p->fpool + 4 * (uint64_t)o->b) : (F + 4 * (uint64_t)o->b))
+#define FD (F + 4 * (uint64_t)o->dst)
+      switch (o->opc) {
+        case PZK_NOP: break;
+        case PZK_U_CONST: U[o->dst] = ((uint64_t)o->b << 32) | o->a; break;
+        case PZK_U_ADD: U[o->dst] = U[o->a] + UB; break;
+        case PZK_U_SUB: U[o->dst] = U[o->a] - UB; break;
+        case PZK_U_MUL: U[o->dst] = U[o->a] * UB; break;
+        case PZK_U_DIV: { uint64_t b = UB; U[o->dst] = b ? U[o->a] / b : 0; break; }
+        case PZK_U_MOD: { uint64_t b = UB; U[o->dst] = b ? U[o->a] % b : 0; break; }
+        case PZK_U_SHR: { uint64_t b = UB; U[o->dst] = b >= 64 ? 0 : U[o->a] >> b; break; }
+        case PZK_U_SHL: { uint64_t b = UB; U[o->dst] = b >= 64 ? 0 : U[o->a] << b; break; }
+        case PZK_U_AND: U[o->dst] = U[o->a] & UB; break;
+        case PZK_U_OR: U[o->dst] = U[o->a] | UB; break;
+        case PZK_U_XOR: U[o->dst] = U[o->a] ^ UB; break;
+        case PZK_U_LT: U[o->dst] = U[o->a] < UB; break;
+        case PZK_U_LE: U[o->dst] = U[o->a] <= UB; break;
+        case PZK_U_EQ: U[o->dst] = U[o->a] == UB; break;
+        case PZK_U_NE: U[o->dst] = U[o->a] != UB; break;
+        case PZK_I_LT: U[o->dst] = (int64_t)U[o->a] < (int64_t)UB; break;
+        case PZK_I_LE: U[o->dst] = (int64_t)U[o->a] <= (int64_t)UB; break;
+        case PZK_U_SEL: U[o->dst] = U[o->a] ? U[o->b] : U[x->c]; break;
+        case PZK_U_LUT: case PZK_U_LUTV: {
+          unsigned idx = 0;
+          if (o->a != PZK_OPERAND_NONE) idx |= (unsigned)(U[o->a] & 1);
+          if (o->b != PZK_OPERAND_NONE) idx |= (unsigned)(U[o->b] & 1) << 1;
+          if (x->c != PZK_OPERAND_NONE) idx |= (unsigned)(U[x->c] & 1) << 2;
+          if (x->d != PZK_OPERAND_NONE) idx |= (unsigned)(U[x->d] & 1) << 3;
+          if (o->opc == PZK_U_LUT) U[o->dst] = (o->imm16 >> idx) & 1;
+          else U[o->dst] = (uint64_t)p->list[x->e + 2 * idx] | ((uint64_t)p->list[x->e + 2 * idx + 1] << 32);
+          break;
+        }
+        case PZK_F_CONST: memcpy(FD, p->fpool + 4 * (uint64_t)o->a, 32); break;
+        case PZK_F_ADD: fadd(FD, FA, FB); break;
+        case PZK_F_SUB: fsub(FD, FA, FB); break;
+        case PZK_F_MUL: fmul(FD, FA, FB); break;
+        case PZK_F_NEG: { uint64_t z[4] = {0, 0, 0, 0}; fsub(FD, z, FA); break; }
+        case PZK_F_INV: finv(FD, FA); break;
+        case PZK_F_FROM_U: { uint64_t w[4] = {U[o->a], 0, 0, 0}; to_mont(FD, w); break; }
+        case PZK_F_FROM_I: {
+          int64_t v = (int64_t)U[o->a];
+          uint64_t w[4] = {v < 0 ? (uint64_t)(-v) : (uint64_t)v, 0, 0, 0}, z[4] = {0, 0, 0, 0};
+          to_mont(w, w);
+          if (v < 0) fsub(FD, z, w); else memcpy(FD, w, 32);
+          break;
+        }
+        case PZK_F_SEL: memcpy(FD, U[o->a] ? (F + 4 * (uint64_t)o->b) : (F + 4 * (uint64_t)x->c), 32); break;
+        case PZK_F_EQ: U[o->dst] = memcmp(FA, FB, 32) == 0; break;
+        case PZK_F_NE: U[o->dst] = memcmp(FA, FB, 32) != 0; break;
+        case PZK_F_CSEL: memcpy(FD, p->fpool + 4 * ((uint64_t)o->b + U[o->a]), 32); break;
+        case PZK_N_FROM_F: from_mont(FD, FA); break;
+        case PZK_F_FROM_N: { uint64_t t[4]; memcpy(t, FA, 32); reduce_p(t); to_mont(FD, t); break; }
+        case PZK_N_FROM_U: { uint64_t w[4] = {U[o->a], 0, 0, 0}; memcpy(FD, w, 32); break; }
+        case PZK_N_BIT: U[o->dst] = o->b < 256 ? (FA[o->b >> 6] >> (o->b & 63)) & 1 : 0; break;
+        case PZK_N_LOW: U[o->dst] = FA[0]; break;
+        case PZK_N_FITS: U[o->dst] = (FA[1] | FA[2] | FA[3]) == 0; break;
+        case PZK_N_SHR: { uint64_t b = UB; uint64_t t[4]; shr4(t, FA, b > 256 ? 256 : (unsigned)b); memcpy(FD, t, 32); break; }
+        case PZK_N_SHL: {
+          uint64_t b = UB; uint64_t t[4] = {0, 0, 0, 0};
+          if (b < 254) { shl4(t, FA, (unsigned)b); t[3] &= 0x3fffffffffffffffull; reduce_p(t); }
+          memcpy(FD, t, 32); break;
+        }
+        case PZK_N_AND: { const uint64_t* b = FB; uint64_t t[4]; for (int i = 0; i < 4; i++) t[i] = FA[i] & b[i]; reduce_p(t); memcpy(FD, t, 32); break; }
+        case PZK_N_OR: { const uint64_t* b = FB; uint64_t t[4]; for (int i = 0; i < 4; i++) t[i] = FA[i] | b[i]; t[3] &= 0x3fffffffffffffffull; reduce_p(t); memcpy(FD, t, 32); break; }
+        case PZK_N_XOR: { const uint64_t* b = FB; uint64_t t[4]; for (int i = 0; i < 4; i++) t[i] = FA[i] ^ b[i]; t[3] &= 0x3fffffffffffffffull; reduce_p(t); memcpy(FD, t, 32); break; }
+        case PZK_N_DIV: { uint64_t q[4]; divmod4(FA, FB, q, NULL); memcpy(FD, q, 32); break; }
+        case PZK_N_MOD: { uint64_t m[4]; divmod4(FA, FB, NULL, m); memcpy(FD, m, 32); break; }
+        case PZK_N_SLT: U[o->dst] = scmp(FA, FB) < 0; break;
+        case PZK_N_SLE: U[o->dst] = scmp(FA, FB) <= 0; break;
+        case PZK_BIGDIV: {
+          const uint32_t* L = p->list + o->a;
+          unsigned n = L[0], k = L[1], m = L[2];
+          uint64_t a[200], b[200], q[200], r[200];
+          for (unsigned i = 0; i < k + m; i++) a[i] = U[L[3 + i]];
+          for (unsigned i = 0; i < k; i++) b[i] = U[L[3 + k + m + i]];
+          int rc = bigdiv(n, k, m, a, b, q, r);
+          if (rc) { status |= PZK_LANE_BIGDIV_PRE; memset(q, 0, sizeof q); memset(r, 0, sizeof r); }
+          for (unsigned i = 0; i <= m; i++) U[L[3 + k + m + k + i]] = q[i];
+          for (unsigned i = 0; i < k; i++) U[L[3 + k + m + k + m + 1 + i]] = r[i];
+          break;
+        }
+        case PZK_ASSERT_NZ: if (U[o->a] == 0) status |= PZK_LANE_ASSERT; break;
+        case PZK_IN_U: {
+          const uint64_t* v = (const uint64_t*)(inputs + 32 * (uint64_t)o->a);
+          uint64_t w[4]; memcpy(w, v, 32);
+          int bits = o->imm16;
+          if (w[1] | w[2] | w[3] || (bits < 64 && (w[0] >> bits))) status |= PZK_LANE_INPUT_RANGE;
+          U[o->dst] = w[0];
+          break;
+        }
+        case PZK_IN_F: {
+          uint64_t w[4]; memcpy(w, inputs + 32 * (uint64_t)o->a, 32);
+          if (cmp4(w, P) >= 0) { status |= PZK_LANE_INPUT_RANGE; reduce_p(w); }
+          to_mont(FD, w);
+          break;
+        }
+        default: fprintf(stderr, "ssa_ref: bad opcode %d\n", o->opc); abort();
+      }
+    }
+    if (check_rows) {
+      for (uint64_t r = sg->row_off; r < sg->row_off + sg->n_rows; r++) {
+        const PzkRow* row = &p->rows[r];
+        const PzkTerm* t = p->terms + row->term_off;
+        uint64_t a[4], b[4], c[4], ab[4];
+        lin_value(p, t, row->na, U, F, a);
+        lin_value(p, t + row->na, row->nb, U, F, b);
+        lin_value(p, t + row->na + row->nb, row->nc, U, F, c);
+        fmul(ab, a, b);
+        if (memcmp(ab, c, 32) != 0) {
+          status |= PZK_LANE_CONSTRAINT;
+          if (bad < 0 || (int64_t)row->index < bad) bad = row->index;
+        }
+      }
+    }
+    if (witness) {
+      for (uint64_t e = sg->exp_off; e < sg->exp_off + sg->n_exp; e++) {
+        const PzkExport* ex = &p->exports[e];
+        uint8_t* dst = witness + 32 * (uint64_t)ex->wire;
+        if (ex->ref == PZK_REF_ZERO) continue;
+        uint32_t cls = PZK_REF_CLS(ex->ref), slot = PZK_REF_SLOT(ex->ref);
+        uint64_t w[4] = {0, 0, 0, 0};
+        if (cls == 2) from_mont(w, F + 4 * (uint64_t)slot);
+        else if (cls == 1 && (int64_t)U[slot] < 0) { uint64_t m[4] = {(uint64_t)(-(int64_t)U[slot]), 0, 0, 0}; sub4(w, P, m); }
+        else w[0] = U[slot];
+        memcpy(dst, w, 32);
+      }
+    }
+  }
+  free(U); free(F);
+  if (first_bad) *first_bad = bad;
+  return status;
+}
+
+/* wtns check semantics on an explicit witness + .r1cs-equivalent rows is done in
+ * oracle/formats.py with Python integers; this file only checks its own rows. */

@@ -1,0 +1,1978 @@
+// compiler.cpp - see compiler.hpp.  Product code (never touches oracle/).
+#include "compiler.hpp"
+
+#include <chrono>
+#include <cstdarg>
+#include <cstring>
+
+namespace pzk {
+
+static const i128 I128_ONE = 1;
+static const i128 BOUND = I128_ONE << 126;
+static const i128 U64_MAX_ = (I128_ONE << 64) - 1;
+static const i128 I64_MIN_ = -(I128_ONE << 63);
+static const i128 I64_MAX_ = (I128_ONE << 63) - 1;
+
+static std::string fmt(const char* f, ...) {
+  char buf[2048];
+  va_list ap; va_start(ap, f); vsnprintf(buf, sizeof buf, f, ap); va_end(ap);
+  return buf;
+}
+
+// ---- circom constant semantics (SURVEY.md section 8a footnote) ---------------------
+static const U256 MASK254 = sub(shl(U256(1), 254), U256(1));
+static inline bool fr_is_neg(const U256& a) { return cmp(a, fr_half()) > 0; }
+static int fr_scmp(const U256& a, const U256& b) {
+  bool na = fr_is_neg(a), nb = fr_is_neg(b);
+  if (na != nb) return na ? -1 : 1;
+  return cmp(a, b);
+}
+static U256 fr_shr_c(const U256& a, const U256& b);
+static U256 fr_shl_c(const U256& a, const U256& b) {
+  if (fr_is_neg(b)) return fr_shr_c(a, fr_neg(b));
+  if (!b.fits64() || b.w[0] >= 254) return U256();
+  return fr_reduce(band(shl(a, (unsigned)b.w[0]), MASK254));
+}
+static U256 fr_shr_c(const U256& a, const U256& b) {
+  if (fr_is_neg(b)) return fr_shl_c(a, fr_neg(b));
+  if (!b.fits64() || b.w[0] >= 254) return U256();
+  return shr(a, (unsigned)b.w[0]);
+}
+static bool fold_bin(int op, const U256& a, const U256& b, U256& r) {
+  switch (op) {
+    case O_ADD: r = fr_add(a, b); return true;
+    case O_SUB: r = fr_sub(a, b); return true;
+    case O_MUL: r = fr_mul(a, b); return true;
+    case O_DIV: r = b.is_zero() ? U256() : fr_mul(a, fr_inv(b)); return true;
+    case O_IDIV: { if (b.is_zero()) { r = U256(); return true; } U256 q, m; divmod(a, b, q, m); r = q; return true; }
+    case O_MOD: { if (b.is_zero()) { r = U256(); return true; } U256 q, m; divmod(a, b, q, m); r = m; return true; }
+    case O_POW: r = fr_pow(a, b); return true;
+    case O_SHL: r = fr_shl_c(a, b); return true;
+    case O_SHR: r = fr_shr_c(a, b); return true;
+    case O_BAND: r = fr_reduce(band(a, b)); return true;
+    case O_BOR: r = fr_reduce(band(bor(a, b), MASK254)); return true;
+    case O_BXOR: r = fr_reduce(band(bxor(a, b), MASK254)); return true;
+    case O_EQ: r = U256(a == b); return true;
+    case O_NE: r = U256(a != b); return true;
+    case O_LT: r = U256(fr_scmp(a, b) < 0); return true;
+    case O_GT: r = U256(fr_scmp(a, b) > 0); return true;
+    case O_LE: r = U256(fr_scmp(a, b) <= 0); return true;
+    case O_GE: r = U256(fr_scmp(a, b) >= 0); return true;
+    case O_LAND: r = U256(!a.is_zero() && !b.is_zero()); return true;
+    case O_LOR: r = U256(!a.is_zero() || !b.is_zero()); return true;
+  }
+  return false;
+}
+static U256 fold_un(int op, const U256& a) {
+  switch (op) {
+    case O_NEG: return fr_neg(a);
+    case O_LNOT: return U256(a.is_zero());
+    case O_BNOT: return fr_reduce(band(bxor(a, MASK254), MASK254));
+  }
+  throw CompileError("bad unary operator");
+}
+// small signed view of a field constant: |v| < 2^62
+static bool small_signed(const U256& c, int64_t& out) {
+  if (c.fits64() && c.w[0] < (1ull << 62)) { out = (int64_t)c.w[0]; return true; }
+  U256 n = sub(FR_P, c);
+  if (n.fits64() && n.w[0] < (1ull << 62)) { out = -(int64_t)n.w[0]; return true; }
+  return false;
+}
+static U256 from_signed(int64_t v) { return v >= 0 ? U256((uint64_t)v) : sub(FR_P, U256((uint64_t)(-v))); }
+
+// ---- linear algebra for constraints -------------------------------------------------
+static void lin_addmul(Lin& dst, const Lin& src, const U256& k) {  // dst += k * src
+  if (k.is_zero()) return;
+  bool one = (k == U256(1));
+  std::vector<std::pair<uint32_t, U256>> out;
+  out.reserve(dst.t.size() + src.t.size());
+  size_t i = 0, j = 0;
+  while (i < dst.t.size() || j < src.t.size()) {
+    if (j >= src.t.size() || (i < dst.t.size() && dst.t[i].first < src.t[j].first)) out.push_back(dst.t[i++]);
+    else if (i >= dst.t.size() || src.t[j].first < dst.t[i].first) {
+      U256 c = one ? src.t[j].second : fr_mul(src.t[j].second, k);
+      if (!c.is_zero()) out.emplace_back(src.t[j].first, c);
+      j++;
+    } else {
+      U256 c = fr_add(dst.t[i].second, one ? src.t[j].second : fr_mul(src.t[j].second, k));
+      if (!c.is_zero()) out.emplace_back(dst.t[i].first, c);
+      i++; j++;
+    }
+  }
+  dst.t.swap(out);
+  dst.k = fr_add(dst.k, one ? src.k : fr_mul(src.k, k));
+}
+static void lin_scale(Lin& l, const U256& k) {
+  if (k == U256(1)) return;
+  if (k.is_zero()) { l.t.clear(); l.k = U256(); return; }
+  for (auto& t : l.t) t.second = fr_mul(t.second, k);
+  l.k = fr_mul(l.k, k);
+}
+
+struct Scope { std::vector<std::pair<int, Value>> vars; };
+typedef std::vector<Scope> Env;
+
+struct Ref {
+  enum K { NONE, VAR, SIG, COMP, UNKNOWN } k = NONE;
+  // SIG
+  Comp* comp = nullptr; Layout* lay = nullptr;
+  uint32_t off = 0; std::vector<int> dims; int skind = 0; int name = -1;
+  // COMP
+  std::vector<int> path;
+};
+
+struct Ctx {  // one template instance being executed (or nullptr inside functions)
+  Layout* lay = nullptr;
+  Comp* comp = nullptr;
+};
+
+struct RowRec { uint64_t off; uint32_t na, nb, nc; };
+
+struct Compiler::Impl {
+  SourceUnit unit;
+  CompileOptions opt;
+  std::string main_path;
+  int phase = 0;  // 0 = A, 1 = B
+  std::unordered_map<std::string, Layout*> layouts;
+  std::vector<Layout*> layout_list;
+  Layout* main_lay = nullptr;
+  std::vector<Comp*> comps;
+
+  // SSA values (id 0 is reserved = "none")
+  std::vector<uint8_t> v_cls;
+  std::vector<i128> v_lo, v_hi;
+  std::vector<int32_t> v_tbl;
+  std::vector<uint32_t> v_convF, v_convN, v_def;
+  std::vector<uint8_t> v_const;
+  std::unordered_map<uint32_t, U256> const_of;
+  std::vector<Table> tables;
+  std::vector<OpRec> ops;
+  std::vector<uint32_t> list_pool;
+  std::vector<U256> fpool;
+  std::unordered_map<U256, uint32_t, U256Hash> fpool_mont, fpool_plain, constU, constF;
+
+  // signals & constraints
+  std::vector<uint32_t> sig_val;  // per signal index -> value id (0 = unassigned)
+  std::vector<RowRec> rows;
+  std::vector<std::pair<uint32_t, uint32_t>> terms;  // (signal index, coef index)
+  std::vector<U256> coefs;
+  std::unordered_map<U256, uint32_t, U256Hash> coef_idx;
+
+  // function memo (scalar constant args)
+  std::unordered_map<std::string, Value> fn_memo;
+  int fn_depth = 0;
+  bool returned = false;
+  Value ret_val;
+
+  CompileStats* stats = nullptr;
+
+  // results of the back end
+  std::vector<uint32_t> sig2wire;
+  std::vector<uint32_t> v_slot;
+  std::vector<PzkOp> out_ops;  // 16-byte records
+  std::vector<PzkSegment> segs;
+  std::vector<PzkRow> out_rows;
+  std::vector<PzkTerm> out_terms;
+  std::vector<PzkExport> out_exports;
+  std::vector<PzkInput> out_inputs;
+  std::vector<uint32_t> out_list;
+  uint32_t n_u_slots = 0, n_f_slots = 0;
+  uint32_t n_pub_out = 0, n_pub_in = 0, n_prv_in = 0;
+  std::string meta_json;
+
+  const std::string& nm(int id) { return unit.names.str(id); }
+  [[noreturn]] void fail(const Stmt* s, const std::string& m) {
+    throw CompileError(fmt("%s:%d: %s", s ? unit.files[s->file].c_str() : "?", s ? s->line : 0, m.c_str()));
+  }
+  [[noreturn]] void fail(const std::string& m) { throw CompileError(m); }
+
+  // ================================================================== values
+  uint32_t new_value(int cls, i128 lo = 0, i128 hi = 0, int32_t tbl = -1) {
+    uint32_t id = (uint32_t)v_cls.size();
+    v_cls.push_back((uint8_t)cls); v_lo.push_back(lo); v_hi.push_back(hi); v_tbl.push_back(tbl);
+    v_convF.push_back(0); v_convN.push_back(0); v_def.push_back((uint32_t)ops.size()); v_const.push_back(0);
+    return id;
+  }
+  uint32_t emit(int opc, uint32_t dst, uint32_t a = 0, uint32_t b = 0, int flags = 0, int imm16 = 0,
+                uint32_t c = PZK_OPERAND_NONE, uint32_t d = PZK_OPERAND_NONE) {
+    OpRec o; o.opc = (uint8_t)opc; o.flags = (uint8_t)flags; o.imm16 = (uint16_t)imm16;
+    o.dst = dst; o.a = a; o.b = b; o.c = c; o.d = d;
+    ops.push_back(o);
+    return dst;
+  }
+  uint32_t pool_mont(const U256& c) {
+    auto it = fpool_mont.find(c);
+    if (it != fpool_mont.end()) return it->second;
+    uint32_t i = (uint32_t)fpool.size(); fpool.push_back(fr_to_mont(c)); fpool_mont[c] = i; return i;
+  }
+  uint32_t pool_plain(const U256& c) {
+    auto it = fpool_plain.find(c);
+    if (it != fpool_plain.end()) return it->second;
+    uint32_t i = (uint32_t)fpool.size(); fpool.push_back(c); fpool_plain[c] = i; return i;
+  }
+  // constant as a narrow (U/I) value
+  bool const_narrow(const U256& c, i128& v) {
+    if (c.fits64()) { v = (i128)c.w[0]; return true; }
+    U256 n = sub(FR_P, c);
+    if (n.fits64() && n.w[0] <= (1ull << 63)) { v = -(i128)n.w[0]; return true; }
+    return false;
+  }
+  uint32_t const_value_U(const U256& c) {  // c must be narrow
+    auto it = constU.find(c);
+    if (it != constU.end()) return it->second;
+    i128 v; if (!const_narrow(c, v)) fail("internal: const_value_U on wide constant");
+    uint64_t bits = (uint64_t)v;
+    uint32_t id = new_value(v >= 0 ? CLS_U : CLS_I, v, v);
+    emit(PZK_U_CONST, id, (uint32_t)bits, (uint32_t)(bits >> 32));
+    v_const[id] = 1; const_of[id] = c; constU[c] = id;
+    return id;
+  }
+  uint32_t const_value_F(const U256& c) {
+    auto it = constF.find(c);
+    if (it != constF.end()) return it->second;
+    uint32_t id = new_value(CLS_F);
+    emit(PZK_F_CONST, id, pool_mont(c));
+    v_const[id] = 1; const_of[id] = c; constF[c] = id;
+    return id;
+  }
+  uint32_t const_value(const U256& c) {
+    i128 v;
+    if (const_narrow(c, v)) return const_value_U(c);
+    return const_value_F(c);
+  }
+
+  bool narrow_of(const SVal& s, i128& lo, i128& hi) {
+    if (s.kind == 0) { i128 v; if (!const_narrow(s.c, v)) return false; lo = hi = v; return true; }
+    if (s.kind != 1) return false;
+    if (v_cls[s.id] == CLS_U || v_cls[s.id] == CLS_I) { lo = v_lo[s.id]; hi = v_hi[s.id]; return true; }
+    return false;
+  }
+  bool exact_u(const SVal& s, i128& hi) {  // canonical value provably in [0, 2^64)
+    if (s.kind == 0) { if (!s.c.fits64()) return false; hi = (i128)s.c.w[0]; return true; }
+    if (s.kind == 1 && v_cls[s.id] == CLS_U) { hi = v_hi[s.id]; return true; }
+    return false;
+  }
+  static int cls_for(i128 lo, i128 hi) {
+    if (lo >= 0 && hi <= U64_MAX_) return CLS_U;
+    if (lo >= I64_MIN_ && hi <= I64_MAX_) return CLS_I;
+    return -1;
+  }
+  uint32_t u_operand(const SVal& s) {
+    if (s.kind == 0) return const_value_U(s.c);
+    return s.id;
+  }
+  uint32_t to_F(const SVal& s) {
+    if (s.kind == 0) return const_value_F(s.c);
+    uint32_t id = s.id;
+    int c = v_cls[id];
+    if (c == CLS_F) return id;
+    if (v_convF[id]) return v_convF[id];
+    uint32_t r = new_value(CLS_F);
+    if (c == CLS_U) emit(PZK_F_FROM_U, r, id);
+    else if (c == CLS_I) emit(PZK_F_FROM_I, r, id);
+    else emit(PZK_F_FROM_N, r, id);
+    v_convF[id] = r;
+    return r;
+  }
+  uint32_t to_N(const SVal& s) {
+    if (s.kind == 0) {
+      uint32_t r = new_value(CLS_N);
+      emit(PZK_F_CONST, r, pool_plain(s.c));
+      return r;
+    }
+    uint32_t id = s.id;
+    int c = v_cls[id];
+    if (c == CLS_N) return id;
+    if (v_convN[id]) return v_convN[id];
+    uint32_t r = new_value(CLS_N);
+    if (c == CLS_U) emit(PZK_N_FROM_U, r, id);
+    else if (c == CLS_F) emit(PZK_N_FROM_F, r, id);
+    else { uint32_t f = to_F(s); emit(PZK_N_FROM_F, r, f); }
+    v_convN[id] = r;
+    return r;
+  }
+  SVal sv(uint32_t id) { return SVal::ssa(id); }
+
+  // ================================================================== tables
+  bool table_of(const SVal& s, Table& t, bool root_only) {
+    if (s.kind == 0) { int64_t v; if (!small_signed(s.c, v)) return false; t.n = 0; t.e[0] = v; return true; }
+    if (s.kind != 1) return false;
+    uint32_t id = s.id;
+    if (!root_only && v_tbl[id] >= 0) { t = tables[v_tbl[id]]; return true; }
+    if (v_cls[id] == CLS_U && v_lo[id] >= 0 && v_hi[id] <= 1) { t.n = 1; t.sup[0] = id; t.e[0] = 0; t.e[1] = 1; return true; }
+    return false;
+  }
+  // evaluate f over the union support of up to three tables
+  bool table_combine(const Table* in, int nin, Table& out, const std::function<bool(const int64_t*, int64_t&)>& f) {
+    uint32_t sup[12]; int n = 0;
+    for (int k = 0; k < nin; k++)
+      for (int j = 0; j < in[k].n; j++) {
+        bool dup = false;
+        for (int q = 0; q < n; q++) if (sup[q] == in[k].sup[j]) dup = true;
+        if (!dup) { if (n >= 12) return false; sup[n++] = in[k].sup[j]; }
+      }
+    if (n > 4) return false;
+    std::sort(sup, sup + n);
+    out.n = (uint8_t)n;
+    for (int j = 0; j < n; j++) out.sup[j] = sup[j];
+    int pos[3][4];
+    for (int k = 0; k < nin; k++)
+      for (int j = 0; j < in[k].n; j++)
+        for (int q = 0; q < n; q++) if (sup[q] == in[k].sup[j]) pos[k][j] = q;
+    for (int idx = 0; idx < (1 << n); idx++) {
+      int64_t args[3];
+      for (int k = 0; k < nin; k++) {
+        int sub = 0;
+        for (int j = 0; j < in[k].n; j++) sub |= ((idx >> pos[k][j]) & 1) << j;
+        args[k] = in[k].e[sub];
+      }
+      if (!f(args, out.e[idx])) return false;
+    }
+    return true;
+  }
+  bool try_table(const SVal* xs, int nx, Table& out, const std::function<bool(const int64_t*, int64_t&)>& f) {
+    Table in[3];
+    bool ok = true;
+    for (int k = 0; k < nx && ok; k++) ok = table_of(xs[k], in[k], false);
+    if (ok && table_combine(in, nx, out, f)) return true;
+    ok = true;
+    for (int k = 0; k < nx && ok; k++) ok = table_of(xs[k], in[k], true);
+    if (ok && table_combine(in, nx, out, f)) return true;
+    return false;
+  }
+  static bool table_is_const(const Table& t, int64_t& v) {
+    for (int i = 1; i < (1 << t.n); i++) if (t.e[i] != t.e[0]) return false;
+    v = t.e[0]; return true;
+  }
+  static bool table_bits(const Table& t) {
+    for (int i = 0; i < (1 << t.n); i++) if (t.e[i] != 0 && t.e[i] != 1) return false;
+    return true;
+  }
+  static void table_range(const Table& t, i128& lo, i128& hi) {
+    lo = hi = t.e[0];
+    for (int i = 1; i < (1 << t.n); i++) { if (t.e[i] < lo) lo = t.e[i]; if (t.e[i] > hi) hi = t.e[i]; }
+  }
+  // materialise a table-valued result as LUT / LUTV over its support
+  uint32_t emit_table_value(const Table& t) {
+    i128 lo, hi; table_range(t, lo, hi);
+    int cls = cls_for(lo, hi);
+    tables.push_back(t);
+    int32_t ti = (int32_t)tables.size() - 1;
+    uint32_t id = new_value(cls, lo, hi, ti);
+    uint32_t s[4] = {PZK_OPERAND_NONE, PZK_OPERAND_NONE, PZK_OPERAND_NONE, PZK_OPERAND_NONE};
+    for (int j = 0; j < t.n; j++) s[j] = t.sup[j];
+    if (table_bits(t)) {
+      int imm = 0;
+      for (int i = 0; i < 16; i++) if (t.e[i & ((1 << t.n) - 1)] == 1) imm |= 1 << i;
+      emit(PZK_U_LUT, id, s[0], s[1], PZK_FLAG_EXT, imm, s[2], s[3]);
+    } else {
+      uint32_t off = (uint32_t)list_pool.size();
+      for (int i = 0; i < 16; i++) {
+        uint64_t v = (uint64_t)t.e[i & ((1 << t.n) - 1)];
+        list_pool.push_back((uint32_t)v); list_pool.push_back((uint32_t)(v >> 32));
+      }
+      emit(PZK_U_LUTV, id, s[0], s[1], PZK_FLAG_EXT, 0, s[2], s[3]);
+      ops.back().imm16 = 0;
+      // ext.e carries the list offset: stash it in a side field by reusing opc-specific storage
+      lutv_off[(uint32_t)ops.size() - 1] = off;
+    }
+    stats->lut++;
+    return id;
+  }
+  std::unordered_map<uint32_t, uint32_t> lutv_off;  // op index -> list offset
+
+  // ================================================================== op emission
+  SVal fold_or_emit_bin(int op, const SVal& a, const SVal& b, const Stmt* at) {
+    if (a.kind == 2 || b.kind == 2) return SVal::unk();
+    if (a.kind == 0 && b.kind == 0) {
+      U256 r;
+      if (!fold_bin(op, a.c, b.c, r)) fail(at, "unsupported operator");
+      return SVal::konst(r);
+    }
+    if (phase == 0) return SVal::unk();
+    return emit_bin(op, a, b, at);
+  }
+
+  bool is_ring(int op) { return op == O_ADD || op == O_SUB || op == O_MUL; }
+
+  SVal emit_bin(int op, SVal a, SVal b, const Stmt* at) {
+    // canonicalise > and >= into < and <=
+    if (op == O_GT) { std::swap(a, b); op = O_LT; }
+    else if (op == O_GE) { std::swap(a, b); op = O_LE; }
+    // algebraic identities
+    if (op == O_ADD) { if (a.kind == 0 && a.c.is_zero()) return b; if (b.kind == 0 && b.c.is_zero()) return a; }
+    if (op == O_SUB && b.kind == 0 && b.c.is_zero()) return a;
+    if (op == O_MUL) {
+      if ((a.kind == 0 && a.c.is_zero()) || (b.kind == 0 && b.c.is_zero())) return SVal::konst(U256());
+      if (a.kind == 0 && a.c == U256(1)) return b;
+      if (b.kind == 0 && b.c == U256(1)) return a;
+    }
+    if (op == O_DIV && b.kind == 0) {
+      if (b.c.is_zero()) return SVal::konst(U256());
+      return emit_bin(O_MUL, a, SVal::konst(fr_inv(b.c)), at);
+    }
+    if (op == O_POW) {
+      if (b.kind != 0 || !b.c.fits64() || b.c.w[0] > 64) fail(at, "** with a signal-dependent or large exponent");
+      SVal r = SVal::konst(U256(1));
+      for (uint64_t i = 0; i < b.c.w[0]; i++) r = (r.kind == 0 && r.c == U256(1)) ? a : emit_bin(O_MUL, r, a, at);
+      return r;
+    }
+    // ---- exhaustive table evaluation over <= 4 root bits
+    {
+      SVal xs[2] = {a, b};
+      Table t;
+      auto f = [&](const int64_t* v, int64_t& r) {
+        U256 out;
+        if (!fold_bin(op, from_signed(v[0]), from_signed(v[1]), out)) return false;
+        return small_signed(out, r);
+      };
+      if (try_table(xs, 2, t, f)) {
+        int64_t cv;
+        if (table_is_const(t, cv)) return SVal::konst(from_signed(cv));
+        bool derived = false;
+        for (int k = 0; k < 2; k++)
+          if (xs[k].kind == 1 && v_tbl[xs[k].id] >= 0 && tables[v_tbl[xs[k].id]].n > 0 &&
+              !(tables[v_tbl[xs[k].id]].n == 1 && tables[v_tbl[xs[k].id]].sup[0] == xs[k].id)) derived = true;
+        if (!is_ring(op) || (table_bits(t) && derived)) return sv(emit_table_value(t));
+        // ring op with a table: emit plain arithmetic below but remember the table
+        SVal r = emit_bin_notable(op, a, b, at);
+        if (r.kind == 1 && (v_cls[r.id] == CLS_U || v_cls[r.id] == CLS_I)) {
+          tables.push_back(t); v_tbl[r.id] = (int32_t)tables.size() - 1;
+          i128 lo, hi; table_range(t, lo, hi);
+          int c = cls_for(lo, hi);
+          if (c >= 0 && c <= v_cls[r.id]) { v_cls[r.id] = (uint8_t)c; v_lo[r.id] = lo; v_hi[r.id] = hi; }
+        }
+        return r;
+      }
+    }
+    return emit_bin_notable(op, a, b, at);
+  }
+
+  SVal emit_u(int opc, const SVal& a, const SVal& b, int cls, i128 lo, i128 hi) {
+    uint32_t id;
+    uint32_t ia = u_operand(a);
+    if (b.kind == 0 && b.c.fits64() && b.c.w[0] < (1ull << 32)) {
+      id = new_value(cls, lo, hi);
+      emit(opc, id, ia, (uint32_t)b.c.w[0], PZK_FLAG_B_IMM);
+    } else {
+      uint32_t ib = u_operand(b);
+      id = new_value(cls, lo, hi);
+      emit(opc, id, ia, ib);
+    }
+    stats->u_ops++;
+    return sv(id);
+  }
+  SVal emit_f(int opc, const SVal& a, const SVal& b) {
+    uint32_t ia = to_F(a);
+    uint32_t id;
+    if (b.kind == 0) {
+      uint32_t pi = pool_mont(b.c);
+      id = new_value(CLS_F);
+      emit(opc, id, ia, pi, PZK_FLAG_B_POOL);
+    } else {
+      uint32_t ib = to_F(b);
+      id = new_value(CLS_F);
+      emit(opc, id, ia, ib);
+    }
+    if (opc == PZK_F_MUL) stats->f_mul++; else stats->f_other++;
+    return sv(id);
+  }
+  // N-class binary op; operand b may be a pool constant (plain) or immediate shift
+  SVal emit_n(int opc, const SVal& a, const SVal& b, bool b_is_shift) {
+    uint32_t ia = to_N(a);
+    uint32_t id;
+    if (b_is_shift) {
+      if (b.kind == 0) {
+        if (!b.c.fits64() || b.c.w[0] > 300) fail("shift amount too large");
+        id = new_value(CLS_N); emit(opc, id, ia, (uint32_t)b.c.w[0], PZK_FLAG_B_IMM);
+      } else {
+        i128 hi; if (!exact_u(b, hi)) fail("shift by a wide signal-dependent amount");
+        id = new_value(CLS_N); emit(opc, id, ia, b.id);
+      }
+    } else if (b.kind == 0) {
+      uint32_t pi = pool_plain(b.c);
+      id = new_value(CLS_N); emit(opc, id, ia, pi, PZK_FLAG_B_POOL);
+    } else {
+      uint32_t ib = to_N(b);
+      id = new_value(CLS_N); emit(opc, id, ia, ib);
+    }
+    stats->f_other++;
+    return sv(id);
+  }
+  SVal n_low(const SVal& n, i128 hi) {
+    uint32_t id = new_value(CLS_U, 0, hi);
+    emit(PZK_N_LOW, id, n.id);
+    return sv(id);
+  }
+  SVal truthy(const SVal& a, const Stmt* at) {  // -> 0/1 value
+    if (a.kind == 0) return SVal::konst(U256(!a.c.is_zero()));
+    i128 lo, hi;
+    if (narrow_of(a, lo, hi) && lo >= 0 && hi <= 1) return a;
+    return emit_bin(O_NE, a, SVal::konst(U256()), at);
+  }
+
+  SVal emit_bin_notable(int op, const SVal& a, const SVal& b, const Stmt* at) {
+    i128 alo, ahi, blo, bhi;
+    bool an = narrow_of(a, alo, ahi), bn = narrow_of(b, blo, bhi);
+    switch (op) {
+      case O_ADD: case O_SUB: case O_MUL: {
+        if (an && bn) {
+          i128 lo, hi; bool ok = true;
+          if (op == O_ADD) { lo = alo + blo; hi = ahi + bhi; }
+          else if (op == O_SUB) { lo = alo - bhi; hi = ahi - blo; }
+          else {
+            i128 c[4]; ok = !__builtin_mul_overflow(alo, blo, &c[0]) && !__builtin_mul_overflow(alo, bhi, &c[1]) &&
+                            !__builtin_mul_overflow(ahi, blo, &c[2]) && !__builtin_mul_overflow(ahi, bhi, &c[3]);
+            if (ok) { lo = hi = c[0]; for (int i = 1; i < 4; i++) { if (c[i] < lo) lo = c[i]; if (c[i] > hi) hi = c[i]; } }
+          }
+          if (ok && lo > -BOUND && hi < BOUND) {
+            int cls = cls_for(lo, hi);
+            if (cls >= 0) {
+              if ((op == O_ADD || op == O_MUL) && a.kind == 0) return emit_u(op == O_ADD ? PZK_U_ADD : PZK_U_MUL, b, a, cls, lo, hi);
+              return emit_u(op == O_ADD ? PZK_U_ADD : op == O_SUB ? PZK_U_SUB : PZK_U_MUL, a, b, cls, lo, hi);
+            }
+          }
+        }
+        if ((op == O_ADD || op == O_MUL) && a.kind == 0) return emit_f(op == O_ADD ? PZK_F_ADD : PZK_F_MUL, b, a);
+        return emit_f(op == O_ADD ? PZK_F_ADD : op == O_SUB ? PZK_F_SUB : PZK_F_MUL, a, b);
+      }
+      case O_DIV: {
+        // a / b = a * inv(b), inv(0) = 0
+        uint32_t ib = to_F(b);
+        uint32_t inv = new_value(CLS_F);
+        emit(PZK_F_INV, inv, ib);
+        stats->f_inv++;
+        if (a.kind == 0 && a.c == U256(1)) return sv(inv);
+        return emit_f(PZK_F_MUL, sv(inv), a);
+      }
+      case O_IDIV: case O_MOD: {
+        i128 ah, bh;
+        if (exact_u(a, ah) && exact_u(b, bh)) {
+          if (b.kind == 0 && b.c.w[0] && (b.c.w[0] & (b.c.w[0] - 1)) == 0) {
+            int k = __builtin_ctzll(b.c.w[0]);
+            if (op == O_IDIV) return emit_u(PZK_U_SHR, a, SVal::konst(U256((uint64_t)k)), CLS_U, 0, ah >> k);
+            return emit_u(PZK_U_AND, a, SVal::konst(U256(b.c.w[0] - 1)), CLS_U, 0, std::min<i128>(ah, (i128)b.c.w[0] - 1));
+          }
+          if (op == O_IDIV) return emit_u(PZK_U_DIV, a, b, CLS_U, 0, ah);
+          return emit_u(PZK_U_MOD, a, b, CLS_U, 0, std::min<i128>(ah, bh > 0 ? bh - 1 : 0));
+        }
+        // wide: power-of-two divisors become shifts / masks
+        if (b.kind == 0 && !b.c.is_zero()) {
+          int bl = b.c.bitlen();
+          if (b.c == shl(U256(1), bl - 1)) {
+            int k = bl - 1;
+            if (op == O_IDIV) return shift_right(a, k, at);
+            if (k <= 64) {
+              SVal n = sv(to_N(a));
+              SVal low = n_low(n, U64_MAX_);
+              if (k == 64) return low;
+              return emit_u(PZK_U_AND, low, SVal::konst(U256((1ull << k) - 1)), CLS_U, 0, ((i128)1 << k) - 1);
+            }
+          }
+        }
+        SVal r = emit_n(op == O_IDIV ? PZK_N_DIV : PZK_N_MOD, a, b, false);
+        if (op == O_MOD && exact_u(b, bh)) return n_low(r, bh > 0 ? bh - 1 : 0);
+        return r;
+      }
+      case O_SHR: {
+        if (b.kind == 0 && b.c.fits64() && b.c.w[0] < 254) return shift_right(a, (int)b.c.w[0], at);
+        i128 ah, bh;
+        if (exact_u(a, ah) && exact_u(b, bh)) return emit_u(PZK_U_SHR, a, b, CLS_U, 0, ah);
+        return emit_n(PZK_N_SHR, a, b, true);
+      }
+      case O_SHL: {
+        i128 ah, bh;
+        if (exact_u(a, ah) && b.kind == 0 && b.c.fits64() && b.c.w[0] < 64) {
+          i128 hi = ah << (int)b.c.w[0];
+          if (hi <= U64_MAX_) return emit_u(PZK_U_SHL, a, b, CLS_U, 0, hi);
+        }
+        (void)bh;
+        return emit_n(PZK_N_SHL, a, b, true);
+      }
+      case O_BAND: case O_BOR: case O_BXOR: {
+        i128 ah, bh;
+        if (exact_u(a, ah) && exact_u(b, bh)) {
+          i128 hi = op == O_BAND ? std::min(ah, bh) : U64_MAX_;
+          if (op != O_BAND) { int bl = 0; i128 m = std::max(ah, bh); while (m) { bl++; m >>= 1; } hi = bl >= 64 ? U64_MAX_ : (((i128)1 << bl) - 1); }
+          if (a.kind == 0) return emit_u(op == O_BAND ? PZK_U_AND : op == O_BOR ? PZK_U_OR : PZK_U_XOR, b, a, CLS_U, 0, hi);
+          return emit_u(op == O_BAND ? PZK_U_AND : op == O_BOR ? PZK_U_OR : PZK_U_XOR, a, b, CLS_U, 0, hi);
+        }
+        if (op == O_BAND) {
+          // (x >> k) & 1 on a wide value -> single bit extract
+          const SVal* wide = nullptr; const SVal* msk = nullptr;
+          if (b.kind == 0) { wide = &a; msk = &b; } else if (a.kind == 0) { wide = &b; msk = &a; }
+          if (wide && msk->c.fits64()) {
+            if (msk->c.w[0] == 1 && wide->kind == 1 && v_cls[wide->id] == CLS_N) {
+              const OpRec& d = ops[v_def[wide->id]];
+              if (d.opc == PZK_N_SHR && (d.flags & PZK_FLAG_B_IMM) && d.dst == wide->id && d.b < 256) {
+                uint32_t id = new_value(CLS_U, 0, 1);
+                emit(PZK_N_BIT, id, d.a, d.b, PZK_FLAG_B_IMM);
+                stats->u_ops++;
+                return sv(id);
+              }
+            }
+            SVal low = n_low(sv(to_N(*wide)), U64_MAX_);
+            return emit_u(PZK_U_AND, low, *msk, CLS_U, 0, (i128)msk->c.w[0]);
+          }
+        }
+        return emit_n(op == O_BAND ? PZK_N_AND : op == O_BOR ? PZK_N_OR : PZK_N_XOR, a, b, false);
+      }
+      case O_LT: case O_LE: {
+        i128 ah, bh;
+        if (exact_u(a, ah) && exact_u(b, bh)) {
+          if (a.kind == 0) {  // c < x  -> need operand a as a value
+            uint32_t ia = const_value_U(a.c);
+            uint32_t id = new_value(CLS_U, 0, 1);
+            emit(op == O_LT ? PZK_U_LT : PZK_U_LE, id, ia, b.id);
+            stats->u_ops++;
+            return sv(id);
+          }
+          return emit_u(op == O_LT ? PZK_U_LT : PZK_U_LE, a, b, CLS_U, 0, 1);
+        }
+        if (an && bn && alo >= I64_MIN_ && ahi <= I64_MAX_ && blo >= I64_MIN_ && bhi <= I64_MAX_) {
+          uint32_t ia = u_operand(a), ib = u_operand(b);
+          uint32_t id = new_value(CLS_U, 0, 1);
+          emit(op == O_LT ? PZK_I_LT : PZK_I_LE, id, ia, ib);
+          stats->u_ops++;
+          return sv(id);
+        }
+        uint32_t ia = to_N(a), ib = to_N(b);
+        uint32_t id = new_value(CLS_U, 0, 1);
+        emit(op == O_LT ? PZK_N_SLT : PZK_N_SLE, id, ia, ib);
+        stats->f_other++;
+        return sv(id);
+      }
+      case O_EQ: case O_NE: {
+        if (an && bn) {
+          bool a_u = alo >= 0, b_u = blo >= 0;
+          bool compat = (a_u && b_u) || (ahi <= I64_MAX_ && bhi <= I64_MAX_);
+          if (compat) {
+            if (a.kind == 0) return emit_u(op == O_EQ ? PZK_U_EQ : PZK_U_NE, b, a, CLS_U, 0, 1);
+            return emit_u(op == O_EQ ? PZK_U_EQ : PZK_U_NE, a, b, CLS_U, 0, 1);
+          }
+        }
+        const SVal& x = a.kind == 0 ? b : a;
+        const SVal& y = a.kind == 0 ? a : b;
+        uint32_t ia = to_F(x);
+        uint32_t id;
+        if (y.kind == 0) { uint32_t pi = pool_mont(y.c); id = new_value(CLS_U, 0, 1); emit(op == O_EQ ? PZK_F_EQ : PZK_F_NE, id, ia, pi, PZK_FLAG_B_POOL); }
+        else { uint32_t ib = to_F(y); id = new_value(CLS_U, 0, 1); emit(op == O_EQ ? PZK_F_EQ : PZK_F_NE, id, ia, ib); }
+        stats->f_other++;
+        return sv(id);
+      }
+      case O_LAND: case O_LOR: {
+        SVal ta = truthy(a, at), tb = truthy(b, at);
+        if (ta.kind == 0) return (op == O_LAND) ? (ta.c.is_zero() ? ta : tb) : (ta.c.is_zero() ? tb : ta);
+        if (tb.kind == 0) return (op == O_LAND) ? (tb.c.is_zero() ? tb : ta) : (tb.c.is_zero() ? ta : tb);
+        return emit_u(op == O_LAND ? PZK_U_AND : PZK_U_OR, ta, tb, CLS_U, 0, 1);
+      }
+    }
+    fail(at, "unsupported operator on signals");
+  }
+
+  SVal shift_right(const SVal& a, int k, const Stmt* at) {
+    (void)at;
+    if (k == 0) return a;
+    i128 ah;
+    if (exact_u(a, ah)) {
+      if (k >= 64) return SVal::konst(U256());
+      return emit_u(PZK_U_SHR, a, SVal::konst(U256((uint64_t)k)), CLS_U, 0, ah >> k);
+    }
+    SVal r = emit_n(PZK_N_SHR, a, SVal::konst(U256((uint64_t)k)), true);
+    if (254 - k <= 64) return n_low(r, (((i128)1) << (254 - k)) - 1);
+    return r;
+  }
+
+  SVal emit_un(int op, const SVal& a, const Stmt* at) {
+    if (a.kind == 2) return SVal::unk();
+    if (a.kind == 0) return SVal::konst(fold_un(op, a.c));
+    if (phase == 0) return SVal::unk();
+    if (op == O_NEG) return emit_bin(O_SUB, SVal::konst(U256()), a, at);
+    if (op == O_LNOT) return emit_bin(O_EQ, a, SVal::konst(U256()), at);
+    // ~x = (x ^ mask) mod p
+    return emit_bin(O_BXOR, a, SVal::konst(MASK254), at);
+  }
+
+  SVal emit_select(const SVal& c, const SVal& x, const SVal& y, const Stmt* at) {
+    if (c.kind == 2 || x.kind == 2 || y.kind == 2) return SVal::unk();
+    if (c.kind == 0) return c.c.is_zero() ? y : x;
+    // table
+    {
+      SVal xs[3] = {c, x, y};
+      Table t;
+      auto f = [&](const int64_t* v, int64_t& r) { r = v[0] != 0 ? v[1] : v[2]; return true; };
+      if (try_table(xs, 3, t, f)) {
+        int64_t cv;
+        if (table_is_const(t, cv)) return SVal::konst(from_signed(cv));
+        return sv(emit_table_value(t));
+      }
+    }
+    SVal tc = truthy(c, at);
+    i128 xlo, xhi, ylo, yhi;
+    if (narrow_of(x, xlo, xhi) && narrow_of(y, ylo, yhi)) {
+      i128 lo = std::min(xlo, ylo), hi = std::max(xhi, yhi);
+      int cls = cls_for(lo, hi);
+      if (cls >= 0) {
+        uint32_t ix = u_operand(x), iy = u_operand(y);
+        uint32_t id = new_value(cls, lo, hi);
+        emit(PZK_U_SEL, id, tc.id, ix, PZK_FLAG_EXT, 0, iy);
+        stats->u_ops++;
+        return sv(id);
+      }
+    }
+    uint32_t ix = to_F(x), iy = to_F(y);
+    uint32_t id = new_value(CLS_F);
+    emit(PZK_F_SEL, id, tc.id, ix, PZK_FLAG_EXT, 0, iy);
+    stats->f_other++;
+    return sv(id);
+  }
+
+  // ================================================================== algebra
+  AlgP alg_const(const U256& c) { AlgP a = std::make_shared<Alg>(); a->deg = 0; a->c.k = c; return a; }
+  AlgP alg_sig(uint32_t sig) { AlgP a = std::make_shared<Alg>(); a->deg = 1; a->c.t.emplace_back(sig, U256(1)); return a; }
+  AlgP alg_bad() { AlgP a = std::make_shared<Alg>(); a->deg = 3; return a; }
+  AlgP alg_of(const SVal& s) {
+    if (s.alg) return s.alg;
+    if (s.kind == 0) return alg_const(s.c);
+    return alg_bad();
+  }
+  AlgP alg_bin(int op, const SVal& a, const SVal& b) {
+    AlgP x = alg_of(a), y = alg_of(b);
+    if (x->deg == 3 || y->deg == 3) {
+      // x * 0 style cancellations are not tracked; anything else is not quadratic
+      return alg_bad();
+    }
+    if (x->deg == 0 && y->deg == 0) { U256 r; if (fold_bin(op, x->c.k, y->c.k, r)) return alg_const(r); return alg_bad(); }
+    switch (op) {
+      case O_ADD: case O_SUB: {
+        if (x->deg == 2 && y->deg == 2) return alg_bad();
+        AlgP r = std::make_shared<Alg>(*(x->deg == 2 ? x : (y->deg == 2 ? y : x)));
+        bool used_x = !(y->deg == 2 && x->deg != 2);
+        U256 k = (op == O_ADD) ? U256(1) : fr_neg(U256(1));
+        if (used_x) { lin_addmul(r->c, y->c, k); r->deg = std::max(x->deg, y->deg); }
+        else {  // r = copy of y (quadratic), x is linear: x +/- y
+          if (op == O_SUB) { lin_scale(r->a, k); lin_scale(r->c, k); }
+          lin_addmul(r->c, x->c, U256(1)); r->deg = 2;
+        }
+        if (r->deg == 1 && r->c.t.empty()) r->deg = 0;
+        return r;
+      }
+      case O_MUL: {
+        if (x->deg == 0 || y->deg == 0) {
+          const AlgP& k = x->deg == 0 ? x : y; const AlgP& v = x->deg == 0 ? y : x;
+          AlgP r = std::make_shared<Alg>(*v);
+          if (r->deg == 2) lin_scale(r->a, k->c.k);
+          lin_scale(r->c, k->c.k);
+          if (k->c.k.is_zero()) { r->deg = 0; r->a = Lin(); r->b = Lin(); }
+          return r;
+        }
+        if (x->deg == 1 && y->deg == 1) {
+          AlgP r = std::make_shared<Alg>(); r->deg = 2; r->a = x->c; r->b = y->c; return r;
+        }
+        return alg_bad();
+      }
+      case O_DIV: {
+        if (y->deg == 0 && !y->c.k.is_zero()) {
+          AlgP r = std::make_shared<Alg>(*x); U256 k = fr_inv(y->c.k);
+          if (r->deg == 2) lin_scale(r->a, k);
+          lin_scale(r->c, k); return r;
+        }
+        return alg_bad();
+      }
+    }
+    return alg_bad();
+  }
+
+  uint32_t coef_id(const U256& c) {
+    auto it = coef_idx.find(c);
+    if (it != coef_idx.end()) return it->second;
+    uint32_t i = (uint32_t)coefs.size(); coefs.push_back(c); coef_idx[c] = i; return i;
+  }
+  // signal index 0xFFFFFFFF denotes the constant-one wire
+  void push_lin(const Lin& l, uint32_t& n) {
+    n = 0;
+    if (!l.k.is_zero()) { terms.emplace_back(0xFFFFFFFFu, coef_id(l.k)); n++; }
+    for (auto& t : l.t) { terms.emplace_back(t.first, coef_id(t.second)); n++; }
+  }
+  // constraint  e == 0  where e = a*b + c   ->  A*B = -C
+  void add_constraint(const AlgP& e, const Stmt* at) {
+    if (e->deg == 3) fail(at, "non-quadratic constraint");
+    if (e->deg == 0) {
+      if (!e->c.k.is_zero()) fail(at, "constraint is constant and false");
+      return;  // circom drops trivially true constraints
+    }
+    RowRec r; r.off = terms.size();
+    Lin negc = e->c; lin_scale(negc, fr_neg(U256(1)));
+    if (e->deg == 2) { push_lin(e->a, r.na); push_lin(e->b, r.nb); }
+    else { r.na = r.nb = 0; }
+    push_lin(negc, r.nc);
+    rows.push_back(r);
+  }
+
+  // ================================================================== environment
+  Value* find_var(Env& env, int name) {
+    for (size_t i = env.size(); i-- > 0;)
+      for (size_t j = env[i].vars.size(); j-- > 0;)
+        if (env[i].vars[j].first == name) return &env[i].vars[j].second;
+    return nullptr;
+  }
+  void declare_var(Env& env, int name, const Value& v) {
+    for (auto& p : env.back().vars) if (p.first == name) { p.second = v; return; }
+    env.back().vars.emplace_back(name, v);
+  }
+  static Value scalar(const SVal& s) { Value v; v.s = s; return v; }
+  static Value zeros(const std::vector<int>& dims) {
+    Value v;
+    if (dims.empty()) return v;
+    v.arr = true; v.a = std::make_shared<AVal>(); v.a->dims = dims;
+    size_t n = 1; for (int d : dims) n *= (size_t)d;
+    v.a->v.assign(n, SVal());
+    return v;
+  }
+  static bool has_unk(const Value& v) {
+    if (!v.arr) return v.s.kind == 2;
+    for (auto& s : v.a->v) if (s.kind == 2) return true;
+    return false;
+  }
+  static bool all_const(const Value& v) {
+    if (!v.arr) return v.s.kind == 0;
+    for (auto& s : v.a->v) if (s.kind != 0) return false;
+    return true;
+  }
+  std::string value_key(const Value& v) {
+    std::string k;
+    if (!v.arr) { k.append((const char*)v.s.c.w, 32); return k; }
+    k.push_back('[');
+    for (int d : v.a->dims) { k += std::to_string(d); k.push_back(','); }
+    for (auto& s : v.a->v) k.append((const char*)s.c.w, 32);
+    k.push_back(']');
+    return k;
+  }
+  int const_int(const SVal& s, const Stmt* at, const char* what) {
+    if (s.kind == 2) fail(at, std::string(what) + " depends on a signal");
+    if (s.kind != 0) fail(at, std::string(what) + " is not a compile-time constant");
+    if (!s.c.fits64() || s.c.w[0] > 0x7fffffff) fail(at, std::string(what) + " out of range");
+    return (int)s.c.w[0];
+  }
+
+  // ================================================================== layouts (phase A)
+  Layout* layout_of(int tname, const std::vector<Value>& args, const Stmt* at) {
+    std::string key = nm(tname);
+    key.push_back('(');
+    for (auto& a : args) { key += value_key(a); key.push_back(';'); }
+    auto it = layouts.find(key);
+    if (it != layouts.end()) return it->second;
+    auto tt = unit.templates.find(tname);
+    if (tt == unit.templates.end()) fail(at, "unknown template " + nm(tname));
+    TemplateDef& td = tt->second;
+    if (td.params.size() != args.size()) fail(at, "wrong number of arguments for template " + nm(tname));
+    Layout* lay = new Layout();
+    lay->tname = tname; lay->args = args;
+    layout_list.push_back(lay);
+    int saved = phase; phase = 0;
+    Env env(1);
+    for (size_t i = 0; i < args.size(); i++) declare_var(env, td.params[i], args[i]);
+    Ctx ctx; ctx.lay = lay;
+    bool sr = returned; returned = false;
+    exec(td.body, env, &ctx);
+    returned = sr;
+    phase = saved;
+    uint32_t off = 0;
+    for (int kind : {2, 1, 0})
+      for (int n : lay->order) {
+        SigInfo& s = lay->sigs[n];
+        if (s.kind != kind) continue;
+        s.off = off;
+        uint32_t cnt = 1; for (int d : s.dims) cnt *= (uint32_t)d;
+        off += cnt;
+        if (kind == 1) lay->n_inputs += cnt;
+      }
+    lay->own = off;
+    for (auto& ck : lay->child_order) { Child& c = lay->children[ck]; c.rel_base = off; off += c.lay->total; }
+    lay->total = off;
+    layouts[key] = lay;
+    return lay;
+  }
+
+  // ================================================================== references
+  static uint32_t prod(const std::vector<int>& d, size_t from = 0) {
+    uint32_t n = 1; for (size_t i = from; i < d.size(); i++) n *= (uint32_t)d[i]; return n;
+  }
+  Ref resolve(Expr* e, Env& env, Ctx* ctx, const Stmt* at) {
+    Ref r;
+    switch (e->k) {
+      case Expr::VAR: {
+        if (find_var(env, e->name)) { r.k = Ref::VAR; return r; }
+        if (!ctx) fail(at, "unknown identifier " + nm(e->name));
+        Layout* lay = ctx->lay;
+        auto si = lay->sigs.find(e->name);
+        if (si != lay->sigs.end()) {
+          r.k = Ref::SIG; r.comp = ctx->comp; r.lay = lay; r.off = si->second.off; r.dims = si->second.dims;
+          r.skind = si->second.kind; r.name = e->name; return r;
+        }
+        auto ci = lay->comp_dims.find(e->name);
+        if (ci != lay->comp_dims.end()) { r.k = Ref::COMP; r.name = e->name; r.dims = ci->second; return r; }
+        fail(at, "unknown identifier " + nm(e->name));
+      }
+      case Expr::IDX: {
+        r = resolve(e->a, env, ctx, at);
+        if (r.k == Ref::VAR || r.k == Ref::UNKNOWN) return r;
+        Value iv = eval(e->b, env, ctx, false, at);
+        int i = const_int(iv.s, at, "signal/component index");
+        if (r.k == Ref::SIG) {
+          if (r.dims.empty()) fail(at, "too many indices on signal " + nm(r.name));
+          if (i >= r.dims[0]) fail(at, fmt("index %d out of range for signal %s (dim %d)", i, nm(r.name).c_str(), r.dims[0]));
+          r.off += (uint32_t)i * prod(r.dims, 1);
+          r.dims.erase(r.dims.begin());
+          return r;
+        }
+        size_t used = r.path.size();
+        if (used >= r.dims.size()) fail(at, "too many indices on component " + nm(r.name));
+        if (i >= r.dims[used]) fail(at, "component index out of range for " + nm(r.name));
+        r.path.push_back(i);
+        return r;
+      }
+      case Expr::MEM: {
+        Ref b = resolve(e->a, env, ctx, at);
+        if (b.k != Ref::COMP || b.path.size() != b.dims.size()) fail(at, "member access on a non-component");
+        if (phase == 0) { r.k = Ref::UNKNOWN; return r; }
+        Comp* child = get_child(ctx->comp, b, at);
+        auto si = child->lay->sigs.find(e->name);
+        if (si == child->lay->sigs.end()) fail(at, "component has no signal " + nm(e->name));
+        r.k = Ref::SIG; r.comp = child; r.lay = child->lay; r.off = si->second.off; r.dims = si->second.dims;
+        r.skind = si->second.kind; r.name = e->name;
+        return r;
+      }
+      default: fail(at, "expression is not assignable");
+    }
+  }
+  static int flat_index(const Ref& c) {
+    int f = 0;
+    for (size_t i = 0; i < c.path.size(); i++) f = f * c.dims[i] + c.path[i];
+    return f;
+  }
+  Comp* get_child(Comp* comp, const Ref& c, const Stmt* at) {
+    auto it = comp->kids.find({c.name, flat_index(c)});
+    if (it == comp->kids.end()) fail(at, "component " + nm(c.name) + " used before it was instantiated");
+    return it->second;
+  }
+
+  // ================================================================== signals
+  SVal read_signal_elem(Comp* comp, uint32_t off, bool alg) {
+    uint32_t sig = comp->base + off;
+    uint32_t vid = sig_val[sig];
+    SVal s;
+    if (vid == 0) s = SVal::konst(U256());
+    else if (v_const[vid]) s = SVal::konst(const_of[vid]);
+    else s = sv(vid);
+    if (alg) s.alg = alg_sig(sig);
+    return s;
+  }
+  Value read_signal(const Ref& r, bool alg) {
+    if (phase == 0) return scalar(SVal::unk());
+    if (r.dims.empty()) return scalar(read_signal_elem(r.comp, r.off, alg));
+    Value v; v.arr = true; v.a = std::make_shared<AVal>(); v.a->dims = r.dims;
+    uint32_t n = prod(r.dims);
+    v.a->v.reserve(n);
+    for (uint32_t i = 0; i < n; i++) v.a->v.push_back(read_signal_elem(r.comp, r.off + i, alg));
+    return v;
+  }
+  void store_signal(const Ref& r, const Value& v, bool constrain, const Stmt* at) {
+    uint32_t n = prod(r.dims);
+    if (r.dims.empty() && v.arr) fail(at, "array assigned to scalar signal " + nm(r.name));
+    if (!r.dims.empty() && (!v.arr || v.a->v.size() != n)) fail(at, "array size mismatch assigning signal " + nm(r.name));
+    for (uint32_t i = 0; i < n; i++) {
+      const SVal& s = r.dims.empty() ? v.s : v.a->v[i];
+      uint32_t sig = r.comp->base + r.off + i;
+      if (sig_val[sig] != 0) fail(at, "signal " + nm(r.name) + " assigned twice");
+      uint32_t vid;
+      if (s.kind == 0) vid = const_value(s.c);
+      else if (s.kind == 1) {
+        vid = s.id;
+        if (v_cls[vid] == CLS_N) vid = to_F(s);
+      } else fail(at, "internal: unknown value stored to a signal");
+      sig_val[sig] = vid;
+      if (constrain) {
+        // rhs - sig == 0
+        SVal self; self.kind = 1; self.alg = alg_sig(sig);
+        AlgP e = alg_bin(O_SUB, s, self);
+        add_constraint(e, at);
+      }
+    }
+    if (r.skind == 1 && r.comp->parent != nullptr) {
+      r.comp->pending -= n;
+      if (r.comp->pending == 0) run_comp(r.comp, at);
+    }
+  }
+
+  void run_comp(Comp* comp, const Stmt* at) {
+    if (comp->ran) fail(at, "component executed twice");
+    comp->ran = true;
+    TemplateDef& td = unit.templates[comp->lay->tname];
+    Env env(1);
+    for (size_t i = 0; i < td.params.size(); i++) declare_var(env, td.params[i], comp->lay->args[i]);
+    Ctx ctx; ctx.lay = comp->lay; ctx.comp = comp;
+    bool sr = returned; returned = false;
+    exec(td.body, env, &ctx);
+    returned = sr;
+  }
+
+  void instantiate(const Ref& c, Expr* rhs, Env& env, Ctx* ctx, const Stmt* at) {
+    if (c.path.size() != c.dims.size()) fail(at, "component array assigned as a whole");
+    if (rhs->k != Expr::CALL) fail(at, "component initialiser must be a template call");
+    std::vector<Value> args;
+    for (Expr* a : rhs->args) args.push_back(eval(a, env, ctx, false, at));
+    for (auto& a : args) {
+      if (has_unk(a)) fail(at, "template argument depends on a signal");
+      if (!all_const(a)) fail(at, "template argument is not a compile-time constant");
+    }
+    std::pair<int, int> key{c.name, flat_index(c)};
+    if (phase == 0) {
+      Layout* lay = ctx->lay;
+      if (lay->children.count(key)) fail(at, "component " + nm(c.name) + " instantiated twice");
+      Child ch; ch.tname = rhs->name; ch.lay = layout_of(rhs->name, args, at); ch.rel_base = 0;
+      lay->children[key] = ch;
+      lay->child_order.push_back(key);
+      return;
+    }
+    Comp* comp = ctx->comp;
+    auto it = comp->lay->children.find(key);
+    if (it == comp->lay->children.end() || it->second.tname != rhs->name) fail(at, "phase mismatch instantiating " + nm(c.name));
+    Layout* sub = layout_of(rhs->name, args, at);
+    if (sub != it->second.lay) fail(at, "phase mismatch (arguments) instantiating " + nm(c.name));
+    Comp* child = new Comp();
+    comps.push_back(child);
+    child->lay = sub; child->base = comp->base + it->second.rel_base; child->pending = sub->n_inputs; child->parent = comp;
+    comp->kids[key] = child;
+    if (child->pending == 0) run_comp(child, at);
+  }
+
+  // ================================================================== expressions
+  Value eval(Expr* e, Env& env, Ctx* ctx, bool alg, const Stmt* at) {
+    switch (e->k) {
+      case Expr::NUM: return scalar(SVal::konst(e->num));
+      case Expr::VAR: {
+        Value* v = find_var(env, e->name);
+        if (v) return *v;
+        Ref r = resolve(e, env, ctx, at);
+        if (r.k == Ref::SIG) return read_signal(r, alg);
+        fail(at, "component " + nm(e->name) + " used as a value");
+      }
+      case Expr::IDX: {
+        // var array fast path
+        Expr* base = e; int depth = 0;
+        while (base->k == Expr::IDX) { base = base->a; depth++; }
+        if (base->k == Expr::VAR) {
+          Value* v = find_var(env, base->name);
+          if (v) {
+            if (!v->arr) { if (v->s.kind == 2) return scalar(SVal::unk()); fail(at, "indexing scalar variable " + nm(base->name)); }
+            std::vector<int> idx(depth);
+            Expr* w = e;
+            for (int i = depth - 1; i >= 0; i--) {
+              Value iv = eval(w->b, env, ctx, false, at);
+              if (iv.s.kind == 2) return scalar(SVal::unk());
+              idx[i] = const_int(iv.s, at, "array index");
+              w = w->a;
+            }
+            AVal& a = *v->a;
+            if ((size_t)depth > a.dims.size()) fail(at, "too many indices on " + nm(base->name));
+            size_t off = 0;
+            for (int i = 0; i < depth; i++) {
+              if (idx[i] >= a.dims[i]) fail(at, fmt("index %d out of range for variable %s (dim %d)", idx[i], nm(base->name).c_str(), a.dims[i]));
+              off = off * (size_t)a.dims[i] + (size_t)idx[i];
+            }
+            if ((size_t)depth == a.dims.size()) return scalar(a.v[off]);
+            size_t stride = 1; for (size_t i = depth; i < a.dims.size(); i++) stride *= (size_t)a.dims[i];
+            Value out; out.arr = true; out.a = std::make_shared<AVal>();
+            out.a->dims.assign(a.dims.begin() + depth, a.dims.end());
+            out.a->v.assign(a.v.begin() + off * stride, a.v.begin() + (off + 1) * stride);
+            return out;
+          }
+        }
+        Ref r = resolve(e, env, ctx, at);
+        if (r.k == Ref::UNKNOWN) return scalar(SVal::unk());
+        if (r.k == Ref::SIG) return read_signal(r, alg);
+        fail(at, "component used as a value");
+      }
+      case Expr::MEM: {
+        Ref r = resolve(e, env, ctx, at);
+        if (r.k == Ref::UNKNOWN) return scalar(SVal::unk());
+        return read_signal(r, alg);
+      }
+      case Expr::CALL: return call_function(e, env, ctx, at);
+      case Expr::ARR: {
+        Value out; out.arr = true; out.a = std::make_shared<AVal>();
+        std::vector<int> sub;
+        for (size_t i = 0; i < e->args.size(); i++) {
+          Value x = eval(e->args[i], env, ctx, alg, at);
+          if (x.arr) { if (i == 0) sub = x.a->dims; out.a->v.insert(out.a->v.end(), x.a->v.begin(), x.a->v.end()); }
+          else out.a->v.push_back(x.s);
+        }
+        out.a->dims.push_back((int)e->args.size());
+        out.a->dims.insert(out.a->dims.end(), sub.begin(), sub.end());
+        return out;
+      }
+      case Expr::UN: {
+        Value a = eval(e->a, env, ctx, alg, at);
+        if (a.arr) fail(at, "unary operator on an array");
+        SVal r = emit_un(e->op, a.s, at);
+        if (alg && r.kind != 2) {
+          if (e->op == O_NEG) r.alg = alg_bin(O_SUB, SVal::konst(U256()), a.s);
+          else r.alg = (r.kind == 0) ? nullptr : alg_bad();
+        }
+        return scalar(r);
+      }
+      case Expr::BIN: {
+        Value a = eval(e->a, env, ctx, alg, at);
+        if (a.arr) fail(at, "binary operator on an array");
+        // short circuit on constants
+        if (a.s.kind == 0) {
+          if (e->op == O_LAND && a.s.c.is_zero()) return scalar(SVal::konst(U256()));
+          if (e->op == O_LOR && !a.s.c.is_zero()) return scalar(SVal::konst(U256(1)));
+        }
+        Value b = eval(e->b, env, ctx, alg, at);
+        if (b.arr) fail(at, "binary operator on an array");
+        SVal r = fold_or_emit_bin(e->op, a.s, b.s, at);
+        if (alg && r.kind != 2) r.alg = alg_bin(e->op, a.s, b.s);
+        return scalar(r);
+      }
+      case Expr::TERN: {
+        Value c = eval(e->a, env, ctx, false, at);
+        if (c.arr) fail(at, "array used as a condition");
+        if (c.s.kind == 2) return scalar(SVal::unk());
+        if (c.s.kind == 0) return eval(c.s.c.is_zero() ? e->c : e->b, env, ctx, alg, at);
+        Value x = eval(e->b, env, ctx, false, at), y = eval(e->c, env, ctx, false, at);
+        if (x.arr || y.arr) fail(at, "signal-dependent selection between arrays");
+        SVal r = emit_select(c.s, x.s, y.s, at);
+        if (alg) r.alg = (r.kind == 0) ? nullptr : alg_bad();
+        return scalar(r);
+      }
+    }
+    fail(at, "bad expression");
+  }
+
+  // ---- functions -----------------------------------------------------------------
+  int id_long_div = -2;
+  Value call_function(Expr* e, Env& env, Ctx* ctx, const Stmt* at) {
+    auto ft = unit.functions.find(e->name);
+    if (ft == unit.functions.end()) fail(at, "unknown function " + nm(e->name));
+    TemplateDef& fd = ft->second;
+    std::vector<Value> args;
+    bool unk = false, konst = true;
+    for (Expr* a : e->args) {
+      args.push_back(eval(a, env, ctx, false, at));
+      if (has_unk(args.back())) unk = true;
+      if (!all_const(args.back())) konst = false;
+    }
+    if (unk) return scalar(SVal::unk());
+    if (fd.params.size() != args.size()) fail(at, "wrong number of arguments for function " + nm(e->name));
+    std::string key;
+    if (konst) {
+      key = nm(e->name); key.push_back('(');
+      for (auto& a : args) { key += value_key(a); key.push_back(';'); }
+      auto it = fn_memo.find(key);
+      if (it != fn_memo.end()) return it->second;
+    } else if (opt.intrinsics) {
+      if (id_long_div == -2) id_long_div = unit.names.get("long_div");
+      Value out;
+      if (e->name == id_long_div && try_bigdiv(args, out, at)) return out;
+    }
+    Env fenv(1);
+    for (size_t i = 0; i < args.size(); i++) declare_var(fenv, fd.params[i], args[i]);
+    bool sr = returned; Value sv_ret = ret_val;
+    returned = false;
+    if (++fn_depth > 400) fail(at, "function recursion too deep");
+    exec(fd.body, fenv, nullptr);
+    fn_depth--;
+    if (!returned) fail(at, "function " + nm(e->name) + " did not return");
+    Value out = ret_val;
+    returned = sr; ret_val = sv_ret;
+    if (konst) fn_memo[key] = out;
+    return out;
+  }
+
+  // long_div(n, k, m, a, b) of /root/reference/circuits/lib/circuits/bigInt/bigIntFunc.circom:190-232
+  // evaluated natively: a has k+m limbs of n bits, b has k limbs (top limb non-zero);
+  // returns out[2][200] with the m+1 quotient limbs and k remainder limbs.
+  bool try_bigdiv(const std::vector<Value>& args, Value& out, const Stmt* at) {
+    if (args.size() != 5) return false;
+    for (int i = 0; i < 3; i++) if (args[i].arr || args[i].s.kind != 0 || !args[i].s.c.fits64()) return false;
+    uint64_t n = args[0].s.c.w[0], k = args[1].s.c.w[0], m = args[2].s.c.w[0];
+    if (n == 0 || n > 64 || k == 0 || k + m > 180 || !args[3].arr || !args[4].arr) return false;
+    if (args[3].a->v.size() < k + m || args[4].a->v.size() < k) return false;
+    i128 lim = n == 64 ? U64_MAX_ : (((i128)1 << n) - 1);
+    std::vector<uint32_t> ids;
+    for (uint64_t i = 0; i < k + m; i++) { i128 hi; const SVal& s = args[3].a->v[i]; if (!exact_u(s, hi) || hi > lim) return false; }
+    for (uint64_t i = 0; i < k; i++) { i128 hi; const SVal& s = args[4].a->v[i]; if (!exact_u(s, hi) || hi > lim) return false; }
+    uint32_t off = (uint32_t)list_pool.size();
+    list_pool.push_back((uint32_t)n); list_pool.push_back((uint32_t)k); list_pool.push_back((uint32_t)m);
+    for (uint64_t i = 0; i < k + m; i++) list_pool.push_back(u_operand(args[3].a->v[i]));
+    for (uint64_t i = 0; i < k; i++) list_pool.push_back(u_operand(args[4].a->v[i]));
+    out = zeros({2, 200});
+    uint32_t first = 0;
+    for (uint64_t i = 0; i <= m; i++) {
+      uint32_t id = new_value(CLS_U, 0, lim);
+      if (i == 0) first = id;
+      list_pool.push_back(id);
+      out.a->v[i] = sv(id);
+    }
+    for (uint64_t i = 0; i < k; i++) {
+      uint32_t id = new_value(CLS_U, 0, lim);
+      list_pool.push_back(id);
+      out.a->v[200 + i] = sv(id);
+    }
+    emit(PZK_BIGDIV, first, off, 0);
+    stats->bigdiv++;
+    (void)at;
+    return true;
+  }
+
+  // ================================================================== statements
+  bool relevant_A(Stmt* s) {  // does the statement matter in phase A?
+    if (!s) return false;
+    if (s->has_decl >= 0) return s->has_decl;
+    bool r = false;
+    switch (s->k) {
+      case Stmt::BLOCK: for (Stmt* c : s->stmts) if (relevant_A(c)) r = true; break;
+      case Stmt::SIGDECL: case Stmt::VARDECL: case Stmt::COMPDECL: case Stmt::INCDEC: case Stmt::RETURN: case Stmt::ASSERT: r = true; break;
+      case Stmt::ASSIGN: r = (s->op == O_ASSIGN); break;
+      case Stmt::IF: r = relevant_A(s->s1) || relevant_A(s->s2); break;
+      case Stmt::FOR: r = relevant_A(s->body); break;
+      case Stmt::WHILE: r = true; break;
+      default: r = false;
+    }
+    s->has_decl = r;
+    return r;
+  }
+  void collect_assigned(Stmt* s, std::vector<int>& out) {
+    if (!s) return;
+    switch (s->k) {
+      case Stmt::BLOCK: for (Stmt* c : s->stmts) collect_assigned(c, out); break;
+      case Stmt::ASSIGN: case Stmt::INCDEC: { Expr* b = s->lhs; while (b->k == Expr::IDX) b = b->a; if (b->k == Expr::VAR) out.push_back(b->name); break; }
+      case Stmt::IF: collect_assigned(s->s1, out); collect_assigned(s->s2, out); break;
+      case Stmt::FOR: collect_assigned(s->s1, out); collect_assigned(s->s2, out); collect_assigned(s->body, out); break;
+      case Stmt::WHILE: collect_assigned(s->body, out); break;
+      case Stmt::SIGDECL: case Stmt::COMPDECL: fail(s, "declaration under a signal-dependent condition");
+      default: break;
+    }
+  }
+
+  void assign_var(Expr* lhs, const Value& v, Env& env, Ctx* ctx, const Stmt* at) {
+    if (lhs->k == Expr::VAR) {
+      Value* slot = find_var(env, lhs->name);
+      if (!slot) fail(at, "assignment to unknown variable " + nm(lhs->name));
+      *slot = v;
+      return;
+    }
+    if (lhs->k != Expr::IDX) fail(at, "bad assignment target");
+    Expr* base = lhs; int depth = 0;
+    while (base->k == Expr::IDX) { base = base->a; depth++; }
+    if (base->k != Expr::VAR) fail(at, "bad assignment target");
+    Value* slot = find_var(env, base->name);
+    if (!slot) fail(at, "assignment to unknown variable " + nm(base->name));
+    std::vector<int> idx(depth);
+    Expr* w = lhs;
+    bool unk = false;
+    for (int i = depth - 1; i >= 0; i--) {
+      Value iv = eval(w->b, env, ctx, false, at);
+      if (iv.s.kind == 2) unk = true; else idx[i] = const_int(iv.s, at, "array index");
+      w = w->a;
+    }
+    if (!slot->arr) { if (slot->s.kind == 2) return; fail(at, "indexing scalar variable " + nm(base->name)); }
+    if (unk) { *slot = scalar(SVal::unk()); return; }
+    if (slot->a.use_count() > 1) slot->a = std::make_shared<AVal>(*slot->a);  // copy on write
+    AVal& a = *slot->a;
+    if ((size_t)depth > a.dims.size()) fail(at, "too many indices on " + nm(base->name));
+    size_t off = 0;
+    for (int i = 0; i < depth; i++) {
+      if (idx[i] >= a.dims[i]) fail(at, fmt("index %d out of range for variable %s (dim %d)", idx[i], nm(base->name).c_str(), a.dims[i]));
+      off = off * (size_t)a.dims[i] + (size_t)idx[i];
+    }
+    if ((size_t)depth == a.dims.size()) {
+      if (v.arr) fail(at, "array assigned to an array element");
+      a.v[off] = v.s;
+      return;
+    }
+    size_t stride = 1; for (size_t i = depth; i < a.dims.size(); i++) stride *= (size_t)a.dims[i];
+    if (!v.arr) fail(at, "scalar assigned to a sub-array");
+    size_t n = std::min(stride, v.a->v.size());
+    for (size_t i = 0; i < n; i++) a.v[off * stride + i] = v.a->v[i];
+  }
+
+  void exec_assign(Stmt* s, Env& env, Ctx* ctx) {
+    int op = s->op;
+    if (phase == 0 && op != O_ASSIGN) return;
+    Ref target = resolve(s->lhs, env, ctx, s);
+    if (target.k == Ref::VAR) {
+      if (op != O_ASSIGN) fail(s, "signal operator used on a variable");
+      Value v = eval(s->rhs, env, ctx, ctx != nullptr && phase == 1, s);
+      assign_var(s->lhs, v, env, ctx, s);
+      return;
+    }
+    if (target.k == Ref::COMP) {
+      if (op != O_ASSIGN) fail(s, "components are assigned with =");
+      instantiate(target, s->rhs, env, ctx, s);
+      return;
+    }
+    if (target.k == Ref::UNKNOWN) return;
+    if (op == O_ASSIGN) fail(s, "signals are assigned with <== or <--");
+    Value v = eval(s->rhs, env, ctx, op == O_CONSTRAIN_L, s);
+    store_signal(target, v, op == O_CONSTRAIN_L, s);
+  }
+
+  void exec(Stmt* s, Env& env, Ctx* ctx) {
+    if (returned) return;
+    switch (s->k) {
+      case Stmt::BLOCK: {
+        env.emplace_back();
+        for (Stmt* c : s->stmts) { exec(c, env, ctx); if (returned) break; }
+        env.pop_back();
+        return;
+      }
+      case Stmt::ASSIGN: exec_assign(s, env, ctx); return;
+      case Stmt::VARDECL: {
+        for (auto& it : s->items) {
+          Value v;
+          if (it.init) v = eval(it.init, env, ctx, ctx != nullptr && phase == 1, s);
+          else {
+            std::vector<int> dd;
+            for (Expr* d : it.dims) dd.push_back(const_int(eval(d, env, ctx, false, s).s, s, "variable dimension"));
+            v = zeros(dd);
+          }
+          declare_var(env, it.name, v);
+        }
+        return;
+      }
+      case Stmt::SIGDECL: {
+        if (!ctx) fail(s, "signal declared inside a function");
+        for (auto& it : s->items) {
+          if (phase == 0) {
+            std::vector<int> dd;
+            for (Expr* d : it.dims) dd.push_back(const_int(eval(d, env, ctx, false, s).s, s, "signal dimension"));
+            if (ctx->lay->sigs.count(it.name)) fail(s, "signal " + nm(it.name) + " declared twice");
+            SigInfo si; si.off = 0; si.dims = dd; si.kind = s->op;
+            ctx->lay->sigs[it.name] = si;
+            ctx->lay->order.push_back(it.name);
+          } else if (it.init) {
+            Ref r; r.k = Ref::SIG; r.comp = ctx->comp; r.lay = ctx->lay;
+            SigInfo& si = ctx->lay->sigs[it.name];
+            r.off = si.off; r.dims = si.dims; r.skind = si.kind; r.name = it.name;
+            Value v = eval(it.init, env, ctx, it.init_op == O_CONSTRAIN_L, s);
+            store_signal(r, v, it.init_op == O_CONSTRAIN_L, s);
+          }
+        }
+        return;
+      }
+      case Stmt::COMPDECL: {
+        if (!ctx) fail(s, "component declared inside a function");
+        for (auto& it : s->items) {
+          if (phase == 0) {
+            std::vector<int> dd;
+            for (Expr* d : it.dims) dd.push_back(const_int(eval(d, env, ctx, false, s).s, s, "component dimension"));
+            if (!ctx->lay->comp_dims.count(it.name)) ctx->lay->comp_dims[it.name] = dd;
+          }
+          if (it.init) {
+            Ref c; c.k = Ref::COMP; c.name = it.name; c.dims = ctx->lay->comp_dims[it.name];
+            instantiate(c, it.init, env, ctx, s);
+          }
+        }
+        return;
+      }
+      case Stmt::IF: {
+        Value c = eval(s->cond, env, ctx, false, s);
+        if (c.arr) fail(s, "array used as a condition");
+        if (c.s.kind == 2) {
+          std::vector<int> names; collect_assigned(s->s1, names); collect_assigned(s->s2, names);
+          for (int n : names) { Value* v = find_var(env, n); if (v) *v = scalar(SVal::unk()); }
+          return;
+        }
+        if (c.s.kind == 1) { exec_data_if(s, c.s, env, ctx); return; }
+        if (!c.s.c.is_zero()) exec(s->s1, env, ctx);
+        else if (s->s2) exec(s->s2, env, ctx);
+        return;
+      }
+      case Stmt::FOR: {
+        if (phase == 0 && !relevant_A(s)) return;
+        env.emplace_back();
+        exec(s->s1, env, ctx);
+        uint64_t guard = 0;
+        while (!returned) {
+          Value c = eval(s->cond, env, ctx, false, s);
+          if (c.s.kind != 0) fail(s, "loop condition depends on a signal");
+          if (c.s.c.is_zero()) break;
+          exec(s->body, env, ctx);
+          if (returned) break;
+          exec(s->s2, env, ctx);
+          if (++guard > 100000000ull) fail(s, "loop does not terminate");
+        }
+        env.pop_back();
+        return;
+      }
+      case Stmt::WHILE: {
+        uint64_t guard = 0;
+        while (!returned) {
+          Value c = eval(s->cond, env, ctx, false, s);
+          if (c.s.kind != 0) fail(s, "while condition depends on a signal");
+          if (c.s.c.is_zero()) break;
+          exec(s->body, env, ctx);
+          if (++guard > 100000000ull) fail(s, "loop does not terminate");
+        }
+        return;
+      }
+      case Stmt::INCDEC: {
+        Value cur = eval(s->lhs, env, ctx, false, s);
+        if (cur.arr) fail(s, "++/-- on an array");
+        SVal r = fold_or_emit_bin(s->op > 0 ? O_ADD : O_SUB, cur.s, SVal::konst(U256(1)), s);
+        assign_var(s->lhs, scalar(r), env, ctx, s);
+        return;
+      }
+      case Stmt::CONSTR: {
+        if (phase == 0) return;
+        if (!ctx) fail(s, "constraint inside a function");
+        Value a = eval(s->lhs, env, ctx, true, s), b = eval(s->rhs, env, ctx, true, s);
+        if (a.arr != b.arr) fail(s, "constraint between an array and a scalar");
+        if (!a.arr) { add_constraint(alg_bin(O_SUB, a.s, b.s), s); return; }
+        if (a.a->v.size() != b.a->v.size()) fail(s, "array constraint size mismatch");
+        for (size_t i = 0; i < a.a->v.size(); i++) add_constraint(alg_bin(O_SUB, a.a->v[i], b.a->v[i]), s);
+        return;
+      }
+      case Stmt::RETURN: {
+        if (ctx) fail(s, "return inside a template");
+        ret_val = eval(s->rhs, env, ctx, false, s);
+        returned = true;
+        return;
+      }
+      case Stmt::ASSERT: {
+        Value c = eval(s->cond, env, ctx, false, s);
+        if (c.s.kind == 2) return;
+        if (c.s.kind == 0) { if (c.s.c.is_zero()) fail(s, "assert failed at compile time"); return; }
+        SVal t = truthy(c.s, s);
+        emit(PZK_ASSERT_NZ, 0, t.id);
+        return;
+      }
+      case Stmt::LOG: return;
+    }
+  }
+
+  // if (signal-dependent) { ... } else { ... } on variables only: run both arms on copies of
+  // the environment and merge every changed variable with a select (if-conversion).
+  void exec_data_if(Stmt* s, const SVal& cond, Env& env, Ctx* ctx) {
+    std::vector<int> names; collect_assigned(s->s1, names); collect_assigned(s->s2, names);
+    Env e1 = env, e2 = env;
+    bool r0 = returned;
+    exec(s->s1, e1, ctx);
+    bool r1 = returned; Value rv1 = ret_val; returned = r0;
+    if (s->s2) exec(s->s2, e2, ctx);
+    bool r2 = returned; Value rv2 = ret_val; returned = r0;
+    if (r1 || r2) fail(s, "return under a signal-dependent condition is not supported");
+    (void)rv1; (void)rv2;
+    std::sort(names.begin(), names.end());
+    names.erase(std::unique(names.begin(), names.end()), names.end());
+    for (int n : names) {
+      Value* dst = find_var(env, n);
+      if (!dst) continue;  // declared inside the arm
+      Value* a = find_var(e1, n); Value* b = find_var(e2, n);
+      if (!a || !b) continue;
+      if (a->arr != b->arr) fail(s, "if-conversion: shape mismatch for " + nm(n));
+      if (!a->arr) { *dst = scalar(emit_select(cond, a->s, b->s, s)); continue; }
+      if (a->a->v.size() != b->a->v.size()) fail(s, "if-conversion: size mismatch for " + nm(n));
+      Value out; out.arr = true; out.a = std::make_shared<AVal>(); out.a->dims = a->a->dims;
+      out.a->v.resize(a->a->v.size());
+      for (size_t i = 0; i < a->a->v.size(); i++) {
+        const SVal& x = a->a->v[i]; const SVal& y = b->a->v[i];
+        if (x.kind == y.kind && ((x.kind == 0 && x.c == y.c) || (x.kind == 1 && x.id == y.id))) out.a->v[i] = x;
+        else out.a->v[i] = emit_select(cond, x, y, s);
+      }
+      *dst = out;
+    }
+  }
+
+  // ================================================================== driver
+  std::vector<std::pair<std::string, std::vector<int>>> main_inputs_desc, main_outputs_desc;
+  std::vector<uint32_t> main_input_sig;  // signal index per flattened input, in wire order
+
+  void run_main() {
+    if (!unit.main.present) fail("no `component main` in " + main_path);
+    Expr* call = unit.main.call;
+    if (call->k != Expr::CALL) fail("main must be a template instantiation");
+    Env env(1);
+    std::vector<Value> args;
+    phase = 0;
+    for (Expr* a : call->args) args.push_back(eval(a, env, nullptr, false, nullptr));
+    main_lay = layout_of(call->name, args, nullptr);
+    uint32_t nsig = main_lay->total;
+    stats->n_signals = nsig;
+    sig_val.assign(nsig, 0);
+    // value 0 is reserved
+    new_value(CLS_U);
+    emit(PZK_NOP, 0);
+    // wire order: 1 | outputs | public inputs | private inputs | rest
+    sig2wire.assign(nsig, 0);
+    uint32_t n_out = 0;
+    for (int n : main_lay->order) { SigInfo& s = main_lay->sigs[n]; if (s.kind == 2) n_out += prod(s.dims); }
+    std::set<int> pub(unit.main.publics.begin(), unit.main.publics.end());
+    for (int p : pub) { auto it = main_lay->sigs.find(p); if (it == main_lay->sigs.end() || it->second.kind != 1) fail("public signal " + nm(p) + " is not a main input"); }
+    uint32_t w = 1;
+    for (int n : main_lay->order) { SigInfo& s = main_lay->sigs[n]; if (s.kind == 2) { for (uint32_t i = 0; i < prod(s.dims); i++) sig2wire[s.off + i] = w++; main_outputs_desc.emplace_back(nm(n), s.dims); } }
+    n_pub_out = n_out;
+    for (int pass = 0; pass < 2; pass++)
+      for (int n : main_lay->order) {
+        SigInfo& s = main_lay->sigs[n];
+        if (s.kind != 1) continue;
+        bool is_pub = pub.count(n) > 0;
+        if ((pass == 0) != is_pub) continue;
+        uint32_t cnt = prod(s.dims);
+        for (uint32_t i = 0; i < cnt; i++) { sig2wire[s.off + i] = w++; main_input_sig.push_back(s.off + i); }
+        main_inputs_desc.emplace_back(nm(n), s.dims);
+        if (is_pub) n_pub_in += cnt; else n_prv_in += cnt;
+      }
+    for (uint32_t sgn = main_lay->n_inputs + n_out; sgn < nsig; sgn++) sig2wire[sgn] = w++;
+    // input ops
+    phase = 1;
+    {
+      uint32_t k = 0;
+      for (auto& d : main_inputs_desc) {
+        int bits = 0;
+        auto it = opt.input_bits.find(d.first);
+        if (it != opt.input_bits.end()) bits = it->second;
+        if (bits < 0 || bits > 64) fail("declared input width must be 1..64 bits (0 = field element)");
+        uint32_t cnt = prod(d.second);
+        for (uint32_t i = 0; i < cnt; i++, k++) {
+          uint32_t id;
+          if (bits > 0) {
+            i128 hi = bits == 64 ? U64_MAX_ : (((i128)1 << bits) - 1);
+            id = new_value(CLS_U, 0, hi);
+            emit(PZK_IN_U, id, k, 0, 0, bits);
+          } else {
+            id = new_value(CLS_F);
+            emit(PZK_IN_F, id, k);
+          }
+          sig_val[main_input_sig[k]] = id;
+          PzkInput pi; pi.wire = sig2wire[main_input_sig[k]]; pi.bits = (uint32_t)bits;
+          out_inputs.push_back(pi);
+        }
+      }
+    }
+    Comp* main = new Comp();
+    comps.push_back(main);
+    main->lay = main_lay; main->base = 0; main->pending = 0; main->parent = nullptr;
+    run_comp(main, nullptr);
+    stats->n_constraints = rows.size();
+    stats->n_values = v_cls.size();
+  }
+
+  // ================================================================== back end
+  void backend();
+  void build_meta();
+};
+
+// ---------------------------------------------------------------------------------------
+// Back end: dead-code elimination, segmentation, liveness, slot allocation, row lowering
+// ---------------------------------------------------------------------------------------
+void Compiler::Impl::backend() {
+  size_t nv = v_cls.size(), nops = ops.size();
+  // ---- operand enumeration helper
+  auto for_operands = [&](const OpRec& o, const std::function<void(uint32_t)>& f) {
+    switch (o.opc) {
+      case PZK_NOP: case PZK_U_CONST: case PZK_F_CONST: case PZK_IN_U: case PZK_IN_F: return;
+      case PZK_BIGDIV: {
+        uint32_t k = list_pool[o.a + 1], m = list_pool[o.a + 2];
+        for (uint32_t i = 0; i < k + m + k; i++) f(list_pool[o.a + 3 + i]);
+        return;
+      }
+      case PZK_ASSERT_NZ: f(o.a); return;
+      case PZK_U_LUT: case PZK_U_LUTV:
+        if (o.a != PZK_OPERAND_NONE) f(o.a);
+        if (o.b != PZK_OPERAND_NONE) f(o.b);
+        if (o.c != PZK_OPERAND_NONE) f(o.c);
+        if (o.d != PZK_OPERAND_NONE) f(o.d);
+        return;
+      case PZK_U_SEL: case PZK_F_SEL: f(o.a); f(o.b); f(o.c); return;
+      case PZK_N_BIT: f(o.a); return;
+      case PZK_F_CSEL: f(o.a); return;
+      default:
+        f(o.a);
+        if (!(o.flags & (PZK_FLAG_B_IMM | PZK_FLAG_B_POOL))) {
+          switch (o.opc) {  // unary ops have no b
+            case PZK_F_NEG: case PZK_F_INV: case PZK_F_FROM_U: case PZK_F_FROM_I: case PZK_N_FROM_F:
+            case PZK_F_FROM_N: case PZK_N_FROM_U: case PZK_N_LOW: case PZK_N_FITS: break;
+            default: f(o.b);
+          }
+        }
+    }
+  };
+  auto for_defs = [&](const OpRec& o, const std::function<void(uint32_t)>& f) {
+    if (o.opc == PZK_NOP || o.opc == PZK_ASSERT_NZ) return;
+    if (o.opc == PZK_BIGDIV) {
+      uint32_t k = list_pool[o.a + 1], m = list_pool[o.a + 2];
+      uint32_t base = o.a + 3 + (k + m) + k;
+      for (uint32_t i = 0; i < m + 1 + k; i++) f(list_pool[base + i]);
+      return;
+    }
+    f(o.dst);
+  };
+  // ---- DCE
+  std::vector<uint8_t> used(nv, 0), keep(nops, 0);
+  for (uint32_t v : sig_val) if (v) used[v] = 1;
+  for (size_t i = nops; i-- > 0;) {
+    const OpRec& o = ops[i];
+    bool live = (o.opc == PZK_ASSERT_NZ) || (o.opc == PZK_IN_U) || (o.opc == PZK_IN_F);
+    if (!live) for_defs(o, [&](uint32_t d) { if (used[d]) live = true; });
+    if (!live) continue;
+    keep[i] = 1;
+    for_operands(o, [&](uint32_t v) { used[v] = 1; });
+  }
+  // ---- segments over kept ops
+  std::vector<uint32_t> def_seg(nv, 0), last_seg(nv, 0), op_seg(nops, 0);
+  {
+    uint64_t rec = 0; uint32_t seg = 0;
+    for (size_t i = 0; i < nops; i++) {
+      if (!keep[i]) continue;
+      uint32_t need = (ops[i].flags & PZK_FLAG_EXT) ? 2 : 1;
+      if (rec + need > opt.seg_ops) { seg++; rec = 0; }
+      rec += need;
+      op_seg[i] = seg;
+      for_defs(ops[i], [&](uint32_t d) { def_seg[d] = seg; last_seg[d] = seg; });
+    }
+    segs.assign(seg + 1, PzkSegment());
+  }
+  for (size_t i = 0; i < nops; i++) {
+    if (!keep[i]) continue;
+    uint32_t s = op_seg[i];
+    for_operands(ops[i], [&](uint32_t v) { if (last_seg[v] < s) last_seg[v] = s; });
+  }
+  // ---- rows: segment = latest definition among their wires
+  size_t nrows = rows.size();
+  std::vector<uint32_t> row_seg(nrows, 0);
+  for (size_t r = 0; r < nrows; r++) {
+    uint32_t s = 0;
+    uint32_t nt = rows[r].na + rows[r].nb + rows[r].nc;
+    for (uint32_t t = 0; t < nt; t++) {
+      uint32_t sig = terms[rows[r].off + t].first;
+      if (sig == 0xFFFFFFFFu) continue;
+      uint32_t v = sig_val[sig];
+      if (v && def_seg[v] > s) s = def_seg[v];
+    }
+    row_seg[r] = s;
+    for (uint32_t t = 0; t < nt; t++) {
+      uint32_t sig = terms[rows[r].off + t].first;
+      if (sig == 0xFFFFFFFFu) continue;
+      uint32_t v = sig_val[sig];
+      if (v && last_seg[v] < s) last_seg[v] = s;
+    }
+  }
+  // ---- slot allocation (free at segment boundaries)
+  v_slot.assign(nv, 0xFFFFFFFFu);
+  std::vector<std::vector<uint32_t>> dying(segs.size());
+  std::vector<uint32_t> free_u, free_f;
+  uint32_t next_u = 0, next_f = 0;
+  {
+    uint32_t cur = 0;
+    auto release = [&](uint32_t seg) {
+      for (uint32_t v : dying[seg]) {
+        if (v_cls[v] == CLS_U || v_cls[v] == CLS_I) free_u.push_back(v_slot[v]); else free_f.push_back(v_slot[v]);
+      }
+    };
+    for (size_t i = 0; i < nops; i++) {
+      if (!keep[i]) continue;
+      while (cur < op_seg[i]) { release(cur); cur++; }
+      for_defs(ops[i], [&](uint32_t d) {
+        bool narrow = (v_cls[d] == CLS_U || v_cls[d] == CLS_I);
+        uint32_t slot;
+        if (narrow) { if (!free_u.empty()) { slot = free_u.back(); free_u.pop_back(); } else slot = next_u++; }
+        else { if (!free_f.empty()) { slot = free_f.back(); free_f.pop_back(); } else slot = next_f++; }
+        v_slot[d] = slot;
+        dying[last_seg[d]].push_back(d);
+      });
+    }
+  }
+  n_u_slots = next_u; n_f_slots = next_f;
+  // ---- emit op records
+  auto slot_of = [&](uint32_t v) -> uint32_t {
+    if (v == PZK_OPERAND_NONE) return v;
+    if (v_slot[v] == 0xFFFFFFFFu) throw CompileError("internal: operand without a slot");
+    return v_slot[v];
+  };
+  out_list = list_pool;
+  out_ops.clear();
+  {
+    uint32_t cur = 0xFFFFFFFFu;
+    for (size_t i = 0; i < nops; i++) {
+      if (!keep[i]) continue;
+      const OpRec& o = ops[i];
+      uint32_t s = op_seg[i];
+      if (s != cur) { cur = s; segs[s].op_off = out_ops.size(); }
+      PzkOp r; r.opc = o.opc; r.flags = o.flags; r.imm16 = o.imm16; r.dst = 0; r.a = o.a; r.b = o.b;
+      switch (o.opc) {
+        case PZK_NOP: break;
+        case PZK_U_CONST: case PZK_F_CONST: case PZK_IN_U: case PZK_IN_F: r.dst = slot_of(o.dst); break;
+        case PZK_ASSERT_NZ: r.a = slot_of(o.a); break;
+        case PZK_BIGDIV: {
+          uint32_t k = list_pool[o.a + 1], m = list_pool[o.a + 2];
+          uint32_t cnt = (k + m) + k + (m + 1) + k;
+          for (uint32_t j = 0; j < cnt; j++) out_list[o.a + 3 + j] = slot_of(list_pool[o.a + 3 + j]);
+          break;
+        }
+        case PZK_N_BIT: case PZK_F_CSEL: r.dst = slot_of(o.dst); r.a = slot_of(o.a); break;
+        case PZK_U_LUT: case PZK_U_LUTV: r.dst = slot_of(o.dst); r.a = slot_of(o.a); r.b = slot_of(o.b); break;
+        default:
+          r.dst = slot_of(o.dst); r.a = slot_of(o.a);
+          if (!(o.flags & (PZK_FLAG_B_IMM | PZK_FLAG_B_POOL))) {
+            switch (o.opc) {
+              case PZK_F_NEG: case PZK_F_INV: case PZK_F_FROM_U: case PZK_F_FROM_I: case PZK_N_FROM_F:
+              case PZK_F_FROM_N: case PZK_N_FROM_U: case PZK_N_LOW: case PZK_N_FITS: r.b = 0; break;
+              default: r.b = slot_of(o.b);
+            }
+          }
+      }
+      out_ops.push_back(r);
+      if (o.flags & PZK_FLAG_EXT) {
+        PzkOpExt x; x.c = slot_of(o.c); x.d = slot_of(o.d); x.e = 0; x.f = 0;
+        if (o.opc == PZK_U_LUTV) x.e = lutv_off[(uint32_t)i];
+        PzkOp raw; memcpy(&raw, &x, sizeof raw);
+        out_ops.push_back(raw);
+      }
+      segs[s].n_ops = out_ops.size() - segs[s].op_off;
+    }
+  }
+  // ---- rows per segment (slot addressed)
+  auto ref_of_sig = [&](uint32_t sig) -> uint32_t {
+    if (sig == 0xFFFFFFFFu) return PZK_REF_ONE;
+    uint32_t v = sig_val[sig];
+    if (!v) return PZK_REF_ZERO;
+    uint32_t cls = v_cls[v] == CLS_U ? 0u : (v_cls[v] == CLS_I ? 1u : 2u);
+    return (cls << 30) | v_slot[v];
+  };
+  {
+    std::vector<std::vector<uint32_t>> by_seg(segs.size());
+    for (size_t r = 0; r < nrows; r++) by_seg[row_seg[r]].push_back((uint32_t)r);
+    for (size_t s = 0; s < segs.size(); s++) {
+      segs[s].row_off = out_rows.size();
+      for (uint32_t r : by_seg[s]) {
+        PzkRow row; row.term_off = (uint32_t)out_terms.size(); row.kind = PZK_ROW_FIELD; row.index = r;
+        uint16_t cnt[3] = {0, 0, 0};
+        uint32_t lens[3] = {rows[r].na, rows[r].nb, rows[r].nc};
+        uint64_t off = rows[r].off;
+        for (int part = 0; part < 3; part++)
+          for (uint32_t t = 0; t < lens[part]; t++, off++) {
+            uint32_t ref = ref_of_sig(terms[off].first);
+            if (ref == PZK_REF_ZERO) continue;  // unassigned wire: value 0
+            PzkTerm pt; pt.ref = ref; pt.coef = terms[off].second;
+            out_terms.push_back(pt); cnt[part]++;
+          }
+        row.na = cnt[0]; row.nb = cnt[1]; row.nc = cnt[2];
+        out_rows.push_back(row);
+      }
+      segs[s].n_rows = out_rows.size() - segs[s].row_off;
+    }
+  }
+  // ---- exports per segment
+  {
+    std::vector<std::vector<PzkExport>> by_seg(segs.size());
+    for (uint32_t sig = 0; sig < sig_val.size(); sig++) {
+      uint32_t v = sig_val[sig];
+      PzkExport e; e.wire = sig2wire[sig];
+      if (!v) { e.ref = PZK_REF_ZERO; by_seg[0].push_back(e); continue; }
+      e.ref = ref_of_sig(sig);
+      by_seg[def_seg[v]].push_back(e);
+    }
+    for (size_t s = 0; s < segs.size(); s++) {
+      segs[s].exp_off = out_exports.size();
+      out_exports.insert(out_exports.end(), by_seg[s].begin(), by_seg[s].end());
+      segs[s].n_exp = out_exports.size() - segs[s].exp_off;
+    }
+  }
+  stats->n_ops = out_ops.size();
+  stats->n_u_slots = n_u_slots; stats->n_f_slots = n_f_slots; stats->n_segments = (uint32_t)segs.size();
+}
+
+static void json_dims(std::string& s, const std::vector<int>& d) {
+  s += "[";
+  for (size_t i = 0; i < d.size(); i++) { if (i) s += ","; s += std::to_string(d[i]); }
+  s += "]";
+}
+
+void Compiler::Impl::build_meta() {
+  std::string s = "{";
+  s += "\"main\":\"" + nm(unit.main.call->name) + "\",";
+  s += "\"n_wires\":" + std::to_string(sig_val.size() + 1) + ",";
+  s += "\"n_constraints\":" + std::to_string(rows.size()) + ",";
+  s += "\"inputs\":[";
+  uint32_t off = 0;
+  for (size_t i = 0; i < main_inputs_desc.size(); i++) {
+    if (i) s += ",";
+    uint32_t cnt = prod(main_inputs_desc[i].second);
+    auto it = opt.input_bits.find(main_inputs_desc[i].first);
+    s += "{\"name\":\"" + main_inputs_desc[i].first + "\",\"dims\":";
+    json_dims(s, main_inputs_desc[i].second);
+    s += ",\"offset\":" + std::to_string(off) + ",\"size\":" + std::to_string(cnt) +
+         ",\"bits\":" + std::to_string(it == opt.input_bits.end() ? 0 : it->second) + "}";
+    off += cnt;
+  }
+  s += "],\"outputs\":[";
+  off = 0;
+  for (size_t i = 0; i < main_outputs_desc.size(); i++) {
+    if (i) s += ",";
+    uint32_t cnt = prod(main_outputs_desc[i].second);
+    s += "{\"name\":\"" + main_outputs_desc[i].first + "\",\"dims\":";
+    json_dims(s, main_outputs_desc[i].second);
+    s += ",\"offset\":" + std::to_string(off) + ",\"size\":" + std::to_string(cnt) + "}";
+    off += cnt;
+  }
+  s += "],\"n_pub_out\":" + std::to_string(n_pub_out) + ",\"n_pub_in\":" + std::to_string(n_pub_in) +
+       ",\"n_prv_in\":" + std::to_string(n_prv_in);
+  s += ",\"stats\":{\"u_ops\":" + std::to_string(stats->u_ops) + ",\"f_mul\":" + std::to_string(stats->f_mul) +
+       ",\"f_inv\":" + std::to_string(stats->f_inv) + ",\"f_other\":" + std::to_string(stats->f_other) +
+       ",\"bigdiv\":" + std::to_string(stats->bigdiv) + ",\"lut\":" + std::to_string(stats->lut) +
+       ",\"op_records\":" + std::to_string(out_ops.size()) + ",\"segments\":" + std::to_string(segs.size()) +
+       ",\"u_slots\":" + std::to_string(n_u_slots) + ",\"f_slots\":" + std::to_string(n_f_slots) + "}";
+  s += "}";
+  meta_json = s;
+}
+
+// ---------------------------------------------------------------------------------------
+Compiler::Compiler(const std::string& main_path, const CompileOptions& opt) : im(new Impl()) {
+  im->opt = opt; im->main_path = main_path; im->stats = &stats;
+}
+Compiler::~Compiler() {
+  for (Layout* l : im->layout_list) delete l;
+  for (Comp* c : im->comps) delete c;
+  delete im;
+}
+void Compiler::run() {
+  auto t0 = std::chrono::steady_clock::now();
+  load_file(im->unit, im->main_path, true, {});
+  im->run_main();
+  im->backend();
+  im->build_meta();
+  stats.seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+std::string Compiler::main_io_json() const { return im->meta_json; }
+
+static void wr(FILE* f, const void* p, size_t n) { if (n && fwrite(p, 1, n, f) != n) throw CompileError("write failed"); }
+static void pad16(FILE* f, uint64_t& pos) { static const char z[16] = {0}; uint64_t r = (16 - pos % 16) % 16; wr(f, z, r); pos += r; }
+
+void Compiler::write_program(const std::string& path) {
+  Impl& m = *im;
+  FILE* f = fopen(path.c_str(), "wb");
+  if (!f) throw CompileError("cannot write " + path);
+  PzkHeader h; memset(&h, 0, sizeof h);
+  h.magic = PZK_MAGIC; h.version = PZK_VERSION;
+  h.n_wires = (uint32_t)m.sig_val.size() + 1;
+  h.n_pub_out = m.n_pub_out; h.n_pub_in = m.n_pub_in; h.n_prv_in = m.n_prv_in;
+  h.n_constraints = (uint32_t)m.rows.size();
+  h.n_u_slots = m.n_u_slots; h.n_f_slots = m.n_f_slots;
+  h.n_segments = (uint32_t)m.segs.size();
+  h.n_fpool = (uint32_t)m.fpool.size();
+  h.n_coef = (uint32_t)m.coefs.size();
+  h.n_inputs = (uint32_t)m.out_inputs.size();
+  h.n_list = (uint32_t)m.out_list.size();
+  h.n_op_records = m.out_ops.size();
+  h.n_rows = m.out_rows.size(); h.n_terms = m.out_terms.size(); h.n_exports = m.out_exports.size();
+  h.stat_u_ops = stats.u_ops; h.stat_f_mul = stats.f_mul; h.stat_f_inv = stats.f_inv;
+  h.stat_f_other = stats.f_other; h.stat_bigdiv = stats.bigdiv;
+  h.reserved[0] = m.meta_json.size();
+  uint64_t pos = 0;
+  auto section = [&](const void* p, size_t n) { wr(f, p, n); pos += n; pad16(f, pos); };
+  section(&h, sizeof h);
+  section(m.segs.data(), m.segs.size() * sizeof(PzkSegment));
+  section(m.out_ops.data(), m.out_ops.size() * sizeof(PzkOp));
+  section(m.fpool.data(), m.fpool.size() * 32);
+  {
+    std::vector<PzkCoef> cs(m.coefs.size());
+    for (size_t i = 0; i < cs.size(); i++) {
+      U256 mm = fr_to_mont(m.coefs[i]), m2 = fr_to_mont(mm);
+      memcpy(cs[i].plain, m.coefs[i].w, 32); memcpy(cs[i].mont, mm.w, 32); memcpy(cs[i].mont2, m2.w, 32);
+    }
+    section(cs.data(), cs.size() * sizeof(PzkCoef));
+  }
+  section(m.out_list.data(), m.out_list.size() * 4);
+  section(m.out_inputs.data(), m.out_inputs.size() * sizeof(PzkInput));
+  section(m.out_rows.data(), m.out_rows.size() * sizeof(PzkRow));
+  section(m.out_terms.data(), m.out_terms.size() * sizeof(PzkTerm));
+  section(m.out_exports.data(), m.out_exports.size() * sizeof(PzkExport));
+  section(m.meta_json.data(), m.meta_json.size());
+  fclose(f);
+}
+
+// iden3 r1cs v1
+void Compiler::write_r1cs(const std::string& path) {
+  Impl& m = *im;
+  FILE* f = fopen(path.c_str(), "wb");
+  if (!f) throw CompileError("cannot write " + path);
+  auto u32 = [&](uint32_t v) { wr(f, &v, 4); };
+  auto u64 = [&](uint64_t v) { wr(f, &v, 8); };
+  uint32_t n_wires = (uint32_t)m.sig_val.size() + 1;
+  wr(f, "r1cs", 4); u32(1); u32(3);
+  // header section
+  u32(1); u64(4 + 32 + 4 * 4 + 8 + 4);
+  u32(32); wr(f, FR_P.w, 32);
+  u32(n_wires); u32(m.n_pub_out); u32(m.n_pub_in); u32(m.n_prv_in);
+  u64(n_wires); u32((uint32_t)m.rows.size());
+  // constraints section
+  uint64_t size = 0;
+  for (auto& r : m.rows) size += 12 + (uint64_t)(r.na + r.nb + r.nc) * 36;
+  u32(2); u64(size);
+  std::vector<std::pair<uint32_t, uint32_t>> tmp;
+  for (auto& r : m.rows) {
+    uint32_t lens[3] = {r.na, r.nb, r.nc};
+    uint64_t off = r.off;
+    for (int part = 0; part < 3; part++) {
+      tmp.clear();
+      for (uint32_t t = 0; t < lens[part]; t++, off++) {
+        uint32_t sig = m.terms[off].first;
+        tmp.emplace_back(sig == 0xFFFFFFFFu ? 0u : m.sig2wire[sig], m.terms[off].second);
+      }
+      std::sort(tmp.begin(), tmp.end());
+      u32((uint32_t)tmp.size());
+      for (auto& t : tmp) { u32(t.first); wr(f, m.coefs[t.second].w, 32); }
+    }
+  }
+  // wire -> label map (identity: O0 layout)
+  u32(3); u64((uint64_t)n_wires * 8);
+  for (uint32_t i = 0; i < n_wires; i++) u64(i);
+  fclose(f);
+}
+
+void Compiler::write_sym(const std::string& path) {
+  Impl& m = *im;
+  FILE* f = fopen(path.c_str(), "w");
+  if (!f) throw CompileError("cannot write " + path);
+  uint32_t comp_counter = 0;
+  std::function<void(Layout*, uint32_t, const std::string&)> walk = [&](Layout* lay, uint32_t base, const std::string& prefix) {
+    uint32_t cid = comp_counter++;
+    std::vector<std::pair<uint32_t, std::string>> lines;
+    for (int n : lay->order) {
+      SigInfo& s = lay->sigs[n];
+      uint32_t cnt = Impl::prod(s.dims);
+      std::vector<int> idx(s.dims.size(), 0);
+      for (uint32_t k = 0; k < cnt; k++) {
+        std::string name = prefix + "." + m.nm(n);
+        for (size_t d = 0; d < idx.size(); d++) name += "[" + std::to_string(idx[d]) + "]";
+        lines.emplace_back(base + s.off + k, name);
+        for (int d = (int)idx.size() - 1; d >= 0; d--) { if (++idx[d] < s.dims[d]) break; idx[d] = 0; }
+      }
+    }
+    std::sort(lines.begin(), lines.end());
+    for (auto& l : lines) {
+      uint32_t w = m.sig2wire[l.first];
+      fprintf(f, "%u,%u,%u,%s\n", w, w, cid, l.second.c_str());
+    }
+    for (auto& ck : lay->child_order) {
+      Child& c = lay->children[ck];
+      std::string name = prefix + "." + m.nm(ck.first);
+      const std::vector<int>& dims = lay->comp_dims[ck.first];
+      if (!dims.empty()) {
+        std::vector<int> idx(dims.size());
+        int rem = ck.second;
+        for (int d = (int)dims.size() - 1; d >= 0; d--) { idx[d] = rem % dims[d]; rem /= dims[d]; }
+        for (int v : idx) name += "[" + std::to_string(v) + "]";
+      }
+      walk(c.lay, base + c.rel_base, name);
+    }
+  };
+  walk(m.main_lay, 0, "main");
+  fclose(f);
+}
+
+}  // namespace pzk

@@ -1,0 +1,130 @@
+// compiler.hpp - circom -> typed linear SSA ("program") + R1CS + SYM.
+//
+// From-scratch lowering of a circom circuit's witness computation (what circom's
+// generated witness_calculator.wasm executes for the reference, call sites
+// /root/reference/test/automatisationTest.js:37-51) into a straight-line program of
+// typed ops (include/pzk_program.h), plus the constraint system in iden3 .r1cs form
+// and the .sym name table.  Symbolic execution in two phases per template instance:
+//   phase A (shape): run the body with signal values unknown to learn the signal
+//            and sub-component layout; cached per (template, arguments);
+//   phase B (emit):  run the body when the instance's last input has been assigned,
+//            emitting one SSA value per computed signal / temporary and one
+//            (A, B, C) row per `<==` / `===`.
+#pragma once
+#include <cstdint>
+#include <functional>
+#include <string>
+#include <vector>
+
+#include "circom_front.hpp"
+#include "pzk_program.h"
+
+namespace pzk {
+
+typedef __int128 i128;
+
+struct Lin {
+  std::vector<std::pair<uint32_t, U256>> t;  // (signal index, coefficient), sorted by signal
+  U256 k;                                    // constant term
+};
+struct Alg {
+  int deg = 0;  // 0 const, 1 linear, 2 quadratic (a*b + c), 3 not representable
+  Lin a, b, c;
+};
+typedef std::shared_ptr<Alg> AlgP;
+
+struct SVal {
+  uint8_t kind = 0;  // 0 constant, 1 SSA value, 2 unknown (phase A)
+  uint32_t id = 0;
+  U256 c;
+  AlgP alg;
+  static SVal konst(const U256& v) { SVal s; s.kind = 0; s.c = v; return s; }
+  static SVal unk() { SVal s; s.kind = 2; return s; }
+  static SVal ssa(uint32_t id) { SVal s; s.kind = 1; s.id = id; return s; }
+};
+
+struct AVal;
+struct Value {
+  bool arr = false;
+  SVal s;
+  std::shared_ptr<AVal> a;
+};
+struct AVal {
+  std::vector<int> dims;
+  std::vector<SVal> v;
+};
+
+struct SigInfo { uint32_t off; std::vector<int> dims; int kind; };  // kind 0 mid, 1 in, 2 out
+
+struct Layout;
+struct Child {
+  int tname;
+  std::string key;
+  uint32_t rel_base;
+  Layout* lay;
+};
+struct Layout {
+  int tname;
+  std::vector<Value> args;
+  std::unordered_map<int, SigInfo> sigs;
+  std::vector<int> order;
+  std::unordered_map<int, std::vector<int>> comp_dims;
+  std::map<std::pair<int, int>, Child> children;
+  std::vector<std::pair<int, int>> child_order;
+  uint32_t own = 0, total = 0, n_inputs = 0;
+};
+
+struct Comp {
+  Layout* lay;
+  uint32_t base;
+  int64_t pending;
+  bool ran = false;
+  std::map<std::pair<int, int>, Comp*> kids;
+  Comp* parent;
+};
+
+struct Table {
+  uint8_t n;
+  uint32_t sup[4];
+  int64_t e[16];
+};
+
+struct OpRec {
+  uint8_t opc, flags;
+  uint16_t imm16;
+  uint32_t dst, a, b, c, d;
+};
+
+enum { CLS_U = 0, CLS_I = 1, CLS_F = 2, CLS_N = 3 };
+
+struct CompileOptions {
+  std::map<std::string, int> input_bits;  // main input name -> declared width (bits)
+  uint32_t seg_ops = 16384;
+  bool verbose = false;
+  bool intrinsics = true;
+};
+
+struct CompileStats {
+  uint64_t n_signals = 0, n_constraints = 0, n_ops = 0, n_values = 0;
+  uint64_t u_ops = 0, f_mul = 0, f_inv = 0, f_other = 0, bigdiv = 0, lut = 0;
+  uint32_t n_u_slots = 0, n_f_slots = 0, n_segments = 0;
+  double seconds = 0;
+};
+
+class Compiler {
+ public:
+  Compiler(const std::string& main_path, const CompileOptions& opt);
+  ~Compiler();
+  void run();
+  void write_program(const std::string& path);
+  void write_r1cs(const std::string& path);
+  void write_sym(const std::string& path);
+  CompileStats stats;
+  std::string main_io_json() const;
+
+ private:
+  struct Impl;
+  Impl* im;
+};
+
+}  // namespace pzk
