@@ -1,0 +1,301 @@
+#!/usr/bin/env python
+"""bench.py - witnesses/sec + R1CS constraints checked/sec for registerIdentity (SHA-256 + RSA-2048).
+
+One "step" = one pass of the hot path (evaluate every signal of every lane, check every
+constraint) over one batch of synthetic passports of the north-star circuit
+RegisterIdentityBuilder(1,256,3,4,600,248,1,1496,3,256) (/root/reference/hardhat.config.ts:29).
+
+  python bench.py [--gpus N --steps K --warmup W] [--batch B]      our arm (CUDA, one rank per GPU)
+  python bench.py --impl reference ...                             CPU arm: the oracle evaluator on host cores
+
+`value` = whole-job witnesses/s with inputs resident in HBM (CUDA events, max over ranks);
+`e2e`   = the same metric through the C ABI call with pinned HOST buffers, H2D + D2H inside the
+          timed region; `roofline` = dominant kernel, algorithmic bytes / CUDA-event time against
+          the measured HBM peak; `cpu_baseline` = oracle/ssa_ref.c on the host cores (a stand-in
+          "port": the reference's wasm calculator cannot run here, no node/circom - BASELINE.md).
+The batch shards across ranks with no collective: scaling is weak.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "witnesses/sec + R1CS constraints checked/sec, registerIdentity SHA256/RSA2048"
+WORKLOAD = "registerIdentity_1_256_3_4_600_248_1_1496_3_256 (SHA-256 + RSA-2048 e=65537), synthetic passports"
+UNIQUE = 256  # distinct signed passports generated on the host; tiled to fill the batch
+
+
+def make_inputs(meta, batch, seed):
+    import numpy as np
+    from passport_zk_circuits_b200 import witness as W
+    from passport_zk_circuits_b200.passports import C3, PassportFactory
+    fac = PassportFactory(C3, seed=seed, n_sig_keys=4, n_aa_keys=4)
+    n = min(UNIQUE, batch)
+    uniq = W.pack_inputs_fast(meta, [fac.make(i).inputs for i in range(n)])
+    reps = (batch + n - 1) // n
+    return np.tile(uniq, (reps, 1, 1))[:batch].copy()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def _ref_worker(args):
+    prog, inputs, check = args
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref as oracle_ref
+    rp = oracle_ref.RefProgram(prog)
+    t = time.time()
+    bad = 0
+    for row in inputs:
+        st, fb, _ = rp.witness(row, want_witness=False, check_rows=check)
+        bad += st != 0
+    return time.time() - t, bad
+
+
+def cpu_reference(prog, inputs, workers, per_worker):
+    """The oracle evaluator (oracle/ssa_ref.c) on `workers` host processes, `per_worker` witnesses each.
+    Returns witnesses/s (wall clock of the slowest worker)."""
+    import multiprocessing as mp
+    jobs = [(prog, inputs[(w * per_worker) % len(inputs):][:per_worker], True) for w in range(workers)]
+    jobs = [(p, i if len(i) == per_worker else inputs[:per_worker], c) for p, i, c in jobs]
+    t0 = time.time()
+    with mp.get_context("spawn").Pool(workers) as pool:
+        res = pool.map(_ref_worker, jobs)
+    wall = time.time() - t0
+    slow = max(r[0] for r in res)
+    assert sum(r[1] for r in res) == 0, "oracle evaluator reported failing lanes on valid passports"
+    return workers * per_worker / slow, wall
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=0, help="passports per GPU per step (0 = default)")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-sample", type=int, default=0, help="witnesses per worker for the CPU baseline")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    from passport_zk_circuits_b200 import witness as W
+    import numpy as np
+
+    prog = W.artifact("c3")
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import ref as oracle_ref
+        oracle_ref.build()
+        rp = oracle_ref.RefProgram(prog)
+        cores = os.cpu_count() or 1
+        per = a.cpu_sample or 4
+        inputs = make_inputs(rp.meta, min(UNIQUE, cores * per), seed=1)
+        for _ in range(max(a.warmup, 0) and 1):
+            cpu_reference(prog, inputs, cores, 1)
+        vals = []
+        for _ in range(a.steps):
+            v, _ = cpu_reference(prog, inputs, cores, per)
+            vals.append(v)
+        v = statistics.mean(vals)
+        line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "witnesses/s", "n_gpus": a.gpus,
+                "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1000.0 * cores * per / v,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64+fr256",
+                "data": "synthetic", "constraints_per_sec": v * rp.n_constraints,
+                "config": {"workload": WORKLOAD, "sample": f"{cores * per} witnesses per step"},
+                "cpu_baseline": {"value": v, "unit": "witnesses/s", "cores": cores, "kind": "port",
+                                 "sample": f"{cores} processes x {per} witnesses per step (oracle/ssa_ref.c)"},
+                "e2e": {"value": v, "unit": "witnesses/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------ our arm (CUDA)
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback for the product path)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    calc = W.WitnessCalculator(prog, device=local_rank)
+    stats = calc.stats()
+    B = a.batch or 32768
+    inputs = make_inputs(calc.meta, B, seed=1 + rank)
+    h2d = inputs.nbytes
+    n_pub = calc.n_public
+    d2h = B * (4 + 8 + n_pub * 32)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # device-resident measurement ------------------------------------------------------
+    calc.upload(inputs)
+    for _ in range(a.warmup):
+        calc.run(True)
+    res = calc.download()
+    assert (res.status == 0).all(), "valid synthetic passports must satisfy every constraint"
+    calc.profile(enable=True, reset=True)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    t0 = time.time()
+    for _ in range(a.steps):
+        calc.run(True)
+    barrier()
+    wall = time.time() - t0
+    clocks = sampler.stop()
+    prof = calc.profile()
+    dev_ms = prof["run"][0]
+    calc.profile(enable=False)
+
+    # end to end through the C ABI with pinned host buffers -------------------------------
+    pin_in = torch.empty(inputs.shape, dtype=torch.int64, pin_memory=True)
+    pin_in.numpy().view(np.uint64)[...] = inputs
+    pin_status = torch.empty(B, dtype=torch.int32, pin_memory=True)
+    pin_bad = torch.empty(B, dtype=torch.int64, pin_memory=True)
+    pin_pub = torch.empty((B, n_pub, 4), dtype=torch.int64, pin_memory=True)
+    L = calc._L
+
+    def e2e_step():
+        rc = L.pzk_witness_batch(calc._h, pin_in.data_ptr(), B, pin_status.data_ptr(), pin_bad.data_ptr(),
+                                 pin_pub.data_ptr(), None, 0, None)
+        assert rc == 0, rc
+    e2e_step()
+    barrier()
+    t1 = time.time()
+    e2e_steps = max(1, min(a.steps, 3))
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_wall = time.time() - t1
+    assert int((pin_status.numpy() != 0).sum()) == 0
+
+    # max over ranks
+    times = torch.tensor([dev_ms / 1000.0, e2e_wall, wall], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    dev_s, e2e_s, wall_s = [float(x) for x in times.tolist()]
+    total = B * world
+    value = total * a.steps / dev_s
+    e2e_value = total * e2e_steps / e2e_s
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak, peak_src = (peaks.get("hbm_gbs"), "measured") if peaks.get("hbm_gbs") else (6650.0, "fallback")
+        # dominant kernel family by CUDA-event time
+        fam = max(("eval", "check"), key=lambda k: prof[k][0])
+        bytes_per_lane = {"eval": stats_bytes(calc, "eval"), "check": stats_bytes(calc, "check")}
+        ms, launches = prof[fam]
+        lanes_per_launch = min(B, calc.tile_lanes())
+        per_launch_bytes = bytes_per_lane[fam] * lanes_per_launch / max(1, calc.meta["stats"]["segments"])
+        achieved = (bytes_per_lane[fam] * B * a.steps) / (ms / 1000.0) / 1e9
+        roofline = {"bound": "hbm", "kernel": fam + "_kernel", "achieved": achieved, "peak": hbm_peak,
+                    "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_witness": bytes_per_lane[fam], "bytes_per_launch": per_launch_bytes,
+                    "avg_launch_ms": ms / max(1, launches), "launches": launches,
+                    "share_of_step": ms / max(1e-9, prof["run"][0])}
+        sm_mhz = clocks.get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0
+        imad_per_witness = 136 * (stats["f_mul"] + 384 * stats["f_inv"])
+        imad_peak = 148 * 64 * sm_mhz * 1e6
+        line = {"metric": METRIC, "value": value, "unit": "witnesses/s", "n_gpus": world, "steps": a.steps,
+                "warmup": a.warmup, "ms_per_step": 1000.0 * dev_s / a.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "u64+fr256", "data": "synthetic",
+                "constraints_per_sec": value * calc.n_constraints,
+                "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": total,
+                           "unique_passports_per_gpu": min(UNIQUE, B), "tile_lanes": calc.tile_lanes(),
+                           "n_wires": calc.n_wires, "n_constraints": calc.n_constraints,
+                           "cache": "slot planes are GBs per tile (>> 126 MB L2); no flush needed",
+                           "parallelism": f"batch sharded over {world} GPU(s), no collective"},
+                "e2e": {"value": e2e_value, "unit": "witnesses/s", "h2d_bytes_per_step": h2d * world,
+                        "d2h_bytes_per_step": d2h * world, "steps": e2e_steps,
+                        "returns": "status + first failing constraint + 5 public signals per passport"},
+                "gpu_launches": int(sum(prof[k][1] for k in ("eval", "check", "export"))),
+                "kernel_ms": {k: prof[k][0] for k in ("eval", "check", "export", "run")},
+                "wall_s": wall_s, "clocks": clocks, "roofline": roofline,
+                "imad": {"per_witness": imad_per_witness, "achieved_per_s": imad_per_witness * value / world,
+                         "peak_per_s": imad_peak, "frac": imad_per_witness * value / world / imad_peak,
+                         "note": "136 IMAD per Montgomery product; inversion counted as its 384-product chain"}}
+        if not a.no_cpu_baseline:
+            sys.path.insert(0, os.path.join(ROOT, "oracle"))
+            import ref as oracle_ref
+            oracle_ref.build()
+            cores = os.cpu_count() or 1
+            per = a.cpu_sample or 4
+            v, cpu_wall = cpu_reference(prog, inputs[:min(len(inputs), UNIQUE)], cores, per)
+            line["cpu_baseline"] = {"value": v, "unit": "witnesses/s", "cores": cores, "kind": "port",
+                                    "sample": f"{cores} processes x {per} witnesses (oracle/ssa_ref.c, same program "
+                                              f"and inputs; reference wasm baseline unavailable on this host)"}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def stats_bytes(calc, fam):
+    s = calc.meta["stats"]
+    if fam == "eval":
+        return s.get("eval_bytes", 0)
+    return s.get("check_bytes", 0)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,87 @@
+"""Builds the compiled programs under artifacts/ (git-ignored, shipped with the repo snapshot).
+
+Reference circuits are compiled from /root/reference when it is mounted (this container);
+the GPU box only uses the prebuilt files.  The root files generated here are the 3-line
+`component main = T(...)` wrappers that test/process_passport.js:573-588 (writeToCircom)
+writes for the reference - no reference source is copied."""
+from __future__ import annotations
+
+import os
+
+from . import witness as W
+from .passports import C3, CircuitParams
+
+REFERENCE = "/root/reference"
+_TESTS = os.path.join(W._ROOT, "tests", "circuits")
+
+
+def _wrapper(name, body):
+    d = os.path.join(W.ARTIFACT_DIR, "_mains")
+    os.makedirs(d, exist_ok=True)
+    path = os.path.join(d, name + ".circom")
+    with open(path, "w") as f:
+        f.write(body)
+    return path
+
+
+def reference_circuits():
+    lib = REFERENCE + "/circuits/lib/circuits"
+    return {
+        # config 1: Poseidon + SparseMerkleTree inclusion
+        "smt80": (f'pragma circom 2.1.6;\ninclude "{REFERENCE}/circuits/merkleTree/SMTVerifier.circom";\n'
+                  "component main {public [root]} = SMTVerifier(80);\n", {}),
+        "poseidon2": (f'pragma circom 2.1.6;\ninclude "{lib}/hasher/poseidon/poseidon.circom";\n'
+                      "component main = PoseidonHash(2);\n", {}),
+        "sha256_1": (f'pragma circom 2.1.6;\ninclude "{lib}/hasher/hash.circom";\n'
+                     "component main = ShaHashChunks(1, 256);\n", {"in": 1}),
+        "babyjub": (f'pragma circom 2.1.6;\ninclude "{lib}/babyjubjub/curve.circom";\n'
+                    "component main = BabyjubjubBase8Multiplication();\n", {}),
+        "rsa2048": (f'pragma circom 2.1.6;\ninclude "{lib}/signatures/rsa.circom";\n'
+                    "component main = RsaVerifyPkcs1v15(64, 32, 65537, 256);\n",
+                    {"signature": 64, "pubkey": 64, "hashed": 1}),
+        # config 3: the north-star circuit (hardhat.config.ts:29)
+        "c3": (C3.main_source(REFERENCE + "/circuits/identityManagement/registerIdentityBuilder.circom"),
+               W.REGISTER_IDENTITY_BITS),
+    }
+
+
+OWN_CIRCUITS = {"t_mix": ("mix.circom", {"u": 16, "bits": 1}),
+                "t_bigdiv": ("bigdiv.circom", {"a": 64, "b": 64})}
+
+BIG = {"c3"}  # ship only the xz-packed program for these
+
+
+def _stale(out, deps):
+    if not os.path.exists(out):
+        return True
+    t = os.path.getmtime(out)
+    return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
+
+
+def build_all(verbose=True):
+    os.makedirs(W.ARTIFACT_DIR, exist_ok=True)
+    deps = [W.LIB_PATH]
+    for name, (fname, bits) in OWN_CIRCUITS.items():
+        prefix = os.path.join(W.ARTIFACT_DIR, name)
+        src = os.path.join(_TESTS, fname)
+        if _stale(prefix + ".pzkp", deps + [src]):
+            if verbose:
+                print("compiling", name)
+            W.compile_circuit(src, prefix, bits)
+    if not os.path.isdir(REFERENCE):
+        return
+    for name, (body, bits) in reference_circuits().items():
+        prefix = os.path.join(W.ARTIFACT_DIR, name)
+        final = prefix + (".pzkp.xz" if name in BIG else ".pzkp")
+        if not _stale(final, deps):
+            continue
+        if verbose:
+            print("compiling", name)
+        main = _wrapper(name, body)
+        W.compile_circuit(main, prefix, bits)
+        if name in BIG:
+            W.pack_artifact(prefix + ".pzkp")
+            for ext in (".r1cs", ".sym"):
+                # too large to ship; regenerate with compile_circuit when needed here
+                if os.path.exists(prefix + ext):
+                    os.replace(prefix + ext, prefix + ext + ".local")

@@ -1198,7 +1198,7 @@ struct Compiler::Impl {
     if (args.size() != 5) return false;
     for (int i = 0; i < 3; i++) if (args[i].arr || args[i].s.kind != 0 || !args[i].s.c.fits64()) return false;
     uint64_t n = args[0].s.c.w[0], k = args[1].s.c.w[0], m = args[2].s.c.w[0];
-    if (n == 0 || n > 64 || k == 0 || k + m > 180 || !args[3].arr || !args[4].arr) return false;
+    if (n != 64 || k < 2 || k > 64 || k + m > 128 || !args[3].arr || !args[4].arr) return false;
     if (args[3].a->v.size() < k + m || args[4].a->v.size() < k) return false;
     i128 lim = n == 64 ? U64_MAX_ : (((i128)1 << n) - 1);
     std::vector<uint32_t> ids;

@@ -1,0 +1,230 @@
+// fr_device.cuh - BN254 Fr arithmetic for sm_100a, 4 x 64-bit Montgomery limbs, R = 2^256.
+//
+// The multiplier works on 32-bit halves (CIOS over 8 limbs): Blackwell's integer multiplier is
+// the 32-bit IMAD on the fma pipe (64 IMAD/clk/SM) and a 64-bit product is four of them, so the
+// product is expressed directly as 32x32->64 multiply-accumulates (IMAD.WIDE).  One Montgomery
+// product = 8x8 product terms + 8x8 reduction terms + 8 m computations = 136 IMAD (the figure
+// DESIGN.md uses for the IMAD roofline).
+#pragma once
+#include <cstdint>
+
+namespace pzkd {
+
+typedef unsigned long long u64;
+typedef unsigned int u32;
+
+struct Fr { u64 v[4]; };
+
+__device__ __constant__ u64 FR_P_C[4] = {0x43e1f593f0000001ull, 0x2833e84879b97091ull,
+                                         0xb85045b68181585dull, 0x30644e72e131a029ull};
+#define P0 0x43e1f593f0000001ull
+#define P1 0x2833e84879b97091ull
+#define P2 0xb85045b68181585dull
+#define P3 0x30644e72e131a029ull
+#define PINV32 0xefffffffu  // -p^-1 mod 2^32
+
+__device__ __forceinline__ u64 addc(u64 a, u64 b, u32& carry) {
+  u64 r;
+  asm("{\n\t.reg .u32 c;\n\tadd.cc.u64 %0, %2, %3;\n\taddc.u32 c, 0, 0;\n\tmov.u32 %1, c;\n\t}" : "=l"(r), "=r"(carry) : "l"(a), "l"(b));
+  return r;
+}
+
+// r = a + b (256-bit), returns carry out
+__device__ __forceinline__ u32 add256(u64* r, const u64* a, const u64* b) {
+  u32 c;
+  asm("add.cc.u64 %0, %5, %9;\n\t"
+      "addc.cc.u64 %1, %6, %10;\n\t"
+      "addc.cc.u64 %2, %7, %11;\n\t"
+      "addc.cc.u64 %3, %8, %12;\n\t"
+      "addc.u32 %4, 0, 0;"
+      : "=l"(r[0]), "=l"(r[1]), "=l"(r[2]), "=l"(r[3]), "=r"(c)
+      : "l"(a[0]), "l"(a[1]), "l"(a[2]), "l"(a[3]), "l"(b[0]), "l"(b[1]), "l"(b[2]), "l"(b[3]));
+  return c;
+}
+// r = a - b (256-bit), returns borrow (1 when a < b)
+__device__ __forceinline__ u32 sub256(u64* r, const u64* a, const u64* b) {
+  u32 c;
+  asm("sub.cc.u64 %0, %5, %9;\n\t"
+      "subc.cc.u64 %1, %6, %10;\n\t"
+      "subc.cc.u64 %2, %7, %11;\n\t"
+      "subc.cc.u64 %3, %8, %12;\n\t"
+      "subc.u32 %4, 0, 0;"
+      : "=l"(r[0]), "=l"(r[1]), "=l"(r[2]), "=l"(r[3]), "=r"(c)
+      : "l"(a[0]), "l"(a[1]), "l"(a[2]), "l"(a[3]), "l"(b[0]), "l"(b[1]), "l"(b[2]), "l"(b[3]));
+  return c & 1;
+}
+__device__ __forceinline__ bool geq_p(const u64* a) {
+  if (a[3] != P3) return a[3] > P3;
+  if (a[2] != P2) return a[2] > P2;
+  if (a[1] != P1) return a[1] > P1;
+  return a[0] >= P0;
+}
+__device__ __forceinline__ void sub_p(u64* a) {
+  const u64 p[4] = {P0, P1, P2, P3};
+  sub256(a, a, p);
+}
+__device__ __forceinline__ void fr_add(u64* r, const u64* a, const u64* b) {
+  u64 t[4];
+  u32 c = add256(t, a, b);
+  if (c || geq_p(t)) sub_p(t);
+  r[0] = t[0]; r[1] = t[1]; r[2] = t[2]; r[3] = t[3];
+}
+__device__ __forceinline__ void fr_sub(u64* r, const u64* a, const u64* b) {
+  u64 t[4];
+  u32 br = sub256(t, a, b);
+  if (br) { const u64 p[4] = {P0, P1, P2, P3}; add256(t, t, p); }
+  r[0] = t[0]; r[1] = t[1]; r[2] = t[2]; r[3] = t[3];
+}
+__device__ __forceinline__ bool fr_is_zero(const u64* a) { return (a[0] | a[1] | a[2] | a[3]) == 0; }
+__device__ __forceinline__ bool fr_eq(const u64* a, const u64* b) {
+  return ((a[0] ^ b[0]) | (a[1] ^ b[1]) | (a[2] ^ b[2]) | (a[3] ^ b[3])) == 0;
+}
+
+// ---- Montgomery product on 8 x 32-bit limbs (CIOS), a*b*2^-256 mod p -------------------
+__device__ __forceinline__ void fr_mul(u64* r64, const u64* a64, const u64* b64) {
+  const u32 p[8] = {0xf0000001u, 0x43e1f593u, 0x79b97091u, 0x2833e848u,
+                    0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
+  u32 a[8], b[8];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    a[2 * i] = (u32)a64[i]; a[2 * i + 1] = (u32)(a64[i] >> 32);
+    b[2 * i] = (u32)b64[i]; b[2 * i + 1] = (u32)(b64[i] >> 32);
+  }
+  u32 t[10];
+#pragma unroll
+  for (int i = 0; i < 10; i++) t[i] = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    // t += a * b[i]
+    u32 bi = b[i];
+    u32 carry = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      // (carry, t[j]) = t[j] + a[j]*bi + carry   -- 64-bit accumulate via mad.wide
+      u64 acc = (u64)a[j] * bi + t[j] + carry;
+      t[j] = (u32)acc;
+      carry = (u32)(acc >> 32);
+    }
+    u64 top = (u64)t[8] + carry;
+    t[8] = (u32)top;
+    t[9] = (u32)(top >> 32);
+    // m = t[0] * pinv mod 2^32 ; t = (t + m*p) / 2^32
+    u32 m = t[0] * PINV32;
+    u64 acc = (u64)m * p[0] + t[0];
+    carry = (u32)(acc >> 32);
+#pragma unroll
+    for (int j = 1; j < 8; j++) {
+      acc = (u64)m * p[j] + t[j] + carry;
+      t[j - 1] = (u32)acc;
+      carry = (u32)(acc >> 32);
+    }
+    top = (u64)t[8] + carry;
+    t[7] = (u32)top;
+    t[8] = t[9] + (u32)(top >> 32);
+  }
+  u64 r[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) r[i] = (u64)t[2 * i] | ((u64)t[2 * i + 1] << 32);
+  if (t[8] || geq_p(r)) sub_p(r);
+  r64[0] = r[0]; r64[1] = r[1]; r64[2] = r[2]; r64[3] = r[3];
+}
+
+__device__ __forceinline__ void fr_to_mont(u64* r, const u64* a) {
+  const u64 r2[4] = {0x1bb8e645ae216da7ull, 0x53fe3ab1e35c59e3ull, 0x8c49833d53bb8085ull, 0x0216d0b17f4e44a5ull};
+  fr_mul(r, a, r2);
+}
+__device__ __forceinline__ void fr_from_mont(u64* r, const u64* a) {
+  const u64 one[4] = {1, 0, 0, 0};
+  fr_mul(r, a, one);
+}
+__device__ __forceinline__ void fr_neg(u64* r, const u64* a) {
+  if (fr_is_zero(a)) { r[0] = r[1] = r[2] = r[3] = 0; return; }
+  const u64 p[4] = {P0, P1, P2, P3};
+  sub256(r, p, a);
+}
+
+// a^(p-2) by square-and-multiply, Montgomery in/out, inv(0) = 0 (circom: x/0 = 0)
+__device__ __noinline__ void fr_inv(u64* r, const u64* a) {
+  const u64 e[4] = {P0 - 2, P1, P2, P3};
+  u64 acc[4] = {0xac96341c4ffffffbull, 0x36fc76959f60cd29ull, 0x666ea36f7879462eull, 0x0e0a77c19a07df2full};  // R
+  u64 base[4] = {a[0], a[1], a[2], a[3]};
+  for (int i = 0; i < 254; i++) {
+    if ((e[i >> 6] >> (i & 63)) & 1) fr_mul(acc, acc, base);
+    fr_mul(base, base, base);
+  }
+  r[0] = acc[0]; r[1] = acc[1]; r[2] = acc[2]; r[3] = acc[3];
+}
+
+// ---- plain 256-bit integer helpers (class N) ----------------------------------------------
+__device__ __forceinline__ int cmp256(const u64* a, const u64* b) {
+#pragma unroll
+  for (int i = 3; i >= 0; i--) { if (a[i] < b[i]) return -1; if (a[i] > b[i]) return 1; }
+  return 0;
+}
+__device__ __forceinline__ void shr256(u64* r, const u64* a, unsigned s) {
+  u64 t[4] = {0, 0, 0, 0};
+  if (s < 256) {
+    unsigned ws = s >> 6, bs = s & 63;
+    for (unsigned i = 0; i + ws < 4; i++) {
+      t[i] = a[i + ws] >> bs;
+      if (bs && i + ws + 1 < 4) t[i] |= a[i + ws + 1] << (64 - bs);
+    }
+  }
+  r[0] = t[0]; r[1] = t[1]; r[2] = t[2]; r[3] = t[3];
+}
+__device__ __forceinline__ void shl256(u64* r, const u64* a, unsigned s) {
+  u64 t[4] = {0, 0, 0, 0};
+  if (s < 256) {
+    unsigned ws = s >> 6, bs = s & 63;
+    for (int i = 3; i >= (int)ws; i--) {
+      t[i] = a[i - ws] << bs;
+      if (bs && i - (int)ws - 1 >= 0) t[i] |= a[i - ws - 1] >> (64 - bs);
+    }
+  }
+  r[0] = t[0]; r[1] = t[1]; r[2] = t[2]; r[3] = t[3];
+}
+__device__ __noinline__ void divmod256(const u64* a, const u64* b, u64* q, u64* m) {
+  u64 qq[4] = {0, 0, 0, 0}, rr[4] = {0, 0, 0, 0};
+  if ((b[0] | b[1] | b[2] | b[3]) != 0) {
+    for (int i = 255; i >= 0; i--) {
+      shl256(rr, rr, 1);
+      rr[0] |= (a[i >> 6] >> (i & 63)) & 1;
+      if (cmp256(rr, b) >= 0) { sub256(rr, rr, b); qq[i >> 6] |= 1ull << (i & 63); }
+    }
+  }
+  if (q) { q[0] = qq[0]; q[1] = qq[1]; q[2] = qq[2]; q[3] = qq[3]; }
+  if (m) { m[0] = rr[0]; m[1] = rr[1]; m[2] = rr[2]; m[3] = rr[3]; }
+}
+__device__ __forceinline__ void reduce_p(u64* a) {
+  while (geq_p(a)) sub_p(a);
+}
+__device__ __forceinline__ bool is_neg_rep(const u64* a) {  // a > p/2
+  const u64 h[4] = {0xa1f0fac9f8000000ull, 0x9419f4243cdcb848ull, 0xdc2822db40c0ac2eull, 0x183227397098d014ull};
+  return cmp256(a, h) > 0;
+}
+__device__ __forceinline__ int scmp256(const u64* a, const u64* b) {
+  bool na = is_neg_rep(a), nb = is_neg_rep(b);
+  if (na != nb) return na ? -1 : 1;
+  return cmp256(a, b);
+}
+
+// ---- 128 / 64 -> 64 division (Hacker's Delight divlu), hi < d required ----------------------
+__device__ __forceinline__ u64 div128by64(u64 hi, u64 lo, u64 d, u64* rem) {
+  const u64 b = 1ull << 32;
+  int s = __clzll(d);
+  d <<= s;
+  u64 vn1 = d >> 32, vn0 = d & 0xffffffffull;
+  u64 un32 = s ? ((hi << s) | (lo >> (64 - s))) : hi;
+  u64 un10 = lo << s;
+  u64 un1 = un10 >> 32, un0 = un10 & 0xffffffffull;
+  u64 q1 = un32 / vn1, rhat = un32 - q1 * vn1;
+  while (q1 >= b || q1 * vn0 > b * rhat + un1) { q1--; rhat += vn1; if (rhat >= b) break; }
+  u64 un21 = un32 * b + un1 - q1 * d;
+  u64 q0 = un21 / vn1;
+  rhat = un21 - q0 * vn1;
+  while (q0 >= b || q0 * vn0 > b * rhat + un0) { q0--; rhat += vn1; if (rhat >= b) break; }
+  if (rem) *rem = (un21 * b + un0 - q0 * d) >> s;
+  return q1 * b + q0;
+}
+
+}  // namespace pzkd

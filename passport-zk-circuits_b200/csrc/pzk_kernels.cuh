@@ -1,0 +1,520 @@
+// pzk_kernels.cuh - the three sm_100a kernels of the hot path.
+//
+//   eval_kernel   : lane-per-witness interpreter of the typed linear SSA program
+//                   (what circom's generated wasm does for the reference, one passport at a time:
+//                   /root/reference/test/automatisationTest.js:40-50).
+//   check_kernel  : A.w * B.w == C.w for every constraint row of a segment, per lane
+//                   (checkConstraints, automatisationTest.js:51 / snarkjs `wtns check`).
+//   export_kernel : slot planes -> canonical 32-byte little-endian wires (.wtns section 2).
+//
+// Data layout (HBM): slot-major, lane-minor planes so that the 32 lanes of a warp touch one
+// 256-byte run per limb:   U[slot][lane] (u64)   F[slot][limb][lane] (4 x u64, Montgomery).
+// The op / row / term streams are identical for every lane: every warp reads them with
+// warp-uniform addresses (one L1/L2 transaction per warp, served from L2 after the first CTA).
+#pragma once
+#include "fr_device.cuh"
+#include "pzk_program.h"
+
+namespace pzkd {
+
+struct EvalParams {
+  const uint4* ops;
+  u64 n_rec;
+  u64* U;
+  u64* F;
+  u64 L;        // lane stride of the planes
+  u64 n_lanes;  // active lanes in this tile
+  const u64* fpool;
+  const u32* list;
+  const u64* inputs;  // [lane][n_inputs][4]
+  u32 n_inputs;
+  u32* status;
+};
+
+#define LDU(slot) (Ul[(u64)(slot) * L])
+#define STU(slot, v) (Ul[(u64)(slot) * L] = (v))
+
+__device__ __forceinline__ void ldF(const u64* Fl, u64 L, u32 slot, u64* v) {
+  const u64* p = Fl + (u64)slot * 4 * L;
+  v[0] = p[0]; v[1] = p[L]; v[2] = p[2 * L]; v[3] = p[3 * L];
+}
+__device__ __forceinline__ void stF(u64* Fl, u64 L, u32 slot, const u64* v) {
+  u64* p = Fl + (u64)slot * 4 * L;
+  p[0] = v[0]; p[L] = v[1]; p[2 * L] = v[2]; p[3 * L] = v[3];
+}
+__device__ __forceinline__ void ldPool(const u64* pool, u32 idx, u64* v) {
+  const ulonglong2* p = reinterpret_cast<const ulonglong2*>(pool + 4 * (u64)idx);
+  ulonglong2 lo = __ldg(p), hi = __ldg(p + 1);
+  v[0] = lo.x; v[1] = lo.y; v[2] = hi.x; v[3] = hi.y;
+}
+
+// ---- long_div intrinsic: Knuth algorithm D, 64-bit digits ---------------------------------
+// a: k+m digits, b: k digits (b[k-1] != 0, k >= 2); q: m+1 digits, r: k digits.
+// Mathematically the unique quotient / remainder that
+// /root/reference/circuits/lib/circuits/bigInt/bigIntFunc.circom:190-232 (long_div) produces.
+__device__ __noinline__ u32 bigdiv_device(const u32* Lst, u64* Ul, u64 L) {
+  const unsigned k = Lst[1], m = Lst[2];
+  const u32* ia = Lst + 3;
+  const u32* ib = ia + (k + m);
+  const u32* oq = ib + k;
+  const u32* orr = oq + (m + 1);
+  u64 un[132], vn[66];
+  u32 st = 0;
+  u64 top = LDU(ib[k - 1]);
+  if (top == 0 || k < 2 || k > 64 || k + m > 128) {
+    for (unsigned i = 0; i <= m; i++) STU(oq[i], 0);
+    for (unsigned i = 0; i < k; i++) STU(orr[i], 0);
+    return PZK_LANE_BIGDIV_PRE;
+  }
+  int s = __clzll(top);
+  // normalise
+  for (int i = (int)k - 1; i > 0; i--) {
+    u64 hi = LDU(ib[i]), lo = LDU(ib[i - 1]);
+    vn[i] = s ? ((hi << s) | (lo >> (64 - s))) : hi;
+  }
+  vn[0] = LDU(ib[0]) << s;
+  const unsigned n_a = k + m;
+  un[n_a] = s ? (LDU(ia[n_a - 1]) >> (64 - s)) : 0;
+  for (int i = (int)n_a - 1; i > 0; i--) {
+    u64 hi = LDU(ia[i]), lo = LDU(ia[i - 1]);
+    un[i] = s ? ((hi << s) | (lo >> (64 - s))) : hi;
+  }
+  un[0] = LDU(ia[0]) << s;
+  for (int j = (int)m; j >= 0; j--) {
+    // estimate the quotient digit from the top two digits
+    u64 u2 = un[j + k], u1 = un[j + k - 1], u0 = un[j + k - 2];
+    u64 qhat, rhat;
+    bool rhat_over = false;
+    if (u2 >= vn[k - 1]) {  // quotient digit would overflow: clamp to B-1
+      qhat = ~0ull;
+      rhat = u1 + vn[k - 1];
+      rhat_over = rhat < u1;
+      // u2 == vn[k-1] in valid inputs (u2 > vn[k-1] cannot happen when a < B^(m+1) * b)
+      if (u2 > vn[k - 1]) st |= PZK_LANE_BIGDIV_PRE;
+    } else {
+      qhat = div128by64(u2, u1, vn[k - 1], &rhat);
+    }
+    while (!rhat_over) {
+      u64 plo = qhat * vn[k - 2], phi = __umul64hi(qhat, vn[k - 2]);
+      if (phi > rhat || (phi == rhat && plo > u0)) {
+        qhat--;
+        u64 nr = rhat + vn[k - 1];
+        rhat_over = nr < rhat;
+        rhat = nr;
+      } else break;
+    }
+    // multiply and subtract
+    u64 borrow = 0, carry = 0;
+    for (unsigned i = 0; i < k; i++) {
+      u64 plo = qhat * vn[i], phi = __umul64hi(qhat, vn[i]);
+      plo += carry; phi += (plo < carry);
+      carry = phi;
+      u64 t = un[i + j] - plo;
+      u64 b1 = un[i + j] < plo;
+      u64 t2 = t - borrow;
+      u64 b2 = t < borrow;
+      un[i + j] = t2;
+      borrow = b1 + b2;
+    }
+    {
+      u64 t = un[j + k] - carry;
+      u64 b1 = un[j + k] < carry;
+      u64 t2 = t - borrow;
+      u64 b2 = t < borrow;
+      un[j + k] = t2;
+      borrow = b1 + b2;
+    }
+    if (borrow) {  // add back
+      qhat--;
+      u64 c = 0;
+      for (unsigned i = 0; i < k; i++) {
+        u64 t = un[i + j] + vn[i];
+        u64 c1 = t < vn[i];
+        u64 t2 = t + c;
+        u64 c2 = t2 < c;
+        un[i + j] = t2;
+        c = c1 + c2;
+      }
+      un[j + k] += c;
+    }
+    STU(oq[j], qhat);
+  }
+  for (unsigned i = 0; i < k; i++) {
+    u64 v = s ? ((un[i] >> s) | (un[i + 1] << (64 - s))) : un[i];
+    STU(orr[i], v);
+  }
+  return st;
+}
+
+__global__ void __launch_bounds__(128) eval_kernel(EvalParams p) {
+  const u64 lane = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (lane >= p.n_lanes) return;
+  const u64 L = p.L;
+  u64* Ul = p.U + lane;
+  u64* Fl = p.F + lane;
+  u32 st = 0;
+  for (u64 pc = 0; pc < p.n_rec; pc++) {
+    const uint4 w = __ldg(p.ops + pc);
+    const u32 opc = w.x & 0xffu, flags = (w.x >> 8) & 0xffu, imm16 = w.x >> 16;
+    const u32 dst = w.y, a = w.z, b = w.w;
+    uint4 x = make_uint4(0, 0, 0, 0);
+    if (flags & PZK_FLAG_EXT) { pc++; x = __ldg(p.ops + pc); }
+    switch (opc) {
+      case PZK_NOP: break;
+      case PZK_U_CONST: STU(dst, ((u64)b << 32) | a); break;
+#define UBV ((flags & PZK_FLAG_B_IMM) ? (u64)b : LDU(b))
+      case PZK_U_ADD: STU(dst, LDU(a) + UBV); break;
+      case PZK_U_SUB: STU(dst, LDU(a) - UBV); break;
+      case PZK_U_MUL: STU(dst, LDU(a) * UBV); break;
+      case PZK_U_DIV: { u64 d = UBV; STU(dst, d ? LDU(a) / d : 0); break; }
+      case PZK_U_MOD: { u64 d = UBV; STU(dst, d ? LDU(a) % d : 0); break; }
+      case PZK_U_SHR: { u64 d = UBV; STU(dst, d >= 64 ? 0 : LDU(a) >> d); break; }
+      case PZK_U_SHL: { u64 d = UBV; STU(dst, d >= 64 ? 0 : LDU(a) << d); break; }
+      case PZK_U_AND: STU(dst, LDU(a) & UBV); break;
+      case PZK_U_OR: STU(dst, LDU(a) | UBV); break;
+      case PZK_U_XOR: STU(dst, LDU(a) ^ UBV); break;
+      case PZK_U_LT: STU(dst, (u64)(LDU(a) < UBV)); break;
+      case PZK_U_LE: STU(dst, (u64)(LDU(a) <= UBV)); break;
+      case PZK_U_EQ: STU(dst, (u64)(LDU(a) == UBV)); break;
+      case PZK_U_NE: STU(dst, (u64)(LDU(a) != UBV)); break;
+      case PZK_I_LT: STU(dst, (u64)((long long)LDU(a) < (long long)UBV)); break;
+      case PZK_I_LE: STU(dst, (u64)((long long)LDU(a) <= (long long)UBV)); break;
+      case PZK_U_SEL: STU(dst, LDU(a) ? LDU(b) : LDU(x.x)); break;
+      case PZK_U_LUT: case PZK_U_LUTV: {
+        u32 idx = 0;
+        if (a != PZK_OPERAND_NONE) idx |= (u32)(LDU(a) & 1);
+        if (b != PZK_OPERAND_NONE) idx |= (u32)(LDU(b) & 1) << 1;
+        if (x.x != PZK_OPERAND_NONE) idx |= (u32)(LDU(x.x) & 1) << 2;
+        if (x.y != PZK_OPERAND_NONE) idx |= (u32)(LDU(x.y) & 1) << 3;
+        if (opc == PZK_U_LUT) STU(dst, (u64)((imm16 >> idx) & 1));
+        else STU(dst, (u64)__ldg(p.list + x.z + 2 * idx) | ((u64)__ldg(p.list + x.z + 2 * idx + 1) << 32));
+        break;
+      }
+      case PZK_F_CONST: { u64 v[4]; ldPool(p.fpool, a, v); stF(Fl, L, dst, v); break; }
+      case PZK_F_ADD: case PZK_F_SUB: case PZK_F_MUL: {
+        u64 va[4], vb[4], r[4];
+        ldF(Fl, L, a, va);
+        if (flags & PZK_FLAG_B_POOL) ldPool(p.fpool, b, vb); else ldF(Fl, L, b, vb);
+        if (opc == PZK_F_ADD) fr_add(r, va, vb);
+        else if (opc == PZK_F_SUB) fr_sub(r, va, vb);
+        else fr_mul(r, va, vb);
+        stF(Fl, L, dst, r);
+        break;
+      }
+      case PZK_F_NEG: { u64 va[4], r[4]; ldF(Fl, L, a, va); fr_neg(r, va); stF(Fl, L, dst, r); break; }
+      case PZK_F_INV: { u64 va[4], r[4]; ldF(Fl, L, a, va); fr_inv(r, va); stF(Fl, L, dst, r); break; }
+      case PZK_F_FROM_U: { u64 va[4] = {LDU(a), 0, 0, 0}, r[4]; fr_to_mont(r, va); stF(Fl, L, dst, r); break; }
+      case PZK_F_FROM_I: {
+        long long v = (long long)LDU(a);
+        u64 va[4] = {v < 0 ? (u64)(-v) : (u64)v, 0, 0, 0}, r[4];
+        fr_to_mont(r, va);
+        if (v < 0) fr_neg(r, r);
+        stF(Fl, L, dst, r);
+        break;
+      }
+      case PZK_F_SEL: { u64 v[4]; ldF(Fl, L, LDU(a) ? b : x.x, v); stF(Fl, L, dst, v); break; }
+      case PZK_F_EQ: case PZK_F_NE: {
+        u64 va[4], vb[4];
+        ldF(Fl, L, a, va);
+        if (flags & PZK_FLAG_B_POOL) ldPool(p.fpool, b, vb); else ldF(Fl, L, b, vb);
+        bool eq = fr_eq(va, vb);
+        STU(dst, (u64)(opc == PZK_F_EQ ? eq : !eq));
+        break;
+      }
+      case PZK_F_CSEL: { u64 v[4]; ldPool(p.fpool, b + (u32)LDU(a), v); stF(Fl, L, dst, v); break; }
+      case PZK_N_FROM_F: { u64 va[4], r[4]; ldF(Fl, L, a, va); fr_from_mont(r, va); stF(Fl, L, dst, r); break; }
+      case PZK_F_FROM_N: { u64 va[4], r[4]; ldF(Fl, L, a, va); reduce_p(va); fr_to_mont(r, va); stF(Fl, L, dst, r); break; }
+      case PZK_N_FROM_U: { u64 v[4] = {LDU(a), 0, 0, 0}; stF(Fl, L, dst, v); break; }
+      case PZK_N_BIT: {
+        u64 limb = (b < 256) ? Fl[((u64)a * 4 + (b >> 6)) * L] : 0;
+        STU(dst, (limb >> (b & 63)) & 1);
+        break;
+      }
+      case PZK_N_LOW: STU(dst, Fl[(u64)a * 4 * L]); break;
+      case PZK_N_FITS: { u64 v[4]; ldF(Fl, L, a, v); STU(dst, (u64)((v[1] | v[2] | v[3]) == 0)); break; }
+      case PZK_N_SHR: { u64 v[4], r[4]; ldF(Fl, L, a, v); u64 d = UBV; shr256(r, v, d > 256 ? 256u : (unsigned)d); stF(Fl, L, dst, r); break; }
+      case PZK_N_SHL: {
+        u64 v[4], r[4] = {0, 0, 0, 0}; ldF(Fl, L, a, v); u64 d = UBV;
+        if (d < 254) { shl256(r, v, (unsigned)d); r[3] &= 0x3fffffffffffffffull; reduce_p(r); }
+        stF(Fl, L, dst, r); break;
+      }
+      case PZK_N_AND: case PZK_N_OR: case PZK_N_XOR: {
+        u64 va[4], vb[4], r[4];
+        ldF(Fl, L, a, va);
+        if (flags & PZK_FLAG_B_POOL) ldPool(p.fpool, b, vb); else ldF(Fl, L, b, vb);
+#pragma unroll
+        for (int i = 0; i < 4; i++) r[i] = opc == PZK_N_AND ? (va[i] & vb[i]) : opc == PZK_N_OR ? (va[i] | vb[i]) : (va[i] ^ vb[i]);
+        r[3] &= 0x3fffffffffffffffull;
+        reduce_p(r);
+        stF(Fl, L, dst, r);
+        break;
+      }
+      case PZK_N_DIV: case PZK_N_MOD: {
+        u64 va[4], vb[4], r[4];
+        ldF(Fl, L, a, va);
+        if (flags & PZK_FLAG_B_POOL) ldPool(p.fpool, b, vb); else ldF(Fl, L, b, vb);
+        if (opc == PZK_N_DIV) divmod256(va, vb, r, nullptr); else divmod256(va, vb, nullptr, r);
+        stF(Fl, L, dst, r);
+        break;
+      }
+      case PZK_N_SLT: case PZK_N_SLE: {
+        u64 va[4], vb[4];
+        ldF(Fl, L, a, va);
+        if (flags & PZK_FLAG_B_POOL) ldPool(p.fpool, b, vb); else ldF(Fl, L, b, vb);
+        int c = scmp256(va, vb);
+        STU(dst, (u64)(opc == PZK_N_SLT ? c < 0 : c <= 0));
+        break;
+      }
+      case PZK_BIGDIV: st |= bigdiv_device(p.list + a, Ul, L); break;
+      case PZK_ASSERT_NZ: if (LDU(a) == 0) st |= PZK_LANE_ASSERT; break;
+      case PZK_IN_U: {
+        const ulonglong2* ip = reinterpret_cast<const ulonglong2*>(p.inputs + ((u64)lane * p.n_inputs + a) * 4);
+        ulonglong2 lo = ip[0], hi = ip[1];
+        if ((lo.y | hi.x | hi.y) != 0 || (imm16 < 64 && (lo.x >> imm16) != 0)) st |= PZK_LANE_INPUT_RANGE;
+        STU(dst, lo.x);
+        break;
+      }
+      case PZK_IN_F: {
+        const ulonglong2* ip = reinterpret_cast<const ulonglong2*>(p.inputs + ((u64)lane * p.n_inputs + a) * 4);
+        ulonglong2 lo = ip[0], hi = ip[1];
+        u64 v[4] = {lo.x, lo.y, hi.x, hi.y}, r[4];
+        if (geq_p(v)) { st |= PZK_LANE_INPUT_RANGE; reduce_p(v); }
+        fr_to_mont(r, v);
+        stF(Fl, L, dst, r);
+        break;
+      }
+      default: st |= 0x80000000u; break;
+    }
+  }
+  if (st) p.status[lane] |= st;
+}
+
+// ------------------------------------------------------------------------------------------
+// Constraint rows.  Terms on narrow (U / I) wires with small coefficients are accumulated as
+// exact integers (3 x 64-bit two's complement); everything else goes through Montgomery form.
+// A row whose three linear combinations stay integer and small is decided without a single
+// field multiplication (that is the SHA-256 bit logic: ~3/4 of all rows).
+// ------------------------------------------------------------------------------------------
+struct CheckParams {
+  const PzkRow* rows;
+  u64 n_rows;
+  const PzkTerm* terms;
+  const PzkCoef* coefs;
+  const unsigned char* coef_kind;  // 0 general, 1 = +small, 2 = -small
+  const u64* coef_mag;             // |coef| for kinds 1, 2
+  const u64* U;
+  const u64* F;
+  u64 L;
+  u64 n_lanes;
+  u32* status;
+  unsigned long long* first_bad;  // min failing constraint index, ~0 = none
+};
+
+struct Acc192 { u64 v[3]; };
+__device__ __forceinline__ void acc_mac(Acc192& a, u64 mag, u64 v, bool neg) {
+  u64 lo = mag * v, hi = __umul64hi(mag, v);
+  if (!neg) {
+    u64 t0 = a.v[0] + lo; u64 c0 = t0 < lo;
+    u64 t1 = a.v[1] + hi; u64 c1 = t1 < hi;
+    u64 t1b = t1 + c0; u64 c1b = t1b < c0;
+    a.v[0] = t0; a.v[1] = t1b; a.v[2] += c1 + c1b;
+  } else {
+    u64 b0 = a.v[0] < lo; u64 t0 = a.v[0] - lo;
+    u64 b1 = a.v[1] < hi; u64 t1 = a.v[1] - hi;
+    u64 b1b = t1 < b0; u64 t1b = t1 - b0;
+    a.v[0] = t0; a.v[1] = t1b; a.v[2] -= b1 + b1b;
+  }
+}
+// signed 192-bit integer -> Montgomery field element
+__device__ __forceinline__ void acc_to_field(const Acc192& a, u64* r) {
+  bool neg = (long long)a.v[2] < 0;
+  u64 m[4] = {a.v[0], a.v[1], a.v[2], 0};
+  if (neg) {
+    m[0] = ~m[0]; m[1] = ~m[1]; m[2] = ~m[2];
+    m[0] += 1; if (m[0] == 0) { m[1] += 1; if (m[1] == 0) m[2] += 1; }
+  }
+  fr_to_mont(r, m);
+  if (neg) fr_neg(r, r);
+}
+
+struct LinVal { Acc192 i; u64 f[4]; bool has_f; };
+
+__device__ __forceinline__ void lin_eval(const CheckParams& p, const PzkTerm* t, u32 n, const u64* Ul, const u64* Fl,
+                                         LinVal& out) {
+  out.i.v[0] = out.i.v[1] = out.i.v[2] = 0;
+  out.f[0] = out.f[1] = out.f[2] = out.f[3] = 0;
+  out.has_f = false;
+  const u64 L = p.L;
+  for (u32 k = 0; k < n; k++) {
+    const uint2 tw = __ldg(reinterpret_cast<const uint2*>(t + k));
+    const u32 ref = tw.x, ci = tw.y;
+    const u32 kind = __ldg(p.coef_kind + ci);
+    if (ref == PZK_REF_ONE) {
+      if (kind) acc_mac(out.i, __ldg(p.coef_mag + ci), 1, kind == 2);
+      else { u64 c[4]; ldPool(reinterpret_cast<const u64*>(p.coefs), ci * 3 + 1, c); fr_add(out.f, out.f, c); out.has_f = true; }
+      continue;
+    }
+    const u32 cls = PZK_REF_CLS(ref), slot = PZK_REF_SLOT(ref);
+    if (cls < 2) {
+      u64 v = Ul[(u64)slot * L];
+      bool vneg = (cls == 1) && ((long long)v < 0);
+      u64 vm = vneg ? (u64)(-(long long)v) : v;
+      if (kind) acc_mac(out.i, __ldg(p.coef_mag + ci), vm, (kind == 2) != vneg);
+      else {
+        u64 c[4], w[4] = {vm, 0, 0, 0}, r[4];
+        ldPool(reinterpret_cast<const u64*>(p.coefs), ci * 3 + 2, c);  // c * R^2
+        fr_mul(r, c, w);
+        if (vneg) fr_sub(out.f, out.f, r); else fr_add(out.f, out.f, r);
+        out.has_f = true;
+      }
+    } else {
+      u64 w[4];
+      ldF(Fl, L, slot, w);
+      if (kind && __ldg(p.coef_mag + ci) == 1) {
+        if (kind == 1) fr_add(out.f, out.f, w); else fr_sub(out.f, out.f, w);
+      } else {
+        u64 c[4], r[4];
+        ldPool(reinterpret_cast<const u64*>(p.coefs), ci * 3 + 1, c);  // c * R
+        fr_mul(r, c, w);
+        fr_add(out.f, out.f, r);
+      }
+      out.has_f = true;
+    }
+  }
+}
+__device__ __forceinline__ bool acc_is_zero(const Acc192& a) { return (a.v[0] | a.v[1] | a.v[2]) == 0; }
+__device__ __forceinline__ bool acc_fits_i64(const Acc192& a) {
+  u64 ext = (u64)((long long)a.v[0] >> 63);
+  return a.v[1] == ext && a.v[2] == ext;
+}
+__device__ __forceinline__ void lin_to_field(const LinVal& l, u64* r) {
+  if (acc_is_zero(l.i)) { r[0] = l.f[0]; r[1] = l.f[1]; r[2] = l.f[2]; r[3] = l.f[3]; return; }
+  u64 t[4];
+  acc_to_field(l.i, t);
+  fr_add(r, t, l.f);
+}
+
+__global__ void __launch_bounds__(128) check_kernel(CheckParams p) {
+  const u64 lane = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (lane >= p.n_lanes) return;
+  const u64* Ul = p.U + lane;
+  const u64* Fl = p.F + lane;
+  unsigned long long bad = ~0ull;
+  for (u64 r = 0; r < p.n_rows; r++) {
+    const uint4 rw = __ldg(reinterpret_cast<const uint4*>(p.rows + r));
+    const u32 term_off = rw.x, na = rw.y & 0xffffu, nb = rw.y >> 16, nc = rw.z & 0xffffu, index = rw.w;
+    const PzkTerm* t = p.terms + term_off;
+    LinVal A, B, C;
+    lin_eval(p, t + na + nb, nc, Ul, Fl, C);
+    bool ok;
+    if (na == 0 || nb == 0) {
+      if (!C.has_f) ok = acc_is_zero(C.i);
+      else { u64 c[4]; lin_to_field(C, c); ok = fr_is_zero(c); }
+    } else {
+      lin_eval(p, t, na, Ul, Fl, A);
+      lin_eval(p, t + na, nb, Ul, Fl, B);
+      if (!A.has_f && !B.has_f && !C.has_f && acc_fits_i64(A.i) && acc_fits_i64(B.i)) {
+        long long a = (long long)A.i.v[0], b = (long long)B.i.v[0];
+        bool neg = (a < 0) != (b < 0);
+        u64 am = a < 0 ? (u64)(-a) : (u64)a, bm = b < 0 ? (u64)(-b) : (u64)b;
+        Acc192 prod; prod.v[0] = prod.v[1] = prod.v[2] = 0;
+        acc_mac(prod, am, bm, neg);
+        ok = prod.v[0] == C.i.v[0] && prod.v[1] == C.i.v[1] && prod.v[2] == C.i.v[2];
+      } else {
+        u64 a[4], b[4], c[4], ab[4];
+        lin_to_field(A, a); lin_to_field(B, b); lin_to_field(C, c);
+        fr_mul(ab, a, b);
+        ok = fr_eq(ab, c);
+      }
+    }
+    if (!ok && (unsigned long long)index < bad) bad = index;
+  }
+  if (bad != ~0ull) {
+    p.status[lane] |= PZK_LANE_CONSTRAINT;
+    if (bad < p.first_bad[lane]) p.first_bad[lane] = bad;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Export: entries (wire <- slot) of one segment for a list of lanes -> canonical 32-byte wires.
+// grid.x covers lanes (fast, coalesced plane reads), grid.y strides over entries.
+// ------------------------------------------------------------------------------------------
+struct ExportParams {
+  const PzkExport* entries;
+  u64 n_entries;
+  const u64* U;
+  const u64* F;
+  u64 L;
+  const u64* lanes;  // tile-local lane per output row, or nullptr = identity
+  u64 lane_base;     // output row offset (identity mode: output row = lane_base + lane)
+  u64 n_rows;        // number of output rows handled
+  u64* out;          // [row][out_wires][4]
+  u64 out_wires;
+  u32 wire_off;      // out index = wire - wire_off
+};
+
+__global__ void __launch_bounds__(128) export_kernel(ExportParams p) {
+  const u64 row = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= p.n_rows) return;
+  const u64 lane = p.lanes ? p.lanes[row] : row;
+  const u64 L = p.L;
+  for (u64 e = blockIdx.y; e < p.n_entries; e += gridDim.y) {
+    const uint2 ew = __ldg(reinterpret_cast<const uint2*>(p.entries + e));
+    const u32 wire = ew.x, ref = ew.y;
+    u64 w[4] = {0, 0, 0, 0};
+    if (ref == PZK_REF_ONE) w[0] = 1;
+    else if (ref != PZK_REF_ZERO) {
+      const u32 cls = PZK_REF_CLS(ref), slot = PZK_REF_SLOT(ref);
+      if (cls == 2) { u64 m[4]; ldF(p.F + lane, L, slot, m); fr_from_mont(w, m); }
+      else {
+        u64 v = p.U[(u64)slot * L + lane];
+        if (cls == 1 && (long long)v < 0) { const u64 pp[4] = {P0, P1, P2, P3}; u64 m[4] = {(u64)(-(long long)v), 0, 0, 0}; sub256(w, pp, m); }
+        else w[0] = v;
+      }
+    }
+    u64* dst = p.out + ((p.lane_base + row) * p.out_wires + (wire - p.wire_off)) * 4;
+    reinterpret_cast<ulonglong2*>(dst)[0] = make_ulonglong2(w[0], w[1]);
+    reinterpret_cast<ulonglong2*>(dst)[1] = make_ulonglong2(w[2], w[3]);
+  }
+}
+
+// one lane, threads over the entries of a segment (full-witness export of selected lanes)
+__global__ void __launch_bounds__(128) export_rows_kernel(ExportParams p) {
+  const u64 lane = p.lanes[0];
+  const u64 L = p.L;
+  for (u64 e = (u64)blockIdx.x * blockDim.x + threadIdx.x; e < p.n_entries; e += (u64)gridDim.x * blockDim.x) {
+    const uint2 ew = __ldg(reinterpret_cast<const uint2*>(p.entries + e));
+    const u32 wire = ew.x, ref = ew.y;
+    u64 w[4] = {0, 0, 0, 0};
+    if (ref == PZK_REF_ONE) w[0] = 1;
+    else if (ref != PZK_REF_ZERO) {
+      const u32 cls = PZK_REF_CLS(ref), slot = PZK_REF_SLOT(ref);
+      if (cls == 2) { u64 m[4]; ldF(p.F + lane, L, slot, m); fr_from_mont(w, m); }
+      else {
+        u64 v = p.U[(u64)slot * L + lane];
+        if (cls == 1 && (long long)v < 0) { const u64 pp[4] = {P0, P1, P2, P3}; u64 m[4] = {(u64)(-(long long)v), 0, 0, 0}; sub256(w, pp, m); }
+        else w[0] = v;
+      }
+    }
+    u64* dst = p.out + (p.lane_base * p.out_wires + (wire - p.wire_off)) * 4;
+    reinterpret_cast<ulonglong2*>(dst)[0] = make_ulonglong2(w[0], w[1]);
+    reinterpret_cast<ulonglong2*>(dst)[1] = make_ulonglong2(w[2], w[3]);
+  }
+}
+
+// canonical AoS witnesses [lane][n_wires][4] -> Montgomery SoA F plane (generic wtns check)
+__global__ void __launch_bounds__(128) load_witness_kernel(const u64* wit, u64 n_wires, u64 n_lanes, u64 L, u64* F,
+                                                           u32* status) {
+  const u64 lane = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (lane >= n_lanes) return;
+  for (u64 wv = blockIdx.y; wv < n_wires; wv += gridDim.y) {
+    const ulonglong2* ip = reinterpret_cast<const ulonglong2*>(wit + (lane * n_wires + wv) * 4);
+    ulonglong2 lo = ip[0], hi = ip[1];
+    u64 v[4] = {lo.x, lo.y, hi.x, hi.y}, r[4];
+    if (geq_p(v)) { atomicOr(status + lane, PZK_LANE_INPUT_RANGE); reduce_p(v); }
+    fr_to_mont(r, v);
+    stF(F + lane, L, (u32)wv, r);
+  }
+}
+
+}  // namespace pzkd

@@ -1,0 +1,433 @@
+"""Host-side mirror of the reference's operator surface, over the C ABI (include/pzk.h).
+
+Reference interface mirrored (all of it lives in un-vendored dependencies there):
+  * circom's generated `witness_calculator.js`: `calculateWitness(input, sanityCheck)`,
+    `calculateWTNSBin(input, sanityCheck)` - call sites
+    /root/reference/test/automatisationTest.js:40-50 and
+    /root/reference/circuits/scripts/gen-witness.sh:25;
+  * `circom_tester`'s `wasm_tester(path)` object: `.calculateWitness`, `.checkConstraints`
+    (/root/reference/test/automatisationTest.js:37-51);
+  * `snarkjs wtns check`.
+Same names, same argument meaning, same error strings.  Python stands in for the Node.js
+host layer because this image has no node (INTEGRATION.md shows the N-API binding); all
+compute happens in libpzk.so on the GPU - there is no CPU fallback here.
+"""
+from __future__ import annotations
+
+import ctypes
+import json
+import lzma
+import os
+import subprocess
+from dataclasses import dataclass
+
+import numpy as np
+
+P = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+LIB_PATH = os.path.join(_HERE, "lib", "libpzk.so")
+ARTIFACT_DIR = os.path.join(_ROOT, "artifacts")
+
+PZK_ENODEVICE = -3
+STATUS_ASSERT, STATUS_CONSTRAINT, STATUS_INPUT_RANGE, STATUS_BIGDIV = 1, 2, 4, 8
+
+
+class PzkError(RuntimeError):
+    pass
+
+
+# ----------------------------------------------------------------------------- build
+def build_library(force=False, verbose=False):
+    """nvcc build of libpzk.so for sm_100a (in-tree, so it travels to the GPU box)."""
+    csrc = os.path.join(_HERE, "csrc")
+    srcs = [os.path.join(csrc, "pzk_api.cu"), os.path.join(csrc, "compiler.cpp")]
+    deps = srcs + [os.path.join(csrc, f) for f in os.listdir(csrc)] + \
+        [os.path.join(_ROOT, "include", f) for f in os.listdir(os.path.join(_ROOT, "include"))]
+    if not force and os.path.exists(LIB_PATH) and all(
+            os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
+        return LIB_PATH
+    os.makedirs(os.path.dirname(LIB_PATH), exist_ok=True)
+    cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+           "-Xcompiler", "-fPIC", "-shared", "-I" + os.path.join(_ROOT, "include"), "-I" + csrc,
+           "-o", LIB_PATH] + srcs
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise PzkError("nvcc failed:\n" + r.stderr[-4000:])
+    if verbose:
+        print(r.stderr)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    """The CUDA library.  Fails loudly when it is missing - nothing falls back to the CPU."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PzkError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+    L = ctypes.CDLL(LIB_PATH)
+    vp, cp, u32, u64, i64 = ctypes.c_void_p, ctypes.c_char_p, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_int64
+    L.pzk_version.restype = cp
+    L.pzk_device_count.restype = ctypes.c_int
+    L.pzk_compile.restype = ctypes.c_int
+    L.pzk_compile.argtypes = [cp, cp, ctypes.POINTER(cp), ctypes.POINTER(ctypes.c_int), ctypes.c_int, u32, cp,
+                              ctypes.c_size_t]
+    L.pzk_circuit_open.restype = ctypes.c_int
+    L.pzk_circuit_open.argtypes = [cp, ctypes.c_int, ctypes.POINTER(vp)]
+    L.pzk_circuit_close.argtypes = [vp]
+    L.pzk_last_error.restype = cp
+    L.pzk_last_error.argtypes = [vp]
+    for f in ("pzk_witness_size", "pzk_input_size", "pzk_public_size", "pzk_constraint_count"):
+        getattr(L, f).restype = u32
+        getattr(L, f).argtypes = [vp]
+    L.pzk_circuit_meta_json.restype = cp
+    L.pzk_circuit_meta_json.argtypes = [vp]
+    L.pzk_circuit_stats.argtypes = [vp] + [ctypes.POINTER(u64)] * 6
+    L.pzk_wtns_size.restype = u64
+    L.pzk_wtns_size.argtypes = [vp]
+    L.pzk_calculate_witness.argtypes = [vp, vp, vp, ctypes.POINTER(u32), ctypes.POINTER(i64)]
+    L.pzk_calculate_wtns_bin.argtypes = [vp, vp, vp, ctypes.POINTER(u32), ctypes.POINTER(i64)]
+    L.pzk_witness_batch.argtypes = [vp, vp, u64, vp, vp, vp, vp, u64, vp]
+    L.pzk_batch_upload.argtypes = [vp, vp, u64]
+    L.pzk_batch_run.argtypes = [vp, ctypes.c_int]
+    L.pzk_batch_download.argtypes = [vp, vp, vp, vp]
+    L.pzk_profile_get.argtypes = [vp, ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(u64)]
+    L.pzk_profile_reset.argtypes = [vp]
+    L.pzk_profile_enable.argtypes = [vp, ctypes.c_int]
+    L.pzk_set_tile_lanes.argtypes = [vp, u64]
+    L.pzk_get_tile_lanes.restype = u64
+    L.pzk_get_tile_lanes.argtypes = [vp]
+    L.pzk_wtns_check.argtypes = [cp, vp, u64, ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(i64), cp,
+                                 ctypes.c_size_t]
+    L.pzk_r1cs_check_batch.argtypes = [cp, vp, u64, ctypes.c_int, vp, vp, ctypes.POINTER(ctypes.c_double), cp,
+                                       ctypes.c_size_t]
+    _lib = L
+    return L
+
+
+# ----------------------------------------------------------------------------- compile
+# declared widths of the reference's input pipeline (process_passport.js writes bits and
+# 64-bit chunks, /root/reference/test/process_passport.js:659-672, 590-626)
+REGISTER_IDENTITY_BITS = {"dg1": 1, "dg15": 1, "encapsulatedContent": 1, "signedAttributes": 1,
+                          "pubkey": 64, "signature": 64}
+
+
+def compile_circuit(main_path, out_prefix, input_bits=None, segment_ops=0):
+    """circom -> program (.pzkp) + .r1cs + .sym; the role of
+    `circom <file> --r1cs --wasm --sym` (/root/reference/circuits/scripts/compile-circuit.sh:34)."""
+    L = lib()
+    input_bits = input_bits or {}
+    names = (ctypes.c_char_p * max(1, len(input_bits)))(*[k.encode() for k in input_bits])
+    widths = (ctypes.c_int * max(1, len(input_bits)))(*list(input_bits.values()))
+    err = ctypes.create_string_buffer(4096)
+    os.makedirs(os.path.dirname(os.path.abspath(out_prefix)), exist_ok=True)
+    rc = L.pzk_compile(os.fsencode(main_path), os.fsencode(out_prefix), names, widths, len(input_bits),
+                       segment_ops, err, len(err))
+    if rc != 0:
+        raise PzkError("compile failed: " + err.value.decode(errors="replace"))
+    return out_prefix + ".pzkp"
+
+
+def pack_artifact(program_path):
+    """xz-compress a program for transport (artifacts/ travels with the repo snapshot)."""
+    with open(program_path, "rb") as f, lzma.open(program_path + ".xz", "wb", preset=1) as g:
+        while True:
+            chunk = f.read(1 << 24)
+            if not chunk:
+                break
+            g.write(chunk)
+    return program_path + ".xz"
+
+
+def artifact(name):
+    """Path of a prebuilt program in artifacts/ (unpacked on first use)."""
+    path = os.path.join(ARTIFACT_DIR, name + ".pzkp")
+    if os.path.exists(path):
+        return path
+    if os.path.exists(path + ".xz"):
+        tmp = path + ".tmp%d" % os.getpid()
+        with lzma.open(path + ".xz", "rb") as g, open(tmp, "wb") as f:
+            while True:
+                chunk = g.read(1 << 24)
+                if not chunk:
+                    break
+                f.write(chunk)
+        os.replace(tmp, path)
+        return path
+    raise PzkError(f"artifact {name} is missing from {ARTIFACT_DIR}: run __graft_entry__.build() where "
+                   "/root/reference is mounted")
+
+
+# ----------------------------------------------------------------------------- inputs
+def _flatten(v, out):
+    if isinstance(v, (list, tuple, np.ndarray)):
+        for x in v:
+            _flatten(x, out)
+    elif isinstance(v, str):
+        out.append(int(v, 16) if v[:2] in ("0x", "0X") else int(v))
+    else:
+        out.append(int(v))
+
+
+def flatten_input(meta, inp: dict) -> bytes:
+    """Object keyed by main input signal name -> n_inputs x 32-byte LE field elements, with the
+    error behaviour of witness_calculator.js."""
+    by_name = {d["name"]: d for d in meta["inputs"]}
+    total = sum(d["size"] for d in meta["inputs"])
+    buf = bytearray(32 * total)
+    n_set = 0
+    for name, val in inp.items():
+        d = by_name.get(name)
+        if d is None:
+            raise PzkError(f"Signal not found: {name}")
+        flat = []
+        _flatten(val, flat)
+        if len(flat) < d["size"]:
+            raise PzkError(f"Not enough values for input signal {name}")
+        if len(flat) > d["size"]:
+            raise PzkError(f"Too many values for input signal {name}")
+        off = d["offset"]
+        for i, x in enumerate(flat):
+            buf[32 * (off + i):32 * (off + i + 1)] = (x % P).to_bytes(32, "little")
+        n_set += len(flat)
+    if n_set != total:
+        raise PzkError(f"Not all inputs have been set. Only {n_set} out of {total}")
+    return bytes(buf)
+
+
+def pack_inputs_fast(meta, inputs: list) -> np.ndarray:
+    """Batch of input objects -> uint64 array [B, n_inputs, 4] (values < 2^64 take the fast
+    path; the general path goes through flatten_input)."""
+    total = sum(d["size"] for d in meta["inputs"])
+    B = len(inputs)
+    out = np.zeros((B, total, 4), dtype=np.uint64)
+    for b, inp in enumerate(inputs):
+        if set(inp.keys()) != {d["name"] for d in meta["inputs"]}:
+            out[b] = np.frombuffer(flatten_input(meta, inp), dtype=np.uint64).reshape(total, 4)
+            continue
+        for d in meta["inputs"]:
+            flat = []
+            _flatten(inp[d["name"]], flat)
+            if len(flat) != d["size"]:
+                raise PzkError(f"{'Not enough' if len(flat) < d['size'] else 'Too many'} values for input signal "
+                               f"{d['name']}")
+            off = d["offset"]
+            if d["bits"] and d["bits"] <= 63:
+                out[b, off:off + d["size"], 0] = np.array(flat, dtype=np.uint64)
+            else:
+                for i, x in enumerate(flat):
+                    x %= P
+                    for limb in range(4):
+                        out[b, off + i, limb] = (x >> (64 * limb)) & 0xFFFFFFFFFFFFFFFF
+    return out
+
+
+@dataclass
+class BatchResult:
+    status: np.ndarray      # uint32 [B]
+    first_bad: np.ndarray   # int64 [B]; -1 when every constraint holds
+    public: np.ndarray      # uint64 [B, n_public, 4] canonical little-endian limbs
+    witnesses: np.ndarray | None = None  # uint64 [n_export, n_wires, 4]
+
+    def public_ints(self, lane):
+        return [int.from_bytes(self.public[lane, i].tobytes(), "little") for i in range(self.public.shape[1])]
+
+
+class WitnessCalculator:
+    """`new WitnessCalculator(wasm)` of circom's witness_calculator.js, with a program instead of
+    the wasm.  One instance is reusable across calls; it is not thread-safe."""
+
+    def __init__(self, program_path, device=0):
+        self._L = lib()
+        self._h = ctypes.c_void_p()
+        rc = self._L.pzk_circuit_open(os.fsencode(program_path), device, ctypes.byref(self._h))
+        if rc != 0:
+            msg = self._L.pzk_last_error(self._h).decode() if self._h else ""
+            if self._h:
+                self._L.pzk_circuit_close(self._h)
+                self._h = ctypes.c_void_p()
+            if rc == PZK_ENODEVICE:
+                raise PzkError("no CUDA device: the witness generator has no CPU fallback")
+            raise PzkError(f"pzk_circuit_open failed ({rc}): {msg}")
+        self.meta = json.loads(self._L.pzk_circuit_meta_json(self._h).decode())
+        self.n_wires = self._L.pzk_witness_size(self._h)
+        self.n_inputs = self._L.pzk_input_size(self._h)
+        self.n_public = self._L.pzk_public_size(self._h)
+        self.n_constraints = self._L.pzk_constraint_count(self._h)
+
+    def close(self):
+        if self._h:
+            self._L.pzk_circuit_close(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise PzkError(f"pzk error {rc}: {self._L.pzk_last_error(self._h).decode()}")
+
+    def stats(self):
+        v = [ctypes.c_uint64() for _ in range(6)]
+        self._L.pzk_circuit_stats(self._h, *[ctypes.byref(x) for x in v])
+        keys = ("op_records", "f_mul", "f_inv", "rows", "terms", "bytes_per_lane")
+        return {k: x.value for k, x in zip(keys, v)}
+
+    # ---- reference operator surface
+    def calculateWitness(self, inp, sanityCheck=True):
+        """Returns the witness as a list of ints (w[0] == 1).  Raises "Assert Failed." when an
+        assert / constraint does not hold, as the wasm does (automatisationTest.js:53-56)."""
+        flat = flatten_input(self.meta, inp)
+        wit = np.zeros((self.n_wires, 4), dtype=np.uint64)
+        st, fb = ctypes.c_uint32(), ctypes.c_int64()
+        self._check(self._L.pzk_calculate_witness(self._h, flat, wit.ctypes.data, ctypes.byref(st), ctypes.byref(fb)))
+        self._raise_status(st.value, fb.value, sanityCheck)
+        raw = wit.tobytes()
+        return [int.from_bytes(raw[32 * i:32 * i + 32], "little") for i in range(self.n_wires)]
+
+    def calculateWTNSBin(self, inp, sanityCheck=True) -> bytes:
+        flat = flatten_input(self.meta, inp)
+        out = ctypes.create_string_buffer(self._L.pzk_wtns_size(self._h))
+        st, fb = ctypes.c_uint32(), ctypes.c_int64()
+        self._check(self._L.pzk_calculate_wtns_bin(self._h, flat, out, ctypes.byref(st), ctypes.byref(fb)))
+        self._raise_status(st.value, fb.value, sanityCheck)
+        return out.raw
+
+    @staticmethod
+    def _raise_status(st, fb, sanity):
+        if st & STATUS_INPUT_RANGE:
+            raise PzkError("Input out of its declared range (status 4)")
+        if st & STATUS_BIGDIV:
+            raise PzkError("Assert Failed. long division precondition violated (status 8)")
+        if st & (STATUS_ASSERT | STATUS_CONSTRAINT):
+            raise PzkError(f"Assert Failed. (status {st}, first failing constraint {fb})")
+
+    # ---- batched product path
+    def calculateWitnessBatch(self, inputs, export_lanes=()) -> BatchResult:
+        """inputs: uint64 array [B, n_inputs, 4] (pack_inputs_fast) or list of input objects."""
+        if not isinstance(inputs, np.ndarray):
+            inputs = pack_inputs_fast(self.meta, list(inputs))
+        inputs = np.ascontiguousarray(inputs, dtype=np.uint64)
+        B = inputs.shape[0]
+        status = np.zeros(B, dtype=np.uint32)
+        first_bad = np.zeros(B, dtype=np.int64)
+        public = np.zeros((B, self.n_public, 4), dtype=np.uint64)
+        lanes = np.ascontiguousarray(np.array(list(export_lanes), dtype=np.uint64))
+        wit = np.zeros((len(lanes), self.n_wires, 4), dtype=np.uint64) if len(lanes) else None
+        self._check(self._L.pzk_witness_batch(self._h, inputs.ctypes.data, B, status.ctypes.data, first_bad.ctypes.data,
+                                              public.ctypes.data, lanes.ctypes.data if len(lanes) else None,
+                                              len(lanes), wit.ctypes.data if wit is not None else None))
+        first_bad[(status & STATUS_CONSTRAINT) == 0] = -1
+        return BatchResult(status, first_bad, public, wit)
+
+    # ---- device-resident measurement path
+    def upload(self, inputs: np.ndarray):
+        inputs = np.ascontiguousarray(inputs, dtype=np.uint64)
+        self._check(self._L.pzk_batch_upload(self._h, inputs.ctypes.data, inputs.shape[0]))
+        self._B = inputs.shape[0]
+
+    def run(self, check_rows=True):
+        self._check(self._L.pzk_batch_run(self._h, 1 if check_rows else 0))
+
+    def download(self) -> BatchResult:
+        B = self._B
+        status = np.zeros(B, dtype=np.uint32)
+        first_bad = np.zeros(B, dtype=np.int64)
+        public = np.zeros((B, self.n_public, 4), dtype=np.uint64)
+        self._check(self._L.pzk_batch_download(self._h, status.ctypes.data, first_bad.ctypes.data, public.ctypes.data))
+        first_bad[(status & STATUS_CONSTRAINT) == 0] = -1
+        return BatchResult(status, first_bad, public)
+
+    def profile(self, enable=None, reset=False):
+        if enable is not None:
+            self._L.pzk_profile_enable(self._h, 1 if enable else 0)
+        if reset:
+            self._L.pzk_profile_reset(self._h)
+        out = {}
+        for i, k in enumerate(("eval", "check", "export", "run")):
+            ms, n = ctypes.c_double(), ctypes.c_uint64()
+            self._L.pzk_profile_get(self._h, i, ctypes.byref(ms), ctypes.byref(n))
+            out[k] = (ms.value, n.value)
+        return out
+
+    def set_tile_lanes(self, lanes):
+        self._check(self._L.pzk_set_tile_lanes(self._h, lanes))
+
+    def tile_lanes(self):
+        return self._L.pzk_get_tile_lanes(self._h)
+
+
+def wtns_check(r1cs_path, wtns: bytes, device=0):
+    """`snarkjs wtns check <r1cs> <wtns>`: (True, -1) or (False, first failing constraint)."""
+    L = lib()
+    verdict, fb = ctypes.c_int(), ctypes.c_int64()
+    err = ctypes.create_string_buffer(1024)
+    rc = L.pzk_wtns_check(os.fsencode(r1cs_path), wtns, len(wtns), device, ctypes.byref(verdict), ctypes.byref(fb),
+                          err, len(err))
+    if rc != 0:
+        raise PzkError(err.value.decode(errors="replace") or f"pzk error {rc}")
+    return bool(verdict.value), fb.value
+
+
+def r1cs_check_batch(r1cs_path, witnesses: np.ndarray, device=0):
+    """witnesses: uint64 [B, n_wires, 4] canonical -> (verdicts bool[B], first_bad int64[B], kernel ms)."""
+    L = lib()
+    witnesses = np.ascontiguousarray(witnesses, dtype=np.uint64)
+    B = witnesses.shape[0]
+    verdicts = np.zeros(B, dtype=np.int32)
+    fb = np.zeros(B, dtype=np.int64)
+    ms = ctypes.c_double()
+    err = ctypes.create_string_buffer(1024)
+    rc = L.pzk_r1cs_check_batch(os.fsencode(r1cs_path), witnesses.ctypes.data, B, device, verdicts.ctypes.data,
+                                fb.ctypes.data, ctypes.byref(ms), err, len(err))
+    if rc != 0:
+        raise PzkError(err.value.decode(errors="replace") or f"pzk error {rc}")
+    return verdicts.astype(bool), fb, ms.value
+
+
+class wasm_tester:
+    """Shape of circom_tester's object (/root/reference/test/automatisationTest.js:37-51):
+    `circuit = wasm_tester(path); w = circuit.calculateWitness(input); circuit.checkConstraints(w)`.
+    `path` is a prebuilt program prefix (".pzkp/.r1cs/.sym") or a .circom file to compile."""
+
+    def __init__(self, path, input_bits=None, device=0, workdir=None):
+        if path.endswith(".circom"):
+            workdir = workdir or os.path.join(ARTIFACT_DIR, "_tester")
+            prefix = os.path.join(workdir, os.path.splitext(os.path.basename(path))[0])
+            compile_circuit(path, prefix, input_bits)
+        else:
+            prefix = path[:-5] if path.endswith(".pzkp") else path
+        self.prefix = prefix
+        self.calc = WitnessCalculator(prefix + ".pzkp", device)
+        self.device = device
+        self._sym = None
+
+    def calculateWitness(self, inp, sanityCheck=True):
+        return self.calc.calculateWitness(inp, sanityCheck)
+
+    def checkConstraints(self, witness):
+        w = np.zeros((1, len(witness), 4), dtype=np.uint64)
+        raw = b"".join(int(x).to_bytes(32, "little") for x in witness)
+        w[0] = np.frombuffer(raw, dtype=np.uint64).reshape(-1, 4)
+        ok, fb, _ = r1cs_check_batch(self.prefix + ".r1cs", w, self.device)
+        if not ok[0]:
+            raise PzkError(f"Constraint doesn't match (constraint {int(fb[0])})")
+        return True
+
+    def symbols(self):
+        """name -> witness index, from the .sym file (map by name)."""
+        if self._sym is None:
+            self._sym = {}
+            with open(self.prefix + ".sym") as f:
+                for line in f:
+                    lab, wi, ci, name = line.rstrip("\n").split(",", 3)
+                    self._sym[name] = int(wi)
+        return self._sym

@@ -1,0 +1,24 @@
+import sys, time, json
+sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/oracle')
+import numpy as np
+from passport_zk_circuits_b200 import witness as W
+from passport_zk_circuits_b200.passports import C3, PassportFactory
+name = sys.argv[1]; B = int(sys.argv[2])
+calc = W.WitnessCalculator(W.artifact(name), 0)
+print(name, 'wires', calc.n_wires, 'constraints', calc.n_constraints, calc.stats())
+if name == 'c3':
+    fac = PassportFactory(C3, seed=1, n_sig_keys=2, n_aa_keys=2)
+    uniq = W.pack_inputs_fast(calc.meta, [fac.make(i).inputs for i in range(64)])
+    inp = np.tile(uniq, ((B + 63) // 64, 1, 1))[:B]
+else:
+    sys.path.insert(0, '/root/repo/tests')
+    from util import random_inputs
+    inp = random_inputs(calc.meta, B, 1, field_bits=248)
+calc.upload(inp)
+calc.profile(enable=True, reset=True)
+for it in range(3):
+    t = time.time(); calc.run(True); dt = time.time() - t
+    pr = calc.profile(); calc.profile(reset=True)
+    print('run', it, 'lanes', B, 'tile', calc.tile_lanes(), 'sec', round(dt, 4), 'witness/s', round(B / dt, 1), {k: (round(v[0], 1), v[1]) for k, v in pr.items()})
+res = calc.download()
+print('status ok', int((res.status == 0).sum()), 'of', B)

@@ -1,0 +1,90 @@
+"""CPU parity: the Python oracle (direct interpreter of the circom sources) against the compiled
+program evaluated by the plain-C oracle evaluator, signal by signal, mapped BY NAME through the
+.sym file.  This validates the product compiler without a GPU."""
+import os
+
+import numpy as np
+import pytest
+
+import circom_oracle as co
+import formats
+import ref as oracle_ref
+from conftest import REFERENCE, has_reference
+from util import ROOT, input_dict, ints_to_u64, random_inputs, u64_to_ints
+
+OWN = {"t_mix": "tests/circuits/mix.circom", "t_bigdiv": "tests/circuits/bigdiv.circom"}
+REF_SMALL = ["poseidon2", "sha256_1", "smt80", "babyjub"]
+
+
+def compare(prog_prefix, circom_main, inputs_u64, expect_ok=True):
+    prog = oracle_ref.RefProgram(prog_prefix + ".pzkp")
+    sym = formats.read_sym(prog_prefix + ".sym")
+    circ = co.Circuit(circom_main)
+    names = circ.signal_names()
+    assert len(names) + 1 == prog.n_wires
+    for row in inputs_u64:
+        st, fb, wit = prog.witness(row)
+        w = circ.calculate_witness(input_dict(prog.meta, row), check=expect_ok)
+        got = u64_to_ints(wit)
+        assert got[0] == 1
+        bad = [(n, got[sym[n]], v) for n, v in zip(names, w) if got[sym[n]] != v]
+        assert not bad, bad[:5]
+        if expect_ok:
+            assert st == 0 and fb == -1
+    return prog
+
+
+def mix_inputs(meta, B, seed):
+    inp = random_inputs(meta, B, seed)
+    return inp
+
+
+def test_own_mix(artifacts_dir):
+    prog = oracle_ref.RefProgram(os.path.join(artifacts_dir, "t_mix.pzkp"))
+    inp = mix_inputs(prog.meta, 6, 11)
+    # make x == y in one row to hit the zero branch of the inversion
+    d = {x["name"]: x for x in prog.meta["inputs"]}
+    inp[0, d["x"]["offset"]] = inp[0, d["y"]["offset"]]
+    compare(os.path.join(artifacts_dir, "t_mix"), os.path.join(ROOT, OWN["t_mix"]), inp)
+
+
+def test_own_bigdiv_intrinsic_equals_function(artifacts_dir):
+    prog = oracle_ref.RefProgram(os.path.join(artifacts_dir, "t_bigdiv.pzkp"))
+    inp = random_inputs(prog.meta, 8, 5)
+    d = {x["name"]: x for x in prog.meta["inputs"]}
+    inp[:, d["b"]["offset"] + 1, 0] |= np.uint64(1)        # top limb of the divisor non-zero
+    inp[1, d["b"]["offset"] + 1, 0] = np.uint64(1)          # tiny top limb: many correction steps
+    inp[2, d["a"]["offset"]:d["a"]["offset"] + 3, 0] = np.uint64(0xFFFFFFFFFFFFFFFF)
+    inp[2, d["b"]["offset"] + 1, 0] = np.uint64(0xFFFFFFFFFFFFFFFF)
+    # the quotient must fit m+1 = 2 limbs: a[2] < b[1] is not required, q < 2^128 always holds here
+    compare(os.path.join(artifacts_dir, "t_bigdiv"), os.path.join(ROOT, OWN["t_bigdiv"]), inp)
+
+
+@pytest.mark.skipif(not has_reference(), reason="/root/reference is not mounted here")
+@pytest.mark.parametrize("name", REF_SMALL)
+def test_reference_small(artifacts_dir, name):
+    prefix = os.path.join(artifacts_dir, name)
+    main = os.path.join(artifacts_dir, "_mains", name + ".circom")
+    prog = oracle_ref.RefProgram(prefix + ".pzkp")
+    if name == "smt80":
+        from passport_zk_circuits_b200.poseidon import poseidon
+        rows = []
+        for key in (12345, 2**200 + 17):
+            vals = {"root": [poseidon([key, key, 1])], "leaf": [key], "key": [key], "siblings": [0] * 80}
+            flat = []
+            for d in prog.meta["inputs"]:
+                flat += vals[d["name"]]
+            rows.append(ints_to_u64(flat))
+        compare(prefix, main, np.stack(rows))
+        # a wrong root still yields a witness (isVerified = 0) and all constraints hold
+        bad = rows[0].copy()
+        d = {x["name"]: x for x in prog.meta["inputs"]}
+        bad[d["root"]["offset"], 0] ^= np.uint64(1)
+        p = compare(prefix, main, np.stack([bad]))
+        st, fb, wit = p.witness(bad)
+        assert u64_to_ints(wit)[1] == 0
+    elif name == "babyjub":
+        inp = random_inputs(prog.meta, 2, 3, field_bits=248)
+        compare(prefix, main, inp)
+    else:
+        compare(prefix, main, random_inputs(prog.meta, 2, 9))

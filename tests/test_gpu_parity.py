@@ -1,0 +1,104 @@
+"""GPU parity (run on the B200 box): the CUDA path, called through the C ABI, against the oracle
+(oracle/ssa_ref.c evaluating the same program; that evaluator is itself pinned to the Python
+interpreter of the circom sources by tests/test_cpu_compiler_vs_oracle.py and tests/golden/).
+Bar: bit-exact - every wire of every exported lane, every status word, every public signal."""
+import os
+
+import numpy as np
+import pytest
+
+import ref as oracle_ref
+from util import ROOT, ints_to_u64, random_inputs, u64_to_ints
+
+pytestmark = pytest.mark.gpu
+
+from passport_zk_circuits_b200 import witness as W  # noqa: E402
+
+
+def run_and_compare(name, inp, export=None, tile=None):
+    prog = W.artifact(name)
+    calc = W.WitnessCalculator(prog, device=0)
+    if tile:
+        calc.set_tile_lanes(tile)
+    B = inp.shape[0]
+    export = list(range(B)) if export is None else list(export)
+    res = calc.calculateWitnessBatch(inp, export_lanes=export)
+    ref = oracle_ref.RefProgram(prog)
+    exp_pos = {lane: j for j, lane in enumerate(export)}
+    for b in range(B):
+        st, fb, wit = ref.witness(inp[b], want_witness=True)
+        assert int(res.status[b]) == st, (name, b, int(res.status[b]), st)
+        assert int(res.first_bad[b]) == fb, (name, b, int(res.first_bad[b]), fb)
+        npub = calc.n_public
+        assert np.array_equal(res.public[b], wit[1:1 + npub]), (name, b, "public signals")
+        if b in exp_pos:
+            got = res.witnesses[exp_pos[b]]
+            if not np.array_equal(got, wit):
+                idx = np.nonzero((got != wit).any(axis=1))[0]
+                raise AssertionError(f"{name} lane {b}: {len(idx)} wires differ, first {idx[:5]}")
+    calc.close()
+    return res
+
+
+def test_mix_ragged_batch_and_tiles():
+    prog = oracle_ref.RefProgram(W.artifact("t_mix"))
+    inp = random_inputs(prog.meta, 301, 21)
+    d = {x["name"]: x for x in prog.meta["inputs"]}
+    inp[5, d["x"]["offset"]] = inp[5, d["y"]["offset"]]
+    run_and_compare("t_mix", inp)                 # one tile, 301 lanes (not a multiple of 128)
+    run_and_compare("t_mix", inp, tile=128)       # three tiles, last one ragged
+    run_and_compare("t_mix", inp[:1])             # batch of one
+
+
+def test_mix_out_of_range_input_is_flagged():
+    prog = oracle_ref.RefProgram(W.artifact("t_mix"))
+    inp = random_inputs(prog.meta, 40, 4)
+    d = {x["name"]: x for x in prog.meta["inputs"]}
+    inp[7, d["bits"]["offset"] + 2, 0] = 2       # a "bit" input that is not a bit
+    inp[9, d["u"]["offset"], 1] = 1              # a 16-bit input with a high limb set
+    res = run_and_compare("t_mix", inp)
+    assert res.status[7] & W.STATUS_INPUT_RANGE and res.status[9] & W.STATUS_INPUT_RANGE
+    assert (np.delete(res.status, [7, 9]) == 0).all()
+
+
+def test_bigdiv_intrinsic():
+    prog = oracle_ref.RefProgram(W.artifact("t_bigdiv"))
+    inp = random_inputs(prog.meta, 257, 8)
+    d = {x["name"]: x for x in prog.meta["inputs"]}
+    inp[:, d["b"]["offset"] + 1, 0] |= np.uint64(1)
+    inp[1, d["b"]["offset"] + 1, 0] = np.uint64(1)
+    inp[2, :, 0] = np.uint64(0xFFFFFFFFFFFFFFFF)
+    inp[3, d["b"]["offset"] + 1, 0] = np.uint64(0)   # precondition violated -> status 8
+    res = run_and_compare("t_bigdiv", inp)
+    assert res.status[3] & W.STATUS_BIGDIV
+
+
+@pytest.mark.parametrize("name,B", [("poseidon2", 200), ("sha256_1", 130), ("babyjub", 66)])
+def test_reference_small(name, B):
+    prog = oracle_ref.RefProgram(W.artifact(name))
+    inp = random_inputs(prog.meta, B, 33, field_bits=248)
+    run_and_compare(name, inp, export=range(0, B, 7))
+
+
+def smt_inputs(meta, keys, break_lane=None):
+    from passport_zk_circuits_b200.poseidon import poseidon
+    rows = []
+    for i, key in enumerate(keys):
+        vals = {"root": [poseidon([key, key, 1])], "leaf": [key], "key": [key], "siblings": [0] * 80}
+        if i == break_lane:
+            vals["root"] = [vals["root"][0] ^ 1]
+        flat = []
+        for d in meta["inputs"]:
+            flat += vals[d["name"]]
+        rows.append(ints_to_u64(flat))
+    return np.stack(rows)
+
+
+def test_smt80_config1():
+    prog = oracle_ref.RefProgram(W.artifact("smt80"))
+    keys = [12345 + 977 * i + (i << 190) for i in range(150)]
+    inp = smt_inputs(prog.meta, keys, break_lane=11)
+    res = run_and_compare("smt80", inp, export=[0, 11, 149])
+    verified = res.public[:, 0, 0]
+    assert verified[11] == 0 and (np.delete(verified, 11) == 1).all()
+    assert (res.status == 0).all()
