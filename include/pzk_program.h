@@ -30,7 +30,7 @@ extern "C" {
 #endif
 
 #define PZK_MAGIC 0x314b5a50u /* "PZK1" */
-#define PZK_VERSION 3u
+#define PZK_VERSION 4u
 
 /* ---- opcodes ------------------------------------------------------------ */
 enum PzkOpcode {
@@ -85,6 +85,15 @@ enum PzkOpcode {
   PZK_N_SLE = 52,
   PZK_N_SHL = 53, /* dst(N) = ((a << b(U)) & (2^254-1)) mod p               */
   PZK_N_FITS = 54, /* dst(U) = (a < 2^64)                                   */
+  /* constraint rows, fused into the op stream right after the op that defines their last wire.
+   * header: imm16 = na, a = nb | nc << 16, b = number of 16-byte term records that follow,
+   * dst = constraint index (.r1cs order).  Terms (A then B then C) are packed two per record:
+   * {ref, coef}.  CHECK_INT: every wire is narrow and the compiler proved |A|,|B| < 2^63,
+   * |C| < 2^126 - exact integer check; coef is an inline int32, or (PZK_TERM_COEF_LIST set in
+   * ref) an offset into the list pool holding an int64.  CHECK_F: Montgomery arithmetic, coef is
+   * an index into the coefficient pool. */
+  PZK_CHECK_INT = 56,
+  PZK_CHECK_F = 57,
   /* macro / control */
   PZK_BIGDIV = 60,    /* long_div intrinsic, operands in the list pool       */
   PZK_ASSERT_NZ = 61, /* lane status |= ASSERT when a(U) == 0                */
@@ -132,9 +141,11 @@ typedef struct PzkTerm {
 } PzkTerm;
 
 #define PZK_REF_CLS(r) ((r) >> 30)
-#define PZK_REF_SLOT(r) ((r) & 0x3fffffffu)
+#define PZK_TERM_COEF_LIST 0x20000000u
+#define PZK_REF_SLOT(r) ((r) & 0x1fffffffu)
 #define PZK_REF_ZERO 0xFFFFFFFFu
 #define PZK_REF_ONE 0xFFFFFFFEu
+#define PZK_REF_ONE_LIST 0xFFFFFFFDu /* constant term whose int64 coefficient is in the list pool */
 #define PZK_OPERAND_NONE 0xFFFFFFFFu
 
 /* row kinds */

@@ -351,6 +351,53 @@ uint32_t pzk_ref_witness(const PzkRefProgram* p, const uint8_t* inputs, uint8_t*
           for (unsigned i = 0; i < k; i++) U[L[3 + k + m + k + m + 1 + i]] = r[i];
           break;
         }
+        case PZK_CHECK_INT: case PZK_CHECK_F: {
+          /* a constraint row fused into the op stream: A.w * B.w == C.w, checked here with
+           * the generic field arithmetic for both kinds (the integer fast path is a device-side
+           * optimisation whose result must agree) */
+          unsigned na = o->imm16, nb = o->a & 0xffffu, nc = o->a >> 16, nrec = o->b;
+          if (check_rows) {
+            const uint32_t* tw = (const uint32_t*)(o + 1);
+            uint64_t acc[3][4];
+            unsigned lens[3] = {na, nb, nc}, k = 0;
+            for (int part = 0; part < 3; part++) {
+              memset(acc[part], 0, 32);
+              for (unsigned i = 0; i < lens[part]; i++, k++) {
+                uint32_t ref = tw[2 * k], cw = tw[2 * k + 1];
+                uint64_t cm[4], v[4], t[4];
+                if (o->opc == PZK_CHECK_INT) {
+                  int64_t c;
+                  if (ref == PZK_REF_ONE_LIST || (ref < PZK_REF_ONE_LIST && (ref & PZK_TERM_COEF_LIST)))
+                    c = (int64_t)((uint64_t)p->list[cw] | ((uint64_t)p->list[cw + 1] << 32));
+                  else c = (int32_t)cw;
+                  uint64_t m[4] = {c < 0 ? (uint64_t)(-c) : (uint64_t)c, 0, 0, 0}, z[4] = {0, 0, 0, 0};
+                  to_mont(cm, m);
+                  if (c < 0) fsub(cm, z, cm);
+                } else memcpy(cm, p->coefs[cw].mont, 32);
+                if (ref >= PZK_REF_ONE_LIST) { fadd(acc[part], acc[part], cm); continue; }
+                uint32_t cls = PZK_REF_CLS(ref), slot = PZK_REF_SLOT(ref);
+                if (cls == 2) memcpy(v, F + 4 * (uint64_t)slot, 32);
+                else {
+                  uint64_t raw = U[slot];
+                  int neg = cls == 1 && (int64_t)raw < 0;
+                  uint64_t m[4] = {neg ? (uint64_t)(-(int64_t)raw) : raw, 0, 0, 0}, z[4] = {0, 0, 0, 0};
+                  to_mont(v, m);
+                  if (neg) fsub(v, z, v);
+                }
+                fmul(t, cm, v);
+                fadd(acc[part], acc[part], t);
+              }
+            }
+            uint64_t ab[4];
+            fmul(ab, acc[0], acc[1]);
+            if (memcmp(ab, acc[2], 32) != 0) {
+              status |= PZK_LANE_CONSTRAINT;
+              if (bad < 0 || (int64_t)o->dst < bad) bad = o->dst;
+            }
+          }
+          pc += nrec;
+          break;
+        }
         case PZK_ASSERT_NZ: if (U[o->a] == 0) status |= PZK_LANE_ASSERT; break;
         case PZK_IN_U: {
           const uint64_t* v = (const uint64_t*)(inputs + 32 * (uint64_t)o->a);

@@ -1,6 +1,6 @@
 // circom_front.hpp - lexer + recursive-descent parser for the circom 2.1.x subset used by
 // passport-zk-circuits.  Produces a plain pointer AST.
-// Product code: independent of oracle/circom_oracle.py (the CPU oracle).
+// Product code: shares nothing with the CPU oracle under oracle/.
 #pragma once
 #include <cstdio>
 #include <cstdlib>

@@ -177,6 +177,7 @@ struct Compiler::Impl {
   std::vector<PzkInput> out_inputs;
   std::vector<uint32_t> out_list;
   uint32_t n_u_slots = 0, n_f_slots = 0;
+  uint64_t n_int_rows = 0, n_field_rows = 0, eval_bytes = 0, check_bytes = 0;
   uint32_t n_pub_out = 0, n_pub_in = 0, n_prv_in = 0;
   std::string meta_json;
 
@@ -1622,43 +1623,57 @@ void Compiler::Impl::backend() {
     keep[i] = 1;
     for_operands(o, [&](uint32_t v) { used[v] = 1; });
   }
-  // ---- segments over kept ops
+  // ---- rows: each one is checked right after the op that defines the last of its wires
+  size_t nrows = rows.size();
+  size_t first_kept = 0;
+  while (first_kept < nops && !keep[first_kept]) first_kept++;
+  std::vector<uint32_t> row_trigger(nrows, (uint32_t)first_kept), row_recs(nrows, 1);
+  for (size_t r = 0; r < nrows; r++) {
+    uint32_t nt = rows[r].na + rows[r].nb + rows[r].nc, live_terms = 0;
+    for (uint32_t t = 0; t < nt; t++) {
+      uint32_t sig = terms[rows[r].off + t].first;
+      if (sig == 0xFFFFFFFFu) { live_terms++; continue; }
+      uint32_t v = sig_val[sig];
+      if (!v) continue;
+      live_terms++;
+      if (v_def[v] > row_trigger[r]) row_trigger[r] = v_def[v];
+    }
+    row_recs[r] = 1 + (live_terms + 1) / 2;
+  }
+  std::vector<uint32_t> row_order(nrows);
+  for (size_t r = 0; r < nrows; r++) row_order[r] = (uint32_t)r;
+  std::stable_sort(row_order.begin(), row_order.end(), [&](uint32_t a, uint32_t b) { return row_trigger[a] < row_trigger[b]; });
+  // ---- segments over kept ops (+ their rows)
   std::vector<uint32_t> def_seg(nv, 0), last_seg(nv, 0), op_seg(nops, 0);
   {
     uint64_t rec = 0; uint32_t seg = 0;
+    size_t rp = 0;
     for (size_t i = 0; i < nops; i++) {
       if (!keep[i]) continue;
-      uint32_t need = (ops[i].flags & PZK_FLAG_EXT) ? 2 : 1;
-      if (rec + need > opt.seg_ops) { seg++; rec = 0; }
+      uint64_t need = (ops[i].flags & PZK_FLAG_EXT) ? 2 : 1;
+      size_t q = rp;
+      while (q < nrows && row_trigger[row_order[q]] == i) { need += row_recs[row_order[q]]; q++; }
+      if (rec && rec + need > opt.seg_ops) { seg++; rec = 0; }
       rec += need;
       op_seg[i] = seg;
+      rp = q;
       for_defs(ops[i], [&](uint32_t d) { def_seg[d] = seg; last_seg[d] = seg; });
     }
     segs.assign(seg + 1, PzkSegment());
   }
   for (size_t i = 0; i < nops; i++) {
     if (!keep[i]) continue;
-    uint32_t s = op_seg[i];
-    for_operands(ops[i], [&](uint32_t v) { if (last_seg[v] < s) last_seg[v] = s; });
+    uint32_t sg = op_seg[i];
+    for_operands(ops[i], [&](uint32_t v) { if (last_seg[v] < sg) last_seg[v] = sg; });
   }
-  // ---- rows: segment = latest definition among their wires
-  size_t nrows = rows.size();
-  std::vector<uint32_t> row_seg(nrows, 0);
   for (size_t r = 0; r < nrows; r++) {
-    uint32_t s = 0;
+    uint32_t sg = op_seg[row_trigger[r]];
     uint32_t nt = rows[r].na + rows[r].nb + rows[r].nc;
     for (uint32_t t = 0; t < nt; t++) {
       uint32_t sig = terms[rows[r].off + t].first;
       if (sig == 0xFFFFFFFFu) continue;
       uint32_t v = sig_val[sig];
-      if (v && def_seg[v] > s) s = def_seg[v];
-    }
-    row_seg[r] = s;
-    for (uint32_t t = 0; t < nt; t++) {
-      uint32_t sig = terms[rows[r].off + t].first;
-      if (sig == 0xFFFFFFFFu) continue;
-      uint32_t v = sig_val[sig];
-      if (v && last_seg[v] < s) last_seg[v] = s;
+      if (v && last_seg[v] < sg) last_seg[v] = sg;
     }
   }
   // ---- slot allocation (free at segment boundaries)
@@ -1687,22 +1702,101 @@ void Compiler::Impl::backend() {
     }
   }
   n_u_slots = next_u; n_f_slots = next_f;
-  // ---- emit op records
+  // ---- emit op records, each followed by the constraint rows it completes
   auto slot_of = [&](uint32_t v) -> uint32_t {
     if (v == PZK_OPERAND_NONE) return v;
     if (v_slot[v] == 0xFFFFFFFFu) throw CompileError("internal: operand without a slot");
     return v_slot[v];
   };
+  auto ref_of_sig = [&](uint32_t sig) -> uint32_t {
+    if (sig == 0xFFFFFFFFu) return PZK_REF_ONE;
+    uint32_t v = sig_val[sig];
+    if (!v) return PZK_REF_ZERO;
+    uint32_t cls = v_cls[v] == CLS_U ? 0u : (v_cls[v] == CLS_I ? 1u : 2u);
+    return (cls << 30) | v_slot[v];
+  };
+  std::unordered_map<uint64_t, uint32_t> icoef_off;  // int64 coefficient -> list offset
+  auto emit_row = [&](uint32_t r) {
+    uint32_t lens[3] = {rows[r].na, rows[r].nb, rows[r].nc};
+    // classification: exact integer check possible?
+    bool is_int = true;
+    unsigned __int128 bound[3] = {0, 0, 0};
+    const unsigned __int128 SAT = (unsigned __int128)1 << 127;
+    {
+      uint64_t off = rows[r].off;
+      for (int part = 0; part < 3 && is_int; part++)
+        for (uint32_t t = 0; t < lens[part]; t++, off++) {
+          uint32_t sig = terms[off].first;
+          int64_t cv;
+          if (!small_signed(coefs[terms[off].second], cv)) { is_int = false; break; }
+          unsigned __int128 mag = (unsigned __int128)(cv < 0 ? -cv : cv);
+          unsigned __int128 vmax = 1;
+          if (sig != 0xFFFFFFFFu) {
+            uint32_t v = sig_val[sig];
+            if (!v) continue;
+            if (v_cls[v] != CLS_U && v_cls[v] != CLS_I) { is_int = false; break; }
+            i128 a = v_lo[v] < 0 ? -v_lo[v] : v_lo[v], b = v_hi[v] < 0 ? -v_hi[v] : v_hi[v];
+            vmax = (unsigned __int128)(a > b ? a : b);
+          }
+          unsigned __int128 add = mag * vmax;  // < 2^62 * 2^64
+          bound[part] = bound[part] + add;
+          if (bound[part] >= SAT) { is_int = false; break; }
+        }
+    }
+    const unsigned __int128 LIM63 = (unsigned __int128)1 << 63, LIM126 = (unsigned __int128)1 << 126;
+    if (is_int && (bound[0] >= LIM63 || bound[1] >= LIM63 || bound[2] >= LIM126)) is_int = false;
+    std::vector<PzkTerm> ts;
+    uint16_t cnt[3] = {0, 0, 0};
+    uint64_t off = rows[r].off;
+    for (int part = 0; part < 3; part++)
+      for (uint32_t t = 0; t < lens[part]; t++, off++) {
+        uint32_t ref = ref_of_sig(terms[off].first);
+        if (ref == PZK_REF_ZERO) continue;
+        PzkTerm pt; pt.ref = ref;
+        if (is_int) {
+          int64_t cv; small_signed(coefs[terms[off].second], cv);
+          if (cv >= INT32_MIN && cv <= INT32_MAX) pt.coef = (uint32_t)(int32_t)cv;
+          else {
+            auto it = icoef_off.find((uint64_t)cv);
+            uint32_t lo;
+            if (it == icoef_off.end()) {
+              lo = (uint32_t)out_list.size();
+              out_list.push_back((uint32_t)(uint64_t)cv); out_list.push_back((uint32_t)((uint64_t)cv >> 32));
+              icoef_off[(uint64_t)cv] = lo;
+            } else lo = it->second;
+            pt.coef = lo;
+            if (ref != PZK_REF_ONE) pt.ref |= PZK_TERM_COEF_LIST; else pt.ref = PZK_REF_ONE_LIST;
+          }
+        } else pt.coef = terms[off].second;
+        // a constant-one term with a list coefficient is flagged through the coefficient word
+        ts.push_back(pt); cnt[part]++;
+      }
+    PzkOp h; h.opc = is_int ? PZK_CHECK_INT : PZK_CHECK_F; h.flags = 0; h.imm16 = cnt[0];
+    h.dst = r; h.a = (uint32_t)cnt[1] | ((uint32_t)cnt[2] << 16); h.b = (uint32_t)((ts.size() + 1) / 2);
+    out_ops.push_back(h);
+    for (size_t k = 0; k < ts.size(); k += 2) {
+      uint32_t wds[4] = {ts[k].ref, ts[k].coef, PZK_REF_ZERO, 0};
+      if (k + 1 < ts.size()) { wds[2] = ts[k + 1].ref; wds[3] = ts[k + 1].coef; }
+      PzkOp raw; memcpy(&raw, wds, 16);
+      out_ops.push_back(raw);
+    }
+    if (is_int) n_int_rows++; else n_field_rows++;
+    for (auto& t : ts) if (t.ref != PZK_REF_ONE && t.ref != PZK_REF_ONE_LIST) check_bytes += (PZK_REF_CLS(t.ref) == 2) ? 32 : 8;
+  };
   out_list = list_pool;
   out_ops.clear();
   {
     uint32_t cur = 0xFFFFFFFFu;
+    size_t rp = 0;
     for (size_t i = 0; i < nops; i++) {
       if (!keep[i]) continue;
       const OpRec& o = ops[i];
       uint32_t s = op_seg[i];
       if (s != cur) { cur = s; segs[s].op_off = out_ops.size(); }
       PzkOp r; r.opc = o.opc; r.flags = o.flags; r.imm16 = o.imm16; r.dst = 0; r.a = o.a; r.b = o.b;
+      auto cls_bytes = [&](uint32_t v) -> uint64_t { return (v == PZK_OPERAND_NONE) ? 0 : ((v_cls[v] == CLS_U || v_cls[v] == CLS_I) ? 8 : 32); };
+      for_operands(o, [&](uint32_t v) { eval_bytes += cls_bytes(v); });
+      for_defs(o, [&](uint32_t v) { eval_bytes += cls_bytes(v); });
       switch (o.opc) {
         case PZK_NOP: break;
         case PZK_U_CONST: case PZK_F_CONST: case PZK_IN_U: case PZK_IN_F: r.dst = slot_of(o.dst); break;
@@ -1732,40 +1826,12 @@ void Compiler::Impl::backend() {
         PzkOp raw; memcpy(&raw, &x, sizeof raw);
         out_ops.push_back(raw);
       }
+      while (rp < nrows && row_trigger[row_order[rp]] == i) { emit_row(row_order[rp]); rp++; }
       segs[s].n_ops = out_ops.size() - segs[s].op_off;
     }
+    if (rp != nrows) throw CompileError("internal: constraint rows left unplaced");
   }
-  // ---- rows per segment (slot addressed)
-  auto ref_of_sig = [&](uint32_t sig) -> uint32_t {
-    if (sig == 0xFFFFFFFFu) return PZK_REF_ONE;
-    uint32_t v = sig_val[sig];
-    if (!v) return PZK_REF_ZERO;
-    uint32_t cls = v_cls[v] == CLS_U ? 0u : (v_cls[v] == CLS_I ? 1u : 2u);
-    return (cls << 30) | v_slot[v];
-  };
-  {
-    std::vector<std::vector<uint32_t>> by_seg(segs.size());
-    for (size_t r = 0; r < nrows; r++) by_seg[row_seg[r]].push_back((uint32_t)r);
-    for (size_t s = 0; s < segs.size(); s++) {
-      segs[s].row_off = out_rows.size();
-      for (uint32_t r : by_seg[s]) {
-        PzkRow row; row.term_off = (uint32_t)out_terms.size(); row.kind = PZK_ROW_FIELD; row.index = r;
-        uint16_t cnt[3] = {0, 0, 0};
-        uint32_t lens[3] = {rows[r].na, rows[r].nb, rows[r].nc};
-        uint64_t off = rows[r].off;
-        for (int part = 0; part < 3; part++)
-          for (uint32_t t = 0; t < lens[part]; t++, off++) {
-            uint32_t ref = ref_of_sig(terms[off].first);
-            if (ref == PZK_REF_ZERO) continue;  // unassigned wire: value 0
-            PzkTerm pt; pt.ref = ref; pt.coef = terms[off].second;
-            out_terms.push_back(pt); cnt[part]++;
-          }
-        row.na = cnt[0]; row.nb = cnt[1]; row.nc = cnt[2];
-        out_rows.push_back(row);
-      }
-      segs[s].n_rows = out_rows.size() - segs[s].row_off;
-    }
-  }
+  for (size_t s2 = 0; s2 < segs.size(); s2++) { segs[s2].row_off = 0; segs[s2].n_rows = 0; }
   // ---- exports per segment
   {
     std::vector<std::vector<PzkExport>> by_seg(segs.size());
@@ -1825,6 +1891,8 @@ void Compiler::Impl::build_meta() {
        ",\"f_inv\":" + std::to_string(stats->f_inv) + ",\"f_other\":" + std::to_string(stats->f_other) +
        ",\"bigdiv\":" + std::to_string(stats->bigdiv) + ",\"lut\":" + std::to_string(stats->lut) +
        ",\"op_records\":" + std::to_string(out_ops.size()) + ",\"segments\":" + std::to_string(segs.size()) +
+       ",\"int_rows\":" + std::to_string(n_int_rows) + ",\"field_rows\":" + std::to_string(n_field_rows) +
+       ",\"eval_bytes\":" + std::to_string(eval_bytes) + ",\"check_bytes\":" + std::to_string(check_bytes) +
        ",\"u_slots\":" + std::to_string(n_u_slots) + ",\"f_slots\":" + std::to_string(n_f_slots) + "}";
   s += "}";
   meta_json = s;

@@ -336,18 +336,11 @@ static int run_batch(pzk_circuit* c, int check_rows, const uint64_t* export_lane
         p.ops = c->d_ops + sg.op_off; p.n_rec = sg.n_ops; p.U = c->d_U; p.F = c->d_F; p.L = L; p.n_lanes = n;
         p.fpool = c->d_fpool; p.list = c->d_list; p.inputs = c->d_inputs + base * c->h.n_inputs * 4;
         p.n_inputs = c->h.n_inputs; p.status = c->d_status + base;
+        p.check_rows = check_rows; p.sc.coefs = c->d_coefs; p.sc.coef_kind = c->d_coef_kind; p.sc.coef_mag = c->d_coef_mag;
+        p.first_bad = c->d_first_bad + base;
         prof_begin(c, 0, ea, eb);
         eval_kernel<<<grid, 128, 0, c->stream>>>(p);
         prof_end(c, 0, ea, eb);
-      }
-      if (check_rows && sg.n_rows) {
-        CheckParams p;
-        p.rows = c->d_rows + sg.row_off; p.n_rows = sg.n_rows; p.terms = c->d_terms; p.coefs = c->d_coefs;
-        p.coef_kind = c->d_coef_kind; p.coef_mag = c->d_coef_mag; p.U = c->d_U; p.F = c->d_F; p.L = L; p.n_lanes = n;
-        p.status = c->d_status + base; p.first_bad = c->d_first_bad + base;
-        prof_begin(c, 1, ea, eb);
-        check_kernel<<<grid, 128, 0, c->stream>>>(p);
-        prof_end(c, 1, ea, eb);
       }
       if (!c->seg[s].pub.empty()) {
         ExportParams p;

