@@ -101,6 +101,8 @@ int pzk_batch_download(pzk_circuit* c, uint32_t* status, int64_t* first_bad, uin
  * which = 0 eval, 1 row check, 2 export/public, 3 whole run.                           */
 int pzk_profile_get(pzk_circuit* c, int which, double* ms, uint64_t* launches);
 void pzk_profile_reset(pzk_circuit* c);
+/* accumulated evaluator time per program segment (ms); returns the number of segments */
+int pzk_profile_segments(pzk_circuit* c, double* ms, uint32_t n);
 void pzk_profile_enable(pzk_circuit* c, int on);
 /* lanes processed per tile (0 = choose from free device memory)                        */
 int pzk_set_tile_lanes(pzk_circuit* c, uint64_t lanes);

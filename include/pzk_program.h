@@ -30,7 +30,7 @@ extern "C" {
 #endif
 
 #define PZK_MAGIC 0x314b5a50u /* "PZK1" */
-#define PZK_VERSION 4u
+#define PZK_VERSION 7u
 
 /* ---- opcodes ------------------------------------------------------------ */
 enum PzkOpcode {
@@ -94,6 +94,8 @@ enum PzkOpcode {
    * an index into the coefficient pool. */
   PZK_CHECK_INT = 56,
   PZK_CHECK_F = 57,
+  PZK_CHECK_I64 = 58, /* like CHECK_INT with |A|,|B|,|A*B|,|C| < 2^63 and inline int32 coefficients only:
+                         plain wrapping 64-bit arithmetic decides the row */
   /* macro / control */
   PZK_BIGDIV = 60,    /* long_div intrinsic, operands in the list pool       */
   PZK_ASSERT_NZ = 61, /* lane status |= ASSERT when a(U) == 0                */
@@ -142,7 +144,22 @@ typedef struct PzkTerm {
 
 #define PZK_REF_CLS(r) ((r) >> 30)
 #define PZK_TERM_COEF_LIST 0x20000000u
-#define PZK_REF_SLOT(r) ((r) & 0x1fffffffu)
+#define PZK_TERM_CELL 0x10000000u /* the wire is read from the shared-memory operand cache */
+#define PZK_TERM_BIT 0x08000000u  /* CHECK_F: the wire is a proven bit - its term is a conditional add */
+#define PZK_REF_SLOT(r) ((r) & 0x07ffffffu)
+
+/* Operand cache.  Every value is always stored to its global slot; in addition the compiler keeps
+ * the values with the nearest next uses in a per-lane shared-memory cache of header.n_cells 8-byte
+ * cells (an F value takes 4 consecutive cells).  Because the whole future of the straight-line
+ * program is known, the allocation is Belady-optimal per segment and eviction is free.
+ *   operand word : bit 31 set -> cell index in bits 0..15, else a global slot
+ *   dst word     : bits 0..21 global slot, bits 22..30 cell + 1 (0 = not cached), bit 31 = the
+ *                  global store is only needed when witnesses are exported (every later read
+ *                  of the value hits the cache)                                                 */
+#define PZK_OPERAND_CELL 0x80000000u
+#define PZK_DST_SLOT(d) ((d) & 0x3fffffu)
+#define PZK_DST_CELL(d) (((d) >> 22) & 0x1ffu)
+#define PZK_DST_OPTIONAL 0x80000000u
 #define PZK_REF_ZERO 0xFFFFFFFFu
 #define PZK_REF_ONE 0xFFFFFFFEu
 #define PZK_REF_ONE_LIST 0xFFFFFFFDu /* constant term whose int64 coefficient is in the list pool */
@@ -192,7 +209,7 @@ typedef struct PzkHeader {
   uint64_t n_op_records;
   uint64_t n_rows, n_terms, n_exports;
   uint64_t stat_u_ops, stat_f_mul, stat_f_inv, stat_f_other, stat_bigdiv;
-  uint64_t reserved[4];
+  uint64_t reserved[4]; /* [0] = length of the JSON metadata, [1] = operand-cache cells per lane */
 } PzkHeader;
 
 /* coefficient pool entry */

@@ -259,6 +259,8 @@ uint32_t pzk_ref_witness(const PzkRefProgram* p, const uint8_t* inputs, uint8_t*
                          int check_rows) {
   uint64_t* U = (uint64_t*)calloc((size_t)p->h.n_u_slots + 1, 8);
   uint64_t* F = (uint64_t*)calloc((size_t)p->h.n_f_slots + 1, 32);
+  uint64_t cells[1100]; /* the shared-memory operand cache of the device, one lane */
+  memset(cells, 0, sizeof cells);
   uint32_t status = 0;
   int64_t bad = -1;
   if (witness) { memset(witness, 0, (size_t)p->h.n_wires * 32); witness[0] = 1; }
@@ -268,77 +270,84 @@ uint32_t pzk_ref_witness(const PzkRefProgram* p, const uint8_t* inputs, uint8_t*
       const PzkOp* o = &p->ops[pc];
       const PzkOpExt* x = (const PzkOpExt*)(o + 1);
       if (o->flags & PZK_FLAG_EXT) pc++;
-#define UB ((o->flags & PZK_FLAG_B_IMM) ? (uint64_t)o->b : U[o->b])
-#define FA (F + 4 * (uint64_t)o->a)
-#define FB ((o->flags & PZK_FLAG_B_POOL) ? (p->fpool + 4 * (uint64_t)o->b) : (F + 4 * (uint64_t)o->b))
-#define FD (F + 4 * (uint64_t)o->dst)
+/* operand words: bit 31 -> cache cell, else global slot; dst words: slot | (cell + 1) << 22 */
+#define RDU(x) (((x) & PZK_OPERAND_CELL) ? cells[(x) & 0xffffu] : U[x])
+#define RDF(x) (((x) & PZK_OPERAND_CELL) ? (cells + ((x) & 0xffffu)) : (F + 4 * (uint64_t)(x)))
+#define WRU(d, v) do { uint64_t v__ = (v); U[PZK_DST_SLOT(d)] = v__; if (PZK_DST_CELL(d)) cells[PZK_DST_CELL(d) - 1] = v__; } while (0)
+#define WRF(d, src) do { uint64_t t__[4]; memcpy(t__, (src), 32); memcpy(F + 4 * (uint64_t)PZK_DST_SLOT(d), t__, 32); \
+                         if (PZK_DST_CELL(d)) memcpy(cells + PZK_DST_CELL(d) - 1, t__, 32); } while (0)
+#define UA RDU(o->a)
+#define UB ((o->flags & PZK_FLAG_B_IMM) ? (uint64_t)o->b : RDU(o->b))
+#define FA RDF(o->a)
+#define FB ((o->flags & PZK_FLAG_B_POOL) ? (p->fpool + 4 * (uint64_t)o->b) : RDF(o->b))
       switch (o->opc) {
         case PZK_NOP: break;
-        case PZK_U_CONST: U[o->dst] = ((uint64_t)o->b << 32) | o->a; break;
-        case PZK_U_ADD: U[o->dst] = U[o->a] + UB; break;
-        case PZK_U_SUB: U[o->dst] = U[o->a] - UB; break;
-        case PZK_U_MUL: U[o->dst] = U[o->a] * UB; break;
-        case PZK_U_DIV: { uint64_t b = UB; U[o->dst] = b ? U[o->a] / b : 0; break; }
-        case PZK_U_MOD: { uint64_t b = UB; U[o->dst] = b ? U[o->a] % b : 0; break; }
-        case PZK_U_SHR: { uint64_t b = UB; U[o->dst] = b >= 64 ? 0 : U[o->a] >> b; break; }
-        case PZK_U_SHL: { uint64_t b = UB; U[o->dst] = b >= 64 ? 0 : U[o->a] << b; break; }
-        case PZK_U_AND: U[o->dst] = U[o->a] & UB; break;
-        case PZK_U_OR: U[o->dst] = U[o->a] | UB; break;
-        case PZK_U_XOR: U[o->dst] = U[o->a] ^ UB; break;
-        case PZK_U_LT: U[o->dst] = U[o->a] < UB; break;
-        case PZK_U_LE: U[o->dst] = U[o->a] <= UB; break;
-        case PZK_U_EQ: U[o->dst] = U[o->a] == UB; break;
-        case PZK_U_NE: U[o->dst] = U[o->a] != UB; break;
-        case PZK_I_LT: U[o->dst] = (int64_t)U[o->a] < (int64_t)UB; break;
-        case PZK_I_LE: U[o->dst] = (int64_t)U[o->a] <= (int64_t)UB; break;
-        case PZK_U_SEL: U[o->dst] = U[o->a] ? U[o->b] : U[x->c]; break;
+        case PZK_U_CONST: WRU(o->dst, ((uint64_t)o->b << 32) | o->a); break;
+        case PZK_U_ADD: WRU(o->dst, UA + UB); break;
+        case PZK_U_SUB: WRU(o->dst, UA - UB); break;
+        case PZK_U_MUL: WRU(o->dst, UA * UB); break;
+        case PZK_U_DIV: { uint64_t b = UB; WRU(o->dst, b ? UA / b : 0); break; }
+        case PZK_U_MOD: { uint64_t b = UB; WRU(o->dst, b ? UA % b : 0); break; }
+        case PZK_U_SHR: { uint64_t b = UB; WRU(o->dst, b >= 64 ? 0 : UA >> b); break; }
+        case PZK_U_SHL: { uint64_t b = UB; WRU(o->dst, b >= 64 ? 0 : UA << b); break; }
+        case PZK_U_AND: WRU(o->dst, UA & UB); break;
+        case PZK_U_OR: WRU(o->dst, UA | UB); break;
+        case PZK_U_XOR: WRU(o->dst, UA ^ UB); break;
+        case PZK_U_LT: WRU(o->dst, UA < UB); break;
+        case PZK_U_LE: WRU(o->dst, UA <= UB); break;
+        case PZK_U_EQ: WRU(o->dst, UA == UB); break;
+        case PZK_U_NE: WRU(o->dst, UA != UB); break;
+        case PZK_I_LT: WRU(o->dst, (int64_t)UA < (int64_t)UB); break;
+        case PZK_I_LE: WRU(o->dst, (int64_t)UA <= (int64_t)UB); break;
+        case PZK_U_SEL: WRU(o->dst, UA ? RDU(o->b) : RDU(x->c)); break;
         case PZK_U_LUT: case PZK_U_LUTV: {
           unsigned idx = 0;
-          if (o->a != PZK_OPERAND_NONE) idx |= (unsigned)(U[o->a] & 1);
-          if (o->b != PZK_OPERAND_NONE) idx |= (unsigned)(U[o->b] & 1) << 1;
-          if (x->c != PZK_OPERAND_NONE) idx |= (unsigned)(U[x->c] & 1) << 2;
-          if (x->d != PZK_OPERAND_NONE) idx |= (unsigned)(U[x->d] & 1) << 3;
-          if (o->opc == PZK_U_LUT) U[o->dst] = (o->imm16 >> idx) & 1;
-          else U[o->dst] = (uint64_t)p->list[x->e + 2 * idx] | ((uint64_t)p->list[x->e + 2 * idx + 1] << 32);
+          if (o->a != PZK_OPERAND_NONE) idx |= (unsigned)(RDU(o->a) & 1);
+          if (o->b != PZK_OPERAND_NONE) idx |= (unsigned)(RDU(o->b) & 1) << 1;
+          if (x->c != PZK_OPERAND_NONE) idx |= (unsigned)(RDU(x->c) & 1) << 2;
+          if (x->d != PZK_OPERAND_NONE) idx |= (unsigned)(RDU(x->d) & 1) << 3;
+          if (o->opc == PZK_U_LUT) WRU(o->dst, (o->imm16 >> idx) & 1);
+          else WRU(o->dst, (uint64_t)p->list[x->e + 2 * idx] | ((uint64_t)p->list[x->e + 2 * idx + 1] << 32));
           break;
         }
-        case PZK_F_CONST: memcpy(FD, p->fpool + 4 * (uint64_t)o->a, 32); break;
-        case PZK_F_ADD: fadd(FD, FA, FB); break;
-        case PZK_F_SUB: fsub(FD, FA, FB); break;
-        case PZK_F_MUL: fmul(FD, FA, FB); break;
-        case PZK_F_NEG: { uint64_t z[4] = {0, 0, 0, 0}; fsub(FD, z, FA); break; }
-        case PZK_F_INV: finv(FD, FA); break;
-        case PZK_F_FROM_U: { uint64_t w[4] = {U[o->a], 0, 0, 0}; to_mont(FD, w); break; }
+        case PZK_F_CONST: WRF(o->dst, p->fpool + 4 * (uint64_t)o->a); break;
+        case PZK_F_ADD: { uint64_t r[4]; fadd(r, FA, FB); WRF(o->dst, r); break; }
+        case PZK_F_SUB: { uint64_t r[4]; fsub(r, FA, FB); WRF(o->dst, r); break; }
+        case PZK_F_MUL: { uint64_t r[4]; fmul(r, FA, FB); WRF(o->dst, r); break; }
+        case PZK_F_NEG: { uint64_t z[4] = {0, 0, 0, 0}, r[4]; fsub(r, z, FA); WRF(o->dst, r); break; }
+        case PZK_F_INV: { uint64_t r[4]; finv(r, FA); WRF(o->dst, r); break; }
+        case PZK_F_FROM_U: { uint64_t w[4] = {UA, 0, 0, 0}, r[4]; to_mont(r, w); WRF(o->dst, r); break; }
         case PZK_F_FROM_I: {
-          int64_t v = (int64_t)U[o->a];
-          uint64_t w[4] = {v < 0 ? (uint64_t)(-v) : (uint64_t)v, 0, 0, 0}, z[4] = {0, 0, 0, 0};
+          int64_t v = (int64_t)UA;
+          uint64_t w[4] = {v < 0 ? (uint64_t)(-v) : (uint64_t)v, 0, 0, 0}, z[4] = {0, 0, 0, 0}, r[4];
           to_mont(w, w);
-          if (v < 0) fsub(FD, z, w); else memcpy(FD, w, 32);
+          if (v < 0) fsub(r, z, w); else memcpy(r, w, 32);
+          WRF(o->dst, r);
           break;
         }
-        case PZK_F_SEL: memcpy(FD, U[o->a] ? (F + 4 * (uint64_t)o->b) : (F + 4 * (uint64_t)x->c), 32); break;
-        case PZK_F_EQ: U[o->dst] = memcmp(FA, FB, 32) == 0; break;
-        case PZK_F_NE: U[o->dst] = memcmp(FA, FB, 32) != 0; break;
-        case PZK_F_CSEL: memcpy(FD, p->fpool + 4 * ((uint64_t)o->b + U[o->a]), 32); break;
-        case PZK_N_FROM_F: from_mont(FD, FA); break;
-        case PZK_F_FROM_N: { uint64_t t[4]; memcpy(t, FA, 32); reduce_p(t); to_mont(FD, t); break; }
-        case PZK_N_FROM_U: { uint64_t w[4] = {U[o->a], 0, 0, 0}; memcpy(FD, w, 32); break; }
-        case PZK_N_BIT: U[o->dst] = o->b < 256 ? (FA[o->b >> 6] >> (o->b & 63)) & 1 : 0; break;
-        case PZK_N_LOW: U[o->dst] = FA[0]; break;
-        case PZK_N_FITS: U[o->dst] = (FA[1] | FA[2] | FA[3]) == 0; break;
-        case PZK_N_SHR: { uint64_t b = UB; uint64_t t[4]; shr4(t, FA, b > 256 ? 256 : (unsigned)b); memcpy(FD, t, 32); break; }
+        case PZK_F_SEL: WRF(o->dst, UA ? RDF(o->b) : RDF(x->c)); break;
+        case PZK_F_EQ: WRU(o->dst, memcmp(FA, FB, 32) == 0); break;
+        case PZK_F_NE: WRU(o->dst, memcmp(FA, FB, 32) != 0); break;
+        case PZK_F_CSEL: WRF(o->dst, p->fpool + 4 * ((uint64_t)o->b + UA)); break;
+        case PZK_N_FROM_F: { uint64_t r[4]; from_mont(r, FA); WRF(o->dst, r); break; }
+        case PZK_F_FROM_N: { uint64_t t[4], r[4]; memcpy(t, FA, 32); reduce_p(t); to_mont(r, t); WRF(o->dst, r); break; }
+        case PZK_N_FROM_U: { uint64_t w[4] = {UA, 0, 0, 0}; WRF(o->dst, w); break; }
+        case PZK_N_BIT: WRU(o->dst, o->b < 256 ? (FA[o->b >> 6] >> (o->b & 63)) & 1 : 0); break;
+        case PZK_N_LOW: WRU(o->dst, FA[0]); break;
+        case PZK_N_FITS: WRU(o->dst, (FA[1] | FA[2] | FA[3]) == 0); break;
+        case PZK_N_SHR: { uint64_t b = UB; uint64_t t[4]; shr4(t, FA, b > 256 ? 256 : (unsigned)b); WRF(o->dst, t); break; }
         case PZK_N_SHL: {
           uint64_t b = UB; uint64_t t[4] = {0, 0, 0, 0};
           if (b < 254) { shl4(t, FA, (unsigned)b); t[3] &= 0x3fffffffffffffffull; reduce_p(t); }
-          memcpy(FD, t, 32); break;
+          WRF(o->dst, t); break;
         }
-        case PZK_N_AND: { const uint64_t* b = FB; uint64_t t[4]; for (int i = 0; i < 4; i++) t[i] = FA[i] & b[i]; reduce_p(t); memcpy(FD, t, 32); break; }
-        case PZK_N_OR: { const uint64_t* b = FB; uint64_t t[4]; for (int i = 0; i < 4; i++) t[i] = FA[i] | b[i]; t[3] &= 0x3fffffffffffffffull; reduce_p(t); memcpy(FD, t, 32); break; }
-        case PZK_N_XOR: { const uint64_t* b = FB; uint64_t t[4]; for (int i = 0; i < 4; i++) t[i] = FA[i] ^ b[i]; t[3] &= 0x3fffffffffffffffull; reduce_p(t); memcpy(FD, t, 32); break; }
-        case PZK_N_DIV: { uint64_t q[4]; divmod4(FA, FB, q, NULL); memcpy(FD, q, 32); break; }
-        case PZK_N_MOD: { uint64_t m[4]; divmod4(FA, FB, NULL, m); memcpy(FD, m, 32); break; }
-        case PZK_N_SLT: U[o->dst] = scmp(FA, FB) < 0; break;
-        case PZK_N_SLE: U[o->dst] = scmp(FA, FB) <= 0; break;
+        case PZK_N_AND: { const uint64_t* b = FB; uint64_t t[4]; for (int i = 0; i < 4; i++) t[i] = FA[i] & b[i]; reduce_p(t); WRF(o->dst, t); break; }
+        case PZK_N_OR: { const uint64_t* b = FB; uint64_t t[4]; for (int i = 0; i < 4; i++) t[i] = FA[i] | b[i]; t[3] &= 0x3fffffffffffffffull; reduce_p(t); WRF(o->dst, t); break; }
+        case PZK_N_XOR: { const uint64_t* b = FB; uint64_t t[4]; for (int i = 0; i < 4; i++) t[i] = FA[i] ^ b[i]; t[3] &= 0x3fffffffffffffffull; reduce_p(t); WRF(o->dst, t); break; }
+        case PZK_N_DIV: { uint64_t q[4]; divmod4(FA, FB, q, NULL); WRF(o->dst, q); break; }
+        case PZK_N_MOD: { uint64_t m[4]; divmod4(FA, FB, NULL, m); WRF(o->dst, m); break; }
+        case PZK_N_SLT: WRU(o->dst, scmp(FA, FB) < 0); break;
+        case PZK_N_SLE: WRU(o->dst, scmp(FA, FB) <= 0); break;
         case PZK_BIGDIV: {
           const uint32_t* L = p->list + o->a;
           unsigned n = L[0], k = L[1], m = L[2];
@@ -351,7 +360,7 @@ uint32_t pzk_ref_witness(const PzkRefProgram* p, const uint8_t* inputs, uint8_t*
           for (unsigned i = 0; i < k; i++) U[L[3 + k + m + k + m + 1 + i]] = r[i];
           break;
         }
-        case PZK_CHECK_INT: case PZK_CHECK_F: {
+        case PZK_CHECK_I64: case PZK_CHECK_INT: case PZK_CHECK_F: {
           /* a constraint row fused into the op stream: A.w * B.w == C.w, checked here with
            * the generic field arithmetic for both kinds (the integer fast path is a device-side
            * optimisation whose result must agree) */
@@ -365,7 +374,7 @@ uint32_t pzk_ref_witness(const PzkRefProgram* p, const uint8_t* inputs, uint8_t*
               for (unsigned i = 0; i < lens[part]; i++, k++) {
                 uint32_t ref = tw[2 * k], cw = tw[2 * k + 1];
                 uint64_t cm[4], v[4], t[4];
-                if (o->opc == PZK_CHECK_INT) {
+                if (o->opc != PZK_CHECK_F) {
                   int64_t c;
                   if (ref == PZK_REF_ONE_LIST || (ref < PZK_REF_ONE_LIST && (ref & PZK_TERM_COEF_LIST)))
                     c = (int64_t)((uint64_t)p->list[cw] | ((uint64_t)p->list[cw + 1] << 32));
@@ -376,9 +385,10 @@ uint32_t pzk_ref_witness(const PzkRefProgram* p, const uint8_t* inputs, uint8_t*
                 } else memcpy(cm, p->coefs[cw].mont, 32);
                 if (ref >= PZK_REF_ONE_LIST) { fadd(acc[part], acc[part], cm); continue; }
                 uint32_t cls = PZK_REF_CLS(ref), slot = PZK_REF_SLOT(ref);
-                if (cls == 2) memcpy(v, F + 4 * (uint64_t)slot, 32);
+                int in_cell = (ref & PZK_TERM_CELL) != 0;
+                if (cls == 2) memcpy(v, in_cell ? (cells + (ref & 0xffffu)) : (F + 4 * (uint64_t)slot), 32);
                 else {
-                  uint64_t raw = U[slot];
+                  uint64_t raw = in_cell ? cells[ref & 0xffffu] : U[slot];
                   int neg = cls == 1 && (int64_t)raw < 0;
                   uint64_t m[4] = {neg ? (uint64_t)(-(int64_t)raw) : raw, 0, 0, 0}, z[4] = {0, 0, 0, 0};
                   to_mont(v, m);
@@ -398,19 +408,19 @@ uint32_t pzk_ref_witness(const PzkRefProgram* p, const uint8_t* inputs, uint8_t*
           pc += nrec;
           break;
         }
-        case PZK_ASSERT_NZ: if (U[o->a] == 0) status |= PZK_LANE_ASSERT; break;
+        case PZK_ASSERT_NZ: if (UA == 0) status |= PZK_LANE_ASSERT; break;
         case PZK_IN_U: {
-          const uint64_t* v = (const uint64_t*)(inputs + 32 * (uint64_t)o->a);
-          uint64_t w[4]; memcpy(w, v, 32);
+          uint64_t w[4]; memcpy(w, inputs + 32 * (uint64_t)o->a, 32);
           int bits = o->imm16;
           if (w[1] | w[2] | w[3] || (bits < 64 && (w[0] >> bits))) status |= PZK_LANE_INPUT_RANGE;
-          U[o->dst] = w[0];
+          WRU(o->dst, w[0]);
           break;
         }
         case PZK_IN_F: {
-          uint64_t w[4]; memcpy(w, inputs + 32 * (uint64_t)o->a, 32);
+          uint64_t w[4], r[4]; memcpy(w, inputs + 32 * (uint64_t)o->a, 32);
           if (cmp4(w, P) >= 0) { status |= PZK_LANE_INPUT_RANGE; reduce_p(w); }
-          to_mont(FD, w);
+          to_mont(r, w);
+          WRF(o->dst, r);
           break;
         }
         default: fprintf(stderr, "ssa_ref: bad opcode %d\n", o->opc); abort();

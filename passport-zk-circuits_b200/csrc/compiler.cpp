@@ -2,6 +2,7 @@
 #include "compiler.hpp"
 
 #include <chrono>
+#include <queue>
 #include <cstdarg>
 #include <cstring>
 
@@ -177,7 +178,8 @@ struct Compiler::Impl {
   std::vector<PzkInput> out_inputs;
   std::vector<uint32_t> out_list;
   uint32_t n_u_slots = 0, n_f_slots = 0;
-  uint64_t n_int_rows = 0, n_field_rows = 0, eval_bytes = 0, check_bytes = 0;
+  uint64_t n_static_rows = 0, n_i64_rows = 0, n_int_rows = 0, n_field_rows = 0, eval_bytes = 0, check_bytes = 0, cache_hit_refs = 0, cache_miss_refs = 0;
+  std::vector<uint32_t> seg_quads;
   uint32_t n_pub_out = 0, n_pub_in = 0, n_prv_in = 0;
   std::string meta_json;
 
@@ -1640,9 +1642,39 @@ void Compiler::Impl::backend() {
     }
     row_recs[r] = 1 + (live_terms + 1) / 2;
   }
+
   std::vector<uint32_t> row_order(nrows);
   for (size_t r = 0; r < nrows; r++) row_order[r] = (uint32_t)r;
   std::stable_sort(row_order.begin(), row_order.end(), [&](uint32_t a, uint32_t b) { return row_trigger[a] < row_trigger[b]; });
+  struct MT { uint32_t val; U256 c; };  // val: value id, 0xFFFFFFFF = constant one
+  // merge the terms of each linear combination by SSA value: wires that alias the same value
+  // (every `a <== b`) collapse, and a row whose combinations cancel completely is satisfied by
+  // construction - it is proven at compile time and needs no run-time work.
+  auto merge_row = [&](uint32_t r, std::vector<MT>* parts) {
+    uint32_t lens[3] = {rows[r].na, rows[r].nb, rows[r].nc};
+    uint64_t off = rows[r].off;
+    for (int part = 0; part < 3; part++) {
+      parts[part].clear();
+      for (uint32_t t = 0; t < lens[part]; t++, off++) {
+        uint32_t sig = terms[off].first;
+        uint32_t val = 0xFFFFFFFFu;
+        if (sig != 0xFFFFFFFFu) { val = sig_val[sig]; if (!val) continue; }
+        const U256& c = coefs[terms[off].second];
+        bool found = false;
+        for (auto& m : parts[part]) if (m.val == val) { m.c = fr_add(m.c, c); found = true; break; }
+        if (!found) parts[part].push_back({val, c});
+      }
+      size_t w = 0;
+      for (size_t k = 0; k < parts[part].size(); k++) if (!parts[part][k].c.is_zero()) parts[part][w++] = parts[part][k];
+      parts[part].resize(w);
+    }
+    return parts[2].empty() && (parts[0].empty() || parts[1].empty());
+  };
+  std::vector<uint8_t> row_static(nrows, 0);
+  {
+    std::vector<MT> parts[3];
+    for (size_t r = 0; r < nrows; r++) if (merge_row((uint32_t)r, parts)) { row_static[r] = 1; n_static_rows++; }
+  }
   // ---- segments over kept ops (+ their rows)
   std::vector<uint32_t> def_seg(nv, 0), last_seg(nv, 0), op_seg(nops, 0);
   {
@@ -1652,7 +1684,7 @@ void Compiler::Impl::backend() {
       if (!keep[i]) continue;
       uint64_t need = (ops[i].flags & PZK_FLAG_EXT) ? 2 : 1;
       size_t q = rp;
-      while (q < nrows && row_trigger[row_order[q]] == i) { need += row_recs[row_order[q]]; q++; }
+      while (q < nrows && row_trigger[row_order[q]] == i) { if (!row_static[row_order[q]]) need += row_recs[row_order[q]]; q++; }
       if (rec && rec + need > opt.seg_ops) { seg++; rec = 0; }
       rec += need;
       op_seg[i] = seg;
@@ -1667,6 +1699,7 @@ void Compiler::Impl::backend() {
     for_operands(ops[i], [&](uint32_t v) { if (last_seg[v] < sg) last_seg[v] = sg; });
   }
   for (size_t r = 0; r < nrows; r++) {
+    if (row_static[r]) continue;
     uint32_t sg = op_seg[row_trigger[r]];
     uint32_t nt = rows[r].na + rows[r].nb + rows[r].nc;
     for (uint32_t t = 0; t < nt; t++) {
@@ -1716,45 +1749,40 @@ void Compiler::Impl::backend() {
     return (cls << 30) | v_slot[v];
   };
   std::unordered_map<uint64_t, uint32_t> icoef_off;  // int64 coefficient -> list offset
+  std::function<uint32_t(uint32_t)> row_ref;
   auto emit_row = [&](uint32_t r) {
-    uint32_t lens[3] = {rows[r].na, rows[r].nb, rows[r].nc};
-    // classification: exact integer check possible?
-    bool is_int = true;
+    std::vector<MT> parts[3];
+    if (merge_row(r, parts)) return;
+    // classification by compile-time bounds
+    bool is_int = true, all32 = true;
     unsigned __int128 bound[3] = {0, 0, 0};
     const unsigned __int128 SAT = (unsigned __int128)1 << 127;
-    {
-      uint64_t off = rows[r].off;
-      for (int part = 0; part < 3 && is_int; part++)
-        for (uint32_t t = 0; t < lens[part]; t++, off++) {
-          uint32_t sig = terms[off].first;
-          int64_t cv;
-          if (!small_signed(coefs[terms[off].second], cv)) { is_int = false; break; }
-          unsigned __int128 mag = (unsigned __int128)(cv < 0 ? -cv : cv);
-          unsigned __int128 vmax = 1;
-          if (sig != 0xFFFFFFFFu) {
-            uint32_t v = sig_val[sig];
-            if (!v) continue;
-            if (v_cls[v] != CLS_U && v_cls[v] != CLS_I) { is_int = false; break; }
-            i128 a = v_lo[v] < 0 ? -v_lo[v] : v_lo[v], b = v_hi[v] < 0 ? -v_hi[v] : v_hi[v];
-            vmax = (unsigned __int128)(a > b ? a : b);
-          }
-          unsigned __int128 add = mag * vmax;  // < 2^62 * 2^64
-          bound[part] = bound[part] + add;
-          if (bound[part] >= SAT) { is_int = false; break; }
+    for (int part = 0; part < 3 && is_int; part++)
+      for (auto& m : parts[part]) {
+        int64_t cv;
+        if (!small_signed(m.c, cv)) { is_int = false; break; }
+        if (cv < INT32_MIN || cv > INT32_MAX) all32 = false;
+        unsigned __int128 mag = (unsigned __int128)(cv < 0 ? -cv : cv), vmax = 1;
+        if (m.val != 0xFFFFFFFFu) {
+          uint32_t v = m.val;
+          if (v_cls[v] != CLS_U && v_cls[v] != CLS_I) { is_int = false; break; }
+          i128 a = v_lo[v] < 0 ? -v_lo[v] : v_lo[v], b = v_hi[v] < 0 ? -v_hi[v] : v_hi[v];
+          vmax = (unsigned __int128)(a > b ? a : b);
         }
-    }
+        bound[part] += mag * vmax;
+        if (bound[part] >= SAT) { is_int = false; break; }
+      }
     const unsigned __int128 LIM63 = (unsigned __int128)1 << 63, LIM126 = (unsigned __int128)1 << 126;
     if (is_int && (bound[0] >= LIM63 || bound[1] >= LIM63 || bound[2] >= LIM126)) is_int = false;
+    bool is_i64 = is_int && all32 && bound[2] < LIM63 && (bound[0] == 0 || bound[1] == 0 || bound[0] * bound[1] < LIM63);
     std::vector<PzkTerm> ts;
     uint16_t cnt[3] = {0, 0, 0};
-    uint64_t off = rows[r].off;
     for (int part = 0; part < 3; part++)
-      for (uint32_t t = 0; t < lens[part]; t++, off++) {
-        uint32_t ref = ref_of_sig(terms[off].first);
-        if (ref == PZK_REF_ZERO) continue;
-        PzkTerm pt; pt.ref = ref;
+      for (auto& m : parts[part]) {
+        PzkTerm pt;
+        pt.ref = (m.val == 0xFFFFFFFFu) ? PZK_REF_ONE : row_ref(m.val);
         if (is_int) {
-          int64_t cv; small_signed(coefs[terms[off].second], cv);
+          int64_t cv; small_signed(m.c, cv);
           if (cv >= INT32_MIN && cv <= INT32_MAX) pt.coef = (uint32_t)(int32_t)cv;
           else {
             auto it = icoef_off.find((uint64_t)cv);
@@ -1765,13 +1793,15 @@ void Compiler::Impl::backend() {
               icoef_off[(uint64_t)cv] = lo;
             } else lo = it->second;
             pt.coef = lo;
-            if (ref != PZK_REF_ONE) pt.ref |= PZK_TERM_COEF_LIST; else pt.ref = PZK_REF_ONE_LIST;
+            if (pt.ref != PZK_REF_ONE) pt.ref |= PZK_TERM_COEF_LIST; else pt.ref = PZK_REF_ONE_LIST;
           }
-        } else pt.coef = terms[off].second;
-        // a constant-one term with a list coefficient is flagged through the coefficient word
+        } else {
+          pt.coef = coef_id(m.c);
+          if (m.val != 0xFFFFFFFFu && v_cls[m.val] == CLS_U && v_lo[m.val] >= 0 && v_hi[m.val] <= 1) pt.ref |= PZK_TERM_BIT;
+        }
         ts.push_back(pt); cnt[part]++;
       }
-    PzkOp h; h.opc = is_int ? PZK_CHECK_INT : PZK_CHECK_F; h.flags = 0; h.imm16 = cnt[0];
+    PzkOp h; h.opc = is_i64 ? PZK_CHECK_I64 : (is_int ? PZK_CHECK_INT : PZK_CHECK_F); h.flags = 0; h.imm16 = cnt[0];
     h.dst = r; h.a = (uint32_t)cnt[1] | ((uint32_t)cnt[2] << 16); h.b = (uint32_t)((ts.size() + 1) / 2);
     out_ops.push_back(h);
     for (size_t k = 0; k < ts.size(); k += 2) {
@@ -1780,57 +1810,227 @@ void Compiler::Impl::backend() {
       PzkOp raw; memcpy(&raw, wds, 16);
       out_ops.push_back(raw);
     }
-    if (is_int) n_int_rows++; else n_field_rows++;
-    for (auto& t : ts) if (t.ref != PZK_REF_ONE && t.ref != PZK_REF_ONE_LIST) check_bytes += (PZK_REF_CLS(t.ref) == 2) ? 32 : 8;
+    if (is_i64) n_i64_rows++; else if (is_int) n_int_rows++; else n_field_rows++;
+    for (auto& t : ts) if (t.ref < PZK_REF_ONE_LIST) check_bytes += (PZK_REF_CLS(t.ref) == 2) ? 32 : 8;
   };
   out_list = list_pool;
   out_ops.clear();
+  // ---- operand cache: use lists (positions in event order: op, then the rows it completes)
+  const uint32_t NC = opt.cells;
+  seg_quads.assign(segs.size(), 0);
   {
+    std::vector<uint64_t> nu(segs.size(), 0), nf(segs.size(), 0);
+    for (size_t i = 0; i < nops; i++) {
+      if (!keep[i] || ops[i].opc == PZK_BIGDIV) continue;
+      for_defs(ops[i], [&](uint32_t d) { ((v_cls[d] == CLS_U || v_cls[d] == CLS_I) ? nu : nf)[op_seg[i]]++; });
+    }
+    for (size_t sg = 0; sg < segs.size(); sg++) {
+      if (!nf[sg] || NC < 8) continue;
+      double share = 4.0 * nf[sg] / (4.0 * nf[sg] + nu[sg]);
+      uint32_t q = (uint32_t)(NC / 4 * share + 0.5);
+      if (q < 1) q = 1;
+      if (nu[sg] && q > NC / 4 - 2) q = NC / 4 - 2;
+      if (q > NC / 4) q = NC / 4;
+      seg_quads[sg] = q;
+    }
+  }
+  std::vector<uint32_t> use_cnt(nv + 1, 0);
+  std::vector<uint32_t> op_pos(nops, 0), seg_last_pos(segs.size(), 0);
+  {
+    uint32_t pos = 0; size_t rp = 0;
+    for (size_t i = 0; i < nops; i++) {
+      if (!keep[i]) continue;
+      op_pos[i] = pos;
+      if (ops[i].opc != PZK_BIGDIV) for_operands(ops[i], [&](uint32_t v) { use_cnt[v]++; });
+      pos++;
+      while (rp < nrows && row_trigger[row_order[rp]] == i) {
+        uint32_t r = row_order[rp], nt = rows[r].na + rows[r].nb + rows[r].nc;
+        if (row_static[r]) { rp++; continue; }
+        for (uint32_t t = 0; t < nt; t++) { uint32_t sig = terms[rows[r].off + t].first; if (sig != 0xFFFFFFFFu && sig_val[sig]) use_cnt[sig_val[sig]]++; }
+        pos++; rp++;
+      }
+      seg_last_pos[op_seg[i]] = pos;
+    }
+  }
+  std::vector<uint64_t> use_off(nv + 1, 0);
+  for (size_t v = 0; v < nv; v++) use_off[v + 1] = use_off[v] + use_cnt[v];
+  std::vector<uint32_t> use_pos(use_off[nv]), use_fill(nv, 0);
+  {
+    uint32_t pos = 0; size_t rp = 0;
+    for (size_t i = 0; i < nops; i++) {
+      if (!keep[i]) continue;
+      if (ops[i].opc != PZK_BIGDIV) for_operands(ops[i], [&](uint32_t v) { use_pos[use_off[v] + use_fill[v]++] = pos; });
+      pos++;
+      while (rp < nrows && row_trigger[row_order[rp]] == i) {
+        uint32_t r = row_order[rp], nt = rows[r].na + rows[r].nb + rows[r].nc;
+        if (row_static[r]) { rp++; continue; }
+        for (uint32_t t = 0; t < nt; t++) { uint32_t sig = terms[rows[r].off + t].first; if (sig != 0xFFFFFFFFu && sig_val[sig]) { uint32_t v = sig_val[sig]; use_pos[use_off[v] + use_fill[v]++] = pos; } }
+        pos++; rp++;
+      }
+    }
+  }
+  std::vector<uint32_t> use_idx(nv, 0);
+  std::vector<int32_t> cell_of(nv, -1);
+  std::vector<uint32_t> cur_next(nv, 0);
+  std::vector<uint8_t> needs_global(nv, 0);
+  int pass = 0;
+  const uint32_t INF = 0xFFFFFFFFu;
+  typedef std::pair<uint32_t, uint32_t> HeapE;  // (next use, value)
+  std::priority_queue<HeapE> heap_u, heap_f;
+  std::vector<uint32_t> free_cells, free_quads, cached_list;
+  uint64_t cache_hits = 0, cache_miss = 0;
+  auto next_use_after = [&](uint32_t v, uint32_t pos, uint32_t seg_end) -> uint32_t {
+    uint32_t& k = use_idx[v];
+    while (k < use_cnt[v] && use_pos[use_off[v] + k] <= pos) k++;
+    if (k >= use_cnt[v]) return INF;
+    uint32_t nx = use_pos[use_off[v] + k];
+    return nx < seg_end ? nx : INF;
+  };
+  auto release = [&](uint32_t v) {
+    if (cell_of[v] < 0) return;
+    if (v_cls[v] == CLS_U || v_cls[v] == CLS_I) free_cells.push_back((uint32_t)cell_of[v]); else free_quads.push_back((uint32_t)cell_of[v]);
+    cell_of[v] = -1;
+  };
+  auto reset_cache = [&](uint32_t seg) {
+    for (uint32_t v : cached_list) cell_of[v] = -1;
+    cached_list.clear();
+    while (!heap_u.empty()) heap_u.pop();
+    while (!heap_f.empty()) heap_f.pop();
+    // partition the cells between singles and quads by the segment's definition mix
+    uint64_t ub = 0, fb = 0;
+    (void)seg;
+    free_cells.clear(); free_quads.clear();
+    uint32_t quads = seg_quads[seg];
+    uint32_t singles = NC - 4 * quads;
+    for (uint32_t c = singles; c-- > 0;) free_cells.push_back(c);
+    for (uint32_t q = quads; q-- > 0;) free_quads.push_back(singles + 4 * q);
+    (void)ub; (void)fb;
+  };
+  auto touch_operand = [&](uint32_t v, uint32_t pos, uint32_t seg_end) {  // after the event used v
+    if (v == PZK_OPERAND_NONE || cell_of[v] < 0) return;
+    uint32_t nx = next_use_after(v, pos, seg_end);
+    if (nx == INF) { release(v); return; }
+    if (nx != cur_next[v]) {
+      cur_next[v] = nx;
+      ((v_cls[v] == CLS_U || v_cls[v] == CLS_I) ? heap_u : heap_f).push({nx, v});
+    }
+  };
+  auto try_cache_def = [&](uint32_t d, uint32_t pos, uint32_t seg_end) -> int32_t {
+    if (NC == 0) return -1;
+    uint32_t nx = next_use_after(d, pos, seg_end);
+    if (nx == INF) return -1;
+    bool narrow = (v_cls[d] == CLS_U || v_cls[d] == CLS_I);
+    std::vector<uint32_t>& fr = narrow ? free_cells : free_quads;
+    std::priority_queue<HeapE>& hp = narrow ? heap_u : heap_f;
+    if (fr.empty()) {
+      // evict the cached value whose next use is furthest away, if it is further than ours
+      while (!hp.empty()) {
+        HeapE top = hp.top();
+        if (cell_of[top.second] < 0 || cur_next[top.second] != top.first) { hp.pop(); continue; }
+        if (top.first <= nx) return -1;
+        hp.pop();
+        release(top.second);
+        break;
+      }
+      if (fr.empty()) return -1;
+    }
+    uint32_t c = fr.back(); fr.pop_back();
+    cell_of[d] = (int32_t)c; cur_next[d] = nx;
+    hp.push({nx, d});
+    cached_list.push_back(d);
+    return (int32_t)c;
+  };
+  auto opnd = [&](uint32_t v) -> uint32_t {
+    if (v == PZK_OPERAND_NONE) return v;
+    if (cell_of[v] >= 0) { cache_hits++; return PZK_OPERAND_CELL | (uint32_t)cell_of[v]; }
+    cache_miss++;
+    needs_global[v] = 1;
+    return slot_of(v);
+  };
+  auto tref = [&](uint32_t v) -> uint32_t {
+    uint32_t cls = v_cls[v] == CLS_U ? 0u : (v_cls[v] == CLS_I ? 1u : 2u);
+    if (cell_of[v] >= 0) { cache_hits++; return (cls << 30) | PZK_TERM_CELL | (uint32_t)cell_of[v]; }
+    cache_miss++;
+    needs_global[v] = 1;
+    return (cls << 30) | v_slot[v];
+  };
+  row_ref = tref;
+  // values that must always reach their global slot: public wires (read by the export kernel)
+  for (uint32_t sg = 0; sg < sig_val.size(); sg++) if (sig_val[sg] && sig2wire[sg] <= n_pub_out + n_pub_in) needs_global[sig_val[sg]] = 1;
+  for (pass = 0; pass < 2; pass++) {
+    // pass 0 learns which values are ever read from their global slot; pass 1 emits
+    out_list = list_pool; out_ops.clear(); icoef_off.clear();
+    std::fill(use_idx.begin(), use_idx.end(), 0u);
+    cache_hits = cache_miss = 0; n_i64_rows = n_int_rows = n_field_rows = 0; eval_bytes = check_bytes = 0;
     uint32_t cur = 0xFFFFFFFFu;
     size_t rp = 0;
+    uint32_t pos = 0;
     for (size_t i = 0; i < nops; i++) {
       if (!keep[i]) continue;
       const OpRec& o = ops[i];
       uint32_t s = op_seg[i];
-      if (s != cur) { cur = s; segs[s].op_off = out_ops.size(); }
+      if (s != cur) { cur = s; segs[s].op_off = out_ops.size(); reset_cache(s); }
+      const uint32_t seg_end = seg_last_pos[s];
       PzkOp r; r.opc = o.opc; r.flags = o.flags; r.imm16 = o.imm16; r.dst = 0; r.a = o.a; r.b = o.b;
       auto cls_bytes = [&](uint32_t v) -> uint64_t { return (v == PZK_OPERAND_NONE) ? 0 : ((v_cls[v] == CLS_U || v_cls[v] == CLS_I) ? 8 : 32); };
       for_operands(o, [&](uint32_t v) { eval_bytes += cls_bytes(v); });
       for_defs(o, [&](uint32_t v) { eval_bytes += cls_bytes(v); });
+      uint32_t ext_c = PZK_OPERAND_NONE, ext_d = PZK_OPERAND_NONE;
+      bool has_dst = false;
       switch (o.opc) {
         case PZK_NOP: break;
-        case PZK_U_CONST: case PZK_F_CONST: case PZK_IN_U: case PZK_IN_F: r.dst = slot_of(o.dst); break;
-        case PZK_ASSERT_NZ: r.a = slot_of(o.a); break;
+        case PZK_U_CONST: case PZK_F_CONST: case PZK_IN_U: case PZK_IN_F: has_dst = true; break;
+        case PZK_ASSERT_NZ: r.a = opnd(o.a); break;
         case PZK_BIGDIV: {
           uint32_t k = list_pool[o.a + 1], m = list_pool[o.a + 2];
           uint32_t cnt = (k + m) + k + (m + 1) + k;
-          for (uint32_t j = 0; j < cnt; j++) out_list[o.a + 3 + j] = slot_of(list_pool[o.a + 3 + j]);
+          for (uint32_t j = 0; j < cnt; j++) { out_list[o.a + 3 + j] = slot_of(list_pool[o.a + 3 + j]); needs_global[list_pool[o.a + 3 + j]] = 1; }
           break;
         }
-        case PZK_N_BIT: case PZK_F_CSEL: r.dst = slot_of(o.dst); r.a = slot_of(o.a); break;
-        case PZK_U_LUT: case PZK_U_LUTV: r.dst = slot_of(o.dst); r.a = slot_of(o.a); r.b = slot_of(o.b); break;
+        case PZK_N_BIT: case PZK_F_CSEL: has_dst = true; r.a = opnd(o.a); break;
+        case PZK_U_LUT: case PZK_U_LUTV: has_dst = true; r.a = opnd(o.a); r.b = opnd(o.b); ext_c = opnd(o.c); ext_d = opnd(o.d); break;
+        case PZK_U_SEL: case PZK_F_SEL: has_dst = true; r.a = opnd(o.a); r.b = opnd(o.b); ext_c = opnd(o.c); break;
         default:
-          r.dst = slot_of(o.dst); r.a = slot_of(o.a);
+          has_dst = true; r.a = opnd(o.a);
           if (!(o.flags & (PZK_FLAG_B_IMM | PZK_FLAG_B_POOL))) {
             switch (o.opc) {
               case PZK_F_NEG: case PZK_F_INV: case PZK_F_FROM_U: case PZK_F_FROM_I: case PZK_N_FROM_F:
               case PZK_F_FROM_N: case PZK_N_FROM_U: case PZK_N_LOW: case PZK_N_FITS: r.b = 0; break;
-              default: r.b = slot_of(o.b);
+              default: r.b = opnd(o.b);
             }
           }
       }
+      // operands die / get re-prioritised, then the result may take a cell
+      if (o.opc != PZK_BIGDIV) for_operands(o, [&](uint32_t v) { touch_operand(v, pos, seg_end); });
+      if (has_dst) {
+        uint32_t slot = slot_of(o.dst);
+        if (slot > 0x3fffffu) throw CompileError("too many live slots for the dst encoding");
+        int32_t cell = try_cache_def(o.dst, pos, seg_end);
+        if (cell >= 0 && cell > 509) throw CompileError("too many cache cells for the dst encoding");
+        r.dst = slot | (cell >= 0 ? ((uint32_t)cell + 1) << 22 : 0);
+        if (pass == 1 && cell >= 0 && !needs_global[o.dst]) r.dst |= PZK_DST_OPTIONAL;
+      }
       out_ops.push_back(r);
       if (o.flags & PZK_FLAG_EXT) {
-        PzkOpExt x; x.c = slot_of(o.c); x.d = slot_of(o.d); x.e = 0; x.f = 0;
+        PzkOpExt x; x.c = ext_c; x.d = ext_d; x.e = 0; x.f = 0;
         if (o.opc == PZK_U_LUTV) x.e = lutv_off[(uint32_t)i];
         PzkOp raw; memcpy(&raw, &x, sizeof raw);
         out_ops.push_back(raw);
       }
-      while (rp < nrows && row_trigger[row_order[rp]] == i) { emit_row(row_order[rp]); rp++; }
+      pos++;
+      while (rp < nrows && row_trigger[row_order[rp]] == i) {
+        uint32_t rr = row_order[rp];
+        if (row_static[rr]) { rp++; continue; }
+        emit_row(rr);
+        uint32_t nt = rows[rr].na + rows[rr].nb + rows[rr].nc;
+        for (uint32_t t = 0; t < nt; t++) { uint32_t sig = terms[rows[rr].off + t].first; if (sig != 0xFFFFFFFFu && sig_val[sig]) touch_operand(sig_val[sig], pos, seg_end); }
+        pos++; rp++;
+      }
       segs[s].n_ops = out_ops.size() - segs[s].op_off;
     }
     if (rp != nrows) throw CompileError("internal: constraint rows left unplaced");
   }
+  cache_hit_refs = cache_hits; cache_miss_refs = cache_miss;
   for (size_t s2 = 0; s2 < segs.size(); s2++) { segs[s2].row_off = 0; segs[s2].n_rows = 0; }
   // ---- exports per segment
   {
@@ -1891,8 +2091,11 @@ void Compiler::Impl::build_meta() {
        ",\"f_inv\":" + std::to_string(stats->f_inv) + ",\"f_other\":" + std::to_string(stats->f_other) +
        ",\"bigdiv\":" + std::to_string(stats->bigdiv) + ",\"lut\":" + std::to_string(stats->lut) +
        ",\"op_records\":" + std::to_string(out_ops.size()) + ",\"segments\":" + std::to_string(segs.size()) +
+       ",\"static_rows\":" + std::to_string(n_static_rows) + ",\"i64_rows\":" + std::to_string(n_i64_rows) +
        ",\"int_rows\":" + std::to_string(n_int_rows) + ",\"field_rows\":" + std::to_string(n_field_rows) +
        ",\"eval_bytes\":" + std::to_string(eval_bytes) + ",\"check_bytes\":" + std::to_string(check_bytes) +
+       ",\"cells\":" + std::to_string(opt.cells) + ",\"cache_hit_refs\":" + std::to_string(cache_hit_refs) +
+       ",\"cache_miss_refs\":" + std::to_string(cache_miss_refs) +
        ",\"u_slots\":" + std::to_string(n_u_slots) + ",\"f_slots\":" + std::to_string(n_f_slots) + "}";
   s += "}";
   meta_json = s;
@@ -1940,6 +2143,7 @@ void Compiler::write_program(const std::string& path) {
   h.stat_u_ops = stats.u_ops; h.stat_f_mul = stats.f_mul; h.stat_f_inv = stats.f_inv;
   h.stat_f_other = stats.f_other; h.stat_bigdiv = stats.bigdiv;
   h.reserved[0] = m.meta_json.size();
+  h.reserved[1] = m.opt.cells;
   uint64_t pos = 0;
   auto section = [&](const void* p, size_t n) { wr(f, p, n); pos += n; pad16(f, pos); };
   section(&h, sizeof h);

@@ -143,16 +143,46 @@ __device__ __forceinline__ void fr_neg(u64* r, const u64* a) {
   sub256(r, p, a);
 }
 
-// a^(p-2) by square-and-multiply, Montgomery in/out, inv(0) = 0 (circom: x/0 = 0)
+// Modular inverse, Montgomery in / out, inv(0) = 0 (circom run-time semantics: x / 0 = 0).
+// Binary extended Euclid on (u, v) = (a, p) with cofactors (x1, x2) mod p: about 380 shift / subtract
+// steps of 256-bit integer work (no multiplications) instead of the ~380 Montgomery products of a
+// Fermat ladder.  Input aR gives (aR)^-1 = a^-1 R^-1; one product with R^3 restores a^-1 R.
+__device__ __forceinline__ void shr1_256(u64* a) {
+  a[0] = (a[0] >> 1) | (a[1] << 63); a[1] = (a[1] >> 1) | (a[2] << 63);
+  a[2] = (a[2] >> 1) | (a[3] << 63); a[3] >>= 1;
+}
+__device__ __forceinline__ void half_mod_p(u64* x) {  // x/2 mod p for x in [0, p)
+  if (x[0] & 1) {
+    const u64 p[4] = {P0, P1, P2, P3};
+    u32 c = add256(x, x, p);  // < 2^255, carry is always 0 but keep it exact
+    shr1_256(x);
+    x[3] |= (u64)c << 63;
+  } else shr1_256(x);
+}
+__device__ __forceinline__ bool geq256(const u64* a, const u64* b) {
+  if (a[3] != b[3]) return a[3] > b[3];
+  if (a[2] != b[2]) return a[2] > b[2];
+  if (a[1] != b[1]) return a[1] > b[1];
+  return a[0] >= b[0];
+}
 __device__ __noinline__ void fr_inv(u64* r, const u64* a) {
-  const u64 e[4] = {P0 - 2, P1, P2, P3};
-  u64 acc[4] = {0xac96341c4ffffffbull, 0x36fc76959f60cd29ull, 0x666ea36f7879462eull, 0x0e0a77c19a07df2full};  // R
-  u64 base[4] = {a[0], a[1], a[2], a[3]};
-  for (int i = 0; i < 254; i++) {
-    if ((e[i >> 6] >> (i & 63)) & 1) fr_mul(acc, acc, base);
-    fr_mul(base, base, base);
+  if (fr_is_zero(a)) { r[0] = r[1] = r[2] = r[3] = 0; return; }
+  u64 u[4] = {a[0], a[1], a[2], a[3]};
+  u64 v[4] = {P0, P1, P2, P3};
+  u64 x1[4] = {1, 0, 0, 0}, x2[4] = {0, 0, 0, 0};
+  // invariants: x1 * a == u, x2 * a == v (mod p); gcd(a, p) = 1
+  while (!((u[0] == 1 && (u[1] | u[2] | u[3]) == 0) || (v[0] == 1 && (v[1] | v[2] | v[3]) == 0))) {
+    while (!(u[0] & 1)) { shr1_256(u); half_mod_p(x1); }
+    while (!(v[0] & 1)) { shr1_256(v); half_mod_p(x2); }
+    if (geq256(u, v)) { sub256(u, u, v); fr_sub(x1, x1, x2); }
+    else { sub256(v, v, u); fr_sub(x2, x2, x1); }
   }
-  r[0] = acc[0]; r[1] = acc[1]; r[2] = acc[2]; r[3] = acc[3];
+  const u64 r3[4] = {0x5e94d8e1b4bf0040ull, 0x2a489cbe1cfbb6b8ull, 0x893cc664a19fcfedull, 0x0cf8594b7fcc657cull};
+  const bool use1 = (u[0] == 1 && (u[1] | u[2] | u[3]) == 0);
+  u64 t[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) t[i] = use1 ? x1[i] : x2[i];
+  fr_mul(r, t, r3);
 }
 
 // ---- plain 256-bit integer helpers (class N) ----------------------------------------------

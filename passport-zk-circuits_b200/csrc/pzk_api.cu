@@ -48,6 +48,7 @@ struct pzk_circuit {
   std::string meta;
   std::vector<SegDev> seg;
   uint64_t bytes_per_lane = 0;
+  size_t smem_bytes = 0;
   // device copies
   uint4* d_ops = nullptr;
   u64* d_fpool = nullptr;
@@ -77,6 +78,8 @@ struct pzk_circuit {
   double prof_ms[4] = {0, 0, 0, 0};
   uint64_t prof_launches[4] = {0, 0, 0, 0};
   std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> pending;
+  std::vector<double> seg_ms;  // accumulated eval time per segment (profiling)
+  std::vector<int> pending_seg;
 };
 
 static void set_err(pzk_circuit* c, const std::string& m) { if (c) c->err = m; }
@@ -205,9 +208,11 @@ int pzk_circuit_open(const char* program_path, int cuda_device, pzk_circuit** ou
   if (pos + c->h.reserved[0] > (uint64_t)sz) { set_err(c, "truncated program file"); return PZK_EFORMAT; }
   c->meta.assign((const char*)(b + pos), c->h.reserved[0]);
   c->bytes_per_lane = (uint64_t)c->h.n_u_slots * 8 + (uint64_t)c->h.n_f_slots * 32;
+  c->smem_bytes = (size_t)c->h.reserved[1] * 8 * 128;
 
   CK(cudaSetDevice(cuda_device));
   CK(cudaStreamCreate(&c->stream));
+  if (c->smem_bytes > 48 * 1024) CK(cudaFuncSetAttribute(eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
   CK(upload(&c->d_ops, c->ops, c->h.n_op_records * sizeof(PzkOp)));
   CK(upload(&c->d_fpool, c->fpool, (size_t)c->h.n_fpool * 32));
   CK(upload(&c->d_coefs, c->coefs, (size_t)c->h.n_coef * sizeof(PzkCoef)));
@@ -291,15 +296,19 @@ static void prof_end(pzk_circuit* c, int which, cudaEvent_t a, cudaEvent_t b) {
   c->pending.push_back({which, {a, b}});
 }
 static void prof_collect(pzk_circuit* c) {
+  size_t evk = 0;
+  if (c->seg_ms.size() != c->h.n_segments) c->seg_ms.assign(c->h.n_segments, 0.0);
   for (auto& p : c->pending) {
     float ms = 0;
     cudaEventSynchronize(p.second.second);
     cudaEventElapsedTime(&ms, p.second.first, p.second.second);
     c->prof_ms[p.first] += ms;
     c->prof_launches[p.first] += 1;
+    if (p.first == 0 && evk < c->pending_seg.size()) c->seg_ms[c->pending_seg[evk++]] += ms;
     cudaEventDestroy(p.second.first); cudaEventDestroy(p.second.second);
   }
   c->pending.clear();
+  c->pending_seg.clear();
 }
 
 // run every tile of the resident batch; optional witness export for selected lanes
@@ -335,16 +344,18 @@ static int run_batch(pzk_circuit* c, int check_rows, const uint64_t* export_lane
         EvalParams p;
         p.ops = c->d_ops + sg.op_off; p.n_rec = sg.n_ops; p.U = c->d_U; p.F = c->d_F; p.L = L; p.n_lanes = n;
         p.fpool = c->d_fpool; p.list = c->d_list; p.inputs = c->d_inputs + base * c->h.n_inputs * 4;
-        p.n_inputs = c->h.n_inputs; p.status = c->d_status + base;
-        p.check_rows = check_rows; p.sc.coefs = c->d_coefs; p.sc.coef_kind = c->d_coef_kind; p.sc.coef_mag = c->d_coef_mag;
+        p.n_inputs = c->h.n_inputs; p.status = c->d_status + base; p.n_u_slots = c->h.n_u_slots; p.n_f_slots = c->h.n_f_slots;
+        p.check_rows = check_rows; p.store_all = (n_export > 0) ? 1 : 0; p.sc.coefs = c->d_coefs; p.sc.coef_kind = c->d_coef_kind; p.sc.coef_mag = c->d_coef_mag;
         p.first_bad = c->d_first_bad + base;
         prof_begin(c, 0, ea, eb);
-        eval_kernel<<<grid, 128, 0, c->stream>>>(p);
+        eval_kernel<<<grid, 128, c->smem_bytes, c->stream>>>(p);
         prof_end(c, 0, ea, eb);
+        if (c->prof) c->pending_seg.push_back((int)s);
       }
       if (!c->seg[s].pub.empty()) {
         ExportParams p;
         p.entries = c->d_pub_entries + c->seg[s].pub_off; p.n_entries = c->seg[s].pub.size();
+        p.n_u_slots = c->h.n_u_slots; p.n_f_slots = c->h.n_f_slots;
         p.U = c->d_U; p.F = c->d_F; p.L = L; p.lanes = nullptr; p.lane_base = base; p.n_rows = n;
         p.out = c->d_public; p.out_wires = n_pub; p.wire_off = 1;
         prof_begin(c, 2, ea, eb);
@@ -356,6 +367,7 @@ static int run_batch(pzk_circuit* c, int check_rows, const uint64_t* export_lane
         for (size_t q = 0; q < tile_lanes.size(); q++) {
           ExportParams p;
           p.entries = c->d_exports + sg.exp_off; p.n_entries = sg.n_exp;
+          p.n_u_slots = c->h.n_u_slots; p.n_f_slots = c->h.n_f_slots;
           p.U = c->d_U; p.F = c->d_F; p.L = L; p.lanes = d_lane_list + q; p.lane_base = tile_rows[q]; p.n_rows = 1;
           p.out = d_witnesses; p.out_wires = c->h.n_wires; p.wire_off = 0;
           unsigned gy = (unsigned)std::min<uint64_t>(std::max<uint64_t>(sg.n_exp / 128, 1), 1024);
@@ -461,7 +473,13 @@ int pzk_profile_get(pzk_circuit* c, int which, double* ms, uint64_t* launches) {
   if (launches) *launches = c->prof_launches[which];
   return PZK_OK;
 }
-void pzk_profile_reset(pzk_circuit* c) { for (int i = 0; i < 4; i++) { c->prof_ms[i] = 0; c->prof_launches[i] = 0; } }
+int pzk_profile_segments(pzk_circuit* c, double* ms, uint32_t n) {
+  if (!c || !ms) return PZK_EINVAL;
+  for (uint32_t i = 0; i < n; i++) ms[i] = i < c->seg_ms.size() ? c->seg_ms[i] : 0.0;
+  return (int)c->seg_ms.size();
+}
+void pzk_profile_reset(pzk_circuit* c) {
+  c->seg_ms.assign(c->seg_ms.size(), 0.0); for (int i = 0; i < 4; i++) { c->prof_ms[i] = 0; c->prof_launches[i] = 0; } }
 void pzk_profile_enable(pzk_circuit* c, int on) { c->prof = on != 0; }
 
 // ---------------------------------------------------------------------------------------

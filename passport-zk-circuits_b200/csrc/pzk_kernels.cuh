@@ -17,6 +17,8 @@
 
 namespace pzkd {
 
+#define PZK_LANE_BLOCK 128
+
 struct StreamCoefs {
   const PzkCoef* coefs;
   const unsigned char* coef_kind;
@@ -28,8 +30,9 @@ struct EvalParams {
   u64 n_rec;
   u64* U;
   u64* F;
-  u64 L;        // lane stride of the planes
+  u64 L;        // lanes in the tile (planes are blocked: [lane / 128][slot][lane % 128])
   u64 n_lanes;  // active lanes in this tile
+  u32 n_u_slots, n_f_slots;
   const u64* fpool;
   const u32* list;
   const u64* inputs;  // [lane][n_inputs][4]
@@ -37,12 +40,23 @@ struct EvalParams {
   u32* status;
   // fused constraint rows
   int check_rows;
+  int store_all;  // 1: every value reaches its global slot (witness export requested)
   StreamCoefs sc;
   unsigned long long* first_bad;
 };
 
 #define LDU(slot) (Ul[(u64)(slot) * L])
 #define STU(slot, v) (Ul[(u64)(slot) * L] = (v))
+// operand words: bit 31 -> shared-memory cell, else global slot (see pzk_program.h)
+#define CELLP(c) (cells + (u64)(c) * NT)
+#define LDO(x) (((x) & PZK_OPERAND_CELL) ? *CELLP((x) & 0xffffu) : Ul[(u64)(x) * L])
+// destination words: global slot always, cell when assigned
+#define STD(d, v)                                                        \
+  do {                                                                   \
+    const u64 v__ = (v);                                                 \
+    if (!((d) & PZK_DST_OPTIONAL) || store_all) Ul[(u64)PZK_DST_SLOT(d) * L] = v__; \
+    if (PZK_DST_CELL(d)) *CELLP(PZK_DST_CELL(d) - 1) = v__;               \
+  } while (0)
 
 __device__ __forceinline__ void ldF(const u64* Fl, u64 L, u32 slot, u64* v) {
   const u64* p = Fl + (u64)slot * 4 * L;
@@ -51,6 +65,19 @@ __device__ __forceinline__ void ldF(const u64* Fl, u64 L, u32 slot, u64* v) {
 __device__ __forceinline__ void stF(u64* Fl, u64 L, u32 slot, const u64* v) {
   u64* p = Fl + (u64)slot * 4 * L;
   p[0] = v[0]; p[L] = v[1]; p[2 * L] = v[2]; p[3 * L] = v[3];
+}
+__device__ __forceinline__ void ldFo(const u64* Fl, u64 L, const u64* cells, u32 NT, u32 x, u64* v) {
+  if (x & PZK_OPERAND_CELL) {
+    const u64* c = cells + (u64)(x & 0xffffu) * NT;
+    v[0] = c[0]; v[1] = c[NT]; v[2] = c[2 * NT]; v[3] = c[3 * NT];
+  } else ldF(Fl, L, x, v);
+}
+__device__ __forceinline__ void stFd(u64* Fl, u64 L, u64* cells, u32 NT, u32 d, const u64* v, bool store_all) {
+  if (!(d & PZK_DST_OPTIONAL) || store_all) stF(Fl, L, PZK_DST_SLOT(d), v);
+  if (PZK_DST_CELL(d)) {
+    u64* c = cells + (u64)(PZK_DST_CELL(d) - 1) * NT;
+    c[0] = v[0]; c[NT] = v[1]; c[2 * NT] = v[2]; c[3 * NT] = v[3];
+  }
 }
 __device__ __forceinline__ void ldPool(const u64* pool, u32 idx, u64* v) {
   const ulonglong2* p = reinterpret_cast<const ulonglong2*>(pool + 4 * (u64)idx);
@@ -315,28 +342,29 @@ __device__ __forceinline__ long long term_icoef(const u32* list, u32 ref, u32 cw
   return (long long)(int)cw;
 }
 // exact integer row: |A|,|B| < 2^63 and |C| < 2^126 proven by the compiler
+#define TERM_U(ref) (((ref) & PZK_TERM_CELL) ? cells[(u64)((ref) & 0xffffu) * NT] : Ul[(u64)PZK_REF_SLOT(ref) * L])
 __device__ __forceinline__ bool check_row_int(const uint4* recs, u32 na, u32 nb, u32 nc, const u32* list,
-                                              const u64* Ul, u64 L) {
+                                              const u64* Ul, u64 L, const u64* cells, u32 NT) {
   long long A = 0, B = 0;
   u64 Clo = 0, Chi = 0;
   u32 k = 0;
   for (u32 i = 0; i < na; i++, k++) {
     const uint2 t = row_term(recs, k);
     long long c = term_icoef(list, t.x, t.y);
-    long long v = (t.x >= PZK_REF_ONE_LIST) ? 1 : (long long)Ul[(u64)PZK_REF_SLOT(t.x) * L];
+    long long v = (t.x >= PZK_REF_ONE_LIST) ? 1 : (long long)TERM_U(t.x);
     A += c * v;
   }
   for (u32 i = 0; i < nb; i++, k++) {
     const uint2 t = row_term(recs, k);
     long long c = term_icoef(list, t.x, t.y);
-    long long v = (t.x >= PZK_REF_ONE_LIST) ? 1 : (long long)Ul[(u64)PZK_REF_SLOT(t.x) * L];
+    long long v = (t.x >= PZK_REF_ONE_LIST) ? 1 : (long long)TERM_U(t.x);
     B += c * v;
   }
   for (u32 i = 0; i < nc; i++, k++) {
     const uint2 t = row_term(recs, k);
     long long c = term_icoef(list, t.x, t.y);
     bool one = t.x >= PZK_REF_ONE_LIST;
-    u64 v = one ? 1ull : Ul[(u64)PZK_REF_SLOT(t.x) * L];
+    u64 v = one ? 1ull : TERM_U(t.x);
     bool vsigned = !one && PZK_REF_CLS(t.x) == 1;
     // 128-bit two's complement product c * v
     u64 lo = (u64)c * v;
@@ -356,7 +384,7 @@ __device__ __forceinline__ bool check_row_int(const uint4* recs, u32 na, u32 nb,
 }
 
 __device__ __noinline__ void lin_eval_stream(const StreamCoefs& sc, const uint4* recs, u32 k0, u32 n, const u64* Ul,
-                                             const u64* Fl, u64 L, LinVal& out) {
+                                             const u64* Fl, u64 L, const u64* cells, u32 NT, LinVal& out) {
   out.i.v[0] = out.i.v[1] = out.i.v[2] = 0;
   out.f[0] = out.f[1] = out.f[2] = out.f[3] = 0;
   out.has_f = false;
@@ -369,9 +397,14 @@ __device__ __noinline__ void lin_eval_stream(const StreamCoefs& sc, const uint4*
       else { u64 c[4]; ldPool(reinterpret_cast<const u64*>(sc.coefs), ci * 3 + 1, c); fr_add(out.f, out.f, c); out.has_f = true; }
       continue;
     }
-    const u32 cls = PZK_REF_CLS(ref), slot = PZK_REF_SLOT(ref);
+    const u32 cls = PZK_REF_CLS(ref);
+    if (ref & PZK_TERM_BIT) {  // proven bit: conditional add of the Montgomery coefficient
+      if (TERM_U(ref) & 1) { u64 c[4]; ldPool(reinterpret_cast<const u64*>(sc.coefs), ci * 3 + 1, c); fr_add(out.f, out.f, c); }
+      out.has_f = true;
+      continue;
+    }
     if (cls < 2) {
-      u64 v = Ul[(u64)slot * L];
+      u64 v = TERM_U(ref);
       bool vneg = (cls == 1) && ((long long)v < 0);
       u64 vm = vneg ? (u64)(-(long long)v) : v;
       if (kind) acc_mac(out.i, __ldg(sc.coef_mag + ci), vm, (kind == 2) != vneg);
@@ -384,7 +417,7 @@ __device__ __noinline__ void lin_eval_stream(const StreamCoefs& sc, const uint4*
       }
     } else {
       u64 w[4];
-      ldF(Fl, L, slot, w);
+      ldFo(Fl, L, cells, NT, (ref & PZK_TERM_CELL) ? (PZK_OPERAND_CELL | (ref & 0xffffu)) : PZK_REF_SLOT(ref), w);
       if (kind && __ldg(sc.coef_mag + ci) == 1) {
         if (kind == 1) fr_add(out.f, out.f, w); else fr_sub(out.f, out.f, w);
       } else {
@@ -398,15 +431,28 @@ __device__ __noinline__ void lin_eval_stream(const StreamCoefs& sc, const uint4*
   }
 }
 __device__ __noinline__ bool check_row_field(const StreamCoefs& sc, const uint4* recs, u32 na, u32 nb, u32 nc,
-                                             const u64* Ul, const u64* Fl, u64 L) {
+                                             const u64* Ul, const u64* Fl, u64 L, const u64* cells, u32 NT) {
   LinVal A, B, C;
-  lin_eval_stream(sc, recs, na + nb, nc, Ul, Fl, L, C);
+  lin_eval_stream(sc, recs, na + nb, nc, Ul, Fl, L, cells, NT, C);
   if (na == 0 || nb == 0) {
     if (!C.has_f) return acc_is_zero(C.i);
     u64 c[4]; lin_to_field(C, c); return fr_is_zero(c);
   }
-  lin_eval_stream(sc, recs, 0, na, Ul, Fl, L, A);
-  lin_eval_stream(sc, recs, na, nb, Ul, Fl, L, B);
+  lin_eval_stream(sc, recs, 0, na, Ul, Fl, L, cells, NT, A);
+  lin_eval_stream(sc, recs, na, nb, Ul, Fl, L, cells, NT, B);
+  if (!A.has_f && !B.has_f && acc_fits_i64(A.i) && acc_fits_i64(B.i)) {
+    // integer x integer: exact 128-bit product, one conversion instead of three field products
+    long long ia = (long long)A.i.v[0], ib = (long long)B.i.v[0];
+    bool neg = (ia < 0) != (ib < 0);
+    u64 am = ia < 0 ? (u64)(-ia) : (u64)ia, bm = ib < 0 ? (u64)(-ib) : (u64)ib;
+    Acc192 prod; prod.v[0] = prod.v[1] = prod.v[2] = 0;
+    acc_mac(prod, am, bm, neg);
+    if (!C.has_f) return prod.v[0] == C.i.v[0] && prod.v[1] == C.i.v[1] && prod.v[2] == C.i.v[2];
+    u64 pf[4], c[4];
+    acc_to_field(prod, pf);
+    lin_to_field(C, c);
+    return fr_eq(pf, c);
+  }
   u64 a[4], b[4], c[4], ab[4];
   lin_to_field(A, a); lin_to_field(B, b); lin_to_field(C, c);
   fr_mul(ab, a, b);
@@ -414,123 +460,154 @@ __device__ __noinline__ bool check_row_field(const StreamCoefs& sc, const uint4*
 }
 
 __global__ void __launch_bounds__(128) eval_kernel(EvalParams p) {
+  extern __shared__ u64 cell_mem[];
   const u64 lane = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   if (lane >= p.n_lanes) return;
-  const u64 L = p.L;
-  u64* Ul = p.U + lane;
-  u64* Fl = p.F + lane;
+  // Blocked planes: the 128 lanes of a CTA own one contiguous region per plane, so the hot slots of
+  // a CTA span a few 2 MB pages instead of one page per slot (the flat [slot][lane] layout was
+  // page-walk bound: consecutive ops touch slots that are megabytes apart).
+  const u64 L = PZK_LANE_BLOCK;
+  const u32 NT = blockDim.x;
+  u64* cells = cell_mem + threadIdx.x;
+  u64* Ul = p.U + (u64)blockIdx.x * p.n_u_slots * PZK_LANE_BLOCK + threadIdx.x;
+  u64* Fl = p.F + (u64)blockIdx.x * p.n_f_slots * 4 * PZK_LANE_BLOCK + threadIdx.x;
   u32 st = 0;
   unsigned long long bad = ~0ull;
+  const bool store_all = p.store_all != 0;
   for (u64 pc = 0; pc < p.n_rec; pc++) {
     const uint4 w = __ldg(p.ops + pc);
     const u32 opc = w.x & 0xffu, flags = (w.x >> 8) & 0xffu, imm16 = w.x >> 16;
     const u32 dst = w.y, a = w.z, b = w.w;
-    uint4 x = make_uint4(0, 0, 0, 0);
-    if (flags & PZK_FLAG_EXT) { pc++; x = __ldg(p.ops + pc); }
+#define FETCH_EXT() const uint4 x = __ldg(p.ops + (++pc))
+#define UBV ((flags & PZK_FLAG_B_IMM) ? (u64)b : LDO(b))
+#define LDFA(v) ldFo(Fl, L, cells, NT, a, v)
+#define LDFB(v) do { if (flags & PZK_FLAG_B_POOL) ldPool(p.fpool, b, v); else ldFo(Fl, L, cells, NT, b, v); } while (0)
+#define STFD(v) stFd(Fl, L, cells, NT, dst, v, store_all)
     switch (opc) {
       case PZK_NOP: break;
-      case PZK_U_CONST: STU(dst, ((u64)b << 32) | a); break;
-#define UBV ((flags & PZK_FLAG_B_IMM) ? (u64)b : LDU(b))
-      case PZK_U_ADD: STU(dst, LDU(a) + UBV); break;
-      case PZK_U_SUB: STU(dst, LDU(a) - UBV); break;
-      case PZK_U_MUL: STU(dst, LDU(a) * UBV); break;
-      case PZK_U_DIV: { u64 d = UBV; STU(dst, d ? LDU(a) / d : 0); break; }
-      case PZK_U_MOD: { u64 d = UBV; STU(dst, d ? LDU(a) % d : 0); break; }
-      case PZK_U_SHR: { u64 d = UBV; STU(dst, d >= 64 ? 0 : LDU(a) >> d); break; }
-      case PZK_U_SHL: { u64 d = UBV; STU(dst, d >= 64 ? 0 : LDU(a) << d); break; }
-      case PZK_U_AND: STU(dst, LDU(a) & UBV); break;
-      case PZK_U_OR: STU(dst, LDU(a) | UBV); break;
-      case PZK_U_XOR: STU(dst, LDU(a) ^ UBV); break;
-      case PZK_U_LT: STU(dst, (u64)(LDU(a) < UBV)); break;
-      case PZK_U_LE: STU(dst, (u64)(LDU(a) <= UBV)); break;
-      case PZK_U_EQ: STU(dst, (u64)(LDU(a) == UBV)); break;
-      case PZK_U_NE: STU(dst, (u64)(LDU(a) != UBV)); break;
-      case PZK_I_LT: STU(dst, (u64)((long long)LDU(a) < (long long)UBV)); break;
-      case PZK_I_LE: STU(dst, (u64)((long long)LDU(a) <= (long long)UBV)); break;
-      case PZK_U_SEL: STU(dst, LDU(a) ? LDU(b) : LDU(x.x)); break;
+      case PZK_U_CONST: STD(dst, ((u64)b << 32) | a); break;
+      case PZK_U_ADD: STD(dst, LDO(a) + UBV); break;
+      case PZK_U_SUB: STD(dst, LDO(a) - UBV); break;
+      case PZK_U_MUL: STD(dst, LDO(a) * UBV); break;
+      case PZK_U_DIV: { u64 d = UBV; STD(dst, d ? LDO(a) / d : 0); break; }
+      case PZK_U_MOD: { u64 d = UBV; STD(dst, d ? LDO(a) % d : 0); break; }
+      case PZK_U_SHR: { u64 d = UBV; STD(dst, d >= 64 ? 0 : LDO(a) >> d); break; }
+      case PZK_U_SHL: { u64 d = UBV; STD(dst, d >= 64 ? 0 : LDO(a) << d); break; }
+      case PZK_U_AND: STD(dst, LDO(a) & UBV); break;
+      case PZK_U_OR: STD(dst, LDO(a) | UBV); break;
+      case PZK_U_XOR: STD(dst, LDO(a) ^ UBV); break;
+      case PZK_U_LT: STD(dst, (u64)(LDO(a) < UBV)); break;
+      case PZK_U_LE: STD(dst, (u64)(LDO(a) <= UBV)); break;
+      case PZK_U_EQ: STD(dst, (u64)(LDO(a) == UBV)); break;
+      case PZK_U_NE: STD(dst, (u64)(LDO(a) != UBV)); break;
+      case PZK_I_LT: STD(dst, (u64)((long long)LDO(a) < (long long)UBV)); break;
+      case PZK_I_LE: STD(dst, (u64)((long long)LDO(a) <= (long long)UBV)); break;
+      case PZK_U_SEL: { FETCH_EXT(); STD(dst, LDO(a) ? LDO(b) : LDO(x.x)); break; }
       case PZK_U_LUT: case PZK_U_LUTV: {
+        FETCH_EXT();
         u32 idx = 0;
-        if (a != PZK_OPERAND_NONE) idx |= (u32)(LDU(a) & 1);
-        if (b != PZK_OPERAND_NONE) idx |= (u32)(LDU(b) & 1) << 1;
-        if (x.x != PZK_OPERAND_NONE) idx |= (u32)(LDU(x.x) & 1) << 2;
-        if (x.y != PZK_OPERAND_NONE) idx |= (u32)(LDU(x.y) & 1) << 3;
-        if (opc == PZK_U_LUT) STU(dst, (u64)((imm16 >> idx) & 1));
-        else STU(dst, (u64)__ldg(p.list + x.z + 2 * idx) | ((u64)__ldg(p.list + x.z + 2 * idx + 1) << 32));
+        if (a != PZK_OPERAND_NONE) idx |= (u32)(LDO(a) & 1);
+        if (b != PZK_OPERAND_NONE) idx |= (u32)(LDO(b) & 1) << 1;
+        if (x.x != PZK_OPERAND_NONE) idx |= (u32)(LDO(x.x) & 1) << 2;
+        if (x.y != PZK_OPERAND_NONE) idx |= (u32)(LDO(x.y) & 1) << 3;
+        if (opc == PZK_U_LUT) STD(dst, (u64)((imm16 >> idx) & 1));
+        else STD(dst, (u64)__ldg(p.list + x.z + 2 * idx) | ((u64)__ldg(p.list + x.z + 2 * idx + 1) << 32));
         break;
       }
-      case PZK_F_CONST: { u64 v[4]; ldPool(p.fpool, a, v); stF(Fl, L, dst, v); break; }
+      case PZK_F_CONST: { u64 v[4]; ldPool(p.fpool, a, v); STFD(v); break; }
       case PZK_F_ADD: case PZK_F_SUB: case PZK_F_MUL: {
         u64 va[4], vb[4], r[4];
-        ldF(Fl, L, a, va);
-        if (flags & PZK_FLAG_B_POOL) ldPool(p.fpool, b, vb); else ldF(Fl, L, b, vb);
+        LDFA(va); LDFB(vb);
         if (opc == PZK_F_ADD) fr_add(r, va, vb);
         else if (opc == PZK_F_SUB) fr_sub(r, va, vb);
         else fr_mul(r, va, vb);
-        stF(Fl, L, dst, r);
+        STFD(r);
         break;
       }
-      case PZK_F_NEG: { u64 va[4], r[4]; ldF(Fl, L, a, va); fr_neg(r, va); stF(Fl, L, dst, r); break; }
-      case PZK_F_INV: { u64 va[4], r[4]; ldF(Fl, L, a, va); fr_inv(r, va); stF(Fl, L, dst, r); break; }
-      case PZK_F_FROM_U: { u64 va[4] = {LDU(a), 0, 0, 0}, r[4]; fr_to_mont(r, va); stF(Fl, L, dst, r); break; }
+      case PZK_F_NEG: { u64 va[4], r[4]; LDFA(va); fr_neg(r, va); STFD(r); break; }
+      case PZK_F_INV: { u64 va[4], r[4]; LDFA(va); fr_inv(r, va); STFD(r); break; }
+      case PZK_F_FROM_U: { u64 va[4] = {LDO(a), 0, 0, 0}, r[4]; fr_to_mont(r, va); STFD(r); break; }
       case PZK_F_FROM_I: {
-        long long v = (long long)LDU(a);
+        long long v = (long long)LDO(a);
         u64 va[4] = {v < 0 ? (u64)(-v) : (u64)v, 0, 0, 0}, r[4];
         fr_to_mont(r, va);
         if (v < 0) fr_neg(r, r);
-        stF(Fl, L, dst, r);
+        STFD(r);
         break;
       }
-      case PZK_F_SEL: { u64 v[4]; ldF(Fl, L, LDU(a) ? b : x.x, v); stF(Fl, L, dst, v); break; }
+      case PZK_F_SEL: { FETCH_EXT(); u64 v[4]; ldFo(Fl, L, cells, NT, LDO(a) ? b : x.x, v); STFD(v); break; }
       case PZK_F_EQ: case PZK_F_NE: {
         u64 va[4], vb[4];
-        ldF(Fl, L, a, va);
-        if (flags & PZK_FLAG_B_POOL) ldPool(p.fpool, b, vb); else ldF(Fl, L, b, vb);
+        LDFA(va); LDFB(vb);
         bool eq = fr_eq(va, vb);
-        STU(dst, (u64)(opc == PZK_F_EQ ? eq : !eq));
+        STD(dst, (u64)(opc == PZK_F_EQ ? eq : !eq));
         break;
       }
-      case PZK_F_CSEL: { u64 v[4]; ldPool(p.fpool, b + (u32)LDU(a), v); stF(Fl, L, dst, v); break; }
-      case PZK_N_FROM_F: { u64 va[4], r[4]; ldF(Fl, L, a, va); fr_from_mont(r, va); stF(Fl, L, dst, r); break; }
-      case PZK_F_FROM_N: { u64 va[4], r[4]; ldF(Fl, L, a, va); reduce_p(va); fr_to_mont(r, va); stF(Fl, L, dst, r); break; }
-      case PZK_N_FROM_U: { u64 v[4] = {LDU(a), 0, 0, 0}; stF(Fl, L, dst, v); break; }
+      case PZK_F_CSEL: { u64 v[4]; ldPool(p.fpool, b + (u32)LDO(a), v); STFD(v); break; }
+      case PZK_N_FROM_F: { u64 va[4], r[4]; LDFA(va); fr_from_mont(r, va); STFD(r); break; }
+      case PZK_F_FROM_N: { u64 va[4], r[4]; LDFA(va); reduce_p(va); fr_to_mont(r, va); STFD(r); break; }
+      case PZK_N_FROM_U: { u64 v[4] = {LDO(a), 0, 0, 0}; STFD(v); break; }
       case PZK_N_BIT: {
-        u64 limb = (b < 256) ? Fl[((u64)a * 4 + (b >> 6)) * L] : 0;
-        STU(dst, (limb >> (b & 63)) & 1);
+        u64 limb = 0;
+        if (b < 256) limb = (a & PZK_OPERAND_CELL) ? *CELLP((a & 0xffffu) + (b >> 6)) : Fl[((u64)a * 4 + (b >> 6)) * L];
+        STD(dst, (limb >> (b & 63)) & 1);
         break;
       }
-      case PZK_N_LOW: STU(dst, Fl[(u64)a * 4 * L]); break;
-      case PZK_N_FITS: { u64 v[4]; ldF(Fl, L, a, v); STU(dst, (u64)((v[1] | v[2] | v[3]) == 0)); break; }
-      case PZK_N_SHR: { u64 v[4], r[4]; ldF(Fl, L, a, v); u64 d = UBV; shr256(r, v, d > 256 ? 256u : (unsigned)d); stF(Fl, L, dst, r); break; }
+      case PZK_N_LOW: STD(dst, (a & PZK_OPERAND_CELL) ? *CELLP(a & 0xffffu) : Fl[(u64)a * 4 * L]); break;
+      case PZK_N_FITS: { u64 v[4]; LDFA(v); STD(dst, (u64)((v[1] | v[2] | v[3]) == 0)); break; }
+      case PZK_N_SHR: { u64 v[4], r[4]; LDFA(v); u64 d = UBV; shr256(r, v, d > 256 ? 256u : (unsigned)d); STFD(r); break; }
       case PZK_N_SHL: {
-        u64 v[4], r[4] = {0, 0, 0, 0}; ldF(Fl, L, a, v); u64 d = UBV;
+        u64 v[4], r[4] = {0, 0, 0, 0}; LDFA(v); u64 d = UBV;
         if (d < 254) { shl256(r, v, (unsigned)d); r[3] &= 0x3fffffffffffffffull; reduce_p(r); }
-        stF(Fl, L, dst, r); break;
+        STFD(r); break;
       }
       case PZK_N_AND: case PZK_N_OR: case PZK_N_XOR: {
         u64 va[4], vb[4], r[4];
-        ldF(Fl, L, a, va);
-        if (flags & PZK_FLAG_B_POOL) ldPool(p.fpool, b, vb); else ldF(Fl, L, b, vb);
+        LDFA(va); LDFB(vb);
 #pragma unroll
         for (int i = 0; i < 4; i++) r[i] = opc == PZK_N_AND ? (va[i] & vb[i]) : opc == PZK_N_OR ? (va[i] | vb[i]) : (va[i] ^ vb[i]);
         r[3] &= 0x3fffffffffffffffull;
         reduce_p(r);
-        stF(Fl, L, dst, r);
+        STFD(r);
         break;
       }
       case PZK_N_DIV: case PZK_N_MOD: {
         u64 va[4], vb[4], r[4];
-        ldF(Fl, L, a, va);
-        if (flags & PZK_FLAG_B_POOL) ldPool(p.fpool, b, vb); else ldF(Fl, L, b, vb);
+        LDFA(va); LDFB(vb);
         if (opc == PZK_N_DIV) divmod256(va, vb, r, nullptr); else divmod256(va, vb, nullptr, r);
-        stF(Fl, L, dst, r);
+        STFD(r);
         break;
       }
       case PZK_N_SLT: case PZK_N_SLE: {
         u64 va[4], vb[4];
-        ldF(Fl, L, a, va);
-        if (flags & PZK_FLAG_B_POOL) ldPool(p.fpool, b, vb); else ldF(Fl, L, b, vb);
+        LDFA(va); LDFB(vb);
         int c = scmp256(va, vb);
-        STU(dst, (u64)(opc == PZK_N_SLT ? c < 0 : c <= 0));
+        STD(dst, (u64)(opc == PZK_N_SLT ? c < 0 : c <= 0));
+        break;
+      }
+      case PZK_CHECK_I64: {
+        // |A|,|B|,|A*B|,|C| < 2^63 proven at compile time: wrapping 64-bit arithmetic is exact
+        if (p.check_rows) {
+          const uint4* recs = p.ops + pc + 1;
+          const u32 na = imm16, nab = na + (a & 0xffffu), tot = nab + (a >> 16);
+          long long A = 0, B = 0, C = 0;
+          for (u32 k = 0; k < tot; k += 2) {
+            const uint4 t = __ldg(recs + (k >> 1));
+            {
+              long long v = (t.x >= PZK_REF_ONE_LIST) ? 1ll : (long long)TERM_U(t.x);
+              long long m = (long long)(int)t.y * v;
+              if (k < na) A += m; else if (k < nab) B += m; else C += m;
+            }
+            if (k + 1 < tot) {
+              long long v = (t.z >= PZK_REF_ONE_LIST) ? 1ll : (long long)TERM_U(t.z);
+              long long m = (long long)(int)t.w * v;
+              if (k + 1 < na) A += m; else if (k + 1 < nab) B += m; else C += m;
+            }
+          }
+          const bool ok = (na == 0 || nab == na) ? (C == 0) : (A * B == C);
+          if (!ok && (unsigned long long)dst < bad) bad = dst;
+        }
+        pc += b;
         break;
       }
       case PZK_CHECK_INT: case PZK_CHECK_F: {
@@ -538,20 +615,20 @@ __global__ void __launch_bounds__(128) eval_kernel(EvalParams p) {
         if (p.check_rows) {
           const uint4* recs = p.ops + pc + 1;
           const u32 na = imm16, nb = a & 0xffffu, nc = a >> 16;
-          bool ok = (opc == PZK_CHECK_INT) ? check_row_int(recs, na, nb, nc, p.list, Ul, L)
-                                           : check_row_field(p.sc, recs, na, nb, nc, Ul, Fl, L);
+          bool ok = (opc == PZK_CHECK_INT) ? check_row_int(recs, na, nb, nc, p.list, Ul, L, cells, NT)
+                                           : check_row_field(p.sc, recs, na, nb, nc, Ul, Fl, L, cells, NT);
           if (!ok && (unsigned long long)dst < bad) bad = dst;
         }
         pc += n_rec;
         break;
       }
       case PZK_BIGDIV: st |= bigdiv_device(p.list + a, Ul, L); break;
-      case PZK_ASSERT_NZ: if (LDU(a) == 0) st |= PZK_LANE_ASSERT; break;
+      case PZK_ASSERT_NZ: if (LDO(a) == 0) st |= PZK_LANE_ASSERT; break;
       case PZK_IN_U: {
         const ulonglong2* ip = reinterpret_cast<const ulonglong2*>(p.inputs + ((u64)lane * p.n_inputs + a) * 4);
         ulonglong2 lo = ip[0], hi = ip[1];
         if ((lo.y | hi.x | hi.y) != 0 || (imm16 < 64 && (lo.x >> imm16) != 0)) st |= PZK_LANE_INPUT_RANGE;
-        STU(dst, lo.x);
+        STD(dst, lo.x);
         break;
       }
       case PZK_IN_F: {
@@ -560,7 +637,7 @@ __global__ void __launch_bounds__(128) eval_kernel(EvalParams p) {
         u64 v[4] = {lo.x, lo.y, hi.x, hi.y}, r[4];
         if (geq_p(v)) { st |= PZK_LANE_INPUT_RANGE; reduce_p(v); }
         fr_to_mont(r, v);
-        stF(Fl, L, dst, r);
+        STFD(r);
         break;
       }
       default: st |= 0x80000000u; break;
@@ -578,6 +655,7 @@ __global__ void __launch_bounds__(128) eval_kernel(EvalParams p) {
 // grid.x covers lanes (fast, coalesced plane reads), grid.y strides over entries.
 // ------------------------------------------------------------------------------------------
 struct ExportParams {
+  u32 n_u_slots, n_f_slots;  // blocked planes (0 = flat layout with stride L)
   const PzkExport* entries;
   u64 n_entries;
   const u64* U;
@@ -603,9 +681,11 @@ __global__ void __launch_bounds__(128) export_kernel(ExportParams p) {
     if (ref == PZK_REF_ONE) w[0] = 1;
     else if (ref != PZK_REF_ZERO) {
       const u32 cls = PZK_REF_CLS(ref), slot = PZK_REF_SLOT(ref);
-      if (cls == 2) { u64 m[4]; ldF(p.F + lane, L, slot, m); fr_from_mont(w, m); }
+      const u64* Ub = p.U + (lane / PZK_LANE_BLOCK) * p.n_u_slots * PZK_LANE_BLOCK + (lane % PZK_LANE_BLOCK);
+      const u64* Fb = p.F + (lane / PZK_LANE_BLOCK) * p.n_f_slots * 4 * PZK_LANE_BLOCK + (lane % PZK_LANE_BLOCK);
+      if (cls == 2) { u64 m[4]; ldF(Fb, PZK_LANE_BLOCK, slot, m); fr_from_mont(w, m); }
       else {
-        u64 v = p.U[(u64)slot * L + lane];
+        u64 v = Ub[(u64)slot * PZK_LANE_BLOCK];
         if (cls == 1 && (long long)v < 0) { const u64 pp[4] = {P0, P1, P2, P3}; u64 m[4] = {(u64)(-(long long)v), 0, 0, 0}; sub256(w, pp, m); }
         else w[0] = v;
       }
@@ -627,9 +707,11 @@ __global__ void __launch_bounds__(128) export_rows_kernel(ExportParams p) {
     if (ref == PZK_REF_ONE) w[0] = 1;
     else if (ref != PZK_REF_ZERO) {
       const u32 cls = PZK_REF_CLS(ref), slot = PZK_REF_SLOT(ref);
-      if (cls == 2) { u64 m[4]; ldF(p.F + lane, L, slot, m); fr_from_mont(w, m); }
+      const u64* Ub = p.U + (lane / PZK_LANE_BLOCK) * p.n_u_slots * PZK_LANE_BLOCK + (lane % PZK_LANE_BLOCK);
+      const u64* Fb = p.F + (lane / PZK_LANE_BLOCK) * p.n_f_slots * 4 * PZK_LANE_BLOCK + (lane % PZK_LANE_BLOCK);
+      if (cls == 2) { u64 m[4]; ldF(Fb, PZK_LANE_BLOCK, slot, m); fr_from_mont(w, m); }
       else {
-        u64 v = p.U[(u64)slot * L + lane];
+        u64 v = Ub[(u64)slot * PZK_LANE_BLOCK];
         if (cls == 1 && (long long)v < 0) { const u64 pp[4] = {P0, P1, P2, P3}; u64 m[4] = {(u64)(-(long long)v), 0, 0, 0}; sub256(w, pp, m); }
         else w[0] = v;
       }

@@ -15,6 +15,7 @@ int main(int argc, char** argv) {
       if (k == std::string::npos) { fprintf(stderr, "bad --bits\n"); return 2; }
       opt.input_bits[s.substr(0, k)] = atoi(s.c_str() + k + 1);
     } else if (!strcmp(argv[i], "--seg") && i + 1 < argc) opt.seg_ops = (uint32_t)atoi(argv[++i]);
+    else if (!strcmp(argv[i], "--cells") && i + 1 < argc) opt.cells = (uint32_t)atoi(argv[++i]);
     else if (!strcmp(argv[i], "--no-intrinsics")) opt.intrinsics = false;
     else { fprintf(stderr, "unknown option %s\n", argv[i]); return 2; }
   }

@@ -5,6 +5,7 @@ from passport_zk_circuits_b200 import witness as W
 from passport_zk_circuits_b200.passports import C3, PassportFactory
 name = sys.argv[1]; B = int(sys.argv[2])
 calc = W.WitnessCalculator(W.artifact(name), 0)
+name = "c3" if name.startswith("c3") else name
 print(name, 'wires', calc.n_wires, 'constraints', calc.n_constraints, calc.stats())
 if name == 'c3':
     fac = PassportFactory(C3, seed=1, n_sig_keys=2, n_aa_keys=2)
@@ -20,5 +21,18 @@ for it in range(3):
     t = time.time(); calc.run(True); dt = time.time() - t
     pr = calc.profile(); calc.profile(reset=True)
     print('run', it, 'lanes', B, 'tile', calc.tile_lanes(), 'sec', round(dt, 4), 'witness/s', round(B / dt, 1), {k: (round(v[0], 1), v[1]) for k, v in pr.items()})
+import ctypes
+nseg = calc.meta['stats']['segments']
+arr = (ctypes.c_double * nseg)()
+calc.profile(enable=True, reset=True); calc.run(True)
+calc._L.pzk_profile_segments.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double), ctypes.c_uint32]
+calc._L.pzk_profile_segments(calc._h, arr, nseg)
+seg = list(arr); tot = sum(seg)
+print('segments', nseg, 'total ms', round(tot, 1))
+import statistics
+print('median seg ms', round(statistics.median(seg), 2), 'top:', sorted([(round(v, 1), i) for i, v in enumerate(seg)], reverse=True)[:25])
+buckets = {}
+for i, v in enumerate(seg): buckets[i * 20 // nseg] = buckets.get(i * 20 // nseg, 0) + v
+print('by 5% of program:', [round(buckets.get(k, 0)) for k in range(20)])
 res = calc.download()
 print('status ok', int((res.status == 0).sum()), 'of', B)

@@ -39,6 +39,11 @@ def test_c3_batch_vs_oracle(c3):
             if not np.array_equal(got, wit):
                 idx = np.nonzero((got != wit).any(axis=1))[0]
                 raise AssertionError(f"lane {b}: {len(idx)} wires differ, first {idx[:5]}")
+    # the same batch without witness export takes the lean path (values that never leave the
+    # shared-memory operand cache are not stored to HBM): identical verdicts and public signals
+    res2 = calc.calculateWitnessBatch(inp)
+    assert np.array_equal(res2.status, res.status) and np.array_equal(res2.first_bad, res.first_bad)
+    assert np.array_equal(res2.public, res.public)
     ok = np.ones(B, dtype=bool)
     ok[[5, 9]] = False
     assert (res.status[ok] == 0).all()

@@ -36,6 +36,9 @@ def run_and_compare(name, inp, export=None, tile=None):
             if not np.array_equal(got, wit):
                 idx = np.nonzero((got != wit).any(axis=1))[0]
                 raise AssertionError(f"{name} lane {b}: {len(idx)} wires differ, first {idx[:5]}")
+    lean = calc.calculateWitnessBatch(inp)      # no export: optional global stores are skipped
+    assert np.array_equal(lean.status, res.status) and np.array_equal(lean.first_bad, res.first_bad)
+    assert np.array_equal(lean.public, res.public)
     calc.close()
     return res
 
@@ -130,8 +133,12 @@ def test_operator_surface_and_wtns_check(tmp_path):
         with pytest.raises(W.PzkError, match="Constraint doesn't match"):
             circuit.checkConstraints(bad)
     # an input that violates a constraint -> "Assert Failed." like the wasm
+    with pytest.raises(W.PzkError, match="declared range"):
+        circuit.calculateWitness(dict(inp, u=[5, 7, 70000, 13]))   # u is declared 16 bits wide
+    smt = W.WitnessCalculator(W.artifact("smt80"), 0)
     with pytest.raises(W.PzkError, match="Assert Failed"):
-        circuit.calculateWitness(dict(inp, u=[5, 7, 70000, 13]))   # u[2]+1 does not fit the 17-bit compare
+        # last sibling must be zero: (isZero[N-1].out - 1) === 0 fails -> the wasm throws "Assert Failed."
+        smt.calculateWitness({"root": 1, "leaf": 2, "key": 2, "siblings": [0] * 79 + [5]})
     with pytest.raises(W.PzkError, match="Curve of the witness"):
         W.wtns_check(prefix + ".r1cs", blob[:28] + bytes(32) + blob[60:])
 
