@@ -196,12 +196,114 @@ struct Compiler::Impl {
     v_convF.push_back(0); v_convN.push_back(0); v_def.push_back((uint32_t)ops.size()); v_const.push_back(0);
     return id;
   }
+  // ---- batched inversion (Montgomery's trick), decided at compile time ----------------------
+  // F_INV results are placeholders until some emitted op needs one of them (or the queue is
+  // full); then the whole queue is materialised with ONE field inversion and 3 products per
+  // element.  inv(0) = 0 is preserved: zeros are replaced by 1 inside the product chain and the
+  // corresponding results forced back to 0.
+  std::vector<std::pair<uint32_t, uint32_t>> pending_inv;  // (operand value, placeholder result)
+  std::vector<uint8_t> v_pending;
+  std::vector<OpRec> deferred;
+  std::vector<uint32_t> deferred_defs;
+  std::vector<std::pair<uint32_t, uint32_t>> deferred_lutv;
+  uint32_t pending_lutv_off = 0;
+  bool flushing = false;
+  static const size_t INV_BATCH = 8;
+  bool op_reads_values(int opc) {
+    switch (opc) { case PZK_NOP: case PZK_U_CONST: case PZK_F_CONST: case PZK_IN_U: case PZK_IN_F: case PZK_BIGDIV: return false; }
+    return true;
+  }
+  bool is_pending(uint32_t v) { return v != PZK_OPERAND_NONE && v < v_pending.size() && v_pending[v]; }
   uint32_t emit(int opc, uint32_t dst, uint32_t a = 0, uint32_t b = 0, int flags = 0, int imm16 = 0,
                 uint32_t c = PZK_OPERAND_NONE, uint32_t d = PZK_OPERAND_NONE) {
+    if (!flushing && !pending_inv.empty() && op_reads_values(opc)) {
+      bool need = is_pending(a);
+      bool b_is_value = !(flags & (PZK_FLAG_B_IMM | PZK_FLAG_B_POOL)) && opc != PZK_N_BIT && opc != PZK_F_CSEL;
+      if (b_is_value && is_pending(b)) need = true;
+      if (is_pending(c) || is_pending(d)) need = true;
+      if (need) {
+        // the op depends on a queued inversion: defer it (and transitively its users) so that
+        // further independent inversions can join the batch
+        OpRec o; o.opc = (uint8_t)opc; o.flags = (uint8_t)flags; o.imm16 = (uint16_t)imm16;
+        o.dst = dst; o.a = a; o.b = b; o.c = c; o.d = d;
+        deferred.push_back(o);
+        if (opc == PZK_U_LUTV) deferred_lutv.push_back({(uint32_t)deferred.size() - 1, pending_lutv_off});
+        if (dst && opc != PZK_ASSERT_NZ) {
+          if (v_pending.size() <= dst) v_pending.resize(dst + 1024, 0);
+          v_pending[dst] = 1;
+          deferred_defs.push_back(dst);
+        }
+        if (deferred.size() > 8192) flush_inversions();
+        return dst;
+      }
+    }
     OpRec o; o.opc = (uint8_t)opc; o.flags = (uint8_t)flags; o.imm16 = (uint16_t)imm16;
     o.dst = dst; o.a = a; o.b = b; o.c = c; o.d = d;
+    if (dst && opc != PZK_ASSERT_NZ && opc != PZK_BIGDIV && dst < v_def.size()) v_def[dst] = (uint32_t)ops.size();
     ops.push_back(o);
     return dst;
+  }
+  uint32_t queue_inversion(uint32_t x) {
+    if (is_pending(x)) flush_inversions();
+    uint32_t r = new_value(CLS_F);
+    if (v_pending.size() <= r) v_pending.resize(r + 1024, 0);
+    v_pending[r] = 1;
+    pending_inv.emplace_back(x, r);
+    stats->f_inv++;
+    if (pending_inv.size() >= INV_BATCH) flush_inversions();
+    return r;
+  }
+  void flush_inversions() {
+    if (pending_inv.empty()) return;
+    flushing = true;
+    std::vector<std::pair<uint32_t, uint32_t>> q;
+    q.swap(pending_inv);
+    for (auto& pr : q) v_pending[pr.second] = 0;
+    size_t n = q.size();
+    if (n == 1) {
+      emit(PZK_F_INV, q[0].second, q[0].first);
+      stats->f_inv_real++;
+    } else {
+      uint32_t one = pool_mont(U256(1)), zero = pool_mont(U256());
+      std::vector<uint32_t> isz(n), xs(n), pre(n);
+      for (size_t i = 0; i < n; i++) {
+        isz[i] = new_value(CLS_U, 0, 1);
+        emit(PZK_F_EQ, isz[i], q[i].first, zero, PZK_FLAG_B_POOL);
+        uint32_t c1 = const_value_F(U256(1));
+        xs[i] = new_value(CLS_F);
+        emit(PZK_F_SEL, xs[i], isz[i], c1, PZK_FLAG_EXT, 0, q[i].first);
+        if (i == 0) pre[0] = xs[0];
+        else { pre[i] = new_value(CLS_F); emit(PZK_F_MUL, pre[i], pre[i - 1], xs[i]); stats->f_mul++; }
+      }
+      (void)one;
+      uint32_t acc = new_value(CLS_F);
+      emit(PZK_F_INV, acc, pre[n - 1]);
+      stats->f_inv_real++;
+      uint32_t c0 = const_value_F(U256());
+      for (size_t i = n; i-- > 0;) {
+        uint32_t inv_i;
+        if (i == 0) inv_i = acc;
+        else {
+          inv_i = new_value(CLS_F); emit(PZK_F_MUL, inv_i, acc, pre[i - 1]); stats->f_mul++;
+          uint32_t nacc = new_value(CLS_F); emit(PZK_F_MUL, nacc, acc, xs[i]); stats->f_mul++;
+          acc = nacc;
+        }
+        emit(PZK_F_SEL, q[i].second, isz[i], c0, PZK_FLAG_EXT, 0, inv_i);
+      }
+    }
+    // now the deferred dependants, in their original order
+    std::vector<OpRec> dq; dq.swap(deferred);
+    std::vector<std::pair<uint32_t, uint32_t>> lq; lq.swap(deferred_lutv);
+    for (uint32_t d : deferred_defs) v_pending[d] = 0;
+    deferred_defs.clear();
+    size_t li = 0;
+    for (size_t k = 0; k < dq.size(); k++) {
+      const OpRec& o = dq[k];
+      if (o.dst && o.opc != PZK_ASSERT_NZ && o.opc != PZK_BIGDIV && o.dst < v_def.size()) v_def[o.dst] = (uint32_t)ops.size();
+      ops.push_back(o);
+      if (li < lq.size() && lq[li].first == k) { lutv_off[(uint32_t)ops.size() - 1] = lq[li].second; li++; }
+    }
+    flushing = false;
   }
   uint32_t pool_mont(const U256& c) {
     auto it = fpool_mont.find(c);
@@ -374,10 +476,10 @@ struct Compiler::Impl {
         uint64_t v = (uint64_t)t.e[i & ((1 << t.n) - 1)];
         list_pool.push_back((uint32_t)v); list_pool.push_back((uint32_t)(v >> 32));
       }
+      pending_lutv_off = off;
+      size_t before = ops.size();
       emit(PZK_U_LUTV, id, s[0], s[1], PZK_FLAG_EXT, 0, s[2], s[3]);
-      ops.back().imm16 = 0;
-      // ext.e carries the list offset: stash it in a side field by reusing opc-specific storage
-      lutv_off[(uint32_t)ops.size() - 1] = off;
+      if (ops.size() > before && ops.back().opc == PZK_U_LUTV && ops.back().dst == id) lutv_off[(uint32_t)ops.size() - 1] = off;
     }
     stats->lut++;
     return id;
@@ -542,9 +644,7 @@ struct Compiler::Impl {
       case O_DIV: {
         // a / b = a * inv(b), inv(0) = 0
         uint32_t ib = to_F(b);
-        uint32_t inv = new_value(CLS_F);
-        emit(PZK_F_INV, inv, ib);
-        stats->f_inv++;
+        uint32_t inv = queue_inversion(ib);
         if (a.kind == 0 && a.c == U256(1)) return sv(inv);
         return emit_f(PZK_F_MUL, sv(inv), a);
       }
@@ -605,7 +705,7 @@ struct Compiler::Impl {
           const SVal* wide = nullptr; const SVal* msk = nullptr;
           if (b.kind == 0) { wide = &a; msk = &b; } else if (a.kind == 0) { wide = &b; msk = &a; }
           if (wide && msk->c.fits64()) {
-            if (msk->c.w[0] == 1 && wide->kind == 1 && v_cls[wide->id] == CLS_N) {
+            if (msk->c.w[0] == 1 && wide->kind == 1 && v_cls[wide->id] == CLS_N && !is_pending(wide->id)) {
               const OpRec& d = ops[v_def[wide->id]];
               if (d.opc == PZK_N_SHR && (d.flags & PZK_FLAG_B_IMM) && d.dst == wide->id && d.b < 256) {
                 uint32_t id = new_value(CLS_U, 0, 1);
@@ -1207,6 +1307,8 @@ struct Compiler::Impl {
     std::vector<uint32_t> ids;
     for (uint64_t i = 0; i < k + m; i++) { i128 hi; const SVal& s = args[3].a->v[i]; if (!exact_u(s, hi) || hi > lim) return false; }
     for (uint64_t i = 0; i < k; i++) { i128 hi; const SVal& s = args[4].a->v[i]; if (!exact_u(s, hi) || hi > lim) return false; }
+    for (uint64_t i = 0; i < k + m; i++) if (args[3].a->v[i].kind == 1 && is_pending(args[3].a->v[i].id)) flush_inversions();
+    for (uint64_t i = 0; i < k; i++) if (args[4].a->v[i].kind == 1 && is_pending(args[4].a->v[i].id)) flush_inversions();
     uint32_t off = (uint32_t)list_pool.size();
     list_pool.push_back((uint32_t)n); list_pool.push_back((uint32_t)k); list_pool.push_back((uint32_t)m);
     for (uint64_t i = 0; i < k + m; i++) list_pool.push_back(u_operand(args[3].a->v[i]));
@@ -1225,6 +1327,7 @@ struct Compiler::Impl {
       out.a->v[200 + i] = sv(id);
     }
     emit(PZK_BIGDIV, first, off, 0);
+    for (uint64_t i = 0; i < (m + 1) + k; i++) v_def[list_pool[off + 3 + (k + m) + k + i]] = (uint32_t)ops.size() - 1;
     stats->bigdiv++;
     (void)at;
     return true;
@@ -1560,6 +1663,7 @@ struct Compiler::Impl {
     comps.push_back(main);
     main->lay = main_lay; main->base = 0; main->pending = 0; main->parent = nullptr;
     run_comp(main, nullptr);
+    flush_inversions();
     stats->n_constraints = rows.size();
     stats->n_values = v_cls.size();
   }
@@ -2088,7 +2192,7 @@ void Compiler::Impl::build_meta() {
   s += "],\"n_pub_out\":" + std::to_string(n_pub_out) + ",\"n_pub_in\":" + std::to_string(n_pub_in) +
        ",\"n_prv_in\":" + std::to_string(n_prv_in);
   s += ",\"stats\":{\"u_ops\":" + std::to_string(stats->u_ops) + ",\"f_mul\":" + std::to_string(stats->f_mul) +
-       ",\"f_inv\":" + std::to_string(stats->f_inv) + ",\"f_other\":" + std::to_string(stats->f_other) +
+       ",\"f_inv\":" + std::to_string(stats->f_inv) + ",\"f_inv_real\":" + std::to_string(stats->f_inv_real) + ",\"f_other\":" + std::to_string(stats->f_other) +
        ",\"bigdiv\":" + std::to_string(stats->bigdiv) + ",\"lut\":" + std::to_string(stats->lut) +
        ",\"op_records\":" + std::to_string(out_ops.size()) + ",\"segments\":" + std::to_string(segs.size()) +
        ",\"static_rows\":" + std::to_string(n_static_rows) + ",\"i64_rows\":" + std::to_string(n_i64_rows) +

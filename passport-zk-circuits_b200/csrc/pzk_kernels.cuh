@@ -383,7 +383,7 @@ __device__ __forceinline__ bool check_row_int(const uint4* recs, u32 na, u32 nb,
   return plo == Clo && phi == Chi;
 }
 
-__device__ __noinline__ void lin_eval_stream(const StreamCoefs& sc, const uint4* recs, u32 k0, u32 n, const u64* Ul,
+__device__ __noinline__ void lin_eval_stream(const StreamCoefs sc, const uint4* recs, u32 k0, u32 n, const u64* Ul,
                                              const u64* Fl, u64 L, const u64* cells, u32 NT, LinVal& out) {
   out.i.v[0] = out.i.v[1] = out.i.v[2] = 0;
   out.f[0] = out.f[1] = out.f[2] = out.f[3] = 0;
@@ -430,7 +430,7 @@ __device__ __noinline__ void lin_eval_stream(const StreamCoefs& sc, const uint4*
     }
   }
 }
-__device__ __noinline__ bool check_row_field(const StreamCoefs& sc, const uint4* recs, u32 na, u32 nb, u32 nc,
+__device__ __noinline__ bool check_row_field(const StreamCoefs sc, const uint4* recs, u32 na, u32 nb, u32 nc,
                                              const u64* Ul, const u64* Fl, u64 L, const u64* cells, u32 NT) {
   LinVal A, B, C;
   lin_eval_stream(sc, recs, na + nb, nc, Ul, Fl, L, cells, NT, C);
@@ -473,15 +473,23 @@ __global__ void __launch_bounds__(128) eval_kernel(EvalParams p) {
   u64* Fl = p.F + (u64)blockIdx.x * p.n_f_slots * 4 * PZK_LANE_BLOCK + threadIdx.x;
   u32 st = 0;
   unsigned long long bad = ~0ull;
+  // kernel parameters are copied into registers once: taking references to the parameter block
+  // would push it to local memory and turn every use into an LDL
   const bool store_all = p.store_all != 0;
-  for (u64 pc = 0; pc < p.n_rec; pc++) {
-    const uint4 w = __ldg(p.ops + pc);
+  const bool check_rows = p.check_rows != 0;
+  const uint4* __restrict__ ops = p.ops;
+  const u64* __restrict__ fpool = p.fpool;
+  const u32* __restrict__ list = p.list;
+  const StreamCoefs sc = p.sc;
+  const u32 n_rec = (u32)p.n_rec;
+  for (u32 pc = 0; pc < n_rec; pc++) {
+    const uint4 w = __ldg(ops + pc);
     const u32 opc = w.x & 0xffu, flags = (w.x >> 8) & 0xffu, imm16 = w.x >> 16;
     const u32 dst = w.y, a = w.z, b = w.w;
-#define FETCH_EXT() const uint4 x = __ldg(p.ops + (++pc))
+#define FETCH_EXT() const uint4 x = __ldg(ops + (++pc))
 #define UBV ((flags & PZK_FLAG_B_IMM) ? (u64)b : LDO(b))
 #define LDFA(v) ldFo(Fl, L, cells, NT, a, v)
-#define LDFB(v) do { if (flags & PZK_FLAG_B_POOL) ldPool(p.fpool, b, v); else ldFo(Fl, L, cells, NT, b, v); } while (0)
+#define LDFB(v) do { if (flags & PZK_FLAG_B_POOL) ldPool(fpool, b, v); else ldFo(Fl, L, cells, NT, b, v); } while (0)
 #define STFD(v) stFd(Fl, L, cells, NT, dst, v, store_all)
     switch (opc) {
       case PZK_NOP: break;
@@ -511,10 +519,10 @@ __global__ void __launch_bounds__(128) eval_kernel(EvalParams p) {
         if (x.x != PZK_OPERAND_NONE) idx |= (u32)(LDO(x.x) & 1) << 2;
         if (x.y != PZK_OPERAND_NONE) idx |= (u32)(LDO(x.y) & 1) << 3;
         if (opc == PZK_U_LUT) STD(dst, (u64)((imm16 >> idx) & 1));
-        else STD(dst, (u64)__ldg(p.list + x.z + 2 * idx) | ((u64)__ldg(p.list + x.z + 2 * idx + 1) << 32));
+        else STD(dst, (u64)__ldg(list + x.z + 2 * idx) | ((u64)__ldg(list + x.z + 2 * idx + 1) << 32));
         break;
       }
-      case PZK_F_CONST: { u64 v[4]; ldPool(p.fpool, a, v); STFD(v); break; }
+      case PZK_F_CONST: { u64 v[4]; ldPool(fpool, a, v); STFD(v); break; }
       case PZK_F_ADD: case PZK_F_SUB: case PZK_F_MUL: {
         u64 va[4], vb[4], r[4];
         LDFA(va); LDFB(vb);
@@ -543,7 +551,7 @@ __global__ void __launch_bounds__(128) eval_kernel(EvalParams p) {
         STD(dst, (u64)(opc == PZK_F_EQ ? eq : !eq));
         break;
       }
-      case PZK_F_CSEL: { u64 v[4]; ldPool(p.fpool, b + (u32)LDO(a), v); STFD(v); break; }
+      case PZK_F_CSEL: { u64 v[4]; ldPool(fpool, b + (u32)LDO(a), v); STFD(v); break; }
       case PZK_N_FROM_F: { u64 va[4], r[4]; LDFA(va); fr_from_mont(r, va); STFD(r); break; }
       case PZK_F_FROM_N: { u64 va[4], r[4]; LDFA(va); reduce_p(va); fr_to_mont(r, va); STFD(r); break; }
       case PZK_N_FROM_U: { u64 v[4] = {LDO(a), 0, 0, 0}; STFD(v); break; }
@@ -587,8 +595,8 @@ __global__ void __launch_bounds__(128) eval_kernel(EvalParams p) {
       }
       case PZK_CHECK_I64: {
         // |A|,|B|,|A*B|,|C| < 2^63 proven at compile time: wrapping 64-bit arithmetic is exact
-        if (p.check_rows) {
-          const uint4* recs = p.ops + pc + 1;
+        if (check_rows) {
+          const uint4* recs = ops + pc + 1;
           const u32 na = imm16, nab = na + (a & 0xffffu), tot = nab + (a >> 16);
           long long A = 0, B = 0, C = 0;
           for (u32 k = 0; k < tot; k += 2) {
@@ -611,18 +619,18 @@ __global__ void __launch_bounds__(128) eval_kernel(EvalParams p) {
         break;
       }
       case PZK_CHECK_INT: case PZK_CHECK_F: {
-        const u32 n_rec = b;
-        if (p.check_rows) {
-          const uint4* recs = p.ops + pc + 1;
+        const u32 row_recs = b;
+        if (check_rows) {
+          const uint4* recs = ops + pc + 1;
           const u32 na = imm16, nb = a & 0xffffu, nc = a >> 16;
-          bool ok = (opc == PZK_CHECK_INT) ? check_row_int(recs, na, nb, nc, p.list, Ul, L, cells, NT)
-                                           : check_row_field(p.sc, recs, na, nb, nc, Ul, Fl, L, cells, NT);
+          bool ok = (opc == PZK_CHECK_INT) ? check_row_int(recs, na, nb, nc, list, Ul, L, cells, NT)
+                                           : check_row_field(sc, recs, na, nb, nc, Ul, Fl, L, cells, NT);
           if (!ok && (unsigned long long)dst < bad) bad = dst;
         }
-        pc += n_rec;
+        pc += row_recs;
         break;
       }
-      case PZK_BIGDIV: st |= bigdiv_device(p.list + a, Ul, L); break;
+      case PZK_BIGDIV: st |= bigdiv_device(list + a, Ul, L); break;
       case PZK_ASSERT_NZ: if (LDO(a) == 0) st |= PZK_LANE_ASSERT; break;
       case PZK_IN_U: {
         const ulonglong2* ip = reinterpret_cast<const ulonglong2*>(p.inputs + ((u64)lane * p.n_inputs + a) * 4);
