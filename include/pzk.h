@@ -107,6 +107,8 @@ void pzk_profile_enable(pzk_circuit* c, int on);
 /* lanes processed per tile (0 = choose from free device memory)                        */
 int pzk_set_tile_lanes(pzk_circuit* c, uint64_t lanes);
 uint64_t pzk_get_tile_lanes(const pzk_circuit* c);
+/* lanes of one full wave of resident CTAs of the evaluator (tiles are sized in whole waves)  */
+uint64_t pzk_wave_lanes(const pzk_circuit* c);
 
 /* ---- snarkjs `wtns check` semantics on an explicit witness -------------------------
  * r1cs_path: iden3 .r1cs v1; wtns: iden3 .wtns v2 bytes.  *verdict = 1 when every

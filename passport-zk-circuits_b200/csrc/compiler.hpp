@@ -100,7 +100,7 @@ enum { CLS_U = 0, CLS_I = 1, CLS_F = 2, CLS_N = 3 };
 struct CompileOptions {
   std::map<std::string, int> input_bits;  // main input name -> declared width (bits)
   uint32_t seg_ops = 16384;
-  uint32_t cells = 48;  // operand-cache cells (8 bytes) per lane in shared memory
+  uint32_t cells = 16;  // operand-cache cells (8 bytes) per lane in shared memory
   bool verbose = false;
   bool intrinsics = true;
 };

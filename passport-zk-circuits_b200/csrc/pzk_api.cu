@@ -49,6 +49,7 @@ struct pzk_circuit {
   std::vector<SegDev> seg;
   uint64_t bytes_per_lane = 0;
   size_t smem_bytes = 0;
+  uint64_t wave_lanes = 0;  // lanes of one full wave of resident CTAs
   // device copies
   uint4* d_ops = nullptr;
   u64* d_fpool = nullptr;
@@ -213,6 +214,12 @@ int pzk_circuit_open(const char* program_path, int cuda_device, pzk_circuit** ou
   CK(cudaSetDevice(cuda_device));
   CK(cudaStreamCreate(&c->stream));
   if (c->smem_bytes > 48 * 1024) CK(cudaFuncSetAttribute(eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
+  {
+    int per_sm = 0, n_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, eval_kernel, 128, c->smem_bytes));
+    CK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, cuda_device));
+    c->wave_lanes = (uint64_t)per_sm * n_sm * 128;
+  }
   CK(upload(&c->d_ops, c->ops, c->h.n_op_records * sizeof(PzkOp)));
   CK(upload(&c->d_fpool, c->fpool, (size_t)c->h.n_fpool * 32));
   CK(upload(&c->d_coefs, c->coefs, (size_t)c->h.n_coef * sizeof(PzkCoef)));
@@ -248,6 +255,7 @@ int pzk_set_tile_lanes(pzk_circuit* c, uint64_t lanes) {
   return PZK_OK;
 }
 uint64_t pzk_get_tile_lanes(const pzk_circuit* c) { return c->L; }
+uint64_t pzk_wave_lanes(const pzk_circuit* c) { return c->wave_lanes; }
 
 static int ensure_tile(pzk_circuit* c, uint64_t want) {
   uint64_t L = c->tile_lanes_cfg;
@@ -257,8 +265,12 @@ static int ensure_tile(pzk_circuit* c, uint64_t want) {
     CK(cudaMemGetInfo(&free_b, &total_b));
     uint64_t budget = (uint64_t)(free_b * 0.80);
     L = budget / (c->bytes_per_lane ? c->bytes_per_lane : 1);
-    uint64_t cap = 148ull * 2048;  // one full wave of resident threads
+    // whole waves only: every segment is one launch, a partially filled last wave is pure tail
+    uint64_t wave = c->wave_lanes ? c->wave_lanes : 148ull * 2048;
+    uint64_t cap = 3 * wave;
     if (L > cap) L = cap;
+    if (L > want) L = want;
+    if (L >= wave) L = L / wave * wave;
     c->tile_auto_capped = (L < want);
   }
   if (L > want) L = want;

@@ -47,15 +47,24 @@ struct EvalParams {
 
 #define LDU(slot) (Ul[(u64)(slot) * L])
 #define STU(slot, v) (Ul[(u64)(slot) * L] = (v))
-// operand words: bit 31 -> shared-memory cell, else global slot (see pzk_program.h)
-#define CELLP(c) (cells + (u64)(c) * NT)
-#define LDO(x) (((x) & PZK_OPERAND_CELL) ? *CELLP((x) & 0xffffu) : Ul[(u64)(x) * L])
+// operand words: bit 31 -> shared-memory cell, else global slot (see pzk_program.h).
+// Cells are addressed with explicit 32-bit shared-space addresses: `cells` is the lane's base
+// (shared window offset + 8 * tid); cell c lives at cells + c * 8 * 128.  (x << 10) turns an operand
+// word or a term ref into that byte offset: the flag bits above bit 21 fall off the top.
+__device__ __forceinline__ u64 lds64(u32 addr) {
+  u64 v;
+  asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts64(u32 addr, u64 v) { asm volatile("st.shared.u64 [%0], %1;" ::"r"(addr), "l"(v) : "memory"); }
+#define CELL_ADDR(x) (cells + ((u32)(x) << 10))
+#define LDO(x) (((x) & PZK_OPERAND_CELL) ? lds64(CELL_ADDR(x)) : Ul[(u64)(x) * L])
 // destination words: global slot always, cell when assigned
 #define STD(d, v)                                                        \
   do {                                                                   \
     const u64 v__ = (v);                                                 \
     if (!((d) & PZK_DST_OPTIONAL) || store_all) Ul[(u64)PZK_DST_SLOT(d) * L] = v__; \
-    if (PZK_DST_CELL(d)) *CELLP(PZK_DST_CELL(d) - 1) = v__;               \
+    if (PZK_DST_CELL(d)) sts64(cells + ((PZK_DST_CELL(d) - 1) << 10), v__); \
   } while (0)
 
 __device__ __forceinline__ void ldF(const u64* Fl, u64 L, u32 slot, u64* v) {
@@ -66,17 +75,19 @@ __device__ __forceinline__ void stF(u64* Fl, u64 L, u32 slot, const u64* v) {
   u64* p = Fl + (u64)slot * 4 * L;
   p[0] = v[0]; p[L] = v[1]; p[2 * L] = v[2]; p[3 * L] = v[3];
 }
-__device__ __forceinline__ void ldFo(const u64* Fl, u64 L, const u64* cells, u32 NT, u32 x, u64* v) {
+__device__ __forceinline__ void ldFo(const u64* Fl, u64 L, u32 cells, u32 NT, u32 x, u64* v) {
+  (void)NT;
   if (x & PZK_OPERAND_CELL) {
-    const u64* c = cells + (u64)(x & 0xffffu) * NT;
-    v[0] = c[0]; v[1] = c[NT]; v[2] = c[2 * NT]; v[3] = c[3 * NT];
+    const u32 c = cells + (x << 10);
+    v[0] = lds64(c); v[1] = lds64(c + 1024); v[2] = lds64(c + 2048); v[3] = lds64(c + 3072);
   } else ldF(Fl, L, x, v);
 }
-__device__ __forceinline__ void stFd(u64* Fl, u64 L, u64* cells, u32 NT, u32 d, const u64* v, bool store_all) {
+__device__ __forceinline__ void stFd(u64* Fl, u64 L, u32 cells, u32 NT, u32 d, const u64* v, bool store_all) {
+  (void)NT;
   if (!(d & PZK_DST_OPTIONAL) || store_all) stF(Fl, L, PZK_DST_SLOT(d), v);
   if (PZK_DST_CELL(d)) {
-    u64* c = cells + (u64)(PZK_DST_CELL(d) - 1) * NT;
-    c[0] = v[0]; c[NT] = v[1]; c[2 * NT] = v[2]; c[3 * NT] = v[3];
+    const u32 c = cells + ((PZK_DST_CELL(d) - 1) << 10);
+    sts64(c, v[0]); sts64(c + 1024, v[1]); sts64(c + 2048, v[2]); sts64(c + 3072, v[3]);
   }
 }
 __device__ __forceinline__ void ldPool(const u64* pool, u32 idx, u64* v) {
@@ -342,9 +353,9 @@ __device__ __forceinline__ long long term_icoef(const u32* list, u32 ref, u32 cw
   return (long long)(int)cw;
 }
 // exact integer row: |A|,|B| < 2^63 and |C| < 2^126 proven by the compiler
-#define TERM_U(ref) (((ref) & PZK_TERM_CELL) ? cells[(u64)((ref) & 0xffffu) * NT] : Ul[(u64)PZK_REF_SLOT(ref) * L])
+#define TERM_U(ref) (((ref) & PZK_TERM_CELL) ? lds64(cells + ((u32)(ref) << 10)) : Ul[(u64)PZK_REF_SLOT(ref) * L])
 __device__ __forceinline__ bool check_row_int(const uint4* recs, u32 na, u32 nb, u32 nc, const u32* list,
-                                              const u64* Ul, u64 L, const u64* cells, u32 NT) {
+                                              const u64* Ul, u64 L, u32 cells, u32 NT) {
   long long A = 0, B = 0;
   u64 Clo = 0, Chi = 0;
   u32 k = 0;
@@ -384,7 +395,7 @@ __device__ __forceinline__ bool check_row_int(const uint4* recs, u32 na, u32 nb,
 }
 
 __device__ __noinline__ void lin_eval_stream(const StreamCoefs sc, const uint4* recs, u32 k0, u32 n, const u64* Ul,
-                                             const u64* Fl, u64 L, const u64* cells, u32 NT, LinVal& out) {
+                                             const u64* Fl, u64 L, u32 cells, u32 NT, LinVal& out) {
   out.i.v[0] = out.i.v[1] = out.i.v[2] = 0;
   out.f[0] = out.f[1] = out.f[2] = out.f[3] = 0;
   out.has_f = false;
@@ -431,7 +442,7 @@ __device__ __noinline__ void lin_eval_stream(const StreamCoefs sc, const uint4* 
   }
 }
 __device__ __noinline__ bool check_row_field(const StreamCoefs sc, const uint4* recs, u32 na, u32 nb, u32 nc,
-                                             const u64* Ul, const u64* Fl, u64 L, const u64* cells, u32 NT) {
+                                             const u64* Ul, const u64* Fl, u64 L, u32 cells, u32 NT) {
   LinVal A, B, C;
   lin_eval_stream(sc, recs, na + nb, nc, Ul, Fl, L, cells, NT, C);
   if (na == 0 || nb == 0) {
@@ -459,7 +470,7 @@ __device__ __noinline__ bool check_row_field(const StreamCoefs sc, const uint4* 
   return fr_eq(ab, c);
 }
 
-__global__ void __launch_bounds__(128) eval_kernel(EvalParams p) {
+__global__ void __launch_bounds__(128, 8) eval_kernel(EvalParams p) {
   extern __shared__ u64 cell_mem[];
   const u64 lane = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   if (lane >= p.n_lanes) return;
@@ -468,7 +479,7 @@ __global__ void __launch_bounds__(128) eval_kernel(EvalParams p) {
   // page-walk bound: consecutive ops touch slots that are megabytes apart).
   const u64 L = PZK_LANE_BLOCK;
   const u32 NT = blockDim.x;
-  u64* cells = cell_mem + threadIdx.x;
+  const u32 cells = (u32)__cvta_generic_to_shared(cell_mem) + threadIdx.x * 8;  // lane base in the shared window
   u64* Ul = p.U + (u64)blockIdx.x * p.n_u_slots * PZK_LANE_BLOCK + threadIdx.x;
   u64* Fl = p.F + (u64)blockIdx.x * p.n_f_slots * 4 * PZK_LANE_BLOCK + threadIdx.x;
   u32 st = 0;
@@ -557,11 +568,11 @@ __global__ void __launch_bounds__(128) eval_kernel(EvalParams p) {
       case PZK_N_FROM_U: { u64 v[4] = {LDO(a), 0, 0, 0}; STFD(v); break; }
       case PZK_N_BIT: {
         u64 limb = 0;
-        if (b < 256) limb = (a & PZK_OPERAND_CELL) ? *CELLP((a & 0xffffu) + (b >> 6)) : Fl[((u64)a * 4 + (b >> 6)) * L];
+        if (b < 256) limb = (a & PZK_OPERAND_CELL) ? lds64(CELL_ADDR(a) + ((b >> 6) << 10)) : Fl[((u64)a * 4 + (b >> 6)) * L];
         STD(dst, (limb >> (b & 63)) & 1);
         break;
       }
-      case PZK_N_LOW: STD(dst, (a & PZK_OPERAND_CELL) ? *CELLP(a & 0xffffu) : Fl[(u64)a * 4 * L]); break;
+      case PZK_N_LOW: STD(dst, (a & PZK_OPERAND_CELL) ? lds64(CELL_ADDR(a)) : Fl[(u64)a * 4 * L]); break;
       case PZK_N_FITS: { u64 v[4]; LDFA(v); STD(dst, (u64)((v[1] | v[2] | v[3]) == 0)); break; }
       case PZK_N_SHR: { u64 v[4], r[4]; LDFA(v); u64 d = UBV; shr256(r, v, d > 256 ? 256u : (unsigned)d); STFD(r); break; }
       case PZK_N_SHL: {

@@ -102,6 +102,8 @@ def lib():
     L.pzk_set_tile_lanes.argtypes = [vp, u64]
     L.pzk_get_tile_lanes.restype = u64
     L.pzk_get_tile_lanes.argtypes = [vp]
+    L.pzk_wave_lanes.restype = u64
+    L.pzk_wave_lanes.argtypes = [vp]
     L.pzk_wtns_check.argtypes = [cp, vp, u64, ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(i64), cp,
                                  ctypes.c_size_t]
     L.pzk_r1cs_check_batch.argtypes = [cp, vp, u64, ctypes.c_int, vp, vp, ctypes.POINTER(ctypes.c_double), cp,
@@ -363,6 +365,9 @@ class WitnessCalculator:
 
     def tile_lanes(self):
         return self._L.pzk_get_tile_lanes(self._h)
+
+    def wave_lanes(self):
+        return self._L.pzk_wave_lanes(self._h)
 
 
 def wtns_check(r1cs_path, wtns: bytes, device=0):

@@ -4,9 +4,11 @@ import numpy as np
 from passport_zk_circuits_b200 import witness as W
 from passport_zk_circuits_b200.passports import C3, PassportFactory
 name = sys.argv[1]; B = int(sys.argv[2])
+WAVES = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 calc = W.WitnessCalculator(W.artifact(name), 0)
 name = "c3" if name.startswith("c3") else name
-print(name, 'wires', calc.n_wires, 'constraints', calc.n_constraints, calc.stats())
+if WAVES: B = WAVES * calc.wave_lanes()
+print(name, 'wave', calc.wave_lanes(), 'B', B, 'wires', calc.n_wires, 'constraints', calc.n_constraints, calc.stats())
 if name == 'c3':
     fac = PassportFactory(C3, seed=1, n_sig_keys=2, n_aa_keys=2)
     uniq = W.pack_inputs_fast(calc.meta, [fac.make(i).inputs for i in range(64)])
