@@ -93,6 +93,19 @@ int pzk_witness_batch(pzk_circuit* c, const uint8_t* inputs_le32, uint64_t batch
                       int64_t* first_bad, uint8_t* public_le32, const uint64_t* export_lanes,
                       uint64_t n_export, uint8_t* witnesses_le32);
 
+/* Packed inputs: most inputs of the passport circuits are bits or 64-bit limbs (what
+ * /root/reference/test/process_passport.js:590-672 writes), so a lane's inputs can cross the bus
+ * as one record of pzk_packed_stride() bytes: [one byte per input declared <= 8 bits] padded to 8,
+ * [8 bytes little endian per input declared <= 64 bits], pad to 16, [32 bytes per field input], record
+ * padded to 16; within a
+ * section the inputs keep their flattened order.  pzk_packed_layout() gives kind (0/1/2) and
+ * byte offset per flattened input.                                                         */
+uint32_t pzk_packed_stride(const pzk_circuit* c);
+int pzk_packed_layout(const pzk_circuit* c, uint32_t* kind, uint32_t* offset);
+int pzk_witness_batch_packed(pzk_circuit* c, const uint8_t* packed, uint64_t batch, uint32_t* status,
+                             int64_t* first_bad, uint8_t* public_le32);
+int pzk_batch_upload_packed(pzk_circuit* c, const uint8_t* packed, uint64_t batch);
+
 /* device-resident variant for measurement: upload once, run many times, download once */
 int pzk_batch_upload(pzk_circuit* c, const uint8_t* inputs_le32, uint64_t batch);
 int pzk_batch_run(pzk_circuit* c, int check_rows); /* all tiles of the uploaded batch    */

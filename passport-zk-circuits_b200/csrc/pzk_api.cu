@@ -69,6 +69,11 @@ struct pzk_circuit {
   // batch state
   uint64_t batch = 0, batch_cap = 0;
   u64* d_inputs = nullptr;
+  uint64_t d_inputs_bytes = 0;
+  bool packed = false;        // layout of the resident batch
+  uint2* d_in_table = nullptr;
+  uint32_t packed_stride = 0;
+  std::vector<uint2> in_table;
   u32* d_status = nullptr;
   unsigned long long* d_first_bad = nullptr;
   u64* d_public = nullptr;
@@ -146,7 +151,7 @@ static void free_batch(pzk_circuit* c) {
   if (c->d_first_bad) cudaFree(c->d_first_bad);
   if (c->d_public) cudaFree(c->d_public);
   c->d_inputs = nullptr; c->d_status = nullptr; c->d_first_bad = nullptr; c->d_public = nullptr;
-  c->batch_cap = 0; c->pub_cap = 0;
+  c->batch_cap = 0; c->pub_cap = 0; c->d_inputs_bytes = 0;
 }
 
 void pzk_circuit_close(pzk_circuit* c) {
@@ -154,7 +159,7 @@ void pzk_circuit_close(pzk_circuit* c) {
   cudaSetDevice(c->device);
   free_tile(c); free_batch(c);
   cudaFree(c->d_ops); cudaFree(c->d_fpool); cudaFree(c->d_coefs); cudaFree(c->d_coef_kind); cudaFree(c->d_coef_mag);
-  cudaFree(c->d_list); cudaFree(c->d_rows); cudaFree(c->d_terms); cudaFree(c->d_exports); cudaFree(c->d_pub_entries);
+  cudaFree(c->d_list); cudaFree(c->d_in_table); cudaFree(c->d_rows); cudaFree(c->d_terms); cudaFree(c->d_exports); cudaFree(c->d_pub_entries);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -208,6 +213,20 @@ int pzk_circuit_open(const char* program_path, int cuda_device, pzk_circuit** ou
   c->exports = (const PzkExport*)(b + pos); pos = al16(pos + c->h.n_exports * sizeof(PzkExport));
   if (pos + c->h.reserved[0] > (uint64_t)sz) { set_err(c, "truncated program file"); return PZK_EFORMAT; }
   c->meta.assign((const char*)(b + pos), c->h.reserved[0]);
+  {
+    // packed input record: [1-byte inputs (declared <= 8 bits)] pad8 [8-byte inputs (<= 64 bits)] [32-byte field inputs]
+    uint32_t n8 = 0, n64 = 0;
+    for (uint32_t k = 0; k < c->h.n_inputs; k++) { uint32_t b_ = c->inputs[k].bits; if (b_ && b_ <= 8) n8++; else if (b_) n64++; }
+    uint32_t off8 = 0, off64 = (n8 + 7) / 8 * 8, offf = (off64 + n64 * 8 + 15) / 16 * 16;  // field section 16-byte aligned
+    c->in_table.resize(c->h.n_inputs ? c->h.n_inputs : 1);
+    for (uint32_t k = 0; k < c->h.n_inputs; k++) {
+      uint32_t b_ = c->inputs[k].bits;
+      if (b_ && b_ <= 8) { c->in_table[k] = make_uint2(0, off8); off8 += 1; }
+      else if (b_) { c->in_table[k] = make_uint2(1, off64); off64 += 8; }
+      else { c->in_table[k] = make_uint2(2, offf); offf += 32; }
+    }
+    c->packed_stride = (offf + 15) / 16 * 16;
+  }
   c->bytes_per_lane = (uint64_t)c->h.n_u_slots * 8 + (uint64_t)c->h.n_f_slots * 32;
   c->smem_bytes = (size_t)c->h.reserved[1] * 8 * 128;
 
@@ -230,6 +249,7 @@ int pzk_circuit_open(const char* program_path, int cuda_device, pzk_circuit** ou
     CK(upload(&c->d_coef_mag, mag.data(), mag.size() * 8));
   }
   CK(upload(&c->d_list, c->list, (size_t)c->h.n_list * 4));
+  CK(upload(&c->d_in_table, c->in_table.data(), c->in_table.size() * sizeof(uint2)));
   CK(upload(&c->d_rows, c->rows, c->h.n_rows * sizeof(PzkRow)));
   CK(upload(&c->d_terms, c->terms, c->h.n_terms * sizeof(PzkTerm)));
   CK(upload(&c->d_exports, c->exports, c->h.n_exports * sizeof(PzkExport)));
@@ -284,11 +304,12 @@ static int ensure_tile(pzk_circuit* c, uint64_t want) {
   return PZK_OK;
 }
 
-static int ensure_batch(pzk_circuit* c, uint64_t batch) {
-  if (batch <= c->batch_cap) return PZK_OK;
+static int ensure_batch(pzk_circuit* c, uint64_t batch, uint64_t input_bytes) {
+  if (batch <= c->batch_cap && input_bytes <= c->d_inputs_bytes) return PZK_OK;
   free_batch(c);
   uint64_t n_pub = c->h.n_pub_out + c->h.n_pub_in;
-  CK(cudaMalloc((void**)&c->d_inputs, std::max<uint64_t>(batch * c->h.n_inputs * 32, 16)));
+  CK(cudaMalloc((void**)&c->d_inputs, std::max<uint64_t>(input_bytes, 16)));
+  c->d_inputs_bytes = input_bytes;
   CK(cudaMalloc((void**)&c->d_status, batch * 4));
   CK(cudaMalloc((void**)&c->d_first_bad, batch * 8));
   CK(cudaMalloc((void**)&c->d_public, std::max<uint64_t>(batch * n_pub * 32, 16)));
@@ -355,7 +376,11 @@ static int run_batch(pzk_circuit* c, int check_rows, const uint64_t* export_lane
       if (sg.n_ops) {
         EvalParams p;
         p.ops = c->d_ops + sg.op_off; p.n_rec = sg.n_ops; p.U = c->d_U; p.F = c->d_F; p.L = L; p.n_lanes = n;
-        p.fpool = c->d_fpool; p.list = c->d_list; p.inputs = c->d_inputs + base * c->h.n_inputs * 4;
+        p.fpool = c->d_fpool; p.list = c->d_list;
+        if (c->packed) {
+          p.inputs = reinterpret_cast<const u64*>(reinterpret_cast<const unsigned char*>(c->d_inputs) + base * c->packed_stride);
+          p.in_table = c->d_in_table; p.in_stride = c->packed_stride;
+        } else { p.inputs = c->d_inputs + base * c->h.n_inputs * 4; p.in_table = nullptr; p.in_stride = 0; }
         p.n_inputs = c->h.n_inputs; p.status = c->d_status + base; p.n_u_slots = c->h.n_u_slots; p.n_f_slots = c->h.n_f_slots;
         p.check_rows = check_rows; p.store_all = (n_export > 0) ? 1 : 0; p.sc.coefs = c->d_coefs; p.sc.coef_kind = c->d_coef_kind; p.sc.coef_mag = c->d_coef_mag;
         p.first_bad = c->d_first_bad + base;
@@ -401,12 +426,37 @@ static int run_batch(pzk_circuit* c, int check_rows, const uint64_t* export_lane
 int pzk_batch_upload(pzk_circuit* c, const uint8_t* inputs_le32, uint64_t batch) {
   if (!c || !inputs_le32 || batch == 0) return PZK_EINVAL;
   CK(cudaSetDevice(c->device));
-  int rc = ensure_batch(c, batch);
+  int rc = ensure_batch(c, batch, batch * c->h.n_inputs * 32);
   if (rc) return rc;
-  c->batch = batch;
+  c->batch = batch; c->packed = false;
   CK(cudaMemcpyAsync(c->d_inputs, inputs_le32, batch * c->h.n_inputs * 32, cudaMemcpyHostToDevice, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   return PZK_OK;
+}
+
+uint32_t pzk_packed_stride(const pzk_circuit* c) { return c->packed_stride; }
+int pzk_packed_layout(const pzk_circuit* c, uint32_t* kind, uint32_t* offset) {
+  if (!c || !kind || !offset) return PZK_EINVAL;
+  for (uint32_t k = 0; k < c->h.n_inputs; k++) { kind[k] = c->in_table[k].x; offset[k] = c->in_table[k].y; }
+  return PZK_OK;
+}
+int pzk_batch_upload_packed(pzk_circuit* c, const uint8_t* packed, uint64_t batch) {
+  if (!c || !packed || batch == 0) return PZK_EINVAL;
+  CK(cudaSetDevice(c->device));
+  int rc = ensure_batch(c, batch, batch * (uint64_t)c->packed_stride);
+  if (rc) return rc;
+  c->batch = batch; c->packed = true;
+  CK(cudaMemcpyAsync(c->d_inputs, packed, batch * (uint64_t)c->packed_stride, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return PZK_OK;
+}
+int pzk_witness_batch_packed(pzk_circuit* c, const uint8_t* packed, uint64_t batch, uint32_t* status,
+                             int64_t* first_bad, uint8_t* public_le32) {
+  int rc = pzk_batch_upload_packed(c, packed, batch);
+  if (rc) return rc;
+  rc = run_batch(c, 1, nullptr, 0, nullptr);
+  if (rc) return rc;
+  return pzk_batch_download(c, status, first_bad, public_le32);
 }
 
 int pzk_batch_run(pzk_circuit* c, int check_rows) {

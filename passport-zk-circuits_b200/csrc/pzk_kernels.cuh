@@ -35,8 +35,10 @@ struct EvalParams {
   u32 n_u_slots, n_f_slots;
   const u64* fpool;
   const u32* list;
-  const u64* inputs;  // [lane][n_inputs][4]
+  const u64* inputs;  // [lane][n_inputs][4], or packed records when in_table != nullptr
   u32 n_inputs;
+  const uint2* in_table;  // packed inputs: per input (kind 0 = u8, 1 = u64, 2 = 32-byte field; byte offset)
+  u32 in_stride;          // bytes per lane of a packed record
   u32* status;
   // fused constraint rows
   int check_rows;
@@ -644,6 +646,14 @@ __global__ void __launch_bounds__(128, 8) eval_kernel(EvalParams p) {
       case PZK_BIGDIV: st |= bigdiv_device(list + a, Ul, L); break;
       case PZK_ASSERT_NZ: if (LDO(a) == 0) st |= PZK_LANE_ASSERT; break;
       case PZK_IN_U: {
+        if (p.in_table) {
+          const uint2 e = __ldg(p.in_table + a);
+          const unsigned char* base = reinterpret_cast<const unsigned char*>(p.inputs) + (u64)lane * p.in_stride + e.y;
+          u64 v = (e.x == 0) ? (u64)*base : *reinterpret_cast<const u64*>(base);
+          if (imm16 < 64 && (v >> imm16) != 0) st |= PZK_LANE_INPUT_RANGE;
+          STD(dst, v);
+          break;
+        }
         const ulonglong2* ip = reinterpret_cast<const ulonglong2*>(p.inputs + ((u64)lane * p.n_inputs + a) * 4);
         ulonglong2 lo = ip[0], hi = ip[1];
         if ((lo.y | hi.x | hi.y) != 0 || (imm16 < 64 && (lo.x >> imm16) != 0)) st |= PZK_LANE_INPUT_RANGE;
@@ -651,7 +661,9 @@ __global__ void __launch_bounds__(128, 8) eval_kernel(EvalParams p) {
         break;
       }
       case PZK_IN_F: {
-        const ulonglong2* ip = reinterpret_cast<const ulonglong2*>(p.inputs + ((u64)lane * p.n_inputs + a) * 4);
+        const ulonglong2* ip = p.in_table
+            ? reinterpret_cast<const ulonglong2*>(reinterpret_cast<const unsigned char*>(p.inputs) + (u64)lane * p.in_stride + __ldg(p.in_table + a).y)
+            : reinterpret_cast<const ulonglong2*>(p.inputs + ((u64)lane * p.n_inputs + a) * 4);
         ulonglong2 lo = ip[0], hi = ip[1];
         u64 v[4] = {lo.x, lo.y, hi.x, hi.y}, r[4];
         if (geq_p(v)) { st |= PZK_LANE_INPUT_RANGE; reduce_p(v); }

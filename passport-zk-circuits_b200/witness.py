@@ -104,6 +104,11 @@ def lib():
     L.pzk_get_tile_lanes.argtypes = [vp]
     L.pzk_wave_lanes.restype = u64
     L.pzk_wave_lanes.argtypes = [vp]
+    L.pzk_packed_stride.restype = u32
+    L.pzk_packed_stride.argtypes = [vp]
+    L.pzk_packed_layout.argtypes = [vp, vp, vp]
+    L.pzk_witness_batch_packed.argtypes = [vp, vp, u64, vp, vp, vp]
+    L.pzk_batch_upload_packed.argtypes = [vp, vp, u64]
     L.pzk_wtns_check.argtypes = [cp, vp, u64, ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(i64), cp,
                                  ctypes.c_size_t]
     L.pzk_r1cs_check_batch.argtypes = [cp, vp, u64, ctypes.c_int, vp, vp, ctypes.POINTER(ctypes.c_double), cp,
@@ -329,6 +334,52 @@ class WitnessCalculator:
                                               len(lanes), wit.ctypes.data if wit is not None else None))
         first_bad[(status & STATUS_CONSTRAINT) == 0] = -1
         return BatchResult(status, first_bad, public, wit)
+
+    # ---- packed inputs (bits as bytes, 64-bit limbs as 8 bytes, field elements as 32 bytes)
+    def packed_layout(self):
+        if not hasattr(self, "_layout"):
+            kind = np.zeros(self.n_inputs, dtype=np.uint32)
+            off = np.zeros(self.n_inputs, dtype=np.uint32)
+            self._check(self._L.pzk_packed_layout(self._h, kind.ctypes.data, off.ctypes.data))
+            self._layout = (kind, off, int(self._L.pzk_packed_stride(self._h)))
+        return self._layout
+
+    def pack(self, inputs: np.ndarray) -> np.ndarray:
+        """uint64 [B, n_inputs, 4] -> uint8 [B, stride] packed records (values must fit their declared width;
+        wider values are truncated here and would have been flagged by the unpacked path)."""
+        kind, off, stride = self.packed_layout()
+        B = inputs.shape[0]
+        out = np.zeros((B, stride), dtype=np.uint8)
+        k8 = np.nonzero(kind == 0)[0]
+        if len(k8):
+            out[:, off[k8]] = inputs[:, k8, 0].astype(np.uint8)
+        k64 = np.nonzero(kind == 1)[0]
+        if len(k64):
+            lo = int(off[k64[0]])
+            assert (off[k64] == lo + 8 * np.arange(len(k64))).all()
+            out[:, lo:lo + 8 * len(k64)] = np.ascontiguousarray(inputs[:, k64, 0]).view(np.uint8).reshape(B, -1)
+        kf = np.nonzero(kind == 2)[0]
+        if len(kf):
+            lo = int(off[kf[0]])
+            assert (off[kf] == lo + 32 * np.arange(len(kf))).all()
+            out[:, lo:lo + 32 * len(kf)] = np.ascontiguousarray(inputs[:, kf, :]).view(np.uint8).reshape(B, -1)
+        return out
+
+    def calculateWitnessBatchPacked(self, packed: np.ndarray) -> BatchResult:
+        packed = np.ascontiguousarray(packed, dtype=np.uint8)
+        B = packed.shape[0]
+        status = np.zeros(B, dtype=np.uint32)
+        first_bad = np.zeros(B, dtype=np.int64)
+        public = np.zeros((B, self.n_public, 4), dtype=np.uint64)
+        self._check(self._L.pzk_witness_batch_packed(self._h, packed.ctypes.data, B, status.ctypes.data,
+                                                     first_bad.ctypes.data, public.ctypes.data))
+        first_bad[(status & STATUS_CONSTRAINT) == 0] = -1
+        return BatchResult(status, first_bad, public)
+
+    def upload_packed(self, packed: np.ndarray):
+        packed = np.ascontiguousarray(packed, dtype=np.uint8)
+        self._check(self._L.pzk_batch_upload_packed(self._h, packed.ctypes.data, packed.shape[0]))
+        self._B = packed.shape[0]
 
     # ---- device-resident measurement path
     def upload(self, inputs: np.ndarray):

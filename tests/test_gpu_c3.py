@@ -44,6 +44,10 @@ def test_c3_batch_vs_oracle(c3):
     res2 = calc.calculateWitnessBatch(inp)
     assert np.array_equal(res2.status, res.status) and np.array_equal(res2.first_bad, res.first_bad)
     assert np.array_equal(res2.public, res.public)
+    # packed input records (bits as bytes, limbs as u64): same results
+    res3 = calc.calculateWitnessBatchPacked(calc.pack(inp))
+    assert np.array_equal(res3.status, res.status) and np.array_equal(res3.first_bad, res.first_bad)
+    assert np.array_equal(res3.public, res.public)
     ok = np.ones(B, dtype=bool)
     ok[[5, 9]] = False
     assert (res.status[ok] == 0).all()

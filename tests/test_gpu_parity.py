@@ -39,6 +39,10 @@ def run_and_compare(name, inp, export=None, tile=None):
     lean = calc.calculateWitnessBatch(inp)      # no export: optional global stores are skipped
     assert np.array_equal(lean.status, res.status) and np.array_equal(lean.first_bad, res.first_bad)
     assert np.array_equal(lean.public, res.public)
+    packed = calc.calculateWitnessBatchPacked(calc.pack(inp))
+    in_range = (res.status & W.STATUS_INPUT_RANGE) == 0      # packing truncates out-of-range values
+    assert np.array_equal(packed.status[in_range], res.status[in_range])
+    assert np.array_equal(packed.public[in_range], res.public[in_range])
     calc.close()
     return res
 
