@@ -24,6 +24,15 @@ def _wrapper(name, body):
     return path
 
 
+# SIGNATURE_TYPE 3 (RSA-2048 PKCS#1 v1.5 + SHA-1, SHA-1 data groups), 10 (RSA-PSS e=3, SHA-256),
+# 13 (RSA-PSS SHA-384 with 1024-bit hash blocks and a different EC shift / block counts)
+C4_VARIANTS = {
+    "c4_sig3": CircuitParams(3, 160, 3, 4, 600, 248, 1, 1496, 3, 256),
+    "c4_sig10": CircuitParams(10, 256, 3, 4, 600, 248, 1, 1496, 3, 256),
+    "c4_sig13": CircuitParams(13, 384, 3, 2, 320, 248, 1, 1496, 2, 256),
+}
+
+
 def reference_circuits():
     lib = REFERENCE + "/circuits/lib/circuits"
     return {
@@ -39,16 +48,27 @@ def reference_circuits():
         "rsa2048": (f'pragma circom 2.1.6;\ninclude "{lib}/signatures/rsa.circom";\n'
                     "component main = RsaVerifyPkcs1v15(64, 32, 65537, 256);\n",
                     {"signature": 64, "pubkey": 64, "hashed": 1}),
+        # config 2: queryIdentity (selective disclosure, date utilities, enforced SMT inclusion); BabyPbk is
+        # bound to the in-tree multiplication by tests/circuits/shims/babypbk.circom
+        "query80": (f'pragma circom 2.1.6;\ninclude "{W._ROOT}/tests/circuits/shims/babypbk.circom";\n'
+                    f'include "{REFERENCE}/circuits/identityManagement/queryIdentity.circom";\n'
+                    "component main { public [eventID, eventData, idStateRoot, selector, currentDate, "
+                    "timestampLowerbound, timestampUpperbound, identityCounterLowerbound, identityCounterUpperbound, "
+                    "birthDateLowerbound, birthDateUpperbound, expirationDateLowerbound, expirationDateUpperbound, "
+                    "citizenshipMask] } = QueryIdentity(80);\n", {"dg1": 1}),
         # config 3: the north-star circuit (hardhat.config.ts:29)
         "c3": (C3.main_source(REFERENCE + "/circuits/identityManagement/registerIdentityBuilder.circom"),
                W.REGISTER_IDENTITY_BITS),
+        # config 4: SHA-1 / RSA-PSS variants with other hash types and shifts
+        **{name: (prm.main_source(REFERENCE + "/circuits/identityManagement/registerIdentityBuilder.circom"),
+                  W.REGISTER_IDENTITY_BITS) for name, prm in C4_VARIANTS.items()},
     }
 
 
 OWN_CIRCUITS = {"t_mix": ("mix.circom", {"u": 16, "bits": 1}),
                 "t_bigdiv": ("bigdiv.circom", {"a": 64, "b": 64})}
 
-BIG = {"c3"}  # ship only the xz-packed program for these
+BIG = {"c3", "c4_sig3", "c4_sig10", "c4_sig13"}  # ship only the xz-packed program for these
 
 
 def _stale(out, deps):

@@ -118,6 +118,7 @@ class RsaKey:
         return m2 + h * self.q
 
 
+# sha1 PKCS#1 DigestInfo is checked by rsa.circom:101-110
 _DIGEST_INFO = {
     "sha256": bytes.fromhex("3031300d060960864801650304020105000420"),
     "sha1": bytes.fromhex("3021300906052b0e03021a05000414"),
@@ -131,15 +132,49 @@ def pkcs1v15_sign(key: RsaKey, msg: bytes, hash_name="sha256"):
     return key.private_op(int.from_bytes(em, "big"))
 
 
+def mgf1(seed: bytes, length: int, hash_name: str) -> bytes:
+    out = b""
+    counter = 0
+    while len(out) < length:
+        out += hashlib.new(hash_name, seed + counter.to_bytes(4, "big")).digest()
+        counter += 1
+    return out[:length]
+
+
+def pss_sign(key: RsaKey, msg: bytes, hash_name: str, salt_len: int, rng) -> int:
+    """RSASSA-PSS (EMSA-PSS, MGF1 with the message hash), the encoding
+    /root/reference/circuits/lib/circuits/signatures/rsaPss.circom:18-254 unpacks."""
+    em_bits = key.bits - 1
+    em_len = (em_bits + 7) // 8
+    m_hash = hashlib.new(hash_name, msg).digest()
+    h_len = len(m_hash)
+    salt = bytes(rng.randrange(256) for _ in range(salt_len))
+    h = hashlib.new(hash_name, b"\x00" * 8 + m_hash + salt).digest()
+    db = b"\x00" * (em_len - salt_len - h_len - 2) + b"\x01" + salt
+    mask = mgf1(h, em_len - h_len - 1, hash_name)
+    masked = bytearray(a ^ b for a, b in zip(db, mask))
+    masked[0] &= 0xFF >> (8 * em_len - em_bits)
+    em = bytes(masked) + h + b"\xbc"
+    return key.private_op(int.from_bytes(em, "big"))
+
+
+# SIGNATURE_TYPE -> (modulus bits, scheme, signature hash bits, public exponent, PSS salt length)
+# (/root/reference/circuits/signatureVerifier/signatureVerification.circom:13-116, SURVEY.md appendix D)
+SIG_SCHEMES = {
+    1: (2048, "pkcs1", 256, 65537, 0), 2: (4096, "pkcs1", 256, 65537, 0), 3: (2048, "pkcs1", 160, 65537, 0),
+    10: (2048, "pss", 256, 3, 32), 11: (2048, "pss", 256, 65537, 32), 12: (2048, "pss", 256, 65537, 64),
+    13: (2048, "pss", 384, 65537, 48),
+}
+
 _KEY_CACHE = {}
 
 
-def key_pool(bits, count, seed):
+def key_pool(bits, count, seed, e=65537):
     """Deterministic pool of RSA keys (the signer certificates of the synthetic state)."""
-    k = (bits, count, seed)
+    k = (bits, count, seed, e)
     if k not in _KEY_CACHE:
-        rng = random.Random((seed << 16) ^ bits ^ 0x5A5A)
-        _KEY_CACHE[k] = [RsaKey(bits, rng) for _ in range(count)]
+        rng = random.Random((seed << 16) ^ bits ^ 0x5A5A ^ (e << 40))
+        _KEY_CACHE[k] = [RsaKey(bits, rng, e) for _ in range(count)]
     return _KEY_CACHE[k]
 
 
@@ -193,13 +228,15 @@ class PassportFactory:
 
     def __init__(self, params: CircuitParams = C3, seed: int = 1, n_sig_keys: int = 4,
                  n_aa_keys: int = 4):
-        if params.sig_type not in (1, 3):
-            raise NotImplementedError("synthetic generator: RSA-2048 PKCS#1 v1.5 (SIG 1/3) only")
+        if params.sig_type not in SIG_SCHEMES:
+            raise NotImplementedError("synthetic generator: RSA PKCS#1 v1.5 / PSS families only (SIG 1-3, 10-13)")
         self.params = params
         self.seed = seed
-        self.sig_hash = 160 if params.sig_type == 3 else 256
-        self.block = 512
-        self.sig_keys = key_pool(2048, n_sig_keys, seed)
+        self.key_bits, self.scheme, self.sig_hash, self.e, self.salt_len = SIG_SCHEMES[params.sig_type]
+        self.block = 512 if self.sig_hash <= 256 else 1024
+        if (512 if params.dg_hash <= 256 else 1024) != self.block:
+            raise ValueError("DG_HASH_TYPE and the signature hash must share a block size (SURVEY.md appendix D)")
+        self.sig_keys = key_pool(self.key_bits, n_sig_keys, seed, self.e)
         self.aa_keys = key_pool(1024, n_aa_keys, seed + 7) if params.aa_algo else []
         self._pkhash = [rsa_pubkey_hash(k.n) for k in self.sig_keys]
         self._roots = [poseidon([h, h, 1]) for h in self._pkhash]
@@ -269,8 +306,10 @@ class PassportFactory:
         ec = bytes(ec)
         # signed attributes
         slen = self.sig_hash // 8
-        lo, hi = self._len_range(2)
+        lo, hi = self._len_range(1024 // self.block)
         lo = max(lo, p.ec_shift // 8 + slen)
+        if lo > hi:
+            raise ValueError("signed attributes do not fit their 1024-bit input")
         sa = bytearray(rng.randrange(256) for _ in range(rng.randint(lo, hi)))
         sa[0] = 0x31
         o = p.ec_shift // 8
@@ -278,15 +317,15 @@ class PassportFactory:
         sa = bytes(sa)
         ki = rng.randrange(len(self.sig_keys))
         key = self.sig_keys[ki]
-        sig = pkcs1v15_sign(key, sa, sgh)
+        sig = pkcs1v15_sign(key, sa, sgh) if self.scheme == "pkcs1" else pss_sign(key, sa, sgh, self.salt_len, rng)
         sk = hashlib.sha256(ec).hexdigest()[:62]
         inputs = {
             "dg1": [str(b) for b in bytes_to_bits(sha_pad(dg1, self.block))],
             "dg15": [str(b) for b in bytes_to_bits(sha_pad(dg15, self.block))] if p.aa_algo else [],
             "signedAttributes": [str(b) for b in bytes_to_bits(sha_pad(sa, self.block))],
             "encapsulatedContent": [str(b) for b in bytes_to_bits(sha_pad(ec, self.block))],
-            "pubkey": [str(c) for c in chunks_le(key.n, 64, 32)],
-            "signature": [str(c) for c in chunks_le(sig, 64, 32)],
+            "pubkey": [str(c) for c in chunks_le(key.n, 64, self.key_bits // 64)],
+            "signature": [str(c) for c in chunks_le(sig, 64, self.key_bits // 64)],
             "skIdentity": "0x" + sk,
             "slaveMerkleRoot": "0x" + format(self._roots[ki], "x"),
             "slaveMerkleInclusionBranches": ["0"] * TREE_DEPTH,

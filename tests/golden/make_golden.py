@@ -55,7 +55,7 @@ def golden(name, sym_path, inputs_list, n_pub, n_samples=4096):
 
 
 def main():
-    which = sys.argv[1:] or ["poseidon2", "sha256_1", "smt80", "c3"]
+    which = sys.argv[1:] or ["poseidon2", "sha256_1", "smt80", "query80", "c3", "c4_sig3", "c4_sig10", "c4_sig13"]
     if "poseidon2" in which:
         golden("poseidon2", os.path.join(ART, "poseidon2.sym"), [{"in": ["1", "2"]}, {"in": ["0", str(co.P - 1)]}], 1)
     if "sha256_1" in which:
@@ -70,6 +70,18 @@ def main():
         for key in (12345, 2 ** 200 + 17):
             ins.append({"root": str(poseidon([key, key, 1])), "leaf": str(key), "key": str(key), "siblings": ["0"] * 80})
         golden("smt80", os.path.join(ART, "smt80.sym"), ins, 2)
+    from passport_zk_circuits_b200.artifacts import C4_VARIANTS
+    for name, prm in C4_VARIANTS.items():
+        if name in which:
+            fac = PassportFactory(prm, seed=42, n_sig_keys=1, n_aa_keys=1)
+            sym = os.path.join(ART, name + ".sym")
+            if not os.path.exists(sym):
+                sym += ".local"
+            golden(name, sym, [fac.make(0).inputs], 5, n_samples=2048)
+    if "query80" in which:
+        from passport_zk_circuits_b200.query_inputs import make_query_input
+        golden("query80", os.path.join(ART, "query80.sym"),
+               [make_query_input(0, seed=7, selector=39), make_query_input(1, seed=7, selector=255)], 23)
     if "c3" in which:
         fac = PassportFactory(C3, seed=42, n_sig_keys=2, n_aa_keys=2)
         sym = os.path.join(ART, "c3.sym")

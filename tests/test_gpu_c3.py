@@ -76,3 +76,69 @@ def test_c3_golden_wtns_bytes(c3):
     blob = calc.calculateWTNSBin(ins[0])
     assert blob[:4] == b"wtns" and len(blob) == 76 + 32 * calc.n_wires
     assert hashlib.sha256(blob[76:]).hexdigest() == g["cases"][0]["wtns_data_sha256"]
+
+
+def _golden_inputs(calc, name):
+    import json
+    import os
+    from util import ROOT
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", name + ".json")))
+    size = {d["name"]: d["size"] for d in calc.meta["inputs"]}
+    ins = [{k: (list(v) if isinstance(v, str) and size[k] > 1 else v) for k, v in c["inputs"].items()} for c in g["cases"]]
+    return g, ins
+
+
+@pytest.mark.parametrize("name", ["c4_sig3", "c4_sig10", "c4_sig13"])
+def test_config4_variants(name):
+    """SHA-1 + RSA PKCS#1 v1.5 (SIG 3), RSA-PSS e=3 (SIG 10), RSA-PSS SHA-384 with 1024-bit blocks (SIG 13):
+    golden .wtns bytes from the Python oracle, then a small synthetic batch against the C oracle."""
+    import hashlib
+    from passport_zk_circuits_b200.artifacts import C4_VARIANTS
+    prog = W.artifact(name)
+    calc = W.WitnessCalculator(prog, device=0)
+    g, ins = _golden_inputs(calc, name)
+    res = calc.calculateWitnessBatch(ins, export_lanes=range(len(ins)))
+    for j, case in enumerate(g["cases"]):
+        assert res.status[j] == 0
+        assert hashlib.sha256(res.witnesses[j].tobytes()).hexdigest() == case["wtns_data_sha256"]
+    fac = PassportFactory(C4_VARIANTS[name], seed=11, n_sig_keys=1, n_aa_keys=1)
+    B = 6
+    inp = W.pack_inputs_fast(calc.meta, [fac.make(i).inputs for i in range(B)])
+    d = {x["name"]: x for x in calc.meta["inputs"]}
+    inp[2, d["signature"]["offset"] + 1, 0] ^= np.uint64(4)
+    out = calc.calculateWitnessBatch(inp)
+    ref = oracle_ref.RefProgram(prog)
+    for b in range(B):
+        st, fb, wit = ref.witness(inp[b], want_witness=True)
+        assert int(out.status[b]) == st and int(out.first_bad[b]) == fb, (b, int(out.status[b]), st)
+        assert np.array_equal(out.public[b], wit[1:1 + calc.n_public])
+    assert out.status[2] != 0 and (np.delete(out.status, 2) == 0).all()
+    calc.close()
+
+
+def test_config2_query_identity():
+    """queryIdentity(80): golden public signals / .wtns bytes, all selectors, enforced SMT inclusion."""
+    import hashlib
+    from passport_zk_circuits_b200.query_inputs import make_query_input
+    prog = W.artifact("query80")
+    calc = W.WitnessCalculator(prog, device=0)
+    g, ins = _golden_inputs(calc, "query80")
+    res = calc.calculateWitnessBatch(ins, export_lanes=range(len(ins)))
+    for j, case in enumerate(g["cases"]):
+        assert res.status[j] == 0
+        assert hashlib.sha256(res.witnesses[j].tobytes()).hexdigest() == case["wtns_data_sha256"]
+        assert [str(v) for v in res.public_ints(j)] == case["public"]
+    B = 150
+    objs = [make_query_input(i, seed=3, selector=(i * 37) & 0xFF) for i in range(B)]
+    objs[17]["idStateRoot"] = str(int(objs[17]["idStateRoot"]) ^ 1)        # not in the tree any more
+    inp = W.pack_inputs_fast(calc.meta, objs)
+    out = calc.calculateWitnessBatch(inp, export_lanes=[0, 17, B - 1])
+    ref = oracle_ref.RefProgram(prog)
+    for b in range(B):
+        st, fb, wit = ref.witness(inp[b], want_witness=True)
+        assert int(out.status[b]) == st and int(out.first_bad[b]) == fb
+        assert np.array_equal(out.public[b], wit[1:1 + calc.n_public])
+        if b in (0, 17, B - 1):
+            assert np.array_equal(out.witnesses[[0, 17, B - 1].index(b)], wit)
+    assert out.status[17] & W.STATUS_CONSTRAINT and (np.delete(out.status, 17) == 0).all()
+    calc.close()
