@@ -396,78 +396,74 @@ __device__ __forceinline__ bool check_row_int(const uint4* recs, u32 na, u32 nb,
   return plo == Clo && phi == Chi;
 }
 
-__device__ __noinline__ void lin_eval_stream(const StreamCoefs sc, const uint4* recs, u32 k0, u32 n, const u64* Ul,
-                                             const u64* Fl, u64 L, u32 cells, u32 NT, LinVal& out) {
-  out.i.v[0] = out.i.v[1] = out.i.v[2] = 0;
-  out.f[0] = out.f[1] = out.f[2] = out.f[3] = 0;
-  out.has_f = false;
-  for (u32 k = k0; k < k0 + n; k++) {
-    const uint2 tw = row_term(recs, k);
+// One linear combination of a CHECK_F row accumulated directly in Montgomery form.
+//   F wire, coefficient +-1      : modular add / sub
+//   F wire, other coefficient    : one Montgomery product
+//   proven bit (PZK_TERM_BIT)    : conditional add of the coefficient
+//   other narrow wire            : |v| * (c R^2) -> one Montgomery product, sign applied after
+__device__ __forceinline__ void lin_field(const StreamCoefs sc, const uint2* terms, u32 k0, u32 k1, const u64* Ul,
+                                          const u64* Fl, u64 L, u32 cells, u64* acc) {
+  acc[0] = acc[1] = acc[2] = acc[3] = 0;
+  for (u32 k = k0; k < k1; k++) {
+    const uint2 tw = __ldg(terms + k);
     const u32 ref = tw.x, ci = tw.y;
-    const u32 kind = __ldg(sc.coef_kind + ci);
-    if (ref == PZK_REF_ONE) {
-      if (kind) acc_mac(out.i, __ldg(sc.coef_mag + ci), 1, kind == 2);
-      else { u64 c[4]; ldPool(reinterpret_cast<const u64*>(sc.coefs), ci * 3 + 1, c); fr_add(out.f, out.f, c); out.has_f = true; }
+    const u64* cbase = reinterpret_cast<const u64*>(sc.coefs);
+    if (ref == PZK_REF_ONE) { u64 c[4]; ldPool(cbase, ci * 3 + 1, c); fr_add(acc, acc, c); continue; }
+    if (ref & PZK_TERM_BIT) {
+      if (TERM_U(ref) & 1) { u64 c[4]; ldPool(cbase, ci * 3 + 1, c); fr_add(acc, acc, c); }
       continue;
     }
     const u32 cls = PZK_REF_CLS(ref);
-    if (ref & PZK_TERM_BIT) {  // proven bit: conditional add of the Montgomery coefficient
-      if (TERM_U(ref) & 1) { u64 c[4]; ldPool(reinterpret_cast<const u64*>(sc.coefs), ci * 3 + 1, c); fr_add(out.f, out.f, c); }
-      out.has_f = true;
-      continue;
-    }
     if (cls < 2) {
       u64 v = TERM_U(ref);
-      bool vneg = (cls == 1) && ((long long)v < 0);
-      u64 vm = vneg ? (u64)(-(long long)v) : v;
-      if (kind) acc_mac(out.i, __ldg(sc.coef_mag + ci), vm, (kind == 2) != vneg);
-      else {
-        u64 c[4], w[4] = {vm, 0, 0, 0}, r[4];
-        ldPool(reinterpret_cast<const u64*>(sc.coefs), ci * 3 + 2, c);
-        fr_mul(r, c, w);
-        if (vneg) fr_sub(out.f, out.f, r); else fr_add(out.f, out.f, r);
-        out.has_f = true;
-      }
+      const bool vneg = (cls == 1) && ((long long)v < 0);
+      if (vneg) v = (u64)(-(long long)v);
+      u64 c[4], w[4] = {v, 0, 0, 0}, r[4];
+      ldPool(cbase, ci * 3 + 2, c);  // c * R^2
+      fr_mul(r, c, w);
+      if (vneg) fr_sub(acc, acc, r); else fr_add(acc, acc, r);
     } else {
       u64 w[4];
-      ldFo(Fl, L, cells, NT, (ref & PZK_TERM_CELL) ? (PZK_OPERAND_CELL | (ref & 0xffffu)) : PZK_REF_SLOT(ref), w);
+      ldFo(Fl, L, cells, 0, (ref & PZK_TERM_CELL) ? (PZK_OPERAND_CELL | (ref & 0xffffu)) : PZK_REF_SLOT(ref), w);
+      const u32 kind = __ldg(sc.coef_kind + ci);
       if (kind && __ldg(sc.coef_mag + ci) == 1) {
-        if (kind == 1) fr_add(out.f, out.f, w); else fr_sub(out.f, out.f, w);
+        if (kind == 1) fr_add(acc, acc, w); else fr_sub(acc, acc, w);
       } else {
         u64 c[4], r[4];
-        ldPool(reinterpret_cast<const u64*>(sc.coefs), ci * 3 + 1, c);
+        ldPool(cbase, ci * 3 + 1, c);  // c * R
         fr_mul(r, c, w);
-        fr_add(out.f, out.f, r);
+        fr_add(acc, acc, r);
       }
-      out.has_f = true;
     }
   }
 }
+
 __device__ __noinline__ bool check_row_field(const StreamCoefs sc, const uint4* recs, u32 na, u32 nb, u32 nc,
                                              const u64* Ul, const u64* Fl, u64 L, u32 cells, u32 NT) {
-  LinVal A, B, C;
-  lin_eval_stream(sc, recs, na + nb, nc, Ul, Fl, L, cells, NT, C);
-  if (na == 0 || nb == 0) {
-    if (!C.has_f) return acc_is_zero(C.i);
-    u64 c[4]; lin_to_field(C, c); return fr_is_zero(c);
+  (void)NT;
+  const uint2* terms = reinterpret_cast<const uint2*>(recs);
+  u64 c[4];
+  lin_field(sc, terms, na + nb, na + nb + nc, Ul, Fl, L, cells, c);
+  if (na == 0 || nb == 0) return fr_is_zero(c);
+  // narrow x narrow with unit coefficients (the limb products of the big-integer multipliers):
+  // exact 128-bit integer product and ONE conversion instead of three field products
+  if (na == 1 && nb == 1) {
+    const uint2 ta = __ldg(terms), tb = __ldg(terms + 1);
+    if (ta.x < PZK_REF_ONE_LIST && tb.x < PZK_REF_ONE_LIST && PZK_REF_CLS(ta.x) == 0 && PZK_REF_CLS(tb.x) == 0 &&
+        !((ta.x | tb.x) & PZK_TERM_BIT)) {
+      const u32 ka = __ldg(sc.coef_kind + ta.y), kb = __ldg(sc.coef_kind + tb.y);
+      if (ka && kb && __ldg(sc.coef_mag + ta.y) == 1 && __ldg(sc.coef_mag + tb.y) == 1) {
+        const u64 va = TERM_U(ta.x), vb = TERM_U(tb.x);
+        u64 w[4] = {va * vb, __umul64hi(va, vb), 0, 0}, pf[4];
+        fr_to_mont(pf, w);
+        if ((ka == 2) != (kb == 2)) fr_neg(pf, pf);
+        return fr_eq(pf, c);
+      }
+    }
   }
-  lin_eval_stream(sc, recs, 0, na, Ul, Fl, L, cells, NT, A);
-  lin_eval_stream(sc, recs, na, nb, Ul, Fl, L, cells, NT, B);
-  if (!A.has_f && !B.has_f && acc_fits_i64(A.i) && acc_fits_i64(B.i)) {
-    // integer x integer: exact 128-bit product, one conversion instead of three field products
-    long long ia = (long long)A.i.v[0], ib = (long long)B.i.v[0];
-    bool neg = (ia < 0) != (ib < 0);
-    u64 am = ia < 0 ? (u64)(-ia) : (u64)ia, bm = ib < 0 ? (u64)(-ib) : (u64)ib;
-    Acc192 prod; prod.v[0] = prod.v[1] = prod.v[2] = 0;
-    acc_mac(prod, am, bm, neg);
-    if (!C.has_f) return prod.v[0] == C.i.v[0] && prod.v[1] == C.i.v[1] && prod.v[2] == C.i.v[2];
-    u64 pf[4], c[4];
-    acc_to_field(prod, pf);
-    lin_to_field(C, c);
-    return fr_eq(pf, c);
-  }
-  u64 a[4], b[4], c[4], ab[4];
-  lin_to_field(A, a); lin_to_field(B, b); lin_to_field(C, c);
+  u64 a[4], b[4], ab[4];
+  lin_field(sc, terms, 0, na, Ul, Fl, L, cells, a);
+  lin_field(sc, terms, na, na + nb, Ul, Fl, L, cells, b);
   fr_mul(ab, a, b);
   return fr_eq(ab, c);
 }
@@ -609,22 +605,20 @@ __global__ void __launch_bounds__(128, 8) eval_kernel(EvalParams p) {
       case PZK_CHECK_I64: {
         // |A|,|B|,|A*B|,|C| < 2^63 proven at compile time: wrapping 64-bit arithmetic is exact
         if (check_rows) {
-          const uint4* recs = ops + pc + 1;
+          const uint2* terms = reinterpret_cast<const uint2*>(ops + pc + 1);
           const u32 na = imm16, nab = na + (a & 0xffffu), tot = nab + (a >> 16);
           long long A = 0, B = 0, C = 0;
-          for (u32 k = 0; k < tot; k += 2) {
-            const uint4 t = __ldg(recs + (k >> 1));
-            {
-              long long v = (t.x >= PZK_REF_ONE_LIST) ? 1ll : (long long)TERM_U(t.x);
-              long long m = (long long)(int)t.y * v;
-              if (k < na) A += m; else if (k < nab) B += m; else C += m;
-            }
-            if (k + 1 < tot) {
-              long long v = (t.z >= PZK_REF_ONE_LIST) ? 1ll : (long long)TERM_U(t.z);
-              long long m = (long long)(int)t.w * v;
-              if (k + 1 < na) A += m; else if (k + 1 < nab) B += m; else C += m;
-            }
-          }
+          u32 k = 0;
+#define I64_TERM(acc)                                                                         \
+  {                                                                                           \
+    const uint2 t = __ldg(terms + k);                                                         \
+    const long long v = (t.x >= PZK_REF_ONE_LIST) ? 1ll : (long long)TERM_U(t.x);             \
+    acc += (long long)(int)t.y * v;                                                           \
+  }
+          for (; k < na; k++) I64_TERM(A)
+          for (; k < nab; k++) I64_TERM(B)
+          for (; k < tot; k++) I64_TERM(C)
+#undef I64_TERM
           const bool ok = (na == 0 || nab == na) ? (C == 0) : (A * B == C);
           if (!ok && (unsigned long long)dst < bad) bad = dst;
         }
