@@ -13,6 +13,7 @@
 #include "compiler.hpp"
 #include "pzk.h"
 #include "pzk_kernels.cuh"
+#include "pzk_r1cs.cuh"
 
 using namespace pzkd;
 
@@ -619,41 +620,71 @@ static int check_batch_impl(R1csHost& r, const uint8_t* witnesses_le32, uint64_t
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_err(err, err_len, "no CUDA device"); return PZK_ENODEVICE; }
 #define CKE(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_err(err, err_len, std::string(#call) + ": " + cudaGetErrorString(e_)); return PZK_ECUDA; } } while (0)
   CKE(cudaSetDevice(cuda_device));
-  PzkRow* d_rows; PzkTerm* d_terms; PzkCoef* d_coefs; unsigned char* d_kind; u64* d_mag;
+  // tiles of the A/B/C stream: at most R1CS_TILE_ROWS rows and R1CS_TILE_TERMS terms, even first term
+  std::vector<R1csTile> tiles;
+  {
+    size_t i = 0, n = r.rows.size();
+    while (i < n) {
+      R1csTile t; t.row0 = (uint32_t)i; t.term0 = r.rows[i].term_off & ~1u;
+      uint32_t end_term = r.rows[i].term_off;
+      uint32_t nr = 0;
+      while (i < n && nr < R1CS_TILE_ROWS) {
+        uint32_t nt = r.rows[i].na + r.rows[i].nb + r.rows[i].nc;
+        if (nt + 2 > R1CS_TILE_TERMS) { set_err(err, err_len, "r1cs: a constraint has too many terms for the streaming tile"); return PZK_EFORMAT; }
+        if (r.rows[i].term_off + nt - t.term0 + 1 > R1CS_TILE_TERMS) break;
+        end_term = r.rows[i].term_off + nt; nr++; i++;
+      }
+      t.n_rows = nr; t.n_terms = end_term - t.term0;
+      tiles.push_back(t);
+    }
+  }
+  PzkRow* d_rows; PzkTerm* d_terms; PzkCoef* d_coefs; unsigned char* d_kind; u64* d_mag; R1csTile* d_tiles;
   std::vector<unsigned char> kind; std::vector<u64> mag;
   classify_coefs(r.coefs.data(), (uint32_t)r.coefs.size(), kind, mag);
+  std::vector<PzkTerm> terms_padded = r.terms;
+  terms_padded.resize(r.terms.size() + 4, PzkTerm{0, 0});
   CKE(upload(&d_rows, r.rows.data(), r.rows.size() * sizeof(PzkRow)));
-  CKE(upload(&d_terms, r.terms.data(), r.terms.size() * sizeof(PzkTerm)));
+  CKE(upload(&d_terms, terms_padded.data(), terms_padded.size() * sizeof(PzkTerm)));
   CKE(upload(&d_coefs, r.coefs.data(), r.coefs.size() * sizeof(PzkCoef)));
   CKE(upload(&d_kind, kind.data(), kind.size()));
   CKE(upload(&d_mag, mag.data(), mag.size() * 8));
+  CKE(upload(&d_tiles, tiles.data(), tiles.size() * sizeof(R1csTile)));
+  CKE(cudaFuncSetAttribute(r1cs_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R1CS_SMEM_BYTES));
   size_t free_b = 0, total_b = 0;
   CKE(cudaMemGetInfo(&free_b, &total_b));
-  uint64_t per_lane = (uint64_t)r.n_wires * 64;  // AoS staging + SoA plane
-  uint64_t L = std::max<uint64_t>(1, (uint64_t)(free_b * 0.8) / per_lane);
-  if (L > batch) L = batch;
-  uint64_t Lp = (L + 31) / 32 * 32;
-  u64 *d_wit, *d_F; u32* d_status; unsigned long long* d_bad; u64* d_U;
+  uint64_t per_lane = (uint64_t)r.n_wires * 64;  // AoS staging + blocked Montgomery plane
+  uint64_t L = std::max<uint64_t>(32, (uint64_t)(free_b * 0.8) / per_lane / 32 * 32);
+  if (L > (batch + 31) / 32 * 32) L = (batch + 31) / 32 * 32;
+  u64 *d_wit, *d_F; u32* d_status; unsigned long long* d_bad;
   CKE(cudaMalloc((void**)&d_wit, L * r.n_wires * 32));
-  CKE(cudaMalloc((void**)&d_F, Lp * r.n_wires * 32));
-  CKE(cudaMalloc((void**)&d_U, 16));
-  CKE(cudaMalloc((void**)&d_status, batch * 4));
-  CKE(cudaMalloc((void**)&d_bad, batch * 8));
-  CKE(cudaMemset(d_status, 0, batch * 4));
-  CKE(cudaMemset(d_bad, 0xff, batch * 8));
+  CKE(cudaMalloc((void**)&d_F, L * r.n_wires * 32));
+  CKE(cudaMemset(d_F, 0, L * r.n_wires * 32));  // padding lanes of the last warp read zeros
+  CKE(cudaMalloc((void**)&d_status, (batch + 32) * 4));
+  CKE(cudaMalloc((void**)&d_bad, (batch + 32) * 8));
+  CKE(cudaMemset(d_status, 0, (batch + 32) * 4));
+  CKE(cudaMemset(d_bad, 0xff, (batch + 32) * 8));
   cudaEvent_t ea, eb; cudaEventCreate(&ea); cudaEventCreate(&eb);
   double total_ms = 0;
+  int n_sm = 148;
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, cuda_device);
   for (uint64_t base = 0; base < batch; base += L) {
     uint64_t n = std::min<uint64_t>(L, batch - base);
     CKE(cudaMemcpy(d_wit, witnesses_le32 + base * r.n_wires * 32, n * r.n_wires * 32, cudaMemcpyHostToDevice));
-    unsigned grid = (unsigned)((n + 127) / 128);
+    unsigned gridl = (unsigned)((n + 127) / 128);
     unsigned gy = (unsigned)std::min<uint64_t>(std::max<uint64_t>(r.n_wires / 64, 1), 4096);
-    load_witness_kernel<<<dim3(grid, gy), 128>>>(d_wit, r.n_wires, n, Lp, d_F, d_status + base);
-    CheckParams p;
-    p.rows = d_rows; p.n_rows = r.rows.size(); p.terms = d_terms; p.coefs = d_coefs; p.coef_kind = d_kind; p.coef_mag = d_mag;
-    p.U = d_U; p.F = d_F; p.L = Lp; p.n_lanes = n; p.status = d_status + base; p.first_bad = d_bad + base;
+    load_witness_blocked_kernel<<<dim3(gridl, gy), 128>>>(d_wit, r.n_wires, n, d_F, d_status + base);
+    R1csParams p;
+    p.rows = d_rows; p.terms = d_terms; p.tiles = d_tiles; p.n_tiles = (u32)tiles.size();
+    // enough chunks to fill the machine ~4 CTAs deep, at least 4 tiles per chunk when possible
+    uint64_t want_ctas = (uint64_t)n_sm * 4;
+    uint64_t chunks = std::max<uint64_t>(1, want_ctas / gridl);
+    if (chunks > tiles.size()) chunks = tiles.size();
+    p.tiles_per_chunk = (u32)((tiles.size() + chunks - 1) / chunks);
+    chunks = (tiles.size() + p.tiles_per_chunk - 1) / p.tiles_per_chunk;
+    p.coefs = d_coefs; p.coef_kind = d_kind; p.coef_mag = d_mag; p.F = d_F; p.n_wires = r.n_wires; p.n_lanes = n;
+    p.status = d_status + base; p.first_bad = d_bad + base;
     cudaEventRecord(ea);
-    check_kernel<<<grid, 128>>>(p);
+    r1cs_stream_kernel<<<dim3((unsigned)chunks, gridl), 128, R1CS_SMEM_BYTES>>>(p);
     cudaEventRecord(eb);
     CKE(cudaDeviceSynchronize());
     float ms = 0; cudaEventElapsedTime(&ms, ea, eb); total_ms += ms;
@@ -667,8 +698,8 @@ static int check_batch_impl(R1csHost& r, const uint8_t* witnesses_le32, uint64_t
   }
   if (kernel_ms) *kernel_ms = total_ms;
   cudaEventDestroy(ea); cudaEventDestroy(eb);
-  cudaFree(d_rows); cudaFree(d_terms); cudaFree(d_coefs); cudaFree(d_kind); cudaFree(d_mag);
-  cudaFree(d_wit); cudaFree(d_F); cudaFree(d_U); cudaFree(d_status); cudaFree(d_bad);
+  cudaFree(d_rows); cudaFree(d_terms); cudaFree(d_coefs); cudaFree(d_kind); cudaFree(d_mag); cudaFree(d_tiles);
+  cudaFree(d_wit); cudaFree(d_F); cudaFree(d_status); cudaFree(d_bad);
   return PZK_OK;
 }
 

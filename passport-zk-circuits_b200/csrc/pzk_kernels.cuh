@@ -3,8 +3,8 @@
 //   eval_kernel   : lane-per-witness interpreter of the typed linear SSA program
 //                   (what circom's generated wasm does for the reference, one passport at a time:
 //                   /root/reference/test/automatisationTest.js:40-50).
-//   check_kernel  : A.w * B.w == C.w for every constraint row of a segment, per lane
-//                   (checkConstraints, automatisationTest.js:51 / snarkjs `wtns check`).
+//                   Constraint rows are fused into the op stream (CHECK_* records); the
+//                   stand-alone checker for explicit witnesses is in pzk_r1cs.cuh.
 //   export_kernel : slot planes -> canonical 32-byte little-endian wires (.wtns section 2).
 //
 // Data layout (HBM): slot-major, lane-minor planes so that the 32 lanes of a warp touch one
@@ -195,153 +195,6 @@ __device__ __noinline__ u32 bigdiv_device(const u32* Lst, u64* Ul, u64 L) {
   }
   return st;
 }
-
-// ------------------------------------------------------------------------------------------
-// Constraint rows.  Terms on narrow (U / I) wires with small coefficients are accumulated as
-// exact integers (3 x 64-bit two's complement); everything else goes through Montgomery form.
-// A row whose three linear combinations stay integer and small is decided without a single
-// field multiplication (that is the SHA-256 bit logic: ~3/4 of all rows).
-// ------------------------------------------------------------------------------------------
-struct CheckParams {
-  const PzkRow* rows;
-  u64 n_rows;
-  const PzkTerm* terms;
-  const PzkCoef* coefs;
-  const unsigned char* coef_kind;  // 0 general, 1 = +small, 2 = -small
-  const u64* coef_mag;             // |coef| for kinds 1, 2
-  const u64* U;
-  const u64* F;
-  u64 L;
-  u64 n_lanes;
-  u32* status;
-  unsigned long long* first_bad;  // min failing constraint index, ~0 = none
-};
-
-struct Acc192 { u64 v[3]; };
-__device__ __forceinline__ void acc_mac(Acc192& a, u64 mag, u64 v, bool neg) {
-  u64 lo = mag * v, hi = __umul64hi(mag, v);
-  if (!neg) {
-    u64 t0 = a.v[0] + lo; u64 c0 = t0 < lo;
-    u64 t1 = a.v[1] + hi; u64 c1 = t1 < hi;
-    u64 t1b = t1 + c0; u64 c1b = t1b < c0;
-    a.v[0] = t0; a.v[1] = t1b; a.v[2] += c1 + c1b;
-  } else {
-    u64 b0 = a.v[0] < lo; u64 t0 = a.v[0] - lo;
-    u64 b1 = a.v[1] < hi; u64 t1 = a.v[1] - hi;
-    u64 b1b = t1 < b0; u64 t1b = t1 - b0;
-    a.v[0] = t0; a.v[1] = t1b; a.v[2] -= b1 + b1b;
-  }
-}
-// signed 192-bit integer -> Montgomery field element
-__device__ __forceinline__ void acc_to_field(const Acc192& a, u64* r) {
-  bool neg = (long long)a.v[2] < 0;
-  u64 m[4] = {a.v[0], a.v[1], a.v[2], 0};
-  if (neg) {
-    m[0] = ~m[0]; m[1] = ~m[1]; m[2] = ~m[2];
-    m[0] += 1; if (m[0] == 0) { m[1] += 1; if (m[1] == 0) m[2] += 1; }
-  }
-  fr_to_mont(r, m);
-  if (neg) fr_neg(r, r);
-}
-
-struct LinVal { Acc192 i; u64 f[4]; bool has_f; };
-
-__device__ __forceinline__ void lin_eval(const CheckParams& p, const PzkTerm* t, u32 n, const u64* Ul, const u64* Fl,
-                                         LinVal& out) {
-  out.i.v[0] = out.i.v[1] = out.i.v[2] = 0;
-  out.f[0] = out.f[1] = out.f[2] = out.f[3] = 0;
-  out.has_f = false;
-  const u64 L = p.L;
-  for (u32 k = 0; k < n; k++) {
-    const uint2 tw = __ldg(reinterpret_cast<const uint2*>(t + k));
-    const u32 ref = tw.x, ci = tw.y;
-    const u32 kind = __ldg(p.coef_kind + ci);
-    if (ref == PZK_REF_ONE) {
-      if (kind) acc_mac(out.i, __ldg(p.coef_mag + ci), 1, kind == 2);
-      else { u64 c[4]; ldPool(reinterpret_cast<const u64*>(p.coefs), ci * 3 + 1, c); fr_add(out.f, out.f, c); out.has_f = true; }
-      continue;
-    }
-    const u32 cls = PZK_REF_CLS(ref), slot = PZK_REF_SLOT(ref);
-    if (cls < 2) {
-      u64 v = Ul[(u64)slot * L];
-      bool vneg = (cls == 1) && ((long long)v < 0);
-      u64 vm = vneg ? (u64)(-(long long)v) : v;
-      if (kind) acc_mac(out.i, __ldg(p.coef_mag + ci), vm, (kind == 2) != vneg);
-      else {
-        u64 c[4], w[4] = {vm, 0, 0, 0}, r[4];
-        ldPool(reinterpret_cast<const u64*>(p.coefs), ci * 3 + 2, c);  // c * R^2
-        fr_mul(r, c, w);
-        if (vneg) fr_sub(out.f, out.f, r); else fr_add(out.f, out.f, r);
-        out.has_f = true;
-      }
-    } else {
-      u64 w[4];
-      ldF(Fl, L, slot, w);
-      if (kind && __ldg(p.coef_mag + ci) == 1) {
-        if (kind == 1) fr_add(out.f, out.f, w); else fr_sub(out.f, out.f, w);
-      } else {
-        u64 c[4], r[4];
-        ldPool(reinterpret_cast<const u64*>(p.coefs), ci * 3 + 1, c);  // c * R
-        fr_mul(r, c, w);
-        fr_add(out.f, out.f, r);
-      }
-      out.has_f = true;
-    }
-  }
-}
-__device__ __forceinline__ bool acc_is_zero(const Acc192& a) { return (a.v[0] | a.v[1] | a.v[2]) == 0; }
-__device__ __forceinline__ bool acc_fits_i64(const Acc192& a) {
-  u64 ext = (u64)((long long)a.v[0] >> 63);
-  return a.v[1] == ext && a.v[2] == ext;
-}
-__device__ __forceinline__ void lin_to_field(const LinVal& l, u64* r) {
-  if (acc_is_zero(l.i)) { r[0] = l.f[0]; r[1] = l.f[1]; r[2] = l.f[2]; r[3] = l.f[3]; return; }
-  u64 t[4];
-  acc_to_field(l.i, t);
-  fr_add(r, t, l.f);
-}
-
-__global__ void __launch_bounds__(128) check_kernel(CheckParams p) {
-  const u64 lane = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (lane >= p.n_lanes) return;
-  const u64* Ul = p.U + lane;
-  const u64* Fl = p.F + lane;
-  unsigned long long bad = ~0ull;
-  for (u64 r = 0; r < p.n_rows; r++) {
-    const uint4 rw = __ldg(reinterpret_cast<const uint4*>(p.rows + r));
-    const u32 term_off = rw.x, na = rw.y & 0xffffu, nb = rw.y >> 16, nc = rw.z & 0xffffu, index = rw.w;
-    const PzkTerm* t = p.terms + term_off;
-    LinVal A, B, C;
-    lin_eval(p, t + na + nb, nc, Ul, Fl, C);
-    bool ok;
-    if (na == 0 || nb == 0) {
-      if (!C.has_f) ok = acc_is_zero(C.i);
-      else { u64 c[4]; lin_to_field(C, c); ok = fr_is_zero(c); }
-    } else {
-      lin_eval(p, t, na, Ul, Fl, A);
-      lin_eval(p, t + na, nb, Ul, Fl, B);
-      if (!A.has_f && !B.has_f && !C.has_f && acc_fits_i64(A.i) && acc_fits_i64(B.i)) {
-        long long a = (long long)A.i.v[0], b = (long long)B.i.v[0];
-        bool neg = (a < 0) != (b < 0);
-        u64 am = a < 0 ? (u64)(-a) : (u64)a, bm = b < 0 ? (u64)(-b) : (u64)b;
-        Acc192 prod; prod.v[0] = prod.v[1] = prod.v[2] = 0;
-        acc_mac(prod, am, bm, neg);
-        ok = prod.v[0] == C.i.v[0] && prod.v[1] == C.i.v[1] && prod.v[2] == C.i.v[2];
-      } else {
-        u64 a[4], b[4], c[4], ab[4];
-        lin_to_field(A, a); lin_to_field(B, b); lin_to_field(C, c);
-        fr_mul(ab, a, b);
-        ok = fr_eq(ab, c);
-      }
-    }
-    if (!ok && (unsigned long long)index < bad) bad = index;
-  }
-  if (bad != ~0ull) {
-    p.status[lane] |= PZK_LANE_CONSTRAINT;
-    if (bad < p.first_bad[lane]) p.first_bad[lane] = bad;
-  }
-}
-
 
 // ---- rows fused into the op stream ---------------------------------------------------------
 // term k of a row lives in record (k >> 1), words (2*(k&1), 2*(k&1)+1)
@@ -744,21 +597,6 @@ __global__ void __launch_bounds__(128) export_rows_kernel(ExportParams p) {
     u64* dst = p.out + (p.lane_base * p.out_wires + (wire - p.wire_off)) * 4;
     reinterpret_cast<ulonglong2*>(dst)[0] = make_ulonglong2(w[0], w[1]);
     reinterpret_cast<ulonglong2*>(dst)[1] = make_ulonglong2(w[2], w[3]);
-  }
-}
-
-// canonical AoS witnesses [lane][n_wires][4] -> Montgomery SoA F plane (generic wtns check)
-__global__ void __launch_bounds__(128) load_witness_kernel(const u64* wit, u64 n_wires, u64 n_lanes, u64 L, u64* F,
-                                                           u32* status) {
-  const u64 lane = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (lane >= n_lanes) return;
-  for (u64 wv = blockIdx.y; wv < n_wires; wv += gridDim.y) {
-    const ulonglong2* ip = reinterpret_cast<const ulonglong2*>(wit + (lane * n_wires + wv) * 4);
-    ulonglong2 lo = ip[0], hi = ip[1];
-    u64 v[4] = {lo.x, lo.y, hi.x, hi.y}, r[4];
-    if (geq_p(v)) { atomicOr(status + lane, PZK_LANE_INPUT_RANGE); reduce_p(v); }
-    fr_to_mont(r, v);
-    stF(F + lane, L, (u32)wv, r);
   }
 }
 

@@ -170,6 +170,25 @@ def artifact(name):
                    "/root/reference is mounted")
 
 
+def artifact_r1cs(name):
+    """Path of a prebuilt .r1cs in artifacts/ (large ones travel xz-packed)."""
+    path = os.path.join(ARTIFACT_DIR, name + ".r1cs")
+    if os.path.exists(path):
+        return path
+    for packed in (path + ".xz",):
+        if os.path.exists(packed):
+            tmp = path + ".tmp%d" % os.getpid()
+            with lzma.open(packed, "rb") as g, open(tmp, "wb") as f:
+                while True:
+                    chunk = g.read(1 << 24)
+                    if not chunk:
+                        break
+                    f.write(chunk)
+            os.replace(tmp, path)
+            return path
+    raise PzkError(f"{name}.r1cs is missing from {ARTIFACT_DIR}")
+
+
 # ----------------------------------------------------------------------------- inputs
 def _flatten(v, out):
     if isinstance(v, (list, tuple, np.ndarray)):

@@ -161,3 +161,33 @@ def test_golden_small(name):
     for j, case in enumerate(g["cases"]):
         assert res.status[j] == 0
         assert hashlib.sha256(res.witnesses[j].tobytes()).hexdigest() == case["wtns_data_sha256"]
+
+
+def test_r1cs_stream_kernel_smt80():
+    """Stand-alone `wtns check` kernel (rows-parallel, TMA-staged A/B/C stream) on 70 explicit
+    witnesses of the SMT(80) circuit; corrupted wires must give the first failing constraint index
+    the Python restatement of snarkjs' loop gives."""
+    import formats
+    import os
+    from util import ROOT
+    prefix = os.path.join(ROOT, "artifacts", "smt80")
+    prog = oracle_ref.RefProgram(prefix + ".pzkp")
+    keys = [777 + 31 * i + (i << 120) for i in range(70)]
+    inp = smt_inputs(prog.meta, keys)
+    calc = W.WitnessCalculator(prefix + ".pzkp", 0)
+    res = calc.calculateWitnessBatch(inp, export_lanes=range(70))
+    wit = res.witnesses.copy()
+    r1 = formats.read_r1cs(prefix + ".r1cs")
+    rng = np.random.default_rng(5)
+    bad_lanes = {3: 100, 40: 90000, 69: int(rng.integers(2, prog.n_wires))}
+    for lane, wire in bad_lanes.items():
+        wit[lane, wire, 0] ^= np.uint64(1)
+    ok, first, ms = W.r1cs_check_batch(prefix + ".r1cs", wit)
+    for lane in range(70):
+        if lane in bad_lanes:
+            w = [int.from_bytes(wit[lane, i].tobytes(), "little") for i in range(prog.n_wires)]
+            assert (bool(ok[lane]), int(first[lane])) == formats.wtns_check(r1, w), lane
+            assert not ok[lane]
+        else:
+            assert ok[lane] and first[lane] == -1
+    assert ms > 0
