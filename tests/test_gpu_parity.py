@@ -191,3 +191,15 @@ def test_r1cs_stream_kernel_smt80():
         else:
             assert ok[lane] and first[lane] == -1
     assert ms > 0
+
+
+@pytest.mark.parametrize("name", ["mont_test", "inv_test", "tma_test"])
+def test_device_unit(name):
+    """tests/cuda/*.cu: PTX Montgomery product == plain formulation, inverse * x == 1, TMA + mbarrier staging."""
+    import os
+    import subprocess
+    from util import ROOT
+    exe = os.path.join(ROOT, "tests", "bin", name)
+    assert os.path.exists(exe), "run __graft_entry__.build() first"
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
