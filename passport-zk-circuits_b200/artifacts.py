@@ -25,11 +25,13 @@ def _wrapper(name, body):
 
 
 # SIGNATURE_TYPE 3 (RSA-2048 PKCS#1 v1.5 + SHA-1, SHA-1 data groups), 10 (RSA-PSS e=3, SHA-256),
-# 13 (RSA-PSS SHA-384 with 1024-bit hash blocks and a different EC shift / block counts)
+# 13 (RSA-PSS SHA-384 with 1024-bit hash blocks and a different EC shift / block counts),
+# 20 (ECDSA over NIST P-256 + SHA-256: 5.5 M constraints, long_div2 / mod_inv hint functions)
 C4_VARIANTS = {
     "c4_sig3": CircuitParams(3, 160, 3, 4, 600, 248, 1, 1496, 3, 256),
     "c4_sig10": CircuitParams(10, 256, 3, 4, 600, 248, 1, 1496, 3, 256),
     "c4_sig13": CircuitParams(13, 384, 3, 2, 320, 248, 1, 1496, 2, 256),
+    "c4_sig20": CircuitParams(20, 256, 3, 4, 600, 248, 1, 1496, 3, 256),
 }
 
 
@@ -66,9 +68,10 @@ def reference_circuits():
 
 
 OWN_CIRCUITS = {"t_mix": ("mix.circom", {"u": 16, "bits": 1}),
-                "t_bigdiv": ("bigdiv.circom", {"a": 64, "b": 64})}
+                "t_bigdiv": ("bigdiv.circom", {"a": 64, "b": 64}),
+                "t_earlyret": ("earlyret.circom", {"v": 16, "a": 64, "b": 64, "c": 1})}
 
-BIG = {"c3", "c4_sig3", "c4_sig10", "c4_sig13"}  # ship only the xz-packed program for these
+BIG = {"c3", "c4_sig3", "c4_sig10", "c4_sig13", "c4_sig20"}  # ship only the xz-packed program for these
 
 
 def _stale(out, deps):

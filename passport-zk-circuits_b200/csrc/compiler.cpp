@@ -164,6 +164,9 @@ struct Compiler::Impl {
   int fn_depth = 0;
   bool returned = false;
   Value ret_val;
+  // `return` under a signal-dependent condition: (condition, value) pairs of the running function;
+  // execution continues (functions are pure) and the results are merged with selects at the end
+  std::vector<std::vector<std::pair<SVal, Value>>> early_returns;
 
   CompileStats* stats = nullptr;
 
@@ -1285,10 +1288,17 @@ struct Compiler::Impl {
     bool sr = returned; Value sv_ret = ret_val;
     returned = false;
     if (++fn_depth > 400) fail(at, "function recursion too deep");
+    early_returns.emplace_back();
     exec(fd.body, fenv, nullptr);
     fn_depth--;
     if (!returned) fail(at, "function " + nm(e->name) + " did not return");
     Value out = ret_val;
+    {
+      std::vector<std::pair<SVal, Value>> er;
+      er.swap(early_returns.back());
+      early_returns.pop_back();
+      for (size_t k = er.size(); k-- > 0;) out = select_value(er[k].first, er[k].second, out, at);
+    }
     returned = sr; ret_val = sv_ret;
     if (konst) fn_memo[key] = out;
     return out;
@@ -1304,15 +1314,28 @@ struct Compiler::Impl {
     if (n != 64 || k < 2 || k > 64 || k + m > 128 || !args[3].arr || !args[4].arr) return false;
     if (args[3].a->v.size() < k + m || args[4].a->v.size() < k) return false;
     i128 lim = n == 64 ? U64_MAX_ : (((i128)1 << n) - 1);
-    std::vector<uint32_t> ids;
-    for (uint64_t i = 0; i < k + m; i++) { i128 hi; const SVal& s = args[3].a->v[i]; if (!exact_u(s, hi) || hi > lim) return false; }
-    for (uint64_t i = 0; i < k; i++) { i128 hi; const SVal& s = args[4].a->v[i]; if (!exact_u(s, hi) || hi > lim) return false; }
-    for (uint64_t i = 0; i < k + m; i++) if (args[3].a->v[i].kind == 1 && is_pending(args[3].a->v[i].id)) flush_inversions();
-    for (uint64_t i = 0; i < k; i++) if (args[4].a->v[i].kind == 1 && is_pending(args[4].a->v[i].id)) flush_inversions();
+    // a limb that is not provably < 2^64 (e.g. the top limb of prod(), a sum of three carries) is
+    // narrowed at run time: low 64 bits + an assertion that nothing was cut off
+    auto narrow_limb = [&](const SVal& s_) -> SVal {
+      i128 hi;
+      if (exact_u(s_, hi) && hi <= lim) return s_;
+      if (s_.kind == 0) return SVal::unk();
+      SVal nn = sv(to_N(s_));
+      uint32_t fits = new_value(CLS_U, 0, 1);
+      emit(PZK_N_FITS, fits, nn.id);
+      emit(PZK_ASSERT_NZ, 0, fits);
+      return n_low(nn, lim);
+    };
+    std::vector<SVal> la(k + m), lb(k);
+    for (uint64_t i = 0; i < k + m; i++) { la[i] = narrow_limb(args[3].a->v[i]); if (la[i].kind == 2) return false; }
+    for (uint64_t i = 0; i < k; i++) { lb[i] = narrow_limb(args[4].a->v[i]); if (lb[i].kind == 2) return false; }
+    // BIGDIV reads its operands through the list pool: none of them may still be deferred
+    for (uint64_t i = 0; i < k + m; i++) if (la[i].kind == 1 && is_pending(la[i].id)) flush_inversions();
+    for (uint64_t i = 0; i < k; i++) if (lb[i].kind == 1 && is_pending(lb[i].id)) flush_inversions();
     uint32_t off = (uint32_t)list_pool.size();
     list_pool.push_back((uint32_t)n); list_pool.push_back((uint32_t)k); list_pool.push_back((uint32_t)m);
-    for (uint64_t i = 0; i < k + m; i++) list_pool.push_back(u_operand(args[3].a->v[i]));
-    for (uint64_t i = 0; i < k; i++) list_pool.push_back(u_operand(args[4].a->v[i]));
+    for (uint64_t i = 0; i < k + m; i++) list_pool.push_back(u_operand(la[i]));
+    for (uint64_t i = 0; i < k; i++) list_pool.push_back(u_operand(lb[i]));
     out = zeros({2, 200});
     uint32_t first = 0;
     for (uint64_t i = 0; i <= m; i++) {
@@ -1560,18 +1583,48 @@ struct Compiler::Impl {
     }
   }
 
+  Value select_value(const SVal& cond, const Value& x, const Value& y, const Stmt* at) {
+    if (x.arr != y.arr) fail(at, "if-conversion: an array and a scalar meet");
+    if (!x.arr) return scalar(emit_select(cond, x.s, y.s, at));
+    if (x.a->v.size() != y.a->v.size()) fail(at, "if-conversion: array size mismatch");
+    Value out; out.arr = true; out.a = std::make_shared<AVal>(); out.a->dims = x.a->dims;
+    out.a->v.resize(x.a->v.size());
+    for (size_t i = 0; i < x.a->v.size(); i++) {
+      const SVal& p = x.a->v[i]; const SVal& q = y.a->v[i];
+      if (p.kind == q.kind && ((p.kind == 0 && p.c == q.c) || (p.kind == 1 && p.id == q.id))) out.a->v[i] = p;
+      else out.a->v[i] = emit_select(cond, p, q, at);
+    }
+    return out;
+  }
+
   // if (signal-dependent) { ... } else { ... } on variables only: run both arms on copies of
-  // the environment and merge every changed variable with a select (if-conversion).
+  // the environment and merge every changed variable with a select (if-conversion).  An arm that
+  // returns (inside a function) records (condition, value) and contributes nothing to the merge.
   void exec_data_if(Stmt* s, const SVal& cond, Env& env, Ctx* ctx) {
     std::vector<int> names; collect_assigned(s->s1, names); collect_assigned(s->s2, names);
     Env e1 = env, e2 = env;
     bool r0 = returned;
+    // returns recorded by nested data-dependent ifs inside an arm only happen on that arm's path:
+    // their conditions get the arm's condition ANDed in
+    size_t er0 = early_returns.empty() ? 0 : early_returns.back().size();
     exec(s->s1, e1, ctx);
     bool r1 = returned; Value rv1 = ret_val; returned = r0;
+    size_t er1 = early_returns.empty() ? 0 : early_returns.back().size();
     if (s->s2) exec(s->s2, e2, ctx);
     bool r2 = returned; Value rv2 = ret_val; returned = r0;
-    if (r1 || r2) fail(s, "return under a signal-dependent condition is not supported");
-    (void)rv1; (void)rv2;
+    size_t er2 = early_returns.empty() ? 0 : early_returns.back().size();
+    if (r1 || r2 || er2 > er0) {
+      if (ctx || early_returns.empty()) fail(s, "return under a signal-dependent condition outside a function");
+      SVal c1 = truthy(cond, s);
+      SVal c0 = emit_bin(O_EQ, c1, SVal::konst(U256()), s);
+      auto& er = early_returns.back();
+      for (size_t i = er0; i < er1; i++) er[i].first = emit_bin(O_BAND, er[i].first, c1, s);
+      for (size_t i = er1; i < er2; i++) er[i].first = emit_bin(O_BAND, er[i].first, c0, s);
+      // earlier entries win at the merge, so an arm's own return goes after its nested ones
+      if (r1) er.insert(er.begin() + er1, std::make_pair(c1, rv1));
+      if (r2) er.emplace_back(c0, rv2);
+    }
+    if (r1 && r2) { returned = true; ret_val = rv2; return; }  // both arms left the function
     std::sort(names.begin(), names.end());
     names.erase(std::unique(names.begin(), names.end()), names.end());
     for (int n : names) {
@@ -1579,17 +1632,9 @@ struct Compiler::Impl {
       if (!dst) continue;  // declared inside the arm
       Value* a = find_var(e1, n); Value* b = find_var(e2, n);
       if (!a || !b) continue;
-      if (a->arr != b->arr) fail(s, "if-conversion: shape mismatch for " + nm(n));
-      if (!a->arr) { *dst = scalar(emit_select(cond, a->s, b->s, s)); continue; }
-      if (a->a->v.size() != b->a->v.size()) fail(s, "if-conversion: size mismatch for " + nm(n));
-      Value out; out.arr = true; out.a = std::make_shared<AVal>(); out.a->dims = a->a->dims;
-      out.a->v.resize(a->a->v.size());
-      for (size_t i = 0; i < a->a->v.size(); i++) {
-        const SVal& x = a->a->v[i]; const SVal& y = b->a->v[i];
-        if (x.kind == y.kind && ((x.kind == 0 && x.c == y.c) || (x.kind == 1 && x.id == y.id))) out.a->v[i] = x;
-        else out.a->v[i] = emit_select(cond, x, y, s);
-      }
-      *dst = out;
+      if (r1) { *dst = *b; continue; }
+      if (r2) { *dst = *a; continue; }
+      *dst = select_value(cond, *a, *b, s);
     }
   }
 
@@ -1718,6 +1763,18 @@ void Compiler::Impl::backend() {
     }
     f(o.dst);
   };
+  // ---- sanity: every operand is defined by an earlier op (catches scheduling bugs of deferred ops)
+  {
+    std::vector<uint32_t> def_at(nv, 0xFFFFFFFFu);
+    for (size_t i = 0; i < nops; i++) for_defs(ops[i], [&](uint32_t d) { if (d < nv) def_at[d] = (uint32_t)i; });
+    for (size_t i = 0; i < nops; i++)
+      for_operands(ops[i], [&](uint32_t v) {
+        if (v == PZK_OPERAND_NONE) return;
+        if (v >= nv || def_at[v] == 0xFFFFFFFFu || def_at[v] >= i)
+          throw CompileError(fmt("internal: op %zu (opc %d) uses value %u defined at op %u (opc %d)", i, (int)ops[i].opc, v,
+                                 v < nv ? def_at[v] : 0u, (v < nv && def_at[v] < nops) ? (int)ops[def_at[v]].opc : -1));
+      });
+  }
   // ---- DCE
   std::vector<uint8_t> used(nv, 0), keep(nops, 0);
   for (uint32_t v : sig_val) if (v) used[v] = 1;
@@ -1842,7 +1899,10 @@ void Compiler::Impl::backend() {
   // ---- emit op records, each followed by the constraint rows it completes
   auto slot_of = [&](uint32_t v) -> uint32_t {
     if (v == PZK_OPERAND_NONE) return v;
-    if (v_slot[v] == 0xFFFFFFFFu) throw CompileError("internal: operand without a slot");
+    if (v_slot[v] == 0xFFFFFFFFu)
+      throw CompileError(fmt("internal: operand without a slot (value %u class %d, defined by op %u opc %d kept %d, used=%d)", v,
+                             (int)v_cls[v], v_def[v], v_def[v] < ops.size() ? (int)ops[v_def[v]].opc : -1,
+                             v_def[v] < ops.size() ? (int)keep[v_def[v]] : -1, (int)used[v]));
     return v_slot[v];
   };
   auto ref_of_sig = [&](uint32_t sig) -> uint32_t {

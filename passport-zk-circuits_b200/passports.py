@@ -158,12 +158,80 @@ def pss_sign(key: RsaKey, msg: bytes, hash_name: str, salt_len: int, rng) -> int
     return key.private_op(int.from_bytes(em, "big"))
 
 
+# NIST P-256 (secp256r1): the curve signatureVerification.circom:177-191 hard-codes for SIGNATURE_TYPE 20
+P256_P = 0xFFFFFFFF00000001000000000000000000000000FFFFFFFFFFFFFFFFFFFFFFFF
+P256_A = P256_P - 3
+P256_B = 0x5AC635D8AA3A93E7B3EBBD55769886BC651D06B0CC53B0F63BCE3C3E27D2604B
+P256_N = 0xFFFFFFFF00000000FFFFFFFFFFFFFFFFBCE6FAADA7179E84F3B9CAC2FC632551
+P256_G = (0x6B17D1F2E12C4247F8BCE6E563A440F277037D812DEB33A0F4A13945D898C296,
+          0x4FE342E2FE1A7F9B8EE7EB4A7C0F9E162BCE33576B315ECECBB6406837BF51F5)
+
+
+def _ec_add(p1, p2, a=P256_A, p=P256_P):
+    if p1 is None:
+        return p2
+    if p2 is None:
+        return p1
+    (x1, y1), (x2, y2) = p1, p2
+    if x1 == x2:
+        if (y1 + y2) % p == 0:
+            return None
+        lam = (3 * x1 * x1 + a) * pow(2 * y1, -1, p) % p
+    else:
+        lam = (y2 - y1) * pow(x2 - x1, -1, p) % p
+    x3 = (lam * lam - x1 - x2) % p
+    return x3, (lam * (x1 - x3) - y1) % p
+
+
+def _ec_mul(k, pt):
+    acc = None
+    while k:
+        if k & 1:
+            acc = _ec_add(acc, pt)
+        pt = _ec_add(pt, pt)
+        k >>= 1
+    return acc
+
+
+class EcKey:
+    """P-256 signer key; `n` is kept so the RSA-shaped call sites (`key.n`) read the x coordinate."""
+
+    def __init__(self, rng):
+        self.d = rng.randrange(1, P256_N)
+        self.x, self.y = _ec_mul(self.d, P256_G)
+        self.n = self.x
+
+    def sign(self, msg: bytes, hash_name: str, rng):
+        z = int.from_bytes(hashlib.new(hash_name, msg).digest(), "big")
+        while True:
+            k = rng.randrange(1, P256_N)
+            r = _ec_mul(k, P256_G)[0] % P256_N
+            s = pow(k, -1, P256_N) * (z + r * self.d) % P256_N
+            if r and s:
+                return r, s
+
+
+def ecdsa_verify(x, y, msg: bytes, hash_name: str, r, s):
+    z = int.from_bytes(hashlib.new(hash_name, msg).digest(), "big")
+    w = pow(s, -1, P256_N)
+    pt = _ec_add(_ec_mul(z * w % P256_N, P256_G), _ec_mul(r * w % P256_N, (x, y)))
+    return pt is not None and pt[0] % P256_N == r
+
+
+def ec_pubkey_hash(x: int, y: int):
+    """Poseidon2 of the low 248 bits of each coordinate
+    (/root/reference/circuits/passportVerification/passportVerificationBuilder.circom:193-231)."""
+    m = (1 << 248) - 1
+    return poseidon([x & m, y & m])
+
+
 # SIGNATURE_TYPE -> (modulus bits, scheme, signature hash bits, public exponent, PSS salt length)
 # (/root/reference/circuits/signatureVerifier/signatureVerification.circom:13-116, SURVEY.md appendix D)
 SIG_SCHEMES = {
     1: (2048, "pkcs1", 256, 65537, 0), 2: (4096, "pkcs1", 256, 65537, 0), 3: (2048, "pkcs1", 160, 65537, 0),
     10: (2048, "pss", 256, 3, 32), 11: (2048, "pss", 256, 65537, 32), 12: (2048, "pss", 256, 65537, 64),
     13: (2048, "pss", 384, 65537, 48),
+    20: (256, "ecdsa", 256, 0, 0),
 }
 
 _KEY_CACHE = {}
@@ -229,16 +297,23 @@ class PassportFactory:
     def __init__(self, params: CircuitParams = C3, seed: int = 1, n_sig_keys: int = 4,
                  n_aa_keys: int = 4):
         if params.sig_type not in SIG_SCHEMES:
-            raise NotImplementedError("synthetic generator: RSA PKCS#1 v1.5 / PSS families only (SIG 1-3, 10-13)")
+            raise NotImplementedError("synthetic generator: RSA PKCS#1 v1.5 / PSS (SIG 1-3, 10-13) and ECDSA P-256 (SIG 20)")
         self.params = params
         self.seed = seed
         self.key_bits, self.scheme, self.sig_hash, self.e, self.salt_len = SIG_SCHEMES[params.sig_type]
         self.block = 512 if self.sig_hash <= 256 else 1024
         if (512 if params.dg_hash <= 256 else 1024) != self.block:
             raise ValueError("DG_HASH_TYPE and the signature hash must share a block size (SURVEY.md appendix D)")
-        self.sig_keys = key_pool(self.key_bits, n_sig_keys, seed, self.e)
+        if self.scheme == "ecdsa":
+            krng = random.Random((seed << 20) ^ 0xEC)
+            self.sig_keys = [EcKey(krng) for _ in range(n_sig_keys)]
+        else:
+            self.sig_keys = key_pool(self.key_bits, n_sig_keys, seed, self.e)
         self.aa_keys = key_pool(1024, n_aa_keys, seed + 7) if params.aa_algo else []
-        self._pkhash = [rsa_pubkey_hash(k.n) for k in self.sig_keys]
+        if self.scheme == "ecdsa":
+            self._pkhash = [ec_pubkey_hash(k.x, k.y) for k in self.sig_keys]
+        else:
+            self._pkhash = [rsa_pubkey_hash(k.n) for k in self.sig_keys]
         self._roots = [poseidon([h, h, 1]) for h in self._pkhash]
 
     # -- message builders -------------------------------------------------
@@ -317,15 +392,22 @@ class PassportFactory:
         sa = bytes(sa)
         ki = rng.randrange(len(self.sig_keys))
         key = self.sig_keys[ki]
-        sig = pkcs1v15_sign(key, sa, sgh) if self.scheme == "pkcs1" else pss_sign(key, sa, sgh, self.salt_len, rng)
+        if self.scheme == "ecdsa":
+            sig = key.sign(sa, sgh, rng)
+            pub_chunks = chunks_le(key.x, 64, 4) + chunks_le(key.y, 64, 4)
+            sig_chunks = chunks_le(sig[0], 64, 4) + chunks_le(sig[1], 64, 4)
+        else:
+            sig = pkcs1v15_sign(key, sa, sgh) if self.scheme == "pkcs1" else pss_sign(key, sa, sgh, self.salt_len, rng)
+            pub_chunks = chunks_le(key.n, 64, self.key_bits // 64)
+            sig_chunks = chunks_le(sig, 64, self.key_bits // 64)
         sk = hashlib.sha256(ec).hexdigest()[:62]
         inputs = {
             "dg1": [str(b) for b in bytes_to_bits(sha_pad(dg1, self.block))],
             "dg15": [str(b) for b in bytes_to_bits(sha_pad(dg15, self.block))] if p.aa_algo else [],
             "signedAttributes": [str(b) for b in bytes_to_bits(sha_pad(sa, self.block))],
             "encapsulatedContent": [str(b) for b in bytes_to_bits(sha_pad(ec, self.block))],
-            "pubkey": [str(c) for c in chunks_le(key.n, 64, self.key_bits // 64)],
-            "signature": [str(c) for c in chunks_le(sig, 64, self.key_bits // 64)],
+            "pubkey": [str(c) for c in pub_chunks],
+            "signature": [str(c) for c in sig_chunks],
             "skIdentity": "0x" + sk,
             "slaveMerkleRoot": "0x" + format(self._roots[ki], "x"),
             "slaveMerkleInclusionBranches": ["0"] * TREE_DEPTH,

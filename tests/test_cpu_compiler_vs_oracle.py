@@ -12,7 +12,8 @@ import ref as oracle_ref
 from conftest import REFERENCE, has_reference
 from util import ROOT, input_dict, ints_to_u64, random_inputs, u64_to_ints
 
-OWN = {"t_mix": "tests/circuits/mix.circom", "t_bigdiv": "tests/circuits/bigdiv.circom"}
+OWN = {"t_mix": "tests/circuits/mix.circom", "t_bigdiv": "tests/circuits/bigdiv.circom",
+       "t_earlyret": "tests/circuits/earlyret.circom"}
 REF_SMALL = ["poseidon2", "sha256_1", "smt80", "babyjub"]
 
 
@@ -58,6 +59,32 @@ def test_own_bigdiv_intrinsic_equals_function(artifacts_dir):
     inp[2, d["b"]["offset"] + 1, 0] = np.uint64(0xFFFFFFFFFFFFFFFF)
     # the quotient must fit m+1 = 2 limbs: a[2] < b[1] is not required, q < 2^128 always holds here
     compare(os.path.join(artifacts_dir, "t_bigdiv"), os.path.join(ROOT, OWN["t_bigdiv"]), inp)
+
+
+def earlyret_inputs(meta, B, seed):
+    inp = random_inputs(meta, B, seed)
+    d = {x["name"]: x for x in meta["inputs"]}
+    inp[:, d["b"]["offset"] + 1, 0] |= np.uint64(1)
+    inp[0, d["x"]["offset"]] = 0                            # inv_or_zero leaves early
+    for i in range(1, 6):                                   # first_set returns 0, 1, 2, 3, 4
+        inp[i, d["v"]["offset"]:d["v"]["offset"] + (i - 1), 0] = 0
+    inp[7, d["v"]["offset"]:d["v"]["offset"] + 4, 0] = 0
+    return inp, d
+
+
+def test_own_early_returns_under_data_dependent_conditions(artifacts_dir):
+    """Functions that `return` inside signal-dependent ifs (the shape of short_div_norm / mod_inv /
+    long_sub_mod, /root/reference/circuits/lib/circuits/bigInt/bigIntFunc.circom:290-312, 430-446,
+    516-522) are if-converted: every path's value must survive with its path condition."""
+    prog = oracle_ref.RefProgram(os.path.join(artifacts_dir, "t_earlyret.pzkp"))
+    inp, d = earlyret_inputs(prog.meta, 48, 3)
+    compare(os.path.join(artifacts_dir, "t_earlyret"), os.path.join(ROOT, OWN["t_earlyret"]), inp)
+    # a dividend limb that only fits 64 bits at run time is narrowed under an assertion
+    row = inp[9].copy()
+    row[d["a"]["offset"] + 2, 0] = np.uint64(0xFFFFFFFFFFFFFFFF)
+    row[d["c"]["offset"], 0] = 1
+    st, _, _ = prog.witness(row)
+    assert st & 1
 
 
 @pytest.mark.skipif(not has_reference(), reason="/root/reference is not mounted here")

@@ -111,7 +111,7 @@ def golden_inputs(meta, case):
     return {k: (list(v) if isinstance(v, str) and size[k] > 1 else v) for k, v in case["inputs"].items()}
 
 
-GOLDEN = ["poseidon2", "sha256_1", "smt80", "query80", "c3", "c4_sig3", "c4_sig10", "c4_sig13"]
+GOLDEN = ["poseidon2", "sha256_1", "smt80", "query80", "c3", "c4_sig3", "c4_sig10", "c4_sig13", "c4_sig20"]
 
 
 @pytest.mark.parametrize("name", GOLDEN)
@@ -187,6 +187,30 @@ def test_synthetic_passport_is_a_valid_signed_document():
     assert len(sha_pad(b"x" * 55)) == 64 and len(sha_pad(b"x" * 56)) == 128
     # determinism
     assert PassportFactory(C3, seed=9, n_sig_keys=2, n_aa_keys=2).make(4).inputs == i
+
+
+def test_ecdsa_passport_through_the_compiled_program(artifacts_dir):
+    """SIGNATURE_TYPE 20 (P-256 + SHA-256, signatureVerification.circom:177-191): the generator's
+    signature verifies in plain Python, the compiled program satisfies all 5.47 M constraints for it,
+    and a flipped signature limb is caught by a constraint (not by an assert)."""
+    from passport_zk_circuits_b200.artifacts import C4_VARIANTS
+    from passport_zk_circuits_b200.passports import P256_N, ecdsa_verify
+    fac = PassportFactory(C4_VARIANTS["c4_sig20"], seed=5, n_sig_keys=1, n_aa_keys=1)
+    p = fac.make(0)
+    key = fac.sig_keys[0]
+    r, s = p.signature
+    assert ecdsa_verify(key.x, key.y, p.sa, "sha256", r, s)
+    assert not ecdsa_verify(key.x, key.y, p.sa, "sha256", r, (s + 1) % P256_N)
+    assert len(p.inputs["pubkey"]) == 8 and len(p.inputs["signature"]) == 8
+    prog = oracle_ref.RefProgram(W.artifact("c4_sig20"))
+    assert prog.n_constraints == 5467606
+    inp = W.pack_inputs_fast(prog.meta, [p.inputs])
+    st, fb, _ = prog.witness(inp[0], want_witness=False)
+    assert st == 0 and fb == -1
+    d = {x["name"]: x for x in prog.meta["inputs"]}
+    inp[0, d["signature"]["offset"], 0] ^= np.uint64(1)
+    st, fb, _ = prog.witness(inp[0], want_witness=False)
+    assert st == W.STATUS_CONSTRAINT and fb >= 0
 
 
 def test_shard_bounds_cover_the_batch():

@@ -80,6 +80,21 @@ def test_bigdiv_intrinsic():
     assert res.status[3] & W.STATUS_BIGDIV
 
 
+def test_early_returns_and_narrowed_limb():
+    prog = oracle_ref.RefProgram(W.artifact("t_earlyret"))
+    inp = random_inputs(prog.meta, 200, 3)
+    d = {x["name"]: x for x in prog.meta["inputs"]}
+    inp[:, d["b"]["offset"] + 1, 0] |= np.uint64(1)
+    inp[0, d["x"]["offset"]] = 0
+    for i in range(1, 6):
+        inp[i, d["v"]["offset"]:d["v"]["offset"] + (i - 1), 0] = 0
+    inp[9, d["a"]["offset"] + 2, 0] = np.uint64(0xFFFFFFFFFFFFFFFF)   # a[2] + c = 2^64 does not fit a limb
+    inp[9, d["c"]["offset"], 0] = 1
+    res = run_and_compare("t_earlyret", inp)
+    assert res.status[9] & W.STATUS_ASSERT
+    assert (np.delete(res.status, 9) == 0).all()
+
+
 @pytest.mark.parametrize("name,B", [("poseidon2", 200), ("sha256_1", 130), ("babyjub", 66)])
 def test_reference_small(name, B):
     prog = oracle_ref.RefProgram(W.artifact(name))
