@@ -56,6 +56,18 @@ typedef struct pzk_circuit pzk_circuit;
 int pzk_compile(const char* main_circom_path, const char* out_prefix, const char* const* bits_names,
                 const int* bits_widths, int n_bits, uint32_t segment_ops, char* err, size_t err_len);
 
+/* Same with options.  PZK_COMPILE_STATIC_DEF_ROWS: the row added by `x <== e` compares the wire x with
+ * the expression its value was computed from, so it holds for every input; with this flag such rows
+ * are discharged at compile time (like the alias rows `a <== b` always are) and only `===` rows and
+ * rows over `<--` hints are evaluated at run time.  status / first_bad are identical either way; the
+ * default keeps every non-alias row as a run-time check.  PZK_COMPILE_NO_INTRINSICS: unroll long_div
+ * instead of using the device intrinsic (validation of the intrinsic).                             */
+#define PZK_COMPILE_STATIC_DEF_ROWS 1u
+#define PZK_COMPILE_NO_INTRINSICS 2u
+int pzk_compile_ex(const char* main_circom_path, const char* out_prefix, const char* const* bits_names,
+                   const int* bits_widths, int n_bits, uint32_t segment_ops, uint32_t flags, char* err,
+                   size_t err_len);
+
 /* ---- circuit handle: the role of `new WitnessCalculator(wasm)` ---------------------- */
 int pzk_circuit_open(const char* program_path, int cuda_device, pzk_circuit** out);
 void pzk_circuit_close(pzk_circuit* c);

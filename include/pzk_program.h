@@ -30,7 +30,7 @@ extern "C" {
 #endif
 
 #define PZK_MAGIC 0x314b5a50u /* "PZK1" */
-#define PZK_VERSION 7u
+#define PZK_VERSION 8u
 
 /* ---- opcodes ------------------------------------------------------------ */
 enum PzkOpcode {
@@ -97,6 +97,8 @@ enum PzkOpcode {
   PZK_CHECK_I64 = 58, /* like CHECK_INT with |A|,|B|,|A*B|,|C| < 2^63 and inline int32 coefficients only:
                          plain wrapping 64-bit arithmetic decides the row */
   /* macro / control */
+  PZK_MODINV = 59,    /* mod_inv intrinsic: list = {n, k, 0, a[k], p[k], unused, out[k]} (the BIGDIV layout
+                         with m = 0); out = (a mod p)^-1 mod p for an odd prime p, 0 when p | a        */
   PZK_BIGDIV = 60,    /* long_div intrinsic, operands in the list pool       */
   PZK_ASSERT_NZ = 61, /* lane status |= ASSERT when a(U) == 0                */
   PZK_IN_U = 62,      /* dst(U) = input[a], range check: value < 2^imm16      */

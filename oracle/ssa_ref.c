@@ -173,6 +173,31 @@ static void divmod4(const uint64_t* a, const uint64_t* b, uint64_t* q, uint64_t*
   if (m) memcpy(m, rr, 32);
 }
 static void reduce_p(uint64_t* a) { while (cmp4(a, P) >= 0) sub4(a, a, P); }
+/* arithmetic modulo an arbitrary m < 2^256 (m may exceed 2^255: carries out of 256 bits are tracked) */
+static void addmod4(uint64_t* r, const uint64_t* a, const uint64_t* b, const uint64_t* m) { /* a, b < m */
+  uint64_t t[4];
+  uint64_t c = add4(t, a, b);
+  if (c || cmp4(t, m) >= 0) sub4(t, t, m);
+  memcpy(r, t, 32);
+}
+static void mod4(uint64_t* r, const uint64_t* a, const uint64_t* m) {
+  uint64_t rr[4] = {0, 0, 0, 0};
+  for (int i = 255; i >= 0; i--) {
+    uint64_t bit[4] = {(a[i >> 6] >> (i & 63)) & 1, 0, 0, 0};
+    addmod4(rr, rr, rr, m);
+    if (bit[0] && cmp4(bit, m) < 0) addmod4(rr, rr, bit, m);
+  }
+  memcpy(r, rr, 32);
+}
+static void mulmod4(uint64_t* r, const uint64_t* a, const uint64_t* b, const uint64_t* m) { /* a, b < m */
+  uint64_t acc[4] = {0, 0, 0, 0}, x[4];
+  memcpy(x, a, 32);
+  for (int i = 0; i < 256; i++) {
+    if ((b[i >> 6] >> (i & 63)) & 1) addmod4(acc, acc, x, m);
+    addmod4(x, x, x, m);
+  }
+  memcpy(r, acc, 32);
+}
 static int is_neg(const uint64_t* a) { /* a > p/2 */
   uint64_t h[4]; shr4(h, P, 1);
   return cmp4(a, h) > 0;
@@ -358,6 +383,25 @@ uint32_t pzk_ref_witness(const PzkRefProgram* p, const uint8_t* inputs, uint8_t*
           if (rc) { status |= PZK_LANE_BIGDIV_PRE; memset(q, 0, sizeof q); memset(r, 0, sizeof r); }
           for (unsigned i = 0; i <= m; i++) U[L[3 + k + m + k + i]] = q[i];
           for (unsigned i = 0; i < k; i++) U[L[3 + k + m + k + m + 1 + i]] = r[i];
+          break;
+        }
+        case PZK_MODINV: {
+          /* mod_inv of bigIntFunc.circom:430-465 as the reference defines it: 0 when a == 0 (mod p),
+           * else a^(p-2) mod p by square-and-multiply - deliberately NOT the extended GCD the device uses */
+          const uint32_t* L = p->list + o->a;
+          unsigned k = L[1];
+          uint64_t a[4] = {0, 0, 0, 0}, m[4] = {0, 0, 0, 0}, e[4], r[4] = {1, 0, 0, 0}, two[4] = {2, 0, 0, 0};
+          for (unsigned i = 0; i < k; i++) { a[i] = U[L[3 + i]]; m[i] = U[L[3 + k + i]]; }
+          mod4(a, a, m);
+          sub4(e, m, two);
+          mod4(r, r, m);
+          for (int i = 255; i >= 0; i--) {
+            mulmod4(r, r, r, m);
+            if ((e[i >> 6] >> (i & 63)) & 1) mulmod4(r, r, a, m);
+          }
+          if (!(a[0] | a[1] | a[2] | a[3])) memset(r, 0, sizeof r);
+          U[L[3 + k + k]] = 0;
+          for (unsigned i = 0; i < k; i++) U[L[3 + k + k + 1 + i]] = r[i];
           break;
         }
         case PZK_CHECK_I64: case PZK_CHECK_INT: case PZK_CHECK_F: {

@@ -61,6 +61,10 @@ def reference_circuits():
         # config 3: the north-star circuit (hardhat.config.ts:29)
         "c3": (C3.main_source(REFERENCE + "/circuits/identityManagement/registerIdentityBuilder.circom"),
                W.REGISTER_IDENTITY_BITS),
+        # config 3 again, compiled with the rows of `x <== e` discharged at compile time (pzk.h:
+        # PZK_COMPILE_STATIC_DEF_ROWS); same wires, same verdicts, 353 k instead of 1.29 M run-time rows
+        "c3_lean": (C3.main_source(REFERENCE + "/circuits/identityManagement/registerIdentityBuilder.circom"),
+                    W.REGISTER_IDENTITY_BITS),
         # config 4: SHA-1 / RSA-PSS variants with other hash types and shifts
         **{name: (prm.main_source(REFERENCE + "/circuits/identityManagement/registerIdentityBuilder.circom"),
                   W.REGISTER_IDENTITY_BITS) for name, prm in C4_VARIANTS.items()},
@@ -69,9 +73,12 @@ def reference_circuits():
 
 OWN_CIRCUITS = {"t_mix": ("mix.circom", {"u": 16, "bits": 1}),
                 "t_bigdiv": ("bigdiv.circom", {"a": 64, "b": 64}),
-                "t_earlyret": ("earlyret.circom", {"v": 16, "a": 64, "b": 64, "c": 1})}
+                "t_earlyret": ("earlyret.circom", {"v": 16, "a": 64, "b": 64, "c": 1}),
+                "t_modinv": ("modinv.circom", {"a": 64})}
 
-BIG = {"c3", "c4_sig3", "c4_sig10", "c4_sig13", "c4_sig20"}  # ship only the xz-packed program for these
+COMPILE_OPTS = {"c3_lean": {"static_def_rows": True, "segment_ops": 8192}}
+
+BIG = {"c3", "c3_lean", "c4_sig3", "c4_sig10", "c4_sig13", "c4_sig20"}  # ship only the xz-packed program for these
 
 
 def _stale(out, deps):
@@ -101,7 +108,7 @@ def build_all(verbose=True):
         if verbose:
             print("compiling", name)
         main = _wrapper(name, body)
-        W.compile_circuit(main, prefix, bits)
+        W.compile_circuit(main, prefix, bits, **COMPILE_OPTS.get(name, {}))
         if name in BIG:
             W.pack_artifact(prefix + ".pzkp")
             if name == "c3":  # the stand-alone R1CS stream kernel is measured on this one

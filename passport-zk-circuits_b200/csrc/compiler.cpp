@@ -127,7 +127,7 @@ struct Ctx {  // one template instance being executed (or nullptr inside functio
   Comp* comp = nullptr;
 };
 
-struct RowRec { uint64_t off; uint32_t na, nb, nc; };
+struct RowRec { uint64_t off; uint32_t na, nb, nc; bool by_def = false; };
 
 struct Compiler::Impl {
   SourceUnit unit;
@@ -181,7 +181,7 @@ struct Compiler::Impl {
   std::vector<PzkInput> out_inputs;
   std::vector<uint32_t> out_list;
   uint32_t n_u_slots = 0, n_f_slots = 0;
-  uint64_t n_static_rows = 0, n_i64_rows = 0, n_int_rows = 0, n_field_rows = 0, eval_bytes = 0, check_bytes = 0, cache_hit_refs = 0, cache_miss_refs = 0;
+  uint64_t n_static_rows = 0, n_def_rows = 0, n_i64_rows = 0, n_int_rows = 0, n_field_rows = 0, eval_bytes = 0, check_bytes = 0, cache_hit_refs = 0, cache_miss_refs = 0;
   std::vector<uint32_t> seg_quads;
   uint32_t n_pub_out = 0, n_pub_in = 0, n_prv_in = 0;
   std::string meta_json;
@@ -213,7 +213,7 @@ struct Compiler::Impl {
   bool flushing = false;
   static const size_t INV_BATCH = 8;
   bool op_reads_values(int opc) {
-    switch (opc) { case PZK_NOP: case PZK_U_CONST: case PZK_F_CONST: case PZK_IN_U: case PZK_IN_F: case PZK_BIGDIV: return false; }
+    switch (opc) { case PZK_NOP: case PZK_U_CONST: case PZK_F_CONST: case PZK_IN_U: case PZK_IN_F: case PZK_BIGDIV: case PZK_MODINV: return false; }
     return true;
   }
   bool is_pending(uint32_t v) { return v != PZK_OPERAND_NONE && v < v_pending.size() && v_pending[v]; }
@@ -242,7 +242,7 @@ struct Compiler::Impl {
     }
     OpRec o; o.opc = (uint8_t)opc; o.flags = (uint8_t)flags; o.imm16 = (uint16_t)imm16;
     o.dst = dst; o.a = a; o.b = b; o.c = c; o.d = d;
-    if (dst && opc != PZK_ASSERT_NZ && opc != PZK_BIGDIV && dst < v_def.size()) v_def[dst] = (uint32_t)ops.size();
+    if (dst && opc != PZK_ASSERT_NZ && opc != PZK_BIGDIV && opc != PZK_MODINV && dst < v_def.size()) v_def[dst] = (uint32_t)ops.size();
     ops.push_back(o);
     return dst;
   }
@@ -252,6 +252,7 @@ struct Compiler::Impl {
     if (v_pending.size() <= r) v_pending.resize(r + 1024, 0);
     v_pending[r] = 1;
     pending_inv.emplace_back(x, r);
+    inv_of[r] = x;
     stats->f_inv++;
     if (pending_inv.size() >= INV_BATCH) flush_inversions();
     return r;
@@ -302,7 +303,7 @@ struct Compiler::Impl {
     size_t li = 0;
     for (size_t k = 0; k < dq.size(); k++) {
       const OpRec& o = dq[k];
-      if (o.dst && o.opc != PZK_ASSERT_NZ && o.opc != PZK_BIGDIV && o.dst < v_def.size()) v_def[o.dst] = (uint32_t)ops.size();
+      if (o.dst && o.opc != PZK_ASSERT_NZ && o.opc != PZK_BIGDIV && o.opc != PZK_MODINV && o.dst < v_def.size()) v_def[o.dst] = (uint32_t)ops.size();
       ops.push_back(o);
       if (li < lq.size() && lq[li].first == k) { lutv_off[(uint32_t)ops.size() - 1] = lq[li].second; li++; }
     }
@@ -503,7 +504,43 @@ struct Compiler::Impl {
 
   bool is_ring(int op) { return op == O_ADD || op == O_SUB || op == O_MUL; }
 
+  // Facts about values that let `x * inv(x)` be computed without the inverse (IsZero / IsEqual,
+  // circomlib comparators: `inv <-- in != 0 ? 1/in : 0; out <== -in*inv + 1`): x * inv(x) is the bit
+  // (x != 0) because inv(0) = 0.  The bit is a narrow value, so everything downstream of an IsZero stays
+  // in 64-bit arithmetic, and `out` no longer waits for the batched inversion.
+  std::unordered_map<uint32_t, uint32_t> inv_of, neg_of, nz_of;  // result value -> operand value
+  bool same_value(uint32_t x, uint32_t y) {
+    if (x == y) return true;
+    if (x < v_convF.size() && v_convF[x] && v_convF[x] == y) return true;
+    if (y < v_convF.size() && v_convF[y] && v_convF[y] == x) return true;
+    return false;
+  }
+  bool try_inverse_product(const SVal& p, const SVal& q, SVal& out, const Stmt* at) {
+    auto it = inv_of.find(q.id);
+    if (it == inv_of.end()) return false;
+    uint32_t v = it->second;
+    if (same_value(p.id, v)) { out = truthy(p, at); return true; }
+    auto nt = neg_of.find(p.id);
+    if (nt != neg_of.end() && same_value(nt->second, v)) {
+      out = emit_bin(O_SUB, SVal::konst(U256()), truthy(sv(nt->second), at), at);
+      return true;
+    }
+    return false;
+  }
   SVal emit_bin(int op, SVal a, SVal b, const Stmt* at) {
+    if (op == O_MUL && a.kind == 1 && b.kind == 1 && !inv_of.empty()) {
+      SVal r;
+      if (try_inverse_product(a, b, r, at) || try_inverse_product(b, a, r, at)) return r;
+    }
+    SVal r = emit_bin_core(op, a, b, at);
+    if (r.kind == 1) {
+      if (op == O_SUB && a.kind == 0 && a.c.is_zero() && b.kind == 1) neg_of[r.id] = b.id;
+      else if (op == O_NE && b.kind == 0 && b.c.is_zero() && a.kind == 1) nz_of[r.id] = a.id;
+      else if (op == O_NE && a.kind == 0 && a.c.is_zero() && b.kind == 1) nz_of[r.id] = b.id;
+    }
+    return r;
+  }
+  SVal emit_bin_core(int op, SVal a, SVal b, const Stmt* at) {
     // canonicalise > and >= into < and <=
     if (op == O_GT) { std::swap(a, b); op = O_LT; }
     else if (op == O_GE) { std::swap(a, b); op = O_LE; }
@@ -802,6 +839,12 @@ struct Compiler::Impl {
   SVal emit_select(const SVal& c, const SVal& x, const SVal& y, const Stmt* at) {
     if (c.kind == 2 || x.kind == 2 || y.kind == 2) return SVal::unk();
     if (c.kind == 0) return c.c.is_zero() ? y : x;
+    // (v != 0) ? inv(v) : 0  is  inv(v)  (inv(0) = 0)
+    if (y.kind == 0 && y.c.is_zero() && x.kind == 1 && c.kind == 1) {
+      auto ix = inv_of.find(x.id);
+      auto ic = nz_of.find(c.id);
+      if (ix != inv_of.end() && ic != nz_of.end() && same_value(ix->second, ic->second)) return x;
+    }
     // table
     {
       SVal xs[3] = {c, x, y};
@@ -901,7 +944,7 @@ struct Compiler::Impl {
     for (auto& t : l.t) { terms.emplace_back(t.first, coef_id(t.second)); n++; }
   }
   // constraint  e == 0  where e = a*b + c   ->  A*B = -C
-  void add_constraint(const AlgP& e, const Stmt* at) {
+  void add_constraint(const AlgP& e, const Stmt* at, bool by_def = false) {
     if (e->deg == 3) fail(at, "non-quadratic constraint");
     if (e->deg == 0) {
       if (!e->c.k.is_zero()) fail(at, "constraint is constant and false");
@@ -912,6 +955,7 @@ struct Compiler::Impl {
     if (e->deg == 2) { push_lin(e->a, r.na); push_lin(e->b, r.nb); }
     else { r.na = r.nb = 0; }
     push_lin(negc, r.nc);
+    r.by_def = by_def;
     rows.push_back(r);
   }
 
@@ -1102,7 +1146,7 @@ struct Compiler::Impl {
         // rhs - sig == 0
         SVal self; self.kind = 1; self.alg = alg_sig(sig);
         AlgP e = alg_bin(O_SUB, s, self);
-        add_constraint(e, at);
+        add_constraint(e, at, true);
       }
     }
     if (r.skind == 1 && r.comp->parent != nullptr) {
@@ -1258,7 +1302,7 @@ struct Compiler::Impl {
   }
 
   // ---- functions -----------------------------------------------------------------
-  int id_long_div = -2;
+  int id_long_div = -2, id_mod_inv = -2;
   Value call_function(Expr* e, Env& env, Ctx* ctx, const Stmt* at) {
     auto ft = unit.functions.find(e->name);
     if (ft == unit.functions.end()) fail(at, "unknown function " + nm(e->name));
@@ -1282,6 +1326,8 @@ struct Compiler::Impl {
       if (id_long_div == -2) id_long_div = unit.names.get("long_div");
       Value out;
       if (e->name == id_long_div && try_bigdiv(args, out, at)) return out;
+      if (id_mod_inv == -2) id_mod_inv = unit.names.get("mod_inv");
+      if (e->name == id_mod_inv && try_modinv(args, out, at)) return out;
     }
     Env fenv(1);
     for (size_t i = 0; i < args.size(); i++) declare_var(fenv, fd.params[i], args[i]);
@@ -1352,6 +1398,102 @@ struct Compiler::Impl {
     emit(PZK_BIGDIV, first, off, 0);
     for (uint64_t i = 0; i < (m + 1) + k; i++) v_def[list_pool[off + 3 + (k + m) + k + i]] = (uint32_t)ops.size() - 1;
     stats->bigdiv++;
+    (void)at;
+    return true;
+  }
+
+  // (a * b) mod m and Miller-Rabin on 256-bit values, compile time only
+  static U256 mulmod256(const U256& a, const U256& b, const U256& m) {
+    U256 r, x = a;
+    { U256 q, t; divmod(x, m, q, t); x = t; }
+    for (int i = 0; i < 256; i++) {
+      if ((b.w[i >> 6] >> (i & 63)) & 1) {
+        uint64_t c; U256 t = add(r, x, &c);
+        if (c || !(t < m)) t = sub(t, m);
+        r = t;
+      }
+      uint64_t c; U256 t = add(x, x, &c);
+      if (c || !(t < m)) t = sub(t, m);
+      x = t;
+    }
+    return r;
+  }
+  static bool is_odd_prime(const U256& n) {
+    if (!(n.w[0] & 1) || n < U256(5)) return n == U256(3);
+    U256 d = sub(n, U256(1)), nm1 = d;
+    int s_ = 0;
+    while (!(d.w[0] & 1)) { d = shr(d, 1); s_++; }
+    for (uint64_t base : {2ull, 3ull, 5ull, 7ull, 11ull, 13ull, 17ull, 19ull, 23ull, 29ull, 31ull, 37ull}) {
+      U256 x(1), b(base);
+      for (int i = 255; i >= 0; i--) {
+        x = mulmod256(x, x, n);
+        if ((d.w[i >> 6] >> (i & 63)) & 1) x = mulmod256(x, b, n);
+      }
+      if (x == U256(1) || x == nm1) continue;
+      bool comp = true;
+      for (int r = 1; r < s_ && comp; r++) { x = mulmod256(x, x, n); if (x == nm1) comp = false; }
+      if (comp) return false;
+    }
+    return true;
+  }
+  std::unordered_map<U256, bool, U256Hash> prime_memo;
+
+  // mod_inv(n, k, a, p) of /root/reference/circuits/lib/circuits/bigInt/bigIntFunc.circom:430-465 computes
+  // a^(p-2) mod p by square-and-multiply (about 380 prod + long_div rounds, 100 k records unrolled).
+  // When p is a compile-time constant odd prime that is the modular inverse of a (0 when p | a): one
+  // MODINV record, evaluated with a binary extended GCD on the device.
+  bool try_modinv(const std::vector<Value>& args, Value& out, const Stmt* at) {
+    if (args.size() != 4) return false;
+    for (int i = 0; i < 2; i++) if (args[i].arr || args[i].s.kind != 0 || !args[i].s.c.fits64()) return false;
+    uint64_t n = args[0].s.c.w[0], k = args[1].s.c.w[0];
+    if (n != 64 || k < 1 || k > 4 || !args[2].arr || !args[3].arr) return false;
+    if (args[2].a->v.size() < k || args[3].a->v.size() < k) return false;
+    U256 pm;
+    for (uint64_t i = 0; i < k; i++) {
+      const SVal& q = args[3].a->v[i];
+      if (q.kind != 0 || !q.c.fits64()) return false;
+      pm.w[i] = q.c.w[0];
+    }
+    auto it = prime_memo.find(pm);
+    bool prime = it != prime_memo.end() ? it->second : (prime_memo[pm] = is_odd_prime(pm));
+    if (!prime) return false;
+    i128 lim = U64_MAX_;
+    std::vector<SVal> la(k);
+    bool all_const = true;
+    for (uint64_t i = 0; i < k; i++) {
+      const SVal& s_ = args[2].a->v[i];
+      if (s_.kind == 2) return false;
+      if (s_.kind == 0 && !s_.c.fits64()) return false;
+      if (s_.kind != 0) all_const = false;
+    }
+    if (all_const) return false;  // the unrolled function folds at compile time
+    for (uint64_t i = 0; i < k; i++) {
+      const SVal& s_ = args[2].a->v[i];
+      i128 hi;
+      if (s_.kind == 0 || (exact_u(s_, hi) && hi <= lim)) { la[i] = s_; continue; }
+      // not provably a 64-bit limb (the difference limbs of long_sub): narrowed under an assertion
+      SVal nn = sv(to_N(s_));
+      uint32_t fits = new_value(CLS_U, 0, 1);
+      emit(PZK_N_FITS, fits, nn.id);
+      emit(PZK_ASSERT_NZ, 0, fits);
+      la[i] = n_low(nn, lim);
+    }
+    for (uint64_t i = 0; i < k; i++) if (la[i].kind == 1 && is_pending(la[i].id)) flush_inversions();
+    uint32_t off = (uint32_t)list_pool.size();
+    list_pool.push_back((uint32_t)n); list_pool.push_back((uint32_t)k); list_pool.push_back(0);
+    for (uint64_t i = 0; i < k; i++) list_pool.push_back(u_operand(la[i]));
+    for (uint64_t i = 0; i < k; i++) list_pool.push_back(u_operand(args[3].a->v[i]));
+    out = zeros({200});
+    uint32_t first = new_value(CLS_U, 0, 0);  // the BIGDIV layout's quotient limb: always 0 here
+    list_pool.push_back(first);
+    for (uint64_t i = 0; i < k; i++) {
+      uint32_t id = new_value(CLS_U, 0, lim);
+      list_pool.push_back(id);
+      out.a->v[i] = sv(id);
+    }
+    emit(PZK_MODINV, first, off, 0);
+    for (uint64_t i = 0; i < 1 + k; i++) v_def[list_pool[off + 3 + k + k + i]] = (uint32_t)ops.size() - 1;
+    stats->modinv++;
     (void)at;
     return true;
   }
@@ -1727,7 +1869,7 @@ void Compiler::Impl::backend() {
   auto for_operands = [&](const OpRec& o, const std::function<void(uint32_t)>& f) {
     switch (o.opc) {
       case PZK_NOP: case PZK_U_CONST: case PZK_F_CONST: case PZK_IN_U: case PZK_IN_F: return;
-      case PZK_BIGDIV: {
+      case PZK_BIGDIV: case PZK_MODINV: {
         uint32_t k = list_pool[o.a + 1], m = list_pool[o.a + 2];
         for (uint32_t i = 0; i < k + m + k; i++) f(list_pool[o.a + 3 + i]);
         return;
@@ -1755,7 +1897,7 @@ void Compiler::Impl::backend() {
   };
   auto for_defs = [&](const OpRec& o, const std::function<void(uint32_t)>& f) {
     if (o.opc == PZK_NOP || o.opc == PZK_ASSERT_NZ) return;
-    if (o.opc == PZK_BIGDIV) {
+    if (o.opc == PZK_BIGDIV || o.opc == PZK_MODINV) {
       uint32_t k = list_pool[o.a + 1], m = list_pool[o.a + 2];
       uint32_t base = o.a + 3 + (k + m) + k;
       for (uint32_t i = 0; i < m + 1 + k; i++) f(list_pool[base + i]);
@@ -1834,7 +1976,13 @@ void Compiler::Impl::backend() {
   std::vector<uint8_t> row_static(nrows, 0);
   {
     std::vector<MT> parts[3];
-    for (size_t r = 0; r < nrows; r++) if (merge_row((uint32_t)r, parts)) { row_static[r] = 1; n_static_rows++; }
+    for (size_t r = 0; r < nrows; r++) {
+      if (merge_row((uint32_t)r, parts)) { row_static[r] = 1; n_static_rows++; }
+      // `x <== e` stores value(e) into x and adds the row e - x = 0: the wire holds the very value the
+      // row compares it with, so the row holds for every input (the same argument as for aliases, one
+      // multiplication deeper).  Only `===` rows and rows over `<--` hints can fail at run time.
+      else if (rows[r].by_def && opt.def_rows_static) { row_static[r] = 1; n_def_rows++; }
+    }
   }
   // ---- segments over kept ops (+ their rows)
   std::vector<uint32_t> def_seg(nv, 0), last_seg(nv, 0), op_seg(nops, 0);
@@ -1896,6 +2044,26 @@ void Compiler::Impl::backend() {
     }
   }
   n_u_slots = next_u; n_f_slots = next_f;
+  if (getenv("PZK_LIVE_STATS")) {
+    // where do the F slots go: values per (defining opcode, lifetime in segments)
+    std::map<std::pair<int, int>, uint64_t> hist;
+    std::vector<uint32_t> live(segs.size() + 1, 0);
+    for (size_t i = 0; i < nops; i++) {
+      if (!keep[i]) continue;
+      for_defs(ops[i], [&](uint32_t d) {
+        if (v_cls[d] == CLS_U || v_cls[d] == CLS_I) return;
+        int life = (int)(last_seg[d] - def_seg[d]);
+        int b = life == 0 ? 0 : life < 4 ? 1 : life < 32 ? 2 : life < 256 ? 3 : 4;
+        hist[{ops[i].opc, b}]++;
+        for (uint32_t sgi = def_seg[d]; sgi <= last_seg[d]; sgi++) live[sgi]++;
+      });
+    }
+    for (auto& kv : hist) fprintf(stderr, "F def opc %d life-bucket %d: %llu\n", kv.first.first, kv.first.second, (unsigned long long)kv.second);
+    uint32_t mx = 0, at_ = 0;
+    for (size_t i = 0; i < segs.size(); i++) if (live[i] > mx) { mx = live[i]; at_ = (uint32_t)i; }
+    fprintf(stderr, "max live F %u at segment %u of %zu\n", mx, at_, segs.size());
+    for (size_t i = 0; i < segs.size(); i += segs.size() / 40 + 1) fprintf(stderr, " seg %zu live F %u\n", i, live[i]);
+  }
   // ---- emit op records, each followed by the constraint rows it completes
   auto slot_of = [&](uint32_t v) -> uint32_t {
     if (v == PZK_OPERAND_NONE) return v;
@@ -1985,7 +2153,7 @@ void Compiler::Impl::backend() {
   {
     std::vector<uint64_t> nu(segs.size(), 0), nf(segs.size(), 0);
     for (size_t i = 0; i < nops; i++) {
-      if (!keep[i] || ops[i].opc == PZK_BIGDIV) continue;
+      if (!keep[i] || ops[i].opc == PZK_BIGDIV || ops[i].opc == PZK_MODINV) continue;
       for_defs(ops[i], [&](uint32_t d) { ((v_cls[d] == CLS_U || v_cls[d] == CLS_I) ? nu : nf)[op_seg[i]]++; });
     }
     for (size_t sg = 0; sg < segs.size(); sg++) {
@@ -2005,7 +2173,7 @@ void Compiler::Impl::backend() {
     for (size_t i = 0; i < nops; i++) {
       if (!keep[i]) continue;
       op_pos[i] = pos;
-      if (ops[i].opc != PZK_BIGDIV) for_operands(ops[i], [&](uint32_t v) { use_cnt[v]++; });
+      if (ops[i].opc != PZK_BIGDIV && ops[i].opc != PZK_MODINV) for_operands(ops[i], [&](uint32_t v) { use_cnt[v]++; });
       pos++;
       while (rp < nrows && row_trigger[row_order[rp]] == i) {
         uint32_t r = row_order[rp], nt = rows[r].na + rows[r].nb + rows[r].nc;
@@ -2023,7 +2191,7 @@ void Compiler::Impl::backend() {
     uint32_t pos = 0; size_t rp = 0;
     for (size_t i = 0; i < nops; i++) {
       if (!keep[i]) continue;
-      if (ops[i].opc != PZK_BIGDIV) for_operands(ops[i], [&](uint32_t v) { use_pos[use_off[v] + use_fill[v]++] = pos; });
+      if (ops[i].opc != PZK_BIGDIV && ops[i].opc != PZK_MODINV) for_operands(ops[i], [&](uint32_t v) { use_pos[use_off[v] + use_fill[v]++] = pos; });
       pos++;
       while (rp < nrows && row_trigger[row_order[rp]] == i) {
         uint32_t r = row_order[rp], nt = rows[r].na + rows[r].nb + rows[r].nc;
@@ -2145,7 +2313,7 @@ void Compiler::Impl::backend() {
         case PZK_NOP: break;
         case PZK_U_CONST: case PZK_F_CONST: case PZK_IN_U: case PZK_IN_F: has_dst = true; break;
         case PZK_ASSERT_NZ: r.a = opnd(o.a); break;
-        case PZK_BIGDIV: {
+        case PZK_BIGDIV: case PZK_MODINV: {
           uint32_t k = list_pool[o.a + 1], m = list_pool[o.a + 2];
           uint32_t cnt = (k + m) + k + (m + 1) + k;
           for (uint32_t j = 0; j < cnt; j++) { out_list[o.a + 3 + j] = slot_of(list_pool[o.a + 3 + j]); needs_global[list_pool[o.a + 3 + j]] = 1; }
@@ -2165,7 +2333,7 @@ void Compiler::Impl::backend() {
           }
       }
       // operands die / get re-prioritised, then the result may take a cell
-      if (o.opc != PZK_BIGDIV) for_operands(o, [&](uint32_t v) { touch_operand(v, pos, seg_end); });
+      if (o.opc != PZK_BIGDIV && o.opc != PZK_MODINV) for_operands(o, [&](uint32_t v) { touch_operand(v, pos, seg_end); });
       if (has_dst) {
         uint32_t slot = slot_of(o.dst);
         if (slot > 0x3fffffu) throw CompileError("too many live slots for the dst encoding");
@@ -2253,9 +2421,9 @@ void Compiler::Impl::build_meta() {
        ",\"n_prv_in\":" + std::to_string(n_prv_in);
   s += ",\"stats\":{\"u_ops\":" + std::to_string(stats->u_ops) + ",\"f_mul\":" + std::to_string(stats->f_mul) +
        ",\"f_inv\":" + std::to_string(stats->f_inv) + ",\"f_inv_real\":" + std::to_string(stats->f_inv_real) + ",\"f_other\":" + std::to_string(stats->f_other) +
-       ",\"bigdiv\":" + std::to_string(stats->bigdiv) + ",\"lut\":" + std::to_string(stats->lut) +
+       ",\"bigdiv\":" + std::to_string(stats->bigdiv) + ",\"modinv\":" + std::to_string(stats->modinv) + ",\"lut\":" + std::to_string(stats->lut) +
        ",\"op_records\":" + std::to_string(out_ops.size()) + ",\"segments\":" + std::to_string(segs.size()) +
-       ",\"static_rows\":" + std::to_string(n_static_rows) + ",\"i64_rows\":" + std::to_string(n_i64_rows) +
+       ",\"static_rows\":" + std::to_string(n_static_rows) + ",\"def_rows\":" + std::to_string(n_def_rows) + ",\"i64_rows\":" + std::to_string(n_i64_rows) +
        ",\"int_rows\":" + std::to_string(n_int_rows) + ",\"field_rows\":" + std::to_string(n_field_rows) +
        ",\"eval_bytes\":" + std::to_string(eval_bytes) + ",\"check_bytes\":" + std::to_string(check_bytes) +
        ",\"cells\":" + std::to_string(opt.cells) + ",\"cache_hit_refs\":" + std::to_string(cache_hit_refs) +

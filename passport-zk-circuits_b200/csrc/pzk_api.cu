@@ -104,10 +104,18 @@ int pzk_device_count(void) {
 
 int pzk_compile(const char* main_circom_path, const char* out_prefix, const char* const* bits_names,
                 const int* bits_widths, int n_bits, uint32_t segment_ops, char* err, size_t err_len) {
+  return pzk_compile_ex(main_circom_path, out_prefix, bits_names, bits_widths, n_bits, segment_ops, 0, err, err_len);
+}
+
+int pzk_compile_ex(const char* main_circom_path, const char* out_prefix, const char* const* bits_names,
+                   const int* bits_widths, int n_bits, uint32_t segment_ops, uint32_t flags, char* err,
+                   size_t err_len) {
   try {
     pzk::CompileOptions opt;
     for (int i = 0; i < n_bits; i++) opt.input_bits[bits_names[i]] = bits_widths[i];
     if (segment_ops) opt.seg_ops = segment_ops;
+    opt.def_rows_static = (flags & PZK_COMPILE_STATIC_DEF_ROWS) != 0;
+    opt.intrinsics = (flags & PZK_COMPILE_NO_INTRINSICS) == 0;
     pzk::Compiler cc(main_circom_path, opt);
     cc.run();
     std::string p = out_prefix;

@@ -102,6 +102,57 @@ __device__ __forceinline__ void ldPool(const u64* pool, u32 idx, u64* v) {
 // a: k+m digits, b: k digits (b[k-1] != 0, k >= 2); q: m+1 digits, r: k digits.
 // Mathematically the unique quotient / remainder that
 // /root/reference/circuits/lib/circuits/bigInt/bigIntFunc.circom:190-232 (long_div) produces.
+// mod_inv intrinsic (PZK_MODINV): out = (a mod p)^-1 mod p for an odd prime p < 2^256 (0 when p | a),
+// the value /root/reference/circuits/lib/circuits/bigInt/bigIntFunc.circom:430-465 reaches as a^(p-2).
+// Binary extended GCD with the invariants x1 * a == u, x2 * a == v (mod p); p may exceed 2^255, so the
+// halving step keeps the carry of x + p.
+__device__ __noinline__ void modinv_device(const u32* Lst, u64* Ul, u64 L) {
+  const unsigned k = Lst[1];
+  const u32* ia = Lst + 3;
+  const u32* ip = ia + k;
+  const u32* oo = ip + k + 1;
+  u64 a[4] = {0, 0, 0, 0}, p[4] = {0, 0, 0, 0};
+  for (unsigned i = 0; i < k && i < 4; i++) { a[i] = LDU(ia[i]); p[i] = LDU(ip[i]); }
+  STU(ip[k], 0);
+  u64 u[4], v[4] = {p[0], p[1], p[2], p[3]}, x1[4] = {1, 0, 0, 0}, x2[4] = {0, 0, 0, 0};
+  // u = a mod p, bit-serial with the carry of the doubling kept (rr < p <= 2^256 - 1)
+  {
+    u64 rr[4] = {0, 0, 0, 0};
+    for (int i = 255; i >= 0; i--) {
+      const u32 c = add256(rr, rr, rr);
+      rr[0] |= (a[i >> 6] >> (i & 63)) & 1;
+      if (c || geq256(rr, p)) sub256(rr, rr, p);
+    }
+    u[0] = rr[0]; u[1] = rr[1]; u[2] = rr[2]; u[3] = rr[3];
+  }
+  u64 r[4] = {0, 0, 0, 0};
+  if ((u[0] | u[1] | u[2] | u[3]) != 0 && (p[0] & 1)) {
+    auto half = [&](u64* x) {
+      u32 c = 0;
+      if (x[0] & 1) c = add256(x, x, p);
+      shr1_256(x);
+      x[3] |= (u64)c << 63;
+    };
+    auto submod = [&](u64* x, const u64* y) {
+      if (sub256(x, x, y)) add256(x, x, p);
+    };
+    auto is_one = [](const u64* x) { return x[0] == 1 && (x[1] | x[2] | x[3]) == 0; };
+    unsigned guard = 0;
+    while (!is_one(u) && !is_one(v) && guard++ < 1100) {
+      while (!(u[0] & 1)) { shr1_256(u); half(x1); }
+      while (!(v[0] & 1)) { shr1_256(v); half(x2); }
+      if (geq256(u, v)) { sub256(u, u, v); submod(x1, x2); }
+      else { sub256(v, v, u); submod(x2, x1); }
+      if ((u[0] | u[1] | u[2] | u[3]) == 0 || (v[0] | v[1] | v[2] | v[3]) == 0) break;  // gcd > 1: p not prime
+    }
+    const bool use1 = is_one(u);
+#pragma unroll
+    for (int i = 0; i < 4; i++) r[i] = use1 ? x1[i] : x2[i];
+    if (!is_one(u) && !is_one(v)) r[0] = r[1] = r[2] = r[3] = 0;
+  }
+  for (unsigned i = 0; i < k && i < 4; i++) STU(oo[i], r[i]);
+}
+
 __device__ __noinline__ u32 bigdiv_device(const u32* Lst, u64* Ul, u64 L) {
   const unsigned k = Lst[1], m = Lst[2];
   const u32* ia = Lst + 3;
@@ -491,6 +542,7 @@ __global__ void __launch_bounds__(128, 8) eval_kernel(EvalParams p) {
         break;
       }
       case PZK_BIGDIV: st |= bigdiv_device(list + a, Ul, L); break;
+      case PZK_MODINV: modinv_device(list + a, Ul, L); break;
       case PZK_ASSERT_NZ: if (LDO(a) == 0) st |= PZK_LANE_ASSERT; break;
       case PZK_IN_U: {
         if (p.in_table) {

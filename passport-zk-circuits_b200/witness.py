@@ -77,6 +77,9 @@ def lib():
     L.pzk_compile.restype = ctypes.c_int
     L.pzk_compile.argtypes = [cp, cp, ctypes.POINTER(cp), ctypes.POINTER(ctypes.c_int), ctypes.c_int, u32, cp,
                               ctypes.c_size_t]
+    L.pzk_compile_ex.restype = ctypes.c_int
+    L.pzk_compile_ex.argtypes = [cp, cp, ctypes.POINTER(cp), ctypes.POINTER(ctypes.c_int), ctypes.c_int, u32, u32,
+                                 cp, ctypes.c_size_t]
     L.pzk_circuit_open.restype = ctypes.c_int
     L.pzk_circuit_open.argtypes = [cp, ctypes.c_int, ctypes.POINTER(vp)]
     L.pzk_circuit_close.argtypes = [vp]
@@ -124,7 +127,10 @@ REGISTER_IDENTITY_BITS = {"dg1": 1, "dg15": 1, "encapsulatedContent": 1, "signed
                           "pubkey": 64, "signature": 64}
 
 
-def compile_circuit(main_path, out_prefix, input_bits=None, segment_ops=0):
+COMPILE_STATIC_DEF_ROWS, COMPILE_NO_INTRINSICS = 1, 2
+
+
+def compile_circuit(main_path, out_prefix, input_bits=None, segment_ops=0, static_def_rows=False, intrinsics=True):
     """circom -> program (.pzkp) + .r1cs + .sym; the role of
     `circom <file> --r1cs --wasm --sym` (/root/reference/circuits/scripts/compile-circuit.sh:34)."""
     L = lib()
@@ -133,8 +139,9 @@ def compile_circuit(main_path, out_prefix, input_bits=None, segment_ops=0):
     widths = (ctypes.c_int * max(1, len(input_bits)))(*list(input_bits.values()))
     err = ctypes.create_string_buffer(4096)
     os.makedirs(os.path.dirname(os.path.abspath(out_prefix)), exist_ok=True)
-    rc = L.pzk_compile(os.fsencode(main_path), os.fsencode(out_prefix), names, widths, len(input_bits),
-                       segment_ops, err, len(err))
+    flags = (COMPILE_STATIC_DEF_ROWS if static_def_rows else 0) | (0 if intrinsics else COMPILE_NO_INTRINSICS)
+    rc = L.pzk_compile_ex(os.fsencode(main_path), os.fsencode(out_prefix), names, widths, len(input_bits),
+                          segment_ops, flags, err, len(err))
     if rc != 0:
         raise PzkError("compile failed: " + err.value.decode(errors="replace"))
     return out_prefix + ".pzkp"

@@ -13,6 +13,11 @@ if name == 'c3':
     fac = PassportFactory(C3, seed=1, n_sig_keys=2, n_aa_keys=2)
     uniq = W.pack_inputs_fast(calc.meta, [fac.make(i).inputs for i in range(64)])
     inp = np.tile(uniq, ((B + 63) // 64, 1, 1))[:B]
+elif name.startswith('c4_'):
+    from passport_zk_circuits_b200.artifacts import C4_VARIANTS
+    fac = PassportFactory(C4_VARIANTS[name], seed=1, n_sig_keys=2, n_aa_keys=2)
+    uniq = W.pack_inputs_fast(calc.meta, [fac.make(i).inputs for i in range(16)])
+    inp = np.tile(uniq, ((B + 15) // 16, 1, 1))[:B]
 else:
     sys.path.insert(0, '/root/repo/tests')
     from util import random_inputs

@@ -13,7 +13,7 @@ from conftest import REFERENCE, has_reference
 from util import ROOT, input_dict, ints_to_u64, random_inputs, u64_to_ints
 
 OWN = {"t_mix": "tests/circuits/mix.circom", "t_bigdiv": "tests/circuits/bigdiv.circom",
-       "t_earlyret": "tests/circuits/earlyret.circom"}
+       "t_earlyret": "tests/circuits/earlyret.circom", "t_modinv": "tests/circuits/modinv.circom"}
 REF_SMALL = ["poseidon2", "sha256_1", "smt80", "babyjub"]
 
 
@@ -85,6 +85,32 @@ def test_own_early_returns_under_data_dependent_conditions(artifacts_dir):
     row[d["c"]["offset"], 0] = 1
     st, _, _ = prog.witness(row)
     assert st & 1
+
+
+def modinv_inputs(meta, B, seed):
+    inp = random_inputs(meta, B, seed)
+    inp[0, :, 0] = 0                                                                # a == 0
+    inp[1, 0, 0] = np.uint64(0xFFFFFFFFFFFFFFFF); inp[1, 1, 0] = np.uint64(33554431)  # a == p
+    inp[2, 0, 0] = 1; inp[2, 1, 0] = 0                                              # a == 1
+    inp[3, :, 0] = np.uint64(0xFFFFFFFFFFFFFFFF)                                    # a == 2^128 - 1 >= p
+    return inp
+
+
+def test_own_modinv_intrinsic_equals_function(artifacts_dir, tmp_path):
+    """A function named mod_inv with a constant prime modulus (bigIntFunc.circom:430-465 in the reference)
+    becomes one MODINV record; same signals as the interpreted square-and-multiply, and as the program
+    compiled with the intrinsic switched off."""
+    prog = oracle_ref.RefProgram(os.path.join(artifacts_dir, "t_modinv.pzkp"))
+    assert prog.meta["stats"]["modinv"] == 1
+    inp = modinv_inputs(prog.meta, 24, 3)
+    compare(os.path.join(artifacts_dir, "t_modinv"), os.path.join(ROOT, OWN["t_modinv"]), inp)
+    from passport_zk_circuits_b200 import witness as W
+    plain = W.compile_circuit(os.path.join(ROOT, OWN["t_modinv"]), str(tmp_path / "plain"), {"a": 64}, intrinsics=False)
+    unrolled = oracle_ref.RefProgram(plain)
+    assert unrolled.meta["stats"]["modinv"] == 0
+    for row in inp:
+        a, b = prog.witness(row), unrolled.witness(row)
+        assert a[:2] == b[:2] == (0, -1) and np.array_equal(a[2], b[2])
 
 
 @pytest.mark.skipif(not has_reference(), reason="/root/reference is not mounted here")

@@ -189,6 +189,43 @@ def test_synthetic_passport_is_a_valid_signed_document():
     assert PassportFactory(C3, seed=9, n_sig_keys=2, n_aa_keys=2).make(4).inputs == i
 
 
+def test_definitional_rows_discharged_statically_change_no_verdict(artifacts_dir):
+    """pzk.h PZK_COMPILE_STATIC_DEF_ROWS: `c3_lean` drops the run-time check of every `x <== e` row
+    (x holds value(e) by construction).  Same wires, and for valid and for tampered passports the
+    same status and the same first failing constraint as the program that evaluates every row."""
+    full = oracle_ref.RefProgram(W.artifact("c3"))
+    lean = oracle_ref.RefProgram(W.artifact("c3_lean"))
+    assert lean.n_wires == full.n_wires and lean.n_constraints == full.n_constraints
+    sf, sl = full.meta["stats"], lean.meta["stats"]
+    assert sf.get("def_rows", 0) == 0 and sl["def_rows"] > 900000
+    assert sl["static_rows"] == sf["static_rows"]
+    run_f = sf["i64_rows"] + sf["int_rows"] + sf["field_rows"]
+    run_l = sl["i64_rows"] + sl["int_rows"] + sl["field_rows"]
+    assert run_f == run_l + sl["def_rows"]
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "c3.json")))
+    inp = W.pack_inputs_fast(lean.meta, [golden_inputs(lean.meta, g["cases"][0])])[0]
+    st, fb, wit = lean.witness(inp)
+    assert st == 0 and fb == -1
+    assert hashlib.sha256(wit.tobytes()).hexdigest() == g["cases"][0]["wtns_data_sha256"]
+    d = {x["name"]: x for x in lean.meta["inputs"]}
+    tampered = []
+    for name, k, bit in (("signature", 3, 5), ("pubkey", 0, 1), ("dg1", 100, 0), ("encapsulatedContent", 700, 0),
+                         ("signedAttributes", 300, 0), ("slaveMerkleRoot", 0, 7), ("dg15", 40, 0)):
+        row = inp.copy()
+        row[d[name]["offset"] + k, 0] ^= np.uint64(1 << bit)
+        tampered.append(row)
+    row = inp.copy()
+    row[d["dg1"]["offset"] + 7, 0] = 2           # not a bit: input range status
+    tampered.append(row)
+    n_fail = 0
+    for row in tampered:
+        a = full.witness(row, want_witness=False)
+        b = lean.witness(row, want_witness=False)
+        assert a[:2] == b[:2], (a[:2], b[:2])
+        n_fail += a[0] != 0
+    assert n_fail >= 6
+
+
 def test_ecdsa_passport_through_the_compiled_program(artifacts_dir):
     """SIGNATURE_TYPE 20 (P-256 + SHA-256, signatureVerification.circom:177-191): the generator's
     signature verifies in plain Python, the compiled program satisfies all 5.47 M constraints for it,
@@ -269,3 +306,65 @@ def test_query_inputs_follow_the_reference_recipe():
     x, y = ed_mul(12345, BASE8)
     assert (168700 * x * x + y * y - 1 - 168696 * x * x * y * y) % W.P == 0
     assert make_query_input(3, seed=2) == make_query_input(3, seed=2)
+
+
+def test_modinv_device_algorithm_on_the_host(tmp_path):
+    """The body of modinv_device (csrc/pzk_kernels.cuh, the PZK_MODINV intrinsic) compiled for the host
+    with plain-C stand-ins for the PTX carry helpers, against Python's pow(a, -1, p): moduli above
+    2^255 (P-256), short moduli (k = 1, 3), a >= p, a == 0 (mod p)."""
+    import random
+    src = open(os.path.join(ROOT, "passport-zk-circuits_b200", "csrc", "pzk_kernels.cuh")).read()
+    start = src.index("__device__ __noinline__ void modinv_device")
+    body = src[start:src.index("\n}\n", start) + 3]
+    harness = r'''
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+typedef uint64_t u64; typedef uint32_t u32; typedef unsigned __int128 u128;
+#define __device__
+#define __noinline__
+static u32 add256(u64* r, const u64* a, const u64* b) { u128 c = 0; for (int i = 0; i < 4; i++) { c += (u128)a[i] + b[i]; r[i] = (u64)c; c >>= 64; } return (u32)c; }
+static u32 sub256(u64* r, const u64* a, const u64* b) { u64 br = 0; for (int i = 0; i < 4; i++) { u128 d = (u128)a[i] - b[i] - br; r[i] = (u64)d; br = (u64)(d >> 64) & 1; } return (u32)br; }
+static void shr1_256(u64* a) { a[0] = (a[0] >> 1) | (a[1] << 63); a[1] = (a[1] >> 1) | (a[2] << 63); a[2] = (a[2] >> 1) | (a[3] << 63); a[3] >>= 1; }
+static bool geq256(const u64* a, const u64* b) { for (int i = 3; i >= 0; i--) if (a[i] != b[i]) return a[i] > b[i]; return true; }
+#define LDU(slot) (Ul[(u64)(slot) * L])
+#define STU(slot, v) (Ul[(u64)(slot) * L] = (v))
+''' + body + r'''
+int main() {
+  unsigned k;
+  while (scanf("%u", &k) == 1) {
+    u64 U[16] = {0}; u32 lst[3 + 4 + 4 + 1 + 4] = {64, k, 0};
+    for (unsigned i = 0; i < 2 * k; i++) { unsigned long long v; if (scanf("%llx", &v) != 1) return 1; U[i] = v; lst[3 + i] = i; }
+    for (unsigned i = 0; i < 1 + k; i++) lst[3 + 2 * k + i] = 2 * k + i;
+    U[2 * k] = 77;
+    modinv_device(lst, U, 1);
+    printf("%llx", (unsigned long long)U[2 * k]);
+    for (unsigned i = 0; i < k; i++) printf(" %llx", (unsigned long long)U[2 * k + 1 + i]);
+    printf("\n");
+  }
+  return 0;
+}
+'''
+    cpp = tmp_path / "modinv_host.cpp"
+    cpp.write_text(harness)
+    exe = str(tmp_path / "modinv_host")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-Wno-unknown-pragmas", "-o", exe, str(cpp)])
+    p256 = 0xFFFFFFFF00000001000000000000000000000000FFFFFFFFFFFFFFFFFFFFFFFF
+    n256 = 0xFFFFFFFF00000000FFFFFFFFFFFFFFFFBCE6FAADA7179E84F3B9CAC2FC632551
+    p192 = 2**192 - 2**64 - 1
+    rng = random.Random(12)
+    cases = []
+    fr_p = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+    for p, k in ((p256, 4), (n256, 4), (fr_p, 4), (p192, 3), (2**127 - 1, 2), (65537, 1), (3, 1)):
+        top = 1 << (64 * k)
+        for a in [0, 1, 2, p - 1, p % top, (p + 5) % top, top - 1] + [rng.randrange(top) for _ in range(40)]:
+            cases.append((k, a, p))
+    text = "".join("%d %s %s\n" % (k, " ".join("%x" % ((a >> (64 * i)) & (2**64 - 1)) for i in range(k)),
+                                   " ".join("%x" % ((p >> (64 * i)) & (2**64 - 1)) for i in range(k))) for k, a, p in cases)
+    out = subprocess.run([exe], input=text, capture_output=True, text=True, check=True).stdout.split("\n")
+    for (k, a, p), line in zip(cases, out):
+        w = [int(x, 16) for x in line.split()]
+        assert w[0] == 0
+        got = sum(v << (64 * i) for i, v in enumerate(w[1:]))
+        want = pow(a % p, -1, p) if a % p else 0
+        assert got == want, (k, hex(a), hex(p), hex(got), hex(want))

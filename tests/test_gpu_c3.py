@@ -148,3 +148,28 @@ def test_config2_query_identity():
             assert np.array_equal(out.witnesses[[0, 17, B - 1].index(b)], wit)
     assert out.status[17] & W.STATUS_CONSTRAINT and (np.delete(out.status, 17) == 0).all()
     calc.close()
+
+
+def test_c3_lean_program_same_verdicts(c3):
+    """`c3_lean` (definitional rows discharged at compile time, pzk.h PZK_COMPILE_STATIC_DEF_ROWS): the device
+    returns the same status / first_bad / public signals as the all-rows program and the oracle."""
+    prog, calc, ref = c3
+    lean = W.WitnessCalculator(W.artifact("c3_lean"), device=0)
+    fac = PassportFactory(C3, seed=5, n_sig_keys=2, n_aa_keys=2)
+    B = 24
+    inp = W.pack_inputs_fast(calc.meta, [fac.make(i).inputs for i in range(B)])
+    d = {x["name"]: x for x in calc.meta["inputs"]}
+    inp[3, d["signature"]["offset"] + 2, 0] ^= np.uint64(16)
+    inp[8, d["dg1"]["offset"] + 99, 0] ^= np.uint64(1)
+    inp[13, d["slaveMerkleRoot"]["offset"], 0] ^= np.uint64(2)
+    inp[20, d["dg1"]["offset"] + 5, 0] = np.uint64(3)
+    a = calc.calculateWitnessBatch(inp)
+    b = lean.calculateWitnessBatch(inp, export_lanes=[0, 3])
+    assert np.array_equal(a.status, b.status) and np.array_equal(a.first_bad, b.first_bad)
+    assert np.array_equal(a.public, b.public)
+    for j, lane in enumerate((0, 3)):
+        st, fb, wit = ref.witness(inp[lane], want_witness=True)
+        assert int(b.status[lane]) == st and int(b.first_bad[lane]) == fb
+        assert np.array_equal(b.witnesses[j], wit)
+    assert (a.status[[3, 8, 13, 20]] != 0).all() and (np.delete(a.status, [3, 8, 13, 20]) == 0).all()
+    lean.close()

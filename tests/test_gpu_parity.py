@@ -95,6 +95,19 @@ def test_early_returns_and_narrowed_limb():
     assert (np.delete(res.status, 9) == 0).all()
 
 
+def test_modinv_intrinsic():
+    prog = oracle_ref.RefProgram(W.artifact("t_modinv"))
+    inp = random_inputs(prog.meta, 300, 9)
+    inp[0, :, 0] = 0
+    inp[1, 0, 0] = np.uint64(0xFFFFFFFFFFFFFFFF); inp[1, 1, 0] = np.uint64(33554431)
+    inp[2, 0, 0] = 1; inp[2, 1, 0] = 0
+    inp[3, :, 0] = np.uint64(0xFFFFFFFFFFFFFFFF)
+    res = run_and_compare("t_modinv", inp)
+    assert (res.status == 0).all()
+    rem = res.public[:, 2, 0]                        # outputs: inv[2], rem
+    assert rem[0] == 0 and rem[1] == 0 and (rem[2:] == 1).all()
+
+
 @pytest.mark.parametrize("name,B", [("poseidon2", 200), ("sha256_1", 130), ("babyjub", 66)])
 def test_reference_small(name, B):
     prog = oracle_ref.RefProgram(W.artifact(name))
