@@ -90,7 +90,10 @@ def _stale(out, deps):
 
 def build_all(verbose=True):
     os.makedirs(W.ARTIFACT_DIR, exist_ok=True)
-    deps = [W.LIB_PATH]
+    # programs depend on the compiler, not on the kernels that share the library with it
+    csrc = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
+    deps = [os.path.join(csrc, f) for f in ("compiler.cpp", "compiler.hpp", "circom_front.hpp", "u256.hpp")]
+    deps.append(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "pzk_program.h"))
     for name, (fname, bits) in OWN_CIRCUITS.items():
         prefix = os.path.join(W.ARTIFACT_DIR, name)
         src = os.path.join(_TESTS, fname)

@@ -47,8 +47,13 @@ struct EvalParams {
   unsigned long long* first_bad;
 };
 
-#define LDU(slot) (Ul[(u64)(slot) * L])
-#define STU(slot, v) (Ul[(u64)(slot) * L] = (v))
+// Slot planes are private to a lane and far larger than any cache, but their accesses still go through
+// L1 (plain ld/st.global): routing them around it with ld/st.global.cg cost 17 % of the throughput
+// (35.5 k instead of 42.6 k witnesses/s, profiles/README.md) - L1 merges the sectors of neighbouring slots.
+#define PLD(ptr) (*(ptr))
+#define PST(ptr, v) (*(ptr) = (v))
+#define LDU(slot) PLD(Ul + (u64)(slot) * L)
+#define STU(slot, v) PST(Ul + (u64)(slot) * L, (v))
 // operand words: bit 31 -> shared-memory cell, else global slot (see pzk_program.h).
 // Cells are addressed with explicit 32-bit shared-space addresses: `cells` is the lane's base
 // (shared window offset + 8 * tid); cell c lives at cells + c * 8 * 128.  (x << 10) turns an operand
@@ -60,22 +65,22 @@ __device__ __forceinline__ u64 lds64(u32 addr) {
 }
 __device__ __forceinline__ void sts64(u32 addr, u64 v) { asm volatile("st.shared.u64 [%0], %1;" ::"r"(addr), "l"(v) : "memory"); }
 #define CELL_ADDR(x) (cells + ((u32)(x) << 10))
-#define LDO(x) (((x) & PZK_OPERAND_CELL) ? lds64(CELL_ADDR(x)) : Ul[(u64)(x) * L])
+#define LDO(x) (((x) & PZK_OPERAND_CELL) ? lds64(CELL_ADDR(x)) : PLD(Ul + (u64)(x) * L))
 // destination words: global slot always, cell when assigned
 #define STD(d, v)                                                        \
   do {                                                                   \
     const u64 v__ = (v);                                                 \
-    if (!((d) & PZK_DST_OPTIONAL) || store_all) Ul[(u64)PZK_DST_SLOT(d) * L] = v__; \
+    if (!((d) & PZK_DST_OPTIONAL) || store_all) PST(Ul + (u64)PZK_DST_SLOT(d) * L, v__); \
     if (PZK_DST_CELL(d)) sts64(cells + ((PZK_DST_CELL(d) - 1) << 10), v__); \
   } while (0)
 
 __device__ __forceinline__ void ldF(const u64* Fl, u64 L, u32 slot, u64* v) {
   const u64* p = Fl + (u64)slot * 4 * L;
-  v[0] = p[0]; v[1] = p[L]; v[2] = p[2 * L]; v[3] = p[3 * L];
+  v[0] = PLD(p); v[1] = PLD(p + L); v[2] = PLD(p + 2 * L); v[3] = PLD(p + 3 * L);
 }
 __device__ __forceinline__ void stF(u64* Fl, u64 L, u32 slot, const u64* v) {
   u64* p = Fl + (u64)slot * 4 * L;
-  p[0] = v[0]; p[L] = v[1]; p[2 * L] = v[2]; p[3 * L] = v[3];
+  PST(p, v[0]); PST(p + L, v[1]); PST(p + 2 * L, v[2]); PST(p + 3 * L, v[3]);
 }
 __device__ __forceinline__ void ldFo(const u64* Fl, u64 L, u32 cells, u32 NT, u32 x, u64* v) {
   (void)NT;
@@ -259,7 +264,7 @@ __device__ __forceinline__ long long term_icoef(const u32* list, u32 ref, u32 cw
   return (long long)(int)cw;
 }
 // exact integer row: |A|,|B| < 2^63 and |C| < 2^126 proven by the compiler
-#define TERM_U(ref) (((ref) & PZK_TERM_CELL) ? lds64(cells + ((u32)(ref) << 10)) : Ul[(u64)PZK_REF_SLOT(ref) * L])
+#define TERM_U(ref) (((ref) & PZK_TERM_CELL) ? lds64(cells + ((u32)(ref) << 10)) : PLD(Ul + (u64)PZK_REF_SLOT(ref) * L))
 __device__ __forceinline__ bool check_row_int(const uint4* recs, u32 na, u32 nb, u32 nc, const u32* list,
                                               const u64* Ul, u64 L, u32 cells, u32 NT) {
   long long A = 0, B = 0;
@@ -470,11 +475,11 @@ __global__ void __launch_bounds__(128, 8) eval_kernel(EvalParams p) {
       case PZK_N_FROM_U: { u64 v[4] = {LDO(a), 0, 0, 0}; STFD(v); break; }
       case PZK_N_BIT: {
         u64 limb = 0;
-        if (b < 256) limb = (a & PZK_OPERAND_CELL) ? lds64(CELL_ADDR(a) + ((b >> 6) << 10)) : Fl[((u64)a * 4 + (b >> 6)) * L];
+        if (b < 256) limb = (a & PZK_OPERAND_CELL) ? lds64(CELL_ADDR(a) + ((b >> 6) << 10)) : PLD(Fl + ((u64)a * 4 + (b >> 6)) * L);
         STD(dst, (limb >> (b & 63)) & 1);
         break;
       }
-      case PZK_N_LOW: STD(dst, (a & PZK_OPERAND_CELL) ? lds64(CELL_ADDR(a)) : Fl[(u64)a * 4 * L]); break;
+      case PZK_N_LOW: STD(dst, (a & PZK_OPERAND_CELL) ? lds64(CELL_ADDR(a)) : PLD(Fl + (u64)a * 4 * L)); break;
       case PZK_N_FITS: { u64 v[4]; LDFA(v); STD(dst, (u64)((v[1] | v[2] | v[3]) == 0)); break; }
       case PZK_N_SHR: { u64 v[4], r[4]; LDFA(v); u64 d = UBV; shr256(r, v, d > 256 ? 256u : (unsigned)d); STFD(r); break; }
       case PZK_N_SHL: {

@@ -27,7 +27,8 @@ P = 2188824287183927522224640574525727508854836440041603434369820418657580849561
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
-LIB_PATH = os.path.join(_HERE, "lib", "libpzk.so")
+# PZK_LIB_PATH selects another build of the same library (kernel A/B measurements); it is still the CUDA library
+LIB_PATH = os.environ.get("PZK_LIB_PATH") or os.path.join(_HERE, "lib", "libpzk.so")
 ARTIFACT_DIR = os.path.join(_ROOT, "artifacts")
 
 PZK_ENODEVICE = -3

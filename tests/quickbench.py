@@ -16,13 +16,17 @@ if name == 'c3':
 elif name.startswith('c4_'):
     from passport_zk_circuits_b200.artifacts import C4_VARIANTS
     fac = PassportFactory(C4_VARIANTS[name], seed=1, n_sig_keys=2, n_aa_keys=2)
-    uniq = W.pack_inputs_fast(calc.meta, [fac.make(i).inputs for i in range(16)])
-    inp = np.tile(uniq, ((B + 15) // 16, 1, 1))[:B]
+    uniq = calc.pack(W.pack_inputs_fast(calc.meta, [fac.make(i).inputs for i in range(16)]))
+    inp = None
+    packed = np.tile(uniq, ((B + 15) // 16, 1))[:B].copy()
 else:
     sys.path.insert(0, '/root/repo/tests')
     from util import random_inputs
     inp = random_inputs(calc.meta, B, 1, field_bits=248)
-calc.upload(inp)
+if inp is None:
+    calc.upload_packed(packed)
+else:
+    calc.upload(inp)
 calc.profile(enable=True, reset=True)
 for it in range(3):
     t = time.time(); calc.run(True); dt = time.time() - t
