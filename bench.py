@@ -272,6 +272,7 @@ def main():
                 "warmup": a.warmup, "ms_per_step": 1000.0 * dev_s / a.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "u64+fr256", "data": "synthetic",
                 "constraints_per_sec": value * calc.n_constraints,
+                "runtime_rows_per_sec": value * (calc.meta["stats"]["i64_rows"] + calc.meta["stats"]["int_rows"] + calc.meta["stats"]["field_rows"]),
                 "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": total,
                            "unique_passports_per_gpu": min(UNIQUE, B), "tile_lanes": calc.tile_lanes(),
                            "n_wires": calc.n_wires, "n_constraints": calc.n_constraints,
@@ -320,41 +321,53 @@ def main():
                                               f"and inputs; reference wasm baseline unavailable on this host)"}
         ms_all = calc.meta["stats"]
         line["rows"] = {"total": calc.n_constraints, "static_alias": ms_all["static_rows"],
+                        "static_table_proof": ms_all.get("table_rows", 0),
+                        "static_symbolic_proof": ms_all.get("symbolic_rows", 0),
                         "static_definitional": ms_all.get("def_rows", 0),
                         "runtime": ms_all["i64_rows"] + ms_all["int_rows"] + ms_all["field_rows"]}
         if world == 1 and not a.no_lean:
-            # same circuit compiled with PZK_COMPILE_STATIC_DEF_ROWS (pzk.h): the rows of `x <== e` are
-            # discharged at compile time, only `===` rows and rows over `<--` hints run.  Reported beside the
-            # headline, never as the headline: `value` above evaluates every non-alias row at run time.
-            try:
-                lean_prog = W.artifact("c3_lean")
-                calc.close()
-                lean = W.WitnessCalculator(lean_prog, device=local_rank)
-                lean.upload_packed(packed)
-                lean.run(True)
-                lres = lean.download()
-                assert np.array_equal(lres.status, res.status) and np.array_equal(lres.public, res.public)
-                lean.profile(enable=True, reset=True)
+            # The same circuit compiled two other ways, measured beside the headline with the same batch:
+            #   all_rows_dynamic: PZK_COMPILE_NO_TABLE_PROOFS - only alias rows are discharged at compile time,
+            #                     every other row is evaluated on the device (the round-1 mid-round program);
+            #   lean_rows:        PZK_COMPILE_STATIC_DEF_ROWS - rows of `x <== e` the provers could not close
+            #                     are dropped on the by-construction argument alone.
+            # `value` above is the default program: alias + table + symbolic proofs, everything else at run time.
+            calc.close()
+
+            def measure_variant(name):
+                try:
+                    vprog = W.artifact(name)
+                except W.PzkError as e:
+                    return {"unavailable": str(e)}
+                v = W.WitnessCalculator(vprog, device=local_rank)
+                v.upload_packed(packed)
+                v.run(True)
+                vres = v.download()
+                assert np.array_equal(vres.status, res.status) and np.array_equal(vres.public, res.public)
+                assert np.array_equal(vres.first_bad, res.first_bad)
+                v.profile(enable=True, reset=True)
                 torch.cuda.synchronize()
-                lsteps = max(1, min(a.steps, 2))
-                for _ in range(lsteps):
-                    lean.run(True)
+                vsteps = max(1, min(a.steps, 2))
+                for _ in range(vsteps):
+                    v.run(True)
                 torch.cuda.synchronize()
-                lms = lean.profile()["run"][0]
-                ls = lean.meta["stats"]
-                lbytes = ls.get("eval_bytes", 0) + ls.get("check_bytes", 0)
-                lv = B * lsteps / (lms / 1e3)
-                line["lean_rows"] = {"value": lv, "unit": "witnesses/s", "steps": lsteps, "ms_per_step": lms / lsteps,
-                                     "tile_lanes": lean.tile_lanes(),
-                                     "rows": {"total": lean.n_constraints, "static_alias": ls["static_rows"],
-                                              "static_definitional": ls.get("def_rows", 0),
-                                              "runtime": ls["i64_rows"] + ls["int_rows"] + ls["field_rows"]},
-                                     "algorithmic_bytes_per_witness": lbytes,
-                                     "roofline_frac": lbytes * lv / 1e9 / hbm_peak,
-                                     "note": "same wires, statuses and public signals (asserted above); not the headline"}
-                lean.close()
-            except W.PzkError as e:
-                line["lean_rows"] = {"unavailable": str(e)}
+                vms = v.profile()["run"][0]
+                vs = v.meta["stats"]
+                vbytes = vs.get("eval_bytes", 0) + vs.get("check_bytes", 0)
+                vv = B * vsteps / (vms / 1e3)
+                out = {"value": vv, "unit": "witnesses/s", "steps": vsteps, "ms_per_step": vms / vsteps,
+                       "tile_lanes": v.tile_lanes(), "op_records_per_witness": vs["op_records"],
+                       "rows": {"total": v.n_constraints, "static_alias": vs["static_rows"],
+                                "static_table_proof": vs.get("table_rows", 0),
+                                "static_symbolic_proof": vs.get("symbolic_rows", 0),
+                                "static_definitional": vs.get("def_rows", 0),
+                                "runtime": vs["i64_rows"] + vs["int_rows"] + vs["field_rows"]},
+                       "algorithmic_bytes_per_witness": vbytes, "roofline_frac": vbytes * vv / 1e9 / hbm_peak,
+                       "note": "same statuses, first_bad and public signals as the headline program (asserted)"}
+                v.close()
+                return out
+            line["all_rows_dynamic"] = measure_variant("c3_allrows")
+            line["lean_rows"] = measure_variant("c3_lean")
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()

@@ -64,6 +64,12 @@ int pzk_compile(const char* main_circom_path, const char* out_prefix, const char
  * instead of using the device intrinsic (validation of the intrinsic).                             */
 #define PZK_COMPILE_STATIC_DEF_ROWS 1u
 #define PZK_COMPILE_NO_INTRINSICS 2u
+/* Beyond alias rows the compiler discharges two more kinds of rows at compile time, each by a proof it
+ * checks itself: rows whose wires are all truth-table functions of <= 8 proven bits (evaluated for every
+ * assignment of those bits), and rows that cancel when their wires are expanded through the ops that
+ * define them (`z <== x + 2^k * y`, `z <== x * y`).  <prefix>.rowkind records the kind per constraint.
+ * This flag keeps both kinds as run-time checks instead.                                              */
+#define PZK_COMPILE_NO_TABLE_PROOFS 4u
 int pzk_compile_ex(const char* main_circom_path, const char* out_prefix, const char* const* bits_names,
                    const int* bits_widths, int n_bits, uint32_t segment_ops, uint32_t flags, char* err,
                    size_t err_len);

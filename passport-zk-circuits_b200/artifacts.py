@@ -65,6 +65,9 @@ def reference_circuits():
         # PZK_COMPILE_STATIC_DEF_ROWS); same wires, same verdicts, 353 k instead of 1.29 M run-time rows
         "c3_lean": (C3.main_source(REFERENCE + "/circuits/identityManagement/registerIdentityBuilder.circom"),
                     W.REGISTER_IDENTITY_BITS),
+        # config 3 with alias proofs only (PZK_COMPILE_NO_TABLE_PROOFS): every other row runs on the device
+        "c3_allrows": (C3.main_source(REFERENCE + "/circuits/identityManagement/registerIdentityBuilder.circom"),
+                       W.REGISTER_IDENTITY_BITS),
         # config 4: SHA-1 / RSA-PSS variants with other hash types and shifts
         **{name: (prm.main_source(REFERENCE + "/circuits/identityManagement/registerIdentityBuilder.circom"),
                   W.REGISTER_IDENTITY_BITS) for name, prm in C4_VARIANTS.items()},
@@ -76,9 +79,10 @@ OWN_CIRCUITS = {"t_mix": ("mix.circom", {"u": 16, "bits": 1}),
                 "t_earlyret": ("earlyret.circom", {"v": 16, "a": 64, "b": 64, "c": 1}),
                 "t_modinv": ("modinv.circom", {"a": 64})}
 
-COMPILE_OPTS = {"c3_lean": {"static_def_rows": True, "segment_ops": 8192}}
+COMPILE_OPTS = {"c3_lean": {"static_def_rows": True},
+                "c3_allrows": {"table_proofs": False, "segment_ops": 16384}}
 
-BIG = {"c3", "c3_lean", "c4_sig3", "c4_sig10", "c4_sig13", "c4_sig20"}  # ship only the xz-packed program for these
+BIG = {"c3", "c3_lean", "c3_allrows", "c4_sig3", "c4_sig10", "c4_sig13", "c4_sig20"}  # ship only the xz-packed program for these
 
 
 def _stale(out, deps):

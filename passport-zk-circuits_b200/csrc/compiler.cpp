@@ -181,7 +181,8 @@ struct Compiler::Impl {
   std::vector<PzkInput> out_inputs;
   std::vector<uint32_t> out_list;
   uint32_t n_u_slots = 0, n_f_slots = 0;
-  uint64_t n_static_rows = 0, n_def_rows = 0, n_i64_rows = 0, n_int_rows = 0, n_field_rows = 0, eval_bytes = 0, check_bytes = 0, cache_hit_refs = 0, cache_miss_refs = 0;
+  std::vector<uint8_t> row_kind;  // per constraint: 0 run-time check, 1 alias, 2 table proof, 3 symbolic proof, 4 definitional
+  uint64_t n_static_rows = 0, n_def_rows = 0, n_table_rows = 0, n_symbolic_rows = 0, n_i64_rows = 0, n_int_rows = 0, n_field_rows = 0, eval_bytes = 0, check_bytes = 0, cache_hit_refs = 0, cache_miss_refs = 0;
   std::vector<uint32_t> seg_quads;
   uint32_t n_pub_out = 0, n_pub_in = 0, n_prv_in = 0;
   std::string meta_json;
@@ -1973,15 +1974,154 @@ void Compiler::Impl::backend() {
     }
     return parts[2].empty() && (parts[0].empty() || parts[1].empty());
   };
-  std::vector<uint8_t> row_static(nrows, 0);
+  std::vector<uint8_t>& row_static = row_kind;
+  row_static.assign(nrows, 0);
   {
     std::vector<MT> parts[3];
+    // A row whose wires are all functions of a few proven bits (truth tables over <= 8 root bits: the
+    // XOR / Maj / Ch / carry rows of SHA, bit checks b * (b - 1) = 0, selectors) is an identity over
+    // those bits: it is evaluated here for every assignment of the roots, with the very tables the device
+    // uses to compute the wires, and discharged when it holds for all of them.
+    auto prove_by_tables = [&](const std::vector<MT>* parts) -> bool {
+      if (!opt.table_rows_static) return false;
+      uint32_t roots[8]; int nr = 0;
+      struct TV { const Table* t; Table self; i128 coef; int pos[4]; };
+      std::vector<TV> tv[3];
+      for (int part = 0; part < 3; part++) {
+        tv[part].clear();
+        for (const MT& m : parts[part]) {
+          TV x; x.t = nullptr;
+          i128 cv;
+          if (!const_narrow(m.c, cv)) return false;
+          x.coef = cv;
+          if (m.val != 0xFFFFFFFFu) {
+            uint32_t id = m.val;
+            if (v_tbl[id] >= 0) x.t = &tables[v_tbl[id]];
+            else if (v_cls[id] == CLS_U && v_lo[id] >= 0 && v_hi[id] <= 1) { x.self.n = 1; x.self.sup[0] = id; x.self.e[0] = 0; x.self.e[1] = 1; }
+            else return false;
+          } else { x.self.n = 0; x.self.e[0] = 1; }
+          tv[part].push_back(x);
+        }
+      }
+      for (int part = 0; part < 3; part++)
+        for (TV& x : tv[part]) {
+          const Table* t = x.t ? x.t : &x.self;
+          for (int j = 0; j < t->n; j++) {
+            int q = 0;
+            while (q < nr && roots[q] != t->sup[j]) q++;
+            if (q == nr) { if (nr >= 8) return false; roots[nr++] = t->sup[j]; }
+            x.pos[j] = q;
+          }
+        }
+      for (int idx = 0; idx < (1 << nr); idx++) {
+        i128 acc[3] = {0, 0, 0};
+        for (int part = 0; part < 3; part++)
+          for (const TV& x : tv[part]) {
+            const Table* t = x.t ? x.t : &x.self;
+            int sub = 0;
+            for (int j = 0; j < t->n; j++) sub |= ((idx >> x.pos[j]) & 1) << j;
+            i128 term;
+            if (__builtin_mul_overflow(x.coef, (i128)t->e[sub], &term) || __builtin_add_overflow(acc[part], term, &acc[part])) return false;
+          }
+        i128 ab;
+        if (__builtin_mul_overflow(acc[0], acc[1], &ab)) return false;
+        // |values| far below p / 2: equality over the integers is equality in the field
+        const i128 lim = (i128)1 << 120;
+        if (ab > lim || ab < -lim || acc[2] > lim || acc[2] < -lim) return false;
+        if (ab != acc[2]) return false;
+      }
+      return true;
+    };
+    // Symbolic proof from the op stream itself: every value is replaced, latest definition first, by the
+    // expression its defining op computes (ADD / SUB / multiplication by a constant / conversions, in U,
+    // I or F class - all exact: narrow ops only exist where the interval analysis excludes a wrap) until
+    // the linear form cancels.  For A * B = C with single-wire A and B the product x * y is matched against
+    // the MUL op that defines a wire of C.  This is what makes `z <== x + 2^k * y` and `z <== x * y`
+    // hold for every input; rows the expansion cannot close stay run-time checks.
+    auto const_of = [&](uint32_t id, U256& out) -> bool {
+      uint32_t di = v_def[id];
+      if (di >= nops) return false;
+      const OpRec& o = ops[di];
+      if (o.dst != id) return false;
+      if (o.opc == PZK_U_CONST) {
+        uint64_t raw = ((uint64_t)o.b << 32) | o.a;
+        if (v_cls[id] == CLS_I && (int64_t)raw < 0) out = fr_neg(U256((uint64_t)(-(int64_t)raw)));
+        else out = U256(raw);
+        return true;
+      }
+      if (o.opc == PZK_F_CONST) { out = fr_from_mont(fpool[o.a]); return true; }
+      return false;
+    };
+    auto prove_symbolic = [&](const std::vector<MT>* parts) -> bool {
+      if (!opt.symbolic_rows_static) return false;
+      std::map<uint32_t, U256> lin;  // value -> coefficient of (A*B - C), constant one under 0xFFFFFFFF
+      auto add = [&](uint32_t v, const U256& c) {
+        if (v != 0xFFFFFFFFu) { U256 k; if (const_of(v, k)) { lin[0xFFFFFFFFu] = fr_add(lin[0xFFFFFFFFu], fr_mul(c, k)); return; } }
+        lin[v] = fr_add(lin[v], c);
+      };
+      for (const MT& m : parts[2]) add(m.val, fr_neg(m.c));
+      bool quad = !parts[0].empty() && !parts[1].empty();
+      uint32_t qx = 0, qy = 0; U256 qc;
+      if (quad) {
+        if (parts[0].size() != 1 || parts[1].size() != 1) return false;
+        qx = parts[0][0].val; qy = parts[1][0].val;
+        if (qx == 0xFFFFFFFFu || qy == 0xFFFFFFFFu) return false;
+        qc = fr_mul(parts[0][0].c, parts[1][0].c);
+      }
+      auto same = [&](uint32_t x, uint32_t y) { return same_value(x, y); };
+      for (int step = 0; step < 48; step++) {
+        // latest-defined value with a non-zero coefficient
+        uint32_t pick = 0; bool any = false;
+        for (auto it = lin.begin(); it != lin.end();) {
+          if (it->second.is_zero()) { it = lin.erase(it); continue; }
+          if (it->first != 0xFFFFFFFFu && (!any || it->first > pick)) { pick = it->first; any = true; }
+          ++it;
+        }
+        if (!any) { auto one = lin.find(0xFFFFFFFFu); return !quad && (one == lin.end() || one->second.is_zero()); }
+        uint32_t di = v_def[pick];
+        if (di >= nops || ops[di].dst != pick) return false;
+        const OpRec& o = ops[di];
+        U256 c = lin[pick];
+        lin.erase(pick);
+        const bool imm = (o.flags & PZK_FLAG_B_IMM) != 0, pool = (o.flags & PZK_FLAG_B_POOL) != 0;
+        switch (o.opc) {
+          case PZK_U_ADD: case PZK_U_SUB: case PZK_F_ADD: case PZK_F_SUB: {
+            const bool sub_ = (o.opc == PZK_U_SUB || o.opc == PZK_F_SUB);
+            add(o.a, c);
+            U256 cb = sub_ ? fr_neg(c) : c;
+            if (imm) add(0xFFFFFFFFu, fr_mul(cb, U256((uint64_t)o.b)));
+            else if (pool) add(0xFFFFFFFFu, fr_mul(cb, fr_from_mont(fpool[o.b])));
+            else add(o.b, cb);
+            break;
+          }
+          case PZK_U_MUL: case PZK_F_MUL: {
+            U256 k;
+            if (imm) { add(o.a, fr_mul(c, U256((uint64_t)o.b))); break; }
+            if (pool) { add(o.a, fr_mul(c, fr_from_mont(fpool[o.b]))); break; }
+            if (const_of(o.b, k)) { add(o.a, fr_mul(c, k)); break; }
+            if (const_of(o.a, k)) { add(o.b, fr_mul(c, k)); break; }
+            // a genuine product: it must be the row's own A * B, with exactly the opposite coefficient
+            if (!quad) return false;
+            if (!((same(o.a, qx) && same(o.b, qy)) || (same(o.a, qy) && same(o.b, qx)))) return false;
+            if (!(fr_add(c, qc).is_zero())) return false;
+            quad = false;
+            break;
+          }
+          case PZK_F_NEG: add(o.a, fr_neg(c)); break;
+          case PZK_F_FROM_U: case PZK_F_FROM_I: add(o.a, c); break;
+          default: return false;
+        }
+      }
+      return false;
+    };
     for (size_t r = 0; r < nrows; r++) {
       if (merge_row((uint32_t)r, parts)) { row_static[r] = 1; n_static_rows++; }
+      else if (prove_by_tables(parts)) { row_static[r] = 2; n_table_rows++; }
+      else if (prove_symbolic(parts)) { row_static[r] = 3; n_symbolic_rows++; }
       // `x <== e` stores value(e) into x and adds the row e - x = 0: the wire holds the very value the
       // row compares it with, so the row holds for every input (the same argument as for aliases, one
       // multiplication deeper).  Only `===` rows and rows over `<--` hints can fail at run time.
-      else if (rows[r].by_def && opt.def_rows_static) { row_static[r] = 1; n_def_rows++; }
+      else if (rows[r].by_def && opt.def_rows_static) { row_static[r] = 4; n_def_rows++; }
     }
   }
   // ---- segments over kept ops (+ their rows)
@@ -2423,7 +2563,7 @@ void Compiler::Impl::build_meta() {
        ",\"f_inv\":" + std::to_string(stats->f_inv) + ",\"f_inv_real\":" + std::to_string(stats->f_inv_real) + ",\"f_other\":" + std::to_string(stats->f_other) +
        ",\"bigdiv\":" + std::to_string(stats->bigdiv) + ",\"modinv\":" + std::to_string(stats->modinv) + ",\"lut\":" + std::to_string(stats->lut) +
        ",\"op_records\":" + std::to_string(out_ops.size()) + ",\"segments\":" + std::to_string(segs.size()) +
-       ",\"static_rows\":" + std::to_string(n_static_rows) + ",\"def_rows\":" + std::to_string(n_def_rows) + ",\"i64_rows\":" + std::to_string(n_i64_rows) +
+       ",\"static_rows\":" + std::to_string(n_static_rows) + ",\"def_rows\":" + std::to_string(n_def_rows) + ",\"table_rows\":" + std::to_string(n_table_rows) + ",\"symbolic_rows\":" + std::to_string(n_symbolic_rows) + ",\"i64_rows\":" + std::to_string(n_i64_rows) +
        ",\"int_rows\":" + std::to_string(n_int_rows) + ",\"field_rows\":" + std::to_string(n_field_rows) +
        ",\"eval_bytes\":" + std::to_string(eval_bytes) + ",\"check_bytes\":" + std::to_string(check_bytes) +
        ",\"cells\":" + std::to_string(opt.cells) + ",\"cache_hit_refs\":" + std::to_string(cache_hit_refs) +
@@ -2496,6 +2636,16 @@ void Compiler::write_program(const std::string& path) {
   section(m.out_terms.data(), m.out_terms.size() * sizeof(PzkTerm));
   section(m.out_exports.data(), m.out_exports.size() * sizeof(PzkExport));
   section(m.meta_json.data(), m.meta_json.size());
+  fclose(f);
+}
+
+// one byte per constraint (.r1cs order): how the row is discharged - 0 checked at run time, 1 alias,
+// 2 table proof, 3 symbolic proof, 4 definitional (only with def_rows_static).  Lets a test evaluate
+// every row independently and confirm that no statically discharged row ever fails.
+void Compiler::write_rowkinds(const std::string& path) {
+  FILE* f = fopen(path.c_str(), "wb");
+  if (!f) throw CompileError("cannot write " + path);
+  wr(f, im->row_kind.data(), im->row_kind.size());
   fclose(f);
 }
 

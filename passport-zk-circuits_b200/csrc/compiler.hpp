@@ -99,10 +99,12 @@ enum { CLS_U = 0, CLS_I = 1, CLS_F = 2, CLS_N = 3 };
 
 struct CompileOptions {
   std::map<std::string, int> input_bits;  // main input name -> declared width (bits)
-  uint32_t seg_ops = 16384;
+  uint32_t seg_ops = 8192;
   uint32_t cells = 16;  // operand-cache cells (8 bytes) per lane in shared memory
   bool verbose = false;
   bool intrinsics = true;
+  bool table_rows_static = true;  // prove rows over table-valued wires by exhaustive evaluation
+  bool symbolic_rows_static = true;  // prove rows by expanding their wires through the defining ops
   bool def_rows_static = false;  // discharge the rows of `x <== e` (they hold by construction) at compile time
 };
 
@@ -121,6 +123,7 @@ class Compiler {
   void write_program(const std::string& path);
   void write_r1cs(const std::string& path);
   void write_sym(const std::string& path);
+  void write_rowkinds(const std::string& path);
   CompileStats stats;
   std::string main_io_json() const;
 

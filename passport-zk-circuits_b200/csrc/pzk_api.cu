@@ -116,12 +116,15 @@ int pzk_compile_ex(const char* main_circom_path, const char* out_prefix, const c
     if (segment_ops) opt.seg_ops = segment_ops;
     opt.def_rows_static = (flags & PZK_COMPILE_STATIC_DEF_ROWS) != 0;
     opt.intrinsics = (flags & PZK_COMPILE_NO_INTRINSICS) == 0;
+    opt.table_rows_static = (flags & PZK_COMPILE_NO_TABLE_PROOFS) == 0;
+    opt.symbolic_rows_static = (flags & PZK_COMPILE_NO_TABLE_PROOFS) == 0;
     pzk::Compiler cc(main_circom_path, opt);
     cc.run();
     std::string p = out_prefix;
     cc.write_program(p + ".pzkp");
     cc.write_r1cs(p + ".r1cs");
     cc.write_sym(p + ".sym");
+    cc.write_rowkinds(p + ".rowkind");
   } catch (std::exception& e) {
     set_err(err, err_len, e.what());
     return PZK_ECOMPILE;

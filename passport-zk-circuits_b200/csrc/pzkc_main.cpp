@@ -18,13 +18,15 @@ int main(int argc, char** argv) {
     else if (!strcmp(argv[i], "--cells") && i + 1 < argc) opt.cells = (uint32_t)atoi(argv[++i]);
     else if (!strcmp(argv[i], "--no-intrinsics")) opt.intrinsics = false;
     else if (!strcmp(argv[i], "--static-def-rows")) opt.def_rows_static = true;
+    else if (!strcmp(argv[i], "--no-table-proofs")) opt.table_rows_static = false;
+    else if (!strcmp(argv[i], "--no-symbolic-proofs")) opt.symbolic_rows_static = false;
     else { fprintf(stderr, "unknown option %s\n", argv[i]); return 2; }
   }
   try {
     pzk::Compiler c(argv[1], opt);
     c.run();
     std::string p = argv[2];
-    c.write_program(p + ".pzkp"); c.write_r1cs(p + ".r1cs"); c.write_sym(p + ".sym");
+    c.write_program(p + ".pzkp"); c.write_r1cs(p + ".r1cs"); c.write_sym(p + ".sym"); c.write_rowkinds(p + ".rowkind");
     auto& s = c.stats;
     printf("signals %llu constraints %llu values %llu op_records %llu segments %u u_slots %u f_slots %u\n"
            "u_ops %llu f_mul %llu f_inv %llu f_other %llu bigdiv %llu modinv %llu lut %llu  (%.2fs)\n",

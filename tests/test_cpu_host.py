@@ -189,28 +189,37 @@ def test_synthetic_passport_is_a_valid_signed_document():
     assert PassportFactory(C3, seed=9, n_sig_keys=2, n_aa_keys=2).make(4).inputs == i
 
 
-def test_definitional_rows_discharged_statically_change_no_verdict(artifacts_dir):
-    """pzk.h PZK_COMPILE_STATIC_DEF_ROWS: `c3_lean` drops the run-time check of every `x <== e` row
-    (x holds value(e) by construction).  Same wires, and for valid and for tampered passports the
-    same status and the same first failing constraint as the program that evaluates every row."""
-    full = oracle_ref.RefProgram(W.artifact("c3"))
+def test_static_row_proofs_change_no_verdict(artifacts_dir):
+    """Three compilations of registerIdentity: `c3_allrows` evaluates every non-alias row at run time
+    (PZK_COMPILE_NO_TABLE_PROOFS), `c3` (the default) discharges table and symbolic rows by compile-time proofs,
+    `c3_lean` also drops the remaining rows of `x <== e` (PZK_COMPILE_STATIC_DEF_ROWS).  Same wires, and for
+    valid and for tampered passports the same status and the same first failing constraint."""
+    full = oracle_ref.RefProgram(W.artifact("c3_allrows"))
+    dflt = oracle_ref.RefProgram(W.artifact("c3"))
     lean = oracle_ref.RefProgram(W.artifact("c3_lean"))
-    assert lean.n_wires == full.n_wires and lean.n_constraints == full.n_constraints
-    sf, sl = full.meta["stats"], lean.meta["stats"]
-    assert sf.get("def_rows", 0) == 0 and sl["def_rows"] > 900000
-    assert sl["static_rows"] == sf["static_rows"]
-    run_f = sf["i64_rows"] + sf["int_rows"] + sf["field_rows"]
-    run_l = sl["i64_rows"] + sl["int_rows"] + sl["field_rows"]
-    assert run_f == run_l + sl["def_rows"]
+    for q in (dflt, lean):
+        assert q.n_wires == full.n_wires and q.n_constraints == full.n_constraints
+    sf, sd, sl = full.meta["stats"], dflt.meta["stats"], lean.meta["stats"]
+
+    def runtime(s_):
+        return s_["i64_rows"] + s_["int_rows"] + s_["field_rows"]
+    assert sf["table_rows"] == 0 and sf["symbolic_rows"] == 0 and sf["def_rows"] == 0
+    assert sd["static_rows"] == sf["static_rows"] == sl["static_rows"]
+    assert sd["table_rows"] > 600000 and sd["symbolic_rows"] > 500000 and sd["def_rows"] == 0
+    assert runtime(sf) == runtime(sd) + sd["table_rows"] + sd["symbolic_rows"]
+    assert runtime(sd) == runtime(sl) + sl["def_rows"] and sl["def_rows"] > 10000
+    assert runtime(sd) < 0.05 * full.n_constraints
     g = json.load(open(os.path.join(ROOT, "tests", "golden", "c3.json")))
-    inp = W.pack_inputs_fast(lean.meta, [golden_inputs(lean.meta, g["cases"][0])])[0]
-    st, fb, wit = lean.witness(inp)
-    assert st == 0 and fb == -1
-    assert hashlib.sha256(wit.tobytes()).hexdigest() == g["cases"][0]["wtns_data_sha256"]
-    d = {x["name"]: x for x in lean.meta["inputs"]}
+    inp = W.pack_inputs_fast(full.meta, [golden_inputs(full.meta, g["cases"][0])])[0]
+    for q in (full, dflt, lean):
+        st, fb, wit = q.witness(inp)
+        assert st == 0 and fb == -1
+        assert hashlib.sha256(wit.tobytes()).hexdigest() == g["cases"][0]["wtns_data_sha256"]
+    d = {x["name"]: x for x in full.meta["inputs"]}
     tampered = []
     for name, k, bit in (("signature", 3, 5), ("pubkey", 0, 1), ("dg1", 100, 0), ("encapsulatedContent", 700, 0),
-                         ("signedAttributes", 300, 0), ("slaveMerkleRoot", 0, 7), ("dg15", 40, 0)):
+                         ("signedAttributes", 300, 0), ("slaveMerkleRoot", 0, 7), ("dg15", 40, 0),
+                         ("signature", 31, 63), ("dg1", 1023, 0), ("encapsulatedContent", 0, 0)):
         row = inp.copy()
         row[d[name]["offset"] + k, 0] ^= np.uint64(1 << bit)
         tampered.append(row)
@@ -220,10 +229,11 @@ def test_definitional_rows_discharged_statically_change_no_verdict(artifacts_dir
     n_fail = 0
     for row in tampered:
         a = full.witness(row, want_witness=False)
-        b = lean.witness(row, want_witness=False)
-        assert a[:2] == b[:2], (a[:2], b[:2])
+        for q in (dflt, lean):
+            b = q.witness(row, want_witness=False)
+            assert a[:2] == b[:2], (a[:2], b[:2])
         n_fail += a[0] != 0
-    assert n_fail >= 6
+    assert n_fail >= 8
 
 
 def test_ecdsa_passport_through_the_compiled_program(artifacts_dir):

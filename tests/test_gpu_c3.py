@@ -175,3 +175,27 @@ def test_c3_lean_program_same_verdicts(c3):
     assert (a.status[[3, 8, 20]] != 0).all() and (np.delete(a.status, [3, 8, 20]) == 0).all()
     assert a.status[20] & W.STATUS_INPUT_RANGE
     lean.close()
+
+
+def test_c3_static_proofs_against_the_full_r1cs_stream_check(c3):
+    """The program checks 4 % of the rows at run time and discharges the rest by compile-time proofs.  Here the
+    full witnesses of valid and tampered passports go through the stand-alone `wtns check` kernel, which
+    evaluates all 2 250 656 rows of the .r1cs: verdict and first failing row must be what the program said."""
+    prog, calc, ref = c3
+    fac = PassportFactory(C3, seed=21, n_sig_keys=2, n_aa_keys=2)
+    B = 10
+    inp = W.pack_inputs_fast(calc.meta, [fac.make(i).inputs for i in range(B)])
+    d = {x["name"]: x for x in calc.meta["inputs"]}
+    inp[1, d["signature"]["offset"] + 9, 0] ^= np.uint64(1 << 40)
+    inp[2, d["pubkey"]["offset"] + 31, 0] ^= np.uint64(1)
+    inp[3, d["dg1"]["offset"] + 500, 0] ^= np.uint64(1)
+    inp[4, d["encapsulatedContent"]["offset"] + 1200, 0] ^= np.uint64(1)
+    inp[5, d["signedAttributes"]["offset"] + 77, 0] ^= np.uint64(1)
+    inp[6, d["dg15"]["offset"] + 300, 0] ^= np.uint64(1)
+    inp[7, d["skIdentity"]["offset"], 0] ^= np.uint64(1 << 17)        # any secret key is a valid witness
+    res = calc.calculateWitnessBatch(inp, export_lanes=range(B))
+    ok, first, _ = W.r1cs_check_batch(W.artifact_r1cs("c3"), res.witnesses)
+    for b in range(B):
+        assert bool(ok[b]) == (res.status[b] == 0), b
+        assert int(first[b]) == int(res.first_bad[b]), (b, int(first[b]), int(res.first_bad[b]))
+    assert [int(s != 0) for s in res.status] == [0, 1, 1, 1, 1, 1, 1, 0, 0, 0]
