@@ -230,23 +230,51 @@ __device__ __forceinline__ bool geq256(const u64* a, const u64* b) {
   if (a[1] != b[1]) return a[1] > b[1];
   return a[0] >= b[0];
 }
-__device__ __noinline__ void fr_inv(u64* r, const u64* a) {
-  if (fr_is_zero(a)) { r[0] = r[1] = r[2] = r[3] = 0; return; }
+// a^-1 mod p for 0 < a < p (plain integers, no Montgomery factor).  One iteration halves u exactly
+// once: when u is odd it is first made >= v by a conditional swap of (u, v) and (x1, x2) and v is
+// subtracted (both odd, so the difference is even).  Every step is a masked select, so the 32 lanes
+// of a warp run one instruction stream and differ only in the trip count (about 1.4 * 254 iterations);
+// the nested `while (even) halve` loops this replaces ran, per warp, the maximum over the lanes of
+// every inner trip count and cost 4-6 times as many issue slots.
+// Invariants: x1 * a == u and x2 * a == v (mod p); v stays odd; u == 0 at the end, v == gcd == 1.
+__device__ __forceinline__ void inv_mod_p_core(u64* out, const u64* a) {
+  const u64 p[4] = {P0, P1, P2, P3};
   u64 u[4] = {a[0], a[1], a[2], a[3]};
   u64 v[4] = {P0, P1, P2, P3};
   u64 x1[4] = {1, 0, 0, 0}, x2[4] = {0, 0, 0, 0};
-  // invariants: x1 * a == u, x2 * a == v (mod p); gcd(a, p) = 1
-  while (!((u[0] == 1 && (u[1] | u[2] | u[3]) == 0) || (v[0] == 1 && (v[1] | v[2] | v[3]) == 0))) {
-    while (!(u[0] & 1)) { shr1_256(u); half_mod_p(x1); }
-    while (!(v[0] & 1)) { shr1_256(v); half_mod_p(x2); }
-    if (geq256(u, v)) { sub256(u, u, v); fr_sub(x1, x1, x2); }
-    else { sub256(v, v, u); fr_sub(x2, x2, x1); }
-  }
-  const u64 r3[4] = {0x5e94d8e1b4bf0040ull, 0x2a489cbe1cfbb6b8ull, 0x893cc664a19fcfedull, 0x0cf8594b7fcc657cull};
-  const bool use1 = (u[0] == 1 && (u[1] | u[2] | u[3]) == 0);
-  u64 t[4];
+  for (int it = 0; it < 1024 && (u[0] | u[1] | u[2] | u[3]) != 0; it++) {
+    const u64 m_odd = 0 - (u[0] & 1);
+    u64 d[4];
+    const u64 m_sw = m_odd & (0 - (u64)sub256(d, u, v));  // borrow: u < v
 #pragma unroll
-  for (int i = 0; i < 4; i++) t[i] = use1 ? x1[i] : x2[i];
+    for (int i = 0; i < 4; i++) {
+      const u64 t = (u[i] ^ v[i]) & m_sw; u[i] ^= t; v[i] ^= t;
+      const u64 s = (x1[i] ^ x2[i]) & m_sw; x1[i] ^= s; x2[i] ^= s;
+    }
+    u64 vv[4], xx[4], pm[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) { vv[i] = v[i] & m_odd; xx[i] = x2[i] & m_odd; }
+    sub256(u, u, vv);
+    const u64 m_b = 0 - (u64)sub256(x1, x1, xx);
+#pragma unroll
+    for (int i = 0; i < 4; i++) pm[i] = p[i] & m_b;
+    add256(x1, x1, pm);
+    shr1_256(u);
+    const u64 m_h = 0 - (x1[0] & 1);
+#pragma unroll
+    for (int i = 0; i < 4; i++) pm[i] = p[i] & m_h;
+    const u32 c = add256(x1, x1, pm);
+    shr1_256(x1);
+    x1[3] |= (u64)c << 63;
+  }
+  out[0] = x2[0]; out[1] = x2[1]; out[2] = x2[2]; out[3] = x2[3];
+}
+__device__ __noinline__ void fr_inv(u64* r, const u64* a) {
+  if (fr_is_zero(a)) { r[0] = r[1] = r[2] = r[3] = 0; return; }
+  // input aR gives (aR)^-1 = a^-1 R^-1; one product with R^3 restores a^-1 R
+  const u64 r3[4] = {0x5e94d8e1b4bf0040ull, 0x2a489cbe1cfbb6b8ull, 0x893cc664a19fcfedull, 0x0cf8594b7fcc657cull};
+  u64 t[4];
+  inv_mod_p_core(t, a);
   fr_mul(r, t, r3);
 }
 

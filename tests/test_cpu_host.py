@@ -378,3 +378,48 @@ int main() {
         got = sum(v << (64 * i) for i, v in enumerate(w[1:]))
         want = pow(a % p, -1, p) if a % p else 0
         assert got == want, (k, hex(a), hex(p), hex(got), hex(want))
+
+
+def test_field_inversion_core_on_the_host(tmp_path):
+    """inv_mod_p_core (csrc/fr_device.cuh: the branch-free binary GCD behind F_INV) compiled for the host
+    with plain-C stand-ins for the PTX carry helpers, against pow(a, -1, p)."""
+    import random
+    src = open(os.path.join(ROOT, "passport-zk-circuits_b200", "csrc", "fr_device.cuh")).read()
+    start = src.index("__device__ __forceinline__ void inv_mod_p_core")
+    body = src[start:src.index("\n}\n", start) + 3]
+    consts = "\n".join(l for l in src.split("\n") if l.startswith("#define P0") or l.startswith("#define P1")
+                       or l.startswith("#define P2") or l.startswith("#define P3"))
+    harness = r'''
+#include <cstdint>
+#include <cstdio>
+typedef uint64_t u64; typedef uint32_t u32; typedef unsigned __int128 u128;
+#define __device__
+#define __forceinline__ inline
+''' + consts + r'''
+static u32 add256(u64* r, const u64* a, const u64* b) { u128 c = 0; for (int i = 0; i < 4; i++) { c += (u128)a[i] + b[i]; r[i] = (u64)c; c >>= 64; } return (u32)c; }
+static u32 sub256(u64* r, const u64* a, const u64* b) { u64 br = 0; for (int i = 0; i < 4; i++) { u128 d = (u128)a[i] - b[i] - br; r[i] = (u64)d; br = (u64)(d >> 64) & 1; } return (u32)br; }
+static void shr1_256(u64* a) { a[0] = (a[0] >> 1) | (a[1] << 63); a[1] = (a[1] >> 1) | (a[2] << 63); a[2] = (a[2] >> 1) | (a[3] << 63); a[3] >>= 1; }
+''' + body + r'''
+int main() {
+  unsigned long long w[4];
+  while (scanf("%llx %llx %llx %llx", &w[0], &w[1], &w[2], &w[3]) == 4) {
+    u64 a[4] = {w[0], w[1], w[2], w[3]}, o[4];
+    inv_mod_p_core(o, a);
+    printf("%llx %llx %llx %llx\n", (unsigned long long)o[0], (unsigned long long)o[1], (unsigned long long)o[2], (unsigned long long)o[3]);
+  }
+  return 0;
+}
+'''
+    cpp = tmp_path / "inv_host.cpp"
+    cpp.write_text(harness)
+    exe = str(tmp_path / "inv_host")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-Wno-unknown-pragmas", "-o", exe, str(cpp)])
+    p = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+    rng = random.Random(3)
+    vals = [1, 2, 3, p - 1, p - 2, (p + 1) // 2, 1 << 253, (1 << 253) - 1, 0xFFFFFFFFFFFFFFFF, 1 << 64]
+    vals += [rng.randrange(1, p) for _ in range(300)] + [rng.randrange(1, 1 << 64) for _ in range(20)]
+    text = "".join(" ".join("%x" % ((a >> (64 * i)) & (2**64 - 1)) for i in range(4)) + "\n" for a in vals)
+    out = subprocess.run([exe], input=text, capture_output=True, text=True, check=True).stdout.split("\n")
+    for a, line in zip(vals, out):
+        got = sum(int(x, 16) << (64 * i) for i, x in enumerate(line.split()))
+        assert got == pow(a, -1, p), hex(a)
