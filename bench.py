@@ -30,6 +30,7 @@ sys.path.insert(0, ROOT)
 METRIC = "witnesses/sec + R1CS constraints checked/sec, registerIdentity SHA256/RSA2048"
 WORKLOAD = "registerIdentity_1_256_3_4_600_248_1_1496_3_256 (SHA-256 + RSA-2048 e=65537), synthetic passports"
 UNIQUE = 256  # distinct signed passports generated on the host; tiled to fill the batch
+NCU_DRAM_BYTES_PER_WAVE_LAUNCH = 1.762766e9 + 1.768963e9   # measured, see roofline.traffic_source
 
 
 def make_inputs(meta, batch, seed):
@@ -264,7 +265,12 @@ def main():
         per_launch_bytes = bytes_per_lane[fam] * lanes_per_launch / max(1, calc.meta["stats"]["segments"])
         achieved = (bytes_per_lane[fam] * B * a.steps) / (ms / 1000.0) / 1e9
         roofline = {"bound": "hbm", "kernel": fam + "_kernel", "achieved": achieved, "peak": hbm_peak,
-                    "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                    "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": NCU_DRAM_BYTES_PER_WAVE_LAUNCH * lanes_per_launch / 151552,
+                    "traffic_source": "ncu --set full, SHA-256 segment 60 of the final program at 151 552 lanes: "
+                                      "dram__bytes_read.sum 1.76 GB + dram__bytes_write.sum 1.77 GB per launch "
+                                      "(profiles/r1_final_ncu_seg60_key_metrics.txt), scaled to this run's lanes per launch; "
+                                      "about 0.11 of the algorithmic bytes - the operand cache and L1 absorb the rest",
+                    "peak_source": peak_src,
                     "algorithmic_bytes_per_witness": bytes_per_lane[fam], "bytes_per_launch": per_launch_bytes,
                     "avg_launch_ms": ms / max(1, launches), "launches": launches,
                     "share_of_step": ms / max(1e-9, prof["run"][0])}

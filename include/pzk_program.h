@@ -30,7 +30,7 @@ extern "C" {
 #endif
 
 #define PZK_MAGIC 0x314b5a50u /* "PZK1" */
-#define PZK_VERSION 8u
+#define PZK_VERSION 9u
 
 /* ---- opcodes ------------------------------------------------------------ */
 enum PzkOpcode {
@@ -56,6 +56,7 @@ enum PzkOpcode {
   PZK_I_LT = 18,  /* signed 64-bit compare -> 0/1                           */
   PZK_I_LE = 19,
   PZK_U_LUTV = 20, /* dst = list64[e + (a | b<<1 | c<<2 | d<<3)]     (ext)  */
+  PZK_U_SHLADD = 21, /* dst = a + (b << imm16), wrapping: x + z * 2^k fused                */
   /* F class */
   PZK_F_CONST = 24, /* dst = fpool[a]                                       */
   PZK_F_ADD = 25,
@@ -110,6 +111,8 @@ enum PzkOpcode {
 #define PZK_FLAG_B_IMM 1u  /* U ops: operand b is the 32-bit immediate in .b */
 #define PZK_FLAG_B_POOL 2u /* F ops: operand b is fpool[.b]                  */
 #define PZK_FLAG_EXT 4u    /* the following 16-byte record is an extension   */
+#define PZK_FLAG_FAST 8u   /* set on U_ADD / U_MUL / U_AND / U_SHR / U_SHLADD (57 % of the ops of the passport circuits): the
+                              evaluator takes them on a two-compare path in front of its opcode dispatch      */
 
 typedef struct PzkOp {
   uint8_t opc;

@@ -309,6 +309,7 @@ uint32_t pzk_ref_witness(const PzkRefProgram* p, const uint8_t* inputs, uint8_t*
         case PZK_NOP: break;
         case PZK_U_CONST: WRU(o->dst, ((uint64_t)o->b << 32) | o->a); break;
         case PZK_U_ADD: WRU(o->dst, UA + UB); break;
+        case PZK_U_SHLADD: WRU(o->dst, UA + (RDU(o->b) << o->imm16)); break;
         case PZK_U_SUB: WRU(o->dst, UA - UB); break;
         case PZK_U_MUL: WRU(o->dst, UA * UB); break;
         case PZK_U_DIV: { uint64_t b = UB; WRU(o->dst, b ? UA / b : 0); break; }

@@ -182,7 +182,7 @@ struct Compiler::Impl {
   std::vector<uint32_t> out_list;
   uint32_t n_u_slots = 0, n_f_slots = 0;
   std::vector<uint8_t> row_kind;  // per constraint: 0 run-time check, 1 alias, 2 table proof, 3 symbolic proof, 4 definitional
-  uint64_t n_static_rows = 0, n_def_rows = 0, n_table_rows = 0, n_symbolic_rows = 0, n_i64_rows = 0, n_int_rows = 0, n_field_rows = 0, eval_bytes = 0, check_bytes = 0, cache_hit_refs = 0, cache_miss_refs = 0;
+  uint64_t n_static_rows = 0, n_def_rows = 0, n_table_rows = 0, n_symbolic_rows = 0, n_fused = 0, n_i64_rows = 0, n_int_rows = 0, n_field_rows = 0, eval_bytes = 0, check_bytes = 0, cache_hit_refs = 0, cache_miss_refs = 0;
   std::vector<uint32_t> seg_quads;
   uint32_t n_pub_out = 0, n_pub_in = 0, n_prv_in = 0;
   std::string meta_json;
@@ -2124,6 +2124,33 @@ void Compiler::Impl::backend() {
       else if (rows[r].by_def && opt.def_rows_static) { row_static[r] = 4; n_def_rows++; }
     }
   }
+  // ---- peephole: x + (z * 2^k) with a single-use product that is not a wire -> one U_SHLADD record
+  // (weighted bit sums: `lc += bit * 2^k`).  Same value in wrapping 64-bit arithmetic, one record less.
+  if (opt.fuse_shladd) {
+    std::vector<uint32_t> uses(nv, 0), def_op(nv, 0xFFFFFFFFu);
+    std::vector<uint8_t> is_sig(nv, 0);
+    for (uint32_t v : sig_val) if (v) is_sig[v] = 1;
+    for (size_t i = 0; i < nops; i++) if (keep[i]) {
+      for_operands(ops[i], [&](uint32_t v) { if (v != PZK_OPERAND_NONE) uses[v]++; });
+      for_defs(ops[i], [&](uint32_t d) { def_op[d] = (uint32_t)i; });
+    }
+    auto shift_of = [&](uint32_t v, uint32_t& src, int& k) -> bool {
+      if (v >= nv || def_op[v] == 0xFFFFFFFFu || is_sig[v] || uses[v] != 1) return false;
+      const OpRec& d = ops[def_op[v]];
+      if (d.opc != PZK_U_MUL || !(d.flags & PZK_FLAG_B_IMM) || d.dst != v) return false;
+      if (d.b == 0 || (d.b & (d.b - 1)) != 0) return false;
+      src = d.a; k = __builtin_ctz(d.b);
+      return true;
+    };
+    for (size_t i = 0; i < nops; i++) {
+      if (!keep[i]) continue;
+      OpRec& o = ops[i];
+      if (o.opc != PZK_U_ADD || (o.flags & PZK_FLAG_B_IMM)) continue;
+      uint32_t src; int k;
+      if (shift_of(o.b, src, k)) { keep[def_op[o.b]] = 0; o.opc = PZK_U_SHLADD; o.b = src; o.imm16 = (uint16_t)k; n_fused++; }
+      else if (shift_of(o.a, src, k)) { keep[def_op[o.a]] = 0; o.opc = PZK_U_SHLADD; o.a = o.b; o.b = src; o.imm16 = (uint16_t)k; n_fused++; }
+    }
+  }
   // ---- segments over kept ops (+ their rows)
   std::vector<uint32_t> def_seg(nv, 0), last_seg(nv, 0), op_seg(nops, 0);
   {
@@ -2444,6 +2471,7 @@ void Compiler::Impl::backend() {
       if (s != cur) { cur = s; segs[s].op_off = out_ops.size(); reset_cache(s); }
       const uint32_t seg_end = seg_last_pos[s];
       PzkOp r; r.opc = o.opc; r.flags = o.flags; r.imm16 = o.imm16; r.dst = 0; r.a = o.a; r.b = o.b;
+      if (o.opc == PZK_U_ADD || o.opc == PZK_U_MUL || o.opc == PZK_U_AND || o.opc == PZK_U_SHR || o.opc == PZK_U_SHLADD) r.flags |= PZK_FLAG_FAST;
       auto cls_bytes = [&](uint32_t v) -> uint64_t { return (v == PZK_OPERAND_NONE) ? 0 : ((v_cls[v] == CLS_U || v_cls[v] == CLS_I) ? 8 : 32); };
       for_operands(o, [&](uint32_t v) { eval_bytes += cls_bytes(v); });
       for_defs(o, [&](uint32_t v) { eval_bytes += cls_bytes(v); });
@@ -2563,7 +2591,7 @@ void Compiler::Impl::build_meta() {
        ",\"f_inv\":" + std::to_string(stats->f_inv) + ",\"f_inv_real\":" + std::to_string(stats->f_inv_real) + ",\"f_other\":" + std::to_string(stats->f_other) +
        ",\"bigdiv\":" + std::to_string(stats->bigdiv) + ",\"modinv\":" + std::to_string(stats->modinv) + ",\"lut\":" + std::to_string(stats->lut) +
        ",\"op_records\":" + std::to_string(out_ops.size()) + ",\"segments\":" + std::to_string(segs.size()) +
-       ",\"static_rows\":" + std::to_string(n_static_rows) + ",\"def_rows\":" + std::to_string(n_def_rows) + ",\"table_rows\":" + std::to_string(n_table_rows) + ",\"symbolic_rows\":" + std::to_string(n_symbolic_rows) + ",\"i64_rows\":" + std::to_string(n_i64_rows) +
+       ",\"static_rows\":" + std::to_string(n_static_rows) + ",\"def_rows\":" + std::to_string(n_def_rows) + ",\"table_rows\":" + std::to_string(n_table_rows) + ",\"symbolic_rows\":" + std::to_string(n_symbolic_rows) + ",\"fused_shladd\":" + std::to_string(n_fused) + ",\"i64_rows\":" + std::to_string(n_i64_rows) +
        ",\"int_rows\":" + std::to_string(n_int_rows) + ",\"field_rows\":" + std::to_string(n_field_rows) +
        ",\"eval_bytes\":" + std::to_string(eval_bytes) + ",\"check_bytes\":" + std::to_string(check_bytes) +
        ",\"cells\":" + std::to_string(opt.cells) + ",\"cache_hit_refs\":" + std::to_string(cache_hit_refs) +

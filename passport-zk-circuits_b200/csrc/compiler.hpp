@@ -105,6 +105,7 @@ struct CompileOptions {
   bool intrinsics = true;
   bool table_rows_static = true;  // prove rows over table-valued wires by exhaustive evaluation
   bool symbolic_rows_static = true;  // prove rows by expanding their wires through the defining ops
+  bool fuse_shladd = true;  // x + z * 2^k with a single-use product -> one U_SHLADD record
   bool def_rows_static = false;  // discharge the rows of `x <== e` (they hold by construction) at compile time
 };
 

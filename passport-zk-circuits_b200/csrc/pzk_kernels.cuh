@@ -409,10 +409,23 @@ __global__ void __launch_bounds__(128, 8) eval_kernel(EvalParams p) {
 #define LDFA(v) ldFo(Fl, L, cells, NT, a, v)
 #define LDFB(v) do { if (flags & PZK_FLAG_B_POOL) ldPool(fpool, b, v); else ldFo(Fl, L, cells, NT, b, v); } while (0)
 #define STFD(v) stFd(Fl, L, cells, NT, dst, v, store_all)
+    // U_ADD / U_MUL / U_AND / U_SHR / U_SHLADD are 57 % of the ops of the passport circuits (weighted bit sums, bit
+    // extraction).  The compiler marks them with PZK_FLAG_FAST; testing the flag instead of the opcode keeps this
+    // exit in front of the six-level compare tree the switch compiles to, and the four results are selected,
+    // not branched on.
+    if (flags & PZK_FLAG_FAST) {
+      const u64 x_ = LDO(a), y_ = UBV;
+      const u64 sh_ = y_ >= 64 ? 0 : x_ >> y_;
+      const u64 r_ = opc == PZK_U_ADD ? x_ + y_ : opc == PZK_U_MUL ? x_ * y_ : opc == PZK_U_AND ? (x_ & y_)
+                   : opc == PZK_U_SHLADD ? x_ + (y_ << imm16) : sh_;
+      STD(dst, r_);
+      continue;
+    }
     switch (opc) {
       case PZK_NOP: break;
       case PZK_U_CONST: STD(dst, ((u64)b << 32) | a); break;
       case PZK_U_ADD: STD(dst, LDO(a) + UBV); break;
+      case PZK_U_SHLADD: STD(dst, LDO(a) + (LDO(b) << imm16)); break;
       case PZK_U_SUB: STD(dst, LDO(a) - UBV); break;
       case PZK_U_MUL: STD(dst, LDO(a) * UBV); break;
       case PZK_U_DIV: { u64 d = UBV; STD(dst, d ? LDO(a) / d : 0); break; }
