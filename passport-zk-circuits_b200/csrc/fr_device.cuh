@@ -230,129 +230,44 @@ __device__ __forceinline__ bool geq256(const u64* a, const u64* b) {
   if (a[1] != b[1]) return a[1] > b[1];
   return a[0] >= b[0];
 }
-// ---- inversion by approximated binary GCD rounds -------------------------------------------------------
-// a^-1 mod p for 0 < a < p (plain integers).  Binary GCD in 17 rounds of 31 steps, after Pornin, "Optimized
-// Binary GCD for Modular Inversion" (2020): the 31 steps of a round run on 64-bit approximations of (a, b) -
-// their top 33 and low 31 bits - and four small cofactors; the round then applies the 2x2 cofactor matrix once
-// to the full-width (a, b), an exact division by 2^31, and to (u, v) with a Montgomery-style division by 2^31
-// modulo p, so that u * y == a and v * y == b (mod p) after every round.  2 * 254 - 1 = 507 < 17 * 31 steps always
-// suffice; then a == 0, b == 1 and v == y^-1.  Every step is a masked select: one instruction stream per warp
-// and a fixed trip count, about 25 k instructions instead of the 70 k of the bit-serial version.
-__device__ __forceinline__ void inv2_lincomb(u64* t, const u64* x, u64 f, const u64* y, u64 g) {
-  // t[0..4] (two's complement, mod 2^320) = x * f + y * g; x, y unsigned 256-bit, f, g signed 64-bit
-  typedef unsigned __int128 u128;
-  u64 c = 0, d = 0;
-  u128 acc = 0;
-#pragma unroll
-  for (int i = 0; i < 4; i++) {
-    const u128 p1 = (u128)x[i] * f + c;
-    const u128 p2 = (u128)y[i] * g + d;
-    c = (u64)(p1 >> 64); d = (u64)(p2 >> 64);
-    acc += (u128)(u64)p1 + (u64)p2;
-    t[i] = (u64)acc; acc >>= 64;
-  }
-  t[4] = (u64)acc + c + d;
-  // (u64)f is f + 2^64 for a negative f: take x * 2^64 back out (same for g)
-  const u64 mf = 0 - (f >> 63), mg = 0 - (g >> 63);
-  u64 borrow = 0;
-#pragma unroll
-  for (int i = 0; i < 4; i++) {
-    const u128 s = (u128)(x[i] & mf) + (y[i] & mg) + borrow;
-    const u128 dd = (u128)t[i + 1] - s;
-    t[i + 1] = (u64)dd;
-    borrow = (u64)(0 - (u64)(dd >> 64)) & 3;   // 0, 1 or 2 limbs borrowed
-  }
-}
-__device__ __forceinline__ void inv2_sar31(u64* r, const u64* t) {  // r[0..3] = low 256 bits of (t >> 31), t 5 limbs
-#pragma unroll
-  for (int i = 0; i < 4; i++) r[i] = (t[i] >> 31) | (t[i + 1] << 33);
-}
-__device__ __forceinline__ void inv_mod_p_core(u64* out, const u64* y) {
-  typedef unsigned __int128 u128;
+// a^-1 mod p for 0 < a < p (plain integers, no Montgomery factor).  One iteration halves u exactly
+// once: when u is odd it is first made >= v by a conditional swap of (u, v) and (x1, x2) and v is
+// subtracted (both odd, so the difference is even).  Every step is a masked select, so the 32 lanes
+// of a warp run one instruction stream and differ only in the trip count (about 1.4 * 254 iterations);
+// the nested `while (even) halve` loops this replaces ran, per warp, the maximum over the lanes of
+// every inner trip count and cost 4-6 times as many issue slots.
+// Invariants: x1 * a == u and x2 * a == v (mod p); v stays odd; u == 0 at the end, v == gcd == 1.
+__device__ __forceinline__ void inv_mod_p_core(u64* out, const u64* a) {
   const u64 p[4] = {P0, P1, P2, P3};
-  const u64 M31 = 0x7fffffffull;
-  const u64 MINV = 0x6fffffffull;  // -p^-1 mod 2^31
-  u64 a[4] = {y[0], y[1], y[2], y[3]}, b[4] = {P0, P1, P2, P3};
-  u64 u[4] = {1, 0, 0, 0}, v[4] = {0, 0, 0, 0};
-  for (int round = 0; round < 17; round++) {
-    // 64-bit approximations: low 31 bits and the 33 bits below the common top bit
-    u64 a_, b_;
-    {
-      const u64 t3 = a[3] | b[3], t2 = a[2] | b[2], t1 = a[1] | b[1];
-      const int j = t3 ? 3 : t2 ? 2 : t1 ? 1 : 0;
-      const u64 top = j == 3 ? t3 : j == 2 ? t2 : j == 1 ? t1 : (a[0] | b[0]);
-      const int n = 64 * j + 64 - (top ? __clzll((long long)top) : 64);
-      if (n <= 64) { a_ = a[0]; b_ = b[0]; }
-      else {
-        const int s = n - 33, idx = s >> 6, off = s & 63;
-        const u64 ah = idx < 3 ? a[idx + 1] : 0, bh = idx < 3 ? b[idx + 1] : 0;
-        const u64 al = a[idx], bl = b[idx];
-        const u64 ta = off ? ((al >> off) | (ah << (64 - off))) : al;
-        const u64 tb = off ? ((bl >> off) | (bh << (64 - off))) : bl;
-        a_ = (a[0] & M31) | ((ta & 0x1ffffffffull) << 31);
-        b_ = (b[0] & M31) | ((tb & 0x1ffffffffull) << 31);
-      }
+  u64 u[4] = {a[0], a[1], a[2], a[3]};
+  u64 v[4] = {P0, P1, P2, P3};
+  u64 x1[4] = {1, 0, 0, 0}, x2[4] = {0, 0, 0, 0};
+  for (int it = 0; it < 1024 && (u[0] | u[1] | u[2] | u[3]) != 0; it++) {
+    const u64 m_odd = 0 - (u[0] & 1);
+    u64 d[4];
+    const u64 m_sw = m_odd & (0 - (u64)sub256(d, u, v));  // borrow: u < v
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const u64 t = (u[i] ^ v[i]) & m_sw; u[i] ^= t; v[i] ^= t;
+      const u64 s = (x1[i] ^ x2[i]) & m_sw; x1[i] ^= s; x2[i] ^= s;
     }
-    u64 f0 = 1, g0 = 0, f1 = 0, g1 = 1;
+    u64 vv[4], xx[4], pm[4];
 #pragma unroll
-    for (int i = 0; i < 31; i++) {
-      const u64 odd = 0 - (a_ & 1);
-      const u64 sw = odd & (0 - (u64)(a_ < b_));
-      u64 t = (a_ ^ b_) & sw; a_ ^= t; b_ ^= t;
-      t = (f0 ^ f1) & sw; f0 ^= t; f1 ^= t;
-      t = (g0 ^ g1) & sw; g0 ^= t; g1 ^= t;
-      a_ -= b_ & odd; f0 -= f1 & odd; g0 -= g1 & odd;
-      a_ >>= 1; f1 <<= 1; g1 <<= 1;
-    }
-    // (a, b) <- |(a f0 + b g0, a f1 + b g1)| / 2^31, the signs move into the cofactors
-    u64 ta[5], tb[5], na[4], nb[4];
-    inv2_lincomb(ta, a, f0, b, g0);
-    inv2_lincomb(tb, a, f1, b, g1);
-    {
-      const u64 sa = 0 - (ta[4] >> 63), sb = 0 - (tb[4] >> 63);
-      inv2_sar31(na, ta); inv2_sar31(nb, tb);
-      // conditional negation of the 256-bit results and of the cofactors
-      u64 ca = sa & 1, cb = sb & 1;
+    for (int i = 0; i < 4; i++) { vv[i] = v[i] & m_odd; xx[i] = x2[i] & m_odd; }
+    sub256(u, u, vv);
+    const u64 m_b = 0 - (u64)sub256(x1, x1, xx);
 #pragma unroll
-      for (int i = 0; i < 4; i++) {
-        const u64 xa = (na[i] ^ sa) + ca; ca = (xa < ca) ? 1 : 0; na[i] = xa;
-        const u64 xb = (nb[i] ^ sb) + cb; cb = (xb < cb) ? 1 : 0; nb[i] = xb;
-      }
-      f0 = (f0 ^ sa) - sa; g0 = (g0 ^ sa) - sa;
-      f1 = (f1 ^ sb) - sb; g1 = (g1 ^ sb) - sb;
-    }
-    // (u, v) <- (u f0 + v g0, u f1 + v g1) / 2^31 mod p
-    u64 tu[5], tv[5];
-    inv2_lincomb(tu, u, f0, v, g0);
-    inv2_lincomb(tv, u, f1, v, g1);
+    for (int i = 0; i < 4; i++) pm[i] = p[i] & m_b;
+    add256(x1, x1, pm);
+    shr1_256(u);
+    const u64 m_h = 0 - (x1[0] & 1);
 #pragma unroll
-    for (int w = 0; w < 2; w++) {
-      u64* t = w ? tv : tu;
-      const u64 k = ((t[0] & M31) * MINV) & M31;
-      // t += k * p  (k < 2^31)
-      u128 acc = 0;
-#pragma unroll
-      for (int i = 0; i < 4; i++) { acc += (u128)p[i] * k + t[i]; t[i] = (u64)acc; acc >>= 64; }
-      t[4] += (u64)acc;
-      u64 r[4];
-      inv2_sar31(r, t);
-      const u64 neg = 0 - (t[4] >> 63);          // t in (-p, 2p): add p when negative
-      u64 c = 0;
-#pragma unroll
-      for (int i = 0; i < 4; i++) { const u128 s = (u128)r[i] + (p[i] & neg) + c; r[i] = (u64)s; c = (u64)(s >> 64); }
-      u64 d[4]; u64 br = 0;                       // subtract p when r >= p
-#pragma unroll
-      for (int i = 0; i < 4; i++) { const u128 s = (u128)r[i] - p[i] - br; d[i] = (u64)s; br = (u64)(s >> 64) & 1; }
-      // after the sar the value may also carry bit 256 set (2p > 2^255 fits 256 bits, so no)
-      const u64 ge = 0 - (u64)(1 - br);
-      u64* dst = w ? v : u;
-#pragma unroll
-      for (int i = 0; i < 4; i++) dst[i] = (d[i] & ge) | (r[i] & ~ge);
-    }
-#pragma unroll
-    for (int i = 0; i < 4; i++) { a[i] = na[i]; b[i] = nb[i]; }
+    for (int i = 0; i < 4; i++) pm[i] = p[i] & m_h;
+    const u32 c = add256(x1, x1, pm);
+    shr1_256(x1);
+    x1[3] |= (u64)c << 63;
   }
-  out[0] = v[0]; out[1] = v[1]; out[2] = v[2]; out[3] = v[3];
+  out[0] = x2[0]; out[1] = x2[1]; out[2] = x2[2]; out[3] = x2[3];
 }
 __device__ __noinline__ void fr_inv(u64* r, const u64* a) {
   if (fr_is_zero(a)) { r[0] = r[1] = r[2] = r[3] = 0; return; }

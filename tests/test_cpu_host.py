@@ -381,13 +381,12 @@ int main() {
 
 
 def test_field_inversion_core_on_the_host(tmp_path):
-    """inv_mod_p_core (csrc/fr_device.cuh: the branch-free, round-based binary GCD behind F_INV) compiled for
-    the host, against pow(a, -1, p)."""
+    """inv_mod_p_core (csrc/fr_device.cuh: the branch-free binary GCD behind F_INV) compiled for the host
+    with plain-C stand-ins for the PTX carry helpers, against pow(a, -1, p)."""
     import random
     src = open(os.path.join(ROOT, "passport-zk-circuits_b200", "csrc", "fr_device.cuh")).read()
-    start = src.index("__device__ __forceinline__ void inv2_lincomb")
-    core = src.index("__device__ __forceinline__ void inv_mod_p_core")
-    body = src[start:src.index("\n}\n", core) + 3]
+    start = src.index("__device__ __forceinline__ void inv_mod_p_core")
+    body = src[start:src.index("\n}\n", start) + 3]
     consts = "\n".join(l for l in src.split("\n") if l.startswith("#define P0") or l.startswith("#define P1")
                        or l.startswith("#define P2") or l.startswith("#define P3"))
     harness = r'''
@@ -396,7 +395,6 @@ def test_field_inversion_core_on_the_host(tmp_path):
 typedef uint64_t u64; typedef uint32_t u32; typedef unsigned __int128 u128;
 #define __device__
 #define __forceinline__ inline
-#define __clzll(x) __builtin_clzll((unsigned long long)(x))
 ''' + consts + r'''
 static u32 add256(u64* r, const u64* a, const u64* b) { u128 c = 0; for (int i = 0; i < 4; i++) { c += (u128)a[i] + b[i]; r[i] = (u64)c; c >>= 64; } return (u32)c; }
 static u32 sub256(u64* r, const u64* a, const u64* b) { u64 br = 0; for (int i = 0; i < 4; i++) { u128 d = (u128)a[i] - b[i] - br; r[i] = (u64)d; br = (u64)(d >> 64) & 1; } return (u32)br; }
@@ -419,8 +417,7 @@ int main() {
     p = 21888242871839275222246405745257275088548364400416034343698204186575808495617
     rng = random.Random(3)
     vals = [1, 2, 3, p - 1, p - 2, (p + 1) // 2, 1 << 253, (1 << 253) - 1, 0xFFFFFFFFFFFFFFFF, 1 << 64]
-    vals += [rng.randrange(1, p) for _ in range(3000)] + [rng.randrange(1, 1 << 64) for _ in range(50)]
-    vals += [rng.randrange(1, 1 << 130) for _ in range(50)] + [p - rng.randrange(1, 1 << 40) for _ in range(50)]
+    vals += [rng.randrange(1, p) for _ in range(300)] + [rng.randrange(1, 1 << 64) for _ in range(20)]
     text = "".join(" ".join("%x" % ((a >> (64 * i)) & (2**64 - 1)) for i in range(4)) + "\n" for a in vals)
     out = subprocess.run([exe], input=text, capture_output=True, text=True, check=True).stdout.split("\n")
     for a, line in zip(vals, out):
