@@ -8,11 +8,17 @@ RegisterIdentityBuilder(1,256,3,4,600,248,1,1496,3,256) (/root/reference/hardhat
   python bench.py [--gpus N --steps K --warmup W] [--batch B]      our arm (CUDA, one rank per GPU)
   python bench.py --impl reference ...                             CPU arm: the oracle evaluator on host cores
 
-`value` = whole-job witnesses/s with inputs resident in HBM (CUDA events, max over ranks);
+`value` = whole-job witnesses/s with inputs resident in HBM (CUDA events, max over ranks), default program
+          `c3`: alias, truth-table and symbolic rows are discharged by compile-time proofs,
+          the remaining rows run on the device; `rows` gives the split;
 `e2e`   = the same metric through the C ABI call with pinned HOST buffers, H2D + D2H inside the
           timed region; `roofline` = dominant kernel, algorithmic bytes / CUDA-event time against
-          the measured HBM peak; `cpu_baseline` = oracle/ssa_ref.c on the host cores (a stand-in
-          "port": the reference's wasm calculator cannot run here, no node/circom - BASELINE.md).
+          the measured HBM peak, `roofline.traffic` = DRAM bytes per launch from the ncu capture;
+`cpu_baseline` / `--impl reference` = oracle/ssa_ref.c on the host cores (a stand-in "port": the reference's
+          wasm calculator cannot run here, no node/circom - BASELINE.md) evaluating `c3_allrows`, the compilation
+          that like the reference evaluates every row at run time;
+`all_rows_dynamic`, `lean_rows` (N=1 only) = the same batch through the `c3_allrows` and `c3_lean` compilations
+          on the GPU, results asserted identical - context for the headline, never the headline.
 The batch shards across ranks with no collective: scaling is weak.
 """
 import argparse
