@@ -186,3 +186,34 @@ def test_statically_discharged_rows_never_fail(artifacts_dir, name):
         seen_fail += bool(bad)
     if name == "smt80":
         assert seen_fail > 0      # arbitrary siblings really do break constraints
+
+
+@pytest.mark.skipif(not has_reference(), reason="/root/reference is not mounted here")
+def test_static_proofs_hold_on_tampered_query_inputs(artifacts_dir):
+    """queryIdentity(80): a valid input and three tampered ones (identity-tree root, a DG1 bit, the secret key).
+    Every row of the .r1cs is evaluated in Python on the produced witness: failing rows must be run-time rows,
+    the first of them the reported first_bad."""
+    import json
+    from passport_zk_circuits_b200 import witness as W
+    prefix = os.path.join(artifacts_dir, "query80")
+    prog = oracle_ref.RefProgram(prefix + ".pzkp")
+    kinds = np.fromfile(prefix + ".rowkind", dtype=np.uint8)
+    r1cs = formats.read_r1cs(prefix + ".r1cs")
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "query80.json")))
+    size = {d["name"]: d["size"] for d in prog.meta["inputs"]}
+    obj = {k: (list(v) if isinstance(v, str) and size[k] > 1 else v) for k, v in g["cases"][0]["inputs"].items()}
+    base = W.pack_inputs_fast(prog.meta, [obj])[0]
+    d = {x["name"]: x for x in prog.meta["inputs"]}
+    rows = [base]
+    for name, k, bit in (("idStateRoot", 0, 0), ("dg1", 200, 0), ("skIdentity", 0, 3)):
+        r = base.copy()
+        r[d[name]["offset"] + k, 0] ^= np.uint64(1 << bit)
+        rows.append(r)
+    n_bad = 0
+    for i, row in enumerate(rows):
+        st, fb, wit = prog.witness(row)
+        bad = _failing_rows(r1cs, u64_to_ints(wit))
+        assert all(kinds[j] == 0 for j in bad), (i, [(j, int(kinds[j])) for j in bad if kinds[j]][:5])
+        assert fb == (bad[0] if bad else -1) and bool(st & 2) == bool(bad)
+        n_bad += bool(bad)
+    assert n_bad >= 2 and not _failing_rows(r1cs, u64_to_ints(prog.witness(base)[2]))
