@@ -58,6 +58,12 @@ def reference_circuits():
                     "timestampLowerbound, timestampUpperbound, identityCounterLowerbound, identityCounterUpperbound, "
                     "birthDateLowerbound, birthDateUpperbound, expirationDateLowerbound, expirationDateUpperbound, "
                     "citizenshipMask] } = QueryIdentity(80);\n", {"dg1": 1}),
+        # one P-256 point doubling of the ECDSA verifier (lib/circuits/ec/curve.circom:281-313): mod_inv, long_div,
+        # long_div2 / short_div with their data-dependent returns, PointOnTangent / PointOnCurve constraints
+        "p256dbl": (f'pragma circom 2.1.6;\ninclude "{lib}/ec/curve.circom";\n'
+                    "component main = EllipticCurveDouble(64, 4, [18446744073709551612, 4294967295, 0, "
+                    "18446744069414584321], [4309448131093880907, 7285987128567378166, 12964664127075681980, "
+                    "6540974713487397863], [18446744073709551615, 4294967295, 0, 18446744069414584321]);\n", {"in": 64}),
         # config 3: the north-star circuit (hardhat.config.ts:29)
         "c3": (C3.main_source(REFERENCE + "/circuits/identityManagement/registerIdentityBuilder.circom"),
                W.REGISTER_IDENTITY_BITS),

@@ -217,3 +217,27 @@ def test_static_proofs_hold_on_tampered_query_inputs(artifacts_dir):
         assert fb == (bad[0] if bad else -1) and bool(st & 2) == bool(bad)
         n_bad += bool(bad)
     assert n_bad >= 2 and not _failing_rows(r1cs, u64_to_ints(prog.witness(base)[2]))
+
+
+@pytest.mark.skipif(not has_reference(), reason="/root/reference is not mounted here")
+def test_reference_p256_doubling(artifacts_dir):
+    """EllipticCurveDouble over P-256 (curve.circom:281-313), the building block of the ECDSA variant: the
+    compiled program - MODINV and BIGDIV intrinsics, predicated returns of short_div_norm / long_sub_mod - equals
+    the Python interpreter of the reference's sources on all 10 065 signals, for points on the curve (all
+    constraints hold, result = 2P) and for an arbitrary input (same signals, constraints fail in both)."""
+    from passport_zk_circuits_b200.passports import P256_G, _ec_add, _ec_mul, chunks_le
+    prefix = os.path.join(artifacts_dir, "p256dbl")
+    main = os.path.join(artifacts_dir, "_mains", "p256dbl.circom")
+    prog = oracle_ref.RefProgram(prefix + ".pzkp")
+    assert prog.meta["stats"]["modinv"] == 1 and prog.meta["stats"]["bigdiv"] >= 1
+    pts = [_ec_mul(0xC0FFEE, P256_G)]
+    rows = [ints_to_u64(chunks_le(x, 64, 4) + chunks_le(y, 64, 4)) for x, y in pts]
+    compare(prefix, main, np.stack(rows))
+    for (x, y), row in zip(pts, rows):
+        st, fb, wit = prog.witness(row)
+        w = u64_to_ints(wit)
+        x2, y2 = _ec_add((x, y), (x, y))
+        assert w[1:9] == chunks_le(x2, 64, 4) + chunks_le(y2, 64, 4)
+    off = ints_to_u64(chunks_le(pts[0][0], 64, 4) + chunks_le(pts[0][1] ^ 5, 64, 4))
+    compare(prefix, main, np.stack([off]), expect_ok=False)
+    assert prog.witness(off)[0] & 2

@@ -108,7 +108,7 @@ def test_modinv_intrinsic():
     assert rem[0] == 0 and rem[1] == 0 and (rem[2:] == 1).all()
 
 
-@pytest.mark.parametrize("name,B", [("poseidon2", 200), ("sha256_1", 130), ("babyjub", 66)])
+@pytest.mark.parametrize("name,B", [("poseidon2", 200), ("sha256_1", 130), ("babyjub", 66), ("p256dbl", 40)])
 def test_reference_small(name, B):
     prog = oracle_ref.RefProgram(W.artifact(name))
     inp = random_inputs(prog.meta, B, 33, field_bits=248)
