@@ -423,3 +423,75 @@ int main() {
     for a, line in zip(vals, out):
         got = sum(int(x, 16) << (64 * i) for i, x in enumerate(line.split()))
         assert got == pow(a, -1, p), hex(a)
+
+
+def _der(tag, body):
+    n = len(body)
+    ln = bytes([n]) if n < 128 else bytes([0x80 | ((n.bit_length() + 7) // 8)]) + n.to_bytes((n.bit_length() + 7) // 8, "big")
+    return bytes([tag]) + ln + body
+
+
+def _der_int(v):
+    return _der(2, v.to_bytes(v.bit_length() // 8 + 1, "big"))
+
+
+def _synthetic_passport_json(seed=77):
+    """A passport JSON as the reference's test/inputs/passport/*.json hold it (dg1, dg15, sod): the SOD is a
+    real CMS SignedData (cryptography's PKCS#7 builder, RSA-2048 PKCS#1 v1.5 + SHA-256, self-signed document
+    signer certificate) over a DER LDSSecurityObject with the SHA-256 hashes of DG1, DG2 and DG15."""
+    import base64
+    import datetime
+    from cryptography import x509
+    from cryptography.hazmat.primitives import hashes, serialization
+    from cryptography.hazmat.primitives.asymmetric import rsa
+    from cryptography.hazmat.primitives.serialization import pkcs7
+    from cryptography.x509.oid import NameOID
+    src = PassportFactory(C3, seed=seed, n_sig_keys=1, n_aa_keys=1).make(0)
+    dg1, dg15 = src.dg1, src.dg15
+    sha256_alg = _der(0x30, bytes.fromhex("0609608648016503040201") + b"\x05\x00")
+    dgs = b"".join(_der(0x30, _der_int(num) + _der(4, hashlib.sha256(d).digest()))
+                   for num, d in ((1, dg1), (2, b"dg2 image"), (15, dg15)))
+    lds = _der(0x30, _der_int(0) + sha256_alg + _der(0x30, dgs))
+    key = rsa.generate_private_key(public_exponent=65537, key_size=2048)
+    who = x509.Name([x509.NameAttribute(NameOID.COUNTRY_NAME, "UA"), x509.NameAttribute(NameOID.COMMON_NAME, "Document Signer")])
+    cert = (x509.CertificateBuilder().subject_name(who).issuer_name(who).public_key(key.public_key())
+            .serial_number(1234567).not_valid_before(datetime.datetime(2024, 1, 1))
+            .not_valid_after(datetime.datetime(2034, 1, 1)).sign(key, hashes.SHA256()))
+    sod = pkcs7.PKCS7SignatureBuilder().set_data(lds).add_signer(cert, key, hashes.SHA256()).sign(
+        serialization.Encoding.DER, [pkcs7.PKCS7Options.Binary, pkcs7.PKCS7Options.NoCapabilities])
+    passport = {"dg1": dg1.hex(), "dg15": base64.b64encode(dg15).decode(), "sod": base64.b64encode(sod).decode()}
+    return passport, key.public_key().public_numbers().n, lds, dg1, dg15
+
+
+def test_process_passport_front_end_on_a_real_cms_sod(tmp_path):
+    """processPassport (test/process_passport.js:674-816) ported: SOD -> encapsulated content, signed
+    attributes, signature, signer key, hash types, the three shifts, AA key position -> the 10 circuit
+    parameters and the input object.  The circuit compiled for exactly those parameters accepts the result
+    (every constraint holds) and rejects it after one signature bit is flipped."""
+    from passport_zk_circuits_b200 import process_passport as PP
+    passport, modulus, lds, dg1, dg15 = _synthetic_passport_json()
+    params, inputs, name = PP.process_passport(passport)
+    assert (params.sig_type, params.dg_hash, params.doc_type, params.aa_algo, params.aa_shift) == (1, 256, 3, 1, 256)
+    assert params.ec_blocks == -(-(len(lds) + 8) // 64) and params.dg15_blocks == 3
+    assert lds[params.dg1_shift // 8:params.dg1_shift // 8 + 32] == hashlib.sha256(dg1).digest()
+    assert lds[params.dg15_shift // 8:params.dg15_shift // 8 + 32] == hashlib.sha256(dg15).digest()
+    assert lds[params.dg15_shift // 8 - 3:params.dg15_shift // 8] == bytes([0x0F, 0x04, 0x20])
+    assert sum(int(c) << (64 * i) for i, c in enumerate(inputs["pubkey"])) == modulus
+    assert name == params.name
+    sa_bits = "".join(inputs["signedAttributes"])
+    sa = int(sa_bits, 2).to_bytes(len(sa_bits) // 8, "big")
+    assert sa[0] == 0x31 and sa[params.ec_shift // 8:params.ec_shift // 8 + 32] == hashlib.sha256(lds).digest()
+    with pytest.raises(PP.Asn1Error):
+        PP.decoded(passport["sod"][:200])
+    if not os.path.isdir("/root/reference"):
+        pytest.skip("/root/reference is not mounted here: the circuit for these parameters cannot be compiled")
+    main = tmp_path / "main.circom"
+    main.write_text(params.main_source("/root/reference/circuits/identityManagement/registerIdentityBuilder.circom"))
+    prog = oracle_ref.RefProgram(W.compile_circuit(str(main), str(tmp_path / "prog"), W.REGISTER_IDENTITY_BITS))
+    inp = W.pack_inputs_fast(prog.meta, [inputs])[0]
+    st, fb, _ = prog.witness(inp, want_witness=False)
+    assert (st, fb) == (0, -1)
+    d = {x["name"]: x for x in prog.meta["inputs"]}
+    inp[d["signature"]["offset"], 0] ^= np.uint64(1)
+    st, fb, _ = prog.witness(inp, want_witness=False)
+    assert st == W.STATUS_CONSTRAINT and fb >= 0
