@@ -27,6 +27,10 @@ def _wrapper(name, body):
 # SIGNATURE_TYPE 3 (RSA-2048 PKCS#1 v1.5 + SHA-1, SHA-1 data groups), 10 (RSA-PSS e=3, SHA-256),
 # 13 (RSA-PSS SHA-384 with 1024-bit hash blocks and a different EC shift / block counts),
 # 20 (ECDSA over NIST P-256 + SHA-256: 5.5 M constraints, long_div2 / mod_inv hint functions)
+# the parameter set process_passport.py extracts from a CMS SignedData SOD as cryptography's PKCS#7 builder lays it
+# out (RSA-2048 + SHA-256 signer, LDS security object with DG1 / DG2 / DG15): the front-end test circuit
+CMS_PARAMS = CircuitParams(1, 256, 3, 3, 600, 240, 1, 864, 3, 256)
+
 C4_VARIANTS = {
     "c4_sig3": CircuitParams(3, 160, 3, 4, 600, 248, 1, 1496, 3, 256),
     "c4_sig10": CircuitParams(10, 256, 3, 4, 600, 248, 1, 1496, 3, 256),
@@ -71,6 +75,8 @@ def reference_circuits():
         # PZK_COMPILE_STATIC_DEF_ROWS); same wires, same verdicts, 353 k instead of 1.29 M run-time rows
         "c3_lean": (C3.main_source(REFERENCE + "/circuits/identityManagement/registerIdentityBuilder.circom"),
                     W.REGISTER_IDENTITY_BITS),
+        "c3_cms": (CMS_PARAMS.main_source(REFERENCE + "/circuits/identityManagement/registerIdentityBuilder.circom"),
+                   W.REGISTER_IDENTITY_BITS),
         # config 3 with alias proofs only (PZK_COMPILE_NO_TABLE_PROOFS): every other row runs on the device
         "c3_allrows": (C3.main_source(REFERENCE + "/circuits/identityManagement/registerIdentityBuilder.circom"),
                        W.REGISTER_IDENTITY_BITS),
@@ -88,7 +94,7 @@ OWN_CIRCUITS = {"t_mix": ("mix.circom", {"u": 16, "bits": 1}),
 COMPILE_OPTS = {"c3_lean": {"static_def_rows": True},
                 "c3_allrows": {"table_proofs": False, "segment_ops": 16384}}
 
-BIG = {"c3", "c3_lean", "c3_allrows", "c4_sig3", "c4_sig10", "c4_sig13", "c4_sig20"}  # ship only the xz-packed program for these
+BIG = {"c3", "c3_lean", "c3_allrows", "c3_cms", "c4_sig3", "c4_sig10", "c4_sig13", "c4_sig20"}  # ship only the xz-packed program for these
 
 
 def _stale(out, deps):

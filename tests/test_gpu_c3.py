@@ -199,3 +199,38 @@ def test_c3_static_proofs_against_the_full_r1cs_stream_check(c3):
         assert bool(ok[b]) == (res.status[b] == 0), b
         assert int(first[b]) == int(res.first_bad[b]), (b, int(first[b]), int(res.first_bad[b]))
     assert [int(s != 0) for s in res.status] == [0, 1, 1, 1, 1, 1, 1, 0, 0, 0]
+
+
+def test_real_passport_front_end_to_device():
+    """process_passport.py (port of the reference's processPassport) on CMS SignedData SODs built here with
+    `cryptography`: extracted parameters name the prebuilt program `c3_cms`, extracted inputs go through the
+    device; valid documents pass every constraint, a document whose DG1 was altered after signing fails, and
+    the device agrees with the oracle lane by lane."""
+    from passport_zk_circuits_b200 import process_passport as PP
+    from passport_zk_circuits_b200.artifacts import CMS_PARAMS
+    from test_cpu_host import _synthetic_passport_json
+    objs = []
+    for seed in (1, 2, 3, 4):
+        passport = _synthetic_passport_json(seed)[0]
+        if seed == 3:
+            raw = bytearray(bytes.fromhex(passport["dg1"]))
+            raw[40] ^= 1
+            # the SOD still holds the hash of the original DG1: find the shift with the original, feed the altered one
+            params, inputs, _ = PP.process_passport(passport)
+            from passport_zk_circuits_b200.passports import bytes_to_bits, sha_pad
+            inputs["dg1"] = [str(b) for b in bytes_to_bits(sha_pad(bytes(raw), 512))]
+        else:
+            params, inputs, _ = PP.process_passport(passport)
+        assert params == CMS_PARAMS
+        objs.append(inputs)
+    prog = W.artifact("c3_cms")
+    calc = W.WitnessCalculator(prog, device=0)
+    inp = W.pack_inputs_fast(calc.meta, objs)
+    out = calc.calculateWitnessBatch(inp)
+    ref = oracle_ref.RefProgram(prog)
+    for b in range(len(objs)):
+        st, fb, wit = ref.witness(inp[b], want_witness=True)
+        assert int(out.status[b]) == st and int(out.first_bad[b]) == fb
+        assert np.array_equal(out.public[b], wit[1:1 + calc.n_public])
+    assert [int(s != 0) for s in out.status] == [0, 0, 1, 0]
+    calc.close()
