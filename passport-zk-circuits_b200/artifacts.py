@@ -142,3 +142,23 @@ def build_all(verbose=True):
                 # too large to ship unpacked; regenerate with compile_circuit when needed here
                 if os.path.exists(prefix + ext):
                     os.replace(prefix + ext, prefix + ext + ".local")
+
+
+def program_for(params: CircuitParams, compile_if_missing: bool = True) -> str:
+    """Circuit parameters (what process_passport.py extracts from a document) -> path of the compiled program:
+    a prebuilt artifact when one was built for exactly these parameters, else a program compiled on first use
+    and cached in artifacts/ under the reference's circuit name (needs the reference's circom sources)."""
+    known = {"c3": C3, "c3_cms": CMS_PARAMS, **C4_VARIANTS}
+    for name, prm in known.items():
+        if prm == params:
+            return W.artifact(name)
+    prefix = os.path.join(W.ARTIFACT_DIR, params.name)
+    if os.path.exists(prefix + ".pzkp"):
+        return prefix + ".pzkp"
+    if not compile_if_missing or not os.path.isdir(REFERENCE):
+        raise W.PzkError(f"no compiled program for {params.name} and the reference's circom sources are not available")
+    os.makedirs(os.path.join(W.ARTIFACT_DIR, "_mains"), exist_ok=True)
+    main = os.path.join(W.ARTIFACT_DIR, "_mains", params.name + ".circom")
+    with open(main, "w") as f:
+        f.write(params.main_source(REFERENCE + "/circuits/identityManagement/registerIdentityBuilder.circom"))
+    return W.compile_circuit(main, prefix, W.REGISTER_IDENTITY_BITS)

@@ -463,6 +463,16 @@ def _synthetic_passport_json(seed=77):
     return passport, key.public_key().public_numbers().n, lds, dg1, dg15
 
 
+def test_program_lookup_by_circuit_parameters(artifacts_dir):
+    from passport_zk_circuits_b200 import artifacts as A
+    from passport_zk_circuits_b200.passports import CircuitParams
+    assert A.program_for(C3) == W.artifact("c3")
+    assert A.program_for(A.CMS_PARAMS) == W.artifact("c3_cms")
+    assert A.program_for(CircuitParams(13, 384, 3, 2, 320, 248, 1, 1496, 2, 256)) == W.artifact("c4_sig13")
+    with pytest.raises(W.PzkError):
+        A.program_for(CircuitParams(1, 256, 3, 4, 608, 248, 1, 1496, 3, 256), compile_if_missing=False)
+
+
 def test_process_passport_front_end_on_a_real_cms_sod(tmp_path):
     """processPassport (test/process_passport.js:674-816) ported: SOD -> encapsulated content, signed
     attributes, signature, signer key, hash types, the three shifts, AA key position -> the 10 circuit
