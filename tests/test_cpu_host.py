@@ -493,6 +493,12 @@ def test_process_passport_front_end_on_a_real_cms_sod(tmp_path):
     assert sa[0] == 0x31 and sa[params.ec_shift // 8:params.ec_shift // 8 + 32] == hashlib.sha256(lds).digest()
     with pytest.raises(PP.Asn1Error):
         PP.decoded(passport["sod"][:200])
+    # the EF.SOD file wraps the CMS object in [APPLICATION 23] (tag 0x77): same extraction
+    import base64
+    cms = base64.b64decode(passport["sod"])
+    wrapped = dict(passport, sod=_der(0x77, cms).hex())
+    assert PP.process_passport(wrapped)[:2] == (params, inputs)
+    assert PP.decoded(wrapped["sod"]).name == "Application_23"
     if not os.path.isdir("/root/reference"):
         pytest.skip("/root/reference is not mounted here: the circuit for these parameters cannot be compiled")
     main = tmp_path / "main.circom"
