@@ -70,6 +70,14 @@ int pzk_compile(const char* main_circom_path, const char* out_prefix, const char
  * define them (`z <== x + 2^k * y`, `z <== x * y`).  <prefix>.rowkind records the kind per constraint.
  * This flag keeps both kinds as run-time checks instead.                                              */
 #define PZK_COMPILE_NO_TABLE_PROOFS 4u
+/* Bit-field views and packed truth tables (pzk_program.h): signals that are bit fields of a word the program
+ * computes anyway (Num2Bits / GetLastNBits outputs, running sums, `bit * 2^i`) get no op of their own, one-bit
+ * truth tables over rotated words (the XOR3 / Ch / Maj arrays of SHA) are packed 32 or 64 to a record, and rows
+ * that are identities over the bits of a word are discharged at compile time (kind 5 in <prefix>.rowkind; a row
+ * that reduces to "the high bits of this word are zero" stays a run-time range check).  Same wires, same
+ * verdicts; these flags switch the rewrite off (validation; PZK_COMPILE_NO_TABLE_PROOFS implies NO_VIEWS). */
+#define PZK_COMPILE_NO_VIEWS 8u
+#define PZK_COMPILE_NO_VECTORIZE 16u
 int pzk_compile_ex(const char* main_circom_path, const char* out_prefix, const char* const* bits_names,
                    const int* bits_widths, int n_bits, uint32_t segment_ops, uint32_t flags, char* err,
                    size_t err_len);

@@ -30,7 +30,7 @@ extern "C" {
 #endif
 
 #define PZK_MAGIC 0x314b5a50u /* "PZK1" */
-#define PZK_VERSION 9u
+#define PZK_VERSION 10u
 
 /* ---- opcodes ------------------------------------------------------------ */
 enum PzkOpcode {
@@ -52,11 +52,20 @@ enum PzkOpcode {
   PZK_U_EQ = 14,
   PZK_U_NE = 15,
   PZK_U_SEL = 16, /* dst = a ? b : c        (ext word holds c)              */
-  PZK_U_LUT = 17, /* dst = (imm16 >> (a | b<<1 | c<<2 | d<<3)) & 1  (ext)  */
+  PZK_U_LUT = 17, /* dst = (imm16 >> (a | b<<1 | c<<2 | d<<3)) & 1  (ext); operand j contributes bit
+                     (ext.f >> 8j) & 255 of its word (0 for plain one-bit values)                     */
   PZK_I_LT = 18,  /* signed 64-bit compare -> 0/1                           */
   PZK_I_LE = 19,
   PZK_U_LUTV = 20, /* dst = list64[e + (a | b<<1 | c<<2 | d<<3)]     (ext)  */
   PZK_U_SHLADD = 21, /* dst = a + (b << imm16), wrapping: x + z * 2^k fused                */
+  PZK_U_EXTRACT = 22, /* dst(U) = ((a >> s) & (2^n - 1)) << k with s = imm16 & 255, k = imm16 >> 8, n = b;
+                         a is a U word, or (PZK_FLAG_NBASE) a plain 256-bit value in the F plane: materialises a
+                         bit-field view of a word (see "views" below)                                          */
+  PZK_V_LUT = 23,     /* packed truth table: 32 or 64 one-bit signals per record.  Bit l of dst =
+                         imm16 >> (x0_l | x1_l << 1 | x2_l << 2 | x3_l << 3) & 1 with x_j = rotr_w(operand_j, rot_j),
+                         w = 32 (operands masked to 32 bits first) or 64 (PZK_FLAG_W64); result masked with the
+                         lane mask.  Extension record: {c, d, rot bytes, lane mask low}; with PZK_FLAG_W64 a second
+                         extension record holds {lane mask high, 0, 0, 0}.  Unused operands are PZK_OPERAND_NONE.   */
   /* F class */
   PZK_F_CONST = 24, /* dst = fpool[a]                                       */
   PZK_F_ADD = 25,
@@ -70,6 +79,8 @@ enum PzkOpcode {
   PZK_F_NE = 33,
   PZK_F_CSEL = 34,   /* dst = fpool[b + a(U)]                                 */
   PZK_F_FROM_I = 35, /* dst = Montgomery(a) for a signed 64-bit a             */
+  PZK_CHECK_RANGE = 36, /* constraint row reduced to a range check by the bit-view prover: row dst (.r1cs index)
+                           holds iff (a >> imm16) == 0; a is a U word or (PZK_FLAG_NBASE) a plain 256-bit value   */
   /* N class (plain 256-bit integers held in F slots) */
   PZK_N_FROM_F = 40, /* dst(N) = canonical(a)                                */
   PZK_F_FROM_N = 41, /* dst(F) = Montgomery(a mod p)                         */
@@ -86,6 +97,7 @@ enum PzkOpcode {
   PZK_N_SLE = 52,
   PZK_N_SHL = 53, /* dst(N) = ((a << b(U)) & (2^254-1)) mod p               */
   PZK_N_FITS = 54, /* dst(U) = (a < 2^64)                                   */
+  PZK_N_EXTRACT = 55, /* dst(N) = ((a >> s) & (2^n - 1)) << k, fields as PZK_U_EXTRACT */
   /* constraint rows, fused into the op stream right after the op that defines their last wire.
    * header: imm16 = na, a = nb | nc << 16, b = number of 16-byte term records that follow,
    * dst = constraint index (.r1cs order).  Terms (A then B then C) are packed two per record:
@@ -113,6 +125,8 @@ enum PzkOpcode {
 #define PZK_FLAG_EXT 4u    /* the following 16-byte record is an extension   */
 #define PZK_FLAG_FAST 8u   /* set on U_ADD / U_MUL / U_AND / U_SHR / U_SHLADD (57 % of the ops of the passport circuits): the
                               evaluator takes them on a two-compare path in front of its opcode dispatch      */
+#define PZK_FLAG_NBASE 16u /* U_EXTRACT / N_EXTRACT / CHECK_RANGE: operand a is a plain 256-bit value (F plane) */
+#define PZK_FLAG_W64 32u   /* V_LUT: 64 lanes, a second extension record follows                              */
 
 typedef struct PzkOp {
   uint8_t opc;
@@ -188,11 +202,25 @@ typedef struct PzkSegment {
   uint64_t exp_off, n_exp;  /* export entries defined in this segment       */
 } PzkSegment;
 
-/* witness export entry: wire <- slot */
+/* witness export entry: wire <- slot, or wire <- a view of one or more words.
+ *
+ * Views.  Most signals of the bit-sliced circuits (SHA, Num2Bits, running sums) are bit fields of a
+ * word the program computes anyway: out[i] = (in >> i) & 1, sum[i] = in & (2^(i+1) - 1), (1 << i) * bit, the
+ * 32 results of one packed PZK_V_LUT record ...  Such a signal has no op of its own; its export entry says
+ * how to read it:
+ *   class 3 (PZK_REF_VIEW)  : value = ((W >> s) & (2^n - 1)) << k, W = the U word in slot PZK_REF_SLOT(ref),
+ *                             or with PZK_REF_VIEW_N a plain 256-bit value in the F plane; aux = s | n << 8 | k << 16
+ *   ref == PZK_REF_TABVIEW  : value = table[idx], a truth-table function of up to 4 bits of words;
+ *                             aux = offset into the list pool: {n, (ref_j, pos_j) x n, 2^n x int64 (lo, hi)};
+ *                             negative entries are field negatives.                                           */
 typedef struct PzkExport {
   uint32_t wire;
   uint32_t ref; /* class bits + slot; PZK_REF_ZERO / PZK_REF_ONE constants */
+  uint32_t aux;
+  uint32_t pad;
 } PzkExport;
+#define PZK_REF_VIEW_N 0x20000000u
+#define PZK_REF_TABVIEW 0xFFFFFFFCu
 
 typedef struct PzkInput {
   uint32_t wire;   /* witness index of this main input element             */

@@ -327,13 +327,56 @@ uint32_t pzk_ref_witness(const PzkRefProgram* p, const uint8_t* inputs, uint8_t*
         case PZK_I_LE: WRU(o->dst, (int64_t)UA <= (int64_t)UB); break;
         case PZK_U_SEL: WRU(o->dst, UA ? RDU(o->b) : RDU(x->c)); break;
         case PZK_U_LUT: case PZK_U_LUTV: {
+          /* operand j contributes bit (ext.f >> 8j) & 255 of its word */
           unsigned idx = 0;
-          if (o->a != PZK_OPERAND_NONE) idx |= (unsigned)(RDU(o->a) & 1);
-          if (o->b != PZK_OPERAND_NONE) idx |= (unsigned)(RDU(o->b) & 1) << 1;
-          if (x->c != PZK_OPERAND_NONE) idx |= (unsigned)(RDU(x->c) & 1) << 2;
-          if (x->d != PZK_OPERAND_NONE) idx |= (unsigned)(RDU(x->d) & 1) << 3;
+          if (o->a != PZK_OPERAND_NONE) idx |= (unsigned)((RDU(o->a) >> (x->f & 255)) & 1);
+          if (o->b != PZK_OPERAND_NONE) idx |= (unsigned)((RDU(o->b) >> ((x->f >> 8) & 255)) & 1) << 1;
+          if (x->c != PZK_OPERAND_NONE) idx |= (unsigned)((RDU(x->c) >> ((x->f >> 16) & 255)) & 1) << 2;
+          if (x->d != PZK_OPERAND_NONE) idx |= (unsigned)((RDU(x->d) >> ((x->f >> 24) & 255)) & 1) << 3;
           if (o->opc == PZK_U_LUT) WRU(o->dst, (o->imm16 >> idx) & 1);
           else WRU(o->dst, (uint64_t)p->list[x->e + 2 * idx] | ((uint64_t)p->list[x->e + 2 * idx + 1] << 32));
+          break;
+        }
+        case PZK_V_LUT: {
+          /* packed truth table, one lane at a time: bit l of operand j = bit (l + rot_j) mod w of its word */
+          unsigned w = (o->flags & PZK_FLAG_W64) ? 64 : 32;
+          uint64_t lanes = x->f;
+          if (w == 64) { lanes |= (uint64_t)((const PzkOpExt*)(o + 2))->c << 32; pc++; }
+          uint32_t refs[4] = {o->a, o->b, x->c, x->d};
+          uint64_t words[4] = {0, 0, 0, 0};
+          for (int j = 0; j < 4; j++) if (refs[j] != PZK_OPERAND_NONE) words[j] = RDU(refs[j]);
+          uint64_t r = 0;
+          for (unsigned l = 0; l < w; l++) {
+            if (!((lanes >> l) & 1)) continue;
+            unsigned idx = 0;
+            for (int j = 0; j < 4; j++) {
+              if (refs[j] == PZK_OPERAND_NONE) continue;
+              unsigned rot = (x->e >> (8 * j)) & 255;
+              idx |= (unsigned)((words[j] >> ((l + rot) % w)) & 1) << j;
+            }
+            r |= (uint64_t)((o->imm16 >> idx) & 1) << l;
+          }
+          WRU(o->dst, r);
+          break;
+        }
+        case PZK_U_EXTRACT: case PZK_N_EXTRACT: {
+          /* ((a >> s) & (2^n - 1)) << k on 256 bits */
+          unsigned s_ = o->imm16 & 255, k_ = o->imm16 >> 8, n_ = o->b;
+          uint64_t v[4] = {0, 0, 0, 0}, m[4] = {0, 0, 0, 0}, one[4] = {1, 0, 0, 0};
+          if (o->flags & PZK_FLAG_NBASE) memcpy(v, RDF(o->a), 32); else v[0] = RDU(o->a);
+          shr4(v, v, s_);
+          if (n_ < 256) { shl4(m, one, n_); sub4(m, m, one); for (int i = 0; i < 4; i++) v[i] &= m[i]; }
+          shl4(v, v, k_);
+          if (o->opc == PZK_U_EXTRACT) WRU(o->dst, v[0]); else WRF(o->dst, v);
+          break;
+        }
+        case PZK_CHECK_RANGE: {
+          if (check_rows) {
+            uint64_t v[4] = {0, 0, 0, 0};
+            if (o->flags & PZK_FLAG_NBASE) memcpy(v, RDF(o->a), 32); else v[0] = RDU(o->a);
+            shr4(v, v, o->imm16);
+            if (!is_zero4(v)) { status |= PZK_LANE_CONSTRAINT; if (bad < 0 || (int64_t)o->dst < bad) bad = o->dst; }
+          }
           break;
         }
         case PZK_F_CONST: WRF(o->dst, p->fpool + 4 * (uint64_t)o->a); break;
@@ -493,7 +536,24 @@ uint32_t pzk_ref_witness(const PzkRefProgram* p, const uint8_t* inputs, uint8_t*
         if (ex->ref == PZK_REF_ZERO) continue;
         uint32_t cls = PZK_REF_CLS(ex->ref), slot = PZK_REF_SLOT(ex->ref);
         uint64_t w[4] = {0, 0, 0, 0};
-        if (cls == 2) from_mont(w, F + 4 * (uint64_t)slot);
+        if (ex->ref == PZK_REF_TABVIEW) {
+          /* truth-table function of bits of words: {n, (slot, pos) x n, 2^n x int64} in the list pool */
+          const uint32_t* L = p->list + ex->aux;
+          unsigned n = L[0], idx = 0;
+          for (unsigned j = 0; j < n; j++) idx |= (unsigned)((U[L[1 + 2 * j]] >> L[2 + 2 * j]) & 1) << j;
+          int64_t v = (int64_t)((uint64_t)L[1 + 2 * n + 2 * idx] | ((uint64_t)L[2 + 2 * n + 2 * idx] << 32));
+          if (v < 0) { uint64_t m[4] = {(uint64_t)(-v), 0, 0, 0}; sub4(w, P, m); } else w[0] = (uint64_t)v;
+        } else if (cls == 3) {
+          /* bit-field view: ((word >> s) & (2^n - 1)) << k */
+          unsigned s_ = ex->aux & 255, n_ = (ex->aux >> 8) & 255, k_ = (ex->aux >> 16) & 255;
+          uint64_t m[4] = {0, 0, 0, 0}, one[4] = {1, 0, 0, 0};
+          if (ex->ref & PZK_REF_VIEW_N) memcpy(w, F + 4 * (uint64_t)slot, 32); else w[0] = U[slot];
+          shr4(w, w, s_);
+          shl4(m, one, n_); sub4(m, m, one);
+          for (int i = 0; i < 4; i++) w[i] &= m[i];
+          shl4(w, w, k_);
+        }
+        else if (cls == 2) from_mont(w, F + 4 * (uint64_t)slot);
         else if (cls == 1 && (int64_t)U[slot] < 0) { uint64_t m[4] = {(uint64_t)(-(int64_t)U[slot]), 0, 0, 0}; sub4(w, P, m); }
         else w[0] = U[slot];
         memcpy(dst, w, 32);

@@ -245,8 +245,12 @@ struct Compiler::Impl {
     o.dst = dst; o.a = a; o.b = b; o.c = c; o.d = d;
     if (dst && opc != PZK_ASSERT_NZ && opc != PZK_BIGDIV && opc != PZK_MODINV && dst < v_def.size()) v_def[dst] = (uint32_t)ops.size();
     ops.push_back(o);
+    if (op_stats) op_tag.push_back(cur_tname);
     return dst;
   }
+  bool op_stats = getenv("PZK_OP_STATS") != nullptr;
+  int cur_tname = -1;
+  std::vector<int> op_tag;
   uint32_t queue_inversion(uint32_t x) {
     if (is_pending(x)) flush_inversions();
     uint32_t r = new_value(CLS_F);
@@ -306,6 +310,7 @@ struct Compiler::Impl {
       const OpRec& o = dq[k];
       if (o.dst && o.opc != PZK_ASSERT_NZ && o.opc != PZK_BIGDIV && o.opc != PZK_MODINV && o.dst < v_def.size()) v_def[o.dst] = (uint32_t)ops.size();
       ops.push_back(o);
+      if (op_stats) op_tag.push_back(cur_tname);
       if (li < lq.size() && lq[li].first == k) { lutv_off[(uint32_t)ops.size() - 1] = lq[li].second; li++; }
     }
     flushing = false;
@@ -1164,7 +1169,9 @@ struct Compiler::Impl {
     for (size_t i = 0; i < td.params.size(); i++) declare_var(env, td.params[i], comp->lay->args[i]);
     Ctx ctx; ctx.lay = comp->lay; ctx.comp = comp;
     bool sr = returned; returned = false;
+    int saved_t = cur_tname; cur_tname = comp->lay->tname;
     exec(td.body, env, &ctx);
+    cur_tname = saved_t;
     returned = sr;
   }
 
@@ -1856,6 +1863,514 @@ struct Compiler::Impl {
     stats->n_values = v_cls.size();
   }
 
+  // ================================================================== bit-field views
+  // (see include/pzk_program.h, "Views")  A value whose defining op only moves bits of one word around -
+  // (x >> i) & 1, x & mask, bit * 2^i, the running sums of Num2Bits / Bits2Num / GetLastNBits
+  // (/root/reference/circuits/lib/circuits/bitify/bitify.circom:10-55, int/arithmetic.circom:161-204) - is
+  // described as a bit field of that word and gets no op of its own.
+  std::vector<ViewD> vw;                 // per value
+  std::vector<uint8_t> v_tabview;        // per value: exported as a truth-table function of bits of words
+  std::vector<uint32_t> alias_of;        // per value: 0 or the value that holds the same number
+  struct RangeRow { uint32_t base; uint16_t bits; };
+  std::unordered_map<uint32_t, RangeRow> range_rows;  // row -> (base >> bits) == 0
+  uint64_t n_range_emitted = 0;
+  uint64_t n_view_rows = 0, n_range_rows = 0, n_vlut = 0, n_vlut_lanes = 0, n_view_sigs = 0, n_tabview_sigs = 0, n_extracts = 0;
+  static int bitlen128(i128 v) { int n = 0; while (v > 0) { n++; v >>= 1; } return n; }
+  uint32_t canon(uint32_t v) const { while (v < alias_of.size() && alias_of[v]) v = alias_of[v]; return v; }
+  // bits of v in terms of a word that has (or will have) a slot
+  bool src_view(uint32_t v, ViewD& d) const {
+    if (v == 0 || v == PZK_OPERAND_NONE || v >= vw.size()) return false;
+    if (vw[v].base) { d = vw[v]; return true; }
+    int c = v_cls[v];
+    if (c == CLS_U && v_lo[v] >= 0) {
+      int n = bitlen128(v_hi[v]);
+      if (n == 0 || n > 64) return false;
+      d.base = v; d.s = 0; d.n = (uint8_t)n; d.k = 0;
+      return true;
+    }
+    if (c == CLS_N && v_def[v] < ops.size() && ops[v_def[v]].dst == v && ops[v_def[v]].opc == PZK_N_FROM_F) {
+      d.base = v; d.s = 0; d.n = 254; d.k = 0;
+      return true;
+    }
+    return false;
+  }
+  static bool pow2_of(const U256& c, int& r) {
+    if (c.is_zero()) return false;
+    int bl = c.bitlen();
+    if (!(c == shl(U256(1), bl - 1))) return false;
+    r = bl - 1;
+    return true;
+  }
+  // keep the bits of the value that lie in positions [lo, hi)
+  static bool view_window(ViewD& d, int lo, int hi) {
+    int t0 = std::max<int>(d.k, lo), t1 = std::min<int>(d.k + d.n, hi);
+    if (t1 <= t0) return false;
+    d.s = (uint8_t)(d.s + (t0 - d.k)); d.n = (uint8_t)(t1 - t0); d.k = (uint8_t)t0;
+    return true;
+  }
+  static bool view_merge(const ViewD& x, const ViewD& y, int limit, ViewD& out) {
+    if (x.base != y.base || (int)x.s - (int)x.k != (int)y.s - (int)y.k) return false;
+    const ViewD& lo = x.k <= y.k ? x : y; const ViewD& hi = x.k <= y.k ? y : x;
+    if (lo.k + lo.n != hi.k) return false;
+    if (lo.k + lo.n + hi.n > limit || lo.n + hi.n > 254) return false;
+    out = lo; out.n = (uint8_t)(lo.n + hi.n);
+    return true;
+  }
+  bool const_operand(const OpRec& o, U256& c) const {  // operand b as a constant
+    if (o.flags & PZK_FLAG_B_IMM) { c = U256((uint64_t)o.b); return true; }
+    if (o.flags & PZK_FLAG_B_POOL) return false;
+    if (o.b < v_const.size() && v_const[o.b] && v_cls[o.b] == CLS_U) { auto it = const_of.find(o.b); if (it != const_of.end()) { c = it->second; return true; } }
+    return false;
+  }
+  // the view the result of op `o` is, given the views of its operands
+  bool try_view(const OpRec& o, ViewD& d) const {
+    U256 c; int r;
+    switch (o.opc) {
+      case PZK_U_AND: {
+        if (!const_operand(o, c) || !c.fits64() || c.w[0] == 0) return false;
+        uint64_t m = c.w[0];
+        int lo = __builtin_ctzll(m), pc = __builtin_popcountll(m);
+        uint64_t run = pc == 64 ? ~0ull : (((1ull << pc) - 1) << lo);
+        if (m != run || !src_view(o.a, d)) return false;
+        return view_window(d, lo, lo + pc);
+      }
+      case PZK_U_SHR: case PZK_N_SHR: {
+        if (!(o.flags & PZK_FLAG_B_IMM) || !src_view(o.a, d)) return false;
+        int sh = (int)o.b;
+        if (sh >= 254 || !view_window(d, sh, 256)) return false;
+        d.k = (uint8_t)(d.k - sh);
+        return true;
+      }
+      case PZK_U_SHL: case PZK_U_MUL: {
+        if (o.opc == PZK_U_MUL && !(o.flags & (PZK_FLAG_B_IMM | PZK_FLAG_B_POOL)) && o.a == o.b) {
+          if (!src_view(o.a, d)) return false;
+          return d.n == 1 && d.k == 0;  // bit * bit
+        }
+        if (!const_operand(o, c) || !c.fits64()) return false;
+        if (o.opc == PZK_U_SHL) { if (!(o.flags & PZK_FLAG_B_IMM)) return false; r = (int)c.w[0]; }
+        else if (!pow2_of(c, r)) return false;
+        if (v_cls[o.dst] != CLS_U || !src_view(o.a, d)) return false;
+        if (d.k + d.n + r > 64) return false;
+        d.k = (uint8_t)(d.k + r);
+        return true;
+      }
+      case PZK_U_ADD: case PZK_F_ADD: {
+        if (o.flags & (PZK_FLAG_B_IMM | PZK_FLAG_B_POOL)) return false;
+        ViewD x, y;
+        if (!src_view(o.a, x) || !src_view(o.b, y)) return false;
+        return view_merge(x, y, o.opc == PZK_U_ADD ? 64 : 253, d);
+      }
+      case PZK_F_MUL: {
+        if (!(o.flags & PZK_FLAG_B_POOL)) {
+          if (o.a == o.b && src_view(o.a, d)) return d.n == 1 && d.k == 0;
+          return false;
+        }
+        c = fr_from_mont(fpool[o.b]);
+        if (!pow2_of(c, r) || !src_view(o.a, d)) return false;
+        if (d.k + d.n + r > 253) return false;
+        d.k = (uint8_t)(d.k + r);
+        return true;
+      }
+      case PZK_N_BIT: {
+        if (!src_view(o.a, d)) return false;
+        int b = (int)o.b;
+        if (!view_window(d, b, b + 1)) return false;
+        d.k = 0;
+        return true;
+      }
+      case PZK_N_LOW:
+        if (!src_view(o.a, d)) return false;
+        return view_window(d, 0, 64);
+      case PZK_N_FROM_U: case PZK_F_FROM_U: return src_view(o.a, d);
+      case PZK_F_FROM_N: case PZK_N_FROM_F:
+        if (!vw[o.a].base) return false;  // only views pass through; a real F value is the base of its own bits
+        d = vw[o.a];
+        return d.k + d.n <= 253;
+    }
+    return false;
+  }
+  // ---- packed truth tables ------------------------------------------------------------------------
+  // One-bit LUT ops whose operands are bits (W_j, q_j + l mod w) of the same words for lanes l = 0, 1, ... -
+  // the 32 XOR3 / Ch / Maj instances of a SHA round, rotations included
+  // (/root/reference/circuits/lib/circuits/hasher/sha2/sha256/sha256Compress.circom:63-84) - become one
+  // V_LUT record computing a whole word; each member signal is then bit l of that word (a view).
+  struct Place { uint32_t word; uint8_t pos; };
+  struct Group {
+    uint32_t word;            // value id of the result
+    int n, w;                 // operands, lane width (32 / 64)
+    uint16_t tbl;
+    uint32_t W[4]; uint8_t q[4];  // operand words and their bit positions for lane 0
+    uint64_t lanes = 0;
+    uint64_t last_join = 0;
+    bool open = true;
+  };
+  std::vector<Group> groups;
+  std::unordered_map<uint32_t, uint32_t> group_of_word;      // word value -> group index
+  std::unordered_map<uint32_t, Place> late_place;            // scalar bit -> (later word, position)
+  std::unordered_map<uint32_t, std::vector<std::pair<uint32_t, uint8_t>>> word_comp;  // word built from scalar bits
+  std::unordered_map<uint64_t, std::vector<uint32_t>> open_groups;  // hash of operand words -> group indices
+
+  static uint16_t permute_table(uint16_t t, int n, const int* perm) {  // operand j of the new table = operand perm[j] of t
+    uint16_t out = 0;
+    for (int idx = 0; idx < 16; idx++) {
+      int src = 0;
+      for (int j = 0; j < n; j++) if ((idx >> j) & 1) src |= 1 << perm[j];
+      if ((t >> src) & 1) out |= (uint16_t)(1u << idx);
+    }
+    return out;
+  }
+  static uint16_t canon_table(uint16_t t, int n) {  // replicate over the unused high index bits
+    uint16_t out = 0;
+    for (int idx = 0; idx < 16; idx++) if ((t >> (idx & ((1 << n) - 1))) & 1) out |= (uint16_t)(1u << idx);
+    return out;
+  }
+
+  void vectorize_sweep(std::vector<uint8_t>& keep, const std::vector<uint8_t>& row_needed,
+                       const std::function<void(const OpRec&, const std::function<void(uint32_t)>&)>& for_operands) {
+    const size_t nops = ops.size();
+    std::vector<OpRec> out;
+    out.reserve(nops / 2);
+    std::vector<int> out_tag;
+    vw.assign(v_cls.size(), ViewD());
+    v_tabview.assign(v_cls.size(), 0);
+    alias_of.assign(v_cls.size(), 0);
+    std::vector<uint8_t> is_real(v_cls.size(), 0);  // the value has (or will have) an op of its own in `out`
+    auto grow = [&]() {
+      size_t n = v_cls.size();
+      if (vw.size() < n) { vw.resize(n); v_tabview.resize(n, 0); alias_of.resize(n, 0); is_real.resize(n, 0); }
+    };
+    int cur_tag = -1;
+    auto push = [&](const OpRec& o) { out.push_back(o); if (op_stats) out_tag.push_back(cur_tag); };
+    std::map<std::tuple<uint32_t, int, int, int, int>, uint32_t> mat_cse;  // (base, s, n, k, class) -> value
+    std::function<uint32_t(uint32_t)> real_of;
+    std::function<void(uint32_t)> close_group;
+    // ---- backward hint: which table-valued values have a consumer that needs them as numbers
+    std::vector<uint8_t> need_real(v_cls.size(), 0);
+    for (size_t v = 0; v < row_needed.size(); v++) if (row_needed[v]) need_real[v] = 1;
+    auto viewable_opc = [&](const OpRec& o) {
+      switch (o.opc) {
+        case PZK_U_AND: case PZK_U_SHR: case PZK_U_SHL: case PZK_N_SHR: return (o.flags & PZK_FLAG_B_IMM) != 0;
+        case PZK_U_MUL: { U256 c; int r; return const_operand(o, c) && pow2_of(c, r); }
+        case PZK_F_MUL: { int r; return (o.flags & PZK_FLAG_B_POOL) && pow2_of(fr_from_mont(fpool[o.b]), r); }
+        case PZK_N_BIT: case PZK_N_LOW: case PZK_N_FROM_U: case PZK_F_FROM_U: return true;
+      }
+      return false;
+    };
+    auto tabled = [&](const OpRec& o) {
+      if (o.dst == 0 || o.dst >= v_tbl.size() || v_tbl[o.dst] < 0) return false;
+      if (v_cls[o.dst] != CLS_U && v_cls[o.dst] != CLS_I) return false;
+      switch (o.opc) {
+        case PZK_U_ADD: case PZK_U_SUB: case PZK_U_MUL: case PZK_U_LUT: case PZK_U_LUTV: case PZK_U_AND: case PZK_U_OR:
+        case PZK_U_XOR: case PZK_U_EQ: case PZK_U_NE: case PZK_U_LT: case PZK_U_LE: case PZK_U_SHR: case PZK_U_SHL: return tables[v_tbl[o.dst]].n >= 1;
+      }
+      return false;
+    };
+    for (size_t i = nops; i-- > 0;) {
+      if (!keep[i]) continue;
+      const OpRec& o = ops[i];
+      if (viewable_opc(o)) continue;
+      if (tabled(o) && !need_real[o.dst]) continue;
+      for_operands(o, [&](uint32_t v) { if (v != PZK_OPERAND_NONE && v < need_real.size()) need_real[v] = 1; });
+    }
+    // ---- placement of a one-bit value inside a word
+    auto place_of = [&](uint32_t b, Place& p) -> bool {
+      if (vw[b].base) {
+        const ViewD& d = vw[b];
+        if (d.n != 1 || d.k != 0 || d.s >= 64) return false;
+        int bc = v_cls[d.base];
+        if (bc != CLS_U) return false;
+        p.word = d.base; p.pos = d.s;
+        return true;
+      }
+      auto it = late_place.find(b);
+      if (it != late_place.end()) { p = it->second; return true; }
+      return false;
+    };
+    // ---- materialisation: the op that gives a view / table view a slot of its own
+    auto word_ready = [&](uint32_t w) {
+      auto g = group_of_word.find(w);
+      if (g != group_of_word.end() && groups[g->second].open) close_group(g->second);
+    };
+    auto emit_lut_positions = [&](uint32_t dst, const Table& t) {
+      OpRec o; memset(&o, 0, sizeof o);
+      o.dst = dst; o.flags = PZK_FLAG_EXT;
+      uint32_t s[4] = {PZK_OPERAND_NONE, PZK_OPERAND_NONE, PZK_OPERAND_NONE, PZK_OPERAND_NONE};
+      uint32_t posw = 0;
+      for (int j = 0; j < t.n; j++) {
+        uint32_t root = t.sup[j];
+        Place p;
+        if (vw[root].base && place_of(root, p)) { word_ready(p.word); s[j] = p.word; posw |= (uint32_t)p.pos << (8 * j); }
+        else s[j] = real_of(root);
+      }
+      o.a = s[0]; o.b = s[1]; o.c = s[2]; o.d = s[3]; o.f = posw;
+      if (table_bits(t)) {
+        int imm = 0;
+        for (int k = 0; k < 16; k++) if (t.e[k & ((1 << t.n) - 1)] == 1) imm |= 1 << k;
+        o.opc = PZK_U_LUT; o.imm16 = (uint16_t)imm;
+      } else {
+        o.opc = PZK_U_LUTV; o.e = (uint32_t)list_pool.size();
+        for (int k = 0; k < 16; k++) { uint64_t v = (uint64_t)t.e[k & ((1 << t.n) - 1)]; list_pool.push_back((uint32_t)v); list_pool.push_back((uint32_t)(v >> 32)); }
+      }
+      push(o);
+    };
+    real_of = [&](uint32_t v) -> uint32_t {
+      if (v == PZK_OPERAND_NONE || v == 0) return v;
+      v = canon(v);
+      if (is_real[v]) return v;
+      if (group_of_word.count(v)) { word_ready(v); return v; }
+      if (v_tabview[v]) {
+        v_tabview[v] = 0; is_real[v] = 1;
+        emit_lut_positions(v, tables[v_tbl[v]]);
+        n_extracts++;
+        return v;
+      }
+      if (!vw[v].base) { is_real[v] = 1; return v; }  // values defined outside the sweep's knowledge (should not happen)
+      ViewD d = vw[v];
+      uint32_t b = real_of(d.base);
+      const int cls = v_cls[v], bcls = v_cls[b];
+      const bool nbase = (bcls == CLS_N || bcls == CLS_F);
+      int bw = nbase ? 254 : bitlen128(v_hi[b]);
+      if (!nbase && d.s == 0 && d.k == 0 && d.n >= bw && cls == CLS_U) { alias_of[v] = b; return b; }
+      auto key = std::make_tuple(b, (int)d.s, (int)d.n, (int)d.k, cls);
+      auto it = mat_cse.find(key);
+      if (it != mat_cse.end()) { alias_of[v] = it->second; return it->second; }
+      mat_cse[key] = v;
+      OpRec o; memset(&o, 0, sizeof o);
+      o.dst = v; o.a = b;
+      auto extract = [&](int opc, uint32_t dst) {
+        OpRec x; memset(&x, 0, sizeof x);
+        x.opc = (uint8_t)opc; x.dst = dst; x.a = b; x.flags = nbase ? PZK_FLAG_NBASE : 0;
+        x.imm16 = (uint16_t)(d.s | (d.k << 8)); x.b = d.n;
+        push(x);
+      };
+      n_extracts++;
+      if (cls == CLS_U) {
+        if (!nbase && d.k == 0 && d.s == 0 && d.n <= 32) { o.opc = PZK_U_AND; o.flags = PZK_FLAG_B_IMM; o.b = d.n == 32 ? 0xffffffffu : ((1u << d.n) - 1); push(o); }
+        else if (!nbase && d.k == 0 && d.s + d.n >= bw) { o.opc = PZK_U_SHR; o.flags = PZK_FLAG_B_IMM; o.b = d.s; push(o); }
+        else if (!nbase && d.s == 0 && d.n >= bw && d.k < 32) { o.opc = PZK_U_MUL; o.flags = PZK_FLAG_B_IMM; o.b = 1u << d.k; push(o); }
+        else extract(PZK_U_EXTRACT, v);
+      } else if (cls == CLS_N) {
+        if (!nbase && d.s == 0 && d.k == 0 && d.n >= bw) { o.opc = PZK_N_FROM_U; push(o); }
+        else extract(PZK_N_EXTRACT, v);
+      } else {  // CLS_F: Montgomery form of the integer
+        if (!nbase && d.s == 0 && d.k == 0 && d.n >= bw) { o.opc = PZK_F_FROM_U; push(o); }
+        else if (d.k + d.n <= 64) {
+          uint32_t t = new_value(CLS_U, 0, d.k + d.n == 64 ? U64_MAX_ : (((i128)1 << (d.k + d.n)) - 1)); grow();
+          extract(PZK_U_EXTRACT, t); is_real[t] = 1;
+          o.opc = PZK_F_FROM_U; o.a = t; push(o);
+        } else {
+          uint32_t t = new_value(CLS_N); grow();
+          extract(PZK_N_EXTRACT, t); is_real[t] = 1;
+          o.opc = PZK_F_FROM_N; o.a = t; push(o);
+        }
+      }
+      is_real[v] = 1;
+      return v;
+    };
+    close_group = [&](uint32_t gi) {
+      Group& g0 = groups[gi];
+      if (!g0.open) return;
+      g0.open = false;
+      uint32_t W[4]; for (int j = 0; j < g0.n; j++) W[j] = real_of(g0.W[j]);
+      Group& g = groups[gi];  // real_of may grow `groups`
+      OpRec o; memset(&o, 0, sizeof o);
+      o.opc = PZK_V_LUT; o.flags = PZK_FLAG_EXT | (g.w == 64 ? PZK_FLAG_W64 : 0); o.imm16 = g.tbl; o.dst = g.word;
+      uint32_t s[4] = {PZK_OPERAND_NONE, PZK_OPERAND_NONE, PZK_OPERAND_NONE, PZK_OPERAND_NONE};
+      uint32_t rot = 0;
+      for (int j = 0; j < g.n; j++) { s[j] = W[j]; rot |= (uint32_t)g.q[j] << (8 * j); }
+      o.a = s[0]; o.b = s[1]; o.c = s[2]; o.d = s[3]; o.e = rot; o.f = (uint32_t)g.lanes; o.g = (uint32_t)(g.lanes >> 32);
+      // exact interval of the word: its highest lane
+      v_lo[g.word] = 0; v_hi[g.word] = (i128)g.lanes;
+      push(o);
+      is_real[g.word] = 1;
+      n_vlut++; n_vlut_lanes += (uint64_t)__builtin_popcountll(g.lanes);
+      if (getenv("PZK_DUMP_GROUPS")) fprintf(stderr, "G n=%d w=%d tbl=%04x lanes=%016llx W=%u,%u,%u q=%d,%d,%d tag=%s\n", g.n, g.w, g.tbl, (unsigned long long)g.lanes, g.W[0], g.n > 1 ? g.W[1] : 0, g.n > 2 ? g.W[2] : 0, g.q[0], g.n > 1 ? g.q[1] : -1, g.n > 2 ? g.q[2] : -1, cur_tag >= 0 ? nm(cur_tag).c_str() : "?");
+    };
+    auto words_key = [&](const uint32_t* W, int n, int w) {
+      uint32_t s[4]; for (int j = 0; j < n; j++) s[j] = W[j];
+      std::sort(s, s + n);
+      uint64_t h = (uint64_t)w * 1315423911u + (uint64_t)n;
+      for (int j = 0; j < n; j++) h = h * 0x9E3779B97F4A7C15ull + s[j];
+      return h;
+    };
+    auto try_group = [&](const OpRec& o, const Table& tb, uint64_t at) -> bool {
+      if (!opt.vectorize || !table_bits(tb) || tb.n < 1) return false;
+      Place pl[4]; int n = tb.n;
+      for (int j = 0; j < n; j++) if (!place_of(canon(tb.sup[j]), pl[j])) return false;
+      uint16_t timm = 0;
+      for (int k = 0; k < 16; k++) if (tb.e[k & ((1 << n) - 1)] == 1) timm |= (uint16_t)(1u << k);
+      int w = 32;
+      for (int j = 0; j < n; j++) if (pl[j].pos >= 32) w = 64;
+      uint32_t Ws[4]; for (int j = 0; j < n; j++) Ws[j] = pl[j].word;
+      const uint16_t T = timm;
+      uint64_t key = words_key(Ws, n, w);
+      auto& cand = open_groups[key];
+      // try to join: some assignment of our operands to the group's operands with one common lane
+      for (size_t ci = cand.size(); ci-- > 0;) {
+        Group& g = groups[cand[ci]];
+        if (!g.open) { cand.erase(cand.begin() + ci); continue; }
+        if (g.n != n || g.w != w) continue;
+        int perm[4] = {0, 1, 2, 3};
+        std::sort(perm, perm + n);
+        do {
+          // our operand perm[j] plays the role of the group's operand j
+          bool ok = true; int lane = -1;
+          for (int j = 0; j < n && ok; j++) {
+            const Place& p = pl[perm[j]];
+            if (p.word != g.W[j]) { ok = false; break; }
+            int l = ((int)p.pos - (int)g.q[j]) & (w - 1);
+            if (lane < 0) lane = l; else if (l != lane) ok = false;
+          }
+          if (!ok || ((g.lanes >> lane) & 1)) continue;
+          // group table indexed by group operand order: bit j of the index = our operand perm[j]
+          // our table T is indexed by our operand order; T' (idx) = T(idx') with idx' bit perm[j] = idx bit j
+          uint16_t Tp = 0;
+          for (int idx = 0; idx < 16; idx++) {
+            int src = 0;
+            for (int j = 0; j < n; j++) if ((idx >> j) & 1) src |= 1 << perm[j];
+            if ((T >> src) & 1) Tp |= (uint16_t)(1u << idx);
+          }
+          Tp = canon_table(Tp, n);
+          if (Tp != g.tbl) continue;
+          g.lanes |= 1ull << lane; g.last_join = at;
+          vw[o.dst].base = g.word; vw[o.dst].s = (uint8_t)lane; vw[o.dst].n = 1; vw[o.dst].k = 0;
+          if (__builtin_popcountll(g.lanes) == w) close_group(cand[ci]);
+          return true;
+        } while (std::next_permutation(perm, perm + n));
+      }
+      // open a new group with this op as lane 0
+      Group g; g.n = n; g.w = w; g.tbl = T; g.lanes = 1; g.last_join = at;
+      for (int j = 0; j < n; j++) { g.W[j] = pl[j].word; g.q[j] = pl[j].pos; }
+      g.word = new_value(CLS_U, 0, w == 64 ? U64_MAX_ : (i128)0xffffffffu); grow();
+      groups.push_back(g);
+      uint32_t gi = (uint32_t)groups.size() - 1;
+      group_of_word[g.word] = gi;
+      cand.push_back(gi);
+      if (cand.size() > 8) { close_group(cand.front()); cand.erase(cand.begin()); }
+      vw[o.dst].base = g.word; vw[o.dst].s = 0; vw[o.dst].n = 1; vw[o.dst].k = 0;
+      return true;
+    };
+    // ---- the sweep
+    std::vector<uint32_t> stale_check;
+    for (size_t i = 0; i < nops; i++) {
+      if (!keep[i]) continue;
+      OpRec o = ops[i];
+      if (op_stats && i < op_tag.size()) cur_tag = op_tag[i];
+      if (o.opc == PZK_U_LUTV) { auto it = lutv_off.find((uint32_t)i); if (it != lutv_off.end()) o.e = it->second; }
+      const uint32_t d = o.dst;
+      bool has_value = !(o.opc == PZK_NOP || o.opc == PZK_ASSERT_NZ || o.opc == PZK_BIGDIV || o.opc == PZK_MODINV);
+      bool dropped = false;
+      if (opt.views && has_value && d) {
+        ViewD dv;
+        // canonical operands first: views built on aliases keep pointing at real words
+        if (try_view(o, dv)) {
+          uint32_t b = canon(dv.base);
+          if (v_tabview[b]) b = real_of(b);
+          if (vw[b].base) {  // cannot happen: bases are words
+            throw CompileError("internal: view of a view");
+          }
+          dv.base = b;
+          vw[d] = dv; dropped = true;
+        } else if (tabled(o)) {
+          const Table& tb = tables[v_tbl[d]];
+          if (try_group(o, tb, i)) dropped = true;
+          else if (!need_real[d]) {
+            // exported as a table over bits of words: every root needs an address (a word and a position)
+            for (int j = 0; j < tb.n; j++) { uint32_t root = canon(tb.sup[j]); Place p; if (!(vw[root].base && place_of(root, p))) real_of(root); }
+            v_tabview[d] = 1; dropped = true;
+          }
+        }
+      }
+      if (dropped) {
+        if (row_needed.size() > d && row_needed[d]) real_of(d);
+      } else {
+        // a real op: its operands need slots
+        switch (o.opc) {
+          case PZK_NOP: case PZK_U_CONST: case PZK_F_CONST: case PZK_IN_U: case PZK_IN_F: break;
+          case PZK_BIGDIV: case PZK_MODINV: {
+            uint32_t k = list_pool[o.a + 1], m = list_pool[o.a + 2];
+            for (uint32_t j = 0; j < k + m + k; j++) list_pool[o.a + 3 + j] = real_of(list_pool[o.a + 3 + j]);
+            break;
+          }
+          case PZK_ASSERT_NZ: case PZK_N_BIT: case PZK_F_CSEL: o.a = real_of(o.a); break;
+          case PZK_U_LUT: case PZK_U_LUTV: {
+            // operands that are bits of words are read in place (bit positions in the extension record)
+            uint32_t* s[4] = {&o.a, &o.b, &o.c, &o.d};
+            uint32_t posw = 0;
+            for (int j = 0; j < 4; j++) {
+              if (*s[j] == PZK_OPERAND_NONE) continue;
+              uint32_t v = canon(*s[j]);
+              Place p;
+              if (!is_real[v] && vw[v].base && place_of(v, p)) { word_ready(p.word); *s[j] = p.word; posw |= (uint32_t)p.pos << (8 * j); }
+              else *s[j] = real_of(v);
+            }
+            o.f = posw;
+            break;
+          }
+          case PZK_U_SEL: case PZK_F_SEL: o.a = real_of(o.a); o.b = real_of(o.b); o.c = real_of(o.c); break;
+          default:
+            o.a = real_of(o.a);
+            if (!(o.flags & (PZK_FLAG_B_IMM | PZK_FLAG_B_POOL))) {
+              switch (o.opc) {
+                case PZK_F_NEG: case PZK_F_INV: case PZK_F_FROM_U: case PZK_F_FROM_I: case PZK_N_FROM_F:
+                case PZK_F_FROM_N: case PZK_N_FROM_U: case PZK_N_LOW: case PZK_N_FITS: break;
+                default: o.b = real_of(o.b);
+              }
+            }
+        }
+        push(o);
+        if (has_value && d) is_real[d] = 1;
+        if (o.opc == PZK_BIGDIV || o.opc == PZK_MODINV) {
+          uint32_t k = list_pool[o.a + 1], m = list_pool[o.a + 2];
+          for (uint32_t j = 0; j < m + 1 + k; j++) is_real[list_pool[o.a + 3 + (k + m) + k + j]] = 1;
+        }
+        // a word assembled from scalar bits (b << k summed in ascending order): the bits get a place in it
+        if (opt.vectorize && o.opc == PZK_U_ADD && !(o.flags & PZK_FLAG_B_IMM) && v_cls[d] == CLS_U) {
+          const OpRec& src = ops[i];  // operands before materialisation
+          std::vector<std::pair<uint32_t, uint8_t>> comp;
+          uint64_t occ = 0; bool ok = true;
+          for (uint32_t opnd : {src.a, src.b}) {
+            uint32_t v = canon(opnd);
+            auto wc = word_comp.find(v);
+            if (wc != word_comp.end()) { for (auto& e : wc->second) { if ((occ >> e.second) & 1) ok = false; occ |= 1ull << e.second; comp.push_back(e); } continue; }
+            // a scalar bit shifted left by k
+            uint32_t bit = 0; int k = -1;
+            const OpRec* def = (v < v_def.size() && v_def[v] < nops && ops[v_def[v]].dst == v) ? &ops[v_def[v]] : nullptr;
+            U256 c; int r;
+            if (v_hi[v] <= 1 && v_lo[v] >= 0 && v_cls[v] == CLS_U) { bit = v; k = 0; }
+            else if (def && def->opc == PZK_U_MUL && const_operand(*def, c) && pow2_of(c, r) && r < 64) {
+              uint32_t x = canon(def->a);
+              if (v_cls[x] == CLS_U && v_lo[x] >= 0 && v_hi[x] <= 1) { bit = x; k = r; }
+            }
+            if (k < 0) { ok = false; break; }
+            if ((occ >> k) & 1) ok = false;
+            occ |= 1ull << k; comp.emplace_back(bit, (uint8_t)k);
+          }
+          if (ok && comp.size() >= 2) {
+            for (auto& e : comp) { Place p; p.word = d; p.pos = e.second; if (!vw[e.first].base) late_place[e.first] = p; }
+            word_comp[d] = std::move(comp);
+          }
+        }
+      }
+      // groups that stopped growing are closed so that their operands can die
+      if ((i & 1023) == 0 && !groups.empty()) {
+        for (auto& kv : open_groups) {
+          auto& cand = kv.second;
+          for (size_t ci = cand.size(); ci-- > 0;) {
+            Group& g = groups[cand[ci]];
+            if (!g.open) { cand.erase(cand.begin() + ci); continue; }
+            if (i - g.last_join > 4096) { uint32_t gi = cand[ci]; cand.erase(cand.begin() + ci); close_group(gi); }
+          }
+        }
+      }
+    }
+    for (size_t gi = 0; gi < groups.size(); gi++) if (groups[gi].open) close_group((uint32_t)gi);
+    ops.swap(out);
+    if (op_stats) op_tag.swap(out_tag);
+    keep.assign(ops.size(), 1);
+    lutv_off.clear();
+  }
+
   // ================================================================== back end
   void backend();
   void build_meta();
@@ -1867,7 +2382,7 @@ struct Compiler::Impl {
 void Compiler::Impl::backend() {
   size_t nv = v_cls.size(), nops = ops.size();
   // ---- operand enumeration helper
-  auto for_operands = [&](const OpRec& o, const std::function<void(uint32_t)>& f) {
+  std::function<void(const OpRec&, const std::function<void(uint32_t)>&)> for_operands = [&](const OpRec& o, const std::function<void(uint32_t)>& f) {
     switch (o.opc) {
       case PZK_NOP: case PZK_U_CONST: case PZK_F_CONST: case PZK_IN_U: case PZK_IN_F: return;
       case PZK_BIGDIV: case PZK_MODINV: {
@@ -1875,8 +2390,8 @@ void Compiler::Impl::backend() {
         for (uint32_t i = 0; i < k + m + k; i++) f(list_pool[o.a + 3 + i]);
         return;
       }
-      case PZK_ASSERT_NZ: f(o.a); return;
-      case PZK_U_LUT: case PZK_U_LUTV:
+      case PZK_ASSERT_NZ: case PZK_U_EXTRACT: case PZK_N_EXTRACT: f(o.a); return;
+      case PZK_U_LUT: case PZK_U_LUTV: case PZK_V_LUT:
         if (o.a != PZK_OPERAND_NONE) f(o.a);
         if (o.b != PZK_OPERAND_NONE) f(o.b);
         if (o.c != PZK_OPERAND_NONE) f(o.c);
@@ -1929,27 +2444,19 @@ void Compiler::Impl::backend() {
     keep[i] = 1;
     for_operands(o, [&](uint32_t v) { used[v] = 1; });
   }
-  // ---- rows: each one is checked right after the op that defines the last of its wires
-  size_t nrows = rows.size();
-  size_t first_kept = 0;
-  while (first_kept < nops && !keep[first_kept]) first_kept++;
-  std::vector<uint32_t> row_trigger(nrows, (uint32_t)first_kept), row_recs(nrows, 1);
-  for (size_t r = 0; r < nrows; r++) {
-    uint32_t nt = rows[r].na + rows[r].nb + rows[r].nc, live_terms = 0;
-    for (uint32_t t = 0; t < nt; t++) {
-      uint32_t sig = terms[rows[r].off + t].first;
-      if (sig == 0xFFFFFFFFu) { live_terms++; continue; }
-      uint32_t v = sig_val[sig];
-      if (!v) continue;
-      live_terms++;
-      if (v_def[v] > row_trigger[r]) row_trigger[r] = v_def[v];
+  auto print_op_stats = [&](const char* tag) {
+    if (!op_stats || op_tag.size() != ops.size()) return;
+    std::map<std::pair<std::string, int>, uint64_t> hist;
+    std::map<std::string, uint64_t> per_t;
+    for (size_t i = 0; i < ops.size(); i++) if (keep[i]) { std::string t = op_tag[i] >= 0 ? nm(op_tag[i]) : "<main>"; hist[{t, ops[i].opc}]++; per_t[t]++; }
+    for (auto& kv : per_t) {
+      fprintf(stderr, "%s %-40s %9llu :", tag, kv.first.c_str(), (unsigned long long)kv.second);
+      for (auto& h : hist) if (h.first.first == kv.first) fprintf(stderr, " %d:%llu", h.first.second, (unsigned long long)h.second);
+      fprintf(stderr, "\n");
     }
-    row_recs[r] = 1 + (live_terms + 1) / 2;
-  }
-
-  std::vector<uint32_t> row_order(nrows);
-  for (size_t r = 0; r < nrows; r++) row_order[r] = (uint32_t)r;
-  std::stable_sort(row_order.begin(), row_order.end(), [&](uint32_t a, uint32_t b) { return row_trigger[a] < row_trigger[b]; });
+  };
+  print_op_stats("T");
+  size_t nrows = rows.size();
   struct MT { uint32_t val; U256 c; };  // val: value id, 0xFFFFFFFF = constant one
   // merge the terms of each linear combination by SSA value: wires that alias the same value
   // (every `a <== b`) collapse, and a row whose combinations cancel completely is satisfied by
@@ -1962,7 +2469,7 @@ void Compiler::Impl::backend() {
       for (uint32_t t = 0; t < lens[part]; t++, off++) {
         uint32_t sig = terms[off].first;
         uint32_t val = 0xFFFFFFFFu;
-        if (sig != 0xFFFFFFFFu) { val = sig_val[sig]; if (!val) continue; }
+        if (sig != 0xFFFFFFFFu) { val = sig_val[sig]; if (!val) continue; val = canon(val); }
         const U256& c = coefs[terms[off].second];
         bool found = false;
         for (auto& m : parts[part]) if (m.val == val) { m.c = fr_add(m.c, c); found = true; break; }
@@ -1982,6 +2489,20 @@ void Compiler::Impl::backend() {
     // XOR / Maj / Ch / carry rows of SHA, bit checks b * (b - 1) = 0, selectors) is an identity over
     // those bits: it is evaluated here for every assignment of the roots, with the very tables the device
     // uses to compute the wires, and discharged when it holds for all of them.
+    auto const_of = [&](uint32_t id, U256& out) -> bool {
+      uint32_t di = v_def[id];
+      if (di >= nops) return false;
+      const OpRec& o = ops[di];
+      if (o.dst != id) return false;
+      if (o.opc == PZK_U_CONST) {
+        uint64_t raw = ((uint64_t)o.b << 32) | o.a;
+        if (v_cls[id] == CLS_I && (int64_t)raw < 0) out = fr_neg(U256((uint64_t)(-(int64_t)raw)));
+        else out = U256(raw);
+        return true;
+      }
+      if (o.opc == PZK_F_CONST) { out = fr_from_mont(fpool[o.a]); return true; }
+      return false;
+    };
     auto prove_by_tables = [&](const std::vector<MT>* parts) -> bool {
       if (!opt.table_rows_static) return false;
       uint32_t roots[8]; int nr = 0;
@@ -1996,7 +2517,9 @@ void Compiler::Impl::backend() {
           x.coef = cv;
           if (m.val != 0xFFFFFFFFu) {
             uint32_t id = m.val;
-            if (v_tbl[id] >= 0) x.t = &tables[v_tbl[id]];
+            U256 kc; int64_t ks;
+            if (const_of(id, kc)) { if (!small_signed(kc, ks)) return false; x.self.n = 0; x.self.e[0] = ks; }
+            else if (v_tbl[id] >= 0) x.t = &tables[v_tbl[id]];
             else if (v_cls[id] == CLS_U && v_lo[id] >= 0 && v_hi[id] <= 1) { x.self.n = 1; x.self.sup[0] = id; x.self.e[0] = 0; x.self.e[1] = 1; }
             else return false;
           } else { x.self.n = 0; x.self.e[0] = 1; }
@@ -2038,20 +2561,6 @@ void Compiler::Impl::backend() {
     // the linear form cancels.  For A * B = C with single-wire A and B the product x * y is matched against
     // the MUL op that defines a wire of C.  This is what makes `z <== x + 2^k * y` and `z <== x * y`
     // hold for every input; rows the expansion cannot close stay run-time checks.
-    auto const_of = [&](uint32_t id, U256& out) -> bool {
-      uint32_t di = v_def[id];
-      if (di >= nops) return false;
-      const OpRec& o = ops[di];
-      if (o.dst != id) return false;
-      if (o.opc == PZK_U_CONST) {
-        uint64_t raw = ((uint64_t)o.b << 32) | o.a;
-        if (v_cls[id] == CLS_I && (int64_t)raw < 0) out = fr_neg(U256((uint64_t)(-(int64_t)raw)));
-        else out = U256(raw);
-        return true;
-      }
-      if (o.opc == PZK_F_CONST) { out = fr_from_mont(fpool[o.a]); return true; }
-      return false;
-    };
     auto prove_symbolic = [&](const std::vector<MT>* parts) -> bool {
       if (!opt.symbolic_rows_static) return false;
       std::map<uint32_t, U256> lin;  // value -> coefficient of (A*B - C), constant one under 0xFFFFFFFF
@@ -2114,22 +2623,188 @@ void Compiler::Impl::backend() {
       }
       return false;
     };
+    // Bit-view proof: every wire of the row is a bit field of some word (or a constant): the row is expanded over
+    // the individual bits of those words, bit(W, t) in {0, 1} unknown, and holds for every input when all
+    // coefficients cancel - `div * 2 + bit * bit === in` of GetLastBitUnsecure, `check[N-1] + div * 2^N === in`,
+    // `in === sum[LEN-1]` of Num2Bits when the interval of `in` fits LEN bits
+    // (/root/reference/circuits/lib/circuits/int/arithmetic.circom:161-204, bitify/bitify.circom:10-32).  When the
+    // only bits left are the high bits W[T..] of one word, each with weight c * 2^t, the row IS the range check
+    // (W >> T) == 0 and is lowered to one CHECK_RANGE record (returns 2).
+    struct BitTerm { uint32_t base; uint32_t bit; U256 c; };
+    std::vector<BitTerm> bt;
+    auto prove_views = [&](const std::vector<MT>* parts, uint32_t& rbase, int& rbits) -> int {
+      if (!opt.views) return 0;
+      bt.clear();
+      U256 konst;
+      auto expand = [&](uint32_t val, const U256& c) -> bool {
+        if (val == 0xFFFFFFFFu) { konst = fr_add(konst, c); return true; }
+        U256 k;
+        if (const_of(val, k)) { konst = fr_add(konst, fr_mul(c, k)); return true; }
+        ViewD d;
+        if (!src_view(val, d)) {
+          if (v_cls[val] != CLS_F || !v_convN[val]) return false;
+          uint32_t nf = v_convN[val];
+          if (v_def[nf] >= nops || !keep[v_def[nf]] || ops[v_def[nf]].opc != PZK_N_FROM_F || ops[v_def[nf]].dst != nf) return false;
+          d.base = nf; d.s = 0; d.n = 254; d.k = 0;
+        }
+        U256 w = c;
+        for (int t = 0; t < d.k; t++) w = fr_add(w, w);
+        for (int t = 0; t < d.n; t++) { bt.push_back({d.base, (uint32_t)(d.s + t), w}); w = fr_add(w, w); }
+        return true;
+      };
+      if (!parts[0].empty() && !parts[1].empty()) {
+        if (parts[0].size() != 1 || parts[1].size() != 1) return 0;
+        uint32_t x = parts[0][0].val, y = parts[1][0].val;
+        if (x == 0xFFFFFFFFu || y == 0xFFFFFFFFu) return 0;
+        ViewD dx, dy;
+        if (!src_view(x, dx) || !src_view(y, dy)) return 0;
+        if (dx.n != 1 || dx.k != 0 || dy.n != 1 || dy.k != 0 || dx.base != dy.base || dx.s != dy.s) return 0;
+        bt.push_back({dx.base, dx.s, fr_mul(parts[0][0].c, parts[1][0].c)});  // bit * bit = bit
+      }
+      for (const MT& m : parts[2]) if (!expand(m.val, fr_neg(m.c))) return 0;
+      if (!konst.is_zero()) return 0;
+      std::sort(bt.begin(), bt.end(), [](const BitTerm& a, const BitTerm& b) { return a.base != b.base ? a.base < b.base : a.bit < b.bit; });
+      size_t w = 0;
+      for (size_t i = 0; i < bt.size();) {
+        BitTerm acc = bt[i]; size_t j = i + 1;
+        while (j < bt.size() && bt[j].base == acc.base && bt[j].bit == acc.bit) { acc.c = fr_add(acc.c, bt[j].c); j++; }
+        if (!acc.c.is_zero()) bt[w++] = acc;
+        i = j;
+      }
+      bt.resize(w);
+      if (bt.empty()) return 1;
+      // residual = c * sum_{t >= T} 2^t bit(W, t) ?
+      uint32_t B = bt[0].base;
+      ViewD id;
+      if (!src_view(B, id) || id.base != B) return 0;  // B must be a word
+      uint32_t T = bt[0].bit;
+      if (T == 0 || bt.size() != (size_t)id.n - T) return 0;
+      U256 c = bt[0].c;
+      for (size_t i = 0; i < bt.size(); i++) {
+        if (bt[i].base != B || bt[i].bit != T + i || !(bt[i].c == c)) return 0;
+        c = fr_add(c, c);
+      }
+      // c0 * 2^(t - T) with c0 != 0: c0 * 2^-T * (W >> T) * 2^T ... the sum is c0 / 2^T * (W - (W mod 2^T)), zero iff W >> T == 0
+      rbase = B; rbits = (int)T;
+      return 2;
+    };
+    // plain views of the scalar program (packed truth tables come later): what the bit-view prover reads
+    vw.assign(nv, ViewD()); v_tabview.assign(nv, 0); alias_of.assign(nv, 0);
+    if (opt.views)
+      for (size_t i = 0; i < nops; i++) {
+        if (!keep[i]) continue;
+        const OpRec& o = ops[i];
+        if (o.opc == PZK_NOP || o.opc == PZK_ASSERT_NZ || o.opc == PZK_BIGDIV || o.opc == PZK_MODINV || !o.dst) continue;
+        ViewD d;
+        if (try_view(o, d)) vw[o.dst] = d;
+      }
     for (size_t r = 0; r < nrows; r++) {
+      uint32_t rbase = 0; int rbits = 0, pv = 0;
       if (merge_row((uint32_t)r, parts)) { row_static[r] = 1; n_static_rows++; }
       else if (prove_by_tables(parts)) { row_static[r] = 2; n_table_rows++; }
       else if (prove_symbolic(parts)) { row_static[r] = 3; n_symbolic_rows++; }
+      else if ((pv = prove_views(parts, rbase, rbits)) == 1) { row_static[r] = 5; n_view_rows++; }
+      else if (pv == 2) { range_rows[(uint32_t)r] = RangeRow{rbase, (uint16_t)rbits}; n_range_rows++; }
+      else if (getenv("PZK_DUMP_ROWS") && !(rows[r].by_def && opt.def_rows_static)) {
+        static int dumped = 0;
+        if (dumped++ < atoi(getenv("PZK_DUMP_ROWS"))) {
+          fprintf(stderr, "row %zu:", r);
+          for (int part = 0; part < 3; part++) {
+            fprintf(stderr, " [");
+            for (auto& m : parts[part]) {
+              if (m.val == 0xFFFFFFFFu) { fprintf(stderr, " 1*%llx", (unsigned long long)m.c.w[0]); continue; }
+              ViewD d; bool hv = src_view(m.val, d);
+              fprintf(stderr, " v%u(cls%d opc%d hi=%llx view=%d:%u,%d,%d,%d t=%s)*%llx", m.val, (int)v_cls[m.val], v_def[m.val] < nops ? (int)ops[v_def[m.val]].opc : -1, (unsigned long long)v_hi[m.val], (int)hv, d.base, d.s, d.n, d.k,
+                      (op_stats && v_def[m.val] < op_tag.size() && op_tag[v_def[m.val]] >= 0) ? nm(op_tag[v_def[m.val]]).c_str() : "?", (unsigned long long)m.c.w[0]);
+            }
+            fprintf(stderr, " ]");
+          }
+          fprintf(stderr, "\n");
+        }
+      }
       // `x <== e` stores value(e) into x and adds the row e - x = 0: the wire holds the very value the
       // row compares it with, so the row holds for every input (the same argument as for aliases, one
       // multiplication deeper).  Only `===` rows and rows over `<--` hints can fail at run time.
       else if (rows[r].by_def && opt.def_rows_static) { row_static[r] = 4; n_def_rows++; }
     }
   }
+  // ---- views and packed truth tables: rewrite the op list (the proofs above read the scalar program)
+  if (opt.views) {
+    std::vector<uint8_t> row_needed(nv, 0);
+    for (size_t r = 0; r < nrows; r++) {
+      if (row_static[r]) continue;
+      auto rr = range_rows.find((uint32_t)r);
+      if (rr != range_rows.end()) { row_needed[rr->second.base] = 1; continue; }
+      uint32_t nt = rows[r].na + rows[r].nb + rows[r].nc;
+      for (uint32_t t = 0; t < nt; t++) { uint32_t sig = terms[rows[r].off + t].first; if (sig != 0xFFFFFFFFu && sig_val[sig]) row_needed[sig_val[sig]] = 1; }
+    }
+    vectorize_sweep(keep, row_needed, for_operands);
+    nv = v_cls.size(); nops = ops.size();
+    v_def.assign(nv, 0xFFFFFFFFu);
+    for (size_t i = 0; i < nops; i++) for_defs(ops[i], [&](uint32_t d) { v_def[d] = (uint32_t)i; });
+    // what must exist after the rewrite: words that signals are exported from (own slot or as the base / a root
+    // of a view), values of run-time rows; everything else that nothing reads goes
+    std::vector<uint8_t> need(nv, 0);
+    auto need_word = [&](uint32_t v) { v = canon(v); if (v < nv) need[v] = 1; };
+    for (uint32_t v : sig_val) {
+      if (!v) continue;
+      if (vw[v].base) need_word(vw[v].base);
+      else if (v_tabview[v]) { const Table& tb = tables[v_tbl[v]]; for (int j = 0; j < tb.n; j++) { uint32_t root = canon(tb.sup[j]); if (vw[root].base && v_def[root] == 0xFFFFFFFFu) need_word(vw[root].base); else need_word(root); } }
+      else need_word(v);
+    }
+    for (size_t r = 0; r < nrows; r++) {
+      if (row_static[r]) continue;
+      auto rr = range_rows.find((uint32_t)r);
+      if (rr != range_rows.end()) { need_word(rr->second.base); continue; }
+      uint32_t nt = rows[r].na + rows[r].nb + rows[r].nc;
+      for (uint32_t t = 0; t < nt; t++) { uint32_t sig = terms[rows[r].off + t].first; if (sig != 0xFFFFFFFFu && sig_val[sig]) need_word(sig_val[sig]); }
+    }
+    for (size_t i = nops; i-- > 0;) {
+      const OpRec& o = ops[i];
+      bool live = (o.opc == PZK_ASSERT_NZ) || (o.opc == PZK_IN_U) || (o.opc == PZK_IN_F) || (o.opc == PZK_NOP && i == 0);
+      if (!live) for_defs(o, [&](uint32_t d) { if (need[d]) live = true; });
+      keep[i] = live;
+      if (live) for_operands(o, [&](uint32_t v) { if (v != PZK_OPERAND_NONE) need[v] = 1; });
+    }
+    used.assign(nv, 1);
+    print_op_stats("V");
+  }
+  // ---- rows: each one is checked right after the op that defines the last of its wires
+  size_t first_kept = 0;
+  while (first_kept < nops && !keep[first_kept]) first_kept++;
+  std::vector<uint32_t> row_trigger(nrows, (uint32_t)first_kept), row_recs(nrows, 1);
+  // values a run-time row reads (a range row reads its word only)
+  auto row_values = [&](uint32_t r, const std::function<void(uint32_t)>& f) {
+    auto rr = range_rows.find(r);
+    if (rr != range_rows.end()) { f(canon(rr->second.base)); return; }
+    uint32_t nt = rows[r].na + rows[r].nb + rows[r].nc;
+    for (uint32_t t = 0; t < nt; t++) {
+      uint32_t sig = terms[rows[r].off + t].first;
+      if (sig == 0xFFFFFFFFu) continue;
+      uint32_t v = sig_val[sig];
+      if (v) f(canon(v));
+    }
+  };
+  for (size_t r = 0; r < nrows; r++) {
+    if (row_kind[r]) continue;
+    uint32_t nt = rows[r].na + rows[r].nb + rows[r].nc, live_terms = 0;
+    for (uint32_t t = 0; t < nt; t++) {
+      uint32_t sig = terms[rows[r].off + t].first;
+      if (sig == 0xFFFFFFFFu || sig_val[sig]) live_terms++;
+    }
+    row_values((uint32_t)r, [&](uint32_t v) { if (v_def[v] != 0xFFFFFFFFu && v_def[v] > row_trigger[r]) row_trigger[r] = v_def[v]; });
+    row_recs[r] = range_rows.count((uint32_t)r) ? 1 : 1 + (live_terms + 1) / 2;
+  }
+
+  std::vector<uint32_t> row_order(nrows);
+  for (size_t r = 0; r < nrows; r++) row_order[r] = (uint32_t)r;
+  std::stable_sort(row_order.begin(), row_order.end(), [&](uint32_t a, uint32_t b) { return row_trigger[a] < row_trigger[b]; });
   // ---- peephole: x + (z * 2^k) with a single-use product that is not a wire -> one U_SHLADD record
   // (weighted bit sums: `lc += bit * 2^k`).  Same value in wrapping 64-bit arithmetic, one record less.
   if (opt.fuse_shladd) {
     std::vector<uint32_t> uses(nv, 0), def_op(nv, 0xFFFFFFFFu);
     std::vector<uint8_t> is_sig(nv, 0);
-    for (uint32_t v : sig_val) if (v) is_sig[v] = 1;
+    for (uint32_t v : sig_val) if (v && !(v < vw.size() && (vw[v].base || v_tabview[v]))) is_sig[canon(v)] = 1;
     for (size_t i = 0; i < nops; i++) if (keep[i]) {
       for_operands(ops[i], [&](uint32_t v) { if (v != PZK_OPERAND_NONE) uses[v]++; });
       for_defs(ops[i], [&](uint32_t d) { def_op[d] = (uint32_t)i; });
@@ -2151,6 +2826,19 @@ void Compiler::Impl::backend() {
       else if (shift_of(o.a, src, k)) { keep[def_op[o.a]] = 0; o.opc = PZK_U_SHLADD; o.a = o.b; o.b = src; o.imm16 = (uint16_t)k; n_fused++; }
     }
   }
+  // words a signal's export entry reads: itself, the base of its view, or the roots of its table view
+  auto sig_words = [&](uint32_t v, const std::function<void(uint32_t)>& f) {
+    if (v < vw.size() && vw[v].base) { f(canon(vw[v].base)); return; }
+    if (v < v_tabview.size() && v_tabview[v]) {
+      const Table& tb = tables[v_tbl[v]];
+      for (int j = 0; j < tb.n; j++) {
+        uint32_t root = canon(tb.sup[j]);
+        if (vw[root].base && v_def[root] == 0xFFFFFFFFu) f(canon(vw[root].base)); else f(root);
+      }
+      return;
+    }
+    f(canon(v));
+  };
   // ---- segments over kept ops (+ their rows)
   std::vector<uint32_t> def_seg(nv, 0), last_seg(nv, 0), op_seg(nops, 0);
   {
@@ -2158,7 +2846,7 @@ void Compiler::Impl::backend() {
     size_t rp = 0;
     for (size_t i = 0; i < nops; i++) {
       if (!keep[i]) continue;
-      uint64_t need = (ops[i].flags & PZK_FLAG_EXT) ? 2 : 1;
+      uint64_t need = ((ops[i].flags & PZK_FLAG_EXT) ? 2 : 1) + ((ops[i].opc == PZK_V_LUT && (ops[i].flags & PZK_FLAG_W64)) ? 1 : 0);
       size_t q = rp;
       while (q < nrows && row_trigger[row_order[q]] == i) { if (!row_static[row_order[q]]) need += row_recs[row_order[q]]; q++; }
       if (rec && rec + need > opt.seg_ops) { seg++; rec = 0; }
@@ -2177,13 +2865,17 @@ void Compiler::Impl::backend() {
   for (size_t r = 0; r < nrows; r++) {
     if (row_static[r]) continue;
     uint32_t sg = op_seg[row_trigger[r]];
-    uint32_t nt = rows[r].na + rows[r].nb + rows[r].nc;
-    for (uint32_t t = 0; t < nt; t++) {
-      uint32_t sig = terms[rows[r].off + t].first;
-      if (sig == 0xFFFFFFFFu) continue;
-      uint32_t v = sig_val[sig];
-      if (v && last_seg[v] < sg) last_seg[v] = sg;
-    }
+    row_values((uint32_t)r, [&](uint32_t v) { if (last_seg[v] < sg) last_seg[v] = sg; });
+  }
+  // an export entry is read after the segment that defines the last of its words: all of them live until then
+  std::vector<uint32_t> sig_seg(sig_val.size(), 0);
+  for (uint32_t sg_i = 0; sg_i < sig_val.size(); sg_i++) {
+    uint32_t v = sig_val[sg_i];
+    if (!v) continue;
+    uint32_t sg = 0;
+    sig_words(v, [&](uint32_t w) { if (def_seg[w] > sg) sg = def_seg[w]; });
+    sig_words(v, [&](uint32_t w) { if (last_seg[w] < sg) last_seg[w] = sg; });
+    sig_seg[sg_i] = sg;
   }
   // ---- slot allocation (free at segment boundaries)
   v_slot.assign(nv, 0xFFFFFFFFu);
@@ -2248,9 +2940,21 @@ void Compiler::Impl::backend() {
     return (cls << 30) | v_slot[v];
   };
   std::unordered_map<uint64_t, uint32_t> icoef_off;  // int64 coefficient -> list offset
-  std::function<uint32_t(uint32_t)> row_ref;
+  std::function<uint32_t(uint32_t)> row_ref, row_opnd;
   auto emit_row = [&](uint32_t r) {
     std::vector<MT> parts[3];
+    {
+      auto rr = range_rows.find(r);
+      if (rr != range_rows.end()) {  // the row is (word >> bits) == 0
+        uint32_t b = canon(rr->second.base);
+        PzkOp h; h.opc = PZK_CHECK_RANGE; h.flags = (v_cls[b] == CLS_U) ? 0 : PZK_FLAG_NBASE; h.imm16 = rr->second.bits;
+        h.dst = r; h.a = row_opnd(b); h.b = 0;
+        out_ops.push_back(h);
+        n_range_emitted++;
+        check_bytes += (v_cls[b] == CLS_U) ? 8 : 32;
+        return;
+      }
+    }
     if (merge_row(r, parts)) return;
     // classification by compile-time bounds
     bool is_int = true, all32 = true;
@@ -2345,7 +3049,7 @@ void Compiler::Impl::backend() {
       while (rp < nrows && row_trigger[row_order[rp]] == i) {
         uint32_t r = row_order[rp], nt = rows[r].na + rows[r].nb + rows[r].nc;
         if (row_static[r]) { rp++; continue; }
-        for (uint32_t t = 0; t < nt; t++) { uint32_t sig = terms[rows[r].off + t].first; if (sig != 0xFFFFFFFFu && sig_val[sig]) use_cnt[sig_val[sig]]++; }
+        (void)nt; row_values(r, [&](uint32_t v) { use_cnt[v]++; });
         pos++; rp++;
       }
       seg_last_pos[op_seg[i]] = pos;
@@ -2363,7 +3067,7 @@ void Compiler::Impl::backend() {
       while (rp < nrows && row_trigger[row_order[rp]] == i) {
         uint32_t r = row_order[rp], nt = rows[r].na + rows[r].nb + rows[r].nc;
         if (row_static[r]) { rp++; continue; }
-        for (uint32_t t = 0; t < nt; t++) { uint32_t sig = terms[rows[r].off + t].first; if (sig != 0xFFFFFFFFu && sig_val[sig]) { uint32_t v = sig_val[sig]; use_pos[use_off[v] + use_fill[v]++] = pos; } }
+        (void)nt; row_values(r, [&](uint32_t v) { use_pos[use_off[v] + use_fill[v]++] = pos; });
         pos++; rp++;
       }
     }
@@ -2454,13 +3158,14 @@ void Compiler::Impl::backend() {
     return (cls << 30) | v_slot[v];
   };
   row_ref = tref;
+  row_opnd = opnd;
   // values that must always reach their global slot: public wires (read by the export kernel)
-  for (uint32_t sg = 0; sg < sig_val.size(); sg++) if (sig_val[sg] && sig2wire[sg] <= n_pub_out + n_pub_in) needs_global[sig_val[sg]] = 1;
+  for (uint32_t sg = 0; sg < sig_val.size(); sg++) if (sig_val[sg] && sig2wire[sg] <= n_pub_out + n_pub_in) sig_words(sig_val[sg], [&](uint32_t w) { needs_global[w] = 1; });
   for (pass = 0; pass < 2; pass++) {
     // pass 0 learns which values are ever read from their global slot; pass 1 emits
     out_list = list_pool; out_ops.clear(); icoef_off.clear();
     std::fill(use_idx.begin(), use_idx.end(), 0u);
-    cache_hits = cache_miss = 0; n_i64_rows = n_int_rows = n_field_rows = 0; eval_bytes = check_bytes = 0;
+    cache_hits = cache_miss = 0; n_i64_rows = n_int_rows = n_field_rows = 0; eval_bytes = check_bytes = 0; n_range_emitted = 0;
     uint32_t cur = 0xFFFFFFFFu;
     size_t rp = 0;
     uint32_t pos = 0;
@@ -2487,8 +3192,8 @@ void Compiler::Impl::backend() {
           for (uint32_t j = 0; j < cnt; j++) { out_list[o.a + 3 + j] = slot_of(list_pool[o.a + 3 + j]); needs_global[list_pool[o.a + 3 + j]] = 1; }
           break;
         }
-        case PZK_N_BIT: case PZK_F_CSEL: has_dst = true; r.a = opnd(o.a); break;
-        case PZK_U_LUT: case PZK_U_LUTV: has_dst = true; r.a = opnd(o.a); r.b = opnd(o.b); ext_c = opnd(o.c); ext_d = opnd(o.d); break;
+        case PZK_N_BIT: case PZK_F_CSEL: case PZK_U_EXTRACT: case PZK_N_EXTRACT: has_dst = true; r.a = opnd(o.a); break;
+        case PZK_U_LUT: case PZK_U_LUTV: case PZK_V_LUT: has_dst = true; r.a = opnd(o.a); r.b = opnd(o.b); ext_c = opnd(o.c); ext_d = opnd(o.d); break;
         case PZK_U_SEL: case PZK_F_SEL: has_dst = true; r.a = opnd(o.a); r.b = opnd(o.b); ext_c = opnd(o.c); break;
         default:
           has_dst = true; r.a = opnd(o.a);
@@ -2512,10 +3217,15 @@ void Compiler::Impl::backend() {
       }
       out_ops.push_back(r);
       if (o.flags & PZK_FLAG_EXT) {
-        PzkOpExt x; x.c = ext_c; x.d = ext_d; x.e = 0; x.f = 0;
-        if (o.opc == PZK_U_LUTV) x.e = lutv_off[(uint32_t)i];
+        PzkOpExt x; x.c = ext_c; x.d = ext_d; x.e = o.e; x.f = o.f;
+        if (o.opc == PZK_U_LUTV && !opt.views) x.e = lutv_off[(uint32_t)i];
         PzkOp raw; memcpy(&raw, &x, sizeof raw);
         out_ops.push_back(raw);
+        if (o.opc == PZK_V_LUT && (o.flags & PZK_FLAG_W64)) {
+          PzkOpExt y; y.c = o.g; y.d = 0; y.e = 0; y.f = 0;
+          memcpy(&raw, &y, sizeof raw);
+          out_ops.push_back(raw);
+        }
       }
       pos++;
       while (rp < nrows && row_trigger[row_order[rp]] == i) {
@@ -2523,7 +3233,7 @@ void Compiler::Impl::backend() {
         if (row_static[rr]) { rp++; continue; }
         emit_row(rr);
         uint32_t nt = rows[rr].na + rows[rr].nb + rows[rr].nc;
-        for (uint32_t t = 0; t < nt; t++) { uint32_t sig = terms[rows[rr].off + t].first; if (sig != 0xFFFFFFFFu && sig_val[sig]) touch_operand(sig_val[sig], pos, seg_end); }
+        (void)nt; row_values(rr, [&](uint32_t v) { touch_operand(v, pos, seg_end); });
         pos++; rp++;
       }
       segs[s].n_ops = out_ops.size() - segs[s].op_off;
@@ -2537,10 +3247,31 @@ void Compiler::Impl::backend() {
     std::vector<std::vector<PzkExport>> by_seg(segs.size());
     for (uint32_t sig = 0; sig < sig_val.size(); sig++) {
       uint32_t v = sig_val[sig];
-      PzkExport e; e.wire = sig2wire[sig];
+      PzkExport e; e.wire = sig2wire[sig]; e.aux = 0; e.pad = 0;
       if (!v) { e.ref = PZK_REF_ZERO; by_seg[0].push_back(e); continue; }
-      e.ref = ref_of_sig(sig);
-      by_seg[def_seg[v]].push_back(e);
+      if (v < vw.size() && vw[v].base) {
+        const ViewD& d = vw[v];
+        uint32_t b = canon(d.base);
+        e.ref = (3u << 30) | ((v_cls[b] == CLS_U) ? 0u : PZK_REF_VIEW_N) | slot_of(b);
+        e.aux = (uint32_t)d.s | ((uint32_t)d.n << 8) | ((uint32_t)d.k << 16);
+        n_view_sigs++;
+      } else if (v < v_tabview.size() && v_tabview[v]) {
+        const Table& tb = tables[v_tbl[v]];
+        e.ref = PZK_REF_TABVIEW; e.aux = (uint32_t)out_list.size();
+        out_list.push_back(tb.n);
+        for (int j = 0; j < tb.n; j++) {
+          uint32_t root = canon(tb.sup[j]);
+          if (vw[root].base && v_def[root] == 0xFFFFFFFFu) { out_list.push_back(slot_of(canon(vw[root].base))); out_list.push_back(vw[root].s); }
+          else { out_list.push_back(slot_of(root)); out_list.push_back(0); }
+        }
+        for (int k = 0; k < (1 << tb.n); k++) { uint64_t x = (uint64_t)tb.e[k]; out_list.push_back((uint32_t)x); out_list.push_back((uint32_t)(x >> 32)); }
+        n_tabview_sigs++;
+      } else {
+        uint32_t cv = canon(v);
+        uint32_t cls = v_cls[cv] == CLS_U ? 0u : (v_cls[cv] == CLS_I ? 1u : 2u);
+        e.ref = (cls << 30) | slot_of(cv);
+      }
+      by_seg[sig_seg[sig]].push_back(e);
     }
     for (size_t s = 0; s < segs.size(); s++) {
       segs[s].exp_off = out_exports.size();
@@ -2591,7 +3322,7 @@ void Compiler::Impl::build_meta() {
        ",\"f_inv\":" + std::to_string(stats->f_inv) + ",\"f_inv_real\":" + std::to_string(stats->f_inv_real) + ",\"f_other\":" + std::to_string(stats->f_other) +
        ",\"bigdiv\":" + std::to_string(stats->bigdiv) + ",\"modinv\":" + std::to_string(stats->modinv) + ",\"lut\":" + std::to_string(stats->lut) +
        ",\"op_records\":" + std::to_string(out_ops.size()) + ",\"segments\":" + std::to_string(segs.size()) +
-       ",\"static_rows\":" + std::to_string(n_static_rows) + ",\"def_rows\":" + std::to_string(n_def_rows) + ",\"table_rows\":" + std::to_string(n_table_rows) + ",\"symbolic_rows\":" + std::to_string(n_symbolic_rows) + ",\"fused_shladd\":" + std::to_string(n_fused) + ",\"i64_rows\":" + std::to_string(n_i64_rows) +
+       ",\"static_rows\":" + std::to_string(n_static_rows) + ",\"def_rows\":" + std::to_string(n_def_rows) + ",\"table_rows\":" + std::to_string(n_table_rows) + ",\"symbolic_rows\":" + std::to_string(n_symbolic_rows) + ",\"view_rows\":" + std::to_string(n_view_rows) + ",\"range_rows\":" + std::to_string(n_range_rows) + ",\"vlut\":" + std::to_string(n_vlut) + ",\"vlut_lanes\":" + std::to_string(n_vlut_lanes) + ",\"view_signals\":" + std::to_string(n_view_sigs) + ",\"tabview_signals\":" + std::to_string(n_tabview_sigs) + ",\"extracts\":" + std::to_string(n_extracts) + ",\"fused_shladd\":" + std::to_string(n_fused) + ",\"i64_rows\":" + std::to_string(n_i64_rows) +
        ",\"int_rows\":" + std::to_string(n_int_rows) + ",\"field_rows\":" + std::to_string(n_field_rows) +
        ",\"eval_bytes\":" + std::to_string(eval_bytes) + ",\"check_bytes\":" + std::to_string(check_bytes) +
        ",\"cells\":" + std::to_string(opt.cells) + ",\"cache_hit_refs\":" + std::to_string(cache_hit_refs) +

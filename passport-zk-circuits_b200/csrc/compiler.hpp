@@ -93,6 +93,15 @@ struct OpRec {
   uint8_t opc, flags;
   uint16_t imm16;
   uint32_t dst, a, b, c, d;
+  uint32_t e = 0, f = 0;  // extension words: LUTV list offset / LUT bit positions, V_LUT rotations / lane mask
+  uint32_t g = 0;         // V_LUT: lane mask high (64-lane groups)
+};
+
+// A value that is a bit field of a word the program computes anyway:
+//   value = ((base >> s) & (2^n - 1)) << k          (base: a U word or a plain 256-bit N value)
+struct ViewD {
+  uint32_t base = 0;  // value id of the word (0 = not a view)
+  uint8_t s = 0, n = 0, k = 0;
 };
 
 enum { CLS_U = 0, CLS_I = 1, CLS_F = 2, CLS_N = 3 };
@@ -107,6 +116,8 @@ struct CompileOptions {
   bool symbolic_rows_static = true;  // prove rows by expanding their wires through the defining ops
   bool fuse_shladd = true;  // x + z * 2^k with a single-use product -> one U_SHLADD record
   bool def_rows_static = false;  // discharge the rows of `x <== e` (they hold by construction) at compile time
+  bool views = true;     // bit-field views + bit-view row proofs (Num2Bits / GetLastNBits / running sums cost no ops)
+  bool vectorize = true; // pack one-bit truth-table ops over rotated words into V_LUT records (needs views)
 };
 
 struct CompileStats {

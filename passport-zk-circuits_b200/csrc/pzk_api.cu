@@ -118,6 +118,8 @@ int pzk_compile_ex(const char* main_circom_path, const char* out_prefix, const c
     opt.intrinsics = (flags & PZK_COMPILE_NO_INTRINSICS) == 0;
     opt.table_rows_static = (flags & PZK_COMPILE_NO_TABLE_PROOFS) == 0;
     opt.symbolic_rows_static = (flags & PZK_COMPILE_NO_TABLE_PROOFS) == 0;
+    opt.views = (flags & (PZK_COMPILE_NO_VIEWS | PZK_COMPILE_NO_TABLE_PROOFS)) == 0;
+    opt.vectorize = opt.views && (flags & PZK_COMPILE_NO_VECTORIZE) == 0;
     pzk::Compiler cc(main_circom_path, opt);
     cc.run();
     std::string p = out_prefix;
@@ -403,6 +405,7 @@ static int run_batch(pzk_circuit* c, int check_rows, const uint64_t* export_lane
       }
       if (!c->seg[s].pub.empty()) {
         ExportParams p;
+        p.list = c->d_list;
         p.entries = c->d_pub_entries + c->seg[s].pub_off; p.n_entries = c->seg[s].pub.size();
         p.n_u_slots = c->h.n_u_slots; p.n_f_slots = c->h.n_f_slots;
         p.U = c->d_U; p.F = c->d_F; p.L = L; p.lanes = nullptr; p.lane_base = base; p.n_rows = n;
@@ -415,6 +418,7 @@ static int run_batch(pzk_circuit* c, int check_rows, const uint64_t* export_lane
         // rows of d_witnesses are indexed by position in export_lanes: handle each contiguous run
         for (size_t q = 0; q < tile_lanes.size(); q++) {
           ExportParams p;
+          p.list = c->d_list;
           p.entries = c->d_exports + sg.exp_off; p.n_entries = sg.n_exp;
           p.n_u_slots = c->h.n_u_slots; p.n_f_slots = c->h.n_f_slots;
           p.U = c->d_U; p.F = c->d_F; p.L = L; p.lanes = d_lane_list + q; p.lane_base = tile_rows[q]; p.n_rows = 1;

@@ -377,6 +377,46 @@ __device__ __noinline__ bool check_row_field(const StreamCoefs sc, const uint4* 
   return fr_eq(ab, c);
 }
 
+
+// ---- packed truth table (PZK_V_LUT): one record computes 32 / 64 one-bit signals --------------------
+// r bit l = T >> (x0_l | x1_l << 1 | x2_l << 2 | x3_l << 3) & 1.  T is warp-uniform, so the masks of the
+// multiplexer tree are uniform values; level 1 folds x0 into the 8 pairs of table bits, levels 2..4 are
+// one LOP3 (bit select) each.  XOR3 / XOR2 / AND2 - the sigma and carry-free sums of SHA - leave early.
+template <typename W>
+__device__ __forceinline__ W vlut_eval(u32 T, W x0, W x1, W x2, W x3) {
+  if (T == 0x9696u) return x0 ^ x1 ^ x2;
+  if (T == 0x6666u) return x0 ^ x1;
+  if (T == 0x8888u) return x0 & x1;
+  W g[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const W m0 = (W)0 - (W)((T >> (2 * k)) & 1u), m1 = (W)0 - (W)((T >> (2 * k + 1)) & 1u);
+    g[k] = m0 ^ (x0 & (m0 ^ m1));
+  }
+#pragma unroll
+  for (int k = 0; k < 4; k++) g[k] = g[2 * k] ^ (x1 & (g[2 * k] ^ g[2 * k + 1]));
+#pragma unroll
+  for (int k = 0; k < 2; k++) g[k] = g[2 * k] ^ (x2 & (g[2 * k] ^ g[2 * k + 1]));
+  return g[0] ^ (x3 & (g[0] ^ g[1]));
+}
+__device__ __forceinline__ u32 rotr32(u32 v, u32 r) { return __funnelshift_r(v, v, r); }
+__device__ __forceinline__ u64 rotr64(u64 v, u32 r) { return r ? ((v >> r) | (v << (64 - r))) : v; }
+
+// bit field of a plain 256-bit value / a word: ((v >> s) & (2^n - 1)) << k  (views, pzk_program.h)
+__device__ __forceinline__ void field256(u64* r, const u64* v, unsigned s, unsigned n, unsigned k) {
+  u64 t[4];
+  shr256(t, v, s);
+  if (n < 256) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int lo = 64 * i;
+      const u64 m = (int)n >= lo + 64 ? ~0ull : ((int)n <= lo ? 0ull : ((1ull << (n - lo)) - 1));
+      t[i] &= m;
+    }
+  }
+  shl256(r, t, k);
+}
+
 __global__ void __launch_bounds__(128, 8) eval_kernel(EvalParams p) {
   extern __shared__ u64 cell_mem[];
   const u64 lane = (u64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -444,13 +484,59 @@ __global__ void __launch_bounds__(128, 8) eval_kernel(EvalParams p) {
       case PZK_U_SEL: { FETCH_EXT(); STD(dst, LDO(a) ? LDO(b) : LDO(x.x)); break; }
       case PZK_U_LUT: case PZK_U_LUTV: {
         FETCH_EXT();
+        // operand j contributes bit (x.w >> 8j) & 255 of its word (0 for plain one-bit values)
         u32 idx = 0;
-        if (a != PZK_OPERAND_NONE) idx |= (u32)(LDO(a) & 1);
-        if (b != PZK_OPERAND_NONE) idx |= (u32)(LDO(b) & 1) << 1;
-        if (x.x != PZK_OPERAND_NONE) idx |= (u32)(LDO(x.x) & 1) << 2;
-        if (x.y != PZK_OPERAND_NONE) idx |= (u32)(LDO(x.y) & 1) << 3;
+        if (a != PZK_OPERAND_NONE) idx |= (u32)((LDO(a) >> (x.w & 255u)) & 1);
+        if (b != PZK_OPERAND_NONE) idx |= (u32)((LDO(b) >> ((x.w >> 8) & 255u)) & 1) << 1;
+        if (x.x != PZK_OPERAND_NONE) idx |= (u32)((LDO(x.x) >> ((x.w >> 16) & 255u)) & 1) << 2;
+        if (x.y != PZK_OPERAND_NONE) idx |= (u32)((LDO(x.y) >> (x.w >> 24)) & 1) << 3;
         if (opc == PZK_U_LUT) STD(dst, (u64)((imm16 >> idx) & 1));
         else STD(dst, (u64)__ldg(list + x.z + 2 * idx) | ((u64)__ldg(list + x.z + 2 * idx + 1) << 32));
+        break;
+      }
+      case PZK_V_LUT: {
+        FETCH_EXT();  // {c, d, rotations, lane mask low}
+        const u32 rot = x.z;
+        if (flags & PZK_FLAG_W64) {
+          const uint4 y = __ldg(ops + (++pc));
+          const u64 lanes = (u64)x.w | ((u64)y.x << 32);
+          const u64 x0 = rotr64(LDO(a), rot & 255u);
+          const u64 x1 = b != PZK_OPERAND_NONE ? rotr64(LDO(b), (rot >> 8) & 255u) : 0;
+          const u64 x2 = x.x != PZK_OPERAND_NONE ? rotr64(LDO(x.x), (rot >> 16) & 255u) : 0;
+          const u64 x3 = x.y != PZK_OPERAND_NONE ? rotr64(LDO(x.y), rot >> 24) : 0;
+          STD(dst, vlut_eval<u64>(imm16, x0, x1, x2, x3) & lanes);
+        } else {
+          const u32 x0 = rotr32((u32)LDO(a), rot & 255u);
+          const u32 x1 = b != PZK_OPERAND_NONE ? rotr32((u32)LDO(b), (rot >> 8) & 255u) : 0;
+          const u32 x2 = x.x != PZK_OPERAND_NONE ? rotr32((u32)LDO(x.x), (rot >> 16) & 255u) : 0;
+          const u32 x3 = x.y != PZK_OPERAND_NONE ? rotr32((u32)LDO(x.y), rot >> 24) : 0;
+          STD(dst, (u64)(vlut_eval<u32>(imm16, x0, x1, x2, x3) & x.w));
+        }
+        break;
+      }
+      case PZK_U_EXTRACT: {
+        const u32 s_ = imm16 & 255u, k_ = imm16 >> 8, n_ = b;
+        u64 v;
+        if (flags & PZK_FLAG_NBASE) { u64 t[4], r[4]; LDFA(t); field256(r, t, s_, n_, k_); v = r[0]; }
+        else { v = LDO(a) >> s_; if (n_ < 64) v &= (1ull << n_) - 1; v <<= k_; }
+        STD(dst, v);
+        break;
+      }
+      case PZK_N_EXTRACT: {
+        const u32 s_ = imm16 & 255u, k_ = imm16 >> 8, n_ = b;
+        u64 t[4] = {0, 0, 0, 0}, r[4];
+        if (flags & PZK_FLAG_NBASE) LDFA(t); else t[0] = LDO(a);
+        field256(r, t, s_, n_, k_);
+        STFD(r);
+        break;
+      }
+      case PZK_CHECK_RANGE: {
+        if (check_rows) {
+          bool ok;
+          if (flags & PZK_FLAG_NBASE) { u64 t[4], r[4]; LDFA(t); shr256(r, t, imm16); ok = (r[0] | r[1] | r[2] | r[3]) == 0; }
+          else ok = imm16 >= 64 || (LDO(a) >> imm16) == 0;
+          if (!ok && (unsigned long long)dst < bad) bad = dst;
+        }
         break;
       }
       case PZK_F_CONST: { u64 v[4]; ldPool(fpool, a, v); STFD(v); break; }
@@ -603,6 +689,7 @@ __global__ void __launch_bounds__(128, 8) eval_kernel(EvalParams p) {
 // grid.x covers lanes (fast, coalesced plane reads), grid.y strides over entries.
 // ------------------------------------------------------------------------------------------
 struct ExportParams {
+  const u32* list;           // list pool (table-view descriptors)
   u32 n_u_slots, n_f_slots;  // blocked planes (0 = flat layout with stride L)
   const PzkExport* entries;
   u64 n_entries;
@@ -617,28 +704,47 @@ struct ExportParams {
   u32 wire_off;      // out index = wire - wire_off
 };
 
+
+// one export entry of one lane -> canonical value (wire <- slot, or wire <- view of words; pzk_program.h)
+__device__ __forceinline__ void export_value(const ExportParams& p, const uint4 ew, u64 lane, u64* w) {
+  const u32 ref = ew.y, aux = ew.z;
+  w[0] = w[1] = w[2] = w[3] = 0;
+  if (ref == PZK_REF_ZERO) return;
+  if (ref == PZK_REF_ONE) { w[0] = 1; return; }
+  const u64* Ub = p.U + (lane / PZK_LANE_BLOCK) * p.n_u_slots * PZK_LANE_BLOCK + (lane % PZK_LANE_BLOCK);
+  const u64* Fb = p.F + (lane / PZK_LANE_BLOCK) * p.n_f_slots * 4 * PZK_LANE_BLOCK + (lane % PZK_LANE_BLOCK);
+  if (ref == PZK_REF_TABVIEW) {
+    const u32* Lp = p.list + aux;
+    const u32 n = __ldg(Lp);
+    u32 idx = 0;
+    for (u32 j = 0; j < n; j++) idx |= (u32)((Ub[(u64)__ldg(Lp + 1 + 2 * j) * PZK_LANE_BLOCK] >> __ldg(Lp + 2 + 2 * j)) & 1) << j;
+    const long long v = (long long)((u64)__ldg(Lp + 1 + 2 * n + 2 * idx) | ((u64)__ldg(Lp + 2 + 2 * n + 2 * idx) << 32));
+    if (v < 0) { const u64 pp[4] = {P0, P1, P2, P3}; u64 m[4] = {(u64)(-v), 0, 0, 0}; sub256(w, pp, m); } else w[0] = (u64)v;
+    return;
+  }
+  const u32 cls = PZK_REF_CLS(ref), slot = PZK_REF_SLOT(ref);
+  if (cls == 3) {
+    const u32 s_ = aux & 255u, n_ = (aux >> 8) & 255u, k_ = (aux >> 16) & 255u;
+    u64 t[4] = {0, 0, 0, 0};
+    if (ref & PZK_REF_VIEW_N) ldF(Fb, PZK_LANE_BLOCK, slot, t); else t[0] = Ub[(u64)slot * PZK_LANE_BLOCK];
+    field256(w, t, s_, n_, k_);
+  } else if (cls == 2) { u64 m[4]; ldF(Fb, PZK_LANE_BLOCK, slot, m); fr_from_mont(w, m); }
+  else {
+    const u64 v = Ub[(u64)slot * PZK_LANE_BLOCK];
+    if (cls == 1 && (long long)v < 0) { const u64 pp[4] = {P0, P1, P2, P3}; u64 m[4] = {(u64)(-(long long)v), 0, 0, 0}; sub256(w, pp, m); }
+    else w[0] = v;
+  }
+}
+
 __global__ void __launch_bounds__(128) export_kernel(ExportParams p) {
   const u64 row = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= p.n_rows) return;
   const u64 lane = p.lanes ? p.lanes[row] : row;
-  const u64 L = p.L;
   for (u64 e = blockIdx.y; e < p.n_entries; e += gridDim.y) {
-    const uint2 ew = __ldg(reinterpret_cast<const uint2*>(p.entries + e));
-    const u32 wire = ew.x, ref = ew.y;
-    u64 w[4] = {0, 0, 0, 0};
-    if (ref == PZK_REF_ONE) w[0] = 1;
-    else if (ref != PZK_REF_ZERO) {
-      const u32 cls = PZK_REF_CLS(ref), slot = PZK_REF_SLOT(ref);
-      const u64* Ub = p.U + (lane / PZK_LANE_BLOCK) * p.n_u_slots * PZK_LANE_BLOCK + (lane % PZK_LANE_BLOCK);
-      const u64* Fb = p.F + (lane / PZK_LANE_BLOCK) * p.n_f_slots * 4 * PZK_LANE_BLOCK + (lane % PZK_LANE_BLOCK);
-      if (cls == 2) { u64 m[4]; ldF(Fb, PZK_LANE_BLOCK, slot, m); fr_from_mont(w, m); }
-      else {
-        u64 v = Ub[(u64)slot * PZK_LANE_BLOCK];
-        if (cls == 1 && (long long)v < 0) { const u64 pp[4] = {P0, P1, P2, P3}; u64 m[4] = {(u64)(-(long long)v), 0, 0, 0}; sub256(w, pp, m); }
-        else w[0] = v;
-      }
-    }
-    u64* dst = p.out + ((p.lane_base + row) * p.out_wires + (wire - p.wire_off)) * 4;
+    const uint4 ew = __ldg(reinterpret_cast<const uint4*>(p.entries + e));
+    u64 w[4];
+    export_value(p, ew, lane, w);
+    u64* dst = p.out + ((p.lane_base + row) * p.out_wires + (ew.x - p.wire_off)) * 4;
     reinterpret_cast<ulonglong2*>(dst)[0] = make_ulonglong2(w[0], w[1]);
     reinterpret_cast<ulonglong2*>(dst)[1] = make_ulonglong2(w[2], w[3]);
   }
@@ -647,24 +753,11 @@ __global__ void __launch_bounds__(128) export_kernel(ExportParams p) {
 // one lane, threads over the entries of a segment (full-witness export of selected lanes)
 __global__ void __launch_bounds__(128) export_rows_kernel(ExportParams p) {
   const u64 lane = p.lanes[0];
-  const u64 L = p.L;
   for (u64 e = (u64)blockIdx.x * blockDim.x + threadIdx.x; e < p.n_entries; e += (u64)gridDim.x * blockDim.x) {
-    const uint2 ew = __ldg(reinterpret_cast<const uint2*>(p.entries + e));
-    const u32 wire = ew.x, ref = ew.y;
-    u64 w[4] = {0, 0, 0, 0};
-    if (ref == PZK_REF_ONE) w[0] = 1;
-    else if (ref != PZK_REF_ZERO) {
-      const u32 cls = PZK_REF_CLS(ref), slot = PZK_REF_SLOT(ref);
-      const u64* Ub = p.U + (lane / PZK_LANE_BLOCK) * p.n_u_slots * PZK_LANE_BLOCK + (lane % PZK_LANE_BLOCK);
-      const u64* Fb = p.F + (lane / PZK_LANE_BLOCK) * p.n_f_slots * 4 * PZK_LANE_BLOCK + (lane % PZK_LANE_BLOCK);
-      if (cls == 2) { u64 m[4]; ldF(Fb, PZK_LANE_BLOCK, slot, m); fr_from_mont(w, m); }
-      else {
-        u64 v = Ub[(u64)slot * PZK_LANE_BLOCK];
-        if (cls == 1 && (long long)v < 0) { const u64 pp[4] = {P0, P1, P2, P3}; u64 m[4] = {(u64)(-(long long)v), 0, 0, 0}; sub256(w, pp, m); }
-        else w[0] = v;
-      }
-    }
-    u64* dst = p.out + (p.lane_base * p.out_wires + (wire - p.wire_off)) * 4;
+    const uint4 ew = __ldg(reinterpret_cast<const uint4*>(p.entries + e));
+    u64 w[4];
+    export_value(p, ew, lane, w);
+    u64* dst = p.out + (p.lane_base * p.out_wires + (ew.x - p.wire_off)) * 4;
     reinterpret_cast<ulonglong2*>(dst)[0] = make_ulonglong2(w[0], w[1]);
     reinterpret_cast<ulonglong2*>(dst)[1] = make_ulonglong2(w[2], w[3]);
   }

@@ -18,8 +18,10 @@ int main(int argc, char** argv) {
     else if (!strcmp(argv[i], "--cells") && i + 1 < argc) opt.cells = (uint32_t)atoi(argv[++i]);
     else if (!strcmp(argv[i], "--no-intrinsics")) opt.intrinsics = false;
     else if (!strcmp(argv[i], "--static-def-rows")) opt.def_rows_static = true;
-    else if (!strcmp(argv[i], "--no-table-proofs")) opt.table_rows_static = false;
+    else if (!strcmp(argv[i], "--no-table-proofs")) { opt.table_rows_static = false; opt.views = false; opt.vectorize = false; }
     else if (!strcmp(argv[i], "--no-symbolic-proofs")) opt.symbolic_rows_static = false;
+    else if (!strcmp(argv[i], "--no-views")) { opt.views = false; opt.vectorize = false; }
+    else if (!strcmp(argv[i], "--no-vectorize")) opt.vectorize = false;
     else { fprintf(stderr, "unknown option %s\n", argv[i]); return 2; }
   }
   try {

@@ -128,11 +128,11 @@ REGISTER_IDENTITY_BITS = {"dg1": 1, "dg15": 1, "encapsulatedContent": 1, "signed
                           "pubkey": 64, "signature": 64}
 
 
-COMPILE_STATIC_DEF_ROWS, COMPILE_NO_INTRINSICS, COMPILE_NO_TABLE_PROOFS = 1, 2, 4
+COMPILE_STATIC_DEF_ROWS, COMPILE_NO_INTRINSICS, COMPILE_NO_TABLE_PROOFS, COMPILE_NO_VIEWS, COMPILE_NO_VECTORIZE = 1, 2, 4, 8, 16
 
 
 def compile_circuit(main_path, out_prefix, input_bits=None, segment_ops=0, static_def_rows=False, intrinsics=True,
-                    table_proofs=True):
+                    table_proofs=True, views=True, vectorize=True):
     """circom -> program (.pzkp) + .r1cs + .sym; the role of
     `circom <file> --r1cs --wasm --sym` (/root/reference/circuits/scripts/compile-circuit.sh:34)."""
     L = lib()
@@ -142,7 +142,8 @@ def compile_circuit(main_path, out_prefix, input_bits=None, segment_ops=0, stati
     err = ctypes.create_string_buffer(4096)
     os.makedirs(os.path.dirname(os.path.abspath(out_prefix)), exist_ok=True)
     flags = ((COMPILE_STATIC_DEF_ROWS if static_def_rows else 0) | (0 if intrinsics else COMPILE_NO_INTRINSICS) |
-             (0 if table_proofs else COMPILE_NO_TABLE_PROOFS))
+             (0 if table_proofs else COMPILE_NO_TABLE_PROOFS) | (0 if views else COMPILE_NO_VIEWS) |
+             (0 if vectorize else COMPILE_NO_VECTORIZE))
     rc = L.pzk_compile_ex(os.fsencode(main_path), os.fsencode(out_prefix), names, widths, len(input_bits),
                           segment_ops, flags, err, len(err))
     if rc != 0:

@@ -174,6 +174,7 @@ def test_statically_discharged_rows_never_fail(artifacts_dir, name):
     st_ = prog.meta["stats"]
     assert int((kinds == 1).sum()) == st_["static_rows"] and int((kinds == 2).sum()) == st_["table_rows"]
     assert int((kinds == 3).sum()) == st_["symbolic_rows"] and int((kinds == 4).sum()) == 0
+    assert int((kinds == 5).sum()) == st_["view_rows"]
     n_lanes = 3 if prog.n_constraints > 50000 else 12
     inp = random_inputs(prog.meta, n_lanes, 77, field_bits=253)
     seen_fail = 0
