@@ -79,6 +79,14 @@ enum PzkOpcode {
   PZK_F_NE = 33,
   PZK_F_CSEL = 34,   /* dst = fpool[b + a(U)]                                 */
   PZK_F_FROM_I = 35, /* dst = Montgomery(a) for a signed 64-bit a             */
+  PZK_BJJ_MUL8 = 37,  /* hint intrinsic for BabyjubjubBase8Multiplication
+                         (/root/reference/circuits/lib/circuits/babyjubjub/curve.circom:143-171): the outputs of its
+                         2n - 1 BabyjubjubAdd instances (n = 254 scalar bits, MSB first: one doubling and one addition
+                         per bit, `(0,0)` standing for "no point" exactly as addZeroBabyjub does, :19-58) computed in
+                         projective coordinates with ONE field inversion instead of two per addition.  They only
+                         replace the `<--` hints of BabyjubjubAdd (:97,101); the rows `(1 + d tau) out === ...` are
+                         still checked.  list = {n, pool a, pool d, pool Bx, pool By, scalar (F), out[2(2n-1)],
+                         scratch[2(2n-1)]}                                                                        */
   PZK_CHECK_RANGE = 36, /* constraint row reduced to a range check by the bit-view prover: row dst (.r1cs index)
                            holds iff (a >> imm16) == 0; a is a U word or (PZK_FLAG_NBASE) a plain 256-bit value   */
   /* N class (plain 256-bit integers held in F slots) */
@@ -151,6 +159,7 @@ typedef struct PzkOpExt {
 #define PZK_LANE_CONSTRAINT 2u   /* some R1CS row failed ("Assert Failed.")      */
 #define PZK_LANE_INPUT_RANGE 4u  /* input outside the declared range / >= p     */
 #define PZK_LANE_BIGDIV_PRE 8u   /* long_div precondition violated (top limb 0) */
+#define PZK_LANE_HINT 16u        /* a hint intrinsic met a zero denominator (BJJ_MUL8; unreachable on curve points) */
 
 /* ---- constraint rows (slot addressed, per segment) ---------------------- */
 /* term.ref : bits 30..31 = class (0 = U unsigned, 1 = I signed 64, 2 = F Montgomery),

@@ -448,6 +448,47 @@ uint32_t pzk_ref_witness(const PzkRefProgram* p, const uint8_t* inputs, uint8_t*
           for (unsigned i = 0; i < k; i++) U[L[3 + k + k + 1 + i]] = r[i];
           break;
         }
+        case PZK_BJJ_MUL8: {
+          /* hints of BabyjubjubBase8Multiplication as the reference computes them: affine BabyjubjubAdd
+           * (/root/reference/circuits/lib/circuits/babyjubjub/curve.circom:71-105) with two field divisions each,
+           * x / 0 = 0, chained through addZeroBabyjub's selection (:19-58) - deliberately NOT the projective
+           * ladder + batched inversion of the device */
+          const uint32_t* L = p->list + o->a;
+          unsigned n = L[0];
+          const uint64_t *ca = p->fpool + 4 * (uint64_t)L[1], *cd = p->fpool + 4 * (uint64_t)L[2];
+          const uint64_t *bx = p->fpool + 4 * (uint64_t)L[3], *by = p->fpool + 4 * (uint64_t)L[4];
+          const uint32_t* out = L + 6;
+          uint64_t sc[4], one[4], S[2][4] = {{0}}, D[2][4], Q[2][4], A[2][4];
+          from_mont(sc, F + 4 * (uint64_t)L[5]);
+          to_mont(one, ONE);
+          unsigned k = 0;
+          for (unsigned i = 0; i < n; i++) {
+            for (int pass = (i > 0 ? 0 : 1); pass < 2; pass++) {
+              const uint64_t (*P1)[4] = pass == 0 ? S : D;
+              const uint64_t (*P2)[4] = pass == 0 ? S : Q;
+              if (pass == 1) {
+                unsigned bi = n - 1 - i;
+                int bit = (int)((sc[bi >> 6] >> (bi & 63)) & 1);
+                memset(Q, 0, sizeof Q);
+                if (bit) { memcpy(Q[0], bx, 32); memcpy(Q[1], by, 32); }
+                if (i == 0) memset(D, 0, sizeof D);
+              }
+              uint64_t beta[4], gamma[4], delta[4], tau[4], t[4], u[4], den[4], num[4], r0[4], r1[4];
+              fmul(beta, P1[0], P2[1]); fmul(gamma, P1[1], P2[0]);
+              fmul(t, P1[0], ca); fsub(t, P1[1], t); fadd(u, P2[0], P2[1]); fmul(delta, t, u);
+              fmul(tau, beta, gamma);
+              fmul(t, tau, cd);
+              fadd(den, one, t); finv(den, den); fadd(num, beta, gamma); fmul(r0, num, den);
+              fsub(den, one, t); finv(den, den); fmul(u, beta, ca); fadd(num, delta, u); fsub(num, num, gamma); fmul(r1, num, den);
+              memcpy(F + 4 * (uint64_t)out[2 * k], r0, 32); memcpy(F + 4 * (uint64_t)out[2 * k + 1], r1, 32);
+              k++;
+              if (pass == 0) { memcpy(D[0], r0, 32); memcpy(D[1], r1, 32); } else { memcpy(A[0], r0, 32); memcpy(A[1], r1, 32); }
+            }
+            int zd = is_zero4(D[0]), zq = is_zero4(Q[0]);
+            memcpy(S, zd ? Q : (zq ? D : A), sizeof S);
+          }
+          break;
+        }
         case PZK_CHECK_I64: case PZK_CHECK_INT: case PZK_CHECK_F: {
           /* a constraint row fused into the op stream: A.w * B.w == C.w, checked here with
            * the generic field arithmetic for both kinds (the integer fast path is a device-side

@@ -212,9 +212,16 @@ struct Compiler::Impl {
   std::vector<std::pair<uint32_t, uint32_t>> deferred_lutv;
   uint32_t pending_lutv_off = 0;
   bool flushing = false;
-  static const size_t INV_BATCH = 8;
+  static const size_t INV_BATCH = 48;
+  // macro ops (long_div, mod_inv, the BabyJubjub ladder) read and write their values through the list pool
+  static bool is_macro(int opc) { return opc == PZK_BIGDIV || opc == PZK_MODINV || opc == PZK_BJJ_MUL8; }
+  void macro_layout(const OpRec& o, uint32_t& op0, uint32_t& nop, uint32_t& def0, uint32_t& ndef) const {
+    if (o.opc == PZK_BJJ_MUL8) { op0 = o.a + 5; nop = 1; def0 = o.a + 6; ndef = 4 * (2 * list_pool[o.a] - 1); return; }
+    uint32_t k = list_pool[o.a + 1], m = list_pool[o.a + 2];
+    op0 = o.a + 3; nop = k + m + k; def0 = op0 + nop; ndef = m + 1 + k;
+  }
   bool op_reads_values(int opc) {
-    switch (opc) { case PZK_NOP: case PZK_U_CONST: case PZK_F_CONST: case PZK_IN_U: case PZK_IN_F: case PZK_BIGDIV: case PZK_MODINV: return false; }
+    switch (opc) { case PZK_NOP: case PZK_U_CONST: case PZK_F_CONST: case PZK_IN_U: case PZK_IN_F: case PZK_BIGDIV: case PZK_MODINV: case PZK_BJJ_MUL8: return false; }
     return true;
   }
   bool is_pending(uint32_t v) { return v != PZK_OPERAND_NONE && v < v_pending.size() && v_pending[v]; }
@@ -243,7 +250,7 @@ struct Compiler::Impl {
     }
     OpRec o; o.opc = (uint8_t)opc; o.flags = (uint8_t)flags; o.imm16 = (uint16_t)imm16;
     o.dst = dst; o.a = a; o.b = b; o.c = c; o.d = d;
-    if (dst && opc != PZK_ASSERT_NZ && opc != PZK_BIGDIV && opc != PZK_MODINV && dst < v_def.size()) v_def[dst] = (uint32_t)ops.size();
+    if (dst && opc != PZK_ASSERT_NZ && !is_macro(opc) && dst < v_def.size()) v_def[dst] = (uint32_t)ops.size();
     ops.push_back(o);
     if (op_stats) op_tag.push_back(cur_tname);
     return dst;
@@ -308,7 +315,7 @@ struct Compiler::Impl {
     size_t li = 0;
     for (size_t k = 0; k < dq.size(); k++) {
       const OpRec& o = dq[k];
-      if (o.dst && o.opc != PZK_ASSERT_NZ && o.opc != PZK_BIGDIV && o.opc != PZK_MODINV && o.dst < v_def.size()) v_def[o.dst] = (uint32_t)ops.size();
+      if (o.dst && o.opc != PZK_ASSERT_NZ && !is_macro(o.opc) && o.dst < v_def.size()) v_def[o.dst] = (uint32_t)ops.size();
       ops.push_back(o);
       if (op_stats) op_tag.push_back(cur_tname);
       if (li < lq.size() && lq[li].first == k) { lutv_off[(uint32_t)ops.size() - 1] = lq[li].second; li++; }
@@ -1170,9 +1177,59 @@ struct Compiler::Impl {
     Ctx ctx; ctx.lay = comp->lay; ctx.comp = comp;
     bool sr = returned; returned = false;
     int saved_t = cur_tname; cur_tname = comp->lay->tname;
+    bool hinted = phase == 1 && opt.intrinsics && try_bjj_hints(comp);
     exec(td.body, env, &ctx);
+    if (hinted) {
+      if (hint_stack.back().next != hint_stack.back().vals.size()) fail(at, "internal: BabyJubjub hint count does not match the template");
+      hint_stack.pop_back();
+    }
     cur_tname = saved_t;
     returned = sr;
+  }
+
+  // BabyjubjubBase8Multiplication (/root/reference/circuits/lib/circuits/babyjubjub/curve.circom:143-171): 507
+  // BabyjubjubAdd instances in one dependent chain, each with two `<--` field divisions (:97,101).  The BJJ_MUL8
+  // record computes all their outputs first (projective ladder + one batched inversion on the device); the template
+  // body then runs as written, except that those two hints take the precomputed values instead of dividing.  Every
+  // constraint of the template is still emitted and checked, so a wrong hint could only fail a row, never pass.
+  struct HintCtx { std::vector<uint32_t> vals; size_t next = 0; };
+  std::vector<HintCtx> hint_stack;
+  int id_bjj_mul8 = -2, id_bjj_add = -2, id_sig_out = -2, id_sig_scalar = -2;
+  bool try_bjj_hints(Comp* comp) {
+    if (id_bjj_mul8 == -2) {
+      id_bjj_mul8 = unit.names.get("BabyjubjubBase8Multiplication"); id_bjj_add = unit.names.get("BabyjubjubAdd");
+      id_sig_out = unit.names.get("out"); id_sig_scalar = unit.names.get("scalar");
+    }
+    if (comp->lay->tname != id_bjj_mul8) return false;
+    auto si = comp->lay->sigs.find(id_sig_scalar);
+    if (si == comp->lay->sigs.end() || si->second.kind != 1 || !si->second.dims.empty()) return false;
+    uint32_t vid = sig_val[comp->base + si->second.off];
+    if (!vid || v_const[vid]) return false;
+    uint32_t sf = to_F(sv(vid));
+    if (is_pending(sf)) flush_inversions();
+    const uint32_t nbits = 254, nadd = 2 * nbits - 1;
+    // curve constants of the template family (curve.circom:84-85, get.circom:9-10)
+    auto dec = [](const char* t) { return parse_number(t, strlen(t)); };
+    U256 ca = dec("168700"), cd = dec("168696");
+    U256 bx = dec("5299619240641551281634865583518297030282874472190772894086521144482721001553");
+    U256 by = dec("16950150798460657717958625567821834550301663161624707787222815936182638968203");
+    uint32_t off = (uint32_t)list_pool.size();
+    list_pool.push_back(nbits);
+    list_pool.push_back(pool_mont(ca)); list_pool.push_back(pool_mont(cd)); list_pool.push_back(pool_mont(bx)); list_pool.push_back(pool_mont(by));
+    list_pool.push_back(sf);
+    HintCtx h;
+    uint32_t first = 0;
+    for (uint32_t i = 0; i < 4 * nadd; i++) {
+      uint32_t id = new_value(CLS_F);
+      if (i == 0) first = id;
+      list_pool.push_back(id);
+      if (i < 2 * nadd) h.vals.push_back(id);
+    }
+    emit(PZK_BJJ_MUL8, first, off, 0);
+    for (uint32_t i = 0; i < 4 * nadd; i++) v_def[list_pool[off + 6 + i]] = (uint32_t)ops.size() - 1;
+    stats->bjj++;
+    hint_stack.push_back(std::move(h));
+    return true;
   }
 
   void instantiate(const Ref& c, Expr* rhs, Env& env, Ctx* ctx, const Stmt* at) {
@@ -1595,6 +1652,13 @@ struct Compiler::Impl {
     }
     if (target.k == Ref::UNKNOWN) return;
     if (op == O_ASSIGN) fail(s, "signals are assigned with <== or <--");
+    if (op == O_WITNESS_L && phase == 1 && !hint_stack.empty() && ctx && ctx->lay->tname == id_bjj_add && target.name == id_sig_out &&
+        target.dims.empty()) {
+      HintCtx& h = hint_stack.back();
+      if (h.next >= h.vals.size()) fail(s, "internal: more BabyjubjubAdd instances than hints");
+      store_signal(target, scalar(sv(h.vals[h.next++])), false, s);
+      return;
+    }
     Value v = eval(s->rhs, env, ctx, op == O_CONSTRAIN_L, s);
     store_signal(target, v, op == O_CONSTRAIN_L, s);
   }
@@ -2258,7 +2322,7 @@ struct Compiler::Impl {
       if (op_stats && i < op_tag.size()) cur_tag = op_tag[i];
       if (o.opc == PZK_U_LUTV) { auto it = lutv_off.find((uint32_t)i); if (it != lutv_off.end()) o.e = it->second; }
       const uint32_t d = o.dst;
-      bool has_value = !(o.opc == PZK_NOP || o.opc == PZK_ASSERT_NZ || o.opc == PZK_BIGDIV || o.opc == PZK_MODINV);
+      bool has_value = !(o.opc == PZK_NOP || o.opc == PZK_ASSERT_NZ || is_macro(o.opc));
       bool dropped = false;
       if (opt.views && has_value && d) {
         ViewD dv;
@@ -2287,9 +2351,9 @@ struct Compiler::Impl {
         // a real op: its operands need slots
         switch (o.opc) {
           case PZK_NOP: case PZK_U_CONST: case PZK_F_CONST: case PZK_IN_U: case PZK_IN_F: break;
-          case PZK_BIGDIV: case PZK_MODINV: {
-            uint32_t k = list_pool[o.a + 1], m = list_pool[o.a + 2];
-            for (uint32_t j = 0; j < k + m + k; j++) list_pool[o.a + 3 + j] = real_of(list_pool[o.a + 3 + j]);
+          case PZK_BIGDIV: case PZK_MODINV: case PZK_BJJ_MUL8: {
+            uint32_t op0, nop, def0, ndef; macro_layout(o, op0, nop, def0, ndef);
+            for (uint32_t j = 0; j < nop; j++) list_pool[op0 + j] = real_of(list_pool[op0 + j]);
             break;
           }
           case PZK_ASSERT_NZ: case PZK_N_BIT: case PZK_F_CSEL: o.a = real_of(o.a); break;
@@ -2320,9 +2384,9 @@ struct Compiler::Impl {
         }
         push(o);
         if (has_value && d) is_real[d] = 1;
-        if (o.opc == PZK_BIGDIV || o.opc == PZK_MODINV) {
-          uint32_t k = list_pool[o.a + 1], m = list_pool[o.a + 2];
-          for (uint32_t j = 0; j < m + 1 + k; j++) is_real[list_pool[o.a + 3 + (k + m) + k + j]] = 1;
+        if (is_macro(o.opc)) {
+          uint32_t op0, nop, def0, ndef; macro_layout(o, op0, nop, def0, ndef);
+          for (uint32_t j = 0; j < ndef; j++) is_real[list_pool[def0 + j]] = 1;
         }
         // a word assembled from scalar bits (b << k summed in ascending order): the bits get a place in it
         if (opt.vectorize && o.opc == PZK_U_ADD && !(o.flags & PZK_FLAG_B_IMM) && v_cls[d] == CLS_U) {
@@ -2385,9 +2449,9 @@ void Compiler::Impl::backend() {
   std::function<void(const OpRec&, const std::function<void(uint32_t)>&)> for_operands = [&](const OpRec& o, const std::function<void(uint32_t)>& f) {
     switch (o.opc) {
       case PZK_NOP: case PZK_U_CONST: case PZK_F_CONST: case PZK_IN_U: case PZK_IN_F: return;
-      case PZK_BIGDIV: case PZK_MODINV: {
-        uint32_t k = list_pool[o.a + 1], m = list_pool[o.a + 2];
-        for (uint32_t i = 0; i < k + m + k; i++) f(list_pool[o.a + 3 + i]);
+      case PZK_BIGDIV: case PZK_MODINV: case PZK_BJJ_MUL8: {
+        uint32_t op0, nop, def0, ndef; macro_layout(o, op0, nop, def0, ndef);
+        for (uint32_t i = 0; i < nop; i++) f(list_pool[op0 + i]);
         return;
       }
       case PZK_ASSERT_NZ: case PZK_U_EXTRACT: case PZK_N_EXTRACT: f(o.a); return;
@@ -2413,10 +2477,9 @@ void Compiler::Impl::backend() {
   };
   auto for_defs = [&](const OpRec& o, const std::function<void(uint32_t)>& f) {
     if (o.opc == PZK_NOP || o.opc == PZK_ASSERT_NZ) return;
-    if (o.opc == PZK_BIGDIV || o.opc == PZK_MODINV) {
-      uint32_t k = list_pool[o.a + 1], m = list_pool[o.a + 2];
-      uint32_t base = o.a + 3 + (k + m) + k;
-      for (uint32_t i = 0; i < m + 1 + k; i++) f(list_pool[base + i]);
+    if (is_macro(o.opc)) {
+      uint32_t op0, nop, def0, ndef; macro_layout(o, op0, nop, def0, ndef);
+      for (uint32_t i = 0; i < ndef; i++) f(list_pool[def0 + i]);
       return;
     }
     f(o.dst);
@@ -2694,7 +2757,7 @@ void Compiler::Impl::backend() {
       for (size_t i = 0; i < nops; i++) {
         if (!keep[i]) continue;
         const OpRec& o = ops[i];
-        if (o.opc == PZK_NOP || o.opc == PZK_ASSERT_NZ || o.opc == PZK_BIGDIV || o.opc == PZK_MODINV || !o.dst) continue;
+        if (o.opc == PZK_NOP || o.opc == PZK_ASSERT_NZ || is_macro(o.opc) || !o.dst) continue;
         ViewD d;
         if (try_view(o, d)) vw[o.dst] = d;
       }
@@ -3024,7 +3087,7 @@ void Compiler::Impl::backend() {
   {
     std::vector<uint64_t> nu(segs.size(), 0), nf(segs.size(), 0);
     for (size_t i = 0; i < nops; i++) {
-      if (!keep[i] || ops[i].opc == PZK_BIGDIV || ops[i].opc == PZK_MODINV) continue;
+      if (!keep[i] || is_macro(ops[i].opc)) continue;
       for_defs(ops[i], [&](uint32_t d) { ((v_cls[d] == CLS_U || v_cls[d] == CLS_I) ? nu : nf)[op_seg[i]]++; });
     }
     for (size_t sg = 0; sg < segs.size(); sg++) {
@@ -3044,7 +3107,7 @@ void Compiler::Impl::backend() {
     for (size_t i = 0; i < nops; i++) {
       if (!keep[i]) continue;
       op_pos[i] = pos;
-      if (ops[i].opc != PZK_BIGDIV && ops[i].opc != PZK_MODINV) for_operands(ops[i], [&](uint32_t v) { use_cnt[v]++; });
+      if (!is_macro(ops[i].opc)) for_operands(ops[i], [&](uint32_t v) { use_cnt[v]++; });
       pos++;
       while (rp < nrows && row_trigger[row_order[rp]] == i) {
         uint32_t r = row_order[rp], nt = rows[r].na + rows[r].nb + rows[r].nc;
@@ -3062,7 +3125,7 @@ void Compiler::Impl::backend() {
     uint32_t pos = 0; size_t rp = 0;
     for (size_t i = 0; i < nops; i++) {
       if (!keep[i]) continue;
-      if (ops[i].opc != PZK_BIGDIV && ops[i].opc != PZK_MODINV) for_operands(ops[i], [&](uint32_t v) { use_pos[use_off[v] + use_fill[v]++] = pos; });
+      if (!is_macro(ops[i].opc)) for_operands(ops[i], [&](uint32_t v) { use_pos[use_off[v] + use_fill[v]++] = pos; });
       pos++;
       while (rp < nrows && row_trigger[row_order[rp]] == i) {
         uint32_t r = row_order[rp], nt = rows[r].na + rows[r].nb + rows[r].nc;
@@ -3186,10 +3249,9 @@ void Compiler::Impl::backend() {
         case PZK_NOP: break;
         case PZK_U_CONST: case PZK_F_CONST: case PZK_IN_U: case PZK_IN_F: has_dst = true; break;
         case PZK_ASSERT_NZ: r.a = opnd(o.a); break;
-        case PZK_BIGDIV: case PZK_MODINV: {
-          uint32_t k = list_pool[o.a + 1], m = list_pool[o.a + 2];
-          uint32_t cnt = (k + m) + k + (m + 1) + k;
-          for (uint32_t j = 0; j < cnt; j++) { out_list[o.a + 3 + j] = slot_of(list_pool[o.a + 3 + j]); needs_global[list_pool[o.a + 3 + j]] = 1; }
+        case PZK_BIGDIV: case PZK_MODINV: case PZK_BJJ_MUL8: {
+          uint32_t op0, nop, def0, ndef; macro_layout(o, op0, nop, def0, ndef);
+          for (uint32_t j = op0; j < def0 + ndef; j++) { out_list[j] = slot_of(list_pool[j]); needs_global[list_pool[j]] = 1; }
           break;
         }
         case PZK_N_BIT: case PZK_F_CSEL: case PZK_U_EXTRACT: case PZK_N_EXTRACT: has_dst = true; r.a = opnd(o.a); break;
@@ -3206,7 +3268,7 @@ void Compiler::Impl::backend() {
           }
       }
       // operands die / get re-prioritised, then the result may take a cell
-      if (o.opc != PZK_BIGDIV && o.opc != PZK_MODINV) for_operands(o, [&](uint32_t v) { touch_operand(v, pos, seg_end); });
+      if (!is_macro(o.opc)) for_operands(o, [&](uint32_t v) { touch_operand(v, pos, seg_end); });
       if (has_dst) {
         uint32_t slot = slot_of(o.dst);
         if (slot > 0x3fffffu) throw CompileError("too many live slots for the dst encoding");

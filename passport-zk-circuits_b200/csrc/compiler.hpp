@@ -122,7 +122,7 @@ struct CompileOptions {
 
 struct CompileStats {
   uint64_t n_signals = 0, n_constraints = 0, n_ops = 0, n_values = 0;
-  uint64_t u_ops = 0, f_mul = 0, f_inv = 0, f_inv_real = 0, f_other = 0, bigdiv = 0, lut = 0, modinv = 0;
+  uint64_t u_ops = 0, f_mul = 0, f_inv = 0, f_inv_real = 0, f_other = 0, bigdiv = 0, lut = 0, modinv = 0, bjj = 0;
   uint32_t n_u_slots = 0, n_f_slots = 0, n_segments = 0;
   double seconds = 0;
 };

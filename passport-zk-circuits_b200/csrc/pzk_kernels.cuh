@@ -252,6 +252,84 @@ __device__ __noinline__ u32 bigdiv_device(const u32* Lst, u64* Ul, u64 L) {
   return st;
 }
 
+
+// ---- BabyJubjub base-8 ladder hints (PZK_BJJ_MUL8) ---------------------------------------------------
+// The outputs of the 2n - 1 BabyjubjubAdd instances of BabyjubjubBase8Multiplication
+// (/root/reference/circuits/lib/circuits/babyjubjub/curve.circom:143-171; adder formula :71-105, the (0,0)
+// "no point" convention and the selection of addZeroBabyjub :19-58), evaluated in projective coordinates
+// (x = X/Z, y = Y/Z; unified twisted-Edwards addition, 13 products) and normalised with ONE inversion for all
+// 507 denominators (Montgomery's trick over the F plane).  Z3 = (A^2 - dCD)(A^2 + dCD) is never zero for points
+// of the curve or for (0,0); should it be, the lane is flagged and its rows fail.
+__device__ __noinline__ void fr_mul_call(u64* r, const u64* a, const u64* b) { fr_mul(r, a, b); }
+struct BjjPt { u64 X[4], Y[4], Z[4]; };
+__device__ __noinline__ void bjj_padd(BjjPt& o, const BjjPt& p, const BjjPt& q, const u64* ca, const u64* cd) {
+  u64 A[4], B[4], C[4], D[4], E[4], F[4], G[4], t[4], u[4];
+  fr_mul_call(A, p.Z, q.Z); fr_mul_call(B, A, A);
+  fr_mul_call(C, p.X, q.X); fr_mul_call(D, p.Y, q.Y);
+  fr_mul_call(E, C, D); fr_mul_call(E, E, cd);
+  fr_sub(F, B, E); fr_add(G, B, E);
+  fr_add(t, p.X, p.Y); fr_add(u, q.X, q.Y); fr_mul_call(t, t, u); fr_sub(t, t, C); fr_sub(t, t, D);
+  fr_mul_call(u, A, F); fr_mul_call(o.X, u, t);
+  fr_mul_call(t, C, ca); fr_sub(t, D, t);
+  fr_mul_call(u, A, G); fr_mul_call(o.Y, u, t);
+  fr_mul_call(o.Z, F, G);
+}
+__device__ __noinline__ u32 bjj_mul8_device(const u32* Lst, const u64* fpool, u64* Fl, u64 L) {
+  const u32 n = Lst[0], nadd = 2 * n - 1;
+  u64 ca[4], cd[4], bx[4], by[4], one[4], sc[4];
+  ldPool(fpool, Lst[1], ca); ldPool(fpool, Lst[2], cd); ldPool(fpool, Lst[3], bx); ldPool(fpool, Lst[4], by);
+  { const u64 o1[4] = {1, 0, 0, 0}; fr_to_mont(one, o1); }
+  { u64 m[4]; ldF(Fl, L, Lst[5], m); fr_from_mont(sc, m); }
+  const u32* out = Lst + 6;
+  const u32* scr = out + 2 * nadd;
+  BjjPt S, Dd, A, Q;
+#pragma unroll
+  for (int i = 0; i < 4; i++) { S.X[i] = S.Y[i] = 0; S.Z[i] = one[i]; }
+  u64 pre[4] = {one[0], one[1], one[2], one[3]};
+  u32 k = 0;
+  for (u32 i = 0; i < n; i++) {
+    if (i > 0) {
+      bjj_padd(Dd, S, S, ca, cd);
+      stF(Fl, L, out[2 * k], Dd.X); stF(Fl, L, out[2 * k + 1], Dd.Y); stF(Fl, L, scr[2 * k], Dd.Z);
+      fr_mul_call(pre, pre, Dd.Z); stF(Fl, L, scr[2 * k + 1], pre);
+      k++;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; j++) { Dd.X[j] = Dd.Y[j] = 0; Dd.Z[j] = one[j]; }
+    }
+    const u32 bi = n - 1 - i;
+    const bool bit = (sc[bi >> 6] >> (bi & 63)) & 1;
+#pragma unroll
+    for (int j = 0; j < 4; j++) { Q.X[j] = bit ? bx[j] : 0; Q.Y[j] = bit ? by[j] : 0; Q.Z[j] = one[j]; }
+    bjj_padd(A, Dd, Q, ca, cd);
+    stF(Fl, L, out[2 * k], A.X); stF(Fl, L, out[2 * k + 1], A.Y); stF(Fl, L, scr[2 * k], A.Z);
+    fr_mul_call(pre, pre, A.Z); stF(Fl, L, scr[2 * k + 1], pre);
+    k++;
+    // addZeroBabyjub: in1 "zero" -> in2, else in2 "zero" -> in1, else the sum (zero = x coordinate 0)
+    const bool zd = fr_is_zero(Dd.X), zq = !bit;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      S.X[j] = zd ? Q.X[j] : (zq ? Dd.X[j] : A.X[j]);
+      S.Y[j] = zd ? Q.Y[j] : (zq ? Dd.Y[j] : A.Y[j]);
+      S.Z[j] = zd ? Q.Z[j] : (zq ? Dd.Z[j] : A.Z[j]);
+    }
+  }
+  u32 st = fr_is_zero(pre) ? PZK_LANE_HINT : 0;
+  u64 inv[4];
+  fr_inv(inv, pre);
+  for (u32 kk = nadd; kk-- > 0;) {
+    u64 z[4], zi[4], x[4], y[4];
+    ldF(Fl, L, scr[2 * kk], z);
+    if (kk > 0) { u64 pp[4]; ldF(Fl, L, scr[2 * kk - 1], pp); fr_mul_call(zi, inv, pp); }
+    else { zi[0] = inv[0]; zi[1] = inv[1]; zi[2] = inv[2]; zi[3] = inv[3]; }
+    fr_mul_call(inv, inv, z);
+    ldF(Fl, L, out[2 * kk], x); ldF(Fl, L, out[2 * kk + 1], y);
+    fr_mul_call(x, x, zi); fr_mul_call(y, y, zi);
+    stF(Fl, L, out[2 * kk], x); stF(Fl, L, out[2 * kk + 1], y);
+  }
+  return st;
+}
+
 // ---- rows fused into the op stream ---------------------------------------------------------
 // term k of a row lives in record (k >> 1), words (2*(k&1), 2*(k&1)+1)
 __device__ __forceinline__ uint2 row_term(const uint4* recs, u32 k) {
@@ -647,6 +725,7 @@ __global__ void __launch_bounds__(128, 8) eval_kernel(EvalParams p) {
       }
       case PZK_BIGDIV: st |= bigdiv_device(list + a, Ul, L); break;
       case PZK_MODINV: modinv_device(list + a, Ul, L); break;
+      case PZK_BJJ_MUL8: st |= bjj_mul8_device(list + a, fpool, Fl, L); break;
       case PZK_ASSERT_NZ: if (LDO(a) == 0) st |= PZK_LANE_ASSERT; break;
       case PZK_IN_U: {
         if (p.in_table) {
