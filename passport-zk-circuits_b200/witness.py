@@ -374,16 +374,34 @@ class WitnessCalculator:
             self._layout = (kind, off, int(self._L.pzk_packed_stride(self._h)))
         return self._layout
 
-    def pack(self, inputs: np.ndarray) -> np.ndarray:
-        """uint64 [B, n_inputs, 4] -> uint8 [B, stride] packed records (values must fit their declared width;
-        wider values are truncated here and would have been flagged by the unpacked path)."""
+    def pack(self, inputs: np.ndarray, on_range: str = "raise"):
+        """uint64 [B, n_inputs, 4] -> uint8 [B, stride] packed records.
+
+        A packed record has room for one byte / eight bytes per narrow input, so a value that does not fit its
+        section cannot cross the boundary; it is rejected HERE instead of being narrowed silently (the kernel's
+        IN_U range check only sees what is in the record).  on_range = "raise": PzkError naming the first offending
+        lane and input; "mask": returns (packed, bad) with bad[b] = True for lanes holding such a value - pass it to
+        calculateWitnessBatchPacked(range_mask=bad), which reports PZK_STATUS_INPUT_RANGE for them exactly as the
+        unpacked path does.  Values that fit the section but exceed the declared width (a 'bit' of 2) are flagged
+        by the kernel."""
         kind, off, stride = self.packed_layout()
+        inputs = np.asarray(inputs)
         B = inputs.shape[0]
         out = np.zeros((B, stride), dtype=np.uint8)
+        bad = np.zeros(B, dtype=bool)
         k8 = np.nonzero(kind == 0)[0]
-        if len(k8):
-            out[:, off[k8]] = inputs[:, k8, 0].astype(np.uint8)
         k64 = np.nonzero(kind == 1)[0]
+        narrow = np.nonzero(kind != 2)[0]
+        if len(narrow):
+            bad |= (inputs[:, narrow, 1:] != 0).any(axis=(1, 2))
+        if len(k8):
+            bad |= (inputs[:, k8, 0] > 255).any(axis=1)
+            out[:, off[k8]] = inputs[:, k8, 0].astype(np.uint8)
+        if bad.any() and on_range == "raise":
+            b = int(np.nonzero(bad)[0][0])
+            wide = [int(k) for k in narrow if inputs[b, k, 1:].any() or (kind[k] == 0 and inputs[b, k, 0] > 255)]
+            raise PzkError(f"Input out of its declared range (status {STATUS_INPUT_RANGE}): lane {b}, flattened input "
+                           f"{wide[0]} does not fit its packed section")
         if len(k64):
             lo = int(off[k64[0]])
             assert (off[k64] == lo + 8 * np.arange(len(k64))).all()
@@ -393,9 +411,12 @@ class WitnessCalculator:
             lo = int(off[kf[0]])
             assert (off[kf] == lo + 32 * np.arange(len(kf))).all()
             out[:, lo:lo + 32 * len(kf)] = np.ascontiguousarray(inputs[:, kf, :]).view(np.uint8).reshape(B, -1)
+        if on_range == "mask":
+            return out, bad
         return out
 
-    def calculateWitnessBatchPacked(self, packed: np.ndarray) -> BatchResult:
+    def calculateWitnessBatchPacked(self, packed: np.ndarray, range_mask=None) -> BatchResult:
+        """range_mask: the per-lane mask pack(..., on_range="mask") returned; those lanes get INPUT_RANGE."""
         packed = np.ascontiguousarray(packed, dtype=np.uint8)
         B = packed.shape[0]
         status = np.zeros(B, dtype=np.uint32)
@@ -403,6 +424,8 @@ class WitnessCalculator:
         public = np.zeros((B, self.n_public, 4), dtype=np.uint64)
         self._check(self._L.pzk_witness_batch_packed(self._h, packed.ctypes.data, B, status.ctypes.data,
                                                      first_bad.ctypes.data, public.ctypes.data))
+        if range_mask is not None:
+            status[np.asarray(range_mask, dtype=bool)] |= STATUS_INPUT_RANGE
         first_bad[(status & STATUS_CONSTRAINT) == 0] = -1
         return BatchResult(status, first_bad, public)
 

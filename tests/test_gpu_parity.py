@@ -39,8 +39,12 @@ def run_and_compare(name, inp, export=None, tile=None):
     lean = calc.calculateWitnessBatch(inp)      # no export: optional global stores are skipped
     assert np.array_equal(lean.status, res.status) and np.array_equal(lean.first_bad, res.first_bad)
     assert np.array_equal(lean.public, res.public)
-    packed = calc.calculateWitnessBatchPacked(calc.pack(inp))
-    in_range = (res.status & W.STATUS_INPUT_RANGE) == 0      # packing truncates out-of-range values
+    # the packed path must flag exactly the lanes the unpacked path flags (values too wide for their packed
+    # section are caught by pack(), values wider than declared by the kernel)
+    rec, too_wide = calc.pack(inp, on_range="mask")
+    packed = calc.calculateWitnessBatchPacked(rec, range_mask=too_wide)
+    assert np.array_equal(packed.status & W.STATUS_INPUT_RANGE, res.status & W.STATUS_INPUT_RANGE)
+    in_range = (res.status & W.STATUS_INPUT_RANGE) == 0
     assert np.array_equal(packed.status[in_range], res.status[in_range])
     assert np.array_equal(packed.public[in_range], res.public[in_range])
     calc.close()
@@ -66,6 +70,24 @@ def test_mix_out_of_range_input_is_flagged():
     res = run_and_compare("t_mix", inp)
     assert res.status[7] & W.STATUS_INPUT_RANGE and res.status[9] & W.STATUS_INPUT_RANGE
     assert (np.delete(res.status, [7, 9]) == 0).all()
+
+
+def test_packed_path_rejects_values_that_do_not_fit_the_record():
+    """a 'bit' of 256 or a limb above 2^64 must not be narrowed silently on the packed path."""
+    calc = W.WitnessCalculator(W.artifact("t_mix"), 0)
+    inp = random_inputs(calc.meta, 16, 5)
+    d = {x["name"]: x for x in calc.meta["inputs"]}
+    inp[3, d["bits"]["offset"], 0] = 256         # wraps to 0 as a byte
+    inp[4, d["u"]["offset"], 2] = 7              # limb 2 of a 16-bit input
+    with pytest.raises(W.PzkError, match="declared range"):
+        calc.pack(inp)
+    rec, bad = calc.pack(inp, on_range="mask")
+    assert list(np.nonzero(bad)[0]) == [3, 4]
+    res = calc.calculateWitnessBatchPacked(rec, range_mask=bad)
+    ref = calc.calculateWitnessBatch(inp)
+    assert np.array_equal(res.status & W.STATUS_INPUT_RANGE, ref.status & W.STATUS_INPUT_RANGE)
+    assert res.status[3] & W.STATUS_INPUT_RANGE and res.status[4] & W.STATUS_INPUT_RANGE
+    calc.close()
 
 
 def test_bigdiv_intrinsic():
