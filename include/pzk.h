@@ -132,12 +132,41 @@ int pzk_witness_batch_packed(pzk_circuit* c, const uint8_t* packed, uint64_t bat
                              int64_t* first_bad, uint8_t* public_le32);
 int pzk_batch_upload_packed(pzk_circuit* c, const uint8_t* packed, uint64_t batch);
 
+/* Streams ("stream-async + pzk_sync").  Every packed call works in tiles of one wave of resident
+ * CTAs; the host-to-device copy of tile k+1 and the device-to-host copy of tile k-1's results run on a second
+ * stream under the kernels of tile k (give it pinned host buffers, or the copies serialise).  The _async form
+ * returns as soon as the work is enqueued: the output arrays are valid after pzk_sync(), and any other call on
+ * the handle syncs first.  digest may be NULL (see "witness digest" below).                                   */
+int pzk_witness_batch_packed_async(pzk_circuit* c, const uint8_t* packed, uint64_t batch, uint32_t* status,
+                                   int64_t* first_bad, uint8_t* public_le32, uint64_t* digest);
+int pzk_sync(pzk_circuit* c);
+
+/* One host thread, several devices: handles[i] is a circuit handle opened on device i with the
+ * same program; the batch is cut into n contiguous shares (share i = lanes [i*batch/n, (i+1)*batch/n)), every
+ * device runs its share asynchronously and all are joined before the call returns.  No collective: the shares
+ * are independent.  Outputs are indexed by the caller's lane numbers.                                        */
+int pzk_witness_batch_packed_multi(pzk_circuit* const* handles, int n_handles, const uint8_t* packed, uint64_t batch,
+                                   uint32_t* status, int64_t* first_bad, uint8_t* public_le32, uint64_t* digest);
+
+/* ---- witness digest: proof that every signal of every lane was computed, without moving 72 MB per witness.
+ * With the digest switched on, every run folds EVERY wire of EVERY lane, on the device, into
+ *     digest[lane][j] = sum over wires i of K(i) * limb_j(w_i)  mod 2^64,   j = 0..3,
+ * w_i the canonical value of wire i exactly as calculateWTNSBin would write it, K(i) = pzk_digest_weight_of(i)
+ * (splitmix64(i) | 1: position sensitive).  A consumer that holds the .wtns of a lane - or the oracle - can
+ * recompute it; tests compare it with the oracle's witness for every lane.  The reference returns the whole
+ * vector (/root/reference/test/automatisationTest.js:40-50); this is its checksum.                          */
+int pzk_batch_set_digest(pzk_circuit* c, int on);
+int pzk_batch_download_digest(pzk_circuit* c, uint64_t* digest /* [batch][4] */);
+uint64_t pzk_digest_weight_of(uint32_t wire);
+int pzk_witness_batch_packed_digest(pzk_circuit* c, const uint8_t* packed, uint64_t batch, uint32_t* status,
+                                    int64_t* first_bad, uint8_t* public_le32, uint64_t* digest);
+
 /* device-resident variant for measurement: upload once, run many times, download once */
 int pzk_batch_upload(pzk_circuit* c, const uint8_t* inputs_le32, uint64_t batch);
 int pzk_batch_run(pzk_circuit* c, int check_rows); /* all tiles of the uploaded batch    */
 int pzk_batch_download(pzk_circuit* c, uint32_t* status, int64_t* first_bad, uint8_t* public_le32);
 /* accumulated CUDA-event time (ms) and launch counts per kernel family since the last reset:
- * which = 0 eval, 1 row check, 2 export/public, 3 whole run.                           */
+ * which = 0 eval, 1 row check, 2 export/public, 3 whole run, 4 witness digest.                           */
 int pzk_profile_get(pzk_circuit* c, int which, double* ms, uint64_t* launches);
 void pzk_profile_reset(pzk_circuit* c);
 /* accumulated evaluator time per program segment (ms); returns the number of segments */
@@ -159,6 +188,27 @@ int pzk_wtns_check(const char* r1cs_path, const uint8_t* wtns, uint64_t wtns_len
 int pzk_r1cs_check_batch(const char* r1cs_path, const uint8_t* witnesses_le32, uint64_t batch,
                          int cuda_device, int* verdicts, int64_t* first_bad, double* kernel_ms,
                          char* err, size_t err_len);
+
+/* The same check with the matrices parsed and uploaded ONCE (the role of snarkjs' readR1cs): open, check any
+ * number of batches, close.  A truncated or malformed file is PZK_EFORMAT; an .r1cs without constraints accepts
+ * every witness.                                                                                             */
+typedef struct pzk_r1cs pzk_r1cs;
+int pzk_r1cs_open(const char* r1cs_path, int cuda_device, pzk_r1cs** out, char* err, size_t err_len);
+void pzk_r1cs_close(pzk_r1cs* r);
+uint32_t pzk_r1cs_wires(const pzk_r1cs* r);
+uint32_t pzk_r1cs_constraints(const pzk_r1cs* r);
+uint64_t pzk_r1cs_terms(const pzk_r1cs* r);
+int pzk_r1cs_check(pzk_r1cs* r, const uint8_t* witnesses_le32, uint64_t batch, int* verdicts, int64_t* first_bad,
+                   double* kernel_ms, char* err, size_t err_len);
+int pzk_r1cs_check_wtns(pzk_r1cs* r, const uint8_t* wtns, uint64_t wtns_len, int* verdict, int64_t* first_bad,
+                        char* err, size_t err_len);
+/* calculateWitness -> checkConstraints without leaving the device (automatisationTest.js:40-51 as two kernels):
+ * evaluates the batch resident in `c` (pzk_batch_upload*), writes every wire of the selected lanes straight into
+ * the checker's planes and checks EVERY row of the .r1cs on them.  The .r1cs must be the one compiled with the
+ * program (same wire layout; a mismatch is "Invalid witness length" / PZK_EFORMAT).  n_lanes full witnesses must
+ * fit in device memory (32 bytes x wires each).                                                               */
+int pzk_r1cs_check_circuit(pzk_r1cs* r, pzk_circuit* c, const uint64_t* lanes, uint64_t n_lanes, int* verdicts,
+                           int64_t* first_bad, double* eval_ms, double* check_ms, char* err, size_t err_len);
 
 int pzk_device_count(void);
 const char* pzk_version(void);

@@ -14,7 +14,8 @@ PARITY STATUS: "parity unpinned" against the real circom wasm (neither node nor
 circom exist in this image and the reference ships no compiled artefacts).
 What *is* pinned: Poseidon against the circomlib vector and test/poseidon.js,
 SHA-1/2 digests against hashlib, RSA against `cryptography`, BabyJubjub against
-an independent affine implementation (tests/test_oracle_*.py).
+an independent affine implementation (tests/test_cpu_host.py, tests/test_cpu_compiler_vs_oracle.py,
+tests/golden/).
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline may import it.
 
@@ -656,8 +657,10 @@ def _zeros(dims):
 
 
 def _copy(v):
-    if isinstance(v, list):
-        return [_copy(x) for x in v]
+    if v.__class__ is list:
+        if v and v[0].__class__ is list:
+            return [_copy(x) for x in v]
+        return v[:]   # circom arrays are rectangular: a list whose first element is a scalar holds scalars only
     return v
 
 
@@ -739,8 +742,10 @@ class Comp:
 class Circuit:
     """One instantiated circuit. `calculate_witness(inputs)` evaluates all signals."""
 
-    def __init__(self, main_path, include_dirs=(), main_override=None):
+    def __init__(self, main_path, include_dirs=(), main_override=None, translate_functions=True):
         self.prog = Program(main_path, include_dirs)
+        # functions are run as translated Python (FunctionTranslator) unless translate_functions=False
+        self.translator = FunctionTranslator(self) if translate_functions else None
         self.layouts = {}
         main = main_override or self.prog.main
         if main is None:
@@ -1309,14 +1314,21 @@ class Circuit:
 
     def call_function(self, e, env, ctx):
         name = e[1]
-        fn = self.prog.get_function(name)
-        if fn is None:
+        if self.prog.get_function(name) is None:
             raise CircomError(f"unknown function {name}")
         args = [self.eval_expr(a, env, ctx) for a in e[2]]
         if any(_has_unk(a) for a in args):
             return UNK
+        if self.translator is not None:
+            return self.translator.call(name, args)
+        return self.interpret_function(name, args)
+
+    def interpret_function(self, name, args):
+        """tree-walking execution of a function body (the definition of the semantics; FunctionTranslator is the
+        fast path and falls back to this for anything outside its subset)"""
+        fn = self.prog.get_function(name)
         key = None
-        if not e[2] or all(not isinstance(a, list) for a in args):
+        if all(not isinstance(a, list) for a in args):
             key = (name, tuple(args))
             hit = self._fn_cache.get(key) if hasattr(self, "_fn_cache") else None
             if hit is not None:
@@ -1334,6 +1346,255 @@ class Circuit:
                 self._fn_cache[key] = _copy(r.v)
             return r.v
         raise CircomError(f"function {name} did not return")
+
+
+# --------------------------------------------------------------------------
+# Function translator: circom `function` bodies -> Python functions
+# --------------------------------------------------------------------------
+class _Unsupported(Exception):
+    pass
+
+
+def _idiv(a, b):
+    if b == 0:
+        raise CircomError("integer division by zero")
+    return a // b
+
+
+def _imod(a, b):
+    if b == 0:
+        raise CircomError("modulo by zero")
+    return a % b
+
+
+def _fdiv(a, b):
+    if b == 0:
+        return 0
+    return (a * pow(b, -1, P)) % P
+
+
+class FunctionTranslator:
+    """The witness-time hint functions of the big-integer library (long_div, mod_inv = a^(p-2) by 380 rounds of
+    prod + long_div, ... /root/reference/circuits/lib/circuits/bigInt/bigIntFunc.circom:126-660) are pure functions
+    of vars; walking their syntax trees costs ~4 us per node, which puts one ECDSA witness (362 mod_inv calls) at
+    hours.  This translates a function's syntax tree ONCE into Python source with exactly the interpreter's
+    semantics (same field operators, block scoping resolved statically, copy-on-assign arrays, lazy && || ?:) and
+    executes that instead.  It is still the reference's own source text that runs - no function is restated by hand;
+    tests/test_cpu_compiler_vs_oracle.py::test_translated_functions_equal_the_tree_walker compares both execution
+    modes on random operands.  Functions using anything outside the subset keep running in the tree walker."""
+    MAX_STMTS = 4000   # the 70 000-line generator tables are evaluated once by the tree walker
+
+    def __init__(self, circuit):
+        self.circuit = circuit
+        self.fns = {}
+        self.n_calls = 0
+
+    def get(self, name):
+        f = self.fns.get(name, False)
+        if f is not False:
+            return f
+        self.fns[name] = None
+        fn = self.circuit.prog.get_function(name)
+        if fn is None:
+            return None
+        try:
+            src = self._translate(name, fn[1], fn[2])
+            glb = {"P": P, "HALF": HALF, "MASK": MASK, "_cp": _copy, "_zeros": _zeros, "_shl": _shl, "_shr": _shr,
+                   "_idiv": _idiv, "_imod": _imod, "_fdiv": _fdiv, "_call": self.call, "CircomError": CircomError,
+                   "AssertFailed": AssertFailed}
+            exec(compile(src, f"<circom function {name}>", "exec"), glb)
+            self.fns[name] = glb["_f"]
+        except _Unsupported:
+            self.fns[name] = None
+        return self.fns[name]
+
+    def call(self, name, args):
+        f = self.get(name)
+        if f is None:
+            return self.circuit.interpret_function(name, args)
+        self.n_calls += 1
+        return f(*[_copy(a) for a in args])
+
+    # ---- translation
+    def _translate(self, name, params, body):
+        self.n_stmts = 0
+        self.uid = 0
+        self.lines = []
+        self.scopes = [{}]
+        pn = []
+        for q in params:
+            pn.append(self._declare(q))
+        self.lines.append("def _f(" + ", ".join(pn) + "):")
+        self._stmt(body, 1)
+        self.lines.append(f"    raise CircomError('function {name} did not return')")
+        return "\n".join(self.lines) + "\n"
+
+    def _declare(self, name):
+        self.uid += 1
+        py = f"v{self.uid}_{re.sub(r'[^A-Za-z0-9_]', '_', name)}"
+        self.scopes[-1][name] = py
+        return py
+
+    def _lookup(self, name):
+        for sc in reversed(self.scopes):
+            if name in sc:
+                return sc[name]
+        raise _Unsupported(name)
+
+    def _emit(self, ind, text):
+        self.lines.append("    " * ind + text)
+
+    def _sg(self, x):
+        return f"({x} - P if {x} > HALF else {x})" if re.fullmatch(r"[A-Za-z0-9_]+", x) else f"(lambda t: t - P if t > HALF else t)({x})"
+
+    def _cond(self, e):
+        """Python truth value of `e != 0`."""
+        if e[0] == "bin":
+            op = e[1]
+            if op in ("<", ">", "<=", ">="):
+                return f"({self._sg(self._expr(e[2]))} {op} {self._sg(self._expr(e[3]))})"
+            if op in ("==", "!="):
+                return f"({self._expr(e[2])} {op} {self._expr(e[3])})"
+            if op == "&&":
+                return f"({self._cond(e[2])} and {self._cond(e[3])})"
+            if op == "||":
+                return f"({self._cond(e[2])} or {self._cond(e[3])})"
+        if e[0] == "un" and e[1] == "!":
+            return f"(not {self._cond(e[2])})"
+        return f"({self._expr(e)} != 0)"
+
+    def _expr(self, e):
+        k = e[0]
+        if k == "num":
+            return str(e[1])
+        if k == "var":
+            return self._lookup(e[1])
+        if k == "bin":
+            op = e[1]
+            if op in ("<", ">", "<=", ">=", "==", "!=", "&&", "||"):
+                return f"(1 if {self._cond(e)} else 0)"
+            a, b = self._expr(e[2]), self._expr(e[3])
+            if op in ("+", "-", "*"):
+                return f"(({a} {op} {b}) % P)"
+            if op == "\\":
+                return f"_idiv({a}, {b})"
+            if op == "%":
+                return f"_imod({a}, {b})"
+            if op == "<<":
+                return f"_shl({a}, {b})"
+            if op == ">>":
+                return f"_shr({a}, {b})"
+            if op == "&":
+                return f"(({a} & {b}) % P)"
+            if op in ("|", "^"):
+                return f"((({a} {op} {b}) & MASK) % P)"
+            if op == "/":
+                return f"_fdiv({a}, {b})"
+            if op == "**":
+                return f"pow({a}, {b}, P)"
+            raise _Unsupported(op)
+        if k == "un":
+            a = self._expr(e[2])
+            if e[1] == "-":
+                return f"((-{a}) % P)"
+            if e[1] == "!":
+                return f"(1 if {a} == 0 else 0)"
+            return f"((({a} ^ MASK) & MASK) % P)"
+        if k == "tern":
+            return f"({self._expr(e[2])} if {self._cond(e[1])} else {self._expr(e[3])})"
+        if k == "idx":
+            idxs = []
+            base = e
+            while base[0] == "idx":
+                idxs.append(base[2])
+                base = base[1]
+            if base[0] != "var":
+                raise _Unsupported("indexed expression")
+            return self._lookup(base[1]) + "".join(f"[{self._expr(i)}]" for i in reversed(idxs))
+        if k == "call":
+            return f"_call({e[1]!r}, [{', '.join(self._expr(a) for a in e[2])}])"
+        if k == "arr":
+            return "[" + ", ".join(self._expr(x) for x in e[1]) + "]"
+        raise _Unsupported(k)
+
+    def _rhs(self, e):
+        """assignment copies arrays; expressions that can only be scalars skip the copy"""
+        x = self._expr(e)
+        return x if e[0] in ("num", "bin", "un") else f"_cp({x})"
+
+    def _lvalue(self, lhs):
+        if lhs[0] == "var":
+            return self._lookup(lhs[1])
+        if lhs[0] == "idx":
+            return self._expr(lhs)
+        raise _Unsupported("assignment target")
+
+    def _stmt(self, s, ind):
+        self.n_stmts += 1
+        if self.n_stmts > self.MAX_STMTS:
+            raise _Unsupported("too large")
+        k = s[0]
+        if k == "block":
+            self.scopes.append({})
+            if not s[1]:
+                self._emit(ind, "pass")
+            for st in s[1]:
+                self._stmt(st, ind)
+            self.scopes.pop()
+        elif k == "vardecl":
+            for name, dims, init in s[1]:
+                if init is not None:
+                    val = self._rhs(init)
+                elif dims:
+                    val = "_zeros([" + ", ".join(self._expr(d) for d in dims) + "])"
+                else:
+                    val = "0"
+                self._emit(ind, f"{self._declare(name)} = {val}")
+        elif k == "assign":
+            op, lhs, rhs = s[1], s[2], s[3]
+            if op == "=":
+                self._emit(ind, f"{self._lvalue(lhs)} = {self._rhs(rhs)}")
+            elif op.endswith("=") and op not in ("<==", "<--"):
+                fake = ("bin", op[:-1], lhs, rhs)
+                self._emit(ind, f"{self._lvalue(lhs)} = {self._expr(fake)}")
+            else:
+                raise _Unsupported(op)
+        elif k == "incdec":
+            lv = self._lvalue(s[1])
+            self._emit(ind, f"{lv} = ({lv} + {s[2]}) % P")
+        elif k == "for":
+            self.scopes.append({})
+            self._stmt(s[1], ind)
+            self._emit(ind, "while True:")
+            self._emit(ind + 1, f"if not {self._cond(s[2])}:")
+            self._emit(ind + 2, "break")
+            self._stmt(s[4], ind + 1)
+            self._stmt(s[3], ind + 1)
+            self.scopes.pop()
+        elif k == "while":
+            self._emit(ind, "while True:")
+            self._emit(ind + 1, f"if not {self._cond(s[1])}:")
+            self._emit(ind + 2, "break")
+            self._stmt(s[2], ind + 1)
+        elif k == "if":
+            self._emit(ind, f"if {self._cond(s[1])}:")
+            self.scopes.append({})
+            self._stmt(s[2], ind + 1)
+            self.scopes.pop()
+            if s[3] is not None:
+                self._emit(ind, "else:")
+                self.scopes.append({})
+                self._stmt(s[3], ind + 1)
+                self.scopes.pop()
+        elif k == "return":
+            self._emit(ind, f"return {self._expr(s[1])}")
+        elif k == "assert":
+            self._emit(ind, f"if not {self._cond(s[1])}:")
+            self._emit(ind + 1, f"raise AssertFailed('assert failed at {s[2]}:{s[3]}')")
+        elif k == "log":
+            self._emit(ind, "pass")
+        else:
+            raise _Unsupported(k)
 
 
 def _assigned_vars(s):

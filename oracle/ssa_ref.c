@@ -587,6 +587,13 @@ uint32_t pzk_ref_witness(const PzkRefProgram* p, const uint8_t* inputs, uint8_t*
         } else if (cls == 3) {
           /* bit-field view: ((word >> s) & (2^n - 1)) << k */
           unsigned s_ = ex->aux & 255, n_ = (ex->aux >> 8) & 255, k_ = (ex->aux >> 16) & 255;
+          if (!(ex->ref & PZK_REF_VIEW_N) && s_ < 64 && n_ + k_ <= 64) {   /* the field stays inside one 64-bit word */
+            uint64_t v = U[slot] >> s_;
+            if (n_ < 64) v &= ((uint64_t)1 << n_) - 1;
+            w[0] = v << k_;
+            memcpy(dst, w, 32);
+            continue;
+          }
           uint64_t m[4] = {0, 0, 0, 0}, one[4] = {1, 0, 0, 0};
           if (ex->ref & PZK_REF_VIEW_N) memcpy(w, F + 4 * (uint64_t)slot, 32); else w[0] = U[slot];
           shr4(w, w, s_);

@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <unordered_map>
 #include <string>
 #include <vector>
 
@@ -80,10 +81,17 @@ struct pzk_circuit {
   u64* d_public = nullptr;
   uint64_t pub_cap = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;  // H2D of the next tile / D2H of the previous one under the evaluator
+  std::vector<cudaEvent_t> run_events; // events of the call in flight (destroyed by pzk_sync)
+  u64* d_lane_list = nullptr;          // export lanes + output rows of the call in flight
+  bool in_flight = false;
+  // witness digest (pzk_batch_set_digest)
+  bool digest_on = false;
+  u64* d_digest = nullptr;             // [batch_cap][4]
   // profiling
   bool prof = false;
-  double prof_ms[4] = {0, 0, 0, 0};
-  uint64_t prof_launches[4] = {0, 0, 0, 0};
+  double prof_ms[5] = {0, 0, 0, 0, 0};
+  uint64_t prof_launches[5] = {0, 0, 0, 0, 0};
   std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> pending;
   std::vector<double> seg_ms;  // accumulated eval time per segment (profiling)
   std::vector<int> pending_seg;
@@ -164,7 +172,8 @@ static void free_batch(pzk_circuit* c) {
   if (c->d_status) cudaFree(c->d_status);
   if (c->d_first_bad) cudaFree(c->d_first_bad);
   if (c->d_public) cudaFree(c->d_public);
-  c->d_inputs = nullptr; c->d_status = nullptr; c->d_first_bad = nullptr; c->d_public = nullptr;
+  if (c->d_digest) cudaFree(c->d_digest);
+  c->d_inputs = nullptr; c->d_status = nullptr; c->d_first_bad = nullptr; c->d_public = nullptr; c->d_digest = nullptr;
   c->batch_cap = 0; c->pub_cap = 0; c->d_inputs_bytes = 0;
 }
 
@@ -174,7 +183,9 @@ void pzk_circuit_close(pzk_circuit* c) {
   free_tile(c); free_batch(c);
   cudaFree(c->d_ops); cudaFree(c->d_fpool); cudaFree(c->d_coefs); cudaFree(c->d_coef_kind); cudaFree(c->d_coef_mag);
   cudaFree(c->d_list); cudaFree(c->d_in_table); cudaFree(c->d_rows); cudaFree(c->d_terms); cudaFree(c->d_exports); cudaFree(c->d_pub_entries);
+  if (c->in_flight) pzk_sync(c);
   if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   delete c;
 }
 
@@ -246,6 +257,7 @@ int pzk_circuit_open(const char* program_path, int cuda_device, pzk_circuit** ou
 
   CK(cudaSetDevice(cuda_device));
   CK(cudaStreamCreate(&c->stream));
+  CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   if (c->smem_bytes > 48 * 1024) CK(cudaFuncSetAttribute(eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
   {
     int per_sm = 0, n_sm = 0;
@@ -327,6 +339,7 @@ static int ensure_batch(pzk_circuit* c, uint64_t batch, uint64_t input_bytes) {
   CK(cudaMalloc((void**)&c->d_status, batch * 4));
   CK(cudaMalloc((void**)&c->d_first_bad, batch * 8));
   CK(cudaMalloc((void**)&c->d_public, std::max<uint64_t>(batch * n_pub * 32, 16)));
+  CK(cudaMalloc((void**)&c->d_digest, batch * 32));
   c->batch_cap = batch;
   return PZK_OK;
 }
@@ -358,32 +371,98 @@ static void prof_collect(pzk_circuit* c) {
   c->pending_seg.clear();
 }
 
-// run every tile of the resident batch; optional witness export for selected lanes
-static int run_batch(pzk_circuit* c, int check_rows, const uint64_t* export_lanes, uint64_t n_export,
-                     u64* d_witnesses /* [n_export][n_wires][4] device */) {
+// ---------------------------------------------------------------------------------------
+// One pass of the hot path over the resident (or streamed) batch.
+// ---------------------------------------------------------------------------------------
+struct RunOpts {
+  int check_rows = 1;
+  // full witnesses of selected lanes (device buffer, canonical): AoS rows or the R1CS checker's blocked layout
+  const uint64_t* export_lanes = nullptr;
+  uint64_t n_export = 0;
+  u64* d_witnesses = nullptr;
+  bool blocked = false;
+  // streamed call: packed host records in, results out, copies of tile k+1 / k-1 under the kernels of tile k
+  const uint8_t* h_packed = nullptr;
+  uint32_t* h_status = nullptr;
+  int64_t* h_first_bad = nullptr;
+  uint8_t* h_public = nullptr;
+  uint64_t* h_digest = nullptr;
+  bool async = false;  // return after enqueueing; pzk_sync() completes the call
+};
+
+static void release_run(pzk_circuit* c) {
+  for (cudaEvent_t e : c->run_events) cudaEventDestroy(e);
+  c->run_events.clear();
+  if (c->d_lane_list) { cudaFree(c->d_lane_list); c->d_lane_list = nullptr; }
+  c->in_flight = false;
+}
+
+int pzk_sync(pzk_circuit* c) {
+  if (!c) return PZK_EINVAL;
   CK(cudaSetDevice(c->device));
-  int rc = ensure_tile(c, c->batch);
+  cudaError_t e1 = cudaStreamSynchronize(c->stream), e2 = cudaStreamSynchronize(c->copy_stream);
+  cudaError_t e3 = cudaGetLastError();
+  release_run(c);
+  prof_collect(c);
+  if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
+    set_err(c, std::string("pzk_sync: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2 != cudaSuccess ? e2 : e3));
+    return PZK_ECUDA;
+  }
+  return PZK_OK;
+}
+
+static int run_batch(pzk_circuit* c, const RunOpts& o) {
+  CK(cudaSetDevice(c->device));
+  if (c->in_flight) { int rc0 = pzk_sync(c); if (rc0) return rc0; }
+  const bool streamed = o.h_packed != nullptr;
+  // a streamed call works in tiles of one wave so that the copies of its neighbours hide under a tile's kernels
+  uint64_t want = c->batch;
+  if (streamed && c->wave_lanes && want > c->wave_lanes && c->tile_lanes_cfg == 0) want = c->wave_lanes;
+  int rc = ensure_tile(c, want);
   if (rc) return rc;
-  const uint64_t L = c->L;
+  const uint64_t L = std::min<uint64_t>(c->L, (want + 127) / 128 * 128);
   const uint32_t n_pub = c->h.n_pub_out + c->h.n_pub_in;
+  const bool digest = c->digest_on;
+  const int store_all = (o.n_export > 0 || digest) ? 1 : 0;
+  const uint64_t n_tiles = (c->batch + L - 1) / L;
+  c->in_flight = true;
+  auto new_event = [&]() { cudaEvent_t e; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); c->run_events.push_back(e); return e; };
+  std::vector<cudaEvent_t> ev_in(streamed ? n_tiles : 0);
+  if (streamed) {
+    for (uint64_t t = 0; t < n_tiles; t++) {
+      const uint64_t base = t * L, n = std::min<uint64_t>(L, c->batch - base);
+      CK(cudaMemcpyAsync(reinterpret_cast<unsigned char*>(c->d_inputs) + base * c->packed_stride, o.h_packed + base * c->packed_stride,
+                         n * (uint64_t)c->packed_stride, cudaMemcpyHostToDevice, c->copy_stream));
+      ev_in[t] = new_event();
+      CK(cudaEventRecord(ev_in[t], c->copy_stream));
+    }
+  }
   CK(cudaMemsetAsync(c->d_status, 0, c->batch * 4, c->stream));
   CK(cudaMemsetAsync(c->d_first_bad, 0xff, c->batch * 8, c->stream));
+  if (digest) digest_init_kernel<<<(unsigned)((c->batch + 255) / 256), 256, 0, c->stream>>>(c->d_digest, c->batch);  // wire 0 = 1
+  // export lanes sorted into tiles: [lane in tile..., output row...] per tile, one upload
+  std::vector<std::vector<u64>> tl(o.n_export ? n_tiles : 0), tr(o.n_export ? n_tiles : 0);
+  std::vector<uint64_t> tl_off(n_tiles + 1, 0);
+  if (o.n_export) {
+    for (uint64_t j = 0; j < o.n_export; j++) { tl[o.export_lanes[j] / L].push_back(o.export_lanes[j] % L); tr[o.export_lanes[j] / L].push_back(j); }
+    std::vector<u64> flat;
+    for (uint64_t t = 0; t < n_tiles; t++) {
+      tl_off[t] = flat.size();
+      flat.insert(flat.end(), tl[t].begin(), tl[t].end());
+      flat.insert(flat.end(), tr[t].begin(), tr[t].end());
+    }
+    tl_off[n_tiles] = flat.size();
+    CK(cudaMalloc((void**)&c->d_lane_list, flat.size() * 8));
+    CK(cudaMemcpyAsync(c->d_lane_list, flat.data(), flat.size() * 8, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));  // `flat` is a local
+  }
   cudaEvent_t ra, rb;
   prof_begin(c, 3, ra, rb);
-  u64* d_lane_list = nullptr;
-  for (uint64_t base = 0; base < c->batch; base += L) {
-    const uint64_t n = std::min<uint64_t>(L, c->batch - base);
+  for (uint64_t t = 0; t < n_tiles; t++) {
+    const uint64_t base = t * L, n = std::min<uint64_t>(L, c->batch - base);
     const unsigned grid = (unsigned)((n + 127) / 128);
-    // export lanes that fall into this tile
-    std::vector<u64> tile_lanes, tile_rows;
-    for (uint64_t j = 0; j < n_export; j++)
-      if (export_lanes[j] >= base && export_lanes[j] < base + n) { tile_lanes.push_back(export_lanes[j] - base); tile_rows.push_back(j); }
-    if (!tile_lanes.empty()) {
-      if (d_lane_list) { cudaFree(d_lane_list); d_lane_list = nullptr; }
-      CK(cudaMalloc((void**)&d_lane_list, tile_lanes.size() * 8));
-      CK(cudaMemcpyAsync(d_lane_list, tile_lanes.data(), tile_lanes.size() * 8, cudaMemcpyHostToDevice, c->stream));
-      CK(cudaStreamSynchronize(c->stream));
-    }
+    if (streamed) CK(cudaStreamWaitEvent(c->stream, ev_in[t], 0));
+    const uint64_t n_tl = o.n_export ? tl[t].size() : 0;
     for (uint32_t s = 0; s < c->h.n_segments; s++) {
       const PzkSegment& sg = c->segs[s];
       cudaEvent_t ea, eb;
@@ -396,52 +475,68 @@ static int run_batch(pzk_circuit* c, int check_rows, const uint64_t* export_lane
           p.in_table = c->d_in_table; p.in_stride = c->packed_stride;
         } else { p.inputs = c->d_inputs + base * c->h.n_inputs * 4; p.in_table = nullptr; p.in_stride = 0; }
         p.n_inputs = c->h.n_inputs; p.status = c->d_status + base; p.n_u_slots = c->h.n_u_slots; p.n_f_slots = c->h.n_f_slots;
-        p.check_rows = check_rows; p.store_all = (n_export > 0) ? 1 : 0; p.sc.coefs = c->d_coefs; p.sc.coef_kind = c->d_coef_kind; p.sc.coef_mag = c->d_coef_mag;
+        p.check_rows = o.check_rows; p.store_all = store_all; p.sc.coefs = c->d_coefs; p.sc.coef_kind = c->d_coef_kind; p.sc.coef_mag = c->d_coef_mag;
         p.first_bad = c->d_first_bad + base;
         prof_begin(c, 0, ea, eb);
         eval_kernel<<<grid, 128, c->smem_bytes, c->stream>>>(p);
         prof_end(c, 0, ea, eb);
         if (c->prof) c->pending_seg.push_back((int)s);
       }
+      ExportParams p;
+      p.list = c->d_list; p.n_u_slots = c->h.n_u_slots; p.n_f_slots = c->h.n_f_slots;
+      p.U = c->d_U; p.F = c->d_F; p.L = L; p.lanes = nullptr; p.rows = nullptr; p.blocked = 0;
       if (!c->seg[s].pub.empty()) {
-        ExportParams p;
-        p.list = c->d_list;
         p.entries = c->d_pub_entries + c->seg[s].pub_off; p.n_entries = c->seg[s].pub.size();
-        p.n_u_slots = c->h.n_u_slots; p.n_f_slots = c->h.n_f_slots;
-        p.U = c->d_U; p.F = c->d_F; p.L = L; p.lanes = nullptr; p.lane_base = base; p.n_rows = n;
-        p.out = c->d_public; p.out_wires = n_pub; p.wire_off = 1;
+        p.lane_base = base; p.n_rows = n; p.out = c->d_public; p.out_wires = n_pub; p.wire_off = 1;
         prof_begin(c, 2, ea, eb);
         export_kernel<<<dim3(grid, 1), 128, 0, c->stream>>>(p);
         prof_end(c, 2, ea, eb);
       }
-      if (!tile_lanes.empty() && sg.n_exp) {
-        // rows of d_witnesses are indexed by position in export_lanes: handle each contiguous run
-        for (size_t q = 0; q < tile_lanes.size(); q++) {
-          ExportParams p;
-          p.list = c->d_list;
-          p.entries = c->d_exports + sg.exp_off; p.n_entries = sg.n_exp;
-          p.n_u_slots = c->h.n_u_slots; p.n_f_slots = c->h.n_f_slots;
-          p.U = c->d_U; p.F = c->d_F; p.L = L; p.lanes = d_lane_list + q; p.lane_base = tile_rows[q]; p.n_rows = 1;
-          p.out = d_witnesses; p.out_wires = c->h.n_wires; p.wire_off = 0;
-          unsigned gy = (unsigned)std::min<uint64_t>(std::max<uint64_t>(sg.n_exp / 128, 1), 1024);
-          prof_begin(c, 2, ea, eb);
-          export_rows_kernel<<<gy, 128, 0, c->stream>>>(p);
-          prof_end(c, 2, ea, eb);
-        }
+      if (digest && sg.n_exp) {
+        // every wire defined in this segment, folded while its slot still holds it
+        p.entries = c->d_exports + sg.exp_off; p.n_entries = sg.n_exp;
+        p.lane_base = base; p.n_rows = n; p.out = c->d_digest; p.out_wires = 0; p.wire_off = 0;
+        unsigned gy = (unsigned)std::min<uint64_t>(std::max<uint64_t>(1, (1184 + grid - 1) / grid), std::max<uint64_t>(1, sg.n_exp / 256));
+        prof_begin(c, 4, ea, eb);
+        digest_kernel<<<dim3(grid, gy), 128, 0, c->stream>>>(p);
+        prof_end(c, 4, ea, eb);
       }
+      if (n_tl && sg.n_exp) {
+        // full witnesses of the selected lanes of this tile: ONE launch per segment
+        p.entries = c->d_exports + sg.exp_off; p.n_entries = sg.n_exp;
+        p.lanes = c->d_lane_list + tl_off[t]; p.rows = p.lanes + n_tl; p.lane_base = 0; p.n_rows = n_tl;
+        p.out = o.d_witnesses; p.out_wires = c->h.n_wires; p.wire_off = 0; p.blocked = o.blocked ? 1 : 0;
+        prof_begin(c, 2, ea, eb);
+        if (n_tl >= 64) {
+          unsigned gx = (unsigned)((n_tl + 127) / 128);
+          unsigned gy = (unsigned)std::min<uint64_t>(std::max<uint64_t>(1, 2368 / gx), std::max<uint64_t>(1, sg.n_exp / 64));
+          export_kernel<<<dim3(gx, gy), 128, 0, c->stream>>>(p);
+        } else {
+          unsigned gx = (unsigned)std::min<uint64_t>(std::max<uint64_t>(sg.n_exp / 128, 1), 1024);
+          export_rows_kernel<<<dim3(gx, (unsigned)n_tl), 128, 0, c->stream>>>(p);
+        }
+        prof_end(c, 2, ea, eb);
+      }
+    }
+    if (streamed) {
+      cudaEvent_t done = new_event();
+      CK(cudaEventRecord(done, c->stream));
+      CK(cudaStreamWaitEvent(c->copy_stream, done, 0));
+      if (o.h_status) CK(cudaMemcpyAsync(o.h_status + base, c->d_status + base, n * 4, cudaMemcpyDeviceToHost, c->copy_stream));
+      if (o.h_first_bad) CK(cudaMemcpyAsync(o.h_first_bad + base, c->d_first_bad + base, n * 8, cudaMemcpyDeviceToHost, c->copy_stream));
+      if (o.h_public) CK(cudaMemcpyAsync(o.h_public + base * n_pub * 32, c->d_public + base * n_pub * 4, n * n_pub * 32, cudaMemcpyDeviceToHost, c->copy_stream));
+      if (o.h_digest && digest) CK(cudaMemcpyAsync(o.h_digest + base * 4, c->d_digest + base * 4, n * 32, cudaMemcpyDeviceToHost, c->copy_stream));
     }
   }
   prof_end(c, 3, ra, rb);
-  CK(cudaStreamSynchronize(c->stream));
-  CK(cudaGetLastError());
-  if (d_lane_list) cudaFree(d_lane_list);
-  prof_collect(c);
-  return PZK_OK;
+  if (o.async) return PZK_OK;
+  return pzk_sync(c);
 }
 
 int pzk_batch_upload(pzk_circuit* c, const uint8_t* inputs_le32, uint64_t batch) {
   if (!c || !inputs_le32 || batch == 0) return PZK_EINVAL;
   CK(cudaSetDevice(c->device));
+  if (c->in_flight) { int rc0 = pzk_sync(c); if (rc0) return rc0; }
   int rc = ensure_batch(c, batch, batch * c->h.n_inputs * 32);
   if (rc) return rc;
   c->batch = batch; c->packed = false;
@@ -459,6 +554,7 @@ int pzk_packed_layout(const pzk_circuit* c, uint32_t* kind, uint32_t* offset) {
 int pzk_batch_upload_packed(pzk_circuit* c, const uint8_t* packed, uint64_t batch) {
   if (!c || !packed || batch == 0) return PZK_EINVAL;
   CK(cudaSetDevice(c->device));
+  if (c->in_flight) { int rc0 = pzk_sync(c); if (rc0) return rc0; }
   int rc = ensure_batch(c, batch, batch * (uint64_t)c->packed_stride);
   if (rc) return rc;
   c->batch = batch; c->packed = true;
@@ -466,23 +562,88 @@ int pzk_batch_upload_packed(pzk_circuit* c, const uint8_t* packed, uint64_t batc
   CK(cudaStreamSynchronize(c->stream));
   return PZK_OK;
 }
+
+static int packed_call(pzk_circuit* c, const uint8_t* packed, uint64_t batch, uint32_t* status, int64_t* first_bad,
+                       uint8_t* public_le32, uint64_t* digest, bool async) {
+  if (!c || !packed || batch == 0) return PZK_EINVAL;
+  if (digest && !c->digest_on) { set_err(c, "digest requested but pzk_batch_set_digest(c, 1) was not called"); return PZK_EINVAL; }
+  CK(cudaSetDevice(c->device));
+  if (c->in_flight) { int rc0 = pzk_sync(c); if (rc0) return rc0; }
+  int rc = ensure_batch(c, batch, batch * (uint64_t)c->packed_stride);
+  if (rc) return rc;
+  c->batch = batch; c->packed = true;
+  RunOpts o;
+  o.h_packed = packed; o.h_status = status; o.h_first_bad = first_bad; o.h_public = public_le32; o.h_digest = digest; o.async = async;
+  return run_batch(c, o);
+}
+
 int pzk_witness_batch_packed(pzk_circuit* c, const uint8_t* packed, uint64_t batch, uint32_t* status,
                              int64_t* first_bad, uint8_t* public_le32) {
-  int rc = pzk_batch_upload_packed(c, packed, batch);
-  if (rc) return rc;
-  rc = run_batch(c, 1, nullptr, 0, nullptr);
-  if (rc) return rc;
-  return pzk_batch_download(c, status, first_bad, public_le32);
+  return packed_call(c, packed, batch, status, first_bad, public_le32, nullptr, false);
+}
+
+int pzk_witness_batch_packed_async(pzk_circuit* c, const uint8_t* packed, uint64_t batch, uint32_t* status,
+                                   int64_t* first_bad, uint8_t* public_le32, uint64_t* digest) {
+  return packed_call(c, packed, batch, status, first_bad, public_le32, digest, true);
+}
+
+int pzk_witness_batch_packed_digest(pzk_circuit* c, const uint8_t* packed, uint64_t batch, uint32_t* status,
+                                    int64_t* first_bad, uint8_t* public_le32, uint64_t* digest) {
+  return packed_call(c, packed, batch, status, first_bad, public_le32, digest, false);
+}
+
+// One host thread, several devices: the batch is cut into contiguous shares (share i = lanes
+// [i * batch / n, (i + 1) * batch / n)), every device runs its share asynchronously, then all are
+// joined.  No collective: the shares are independent.
+int pzk_witness_batch_packed_multi(pzk_circuit* const* handles, int n_handles, const uint8_t* packed, uint64_t batch,
+                                   uint32_t* status, int64_t* first_bad, uint8_t* public_le32, uint64_t* digest) {
+  if (!handles || n_handles <= 0 || !packed || batch == 0) return PZK_EINVAL;
+  int rc = PZK_OK;
+  int launched = 0;
+  for (int i = 0; i < n_handles; i++) {
+    pzk_circuit* c = handles[i];
+    if (!c || c->packed_stride != handles[0]->packed_stride || c->h.n_wires != handles[0]->h.n_wires) { rc = PZK_EINVAL; break; }
+    const uint64_t lo = batch * (uint64_t)i / n_handles, hi = batch * (uint64_t)(i + 1) / n_handles;
+    if (hi == lo) { launched++; continue; }
+    const uint64_t n_pub = c->h.n_pub_out + c->h.n_pub_in;
+    rc = packed_call(c, packed + lo * c->packed_stride, hi - lo, status ? status + lo : nullptr,
+                     first_bad ? first_bad + lo : nullptr, public_le32 ? public_le32 + lo * n_pub * 32 : nullptr,
+                     digest ? digest + lo * 4 : nullptr, true);
+    if (rc) break;
+    launched++;
+  }
+  for (int i = 0; i < launched && i < n_handles; i++) {
+    int r2 = pzk_sync(handles[i]);
+    if (rc == PZK_OK) rc = r2;
+  }
+  return rc;
+}
+
+int pzk_batch_set_digest(pzk_circuit* c, int on) {
+  if (!c) return PZK_EINVAL;
+  c->digest_on = on != 0;
+  return PZK_OK;
+}
+uint64_t pzk_digest_weight_of(uint32_t wire) { return pzk_digest_weight(wire); }
+int pzk_batch_download_digest(pzk_circuit* c, uint64_t* digest) {
+  if (!c || c->batch == 0 || !digest) return PZK_EINVAL;
+  if (!c->digest_on) { set_err(c, "pzk_batch_set_digest(c, 1) was not called before the run"); return PZK_EINVAL; }
+  CK(cudaSetDevice(c->device));
+  if (c->in_flight) { int rc0 = pzk_sync(c); if (rc0) return rc0; }
+  CK(cudaMemcpy(digest, c->d_digest, c->batch * 32, cudaMemcpyDeviceToHost));
+  return PZK_OK;
 }
 
 int pzk_batch_run(pzk_circuit* c, int check_rows) {
   if (!c || c->batch == 0) return PZK_EINVAL;
-  return run_batch(c, check_rows, nullptr, 0, nullptr);
+  RunOpts o; o.check_rows = check_rows;
+  return run_batch(c, o);
 }
 
 int pzk_batch_download(pzk_circuit* c, uint32_t* status, int64_t* first_bad, uint8_t* public_le32) {
   if (!c || c->batch == 0) return PZK_EINVAL;
   CK(cudaSetDevice(c->device));
+  if (c->in_flight) { int rc0 = pzk_sync(c); if (rc0) return rc0; }
   uint64_t n_pub = c->h.n_pub_out + c->h.n_pub_in;
   if (status) CK(cudaMemcpyAsync(status, c->d_status, c->batch * 4, cudaMemcpyDeviceToHost, c->stream));
   if (first_bad) CK(cudaMemcpyAsync(first_bad, c->d_first_bad, c->batch * 8, cudaMemcpyDeviceToHost, c->stream));
@@ -504,7 +665,8 @@ int pzk_witness_batch(pzk_circuit* c, const uint8_t* inputs_le32, uint64_t batch
     CK(cudaMalloc((void**)&d_wit, n_export * c->h.n_wires * 32));
     CK(cudaMemsetAsync(d_wit, 0, n_export * c->h.n_wires * 32, c->stream));
   }
-  rc = run_batch(c, 1, export_lanes, n_export, d_wit);
+  RunOpts o; o.export_lanes = export_lanes; o.n_export = n_export; o.d_witnesses = d_wit;
+  rc = run_batch(c, o);
   if (rc == PZK_OK && n_export) {
     cudaError_t e = cudaMemcpy(witnesses_le32, d_wit, n_export * c->h.n_wires * 32, cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) { set_err(c, cudaGetErrorString(e)); rc = PZK_ECUDA; }
@@ -546,7 +708,7 @@ int pzk_calculate_wtns_bin(pzk_circuit* c, const uint8_t* inputs_le32, uint8_t* 
 }
 
 int pzk_profile_get(pzk_circuit* c, int which, double* ms, uint64_t* launches) {
-  if (!c || which < 0 || which > 3) return PZK_EINVAL;
+  if (!c || which < 0 || which > 4) return PZK_EINVAL;
   if (ms) *ms = c->prof_ms[which];
   if (launches) *launches = c->prof_launches[which];
   return PZK_OK;
@@ -557,205 +719,372 @@ int pzk_profile_segments(pzk_circuit* c, double* ms, uint32_t n) {
   return (int)c->seg_ms.size();
 }
 void pzk_profile_reset(pzk_circuit* c) {
-  c->seg_ms.assign(c->seg_ms.size(), 0.0); for (int i = 0; i < 4; i++) { c->prof_ms[i] = 0; c->prof_launches[i] = 0; } }
+  c->seg_ms.assign(c->seg_ms.size(), 0.0); for (int i = 0; i < 5; i++) { c->prof_ms[i] = 0; c->prof_launches[i] = 0; } }
 void pzk_profile_enable(pzk_circuit* c, int on) { c->prof = on != 0; }
 
 // ---------------------------------------------------------------------------------------
-// Generic `wtns check`: any iden3 .r1cs against explicit witnesses (all wires field class).
+// Generic `wtns check`: any iden3 .r1cs against explicit witnesses.  The matrices are parsed and uploaded ONCE
+// per pzk_r1cs handle (the role of snarkjs' readR1cs); witnesses are checked in canonical form, either from host
+// memory (pzk_r1cs_check) or handed over on the device by the evaluator (pzk_r1cs_check_circuit).
 // ---------------------------------------------------------------------------------------
-struct R1csHost {
-  uint32_t n_wires = 0, n_constraints = 0;
+struct pzk_r1cs {
+  int device = 0;
+  uint32_t n_wires = 0, n_constraints = 0, n_pub_out = 0, n_pub_in = 0, n_prv_in = 0;
+  uint64_t n_terms = 0;
   std::vector<PzkRow> rows;
   std::vector<PzkTerm> terms;
   std::vector<PzkCoef> coefs;
+  std::vector<R1csTile> tiles;
+  PzkRow* d_rows = nullptr; PzkTerm* d_terms = nullptr; PzkCoef* d_coefs = nullptr;
+  unsigned char* d_kind = nullptr; u64* d_mag = nullptr; R1csTile* d_tiles = nullptr;
+  // witness planes of the last call are kept and reused while they are large enough
+  u64* d_W = nullptr; uint64_t W_lanes = 0;
+  u32* d_status = nullptr; unsigned long long* d_bad = nullptr; uint64_t st_cap = 0;
 };
 
-static int parse_r1cs(const char* path, R1csHost& r, std::string& err) {
+struct CoefKey {
+  uint64_t w[4];
+  bool operator==(const CoefKey& o) const { return w[0] == o.w[0] && w[1] == o.w[1] && w[2] == o.w[2] && w[3] == o.w[3]; }
+};
+struct CoefKeyHash {
+  size_t operator()(const CoefKey& k) const { return (size_t)(k.w[0] * 0x9e3779b97f4a7c15ull ^ k.w[1] * 0xc2b2ae3d27d4eb4full ^ k.w[2] * 0x165667b19e3779f9ull ^ k.w[3]); }
+};
+
+// every length in the file is checked against the bytes that are really there (a truncated or malformed
+// .r1cs is PZK_EFORMAT, never an out-of-bounds read)
+static int parse_r1cs(const char* path, pzk_r1cs& r, std::string& err) {
   FILE* f = fopen(path, "rb");
   if (!f) { err = std::string("cannot open ") + path; return PZK_EIO; }
   fseek(f, 0, SEEK_END); long sz = ftell(f); fseek(f, 0, SEEK_SET);
+  if (sz < 0) { fclose(f); err = "cannot size file"; return PZK_EIO; }
   std::vector<uint8_t> buf((size_t)sz);
-  if (fread(buf.data(), 1, (size_t)sz, f) != (size_t)sz) { fclose(f); err = "short read"; return PZK_EIO; }
+  if (sz && fread(buf.data(), 1, (size_t)sz, f) != (size_t)sz) { fclose(f); err = "short read"; return PZK_EIO; }
   fclose(f);
-  if (sz < 12 || memcmp(buf.data(), "r1cs", 4) != 0) { err = "not an r1cs file"; return PZK_EFORMAT; }
+  const uint64_t size = (uint64_t)sz;
+  if (size < 12 || memcmp(buf.data(), "r1cs", 4) != 0) { err = "not an r1cs file"; return PZK_EFORMAT; }
   uint32_t nsec; memcpy(&nsec, buf.data() + 8, 4);
-  size_t pos = 12;
-  const uint8_t* hdr = nullptr; const uint8_t* cons = nullptr; uint64_t cons_len = 0;
-  for (uint32_t s = 0; s < nsec && pos + 12 <= (size_t)sz; s++) {
+  uint64_t pos = 12;
+  const uint8_t* hdr = nullptr; uint64_t hdr_len = 0; const uint8_t* cons = nullptr; uint64_t cons_len = 0;
+  for (uint32_t s = 0; s < nsec; s++) {
+    if (pos + 12 > size) { err = "r1cs: truncated section table"; return PZK_EFORMAT; }
     uint32_t type; uint64_t len; memcpy(&type, buf.data() + pos, 4); memcpy(&len, buf.data() + pos + 4, 8);
     pos += 12;
-    if (type == 1) hdr = buf.data() + pos;
+    if (len > size - pos) { err = "r1cs: section " + std::to_string(type) + " runs past the end of the file"; return PZK_EFORMAT; }
+    if (type == 1) { hdr = buf.data() + pos; hdr_len = len; }
     if (type == 2) { cons = buf.data() + pos; cons_len = len; }
     pos += len;
   }
   if (!hdr || !cons) { err = "r1cs: missing header or constraint section"; return PZK_EFORMAT; }
+  if (hdr_len < 4) { err = "r1cs: header section too short"; return PZK_EFORMAT; }
   uint32_t n8; memcpy(&n8, hdr, 4);
-  if (n8 != 32 || memcmp(hdr + 4, pzk::FR_P.w, 32) != 0) { err = "r1cs: prime is not the BN254 scalar field"; return PZK_EFORMAT; }
+  if (n8 != 32 || hdr_len < 4 + 32 + 28 || memcmp(hdr + 4, pzk::FR_P.w, 32) != 0) { err = "r1cs: prime is not the BN254 scalar field"; return PZK_EFORMAT; }
   memcpy(&r.n_wires, hdr + 36, 4);
+  memcpy(&r.n_pub_out, hdr + 40, 4); memcpy(&r.n_pub_in, hdr + 44, 4); memcpy(&r.n_prv_in, hdr + 48, 4);
   memcpy(&r.n_constraints, hdr + 36 + 16 + 8, 4);
-  std::map<std::string, uint32_t> cidx;
+  if (r.n_wires == 0) { err = "r1cs: no wires"; return PZK_EFORMAT; }
+  if ((uint64_t)r.n_constraints * 12 > cons_len) { err = "r1cs: constraint section shorter than its constraint count"; return PZK_EFORMAT; }
+  std::unordered_map<CoefKey, uint32_t, CoefKeyHash> cidx;
+  r.rows.reserve(r.n_constraints);
+  r.terms.reserve(cons_len / 36);
   const uint8_t* q = cons; const uint8_t* end = cons + cons_len;
   for (uint32_t i = 0; i < r.n_constraints; i++) {
     PzkRow row; row.term_off = (uint32_t)r.terms.size(); row.kind = 0; row.index = i;
     uint16_t cnt[3];
     for (int part = 0; part < 3; part++) {
-      if (q + 4 > end) { err = "r1cs: truncated"; return PZK_EFORMAT; }
+      if (end - q < 4) { err = "r1cs: truncated"; return PZK_EFORMAT; }
       uint32_t n; memcpy(&n, q, 4); q += 4;
       if (n > 65535) { err = "r1cs: linear combination too long"; return PZK_EFORMAT; }
+      if ((uint64_t)(end - q) < (uint64_t)n * 36) { err = "r1cs: truncated"; return PZK_EFORMAT; }
       cnt[part] = (uint16_t)n;
       for (uint32_t k = 0; k < n; k++) {
-        if (q + 36 > end) { err = "r1cs: truncated"; return PZK_EFORMAT; }
         uint32_t wire; memcpy(&wire, q, 4);
-        std::string key((const char*)q + 4, 32);
+        CoefKey key; memcpy(key.w, q + 4, 32);
         q += 36;
+        if (wire >= r.n_wires) { err = "r1cs: wire index out of range"; return PZK_EFORMAT; }
         auto it = cidx.find(key);
         uint32_t ci;
         if (it == cidx.end()) {
-          ci = (uint32_t)r.coefs.size(); cidx[key] = ci;
-          PzkCoef pc; memcpy(pc.plain, key.data(), 32);
-          pzk::U256 v = pzk::U256::from_limbs(pc.plain[0], pc.plain[1], pc.plain[2], pc.plain[3]);
-          pzk::U256 m1 = pzk::fr_to_mont(pzk::fr_reduce(v)), m2 = pzk::fr_to_mont(m1);
-          memcpy(pc.mont, m1.w, 32); memcpy(pc.mont2, m2.w, 32);
+          ci = (uint32_t)r.coefs.size(); cidx.emplace(key, ci);
+          PzkCoef pc;
+          pzk::U256 v = pzk::fr_reduce(pzk::U256::from_limbs(key.w[0], key.w[1], key.w[2], key.w[3]));
+          pzk::U256 m1 = pzk::fr_to_mont(v), m2 = pzk::fr_to_mont(m1);
+          memcpy(pc.plain, v.w, 32); memcpy(pc.mont, m1.w, 32); memcpy(pc.mont2, m2.w, 32);
           r.coefs.push_back(pc);
         } else ci = it->second;
         PzkTerm t; t.ref = (2u << 30) | wire; t.coef = ci;
-        if (wire >= r.n_wires) { err = "r1cs: wire index out of range"; return PZK_EFORMAT; }
         r.terms.push_back(t);
       }
     }
     row.na = cnt[0]; row.nb = cnt[1]; row.nc = cnt[2];
     r.rows.push_back(row);
   }
+  r.n_terms = r.terms.size();
+  if (r.n_terms >= (1ull << 32)) { err = "r1cs: too many terms"; return PZK_EFORMAT; }
+  // tiles of the A/B/C stream: at most R1CS_TILE_ROWS rows and R1CS_TILE_TERMS terms, even first term
+  size_t i = 0, n = r.rows.size();
+  while (i < n) {
+    R1csTile t; t.row0 = (uint32_t)i; t.term0 = r.rows[i].term_off & ~1u;
+    uint32_t end_term = r.rows[i].term_off;
+    uint32_t nr = 0;
+    while (i < n && nr < R1CS_TILE_ROWS) {
+      uint32_t nt = r.rows[i].na + r.rows[i].nb + r.rows[i].nc;
+      if (nt + 2 > R1CS_TILE_TERMS) { err = "r1cs: a constraint has too many terms for the streaming tile"; return PZK_EFORMAT; }
+      if (r.rows[i].term_off + nt - t.term0 + 1 > R1CS_TILE_TERMS) break;
+      end_term = r.rows[i].term_off + nt; nr++; i++;
+    }
+    t.n_rows = nr; t.n_terms = end_term - t.term0;
+    r.tiles.push_back(t);
+  }
   return PZK_OK;
 }
 
-static int check_batch_impl(R1csHost& r, const uint8_t* witnesses_le32, uint64_t batch, int cuda_device,
-                            int* verdicts, int64_t* first_bad, double* kernel_ms, char* err, size_t err_len) {
-  int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_err(err, err_len, "no CUDA device"); return PZK_ENODEVICE; }
 #define CKE(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_err(err, err_len, std::string(#call) + ": " + cudaGetErrorString(e_)); return PZK_ECUDA; } } while (0)
-  CKE(cudaSetDevice(cuda_device));
-  // tiles of the A/B/C stream: at most R1CS_TILE_ROWS rows and R1CS_TILE_TERMS terms, even first term
-  std::vector<R1csTile> tiles;
-  {
-    size_t i = 0, n = r.rows.size();
-    while (i < n) {
-      R1csTile t; t.row0 = (uint32_t)i; t.term0 = r.rows[i].term_off & ~1u;
-      uint32_t end_term = r.rows[i].term_off;
-      uint32_t nr = 0;
-      while (i < n && nr < R1CS_TILE_ROWS) {
-        uint32_t nt = r.rows[i].na + r.rows[i].nb + r.rows[i].nc;
-        if (nt + 2 > R1CS_TILE_TERMS) { set_err(err, err_len, "r1cs: a constraint has too many terms for the streaming tile"); return PZK_EFORMAT; }
-        if (r.rows[i].term_off + nt - t.term0 + 1 > R1CS_TILE_TERMS) break;
-        end_term = r.rows[i].term_off + nt; nr++; i++;
-      }
-      t.n_rows = nr; t.n_terms = end_term - t.term0;
-      tiles.push_back(t);
-    }
-  }
-  PzkRow* d_rows; PzkTerm* d_terms; PzkCoef* d_coefs; unsigned char* d_kind; u64* d_mag; R1csTile* d_tiles;
+
+void pzk_r1cs_close(pzk_r1cs* r) {
+  if (!r) return;
+  cudaSetDevice(r->device);
+  cudaFree(r->d_rows); cudaFree(r->d_terms); cudaFree(r->d_coefs); cudaFree(r->d_kind); cudaFree(r->d_mag); cudaFree(r->d_tiles);
+  cudaFree(r->d_W); cudaFree(r->d_status); cudaFree(r->d_bad);
+  delete r;
+}
+
+int pzk_r1cs_open(const char* r1cs_path, int cuda_device, pzk_r1cs** out, char* err, size_t err_len) {
+  if (!r1cs_path || !out) return PZK_EINVAL;
+  *out = nullptr;
+  pzk_r1cs* r = new pzk_r1cs();
+  r->device = cuda_device;
+  std::string e;
+  int rc = parse_r1cs(r1cs_path, *r, e);   // format errors are reported before any device work
+  if (rc) { set_err(err, err_len, e); delete r; return rc; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_err(err, err_len, "no CUDA device"); delete r; return PZK_ENODEVICE; }
+  if (cuda_device < 0 || cuda_device >= ndev) { delete r; return PZK_EINVAL; }
+  auto fail = [&](cudaError_t ce, const char* what) { set_err(err, err_len, std::string(what) + ": " + cudaGetErrorString(ce)); pzk_r1cs_close(r); return PZK_ECUDA; };
+  cudaError_t ce;
+  if ((ce = cudaSetDevice(cuda_device)) != cudaSuccess) return fail(ce, "cudaSetDevice");
   std::vector<unsigned char> kind; std::vector<u64> mag;
-  classify_coefs(r.coefs.data(), (uint32_t)r.coefs.size(), kind, mag);
-  std::vector<PzkTerm> terms_padded = r.terms;
-  terms_padded.resize(r.terms.size() + 4, PzkTerm{0, 0});
-  CKE(upload(&d_rows, r.rows.data(), r.rows.size() * sizeof(PzkRow)));
-  CKE(upload(&d_terms, terms_padded.data(), terms_padded.size() * sizeof(PzkTerm)));
-  CKE(upload(&d_coefs, r.coefs.data(), r.coefs.size() * sizeof(PzkCoef)));
-  CKE(upload(&d_kind, kind.data(), kind.size()));
-  CKE(upload(&d_mag, mag.data(), mag.size() * 8));
-  CKE(upload(&d_tiles, tiles.data(), tiles.size() * sizeof(R1csTile)));
-  CKE(cudaFuncSetAttribute(r1cs_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R1CS_SMEM_BYTES));
-  size_t free_b = 0, total_b = 0;
-  CKE(cudaMemGetInfo(&free_b, &total_b));
-  uint64_t per_lane = (uint64_t)r.n_wires * 64;  // AoS staging + blocked Montgomery plane
-  uint64_t L = std::max<uint64_t>(32, (uint64_t)(free_b * 0.8) / per_lane / 32 * 32);
-  if (L > (batch + 31) / 32 * 32) L = (batch + 31) / 32 * 32;
-  u64 *d_wit, *d_F; u32* d_status; unsigned long long* d_bad;
-  CKE(cudaMalloc((void**)&d_wit, L * r.n_wires * 32));
-  CKE(cudaMalloc((void**)&d_F, L * r.n_wires * 32));
-  CKE(cudaMemset(d_F, 0, L * r.n_wires * 32));  // padding lanes of the last warp read zeros
-  CKE(cudaMalloc((void**)&d_status, (batch + 32) * 4));
-  CKE(cudaMalloc((void**)&d_bad, (batch + 32) * 8));
-  CKE(cudaMemset(d_status, 0, (batch + 32) * 4));
-  CKE(cudaMemset(d_bad, 0xff, (batch + 32) * 8));
-  cudaEvent_t ea, eb; cudaEventCreate(&ea); cudaEventCreate(&eb);
-  double total_ms = 0;
-  int n_sm = 148;
-  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, cuda_device);
-  for (uint64_t base = 0; base < batch; base += L) {
-    uint64_t n = std::min<uint64_t>(L, batch - base);
-    CKE(cudaMemcpy(d_wit, witnesses_le32 + base * r.n_wires * 32, n * r.n_wires * 32, cudaMemcpyHostToDevice));
-    unsigned gridl = (unsigned)((n + 127) / 128);
-    unsigned gy = (unsigned)std::min<uint64_t>(std::max<uint64_t>(r.n_wires / 64, 1), 4096);
-    load_witness_blocked_kernel<<<dim3(gridl, gy), 128>>>(d_wit, r.n_wires, n, d_F, d_status + base);
-    R1csParams p;
-    p.rows = d_rows; p.terms = d_terms; p.tiles = d_tiles; p.n_tiles = (u32)tiles.size();
-    // enough chunks to fill the machine ~4 CTAs deep, at least 4 tiles per chunk when possible
-    uint64_t want_ctas = (uint64_t)n_sm * 4;
-    uint64_t chunks = std::max<uint64_t>(1, want_ctas / gridl);
-    if (chunks > tiles.size()) chunks = tiles.size();
-    p.tiles_per_chunk = (u32)((tiles.size() + chunks - 1) / chunks);
-    chunks = (tiles.size() + p.tiles_per_chunk - 1) / p.tiles_per_chunk;
-    p.coefs = d_coefs; p.coef_kind = d_kind; p.coef_mag = d_mag; p.F = d_F; p.n_wires = r.n_wires; p.n_lanes = n;
-    p.status = d_status + base; p.first_bad = d_bad + base;
-    cudaEventRecord(ea);
-    r1cs_stream_kernel<<<dim3((unsigned)chunks, gridl), 128, R1CS_SMEM_BYTES>>>(p);
-    cudaEventRecord(eb);
-    CKE(cudaDeviceSynchronize());
-    float ms = 0; cudaEventElapsedTime(&ms, ea, eb); total_ms += ms;
+  classify_coefs(r->coefs.data(), (uint32_t)r->coefs.size(), kind, mag);
+  std::vector<PzkTerm> terms_padded = r->terms;
+  terms_padded.resize(r->terms.size() + 4, PzkTerm{2u << 30, 0});  // padding terms read wire 0
+  if ((ce = upload(&r->d_rows, r->rows.data(), r->rows.size() * sizeof(PzkRow))) != cudaSuccess) return fail(ce, "upload rows");
+  if ((ce = upload(&r->d_terms, terms_padded.data(), terms_padded.size() * sizeof(PzkTerm))) != cudaSuccess) return fail(ce, "upload terms");
+  if ((ce = upload(&r->d_coefs, r->coefs.data(), r->coefs.size() * sizeof(PzkCoef))) != cudaSuccess) return fail(ce, "upload coefficients");
+  if ((ce = upload(&r->d_kind, kind.data(), kind.size())) != cudaSuccess) return fail(ce, "upload coefficient kinds");
+  if ((ce = upload(&r->d_mag, mag.data(), mag.size() * 8)) != cudaSuccess) return fail(ce, "upload coefficient magnitudes");
+  if ((ce = upload(&r->d_tiles, r->tiles.data(), r->tiles.size() * sizeof(R1csTile))) != cudaSuccess) return fail(ce, "upload tiles");
+  if ((ce = cudaFuncSetAttribute(r1cs_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R1CS_SMEM_BYTES)) != cudaSuccess) return fail(ce, "cudaFuncSetAttribute");
+  // the host copies are only needed for parsing
+  std::vector<PzkTerm>().swap(r->terms); std::vector<PzkCoef>().swap(r->coefs);
+  *out = r;
+  return PZK_OK;
+}
+
+uint32_t pzk_r1cs_wires(const pzk_r1cs* r) { return r ? r->n_wires : 0; }
+uint32_t pzk_r1cs_constraints(const pzk_r1cs* r) { return r ? r->n_constraints : 0; }
+uint64_t pzk_r1cs_terms(const pzk_r1cs* r) { return r ? r->n_terms : 0; }
+
+// witness planes for `lanes` lanes (rounded up to whole warps), status / first_bad for `batch`
+static int r1cs_reserve(pzk_r1cs* r, uint64_t lanes, uint64_t batch, char* err, size_t err_len) {
+  lanes = (lanes + 31) / 32 * 32;
+  if (lanes > r->W_lanes) {
+    if (r->d_W) { cudaFree(r->d_W); r->d_W = nullptr; r->W_lanes = 0; }
+    CKE(cudaMalloc((void**)&r->d_W, lanes * r->n_wires * 32));
+    r->W_lanes = lanes;
   }
+  if (batch + 32 > r->st_cap) {
+    if (r->d_status) cudaFree(r->d_status);
+    if (r->d_bad) cudaFree(r->d_bad);
+    r->d_status = nullptr; r->d_bad = nullptr; r->st_cap = 0;
+    CKE(cudaMalloc((void**)&r->d_status, (batch + 32) * 4));
+    CKE(cudaMalloc((void**)&r->d_bad, (batch + 32) * 8));
+    r->st_cap = batch + 32;
+  }
+  return PZK_OK;
+}
+
+// lanes per pass that fit next to what is already resident on the device
+static uint64_t r1cs_lanes_that_fit(pzk_r1cs* r, uint64_t batch, uint64_t extra_per_lane) {
+  size_t free_b = 0, total_b = 0;
+  cudaMemGetInfo(&free_b, &total_b);
+  uint64_t have = (uint64_t)free_b + r->W_lanes * r->n_wires * 32;
+  uint64_t per_lane = (uint64_t)r->n_wires * 32 + extra_per_lane;
+  uint64_t L = std::max<uint64_t>(32, (uint64_t)(have * 0.85) / per_lane / 32 * 32);
+  return std::min<uint64_t>(L, (batch + 31) / 32 * 32);
+}
+
+// one launch of the stream kernel over n lanes whose canonical wires are in r->d_W
+static int r1cs_launch(pzk_r1cs* r, uint64_t n, uint64_t out_base, cudaStream_t stream, float* ms, char* err, size_t err_len) {
+  if (r->n_constraints == 0) { if (ms) *ms = 0; return PZK_OK; }   // nothing to check: every verdict stays 1
+  int n_sm = 148;
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, r->device);
+  const unsigned gridl = (unsigned)((n + 127) / 128);
+  R1csParams p;
+  p.rows = r->d_rows; p.terms = r->d_terms; p.tiles = r->d_tiles; p.n_tiles = (u32)r->tiles.size();
+  // row chunks: fill the machine about 2 resident waves deep (6 CTAs per SM), at least one tile per chunk
+  uint64_t want_ctas = (uint64_t)n_sm * 12;
+  uint64_t chunks = std::max<uint64_t>(1, want_ctas / gridl);
+  if (chunks > r->tiles.size()) chunks = r->tiles.size();
+  p.tiles_per_chunk = (u32)((r->tiles.size() + chunks - 1) / chunks);
+  chunks = (r->tiles.size() + p.tiles_per_chunk - 1) / p.tiles_per_chunk;
+  p.coefs = r->d_coefs; p.coef_kind = r->d_kind; p.coef_mag = r->d_mag; p.W = r->d_W; p.n_wires = r->n_wires; p.n_lanes = n;
+  p.status = r->d_status + out_base; p.first_bad = r->d_bad + out_base;
+  cudaEvent_t ea, eb; cudaEventCreate(&ea); cudaEventCreate(&eb);
+  cudaEventRecord(ea, stream);
+  r1cs_stream_kernel<<<dim3((unsigned)chunks, gridl), 128, R1CS_SMEM_BYTES, stream>>>(p);
+  cudaEventRecord(eb, stream);
+  cudaError_t ce = cudaStreamSynchronize(stream);
+  if (ce == cudaSuccess) ce = cudaGetLastError();
+  float t = 0; cudaEventElapsedTime(&t, ea, eb);
+  cudaEventDestroy(ea); cudaEventDestroy(eb);
+  if (ce != cudaSuccess) { set_err(err, err_len, std::string("r1cs_stream_kernel: ") + cudaGetErrorString(ce)); return PZK_ECUDA; }
+  if (ms) *ms = t;
+  return PZK_OK;
+}
+
+static int r1cs_collect(pzk_r1cs* r, uint64_t batch, int* verdicts, int64_t* first_bad, char* err, size_t err_len) {
   std::vector<u32> st(batch); std::vector<unsigned long long> bad(batch);
-  CKE(cudaMemcpy(st.data(), d_status, batch * 4, cudaMemcpyDeviceToHost));
-  CKE(cudaMemcpy(bad.data(), d_bad, batch * 8, cudaMemcpyDeviceToHost));
+  CKE(cudaMemcpy(st.data(), r->d_status, batch * 4, cudaMemcpyDeviceToHost));
+  CKE(cudaMemcpy(bad.data(), r->d_bad, batch * 8, cudaMemcpyDeviceToHost));
   for (uint64_t i = 0; i < batch; i++) {
     verdicts[i] = (st[i] & PZK_LANE_CONSTRAINT) ? 0 : 1;
     if (first_bad) first_bad[i] = (st[i] & PZK_LANE_CONSTRAINT) ? (int64_t)bad[i] : -1;
   }
-  if (kernel_ms) *kernel_ms = total_ms;
-  cudaEventDestroy(ea); cudaEventDestroy(eb);
-  cudaFree(d_rows); cudaFree(d_terms); cudaFree(d_coefs); cudaFree(d_kind); cudaFree(d_mag); cudaFree(d_tiles);
-  cudaFree(d_wit); cudaFree(d_F); cudaFree(d_status); cudaFree(d_bad);
   return PZK_OK;
+}
+
+int pzk_r1cs_check(pzk_r1cs* r, const uint8_t* witnesses_le32, uint64_t batch, int* verdicts, int64_t* first_bad,
+                   double* kernel_ms, char* err, size_t err_len) {
+  if (!r || !witnesses_le32 || !verdicts || batch == 0) return PZK_EINVAL;
+  CKE(cudaSetDevice(r->device));
+  const uint64_t L = r1cs_lanes_that_fit(r, batch, (uint64_t)r->n_wires * 32);  // + the AoS staging buffer
+  int rc = r1cs_reserve(r, L, batch, err, err_len);
+  if (rc) return rc;
+  u64* d_wit = nullptr;
+  CKE(cudaMalloc((void**)&d_wit, std::min<uint64_t>(L, batch) * r->n_wires * 32));
+  CKE(cudaMemset(r->d_status, 0, (batch + 32) * 4));
+  CKE(cudaMemset(r->d_bad, 0xff, (batch + 32) * 8));
+  double total_ms = 0;
+  for (uint64_t base = 0; base < batch && rc == PZK_OK; base += L) {
+    const uint64_t n = std::min<uint64_t>(L, batch - base);
+    cudaError_t ce = cudaMemcpy(d_wit, witnesses_le32 + base * r->n_wires * 32, n * r->n_wires * 32, cudaMemcpyHostToDevice);
+    if (ce != cudaSuccess) { set_err(err, err_len, cudaGetErrorString(ce)); rc = PZK_ECUDA; break; }
+    if (n % 32) cudaMemset(r->d_W + (n / 32) * r->n_wires * 128, 0, (uint64_t)r->n_wires * 1024);  // padding lanes of the last warp
+    const unsigned gridl = (unsigned)((n + 127) / 128);
+    const unsigned gy = (unsigned)std::min<uint64_t>(std::max<uint64_t>(r->n_wires / 64, 1), 4096);
+    load_witness_blocked_kernel<<<dim3(gridl, gy), 128>>>(d_wit, r->n_wires, n, r->d_W, r->d_status + base);
+    float ms = 0;
+    rc = r1cs_launch(r, n, base, 0, &ms, err, err_len);
+    total_ms += ms;
+  }
+  cudaFree(d_wit);
+  if (rc) return rc;
+  if (kernel_ms) *kernel_ms = total_ms;
+  return r1cs_collect(r, batch, verdicts, first_bad, err, err_len);
+}
+
+// Device-resident hand-off (the north star's two kernels back to back): the evaluator runs the resident batch
+// of `c` and writes every wire of the selected lanes straight into the checker's planes - canonical values,
+// blocked by warps, no host round trip of the 72 MB witnesses - then the stream kernel checks EVERY row of the
+// .r1cs on them.  Wires are matched by index: the .r1cs must be the one compiled with the program.
+int pzk_r1cs_check_circuit(pzk_r1cs* r, pzk_circuit* c, const uint64_t* lanes, uint64_t n_lanes, int* verdicts,
+                           int64_t* first_bad, double* eval_ms, double* check_ms, char* err, size_t err_len) {
+  if (!r || !c || !lanes || !verdicts || n_lanes == 0 || c->batch == 0) return PZK_EINVAL;
+  if (r->device != c->device) { set_err(err, err_len, "the r1cs handle and the circuit live on different devices"); return PZK_EINVAL; }
+  if (r->n_wires != c->h.n_wires || r->n_constraints != c->h.n_constraints) {
+    set_err(err, err_len, "Invalid witness length. Circuit: " + std::to_string(r->n_wires) + ", witness: " + std::to_string(c->h.n_wires) +
+                              " (this .r1cs does not belong to the program: different wire layout)");
+    return PZK_EFORMAT;
+  }
+  for (uint64_t j = 0; j < n_lanes; j++) if (lanes[j] >= c->batch) return PZK_EINVAL;
+  CKE(cudaSetDevice(r->device));
+  const uint64_t fit = r1cs_lanes_that_fit(r, n_lanes, 0);
+  if (fit < (n_lanes + 31) / 32 * 32) { set_err(err, err_len, "not enough device memory for " + std::to_string(n_lanes) + " full witnesses (" + std::to_string(fit) + " fit)"); return PZK_ENOMEM; }
+  int rc = r1cs_reserve(r, n_lanes, n_lanes, err, err_len);
+  if (rc) return rc;
+  CKE(cudaMemsetAsync(r->d_status, 0, (n_lanes + 32) * 4, c->stream));
+  CKE(cudaMemsetAsync(r->d_bad, 0xff, (n_lanes + 32) * 8, c->stream));
+  // the evaluator's export writes every wire 1.. of every selected lane; padding lanes of the last warp read zeros
+  if (n_lanes % 32) CKE(cudaMemsetAsync(r->d_W + (n_lanes / 32) * r->n_wires * 128, 0, (uint64_t)r->n_wires * 1024, c->stream));
+  cudaEvent_t ea, eb; cudaEventCreate(&ea); cudaEventCreate(&eb);
+  cudaEventRecord(ea, c->stream);
+  RunOpts o; o.export_lanes = lanes; o.n_export = n_lanes; o.d_witnesses = r->d_W; o.blocked = true;
+  rc = run_batch(c, o);
+  if (rc) { set_err(err, err_len, c->err); cudaEventDestroy(ea); cudaEventDestroy(eb); return rc; }
+  wire0_blocked_kernel<<<(unsigned)((n_lanes + 127) / 128), 128, 0, c->stream>>>(r->d_W, r->n_wires, n_lanes);
+  cudaEventRecord(eb, c->stream);
+  CKE(cudaStreamSynchronize(c->stream));
+  float t_eval = 0; cudaEventElapsedTime(&t_eval, ea, eb);
+  cudaEventDestroy(ea); cudaEventDestroy(eb);
+  float t_check = 0;
+  rc = r1cs_launch(r, n_lanes, 0, c->stream, &t_check, err, err_len);
+  if (rc) return rc;
+  if (eval_ms) *eval_ms = t_eval;
+  if (check_ms) *check_ms = t_check;
+  return r1cs_collect(r, n_lanes, verdicts, first_bad, err, err_len);
 }
 
 int pzk_r1cs_check_batch(const char* r1cs_path, const uint8_t* witnesses_le32, uint64_t batch, int cuda_device,
                          int* verdicts, int64_t* first_bad, double* kernel_ms, char* err, size_t err_len) {
   if (!r1cs_path || !witnesses_le32 || !verdicts || batch == 0) return PZK_EINVAL;
-  R1csHost r; std::string e;
-  int rc = parse_r1cs(r1cs_path, r, e);
-  if (rc) { set_err(err, err_len, e); return rc; }
-  return check_batch_impl(r, witnesses_le32, batch, cuda_device, verdicts, first_bad, kernel_ms, err, err_len);
+  pzk_r1cs* r = nullptr;
+  int rc = pzk_r1cs_open(r1cs_path, cuda_device, &r, err, err_len);
+  if (rc) return rc;
+  rc = pzk_r1cs_check(r, witnesses_le32, batch, verdicts, first_bad, kernel_ms, err, err_len);
+  pzk_r1cs_close(r);
+  return rc;
 }
 
-int pzk_wtns_check(const char* r1cs_path, const uint8_t* wtns, uint64_t wtns_len, int cuda_device, int* verdict,
-                   int64_t* first_bad, char* err, size_t err_len) {
-  if (!r1cs_path || !wtns || !verdict) return PZK_EINVAL;
+// section table of a .wtns image, every length checked against wtns_len
+static int parse_wtns(const uint8_t* wtns, uint64_t wtns_len, const uint8_t** data, uint32_t* n_wires, char* err, size_t err_len) {
   if (wtns_len < 12 || memcmp(wtns, "wtns", 4) != 0) { set_err(err, err_len, "not a wtns file"); return PZK_EFORMAT; }
   uint32_t nsec; memcpy(&nsec, wtns + 8, 4);
   uint64_t pos = 12;
-  const uint8_t* hdr = nullptr; const uint8_t* data = nullptr; uint64_t data_len = 0;
-  for (uint32_t s = 0; s < nsec && pos + 12 <= wtns_len; s++) {
+  const uint8_t* hdr = nullptr; uint64_t hdr_len = 0; const uint8_t* dat = nullptr; uint64_t data_len = 0;
+  for (uint32_t s = 0; s < nsec; s++) {
+    if (pos + 12 > wtns_len) { set_err(err, err_len, "wtns: truncated section table"); return PZK_EFORMAT; }
     uint32_t type; uint64_t len; memcpy(&type, wtns + pos, 4); memcpy(&len, wtns + pos + 4, 8);
     pos += 12;
-    if (type == 1) hdr = wtns + pos;
-    if (type == 2) { data = wtns + pos; data_len = len; }
+    if (len > wtns_len - pos) { set_err(err, err_len, "wtns: section runs past the end of the buffer"); return PZK_EFORMAT; }
+    if (type == 1) { hdr = wtns + pos; hdr_len = len; }
+    if (type == 2) { dat = wtns + pos; data_len = len; }
     pos += len;
   }
-  if (!hdr || !data) { set_err(err, err_len, "wtns: missing section"); return PZK_EFORMAT; }
+  if (!hdr || !dat) { set_err(err, err_len, "wtns: missing section"); return PZK_EFORMAT; }
+  if (hdr_len < 4) { set_err(err, err_len, "wtns: header section too short"); return PZK_EFORMAT; }
   uint32_t n8, nw; memcpy(&n8, hdr, 4);
-  if (n8 != 32 || memcmp(hdr + 4, pzk::FR_P.w, 32) != 0) {
+  if (n8 != 32 || hdr_len < 40 || memcmp(hdr + 4, pzk::FR_P.w, 32) != 0) {
     set_err(err, err_len, "Curve of the witness does not match the curve of the r1cs");
     return PZK_EFORMAT;
   }
   memcpy(&nw, hdr + 36, 4);
   if (data_len != 32ull * nw) { set_err(err, err_len, "wtns: bad data section length"); return PZK_EFORMAT; }
-  R1csHost r; std::string e;
-  int rc = parse_r1cs(r1cs_path, r, e);
-  if (rc) { set_err(err, err_len, e); return rc; }
-  if (r.n_wires != nw) { set_err(err, err_len, "Invalid witness length. Circuit: " + std::to_string(r.n_wires) + ", witness: " + std::to_string(nw)); return PZK_EFORMAT; }
+  *data = dat; *n_wires = nw;
+  return PZK_OK;
+}
+
+int pzk_r1cs_check_wtns(pzk_r1cs* r, const uint8_t* wtns, uint64_t wtns_len, int* verdict, int64_t* first_bad,
+                        char* err, size_t err_len) {
+  if (!r || !wtns || !verdict) return PZK_EINVAL;
+  const uint8_t* data = nullptr; uint32_t nw = 0;
+  int rc = parse_wtns(wtns, wtns_len, &data, &nw, err, err_len);
+  if (rc) return rc;
+  if (r->n_wires != nw) { set_err(err, err_len, "Invalid witness length. Circuit: " + std::to_string(r->n_wires) + ", witness: " + std::to_string(nw)); return PZK_EFORMAT; }
   int64_t fb = -1;
-  rc = check_batch_impl(r, data, 1, cuda_device, verdict, &fb, nullptr, err, err_len);
+  rc = pzk_r1cs_check(r, data, 1, verdict, &fb, nullptr, err, err_len);
   if (first_bad) *first_bad = fb;
   return rc;
 }
 
+int pzk_wtns_check(const char* r1cs_path, const uint8_t* wtns, uint64_t wtns_len, int cuda_device, int* verdict,
+                   int64_t* first_bad, char* err, size_t err_len) {
+  if (!r1cs_path || !wtns || !verdict) return PZK_EINVAL;
+  const uint8_t* data = nullptr; uint32_t nw = 0;
+  int rc = parse_wtns(wtns, wtns_len, &data, &nw, err, err_len);   // format errors before any device work
+  if (rc) return rc;
+  pzk_r1cs* r = nullptr;
+  rc = pzk_r1cs_open(r1cs_path, cuda_device, &r, err, err_len);
+  if (rc) return rc;
+  rc = pzk_r1cs_check_wtns(r, wtns, wtns_len, verdict, first_bad, err, err_len);
+  pzk_r1cs_close(r);
+  return rc;
+}

@@ -769,20 +769,32 @@ __global__ void __launch_bounds__(128, 8) eval_kernel(EvalParams p) {
 // ------------------------------------------------------------------------------------------
 struct ExportParams {
   const u32* list;           // list pool (table-view descriptors)
-  u32 n_u_slots, n_f_slots;  // blocked planes (0 = flat layout with stride L)
+  u32 n_u_slots, n_f_slots;  // blocked planes
   const PzkExport* entries;
   u64 n_entries;
   const u64* U;
   const u64* F;
   u64 L;
   const u64* lanes;  // tile-local lane per output row, or nullptr = identity
+  const u64* rows;   // output row per entry of `lanes`, or nullptr = lane_base + index
   u64 lane_base;     // output row offset (identity mode: output row = lane_base + lane)
   u64 n_rows;        // number of output rows handled
-  u64* out;          // [row][out_wires][4]
+  u64* out;          // [row][out_wires][4], or (blocked) [row / 32][out_wires][limb][row % 32]
   u64 out_wires;
   u32 wire_off;      // out index = wire - wire_off
+  u32 blocked;       // 1: the R1CS stream kernel's layout (pzk_r1cs.cuh) - device-resident hand-off
 };
 
+__device__ __forceinline__ void export_store(const ExportParams& p, u64 row_out, u32 wire, const u64* w) {
+  if (p.blocked) {
+    u64* dst = p.out + ((row_out >> 5) * p.out_wires + (wire - p.wire_off)) * 128 + (row_out & 31);
+    dst[0] = w[0]; dst[32] = w[1]; dst[64] = w[2]; dst[96] = w[3];
+  } else {
+    u64* dst = p.out + (row_out * p.out_wires + (wire - p.wire_off)) * 4;
+    reinterpret_cast<ulonglong2*>(dst)[0] = make_ulonglong2(w[0], w[1]);
+    reinterpret_cast<ulonglong2*>(dst)[1] = make_ulonglong2(w[2], w[3]);
+  }
+}
 
 // one export entry of one lane -> canonical value (wire <- slot, or wire <- view of words; pzk_program.h)
 __device__ __forceinline__ void export_value(const ExportParams& p, const uint4 ew, u64 lane, u64* w) {
@@ -815,31 +827,87 @@ __device__ __forceinline__ void export_value(const ExportParams& p, const uint4 
   }
 }
 
+// lanes across the threads (coalesced plane reads), grid.y strides over the entries: public signals of every
+// lane, full witnesses of many selected lanes
 __global__ void __launch_bounds__(128) export_kernel(ExportParams p) {
   const u64 row = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= p.n_rows) return;
   const u64 lane = p.lanes ? p.lanes[row] : row;
+  const u64 row_out = p.rows ? p.rows[row] : p.lane_base + row;
   for (u64 e = blockIdx.y; e < p.n_entries; e += gridDim.y) {
     const uint4 ew = __ldg(reinterpret_cast<const uint4*>(p.entries + e));
     u64 w[4];
     export_value(p, ew, lane, w);
-    u64* dst = p.out + ((p.lane_base + row) * p.out_wires + (ew.x - p.wire_off)) * 4;
-    reinterpret_cast<ulonglong2*>(dst)[0] = make_ulonglong2(w[0], w[1]);
-    reinterpret_cast<ulonglong2*>(dst)[1] = make_ulonglong2(w[2], w[3]);
+    export_store(p, row_out, ew.x, w);
   }
 }
 
-// one lane, threads over the entries of a segment (full-witness export of selected lanes)
+// entries across the threads, grid.y = selected lane: full witnesses of a few lanes in ONE launch per segment
 __global__ void __launch_bounds__(128) export_rows_kernel(ExportParams p) {
-  const u64 lane = p.lanes[0];
+  const u64 lane = p.lanes[blockIdx.y];
+  const u64 row_out = p.rows ? p.rows[blockIdx.y] : p.lane_base + blockIdx.y;
   for (u64 e = (u64)blockIdx.x * blockDim.x + threadIdx.x; e < p.n_entries; e += (u64)gridDim.x * blockDim.x) {
     const uint4 ew = __ldg(reinterpret_cast<const uint4*>(p.entries + e));
     u64 w[4];
     export_value(p, ew, lane, w);
-    u64* dst = p.out + (p.lane_base * p.out_wires + (ew.x - p.wire_off)) * 4;
-    reinterpret_cast<ulonglong2*>(dst)[0] = make_ulonglong2(w[0], w[1]);
-    reinterpret_cast<ulonglong2*>(dst)[1] = make_ulonglong2(w[2], w[3]);
+    export_store(p, row_out, ew.x, w);
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// Witness digest: every wire of every lane folded into a per-lane 256-bit checksum without writing the
+// 72 MB witness: digest[lane][j] = sum over wires i of K(i) * limb_j(w_i) mod 2^64, K(i) = splitmix64(i) | 1,
+// w_i the canonical value of wire i (.wtns section 2).  The weights make it position sensitive and the sum
+// makes it independent of the order in which the export entries are visited (they are grouped by the program
+// segment that defines them, not by wire).  One thread = one lane over the entries of one segment; grid.y
+// splits the entries when there are few lanes.  /root/reference/test/automatisationTest.js:40-50 returns
+// the whole vector; this is the proof that every signal was computed when it is not exported.
+// ------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ u64 pzk_digest_weight(u32 wire) {
+  u64 z = (u64)wire + 0x9e3779b97f4a7c15ull;
+  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+  z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+  return (z ^ (z >> 31)) | 1ull;
+}
+
+// wire 0 is the constant 1 and has no export entry: every lane's digest starts at K(0) * 1
+__global__ void digest_init_kernel(u64* digest, u64 n_lanes) {
+  const u64 lane = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (lane >= n_lanes) return;
+  digest[4 * lane] = pzk_digest_weight(0);
+  digest[4 * lane + 1] = digest[4 * lane + 2] = digest[4 * lane + 3] = 0;
+}
+
+__global__ void __launch_bounds__(128) digest_kernel(ExportParams p) {
+  const u64 lane = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (lane >= p.n_rows) return;
+  const u64 per = (p.n_entries + gridDim.y - 1) / gridDim.y;
+  const u64 e0 = (u64)blockIdx.y * per, e1 = min(p.n_entries, e0 + per);
+  const u64* Ub = p.U + (lane / PZK_LANE_BLOCK) * p.n_u_slots * PZK_LANE_BLOCK + (lane % PZK_LANE_BLOCK);
+  u64 acc[4] = {0, 0, 0, 0};
+  for (u64 e = e0; e < e1; e++) {
+    const uint4 ew = __ldg(reinterpret_cast<const uint4*>(p.entries + e));
+    const u64 K = pzk_digest_weight(ew.x);
+    const u32 ref = ew.y, aux = ew.z;
+    // fast paths: a U word, or a bit field of a U word that stays inside 64 bits (most wires of the passport circuits)
+    if (ref < PZK_REF_TABVIEW && PZK_REF_CLS(ref) == 0) { acc[0] += K * Ub[(u64)PZK_REF_SLOT(ref) * PZK_LANE_BLOCK]; continue; }
+    if (ref < PZK_REF_TABVIEW && PZK_REF_CLS(ref) == 3 && !(ref & PZK_REF_VIEW_N)) {
+      const u32 s_ = aux & 255u, n_ = (aux >> 8) & 255u, k_ = (aux >> 16) & 255u;
+      if (s_ < 64 && n_ + k_ <= 64) {
+        u64 v = Ub[(u64)PZK_REF_SLOT(ref) * PZK_LANE_BLOCK] >> s_;
+        if (n_ < 64) v &= (1ull << n_) - 1;
+        acc[0] += K * (v << k_);
+        continue;
+      }
+    }
+    u64 w[4];
+    export_value(p, ew, lane, w);
+#pragma unroll
+    for (int j = 0; j < 4; j++) acc[j] += K * w[j];
+  }
+  unsigned long long* d = reinterpret_cast<unsigned long long*>(p.out) + (p.lane_base + lane) * 4;
+#pragma unroll
+  for (int j = 0; j < 4; j++) if (acc[j]) atomicAdd(d + j, (unsigned long long)acc[j]);
 }
 
 }  // namespace pzkd

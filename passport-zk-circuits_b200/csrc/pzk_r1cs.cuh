@@ -2,13 +2,20 @@
 // checkConstraints (/root/reference/test/automatisationTest.js:51) for explicit witnesses.
 //
 // Any iden3 .r1cs, any number of witnesses.  A full registerIdentity witness is 72 MB, so only
-// ~1000 fit in HBM at once: the parallelism comes from the ROWS, not from the lanes.
+// ~1500 fit in HBM at once: the parallelism comes from the ROWS, not from the lanes.
 //   grid  = (row chunks, groups of 128 lanes);  CTA = 4 warps, warp w owns lanes [32w, 32w+32)
-//   witness layout  F[lane / 32][wire][limb][lane % 32]   (Montgomery, a wire of one warp = 1 KB)
+//   witness layout  W[lane / 32][wire][limb][lane % 32]   (CANONICAL values, a wire of one warp = 1 KB)
+// Wires stay canonical (the .wtns representation): a term with coefficient +-1 is a modular add, a term whose
+// wire is 0 or 1 in every lane of the warp is a conditional add of the coefficient, any other term is one
+// Montgomery product mont(c R, w) = c w, so linear combinations are accumulated as plain residues and no wire
+// is ever converted; the product of a quadratic row costs two Montgomery products (a R, then a R * b / R), or
+// none when A or B is a bit in every lane.  Loading explicit witnesses is a pure transpose, and the evaluator's
+// export writes this layout directly (device-resident hand-off, pzk_api.cu).
 // The A/B/C matrices are streamed through shared memory in tiles with TMA bulk copies
 // (cp.async.bulk + mbarrier, double buffered): one elected thread issues the copy of the next
 // tile's row headers and terms while the four warps consume the current one, so the stream is
-// read once per CTA instead of once per warp.  The per-lane work is a gather of 32-byte wires:
+// read once per CTA instead of once per warp.  The per-lane work is a gather of 32-byte wires with the next
+// term's wire requested while the current one is consumed:
 // HBM bound (algorithmic bytes = 32 B x terms x lanes + the matrix stream per CTA).
 #pragma once
 #include "fr_device.cuh"
@@ -29,15 +36,15 @@ struct R1csParams {
   const PzkCoef* coefs;
   const unsigned char* coef_kind;  // 0 general, 1 = +small, 2 = -small
   const u64* coef_mag;
-  const u64* F;  // [lane/32][wire][limb][32]
+  const u64* W;  // [lane/32][wire][limb][32], canonical
   u64 n_wires;
   u64 n_lanes;
   u32* status;
   unsigned long long* first_bad;
 };
 
-#define R1CS_TILE_ROWS 256
-#define R1CS_TILE_TERMS 1536
+#define R1CS_TILE_ROWS 128
+#define R1CS_TILE_TERMS 768
 #define R1CS_SMEM_BYTES (2 * (R1CS_TILE_ROWS * 16 + R1CS_TILE_TERMS * 8) + 16)
 
 __device__ __forceinline__ void mbar_init(u32 bar, u32 count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
@@ -56,40 +63,33 @@ __device__ __forceinline__ void tma_load_1d(u32 dst, const void* src, u32 bytes,
                "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
-__device__ __forceinline__ void ldW(const u64* Fb, u64 wire, u64* v) {  // Fb: lane-block base + lane%32
-  const u64* p = Fb + wire * 128;
+__device__ __forceinline__ void ldW(const u64* Wb, u64 wire, u64* v) {  // Wb: lane-block base + lane%32
+  const u64* p = Wb + wire * 128;
   v[0] = p[0]; v[1] = p[32]; v[2] = p[64]; v[3] = p[96];
 }
+__device__ __forceinline__ bool is_bit256(const u64* w) { return (w[0] >> 1 | w[1] | w[2] | w[3]) == 0; }
 
-__device__ __forceinline__ void r1cs_lin(const R1csParams& p, const PzkTerm* t, u32 n, const u64* Fb, u64* acc) {
-  const u64 RONE[4] = {0xac96341c4ffffffbull, 0x36fc76959f60cd29ull, 0x666ea36f7879462eull, 0x0e0a77c19a07df2full};
-  acc[0] = acc[1] = acc[2] = acc[3] = 0;
-  for (u32 k = 0; k < n; k++) {
-    const u32 ref = t[k].ref, ci = t[k].coef;
-    u64 w[4];
-    ldW(Fb, PZK_REF_SLOT(ref), w);
-    const u32 kind = __ldg(p.coef_kind + ci);
-    const u64 mag = __ldg(p.coef_mag + ci);
-    if (kind && mag == 1) {
-      if (kind == 1) fr_add(acc, acc, w); else fr_sub(acc, acc, w);
-      continue;
-    }
-    // most wires of the passport circuits are bits: when every lane of the warp holds 0 or 1 the
-    // term is a conditional add of the coefficient, no multiplication
-    const bool is0 = fr_is_zero(w), is1 = fr_eq(w, RONE);
-    u64 c[4];
-    ldPool(reinterpret_cast<const u64*>(p.coefs), ci * 3 + 1, c);
-    if (__all_sync(0xffffffffu, is0 || is1)) {
-      if (is1) fr_add(acc, acc, c);
-    } else {
-      u64 r[4];
-      fr_mul(r, c, w);
-      fr_add(acc, acc, r);
-    }
+// acc (plain residue) += coefficient ci * canonical wire w
+__device__ __forceinline__ void r1cs_term(const R1csParams& p, u32 ci, const u64* w, u64* acc) {
+  const u32 kind = __ldg(p.coef_kind + ci);
+  if (kind && __ldg(p.coef_mag + ci) == 1) {
+    if (kind == 1) fr_add(acc, acc, w); else fr_sub(acc, acc, w);
+    return;
+  }
+  // most wires of the passport circuits are bits: when every lane of the warp holds 0 or 1 the
+  // term is a conditional add of the coefficient, no multiplication
+  u64 c[4];
+  if (__all_sync(0xffffffffu, is_bit256(w))) {
+    if (w[0]) { ldPool(reinterpret_cast<const u64*>(p.coefs), ci * 3, c); fr_add(acc, acc, c); }
+  } else {
+    u64 r[4];
+    ldPool(reinterpret_cast<const u64*>(p.coefs), ci * 3 + 1, c);  // c * R
+    fr_mul(r, c, w);
+    fr_add(acc, acc, r);
   }
 }
 
-__global__ void __launch_bounds__(128) r1cs_stream_kernel(R1csParams p) {
+__global__ void __launch_bounds__(128, 6) r1cs_stream_kernel(R1csParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   const u32 sbase = (u32)__cvta_generic_to_shared(smem);
   const u32 buf_bytes = R1CS_TILE_ROWS * 16 + R1CS_TILE_TERMS * 8;
@@ -97,10 +97,10 @@ __global__ void __launch_bounds__(128) r1cs_stream_kernel(R1csParams p) {
   const u32 warp = threadIdx.x >> 5, lane32 = threadIdx.x & 31;
   const u64 lane = ((u64)blockIdx.y * 4 + warp) * 32 + lane32;
   const bool active = lane < p.n_lanes;
-  // whole warps take the row loop together (it contains a full-mask vote); lanes past the batch in
+  // whole warps take the row loop together (it contains full-mask votes); lanes past the batch in
   // the last warp compute on padding and never write a verdict
   const bool warp_active = ((u64)blockIdx.y * 4 + warp) * 32 < p.n_lanes;
-  const u64* Fb = p.F + ((u64)blockIdx.y * 4 + warp) * p.n_wires * 128 + lane32;
+  const u64* Wb = p.W + ((u64)blockIdx.y * 4 + warp) * p.n_wires * 128 + lane32;
   const u32 tile_lo = blockIdx.x * p.tiles_per_chunk;
   const u32 tile_hi = min(p.n_tiles, tile_lo + p.tiles_per_chunk);
   if (tile_lo >= tile_hi) return;
@@ -118,6 +118,7 @@ __global__ void __launch_bounds__(128) r1cs_stream_kernel(R1csParams p) {
     tma_load_1d(dst + R1CS_TILE_ROWS * 16, p.terms + tl.term0, tb, bar0 + 8 * slot);
   };
   if (threadIdx.x == 0) issue(tile_lo, 0);
+  const u64 R2[4] = {0x1bb8e645ae216da7ull, 0x53fe3ab1e35c59e3ull, 0x8c49833d53bb8085ull, 0x0216d0b17f4e44a5ull};
   unsigned long long bad = ~0ull;
   u32 phase0 = 0, phase1 = 0;
   for (u32 tile = tile_lo; tile < tile_hi; tile++) {
@@ -127,20 +128,44 @@ __global__ void __launch_bounds__(128) r1cs_stream_kernel(R1csParams p) {
     const R1csTile tl = p.tiles[tile];
     const PzkRow* rows = reinterpret_cast<const PzkRow*>(smem + slot * buf_bytes);
     const PzkTerm* terms = reinterpret_cast<const PzkTerm*>(smem + slot * buf_bytes + R1CS_TILE_ROWS * 16);
-    if (warp_active) {
+    if (warp_active && tl.n_rows) {
+      // the terms of the tile are one contiguous list: the wire of term t + 1 is requested before term t is
+      // consumed (two gathers in flight per warp on top of the warps of the other CTAs of the SM)
+      const u32 t_first = rows[0].term_off - tl.term0;
+      const u32 t_end = tl.n_terms;
+      u32 t = t_first;
+      u64 wn[4];
+      ldW(Wb, PZK_REF_SLOT(terms[t].ref), wn);
       for (u32 r = 0; r < tl.n_rows; r++) {
         const PzkRow row = rows[r];
-        const PzkTerm* t = terms + (row.term_off - tl.term0);
-        u64 a[4], b[4], c[4];
-        r1cs_lin(p, t + row.na + row.nb, row.nc, Fb, c);
+        u64 acc[3][4];
+#pragma unroll
+        for (int q = 0; q < 3; q++) acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0;
+        const u32 na = row.na, nab = na + row.nb, nt = nab + row.nc;
+        for (u32 k = 0; k < nt; k++, t++) {
+          u64 w[4] = {wn[0], wn[1], wn[2], wn[3]};
+          const u32 ci = terms[t].coef;
+          if (t + 1 < t_end) ldW(Wb, PZK_REF_SLOT(terms[t + 1].ref), wn);
+          if (k < na) r1cs_term(p, ci, w, acc[0]);
+          else if (k < nab) r1cs_term(p, ci, w, acc[1]);
+          else r1cs_term(p, ci, w, acc[2]);
+        }
         bool ok;
-        if (row.na == 0 || row.nb == 0) ok = fr_is_zero(c);
+        if (na == 0 || nab == na) ok = fr_is_zero(acc[2]);
         else {
-          r1cs_lin(p, t, row.na, Fb, a);
-          r1cs_lin(p, t + row.na, row.nb, Fb, b);
           u64 ab[4];
-          fr_mul(ab, a, b);
-          ok = fr_eq(ab, c);
+          if (__all_sync(0xffffffffu, is_bit256(acc[0]))) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) ab[j] = acc[0][0] ? acc[1][j] : 0;
+          } else if (__all_sync(0xffffffffu, is_bit256(acc[1]))) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) ab[j] = acc[1][0] ? acc[0][j] : 0;
+          } else {
+            u64 ar[4];
+            fr_mul(ar, acc[0], R2);   // a R
+            fr_mul(ab, ar, acc[1]);   // a b
+          }
+          ok = fr_eq(ab, acc[2]);
         }
         if (!ok && (unsigned long long)row.index < bad) bad = row.index;
       }
@@ -153,21 +178,29 @@ __global__ void __launch_bounds__(128) r1cs_stream_kernel(R1csParams p) {
   }
 }
 
-// canonical AoS witnesses [lane][n_wires][4] -> Montgomery blocked planes [lane/32][wire][limb][32]
-__global__ void __launch_bounds__(128) load_witness_blocked_kernel(const u64* wit, u64 n_wires, u64 n_lanes, u64* F,
+// canonical AoS witnesses [lane][n_wires][4] -> canonical blocked planes [lane/32][wire][limb][32]
+// (values >= p are flagged and reduced: snarkjs reads them modulo the prime)
+__global__ void __launch_bounds__(128) load_witness_blocked_kernel(const u64* wit, u64 n_wires, u64 n_lanes, u64* W,
                                                                    u32* status) {
   const u64 lane = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   if (lane >= n_lanes) return;
-  u64* Fb = F + (lane / 32) * n_wires * 128 + (lane % 32);
+  u64* Wb = W + (lane / 32) * n_wires * 128 + (lane % 32);
   for (u64 wv = blockIdx.y; wv < n_wires; wv += gridDim.y) {
     const ulonglong2* ip = reinterpret_cast<const ulonglong2*>(wit + (lane * n_wires + wv) * 4);
     ulonglong2 lo = ip[0], hi = ip[1];
-    u64 v[4] = {lo.x, lo.y, hi.x, hi.y}, r[4];
+    u64 v[4] = {lo.x, lo.y, hi.x, hi.y};
     if (geq_p(v)) { atomicOr(status + lane, PZK_LANE_INPUT_RANGE); reduce_p(v); }
-    fr_to_mont(r, v);
-    u64* q = Fb + wv * 128;
-    q[0] = r[0]; q[32] = r[1]; q[64] = r[2]; q[96] = r[3];
+    u64* q = Wb + wv * 128;
+    q[0] = v[0]; q[32] = v[1]; q[64] = v[2]; q[96] = v[3];
   }
+}
+
+// hand-off from the evaluator: its export covers wires 1..n-1, wire 0 is the constant 1
+__global__ void wire0_blocked_kernel(u64* W, u64 n_wires, u64 n_lanes) {
+  const u64 lane = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (lane >= n_lanes) return;
+  u64* q = W + (lane / 32) * n_wires * 128 + (lane % 32);
+  q[0] = 1; q[32] = 0; q[64] = 0; q[96] = 0;
 }
 
 }  // namespace pzkd

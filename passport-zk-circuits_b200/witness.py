@@ -117,6 +117,25 @@ def lib():
                                  ctypes.c_size_t]
     L.pzk_r1cs_check_batch.argtypes = [cp, vp, u64, ctypes.c_int, vp, vp, ctypes.POINTER(ctypes.c_double), cp,
                                        ctypes.c_size_t]
+    L.pzk_witness_batch_packed_async.argtypes = [vp, vp, u64, vp, vp, vp, vp]
+    L.pzk_witness_batch_packed_digest.argtypes = [vp, vp, u64, vp, vp, vp, vp]
+    L.pzk_witness_batch_packed_multi.argtypes = [ctypes.POINTER(vp), ctypes.c_int, vp, u64, vp, vp, vp, vp]
+    L.pzk_sync.argtypes = [vp]
+    L.pzk_batch_set_digest.argtypes = [vp, ctypes.c_int]
+    L.pzk_batch_download_digest.argtypes = [vp, vp]
+    L.pzk_digest_weight_of.restype = u64
+    L.pzk_digest_weight_of.argtypes = [u32]
+    L.pzk_r1cs_open.argtypes = [cp, ctypes.c_int, ctypes.POINTER(vp), cp, ctypes.c_size_t]
+    L.pzk_r1cs_close.argtypes = [vp]
+    for f in ("pzk_r1cs_wires", "pzk_r1cs_constraints"):
+        getattr(L, f).restype = u32
+        getattr(L, f).argtypes = [vp]
+    L.pzk_r1cs_terms.restype = u64
+    L.pzk_r1cs_terms.argtypes = [vp]
+    L.pzk_r1cs_check.argtypes = [vp, vp, u64, vp, vp, ctypes.POINTER(ctypes.c_double), cp, ctypes.c_size_t]
+    L.pzk_r1cs_check_wtns.argtypes = [vp, vp, u64, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(i64), cp, ctypes.c_size_t]
+    L.pzk_r1cs_check_circuit.argtypes = [vp, vp, vp, u64, vp, vp, ctypes.POINTER(ctypes.c_double),
+                                         ctypes.POINTER(ctypes.c_double), cp, ctypes.c_size_t]
     _lib = L
     return L
 
@@ -270,6 +289,7 @@ class BatchResult:
     first_bad: np.ndarray   # int64 [B]; -1 when every constraint holds
     public: np.ndarray      # uint64 [B, n_public, 4] canonical little-endian limbs
     witnesses: np.ndarray | None = None  # uint64 [n_export, n_wires, 4]
+    digest: np.ndarray | None = None     # uint64 [B, 4] witness digest (set_digest(True))
 
     def public_ints(self, lane):
         return [int.from_bytes(self.public[lane, i].tobytes(), "little") for i in range(self.public.shape[1])]
@@ -415,19 +435,28 @@ class WitnessCalculator:
             return out, bad
         return out
 
-    def calculateWitnessBatchPacked(self, packed: np.ndarray, range_mask=None) -> BatchResult:
-        """range_mask: the per-lane mask pack(..., on_range="mask") returned; those lanes get INPUT_RANGE."""
+    def calculateWitnessBatchPacked(self, packed: np.ndarray, range_mask=None, digest=False) -> BatchResult:
+        """range_mask: the per-lane mask pack(..., on_range="mask") returned; those lanes get INPUT_RANGE.
+        digest=True (after set_digest(True)): the result carries the per-lane witness digest."""
         packed = np.ascontiguousarray(packed, dtype=np.uint8)
         B = packed.shape[0]
         status = np.zeros(B, dtype=np.uint32)
         first_bad = np.zeros(B, dtype=np.int64)
         public = np.zeros((B, self.n_public, 4), dtype=np.uint64)
-        self._check(self._L.pzk_witness_batch_packed(self._h, packed.ctypes.data, B, status.ctypes.data,
-                                                     first_bad.ctypes.data, public.ctypes.data))
+        dig = np.zeros((B, 4), dtype=np.uint64) if digest else None
+        if digest:
+            self._check(self._L.pzk_witness_batch_packed_digest(self._h, packed.ctypes.data, B, status.ctypes.data,
+                                                                first_bad.ctypes.data, public.ctypes.data, dig.ctypes.data))
+        else:
+            self._check(self._L.pzk_witness_batch_packed(self._h, packed.ctypes.data, B, status.ctypes.data,
+                                                         first_bad.ctypes.data, public.ctypes.data))
+        self._B = B
         if range_mask is not None:
             status[np.asarray(range_mask, dtype=bool)] |= STATUS_INPUT_RANGE
         first_bad[(status & STATUS_CONSTRAINT) == 0] = -1
-        return BatchResult(status, first_bad, public)
+        res = BatchResult(status, first_bad, public)
+        res.digest = dig
+        return res
 
     def upload_packed(self, packed: np.ndarray):
         packed = np.ascontiguousarray(packed, dtype=np.uint8)
@@ -458,11 +487,24 @@ class WitnessCalculator:
         if reset:
             self._L.pzk_profile_reset(self._h)
         out = {}
-        for i, k in enumerate(("eval", "check", "export", "run")):
+        for i, k in enumerate(("eval", "check", "export", "run", "digest")):
             ms, n = ctypes.c_double(), ctypes.c_uint64()
             self._L.pzk_profile_get(self._h, i, ctypes.byref(ms), ctypes.byref(n))
             out[k] = (ms.value, n.value)
         return out
+
+    # ---- witness digest (pzk.h): every wire of every lane folded on the device
+    def set_digest(self, on=True):
+        self._check(self._L.pzk_batch_set_digest(self._h, 1 if on else 0))
+        self._digest = bool(on)
+
+    def download_digest(self) -> np.ndarray:
+        out = np.zeros((self._B, 4), dtype=np.uint64)
+        self._check(self._L.pzk_batch_download_digest(self._h, out.ctypes.data))
+        return out
+
+    def sync(self):
+        self._check(self._L.pzk_sync(self._h))
 
     def set_tile_lanes(self, lanes):
         self._check(self._L.pzk_set_tile_lanes(self._h, lanes))
@@ -484,6 +526,163 @@ def wtns_check(r1cs_path, wtns: bytes, device=0):
     if rc != 0:
         raise PzkError(err.value.decode(errors="replace") or f"pzk error {rc}")
     return bool(verdict.value), fb.value
+
+
+def program_histogram(program_path: str) -> dict:
+    """Record counts per opcode of a compiled program (host-side read of the file; names from pzk_program.h) plus
+    the derived per-witness figures the roofline accounting uses: explicit Fr products, products inside the
+    hint intrinsics, one product per quadratic field row, narrow (64-bit) records."""
+    import re
+    import struct
+    blob = open(program_path, "rb").read()
+    n_segments = struct.unpack_from("<I", blob, 36)[0]
+    n_list = struct.unpack_from("<I", blob, 52)[0]
+    n_fpool, n_coef = struct.unpack_from("<II", blob, 40)
+    n_rec = struct.unpack_from("<Q", blob, 56)[0]
+
+    def al(x):
+        return (x + 15) & ~15
+    pos = al(160) + al(n_segments * 48)
+    ops = np.frombuffer(blob, dtype=np.uint32, count=n_rec * 4, offset=pos).reshape(-1, 4)
+    pos = al(pos + n_rec * 16)
+    pos = al(pos + n_fpool * 32)
+    pos = al(pos + n_coef * 96)
+    lst = np.frombuffer(blob, dtype=np.uint32, count=n_list, offset=pos)
+    hdr = open(os.path.join(_ROOT, "include", "pzk_program.h")).read()
+    names = {int(m.group(2)): m.group(1) for m in re.finditer(r"PZK_(\w+) = (\d+)", hdr)}
+    hist = {}
+    quad_field_rows = 0
+    bjj_products = 0
+    pc = 0
+    w0 = ops[:, 0]
+    while pc < n_rec:
+        w = int(w0[pc])
+        opc, fl = w & 0xff, (w >> 8) & 0xff
+        nm = names.get(opc, str(opc))
+        hist[nm] = hist.get(nm, 0) + 1
+        if opc in (56, 57, 58):
+            if opc == 57 and (w >> 16) and (int(ops[pc, 2]) & 0xffff):
+                quad_field_rows += 1
+            pc += int(ops[pc, 3])
+        elif opc == 37:
+            n = int(lst[int(ops[pc, 2])])
+            bjj_products += (2 * n - 1) * (13 + 4)      # 13 per projective addition, 1 prefix + 3 to normalise
+        if fl & 4:
+            pc += 1
+        if opc == 23 and fl & 32:
+            pc += 1
+        pc += 1
+    narrow = sum(v for k, v in hist.items() if k.startswith(("U_", "I_", "V_")) or k in ("N_BIT", "N_LOW", "N_FITS", "IN_U", "CHECK_I64", "CHECK_INT", "CHECK_RANGE"))
+    fr_products = hist.get("F_MUL", 0) + bjj_products + quad_field_rows
+    return {"records": hist, "fr_products": fr_products, "explicit_f_mul": hist.get("F_MUL", 0),
+            "intrinsic_products": bjj_products, "quadratic_field_rows": quad_field_rows, "narrow_records": narrow,
+            "algorithmic_imad": 136 * fr_products + narrow}
+
+
+def digest_weights(n_wires: int) -> np.ndarray:
+    """K(i) of the witness digest (pzk.h: splitmix64(i) | 1) for wires 0..n_wires-1."""
+    with np.errstate(over="ignore"):
+        z = np.arange(n_wires, dtype=np.uint64) + np.uint64(0x9e3779b97f4a7c15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xbf58476d1ce4e5b9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94d049bb133111eb)
+        return (z ^ (z >> np.uint64(31))) | np.uint64(1)
+
+
+def witness_digest(witness: np.ndarray) -> np.ndarray:
+    """Host restatement of the device digest: witness uint64 [n_wires, 4] canonical -> uint64 [4]."""
+    w = np.ascontiguousarray(witness, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        return (w * digest_weights(w.shape[0])[:, None]).sum(axis=0, dtype=np.uint64)
+
+
+def witness_batch_packed_multi(calcs, packed: np.ndarray, digest=False) -> "BatchResult":
+    """One host thread, several devices: `calcs` are WitnessCalculators of the same program opened on different
+    devices; contiguous shares of the batch run concurrently (pzk_witness_batch_packed_multi)."""
+    L = lib()
+    packed = np.ascontiguousarray(packed, dtype=np.uint8)
+    B = packed.shape[0]
+    c0 = calcs[0]
+    status = np.zeros(B, dtype=np.uint32)
+    first_bad = np.zeros(B, dtype=np.int64)
+    public = np.zeros((B, c0.n_public, 4), dtype=np.uint64)
+    dig = np.zeros((B, 4), dtype=np.uint64) if digest else None
+    hs = (ctypes.c_void_p * len(calcs))(*[c._h for c in calcs])
+    rc = L.pzk_witness_batch_packed_multi(hs, len(calcs), packed.ctypes.data, B, status.ctypes.data, first_bad.ctypes.data,
+                                          public.ctypes.data, dig.ctypes.data if digest else None)
+    if rc != 0:
+        msgs = [L.pzk_last_error(c._h).decode(errors="replace") for c in calcs]
+        raise PzkError(next((m for m in msgs if m), f"pzk error {rc}"))
+    first_bad[(status & STATUS_CONSTRAINT) == 0] = -1
+    res = BatchResult(status, first_bad, public)
+    res.digest = dig
+    return res
+
+
+class R1cs:
+    """An .r1cs parsed and resident on the device (pzk_r1cs_open): `wtns check` for any number of batches."""
+
+    def __init__(self, r1cs_path, device=0):
+        self._L = lib()
+        self._h = ctypes.c_void_p()
+        err = ctypes.create_string_buffer(1024)
+        rc = self._L.pzk_r1cs_open(os.fsencode(r1cs_path), device, ctypes.byref(self._h), err, len(err))
+        if rc != 0:
+            self._h = None
+            raise PzkError(err.value.decode(errors="replace") or f"pzk error {rc}")
+        self.n_wires = self._L.pzk_r1cs_wires(self._h)
+        self.n_constraints = self._L.pzk_r1cs_constraints(self._h)
+        self.n_terms = self._L.pzk_r1cs_terms(self._h)
+
+    def close(self):
+        if self._h:
+            self._L.pzk_r1cs_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, witnesses: np.ndarray):
+        """witnesses: uint64 [B, n_wires, 4] canonical -> (verdicts bool[B], first_bad int64[B], kernel ms)."""
+        witnesses = np.ascontiguousarray(witnesses, dtype=np.uint64)
+        B = witnesses.shape[0]
+        if witnesses.shape[1] != self.n_wires:
+            raise PzkError(f"Invalid witness length. Circuit: {self.n_wires}, witness: {witnesses.shape[1]}")
+        verdicts = np.zeros(B, dtype=np.int32)
+        fb = np.zeros(B, dtype=np.int64)
+        ms = ctypes.c_double()
+        err = ctypes.create_string_buffer(1024)
+        rc = self._L.pzk_r1cs_check(self._h, witnesses.ctypes.data, B, verdicts.ctypes.data, fb.ctypes.data,
+                                    ctypes.byref(ms), err, len(err))
+        if rc != 0:
+            raise PzkError(err.value.decode(errors="replace") or f"pzk error {rc}")
+        return verdicts.astype(bool), fb, ms.value
+
+    def check_wtns(self, wtns: bytes):
+        verdict, fb = ctypes.c_int(), ctypes.c_int64()
+        err = ctypes.create_string_buffer(1024)
+        rc = self._L.pzk_r1cs_check_wtns(self._h, wtns, len(wtns), ctypes.byref(verdict), ctypes.byref(fb), err, len(err))
+        if rc != 0:
+            raise PzkError(err.value.decode(errors="replace") or f"pzk error {rc}")
+        return bool(verdict.value), fb.value
+
+    def check_circuit(self, calc: "WitnessCalculator", lanes):
+        """calculateWitness -> checkConstraints on the device: evaluates the batch resident in `calc`
+        (upload / upload_packed) and checks every row of this .r1cs on the witnesses of `lanes`.
+        -> (verdicts bool[n], first_bad int64[n], eval ms, check ms)"""
+        lanes = np.ascontiguousarray(np.array(list(lanes), dtype=np.uint64))
+        n = len(lanes)
+        verdicts = np.zeros(n, dtype=np.int32)
+        fb = np.zeros(n, dtype=np.int64)
+        t_eval, t_check = ctypes.c_double(), ctypes.c_double()
+        err = ctypes.create_string_buffer(1024)
+        rc = self._L.pzk_r1cs_check_circuit(self._h, calc._h, lanes.ctypes.data, n, verdicts.ctypes.data, fb.ctypes.data,
+                                            ctypes.byref(t_eval), ctypes.byref(t_check), err, len(err))
+        if rc != 0:
+            raise PzkError(err.value.decode(errors="replace") or f"pzk error {rc}")
+        return verdicts.astype(bool), fb, t_eval.value, t_check.value
 
 
 def r1cs_check_batch(r1cs_path, witnesses: np.ndarray, device=0):

@@ -5,6 +5,7 @@ import hashlib
 import json
 import os
 import re
+import struct
 import subprocess
 import sys
 
@@ -513,3 +514,62 @@ def test_process_passport_front_end_on_a_real_cms_sod(tmp_path):
     inp[d["signature"]["offset"], 0] ^= np.uint64(1)
     st, fb, _ = prog.witness(inp, want_witness=False)
     assert st == W.STATUS_CONSTRAINT and fb >= 0
+
+
+def test_malformed_r1cs_and_wtns_are_format_errors_not_wild_reads(artifacts_dir, tmp_path):
+    """every section length of an .r1cs / .wtns is checked against the bytes that are there.
+    Parsing happens before any device work, so this runs without a GPU."""
+    L = W.lib()
+    good = open(os.path.join(artifacts_dir, "t_mix.r1cs"), "rb").read()
+    err = ctypes.create_string_buffer(512)
+
+    def open_rc(blob):
+        pth = tmp_path / "x.r1cs"
+        pth.write_bytes(blob)
+        h = ctypes.c_void_p()
+        rc = L.pzk_r1cs_open(str(pth).encode(), 0, ctypes.byref(h), err, len(err))
+        if rc == 0:
+            L.pzk_r1cs_close(h)
+        return rc
+
+    ok = open_rc(good)
+    assert ok in (0, -3), (ok, err.value)          # PZK_OK on a GPU box, PZK_ENODEVICE here
+    for cut in (len(good) - 1, len(good) // 2, 100, 40, 13, 11, 3, 0):
+        assert open_rc(good[:cut]) == -7, (cut, err.value)                       # PZK_EFORMAT
+    # a section header that claims more bytes than the file holds
+    bad = bytearray(good)
+    struct.pack_into("<Q", bad, 16, 1 << 40)
+    assert open_rc(bytes(bad)) == -7
+    # constraint count larger than the constraint section
+    hdr_pos = None
+    pos = 12
+    for _ in range(struct.unpack_from("<I", good, 8)[0]):
+        typ, ln = struct.unpack_from("<IQ", good, pos)
+        if typ == 1:
+            hdr_pos = pos + 12
+        pos += 12 + ln
+    bad = bytearray(good)
+    struct.pack_into("<I", bad, hdr_pos + 36 + 24, 1 << 30)
+    assert open_rc(bytes(bad)) == -7
+    # wtns: truncated images and lying section lengths
+    wt = formats.write_wtns([1, 2, 3, 4])
+    v, fb = ctypes.c_int(), ctypes.c_int64()
+    r1 = os.path.join(artifacts_dir, "t_mix.r1cs").encode()
+    for cut in (len(wt) - 1, 60, 20, 11):
+        assert L.pzk_wtns_check(r1, wt[:cut], cut, 0, ctypes.byref(v), ctypes.byref(fb), err, len(err)) == -7, cut
+    bad = bytearray(wt)
+    struct.pack_into("<Q", bad, 16, 1 << 40)
+    assert L.pzk_wtns_check(r1, bytes(bad), len(bad), 0, ctypes.byref(v), ctypes.byref(fb), err, len(err)) == -7
+
+
+def test_witness_digest_host_restatement_matches_the_c_weights():
+    L = W.lib()
+    k = W.digest_weights(1000)
+    for i in (0, 1, 2, 77, 999):
+        assert int(k[i]) == L.pzk_digest_weight_of(i)
+    w = np.zeros((3, 4), dtype=np.uint64)
+    w[0, 0] = 1
+    w[2] = [5, 6, 7, 8]
+    d = W.witness_digest(w)
+    M = (1 << 64) - 1
+    assert [int(x) for x in d] == [(int(k[0]) + 5 * int(k[2])) & M, (6 * int(k[2])) & M, (7 * int(k[2])) & M, (8 * int(k[2])) & M]

@@ -253,3 +253,17 @@ def test_device_unit(name):
     assert os.path.exists(exe), "run __graft_entry__.build() first"
     out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stdout + out.stderr
+
+
+def test_imad_peak_microbenchmark():
+    """tests/cuda/imad_peak.cu: the measured denominators bench.py's roofline uses (dependent-free IMAD rate,
+    Montgomery products per second with register operands)."""
+    import json
+    import os
+    import subprocess
+    from util import ROOT
+    out = subprocess.run([os.path.join(ROOT, "tests", "bin", "imad_peak")], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    d = json.loads(out.stdout.strip().splitlines()[-1])
+    # 148 SMs x 64 IMAD / clock at ~1.9 GHz is 1.8e13; anything far below means the benchmark did not fill the GPU
+    assert 5e12 < d["imad_per_s"] < 4e13 and d["fr_mul_per_s"] * 136 <= d["imad_per_s"] * 1.05, d
