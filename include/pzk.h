@@ -149,15 +149,15 @@ int pzk_witness_batch_packed_multi(pzk_circuit* const* handles, int n_handles, c
                                    uint32_t* status, int64_t* first_bad, uint8_t* public_le32, uint64_t* digest);
 
 /* ---- witness digest: proof that every signal of every lane was computed, without moving 72 MB per witness.
- * With the digest switched on, every run folds EVERY wire of EVERY lane, on the device, into
- *     digest[lane][j] = sum over wires i of K(i) * limb_j(w_i)  mod 2^64,   j = 0..3,
- * w_i the canonical value of wire i exactly as calculateWTNSBin would write it, K(i) = pzk_digest_weight_of(i)
- * (splitmix64(i) | 1: position sensitive).  A consumer that holds the .wtns of a lane - or the oracle - can
- * recompute it; tests compare it with the oracle's witness for every lane.  The reference returns the whole
- * vector (/root/reference/test/automatisationTest.js:40-50); this is its checksum.                          */
+ * With the digest switched on, every run folds EVERY wire of EVERY lane, on the device, into one field element
+ *     digest[lane] = sum over wires i of c(i) * w_i   mod p        (32 bytes little endian, canonical)
+ * w_i the canonical value of wire i exactly as calculateWTNSBin would write it, c(i) = pzk_digest_weight_of(i)
+ * (32-bit odd weights from splitmix64: position sensitive).  A consumer that holds the .wtns of a lane - or the
+ * oracle - can recompute it; tests compare it with the oracle's witness for every lane.  The reference returns
+ * the whole vector (/root/reference/test/automatisationTest.js:40-50); this is its checksum.                */
 int pzk_batch_set_digest(pzk_circuit* c, int on);
 int pzk_batch_download_digest(pzk_circuit* c, uint64_t* digest /* [batch][4] */);
-uint64_t pzk_digest_weight_of(uint32_t wire);
+uint32_t pzk_digest_weight_of(uint32_t wire);
 int pzk_witness_batch_packed_digest(pzk_circuit* c, const uint8_t* packed, uint64_t batch, uint32_t* status,
                                     int64_t* first_bad, uint8_t* public_le32, uint64_t* digest);
 

@@ -36,6 +36,20 @@ C4_VARIANTS = {
     "c4_sig10": CircuitParams(10, 256, 3, 4, 600, 248, 1, 1496, 3, 256),
     "c4_sig13": CircuitParams(13, 384, 3, 2, 320, 248, 1, 1496, 2, 256),
     "c4_sig20": CircuitParams(20, 256, 3, 4, 600, 248, 1, 1496, 3, 256),
+    # the remaining arms of the dispatch (signatureVerification.circom:26-116, identity.circom:26-84): RSA-4096,
+    # RSA-3072 with e = 37187 (48 chunks: the non-Karatsuba multiplier), PSS with e = 65537 / salt 64 / 3072 bits,
+    # brainpoolP256r1, secp224r1 (7 chunks of 32 bits, SHA-224 over the signed attributes), a document without
+    # DG15 (AA_SIGNATURE_ALGO = 0), an EC active-authentication key in DG15, a TD1 document
+    "c4_sig2": CircuitParams(2, 256, 3, 4, 600, 248, 1, 1496, 3, 256),
+    "c4_sig4": CircuitParams(4, 160, 3, 4, 600, 248, 1, 1496, 3, 256),
+    "c4_sig11": CircuitParams(11, 256, 3, 4, 600, 248, 1, 1496, 3, 256),
+    "c4_sig12": CircuitParams(12, 256, 3, 4, 600, 248, 1, 1496, 3, 256),
+    "c4_sig14": CircuitParams(14, 256, 3, 4, 600, 248, 1, 1496, 3, 256),
+    "c4_sig21": CircuitParams(21, 256, 3, 4, 600, 248, 1, 1496, 3, 256),
+    "c4_sig24": CircuitParams(24, 256, 3, 4, 600, 248, 1, 1496, 3, 256),
+    "c4_na": CircuitParams(1, 256, 3, 3, 600, 248, 0, 0, 0, 0),
+    "c4_ecaa": CircuitParams(1, 256, 3, 4, 600, 248, 20, 1496, 2, 256),
+    "c4_td1": CircuitParams(1, 256, 1, 4, 600, 248, 1, 1496, 3, 256),
 }
 
 
@@ -94,7 +108,7 @@ OWN_CIRCUITS = {"t_mix": ("mix.circom", {"u": 16, "bits": 1}),
 COMPILE_OPTS = {"c3_lean": {"static_def_rows": True},
                 "c3_allrows": {"table_proofs": False, "segment_ops": 16384}}
 
-BIG = {"c3", "c3_lean", "c3_allrows", "c3_cms", "c4_sig3", "c4_sig10", "c4_sig13", "c4_sig20"}  # ship only the xz-packed program for these
+BIG = {"c3", "c3_lean", "c3_allrows", "c3_cms"} | set(C4_VARIANTS)  # ship only the xz-packed program for these
 
 
 def _stale(out, deps):

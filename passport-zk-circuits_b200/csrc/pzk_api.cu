@@ -88,6 +88,10 @@ struct pzk_circuit {
   // witness digest (pzk_batch_set_digest)
   bool digest_on = false;
   u64* d_digest = nullptr;             // [batch_cap][4]
+  u64* d_dig_state = nullptr;          // [DIG_STATE_PIECES][batch_cap] carry-save accumulators
+  DigRec* d_dig_recs = nullptr;        // digest program: records per segment
+  ulonglong2* d_dig_tab = nullptr;     // per-bit coefficient tables
+  std::vector<std::pair<uint64_t, uint64_t>> dig_seg;  // (offset, count) of each segment's digest records
   // profiling
   bool prof = false;
   double prof_ms[5] = {0, 0, 0, 0, 0};
@@ -173,6 +177,8 @@ static void free_batch(pzk_circuit* c) {
   if (c->d_first_bad) cudaFree(c->d_first_bad);
   if (c->d_public) cudaFree(c->d_public);
   if (c->d_digest) cudaFree(c->d_digest);
+  if (c->d_dig_state) cudaFree(c->d_dig_state);
+  c->d_dig_state = nullptr;
   c->d_inputs = nullptr; c->d_status = nullptr; c->d_first_bad = nullptr; c->d_public = nullptr; c->d_digest = nullptr;
   c->batch_cap = 0; c->pub_cap = 0; c->d_inputs_bytes = 0;
 }
@@ -182,6 +188,7 @@ void pzk_circuit_close(pzk_circuit* c) {
   cudaSetDevice(c->device);
   free_tile(c); free_batch(c);
   cudaFree(c->d_ops); cudaFree(c->d_fpool); cudaFree(c->d_coefs); cudaFree(c->d_coef_kind); cudaFree(c->d_coef_mag);
+  cudaFree(c->d_dig_recs); cudaFree(c->d_dig_tab);
   cudaFree(c->d_list); cudaFree(c->d_in_table); cudaFree(c->d_rows); cudaFree(c->d_terms); cudaFree(c->d_exports); cudaFree(c->d_pub_entries);
   if (c->in_flight) pzk_sync(c);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -204,6 +211,57 @@ static void classify_coefs(const PzkCoef* coefs, uint32_t n, std::vector<unsigne
     if (v.fits64() && v.w[0] < (1ull << 63)) { kind[i] = 1; mag[i] = v.w[0]; continue; }
     pzk::U256 nv = pzk::sub(pzk::FR_P, v);
     if (nv.fits64() && nv.w[0] < (1ull << 63)) { kind[i] = 2; mag[i] = nv.w[0]; }
+  }
+}
+
+// The digest program: the export entries of every segment compiled into digest records (pzk_kernels.cuh).
+// All bit-field views of one word collapse into one table of per-bit 128-bit coefficients.
+static void build_digest_program(pzk_circuit* c, std::vector<DigRec>& recs, std::vector<ulonglong2>& tab) {
+  typedef unsigned __int128 u128;
+  c->dig_seg.assign(c->h.n_segments, {0, 0});
+  for (uint32_t s = 0; s < c->h.n_segments; s++) {
+    const PzkSegment& sg = c->segs[s];
+    c->dig_seg[s].first = recs.size();
+    std::map<uint64_t, std::vector<u128>> words;  // (is_N << 32 | slot) -> coefficient per bit
+    u128 konst = 0;
+    for (uint64_t e = sg.exp_off; e < sg.exp_off + sg.n_exp; e++) {
+      const PzkExport& x = c->exports[e];
+      const uint32_t cw = pzk_digest_weight(x.wire);
+      if (x.ref == PZK_REF_ZERO) continue;
+      if (x.ref == PZK_REF_ONE) { konst += cw; continue; }
+      DigRec r; r.type_nbits = 0; r.slot = PZK_REF_SLOT(x.ref); r.a = cw; r.b = 0;
+      if (x.ref == PZK_REF_TABVIEW) { r.type_nbits = DIG_GENERIC; r.slot = 0; r.a = (uint32_t)e; r.b = cw; recs.push_back(r); continue; }
+      const uint32_t cls = PZK_REF_CLS(x.ref);
+      if (cls == 3) {
+        const uint32_t s_ = x.aux & 255u, n_ = (x.aux >> 8) & 255u, k_ = (x.aux >> 16) & 255u;
+        const bool isn = (x.ref & PZK_REF_VIEW_N) != 0;
+        const uint32_t width = isn ? 256 : 64;
+        if (n_ + k_ <= 64 && s_ < width) {
+          std::vector<u128>& T = words[((uint64_t)isn << 32) | r.slot];
+          if (T.empty()) T.assign(width, 0);
+          for (uint32_t b = s_; b < s_ + n_ && b < width; b++) T[b] += (u128)cw << (b - s_ + k_);
+        } else if (n_ != 0 && s_ < width) { r.type_nbits = DIG_GENERIC; r.slot = 0; r.a = (uint32_t)e; r.b = cw; recs.push_back(r); }
+        continue;
+      }
+      r.type_nbits = cls == 0 ? DIG_PLAIN_U : cls == 1 ? DIG_PLAIN_I : DIG_PLAIN_F;
+      recs.push_back(r);
+    }
+    for (auto& kv : words) {
+      uint32_t nbits = 0;
+      for (uint32_t b = 0; b < kv.second.size(); b++) if (kv.second[b]) nbits = b + 1;
+      if (!nbits) continue;
+      DigRec r; r.type_nbits = ((kv.first >> 32) ? DIG_WORD_N : DIG_WORD_U) | (nbits << 8);
+      r.slot = (uint32_t)kv.first; r.a = (uint32_t)tab.size(); r.b = 0;
+      for (uint32_t b = 0; b < nbits; b++) tab.push_back(make_ulonglong2((u64)kv.second[b], (u64)(kv.second[b] >> 64)));
+      recs.push_back(r);
+    }
+    while (konst) {  // constant wires (value 1): 64 bits at a time
+      DigRec r; r.type_nbits = DIG_CONST; r.slot = 0; r.a = (uint32_t)konst; r.b = (uint32_t)(konst >> 32);
+      recs.push_back(r);
+      konst >>= 64;
+      if (konst) { set_err(c, "digest: constant overflow"); break; }
+    }
+    c->dig_seg[s].second = recs.size() - c->dig_seg[s].first;
   }
 }
 
@@ -290,6 +348,12 @@ int pzk_circuit_open(const char* program_path, int cuda_device, pzk_circuit** ou
       if (c->exports[e].wire >= 1 && c->exports[e].wire <= n_pub) { c->seg[s].pub.push_back(c->exports[e]); all_pub.push_back(c->exports[e]); }
   }
   CK(upload(&c->d_pub_entries, all_pub.data(), all_pub.size() * sizeof(PzkExport)));
+  {
+    std::vector<DigRec> recs; std::vector<ulonglong2> tab;
+    build_digest_program(c, recs, tab);
+    CK(upload(&c->d_dig_recs, recs.data(), recs.size() * sizeof(DigRec)));
+    CK(upload(&c->d_dig_tab, tab.data(), tab.size() * sizeof(ulonglong2)));
+  }
   return PZK_OK;
 }
 
@@ -340,6 +404,7 @@ static int ensure_batch(pzk_circuit* c, uint64_t batch, uint64_t input_bytes) {
   CK(cudaMalloc((void**)&c->d_first_bad, batch * 8));
   CK(cudaMalloc((void**)&c->d_public, std::max<uint64_t>(batch * n_pub * 32, 16)));
   CK(cudaMalloc((void**)&c->d_digest, batch * 32));
+  CK(cudaMalloc((void**)&c->d_dig_state, batch * 8 * DIG_STATE_PIECES));
   c->batch_cap = batch;
   return PZK_OK;
 }
@@ -439,7 +504,7 @@ static int run_batch(pzk_circuit* c, const RunOpts& o) {
   }
   CK(cudaMemsetAsync(c->d_status, 0, c->batch * 4, c->stream));
   CK(cudaMemsetAsync(c->d_first_bad, 0xff, c->batch * 8, c->stream));
-  if (digest) digest_init_kernel<<<(unsigned)((c->batch + 255) / 256), 256, 0, c->stream>>>(c->d_digest, c->batch);  // wire 0 = 1
+  if (digest) CK(cudaMemsetAsync(c->d_dig_state, 0, c->batch_cap * 8 * DIG_STATE_PIECES, c->stream));
   // export lanes sorted into tiles: [lane in tile..., output row...] per tile, one upload
   std::vector<std::vector<u64>> tl(o.n_export ? n_tiles : 0), tr(o.n_export ? n_tiles : 0);
   std::vector<uint64_t> tl_off(n_tiles + 1, 0);
@@ -492,13 +557,14 @@ static int run_batch(pzk_circuit* c, const RunOpts& o) {
         export_kernel<<<dim3(grid, 1), 128, 0, c->stream>>>(p);
         prof_end(c, 2, ea, eb);
       }
-      if (digest && sg.n_exp) {
+      if (digest && c->dig_seg[s].second) {
         // every wire defined in this segment, folded while its slot still holds it
-        p.entries = c->d_exports + sg.exp_off; p.n_entries = sg.n_exp;
-        p.lane_base = base; p.n_rows = n; p.out = c->d_digest; p.out_wires = 0; p.wire_off = 0;
-        unsigned gy = (unsigned)std::min<uint64_t>(std::max<uint64_t>(1, (1184 + grid - 1) / grid), std::max<uint64_t>(1, sg.n_exp / 256));
+        DigestParams dp;
+        dp.recs = c->d_dig_recs + c->dig_seg[s].first; dp.n_recs = c->dig_seg[s].second; dp.tab = c->d_dig_tab;
+        dp.exports = c->d_exports; dp.ex = p; dp.n_lanes = n; dp.state = c->d_dig_state; dp.state_stride = c->batch_cap; dp.lane_base = base;
+        unsigned gy = (unsigned)std::min<uint64_t>(std::max<uint64_t>(1, (1184 + grid - 1) / grid), std::max<uint64_t>(1, dp.n_recs / 64));
         prof_begin(c, 4, ea, eb);
-        digest_kernel<<<dim3(grid, gy), 128, 0, c->stream>>>(p);
+        digest_kernel<<<dim3(grid, gy), 128, 0, c->stream>>>(dp);
         prof_end(c, 4, ea, eb);
       }
       if (n_tl && sg.n_exp) {
@@ -518,6 +584,7 @@ static int run_batch(pzk_circuit* c, const RunOpts& o) {
         prof_end(c, 2, ea, eb);
       }
     }
+    if (digest) digest_finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->d_dig_state, c->batch_cap, base, n, c->d_digest);
     if (streamed) {
       cudaEvent_t done = new_event();
       CK(cudaEventRecord(done, c->stream));
@@ -624,7 +691,7 @@ int pzk_batch_set_digest(pzk_circuit* c, int on) {
   c->digest_on = on != 0;
   return PZK_OK;
 }
-uint64_t pzk_digest_weight_of(uint32_t wire) { return pzk_digest_weight(wire); }
+uint32_t pzk_digest_weight_of(uint32_t wire) { return pzk_digest_weight(wire); }
 int pzk_batch_download_digest(pzk_circuit* c, uint64_t* digest) {
   if (!c || c->batch == 0 || !digest) return PZK_EINVAL;
   if (!c->digest_on) { set_err(c, "pzk_batch_set_digest(c, 1) was not called before the run"); return PZK_EINVAL; }

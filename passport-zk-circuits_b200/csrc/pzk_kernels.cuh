@@ -855,59 +855,189 @@ __global__ void __launch_bounds__(128) export_rows_kernel(ExportParams p) {
 }
 
 // ------------------------------------------------------------------------------------------
-// Witness digest: every wire of every lane folded into a per-lane 256-bit checksum without writing the
-// 72 MB witness: digest[lane][j] = sum over wires i of K(i) * limb_j(w_i) mod 2^64, K(i) = splitmix64(i) | 1,
-// w_i the canonical value of wire i (.wtns section 2).  The weights make it position sensitive and the sum
-// makes it independent of the order in which the export entries are visited (they are grouped by the program
-// segment that defines them, not by wire).  One thread = one lane over the entries of one segment; grid.y
-// splits the entries when there are few lanes.  /root/reference/test/automatisationTest.js:40-50 returns
-// the whole vector; this is the proof that every signal was computed when it is not exported.
+// Witness digest: every wire of every lane folded into one field element per lane without writing the 72 MB
+// witness:      digest = sum over wires i of c(i) * w_i   mod p,     c(i) = (splitmix64(i) >> 32) | 1  (32 bits, odd)
+// w_i the canonical value of wire i (.wtns section 2).  The weights make it position sensitive; a sum does not
+// care in which order the wires are visited, and it is linear in every representation the evaluator keeps:
+//   * a bit-field view ((W >> s) & (2^n - 1)) << k is a sum of bits of W times powers of two, so ALL the views of
+//     one word (110 per word on average in registerIdentity) collapse into one table of per-bit coefficients
+//     C_b = sum over views containing bit b of c(i) 2^(b - s + k), built when the program is loaded:
+//     one conditional 128-bit add per bit of the word instead of a shift / mask / multiply per wire;
+//   * a Montgomery value w R is accumulated as the 320-bit integer sum of c(i) * (w R) and reduced and converted
+//     ONCE per lane at the end (no from_mont per wire);
+//   * narrow words are 64 x 32 -> 96-bit products in a 128-bit accumulator (negative I-class values in a second).
+// The export entries are compiled into 16-byte digest records per program segment (pzk_api.cu: build_digest_program).
+// Partial sums of one launch are added to the per-lane state in carry-save form (32-bit pieces in 64-bit words,
+// atomicAdd), so grid.y can split the records when there are few lanes; digest_finalize_kernel normalises.
+// /root/reference/test/automatisationTest.js:40-50 returns the whole vector; this is its checksum.
 // ------------------------------------------------------------------------------------------
-__host__ __device__ __forceinline__ u64 pzk_digest_weight(u32 wire) {
+__host__ __device__ __forceinline__ u32 pzk_digest_weight(u32 wire) {
   u64 z = (u64)wire + 0x9e3779b97f4a7c15ull;
   z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
   z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
-  return (z ^ (z >> 31)) | 1ull;
+  return (u32)((z ^ (z >> 31)) >> 32) | 1u;
 }
 
-// wire 0 is the constant 1 and has no export entry: every lane's digest starts at K(0) * 1
-__global__ void digest_init_kernel(u64* digest, u64 n_lanes) {
-  const u64 lane = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (lane >= n_lanes) return;
-  digest[4 * lane] = pzk_digest_weight(0);
-  digest[4 * lane + 1] = digest[4 * lane + 2] = digest[4 * lane + 3] = 0;
-}
+enum { DIG_WORD_U = 1, DIG_WORD_N = 2, DIG_PLAIN_U = 3, DIG_PLAIN_I = 4, DIG_PLAIN_F = 5, DIG_GENERIC = 6, DIG_CONST = 7 };
+struct DigRec { u32 type_nbits; u32 slot; u32 a; u32 b; };  // type in bits 0..7, nbits in bits 8..31
+#define DIG_STATE_PIECES 28  // accN 4, accNeg 4, accM 10, accP 10 (32-bit pieces, carry-save)
 
-__global__ void __launch_bounds__(128) digest_kernel(ExportParams p) {
-  const u64 lane = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (lane >= p.n_rows) return;
-  const u64 per = (p.n_entries + gridDim.y - 1) / gridDim.y;
-  const u64 e0 = (u64)blockIdx.y * per, e1 = min(p.n_entries, e0 + per);
-  const u64* Ub = p.U + (lane / PZK_LANE_BLOCK) * p.n_u_slots * PZK_LANE_BLOCK + (lane % PZK_LANE_BLOCK);
-  u64 acc[4] = {0, 0, 0, 0};
-  for (u64 e = e0; e < e1; e++) {
-    const uint4 ew = __ldg(reinterpret_cast<const uint4*>(p.entries + e));
-    const u64 K = pzk_digest_weight(ew.x);
-    const u32 ref = ew.y, aux = ew.z;
-    // fast paths: a U word, or a bit field of a U word that stays inside 64 bits (most wires of the passport circuits)
-    if (ref < PZK_REF_TABVIEW && PZK_REF_CLS(ref) == 0) { acc[0] += K * Ub[(u64)PZK_REF_SLOT(ref) * PZK_LANE_BLOCK]; continue; }
-    if (ref < PZK_REF_TABVIEW && PZK_REF_CLS(ref) == 3 && !(ref & PZK_REF_VIEW_N)) {
-      const u32 s_ = aux & 255u, n_ = (aux >> 8) & 255u, k_ = (aux >> 16) & 255u;
-      if (s_ < 64 && n_ + k_ <= 64) {
-        u64 v = Ub[(u64)PZK_REF_SLOT(ref) * PZK_LANE_BLOCK] >> s_;
-        if (n_ < 64) v &= (1ull << n_) - 1;
-        acc[0] += K * (v << k_);
-        continue;
-      }
-    }
-    u64 w[4];
-    export_value(p, ew, lane, w);
+struct DigestParams {
+  const DigRec* recs;
+  u64 n_recs;
+  const ulonglong2* tab;     // per-bit coefficients (lo, hi)
+  const PzkExport* exports;  // for DIG_GENERIC
+  ExportParams ex;           // planes, list pool
+  u64 n_lanes;
+  u64* state;                // [piece][state_stride]
+  u64 state_stride;
+  u64 lane_base;
+};
+
+__device__ __forceinline__ void add128(u64* acc, u64 lo, u64 hi) {
+  asm("add.cc.u64 %0, %0, %2; addc.u64 %1, %1, %3;" : "+l"(acc[0]), "+l"(acc[1]) : "l"(lo), "l"(hi));
+}
+// acc (5 x 64) += c * w (4 x 64), c < 2^32
+__device__ __forceinline__ void mac320(u64* acc, u32 c, const u64* w) {
+  u64 carry = 0;
 #pragma unroll
-    for (int j = 0; j < 4; j++) acc[j] += K * w[j];
+  for (int j = 0; j < 4; j++) {
+    const u64 lo = (u64)c * w[j], hi = __umul64hi((u64)c, w[j]);
+    u64 t = acc[j] + lo;
+    u64 c1 = t < lo;
+    u64 t2 = t + carry;
+    u64 c2 = t2 < carry;
+    acc[j] = t2;
+    carry = hi + c1 + c2;  // hi < 2^32: no overflow
   }
-  unsigned long long* d = reinterpret_cast<unsigned long long*>(p.out) + (p.lane_base + lane) * 4;
-#pragma unroll
-  for (int j = 0; j < 4; j++) if (acc[j]) atomicAdd(d + j, (unsigned long long)acc[j]);
+  acc[4] += carry;
+}
+
+__global__ void __launch_bounds__(128) digest_kernel(DigestParams p) {
+  const u64 lane = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (lane >= p.n_lanes) return;
+  const u64 per = (p.n_recs + gridDim.y - 1) / gridDim.y;
+  const u64 r0 = (u64)blockIdx.y * per, r1 = min(p.n_recs, r0 + per);
+  const u64* Ub = p.ex.U + (lane / PZK_LANE_BLOCK) * p.ex.n_u_slots * PZK_LANE_BLOCK + (lane % PZK_LANE_BLOCK);
+  const u64* Fb = p.ex.F + (lane / PZK_LANE_BLOCK) * p.ex.n_f_slots * 4 * PZK_LANE_BLOCK + (lane % PZK_LANE_BLOCK);
+  u64 accN[2] = {0, 0}, accNeg[2] = {0, 0}, accM[5] = {0, 0, 0, 0, 0}, accP[5] = {0, 0, 0, 0, 0};
+  for (u64 r = r0; r < r1; r++) {
+    const uint4 rw = __ldg(reinterpret_cast<const uint4*>(p.recs + r));
+    const u32 type = rw.x & 255u, nbits = rw.x >> 8;
+    switch (type) {
+      case DIG_WORD_U: {
+        const u64 W = Ub[(u64)rw.y * PZK_LANE_BLOCK];
+        const ulonglong2* T = p.tab + rw.z;
+#pragma unroll 4
+        for (u32 b = 0; b < nbits; b++) {
+          const ulonglong2 t = __ldg(T + b);
+          const u64 m = 0ull - ((W >> b) & 1ull);
+          add128(accN, t.x & m, t.y & m);
+        }
+        break;
+      }
+      case DIG_WORD_N: {
+        const ulonglong2* T = p.tab + rw.z;
+        for (u32 j = 0; j * 64 < nbits; j++) {
+          const u64 W = Fb[((u64)rw.y * 4 + j) * PZK_LANE_BLOCK];
+          const u32 nb = min(64u, nbits - j * 64);
+#pragma unroll 4
+          for (u32 b = 0; b < nb; b++) {
+            const ulonglong2 t = __ldg(T + j * 64 + b);
+            const u64 m = 0ull - ((W >> b) & 1ull);
+            add128(accN, t.x & m, t.y & m);
+          }
+        }
+        break;
+      }
+      case DIG_PLAIN_U: {
+        const u64 v = Ub[(u64)rw.y * PZK_LANE_BLOCK];
+        add128(accN, (u64)rw.z * v, __umul64hi((u64)rw.z, v));
+        break;
+      }
+      case DIG_PLAIN_I: {
+        const long long v = (long long)Ub[(u64)rw.y * PZK_LANE_BLOCK];
+        const u64 mag = v < 0 ? (u64)(-v) : (u64)v;
+        add128(v < 0 ? accNeg : accN, (u64)rw.z * mag, __umul64hi((u64)rw.z, mag));
+        break;
+      }
+      case DIG_PLAIN_F: {
+        u64 w[4];
+        ldF(Fb, PZK_LANE_BLOCK, rw.y, w);
+        mac320(accM, rw.z, w);
+        break;
+      }
+      case DIG_GENERIC: {
+        const uint4 ew = __ldg(reinterpret_cast<const uint4*>(p.exports + rw.z));
+        u64 w[4];
+        export_value(p.ex, ew, lane, w);
+        mac320(accP, rw.w, w);
+        break;
+      }
+      case DIG_CONST: add128(accN, (u64)rw.z | ((u64)rw.w << 32), 0); break;
+      default: break;
+    }
+  }
+  unsigned long long* st = reinterpret_cast<unsigned long long*>(p.state) + p.lane_base + lane;
+  const u64 S = p.state_stride;
+  auto put = [&](u32 piece0, const u64* acc, int n) {
+    for (int j = 0; j < n; j++) {
+      const u64 lo = acc[j] & 0xffffffffull, hi = acc[j] >> 32;
+      if (lo) atomicAdd(st + (u64)(piece0 + 2 * j) * S, (unsigned long long)lo);
+      if (hi) atomicAdd(st + (u64)(piece0 + 2 * j + 1) * S, (unsigned long long)hi);
+    }
+  };
+  put(0, accN, 2); put(4, accNeg, 2); put(8, accM, 5); put(18, accP, 5);
+}
+
+// pieces (value = sum piece_k 2^(32 k)) -> limbs
+__device__ __forceinline__ void dig_normalise(const u64* state, u64 S, u32 piece0, int n_pieces, u64* limbs, int n_limbs) {
+  for (int j = 0; j < n_limbs; j++) limbs[j] = 0;
+  for (int k = 0; k < n_pieces; k++) {
+    const unsigned __int128 add = (unsigned __int128)state[(u64)(piece0 + k) * S] << (32 * (k & 1));  // < 2^96
+    const int j = k >> 1;
+    unsigned __int128 t = (unsigned __int128)limbs[j] + (u64)add;
+    limbs[j] = (u64)t;
+    u64 carry = (u64)(t >> 64) + (u64)(add >> 64);
+    for (int q = j + 1; q < n_limbs && carry; q++) {
+      t = (unsigned __int128)limbs[q] + carry;
+      limbs[q] = (u64)t;
+      carry = (u64)(t >> 64);
+    }
+  }
+}
+// 320-bit integer -> residue mod p
+__device__ __forceinline__ void dig_reduce320(const u64* x, u64* r) {
+  u64 lo[4] = {x[0], x[1], x[2], x[3]};
+  reduce_p(lo);
+  const u64 hi[4] = {x[4], 0, 0, 0};
+  u64 hr[4];
+  fr_to_mont(hr, hi);  // x[4] * 2^256 mod p
+  fr_add(r, lo, hr);
+}
+
+__global__ void digest_finalize_kernel(const u64* state, u64 S, u64 lane_base, u64 n_lanes, u64* digest) {
+  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_lanes) return;
+  const u64* st = state + lane_base + i;
+  u64 n3[3], g3[3], m5[5], p5[5];
+  dig_normalise(st, S, 0, 4, n3, 3);
+  dig_normalise(st, S, 4, 4, g3, 3);
+  dig_normalise(st, S, 8, 10, m5, 5);
+  dig_normalise(st, S, 18, 10, p5, 5);
+  u64 d[4], t[4], u[4];
+  dig_reduce320(p5, d);
+  dig_reduce320(m5, t);
+  fr_from_mont(u, t);
+  fr_add(d, d, u);
+  // wire 0 is the constant 1 and has no export entry
+  u64 nn[4] = {n3[0], n3[1], n3[2], 0}, gg[4] = {g3[0], g3[1], g3[2], 0};
+  const u64 w0[4] = {pzk_digest_weight(0), 0, 0, 0};
+  fr_add(d, d, nn);
+  fr_add(d, d, w0);
+  fr_sub(d, d, gg);
+  u64* out = digest + (lane_base + i) * 4;
+  out[0] = d[0]; out[1] = d[1]; out[2] = d[2]; out[3] = d[3];
 }
 
 }  // namespace pzkd

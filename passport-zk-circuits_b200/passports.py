@@ -158,13 +158,47 @@ def pss_sign(key: RsaKey, msg: bytes, hash_name: str, salt_len: int, rng) -> int
     return key.private_op(int.from_bytes(em, "big"))
 
 
-# NIST P-256 (secp256r1): the curve signatureVerification.circom:177-191 hard-codes for SIGNATURE_TYPE 20
+# Curves of the ECDSA signature types (/root/reference/circuits/signatureVerifier/signatureVerification.circom:
+# 177-191 SIG 20 = NIST P-256, :192-205 SIG 21 = brainpoolP256r1, :234-247 SIG 24 = secp224r1 in 7 chunks of 32 bits;
+# the domain parameters are the published ones (FIPS 186-4 D.1.2, RFC 5639 3.4) and are checked against the
+# `cryptography` package by tests/test_cpu_host.py)
+@dataclass(frozen=True)
+class Curve:
+    name: str
+    p: int
+    a: int
+    b: int
+    n: int
+    gx: int
+    gy: int
+    chunk_bits: int
+    chunks: int
+
+
 P256_P = 0xFFFFFFFF00000001000000000000000000000000FFFFFFFFFFFFFFFFFFFFFFFF
 P256_A = P256_P - 3
 P256_B = 0x5AC635D8AA3A93E7B3EBBD55769886BC651D06B0CC53B0F63BCE3C3E27D2604B
 P256_N = 0xFFFFFFFF00000000FFFFFFFFFFFFFFFFBCE6FAADA7179E84F3B9CAC2FC632551
 P256_G = (0x6B17D1F2E12C4247F8BCE6E563A440F277037D812DEB33A0F4A13945D898C296,
           0x4FE342E2FE1A7F9B8EE7EB4A7C0F9E162BCE33576B315ECECBB6406837BF51F5)
+CURVE_P256 = Curve("secp256r1", P256_P, P256_A, P256_B, P256_N, P256_G[0], P256_G[1], 64, 4)
+CURVE_BP256 = Curve(
+    "brainpoolP256r1",
+    0xA9FB57DBA1EEA9BC3E660A909D838D726E3BF623D52620282013481D1F6E5377,
+    0x7D5A0975FC2C3057EEF67530417AFFE7FB8055C126DC5C6CE94A4B44F330B5D9,
+    0x26DC5C6CE94A4B44F330B5D9BBD77CBF958416295CF7E1CE6BCCDC18FF8C07B6,
+    0xA9FB57DBA1EEA9BC3E660A909D838D718C397AA3B561A6F7901E0E82974856A7,
+    0x8BD2AEB9CB7E57CB2C4B482FFC81B7AFB9DE27E1E3BD23C23A4453BD9ACE3262,
+    0x547EF835C3DAC4FD97F8461A14611DC9C27745132DED8E545C1D54C72F046997, 64, 4)
+CURVE_P224 = Curve(
+    "secp224r1",
+    0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFF000000000000000000000001,
+    0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFF000000000000000000000001 - 3,
+    0xB4050A850C04B3ABF54132565044B0B7D7BFD8BA270B39432355FFB4,
+    0xFFFFFFFFFFFFFFFFFFFFFFFFFFFF16A2E0B8F03E13DD29455C5C2A3D,
+    0xB70E0CBD6BB4BF7F321390B94A03C1D356C21122343280D6115C1D21,
+    0xBD376388B5F723FB4C22DFE6CD4375A05A07476444D5819985007E34, 32, 7)
+SIG_CURVES = {20: CURVE_P256, 21: CURVE_BP256, 24: CURVE_P224}
 
 
 def _ec_add(p1, p2, a=P256_A, p=P256_P):
@@ -183,39 +217,50 @@ def _ec_add(p1, p2, a=P256_A, p=P256_P):
     return x3, (lam * (x1 - x3) - y1) % p
 
 
-def _ec_mul(k, pt):
+def _ec_mul(k, pt, curve=CURVE_P256):
     acc = None
     while k:
         if k & 1:
-            acc = _ec_add(acc, pt)
-        pt = _ec_add(pt, pt)
+            acc = _ec_add(acc, pt, curve.a, curve.p)
+        pt = _ec_add(pt, pt, curve.a, curve.p)
         k >>= 1
     return acc
 
 
-class EcKey:
-    """P-256 signer key; `n` is kept so the RSA-shaped call sites (`key.n`) read the x coordinate."""
+def _ecdsa_z(msg: bytes, hash_name: str, curve: Curve) -> int:
+    """leftmost min(hash bits, bit length of n) bits of the digest (FIPS 186-4 6.4)"""
+    d = hashlib.new(hash_name, msg).digest()
+    z = int.from_bytes(d, "big")
+    extra = len(d) * 8 - curve.n.bit_length()
+    return z >> extra if extra > 0 else z
 
-    def __init__(self, rng):
-        self.d = rng.randrange(1, P256_N)
-        self.x, self.y = _ec_mul(self.d, P256_G)
+
+class EcKey:
+    """ECDSA signer key; `n` is kept so the RSA-shaped call sites (`key.n`) read the x coordinate."""
+
+    def __init__(self, rng, curve: Curve = CURVE_P256):
+        self.curve = curve
+        self.d = rng.randrange(1, curve.n)
+        self.x, self.y = _ec_mul(self.d, (curve.gx, curve.gy), curve)
         self.n = self.x
 
     def sign(self, msg: bytes, hash_name: str, rng):
-        z = int.from_bytes(hashlib.new(hash_name, msg).digest(), "big")
+        cv = self.curve
+        z = _ecdsa_z(msg, hash_name, cv)
         while True:
-            k = rng.randrange(1, P256_N)
-            r = _ec_mul(k, P256_G)[0] % P256_N
-            s = pow(k, -1, P256_N) * (z + r * self.d) % P256_N
+            k = rng.randrange(1, cv.n)
+            r = _ec_mul(k, (cv.gx, cv.gy), cv)[0] % cv.n
+            s = pow(k, -1, cv.n) * (z + r * self.d) % cv.n
             if r and s:
                 return r, s
 
 
-def ecdsa_verify(x, y, msg: bytes, hash_name: str, r, s):
-    z = int.from_bytes(hashlib.new(hash_name, msg).digest(), "big")
-    w = pow(s, -1, P256_N)
-    pt = _ec_add(_ec_mul(z * w % P256_N, P256_G), _ec_mul(r * w % P256_N, (x, y)))
-    return pt is not None and pt[0] % P256_N == r
+def ecdsa_verify(x, y, msg: bytes, hash_name: str, r, s, curve: Curve = CURVE_P256):
+    z = _ecdsa_z(msg, hash_name, curve)
+    w = pow(s, -1, curve.n)
+    pt = _ec_add(_ec_mul(z * w % curve.n, (curve.gx, curve.gy), curve), _ec_mul(r * w % curve.n, (x, y), curve),
+                 curve.a, curve.p)
+    return pt is not None and pt[0] % curve.n == r
 
 
 def ec_pubkey_hash(x: int, y: int):
@@ -230,8 +275,9 @@ def ec_pubkey_hash(x: int, y: int):
 SIG_SCHEMES = {
     1: (2048, "pkcs1", 256, 65537, 0), 2: (4096, "pkcs1", 256, 65537, 0), 3: (2048, "pkcs1", 160, 65537, 0),
     10: (2048, "pss", 256, 3, 32), 11: (2048, "pss", 256, 65537, 32), 12: (2048, "pss", 256, 65537, 64),
-    13: (2048, "pss", 384, 65537, 48),
-    20: (256, "ecdsa", 256, 0, 0),
+    4: (3072, "pkcs1", 160, 37187, 0),
+    13: (2048, "pss", 384, 65537, 48), 14: (3072, "pss", 256, 65537, 32),
+    20: (256, "ecdsa", 256, 0, 0), 21: (256, "ecdsa", 256, 0, 0), 24: (224, "ecdsa", 224, 0, 0),
 }
 
 _KEY_CACHE = {}
@@ -297,19 +343,29 @@ class PassportFactory:
     def __init__(self, params: CircuitParams = C3, seed: int = 1, n_sig_keys: int = 4,
                  n_aa_keys: int = 4):
         if params.sig_type not in SIG_SCHEMES:
-            raise NotImplementedError("synthetic generator: RSA PKCS#1 v1.5 / PSS (SIG 1-3, 10-13) and ECDSA P-256 (SIG 20)")
+            raise NotImplementedError("synthetic generator: RSA PKCS#1 v1.5 / PSS (SIG 1-4, 10-14) and ECDSA (SIG 20, 21, 24)")
         self.params = params
         self.seed = seed
         self.key_bits, self.scheme, self.sig_hash, self.e, self.salt_len = SIG_SCHEMES[params.sig_type]
         self.block = 512 if self.sig_hash <= 256 else 1024
         if (512 if params.dg_hash <= 256 else 1024) != self.block:
             raise ValueError("DG_HASH_TYPE and the signature hash must share a block size (SURVEY.md appendix D)")
+        # the encapsulated content is hashed with the signature hash, except for SIG 24 where it stays SHA-256
+        # (passportVerificationBuilder.circom:51-59: EC_HASH_TYPE is fixed before HASH_TYPE becomes 224)
+        self.ec_hash = 256 if params.sig_type == 24 else self.sig_hash
         if self.scheme == "ecdsa":
             krng = random.Random((seed << 20) ^ 0xEC)
-            self.sig_keys = [EcKey(krng) for _ in range(n_sig_keys)]
+            self.curve = SIG_CURVES[params.sig_type]
+            self.sig_keys = [EcKey(krng, self.curve) for _ in range(n_sig_keys)]
         else:
             self.sig_keys = key_pool(self.key_bits, n_sig_keys, seed, self.e)
-        self.aa_keys = key_pool(1024, n_aa_keys, seed + 7) if params.aa_algo else []
+        if 0 < params.aa_algo < 20:
+            self.aa_keys = key_pool(1024, n_aa_keys, seed + 7)
+        elif params.aa_algo >= 20:
+            arng = random.Random((seed << 20) ^ 0xAA)
+            self.aa_keys = [EcKey(arng, CURVE_P256) for _ in range(n_aa_keys)]   # identity.circom:51-79: x, y at AA_SHIFT
+        else:
+            self.aa_keys = []
         if self.scheme == "ecdsa":
             self._pkhash = [ec_pubkey_hash(k.x, k.y) for k in self.sig_keys]
         else:
@@ -332,6 +388,14 @@ class PassportFactory:
         if not p.aa_algo:
             return b""
         key = self.aa_keys[rng.randrange(len(self.aa_keys))]
+        if p.aa_algo >= 20:
+            # EC active-authentication key: uncompressed point, x at AA_SHIFT, y right behind it
+            body = bytes(rng.randrange(256) for _ in range(p.aa_shift // 8 - 1)) + b"\x04" + \
+                key.x.to_bytes(32, "big") + key.y.to_bytes(32, "big")
+            lo, hi = self._len_range(p.dg15_blocks)
+            if len(body) > hi:
+                raise ValueError("DG15 does not fit the requested block count")
+            return body + bytes(rng.randrange(256) for _ in range(max(0, lo - len(body))))
         # DER SubjectPublicKeyInfo (RSA-1024) inside tag 6F: the modulus starts at byte 32
         hdr = bytes.fromhex("6f81a230819f300d06092a864886f70d010101050003818d0030818902818100")
         body = hdr + key.n.to_bytes(128, "big") + bytes.fromhex("0203010001")
@@ -380,7 +444,7 @@ class PassportFactory:
             ec[o:o + hlen] = hashlib.new(dgh, dg15).digest()
         ec = bytes(ec)
         # signed attributes
-        slen = self.sig_hash // 8
+        slen = self.ec_hash // 8
         lo, hi = self._len_range(1024 // self.block)
         lo = max(lo, p.ec_shift // 8 + slen)
         if lo > hi:
@@ -388,14 +452,15 @@ class PassportFactory:
         sa = bytearray(rng.randrange(256) for _ in range(rng.randint(lo, hi)))
         sa[0] = 0x31
         o = p.ec_shift // 8
-        sa[o:o + slen] = hashlib.new(sgh, ec).digest()
+        sa[o:o + slen] = hashlib.new(_hash_name(self.ec_hash), ec).digest()
         sa = bytes(sa)
         ki = rng.randrange(len(self.sig_keys))
         key = self.sig_keys[ki]
         if self.scheme == "ecdsa":
             sig = key.sign(sa, sgh, rng)
-            pub_chunks = chunks_le(key.x, 64, 4) + chunks_le(key.y, 64, 4)
-            sig_chunks = chunks_le(sig[0], 64, 4) + chunks_le(sig[1], 64, 4)
+            cb, cn = self.curve.chunk_bits, self.curve.chunks
+            pub_chunks = chunks_le(key.x, cb, cn) + chunks_le(key.y, cb, cn)
+            sig_chunks = chunks_le(sig[0], cb, cn) + chunks_le(sig[1], cb, cn)
         else:
             sig = pkcs1v15_sign(key, sa, sgh) if self.scheme == "pkcs1" else pss_sign(key, sa, sgh, self.salt_len, rng)
             pub_chunks = chunks_le(key.n, 64, self.key_bits // 64)

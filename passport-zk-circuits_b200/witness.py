@@ -123,7 +123,7 @@ def lib():
     L.pzk_sync.argtypes = [vp]
     L.pzk_batch_set_digest.argtypes = [vp, ctypes.c_int]
     L.pzk_batch_download_digest.argtypes = [vp, vp]
-    L.pzk_digest_weight_of.restype = u64
+    L.pzk_digest_weight_of.restype = u32
     L.pzk_digest_weight_of.argtypes = [u32]
     L.pzk_r1cs_open.argtypes = [cp, ctypes.c_int, ctypes.POINTER(vp), cp, ctypes.c_size_t]
     L.pzk_r1cs_close.argtypes = [vp]
@@ -580,19 +580,30 @@ def program_histogram(program_path: str) -> dict:
 
 
 def digest_weights(n_wires: int) -> np.ndarray:
-    """K(i) of the witness digest (pzk.h: splitmix64(i) | 1) for wires 0..n_wires-1."""
+    """c(i) of the witness digest (pzk.h: (splitmix64(i) >> 32) | 1) for wires 0..n_wires-1, as uint64."""
     with np.errstate(over="ignore"):
         z = np.arange(n_wires, dtype=np.uint64) + np.uint64(0x9e3779b97f4a7c15)
         z = (z ^ (z >> np.uint64(30))) * np.uint64(0xbf58476d1ce4e5b9)
         z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94d049bb133111eb)
-        return (z ^ (z >> np.uint64(31))) | np.uint64(1)
+        return ((z ^ (z >> np.uint64(31))) >> np.uint64(32)) | np.uint64(1)
 
 
 def witness_digest(witness: np.ndarray) -> np.ndarray:
-    """Host restatement of the device digest: witness uint64 [n_wires, 4] canonical -> uint64 [4]."""
+    """Host restatement of the device digest: witness uint64 [n_wires, 4] canonical -> uint64 [4], the canonical
+    little-endian limbs of  sum_i c(i) * w_i mod p.  Exact: the 32-bit halves of every limb are weighted and
+    summed separately (32 x 32-bit products, their halves summed in 64 bits), then recombined with Python ints."""
     w = np.ascontiguousarray(witness, dtype=np.uint64)
-    with np.errstate(over="ignore"):
-        return (w * digest_weights(w.shape[0])[:, None]).sum(axis=0, dtype=np.uint64)
+    c = digest_weights(w.shape[0])
+    total = 0
+    m32 = np.uint64(0xffffffff)
+    for limb in range(4):
+        for half in range(2):
+            part = (w[:, limb] >> np.uint64(32 * half)) & m32
+            prod = part * c                                    # < 2^64, exact
+            s = int((prod & m32).sum(dtype=np.uint64)) + (int((prod >> np.uint64(32)).sum(dtype=np.uint64)) << 32)
+            total += s << (64 * limb + 32 * half)
+    total %= P
+    return np.frombuffer(total.to_bytes(32, "little"), dtype=np.uint64).copy()
 
 
 def witness_batch_packed_multi(calcs, packed: np.ndarray, digest=False) -> "BatchResult":

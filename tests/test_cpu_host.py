@@ -566,10 +566,9 @@ def test_witness_digest_host_restatement_matches_the_c_weights():
     L = W.lib()
     k = W.digest_weights(1000)
     for i in (0, 1, 2, 77, 999):
-        assert int(k[i]) == L.pzk_digest_weight_of(i)
-    w = np.zeros((3, 4), dtype=np.uint64)
-    w[0, 0] = 1
-    w[2] = [5, 6, 7, 8]
-    d = W.witness_digest(w)
-    M = (1 << 64) - 1
-    assert [int(x) for x in d] == [(int(k[0]) + 5 * int(k[2])) & M, (6 * int(k[2])) & M, (7 * int(k[2])) & M, (8 * int(k[2])) & M]
+        assert int(k[i]) == L.pzk_digest_weight_of(i) and int(k[i]) < 2 ** 32 and int(k[i]) & 1
+    rng = np.random.default_rng(3)
+    w = rng.integers(0, 2 ** 63, size=(1000, 4), dtype=np.uint64)
+    w[:, 3] >>= np.uint64(3)
+    want = sum(int(k[i]) * int.from_bytes(w[i].tobytes(), "little") for i in range(1000)) % W.P
+    assert int.from_bytes(W.witness_digest(w).tobytes(), "little") == want
