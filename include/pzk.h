@@ -84,6 +84,16 @@ int pzk_compile_ex(const char* main_circom_path, const char* out_prefix, const c
 
 /* ---- circuit handle: the role of `new WitnessCalculator(wasm)` ---------------------- */
 int pzk_circuit_open(const char* program_path, int cuda_device, pzk_circuit** out);
+/* The same with the wires numbered after an EXTERNAL .sym - the one the circom compiler wrote for this circuit at
+ * whatever optimisation level the consumer's .r1cs / .zkey were built with (the reference compiles with --O2 / --O1:
+ * /root/reference/circuits/scripts/compile-circuit.sh:34, circuits/lib/circuits/scripts/compile-circuit.sh:34).
+ * Signals are matched by qualified name between program_sym_path (written by pzk_compile next to the program) and
+ * external_sym_path; a signal the external file lists with witness index -1 (optimised away), or not at all, is
+ * dropped, signals it merges into one wire are written once.  pzk_witness_size(), calculateWitness,
+ * calculateWTNSBin and the witness digest then follow the external numbering, so the .wtns is consumable by the
+ * external .r1cs (pzk_r1cs_open on it) and its proving key.                                                  */
+int pzk_circuit_open_ex(const char* program_path, const char* program_sym_path, const char* external_sym_path,
+                        int cuda_device, pzk_circuit** out);
 void pzk_circuit_close(pzk_circuit* c);
 const char* pzk_last_error(const pzk_circuit* c);
 uint32_t pzk_witness_size(const pzk_circuit* c);    /* nWitness (wire 0 = 1)              */

@@ -433,9 +433,13 @@ uint32_t pzk_ref_witness(const PzkRefProgram* p, const uint8_t* inputs, uint8_t*
           /* mod_inv of bigIntFunc.circom:430-465 as the reference defines it: 0 when a == 0 (mod p),
            * else a^(p-2) mod p by square-and-multiply - deliberately NOT the extended GCD the device uses */
           const uint32_t* L = p->list + o->a;
-          unsigned k = L[1];
+          unsigned nb = L[0], k = L[1];   /* k limbs of nb bits */
           uint64_t a[4] = {0, 0, 0, 0}, m[4] = {0, 0, 0, 0}, e[4], r[4] = {1, 0, 0, 0}, two[4] = {2, 0, 0, 0};
-          for (unsigned i = 0; i < k; i++) { a[i] = U[L[3 + i]]; m[i] = U[L[3 + k + i]]; }
+          for (unsigned i = 0; i < k; i++) {
+            unsigned pos = i * nb;
+            a[pos >> 6] |= U[L[3 + i]] << (pos & 63);
+            m[pos >> 6] |= U[L[3 + k + i]] << (pos & 63);
+          }
           mod4(a, a, m);
           sub4(e, m, two);
           mod4(r, r, m);
@@ -445,7 +449,10 @@ uint32_t pzk_ref_witness(const PzkRefProgram* p, const uint8_t* inputs, uint8_t*
           }
           if (!(a[0] | a[1] | a[2] | a[3])) memset(r, 0, sizeof r);
           U[L[3 + k + k]] = 0;
-          for (unsigned i = 0; i < k; i++) U[L[3 + k + k + 1 + i]] = r[i];
+          for (unsigned i = 0; i < k; i++) {
+            unsigned pos = i * nb;
+            U[L[3 + k + k + 1 + i]] = (r[pos >> 6] >> (pos & 63)) & (nb >= 64 ? ~0ull : ((1ull << nb) - 1));
+          }
           break;
         }
         case PZK_BJJ_MUL8: {

@@ -118,7 +118,7 @@ def _stale(out, deps):
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
 
 
-def build_all(verbose=True):
+def build_all(verbose=True, only=None):
     os.makedirs(W.ARTIFACT_DIR, exist_ok=True)
     # programs depend on the compiler, not on the kernels that share the library with it
     csrc = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
@@ -134,6 +134,8 @@ def build_all(verbose=True):
     if not os.path.isdir(REFERENCE):
         return
     for name, (body, bits) in reference_circuits().items():
+        if only is not None and name not in only:
+            continue
         prefix = os.path.join(W.ARTIFACT_DIR, name)
         final = prefix + (".pzkp.xz" if name in BIG else ".pzkp")
         if not _stale(final, deps):

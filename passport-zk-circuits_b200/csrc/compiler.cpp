@@ -1415,6 +1415,28 @@ struct Compiler::Impl {
     return out;
   }
 
+  // a limb that is not provably < 2^n is narrowed at run time: its low n bits + assertions that nothing was cut off
+  SVal narrow_limb_checked(const SVal& s_, uint64_t n) {
+    const i128 lim = n == 64 ? U64_MAX_ : (((i128)1 << n) - 1);
+    i128 hi;
+    if (exact_u(s_, hi) && hi <= lim) return s_;
+    if (s_.kind == 0) return SVal::unk();
+    SVal low;
+    if (exact_u(s_, hi)) low = s_;   // a 64-bit word wider than the limb
+    else {
+      SVal nn = sv(to_N(s_));
+      uint32_t fits = new_value(CLS_U, 0, 1);
+      emit(PZK_N_FITS, fits, nn.id);
+      emit(PZK_ASSERT_NZ, 0, fits);
+      low = n_low(nn, U64_MAX_);
+    }
+    if (n == 64) return low;
+    SVal top = emit_u(PZK_U_SHR, low, SVal::konst(U256(n)), CLS_U, 0, (i128)(U64_MAX_ >> n));
+    SVal none = emit_u(PZK_U_EQ, top, SVal::konst(U256()), CLS_U, 0, 1);
+    emit(PZK_ASSERT_NZ, 0, none.id);
+    return emit_u(PZK_U_AND, low, SVal::konst(U256((uint64_t)lim)), CLS_U, 0, lim);
+  }
+
   // long_div(n, k, m, a, b) of /root/reference/circuits/lib/circuits/bigInt/bigIntFunc.circom:190-232
   // evaluated natively: a has k+m limbs of n bits, b has k limbs (top limb non-zero);
   // returns out[2][200] with the m+1 quotient limbs and k remainder limbs.
@@ -1422,21 +1444,10 @@ struct Compiler::Impl {
     if (args.size() != 5) return false;
     for (int i = 0; i < 3; i++) if (args[i].arr || args[i].s.kind != 0 || !args[i].s.c.fits64()) return false;
     uint64_t n = args[0].s.c.w[0], k = args[1].s.c.w[0], m = args[2].s.c.w[0];
-    if (n != 64 || k < 2 || k > 64 || k + m > 128 || !args[3].arr || !args[4].arr) return false;
+    if ((n != 64 && n != 32) || k < 2 || k > 64 || k + m > 128 || (n == 32 && k < 3) || !args[3].arr || !args[4].arr) return false;
     if (args[3].a->v.size() < k + m || args[4].a->v.size() < k) return false;
     i128 lim = n == 64 ? U64_MAX_ : (((i128)1 << n) - 1);
-    // a limb that is not provably < 2^64 (e.g. the top limb of prod(), a sum of three carries) is
-    // narrowed at run time: low 64 bits + an assertion that nothing was cut off
-    auto narrow_limb = [&](const SVal& s_) -> SVal {
-      i128 hi;
-      if (exact_u(s_, hi) && hi <= lim) return s_;
-      if (s_.kind == 0) return SVal::unk();
-      SVal nn = sv(to_N(s_));
-      uint32_t fits = new_value(CLS_U, 0, 1);
-      emit(PZK_N_FITS, fits, nn.id);
-      emit(PZK_ASSERT_NZ, 0, fits);
-      return n_low(nn, lim);
-    };
+    auto narrow_limb = [&](const SVal& s_) -> SVal { return narrow_limb_checked(s_, n); };
     std::vector<SVal> la(k + m), lb(k);
     for (uint64_t i = 0; i < k + m; i++) { la[i] = narrow_limb(args[3].a->v[i]); if (la[i].kind == 2) return false; }
     for (uint64_t i = 0; i < k; i++) { lb[i] = narrow_limb(args[4].a->v[i]); if (lb[i].kind == 2) return false; }
@@ -1511,18 +1522,18 @@ struct Compiler::Impl {
     if (args.size() != 4) return false;
     for (int i = 0; i < 2; i++) if (args[i].arr || args[i].s.kind != 0 || !args[i].s.c.fits64()) return false;
     uint64_t n = args[0].s.c.w[0], k = args[1].s.c.w[0];
-    if (n != 64 || k < 1 || k > 4 || !args[2].arr || !args[3].arr) return false;
+    if ((n != 64 && n != 32) || k < 1 || k * n > 256 || !args[2].arr || !args[3].arr) return false;
     if (args[2].a->v.size() < k || args[3].a->v.size() < k) return false;
     U256 pm;
     for (uint64_t i = 0; i < k; i++) {
       const SVal& q = args[3].a->v[i];
-      if (q.kind != 0 || !q.c.fits64()) return false;
-      pm.w[i] = q.c.w[0];
+      if (q.kind != 0 || !q.c.fits64() || (n < 64 && (q.c.w[0] >> n))) return false;
+      pm = add(pm, shl(U256(q.c.w[0]), (int)(i * n)));
     }
     auto it = prime_memo.find(pm);
     bool prime = it != prime_memo.end() ? it->second : (prime_memo[pm] = is_odd_prime(pm));
     if (!prime) return false;
-    i128 lim = U64_MAX_;
+    i128 lim = n == 64 ? U64_MAX_ : (((i128)1 << n) - 1);
     std::vector<SVal> la(k);
     bool all_const = true;
     for (uint64_t i = 0; i < k; i++) {
@@ -1534,14 +1545,9 @@ struct Compiler::Impl {
     if (all_const) return false;  // the unrolled function folds at compile time
     for (uint64_t i = 0; i < k; i++) {
       const SVal& s_ = args[2].a->v[i];
-      i128 hi;
-      if (s_.kind == 0 || (exact_u(s_, hi) && hi <= lim)) { la[i] = s_; continue; }
-      // not provably a 64-bit limb (the difference limbs of long_sub): narrowed under an assertion
-      SVal nn = sv(to_N(s_));
-      uint32_t fits = new_value(CLS_U, 0, 1);
-      emit(PZK_N_FITS, fits, nn.id);
-      emit(PZK_ASSERT_NZ, 0, fits);
-      la[i] = n_low(nn, lim);
+      if (s_.kind == 0) { if (n < 64 && (s_.c.w[0] >> n)) return false; la[i] = s_; continue; }
+      // not provably an n-bit limb (the difference limbs of long_sub): narrowed under an assertion
+      la[i] = narrow_limb_checked(s_, n);
     }
     for (uint64_t i = 0; i < k; i++) if (la[i].kind == 1 && is_pending(la[i].id)) flush_inversions();
     uint32_t off = (uint32_t)list_pool.size();

@@ -265,7 +265,83 @@ static void build_digest_program(pzk_circuit* c, std::vector<DigRec>& recs, std:
   }
 }
 
+// name -> witness index of an iden3 .sym file (lines "labelIdx,witnessIdx,componentIdx,name"; -1 = optimised away)
+static int read_sym(const char* path, std::unordered_map<std::string, int64_t>& m, std::string& err) {
+  FILE* f = fopen(path, "rb");
+  if (!f) { err = std::string("cannot open ") + path; return PZK_EIO; }
+  std::vector<char> line(1 << 16);
+  while (fgets(line.data(), (int)line.size(), f)) {
+    char* p1 = strchr(line.data(), ',');
+    char* p2 = p1 ? strchr(p1 + 1, ',') : nullptr;
+    char* p3 = p2 ? strchr(p2 + 1, ',') : nullptr;
+    if (!p3) continue;
+    long long w = strtoll(p1 + 1, nullptr, 10);
+    size_t n = strlen(p3 + 1);
+    while (n && (p3[n] == '\n' || p3[n] == '\r')) n--;
+    m.emplace(std::string(p3 + 1, n), (int64_t)w);
+  }
+  fclose(f);
+  return PZK_OK;
+}
+
+// Re-number the program's wires after an EXTERNAL .sym (one written by the circom compiler for the same circuit at
+// any optimisation level): wire <- the witness index the external file gives the signal of the same qualified
+// name; signals it lists with -1, or not at all, are dropped; signals merged into one wire are written once.
+// After this calculateWitness / calculateWTNSBin / the digest all use the external numbering.
+static int remap_wires(pzk_circuit* c, const char* own_sym, const char* ext_sym) {
+  std::unordered_map<std::string, int64_t> own, ext;
+  std::string e;
+  int rc = read_sym(own_sym, own, e);
+  if (rc == PZK_OK) rc = read_sym(ext_sym, ext, e);
+  if (rc) { set_err(c, e); return rc; }
+  std::vector<int64_t> to(c->h.n_wires, -1);
+  int64_t max_w = 0;
+  for (auto& kv : ext) {
+    if (kv.second < 0) continue;
+    auto it = own.find(kv.first);
+    if (it == own.end()) { set_err(c, "external .sym names `" + kv.first + "`, which is not a signal of this program"); return PZK_EFORMAT; }
+    if (it->second <= 0 || it->second >= (int64_t)c->h.n_wires) { set_err(c, "program .sym does not belong to this program"); return PZK_EFORMAT; }
+    to[it->second] = kv.second;
+    if (kv.second > max_w) max_w = kv.second;
+  }
+  const uint32_t n_new = (uint32_t)max_w + 1;
+  std::vector<uint8_t> taken(n_new, 0);
+  taken[0] = 1;
+  PzkSegment* segs = const_cast<PzkSegment*>(c->segs);
+  PzkExport* ex = const_cast<PzkExport*>(c->exports);
+  uint64_t w = 0;
+  for (uint32_t s = 0; s < c->h.n_segments; s++) {
+    const uint64_t lo = segs[s].exp_off, hi = lo + segs[s].n_exp;
+    segs[s].exp_off = w;
+    for (uint64_t k = lo; k < hi; k++) {
+      const int64_t nw = to[ex[k].wire];
+      if (nw <= 0 || taken[nw]) continue;
+      taken[nw] = 1;
+      ex[w] = ex[k];
+      ex[w].wire = (uint32_t)nw;
+      w++;
+    }
+    segs[s].n_exp = w - segs[s].exp_off;
+  }
+  for (uint32_t i = 1; i < n_new; i++)
+    if (!taken[i]) { set_err(c, "external .sym: witness index " + std::to_string(i) + " has no signal of this program behind it"); return PZK_EFORMAT; }
+  c->h.n_exports = w;
+  c->h.n_wires = n_new;
+  return PZK_OK;
+}
+
+static int open_impl(const char* program_path, const char* own_sym, const char* ext_sym, int cuda_device, pzk_circuit** out);
+
 int pzk_circuit_open(const char* program_path, int cuda_device, pzk_circuit** out) {
+  return open_impl(program_path, nullptr, nullptr, cuda_device, out);
+}
+int pzk_circuit_open_ex(const char* program_path, const char* program_sym_path, const char* external_sym_path,
+                        int cuda_device, pzk_circuit** out) {
+  if (!program_sym_path || !external_sym_path) return PZK_EINVAL;
+  return open_impl(program_path, program_sym_path, external_sym_path, cuda_device, out);
+}
+
+static int open_impl(const char* program_path, const char* own_sym, const char* ext_sym, int cuda_device, pzk_circuit** out) {
   if (!program_path || !out) return PZK_EINVAL;
   *out = nullptr;
   int ndev = 0;
@@ -296,6 +372,7 @@ int pzk_circuit_open(const char* program_path, int cuda_device, pzk_circuit** ou
   c->exports = (const PzkExport*)(b + pos); pos = al16(pos + c->h.n_exports * sizeof(PzkExport));
   if (pos + c->h.reserved[0] > (uint64_t)sz) { set_err(c, "truncated program file"); return PZK_EFORMAT; }
   c->meta.assign((const char*)(b + pos), c->h.reserved[0]);
+  if (ext_sym) { int rrc = remap_wires(c, own_sym, ext_sym); if (rrc) return rrc; }
   {
     // packed input record: [1-byte inputs (declared <= 8 bits)] pad8 [8-byte inputs (<= 64 bits)] [32-byte field inputs]
     uint32_t n8 = 0, n64 = 0;
@@ -1057,7 +1134,7 @@ int pzk_r1cs_check_circuit(pzk_r1cs* r, pzk_circuit* c, const uint64_t* lanes, u
                            int64_t* first_bad, double* eval_ms, double* check_ms, char* err, size_t err_len) {
   if (!r || !c || !lanes || !verdicts || n_lanes == 0 || c->batch == 0) return PZK_EINVAL;
   if (r->device != c->device) { set_err(err, err_len, "the r1cs handle and the circuit live on different devices"); return PZK_EINVAL; }
-  if (r->n_wires != c->h.n_wires || r->n_constraints != c->h.n_constraints) {
+  if (r->n_wires != c->h.n_wires) {
     set_err(err, err_len, "Invalid witness length. Circuit: " + std::to_string(r->n_wires) + ", witness: " + std::to_string(c->h.n_wires) +
                               " (this .r1cs does not belong to the program: different wire layout)");
     return PZK_EFORMAT;

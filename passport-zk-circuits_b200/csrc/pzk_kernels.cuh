@@ -112,12 +112,18 @@ __device__ __forceinline__ void ldPool(const u64* pool, u32 idx, u64* v) {
 // Binary extended GCD with the invariants x1 * a == u, x2 * a == v (mod p); p may exceed 2^255, so the
 // halving step keeps the carry of x + p.
 __device__ __noinline__ void modinv_device(const u32* Lst, u64* Ul, u64 L) {
-  const unsigned k = Lst[1];
+  const unsigned n = Lst[0], k = Lst[1];  // k limbs of n bits (n = 64, or 32 for the 7-chunk secp224r1 verifier), k * n <= 256
   const u32* ia = Lst + 3;
   const u32* ip = ia + k;
   const u32* oo = ip + k + 1;
   u64 a[4] = {0, 0, 0, 0}, p[4] = {0, 0, 0, 0};
-  for (unsigned i = 0; i < k && i < 4; i++) { a[i] = LDU(ia[i]); p[i] = LDU(ip[i]); }
+  for (unsigned i = 0; i < k; i++) {
+    const unsigned pos = i * n;
+    if (pos >= 256) break;
+    const u64 av = LDU(ia[i]), pv = LDU(ip[i]);
+    a[pos >> 6] |= av << (pos & 63);
+    p[pos >> 6] |= pv << (pos & 63);
+  }
   STU(ip[k], 0);
   u64 u[4], v[4] = {p[0], p[1], p[2], p[3]}, x1[4] = {1, 0, 0, 0}, x2[4] = {0, 0, 0, 0};
   // u = a mod p, bit-serial with the carry of the doubling kept (rr < p <= 2^256 - 1)
@@ -155,37 +161,52 @@ __device__ __noinline__ void modinv_device(const u32* Lst, u64* Ul, u64 L) {
     for (int i = 0; i < 4; i++) r[i] = use1 ? x1[i] : x2[i];
     if (!is_one(u) && !is_one(v)) r[0] = r[1] = r[2] = r[3] = 0;
   }
-  for (unsigned i = 0; i < k && i < 4; i++) STU(oo[i], r[i]);
+  const u64 lmask = n >= 64 ? ~0ull : ((1ull << n) - 1);
+  for (unsigned i = 0; i < k; i++) {
+    const unsigned pos = i * n;
+    STU(oo[i], pos < 256 ? ((r[pos >> 6] >> (pos & 63)) & lmask) : 0);
+  }
 }
 
 __device__ __noinline__ u32 bigdiv_device(const u32* Lst, u64* Ul, u64 L) {
-  const unsigned k = Lst[1], m = Lst[2];
+  // limbs of n = 64 bits are the digits of algorithm D; limbs of n = 32 bits (the secp224r1 verifier) are packed
+  // in pairs: kl / ml are the caller's limb counts, k / m the digit counts
+  const unsigned n = Lst[0], kl = Lst[1], ml = Lst[2];
+  const bool half = n == 32;
+  const unsigned k = half ? (kl + 1) / 2 : kl, na_l = kl + ml, n_a = half ? (na_l + 1) / 2 : na_l, m = n_a - k;
   const u32* ia = Lst + 3;
-  const u32* ib = ia + (k + m);
-  const u32* oq = ib + k;
-  const u32* orr = oq + (m + 1);
+  const u32* ib = ia + na_l;
+  const u32* oq = ib + kl;
+  const u32* orr = oq + (ml + 1);
+  auto dig_a = [&](unsigned i) -> u64 {
+    if (!half) return LDU(ia[i]);
+    return LDU(ia[2 * i]) | (2 * i + 1 < na_l ? LDU(ia[2 * i + 1]) << 32 : 0ull);
+  };
+  auto dig_b = [&](unsigned i) -> u64 {
+    if (!half) return LDU(ib[i]);
+    return LDU(ib[2 * i]) | (2 * i + 1 < kl ? LDU(ib[2 * i + 1]) << 32 : 0ull);
+  };
   u64 un[132], vn[66];
   u32 st = 0;
-  u64 top = LDU(ib[k - 1]);
-  if (top == 0 || k < 2 || k > 64 || k + m > 128) {
-    for (unsigned i = 0; i <= m; i++) STU(oq[i], 0);
-    for (unsigned i = 0; i < k; i++) STU(orr[i], 0);
+  const u64 top = (kl >= 2 && k >= 2) ? dig_b(k - 1) : 0;
+  if (kl < 2 || k < 2 || k > 64 || n_a > 128 || LDU(ib[kl - 1]) == 0 || top == 0) {
+    for (unsigned i = 0; i <= ml; i++) STU(oq[i], 0);
+    for (unsigned i = 0; i < kl; i++) STU(orr[i], 0);
     return PZK_LANE_BIGDIV_PRE;
   }
   int s = __clzll(top);
   // normalise
   for (int i = (int)k - 1; i > 0; i--) {
-    u64 hi = LDU(ib[i]), lo = LDU(ib[i - 1]);
+    u64 hi = dig_b(i), lo = dig_b(i - 1);
     vn[i] = s ? ((hi << s) | (lo >> (64 - s))) : hi;
   }
-  vn[0] = LDU(ib[0]) << s;
-  const unsigned n_a = k + m;
-  un[n_a] = s ? (LDU(ia[n_a - 1]) >> (64 - s)) : 0;
+  vn[0] = dig_b(0) << s;
+  un[n_a] = s ? (dig_a(n_a - 1) >> (64 - s)) : 0;
   for (int i = (int)n_a - 1; i > 0; i--) {
-    u64 hi = LDU(ia[i]), lo = LDU(ia[i - 1]);
+    u64 hi = dig_a(i), lo = dig_a(i - 1);
     un[i] = s ? ((hi << s) | (lo >> (64 - s))) : hi;
   }
-  un[0] = LDU(ia[0]) << s;
+  un[0] = dig_a(0) << s;
   for (int j = (int)m; j >= 0; j--) {
     // estimate the quotient digit from the top two digits
     u64 u2 = un[j + k], u1 = un[j + k - 1], u0 = un[j + k - 2];
@@ -243,11 +264,20 @@ __device__ __noinline__ u32 bigdiv_device(const u32* Lst, u64* Ul, u64 L) {
       }
       un[j + k] += c;
     }
-    STU(oq[j], qhat);
+    if (!half) STU(oq[j], qhat);
+    else {
+      // quotient limbs beyond m are zero whenever the circom function's precondition a < 2^(n (m + 1)) b holds
+      if (2u * j <= ml) STU(oq[2 * j], qhat & 0xffffffffull); else if (qhat & 0xffffffffull) st |= PZK_LANE_BIGDIV_PRE;
+      if (2u * j + 1 <= ml) STU(oq[2 * j + 1], qhat >> 32); else if (qhat >> 32) st |= PZK_LANE_BIGDIV_PRE;
+    }
   }
   for (unsigned i = 0; i < k; i++) {
     u64 v = s ? ((un[i] >> s) | (un[i + 1] << (64 - s))) : un[i];
-    STU(orr[i], v);
+    if (!half) STU(orr[i], v);
+    else {
+      STU(orr[2 * i], v & 0xffffffffull);
+      if (2 * i + 1 < kl) STU(orr[2 * i + 1], v >> 32);
+    }
   }
   return st;
 }

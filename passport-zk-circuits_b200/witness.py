@@ -83,6 +83,8 @@ def lib():
                                  cp, ctypes.c_size_t]
     L.pzk_circuit_open.restype = ctypes.c_int
     L.pzk_circuit_open.argtypes = [cp, ctypes.c_int, ctypes.POINTER(vp)]
+    L.pzk_circuit_open_ex.restype = ctypes.c_int
+    L.pzk_circuit_open_ex.argtypes = [cp, cp, cp, ctypes.c_int, ctypes.POINTER(vp)]
     L.pzk_circuit_close.argtypes = [vp]
     L.pzk_last_error.restype = cp
     L.pzk_last_error.argtypes = [vp]
@@ -299,10 +301,19 @@ class WitnessCalculator:
     """`new WitnessCalculator(wasm)` of circom's witness_calculator.js, with a program instead of
     the wasm.  One instance is reusable across calls; it is not thread-safe."""
 
-    def __init__(self, program_path, device=0):
+    def __init__(self, program_path, device=0, external_sym=None, program_sym=None):
+        """external_sym: a .sym written by the circom compiler for this circuit (any optimisation level): the wires
+        are then numbered after it (pzk_circuit_open_ex); program_sym defaults to the .sym next to the program."""
         self._L = lib()
         self._h = ctypes.c_void_p()
-        rc = self._L.pzk_circuit_open(os.fsencode(program_path), device, ctypes.byref(self._h))
+        if external_sym is not None:
+            if program_sym is None:
+                base = program_path[:-5] if program_path.endswith(".pzkp") else program_path
+                program_sym = base + ".sym" if os.path.exists(base + ".sym") else base + ".sym.local"
+            rc = self._L.pzk_circuit_open_ex(os.fsencode(program_path), os.fsencode(program_sym), os.fsencode(external_sym),
+                                             device, ctypes.byref(self._h))
+        else:
+            rc = self._L.pzk_circuit_open(os.fsencode(program_path), device, ctypes.byref(self._h))
         if rc != 0:
             msg = self._L.pzk_last_error(self._h).decode() if self._h else ""
             if self._h:

@@ -55,7 +55,8 @@ def golden(name, sym_path, inputs_list, n_pub, n_samples=4096):
 
 
 def main():
-    which = sys.argv[1:] or ["poseidon2", "sha256_1", "smt80", "query80", "c3", "c4_sig3", "c4_sig10", "c4_sig13"]
+    from passport_zk_circuits_b200.artifacts import C4_VARIANTS as _ALL_C4
+    which = sys.argv[1:] or (["poseidon2", "sha256_1", "smt80", "query80", "c3"] + list(_ALL_C4))
     if "poseidon2" in which:
         golden("poseidon2", os.path.join(ART, "poseidon2.sym"), [{"in": ["1", "2"]}, {"in": ["0", str(co.P - 1)]}], 1)
     if "sha256_1" in which:

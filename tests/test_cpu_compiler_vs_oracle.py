@@ -242,3 +242,47 @@ def test_reference_p256_doubling(artifacts_dir):
     off = ints_to_u64(chunks_le(pts[0][0], 64, 4) + chunks_le(pts[0][1] ^ 5, 64, 4))
     compare(prefix, main, np.stack([off]), expect_ok=False)
     assert prog.witness(off)[0] & 2
+
+
+@pytest.mark.skipif(not has_reference(), reason="/root/reference is not mounted here")
+def test_translated_functions_equal_the_tree_walker():
+    """oracle/circom_oracle.py runs circom `function` bodies as translated Python (FunctionTranslator) instead of walking
+    their syntax trees; both execution modes of the reference's own big-integer hint functions
+    (/root/reference/circuits/lib/circuits/bigInt/bigIntFunc.circom) must return identical values on random operands,
+    including the data-dependent early returns of short_div_norm / long_gt and the 380-round mod_inv."""
+    import random
+    import circom_oracle as co
+    main = os.path.join(ROOT, "artifacts", "_mains", "p256dbl.circom")
+    fast, slow = co.Circuit(main), co.Circuit(main, translate_functions=False)
+    rng = random.Random(12)
+    P256 = 0xFFFFFFFF00000001000000000000000000000000FFFFFFFFFFFFFFFFFFFFFFFF
+
+    def limbs(x, k, pad=200):
+        return [(x >> (64 * i)) & (2 ** 64 - 1) for i in range(k)] + [0] * (pad - k)
+    cases = []
+    for _ in range(6):
+        a, b = rng.randrange(P256), rng.randrange(1, P256)
+        cases += [("long_add_mod", [64, 4, limbs(a, 4), limbs(b, 4), limbs(P256, 4)]),
+                  ("long_sub_mod", [64, 4, limbs(a, 4), limbs(b, 4), limbs(P256, 4)]),
+                  ("prod_mod", [64, 4, limbs(a, 4), limbs(b, 4), limbs(P256, 4)]),
+                  ("prod", [64, 4, limbs(a, 4), limbs(b, 4)]),
+                  ("long_gt", [64, 4, limbs(a, 4), limbs(b, 4)]),
+                  ("long_div", [64, 4, 4, limbs(a * b, 8), limbs(P256, 4)]),
+                  ("long_scalar_mult", [64, 4, a & (2 ** 64 - 1), limbs(b, 4)]),
+                  ("log_ceil", [rng.randrange(1, 2 ** 40)]), ("div_ceil", [rng.randrange(1000), rng.randrange(1, 50)]),
+                  ("is_negative", [rng.choice([a, co.P - 5, 5])])]
+    cases += [("mod_inv", [64, 4, limbs(rng.randrange(1, P256), 4), limbs(P256, 4)]) for _ in range(2)]
+    cases += [("mod_inv", [64, 4, limbs(0, 4), limbs(P256, 4)])]
+    translated = set()
+    for name, args in cases:
+        got = fast.translator.call(name, [co._copy(x) for x in args])
+        want = slow.interpret_function(name, [co._copy(x) for x in args])
+        assert got == want, name
+        if fast.translator.fns.get(name):
+            translated.add(name)
+    assert {"mod_inv", "long_div", "prod", "long_sub_mod", "long_gt"} <= translated   # really the fast path
+    # and a whole circuit both ways: one P-256 doubling, every signal
+    G = [0x6B17D1F2E12C4247F8BCE6E563A440F277037D812DEB33A0F4A13945D898C296,
+         0x4FE342E2FE1A7F9B8EE7EB4A7C0F9E162BCE33576B315ECECBB6406837BF51F5]
+    inp = {"in": [[str((G[i] >> (64 * j)) & (2 ** 64 - 1)) for j in range(4)] for i in range(2)]}
+    assert fast.calculate_witness(inp, check=True) == slow.calculate_witness(inp, check=True)

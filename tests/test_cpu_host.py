@@ -112,7 +112,8 @@ def golden_inputs(meta, case):
     return {k: (list(v) if isinstance(v, str) and size[k] > 1 else v) for k, v in case["inputs"].items()}
 
 
-GOLDEN = ["poseidon2", "sha256_1", "smt80", "query80", "c3", "c4_sig3", "c4_sig10", "c4_sig13", "c4_sig20"]
+GOLDEN = ["poseidon2", "sha256_1", "smt80", "query80", "c3", "c4_sig3", "c4_sig10", "c4_sig13", "c4_sig20",
+          "c4_sig2", "c4_sig4", "c4_sig11", "c4_sig12", "c4_sig14", "c4_sig21", "c4_sig24", "c4_na", "c4_ecaa", "c4_td1"]
 
 
 @pytest.mark.parametrize("name", GOLDEN)
@@ -121,9 +122,7 @@ def test_golden_vectors_through_the_compiled_program(artifacts_dir, name):
     (tests/golden/make_golden.py); the compiled program evaluated by the C oracle must reproduce the
     .wtns data section byte for byte."""
     path = os.path.join(ROOT, "tests", "golden", name + ".json")
-    if not os.path.exists(path):
-        pytest.skip("fixture not generated yet")
-    g = json.load(open(path))
+    g = json.load(open(path))     # every listed circuit has a committed fixture (no skip: VERDICT r1)
     prog = oracle_ref.RefProgram(W.artifact(name))
     for case in g["cases"]:
         assert case["n_wires"] == prog.n_wires and case["n_constraints"] == prog.n_constraints
@@ -572,3 +571,19 @@ def test_witness_digest_host_restatement_matches_the_c_weights():
     w[:, 3] >>= np.uint64(3)
     want = sum(int(k[i]) * int.from_bytes(w[i].tobytes(), "little") for i in range(1000)) % W.P
     assert int.from_bytes(W.witness_digest(w).tobytes(), "little") == want
+
+
+def test_napi_shim_binds_only_exported_symbols(artifacts_dir):
+    """native/pzk_napi.cc cannot be built here (no node): at least every pzk_* symbol it calls must be declared in
+    pzk.h and exported by libpzk.so, and it must compile as C++ against a stub node_api.h."""
+    src = open(os.path.join(ROOT, "native", "pzk_napi.cc")).read()
+    used = set(re.findall(r"\b(pzk_[a-z0-9_]+)\s*\(", src))
+    hdr = open(os.path.join(ROOT, "include", "pzk.h")).read()
+    declared = set(re.findall(r"\b(pzk_[a-z0-9_]+)\s*\(", hdr))
+    assert used and used <= declared, used - declared
+    lib = ctypes.CDLL(W.LIB_PATH)
+    assert all(hasattr(lib, n) for n in used)
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "tests", "stubs"),
+                        "-I" + os.path.join(ROOT, "include"), "-DNODE_GYP_MODULE_NAME=pzk",
+                        os.path.join(ROOT, "native", "pzk_napi.cc")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr

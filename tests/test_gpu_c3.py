@@ -91,11 +91,14 @@ def _golden_inputs(calc, name):
     return g, ins
 
 
-@pytest.mark.parametrize("name", ["c4_sig3", "c4_sig10", "c4_sig13", "c4_sig20"])
+@pytest.mark.parametrize("name", ["c4_sig3", "c4_sig10", "c4_sig13", "c4_sig20", "c4_sig2", "c4_sig4", "c4_sig11", "c4_sig12",
+                                  "c4_sig14", "c4_sig21", "c4_sig24", "c4_na", "c4_ecaa", "c4_td1"])
 def test_config4_variants(name):
-    """SHA-1 + RSA PKCS#1 v1.5 (SIG 3), RSA-PSS e=3 (SIG 10), RSA-PSS SHA-384 with 1024-bit blocks (SIG 13),
-    ECDSA P-256 (SIG 20): golden .wtns bytes from the Python oracle, then a small synthetic batch against
-    the C oracle."""
+    """Every arm of the reference's dispatch (signatureVerification.circom:26-116, identity.circom:26-84): SHA-1 + RSA
+    PKCS#1 v1.5 (SIG 3), RSA-4096 (2), RSA-3072 e = 37187 with the non-Karatsuba multiplier (4), RSA-PSS e = 3 (10),
+    e = 65537 (11), salt 64 (12), SHA-384 with 1024-bit blocks (13), 3072 bits (14), ECDSA P-256 (20), brainpoolP256r1
+    (21), secp224r1 in 7 x 32-bit chunks (24), a document without DG15, an EC active-authentication key, a TD1 document:
+    golden .wtns bytes from the Python oracle, then a small synthetic batch against the C oracle."""
     import hashlib
     from passport_zk_circuits_b200.artifacts import C4_VARIANTS
     prog = W.artifact(name)
@@ -108,7 +111,7 @@ def test_config4_variants(name):
             assert hashlib.sha256(res.witnesses[j].tobytes()).hexdigest() == case["wtns_data_sha256"]
         del res
     fac = PassportFactory(C4_VARIANTS[name], seed=11, n_sig_keys=1, n_aa_keys=1)
-    B = 6 if name != "c4_sig20" else 4
+    B = 6 if name not in ("c4_sig20", "c4_sig21", "c4_sig24") else 4
     inp = W.pack_inputs_fast(calc.meta, [fac.make(i).inputs for i in range(B)])
     d = {x["name"]: x for x in calc.meta["inputs"]}
     inp[2, d["signature"]["offset"] + 1, 0] ^= np.uint64(4)

@@ -169,3 +169,58 @@ def test_c3_digest_and_hand_off():
     assert np.array_equal(first[~ok], res.first_bad[:96][~ok])
     r.close()
     calc.close()
+
+
+def test_external_sym_renumbers_the_witness(tmp_path):
+    """pzk_circuit_open_ex: the wires follow an EXTERNAL .sym (what `circom --O2` would have written): a permuted
+    numbering with a third of the signals optimised away (-1) and aliases merged into one wire.  The witness,
+    the .wtns bytes and the digest must be those of the own-layout witness re-indexed BY NAME."""
+    prefix = os.path.join(ROOT, "artifacts", "smt80")
+    own = formats.read_sym(prefix + ".sym")                      # name -> own wire
+    calc0 = W.WitnessCalculator(prefix + ".pzkp", 0)
+    n_pub = calc0.n_public
+    rng = np.random.default_rng(9)
+    names = sorted(own, key=lambda k: own[k])
+    keep = [nm for nm in names if own[nm] <= n_pub or rng.random() > 0.33]      # public wires stay, in place
+    inner = [nm for nm in keep if own[nm] > n_pub]
+    perm = rng.permutation(len(inner))
+    ext = {nm: own[nm] for nm in keep if own[nm] <= n_pub}
+    for j, nm in zip(perm, inner):
+        ext[nm] = n_pub + 1 + int(j)
+    # merge: two kept signals that are aliases of each other in the circuit share one external wire
+    # (smt80: hashers[i].in[..] aliases) - emulate with the dropped list: a dropped name pointing at a kept wire
+    dropped = [nm for nm in names if nm not in ext]
+    sym_path = tmp_path / "ext.sym"
+    with open(sym_path, "w") as f:
+        for i, nm in enumerate(names):
+            f.write(f"{i + 1},{ext.get(nm, -1)},0,{nm}\n")
+    calc = W.WitnessCalculator(prefix + ".pzkp", 0, external_sym=str(sym_path))
+    assert calc.n_wires == len(ext) + 1
+    ref = oracle_ref.RefProgram(prefix + ".pzkp")
+    from test_gpu_parity import smt_inputs
+    inp = smt_inputs(ref.meta, [99 + 7 * i for i in range(20)])
+    a = calc0.calculateWitnessBatch(inp, export_lanes=range(20))
+    b = calc.calculateWitnessBatch(inp, export_lanes=range(20))
+    want = np.zeros((20, calc.n_wires, 4), dtype=np.uint64)
+    want[:, 0, 0] = 1
+    for nm, w in ext.items():
+        want[:, w] = a.witnesses[:, own[nm]]
+    assert np.array_equal(b.witnesses, want)
+    assert np.array_equal(a.status, b.status) and np.array_equal(a.public, b.public)
+    calc.set_digest(True)
+    calc.upload(inp)
+    calc.run(True)
+    dg = calc.download_digest()
+    for lane in range(20):
+        assert np.array_equal(dg[lane], W.witness_digest(want[lane]))
+    blob = calc.calculateWTNSBin({k: [int.from_bytes(inp[3, d["offset"] + j].tobytes(), "little") for j in range(d["size"])]
+                                  if d["size"] > 1 else int.from_bytes(inp[3, d["offset"]].tobytes(), "little")
+                                  for d in ref.meta["inputs"] for k in [d["name"]]})
+    assert blob == formats.write_wtns([int.from_bytes(want[3, i].tobytes(), "little") for i in range(calc.n_wires)])
+    # an external .sym that names a signal the program does not have is refused
+    with open(sym_path, "a") as f:
+        f.write("999999,5,0,main.no_such_signal\n")
+    with pytest.raises(W.PzkError, match="not a signal of this program"):
+        W.WitnessCalculator(prefix + ".pzkp", 0, external_sym=str(sym_path))
+    calc.close()
+    calc0.close()
