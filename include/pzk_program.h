@@ -12,6 +12,10 @@
  *   F : BN254 Fr element in Montgomery form, 4 x 64-bit limbs (R = 2^256)
  *   N : canonical (non-Montgomery) 256-bit integer, lives in an F slot; only a
  *       temporary for circom's integer operators (>> & \ % < ...) on wide values
+ *   Z : exact signed integer |v| < 2^250 in 256-bit two's complement, lives in an F slot: values the compiler
+ *       proves to be integers too wide for 64 bits but far below p / 2 (the limb products, Karatsuba sums and
+ *       carries of the big-integer multipliers).  + - * are plain integer instructions instead of Montgomery
+ *       products; the canonical value of a negative v is p + v
  *
  * Storage: two slot planes per lane tile, slot-major / lane-minor so that a warp
  * touches 32 consecutive words:
@@ -30,7 +34,7 @@ extern "C" {
 #endif
 
 #define PZK_MAGIC 0x314b5a50u /* "PZK1" */
-#define PZK_VERSION 10u
+#define PZK_VERSION 11u
 
 /* ---- opcodes ------------------------------------------------------------ */
 enum PzkOpcode {
@@ -124,7 +128,15 @@ enum PzkOpcode {
   PZK_ASSERT_NZ = 61, /* lane status |= ASSERT when a(U) == 0                */
   PZK_IN_U = 62,      /* dst(U) = input[a], range check: value < 2^imm16      */
   PZK_IN_F = 63,      /* dst(F) = Montgomery(input[a]); value must be < p    */
-  PZK_OPCODE_MAX = 64
+  /* Z class (exact wide integers, two's complement in the F plane) */
+  PZK_Z_ADD = 64,    /* dst = a + b                (b may be a pool constant: PZK_FLAG_B_POOL, raw two's complement) */
+  PZK_Z_SUB = 65,
+  PZK_Z_MUL = 66,    /* dst = a * b mod 2^256; imm16 = la | lb << 4: when non-zero both operands are non-negative and
+                        fit la / lb 32-bit limbs (schoolbook la x lb instead of the truncated 8 x 8)            */
+  PZK_Z_FROM_U = 67, /* dst(Z) = a(U)                                                                          */
+  PZK_Z_FROM_I = 68, /* dst(Z) = a(I), sign extended                                                            */
+  PZK_Z_CONST = 69,  /* dst(Z) = fpool[a] (raw two's complement)                                                */
+  PZK_OPCODE_MAX = 80
 };
 
 /* flags */
@@ -135,6 +147,8 @@ enum PzkOpcode {
                               evaluator takes them on a two-compare path in front of its opcode dispatch      */
 #define PZK_FLAG_NBASE 16u /* U_EXTRACT / N_EXTRACT / CHECK_RANGE: operand a is a plain 256-bit value (F plane) */
 #define PZK_FLAG_W64 32u   /* V_LUT: 64 lanes, a second extension record follows                              */
+#define PZK_FLAG_ZSRC 64u  /* N_FROM_F / F_FROM_N: operand a is a Z value: dst(N) = canonical(a) = a < 0 ? p + a : a,
+                              dst(F) = Montgomery(a)                                                           */
 
 typedef struct PzkOp {
   uint8_t opc;
@@ -162,7 +176,7 @@ typedef struct PzkOpExt {
 #define PZK_LANE_HINT 16u        /* a hint intrinsic met a zero denominator (BJJ_MUL8; unreachable on curve points) */
 
 /* ---- constraint rows (slot addressed, per segment) ---------------------- */
-/* term.ref : bits 30..31 = class (0 = U unsigned, 1 = I signed 64, 2 = F Montgomery),
+/* term.ref : bits 30..31 = class (0 = U unsigned, 1 = I signed 64, 2 = F Montgomery, 3 = Z signed 256-bit integer),
  *            bits 0..29 = slot
  * term.coef: index into the coefficient pool                                */
 typedef struct PzkTerm {
@@ -229,6 +243,7 @@ typedef struct PzkExport {
   uint32_t pad;
 } PzkExport;
 #define PZK_REF_VIEW_N 0x20000000u
+#define PZK_REF_Z 0x10000000u /* export entry of class 2: the F-plane slot holds a Z value (canonical = v < 0 ? p + v : v) */
 #define PZK_REF_TABVIEW 0xFFFFFFFCu
 
 typedef struct PzkInput {

@@ -202,6 +202,30 @@ static int is_neg(const uint64_t* a) { /* a > p/2 */
   uint64_t h[4]; shr4(h, P, 1);
   return cmp4(a, h) > 0;
 }
+/* ---- Z class (pzk_program.h): exact signed integers in 256-bit two's complement ---- */
+static void z_canonical(uint64_t* r, const uint64_t* z) { /* v < 0 ? p + v : v */
+  memcpy(r, z, 32);
+  if ((int64_t)z[3] < 0) add4(r, r, P);
+}
+static void z_to_mont(uint64_t* r, const uint64_t* z) {
+  uint64_t m[4], zero[4] = {0, 0, 0, 0};
+  int neg = (int64_t)z[3] < 0;
+  if (neg) sub4(m, zero, z); else memcpy(m, z, 32);
+  to_mont(r, m);
+  if (neg) fsub(r, zero, r);
+}
+static void z_mul(uint64_t* r, const uint64_t* a, const uint64_t* b) { /* a * b mod 2^256 */
+  uint64_t t[4] = {0, 0, 0, 0};
+  for (int i = 0; i < 4; i++) {
+    uint64_t carry = 0;
+    for (int j = 0; i + j < 4; j++) {
+      u128 x = (u128)a[i] * b[j] + t[i + j] + carry;
+      t[i + j] = (uint64_t)x; carry = (uint64_t)(x >> 64);
+    }
+  }
+  memcpy(r, t, 32);
+}
+
 static int scmp(const uint64_t* a, const uint64_t* b) {
   int na = is_neg(a), nb = is_neg(b);
   if (na != nb) return na ? -1 : 1;
@@ -398,8 +422,18 @@ uint32_t pzk_ref_witness(const PzkRefProgram* p, const uint8_t* inputs, uint8_t*
         case PZK_F_EQ: WRU(o->dst, memcmp(FA, FB, 32) == 0); break;
         case PZK_F_NE: WRU(o->dst, memcmp(FA, FB, 32) != 0); break;
         case PZK_F_CSEL: WRF(o->dst, p->fpool + 4 * ((uint64_t)o->b + UA)); break;
-        case PZK_N_FROM_F: { uint64_t r[4]; from_mont(r, FA); WRF(o->dst, r); break; }
-        case PZK_F_FROM_N: { uint64_t t[4], r[4]; memcpy(t, FA, 32); reduce_p(t); to_mont(r, t); WRF(o->dst, r); break; }
+        case PZK_N_FROM_F: { uint64_t r[4]; if (o->flags & PZK_FLAG_ZSRC) z_canonical(r, FA); else from_mont(r, FA); WRF(o->dst, r); break; }
+        case PZK_F_FROM_N: {
+          uint64_t t[4], r[4];
+          if (o->flags & PZK_FLAG_ZSRC) z_to_mont(r, FA); else { memcpy(t, FA, 32); reduce_p(t); to_mont(r, t); }
+          WRF(o->dst, r); break;
+        }
+        case PZK_Z_ADD: { uint64_t r[4]; add4(r, FA, FB); WRF(o->dst, r); break; }
+        case PZK_Z_SUB: { uint64_t r[4]; sub4(r, FA, FB); WRF(o->dst, r); break; }
+        case PZK_Z_MUL: { uint64_t r[4]; z_mul(r, FA, FB); WRF(o->dst, r); break; }
+        case PZK_Z_FROM_U: { uint64_t w[4] = {UA, 0, 0, 0}; WRF(o->dst, w); break; }
+        case PZK_Z_FROM_I: { uint64_t x_ = UA, sx = (uint64_t)((int64_t)x_ >> 63); uint64_t w[4] = {x_, sx, sx, sx}; WRF(o->dst, w); break; }
+        case PZK_Z_CONST: WRF(o->dst, p->fpool + 4 * (uint64_t)o->a); break;
         case PZK_N_FROM_U: { uint64_t w[4] = {UA, 0, 0, 0}; WRF(o->dst, w); break; }
         case PZK_N_BIT: WRU(o->dst, o->b < 256 ? (FA[o->b >> 6] >> (o->b & 63)) & 1 : 0); break;
         case PZK_N_LOW: WRU(o->dst, FA[0]); break;
@@ -523,6 +557,7 @@ uint32_t pzk_ref_witness(const PzkRefProgram* p, const uint8_t* inputs, uint8_t*
                 uint32_t cls = PZK_REF_CLS(ref), slot = PZK_REF_SLOT(ref);
                 int in_cell = (ref & PZK_TERM_CELL) != 0;
                 if (cls == 2) memcpy(v, in_cell ? (cells + (ref & 0xffffu)) : (F + 4 * (uint64_t)slot), 32);
+                else if (cls == 3) z_to_mont(v, in_cell ? (cells + (ref & 0xffffu)) : (F + 4 * (uint64_t)slot));
                 else {
                   uint64_t raw = in_cell ? cells[ref & 0xffffu] : U[slot];
                   int neg = cls == 1 && (int64_t)raw < 0;
@@ -608,6 +643,7 @@ uint32_t pzk_ref_witness(const PzkRefProgram* p, const uint8_t* inputs, uint8_t*
           for (int i = 0; i < 4; i++) w[i] &= m[i];
           shl4(w, w, k_);
         }
+        else if (cls == 2 && (ex->ref & PZK_REF_Z)) z_canonical(w, F + 4 * (uint64_t)slot);
         else if (cls == 2) from_mont(w, F + 4 * (uint64_t)slot);
         else if (cls == 1 && (int64_t)U[slot] < 0) { uint64_t m[4] = {(uint64_t)(-(int64_t)U[slot]), 0, 0, 0}; sub4(w, P, m); }
         else w[0] = U[slot];

@@ -80,6 +80,12 @@ static bool small_signed(const U256& c, int64_t& out) {
   return false;
 }
 static U256 from_signed(int64_t v) { return v >= 0 ? U256((uint64_t)v) : sub(FR_P, U256((uint64_t)(-v))); }
+// field element of a Z-class constant stored as a 256-bit two's complement pattern
+static U256 z_field(const U256& pat) {
+  if (!(pat.w[3] >> 63)) return pat;
+  U256 zero;
+  return sub(FR_P, sub(zero, pat));
+}
 
 // ---- linear algebra for constraints -------------------------------------------------
 static void lin_addmul(Lin& dst, const Lin& src, const U256& k) {  // dst += k * src
@@ -144,13 +150,16 @@ struct Compiler::Impl {
   std::vector<i128> v_lo, v_hi;
   std::vector<int32_t> v_tbl;
   std::vector<uint32_t> v_convF, v_convN, v_def;
+  std::vector<uint32_t> v_convZ;   // Z-class copy of a narrow value
+  std::vector<uint16_t> v_zb;      // Z values: |v| < 2^v_zb
+  std::vector<uint8_t> v_zneg;     // Z values: may be negative
   std::vector<uint8_t> v_const;
   std::unordered_map<uint32_t, U256> const_of;
   std::vector<Table> tables;
   std::vector<OpRec> ops;
   std::vector<uint32_t> list_pool;
   std::vector<U256> fpool;
-  std::unordered_map<U256, uint32_t, U256Hash> fpool_mont, fpool_plain, constU, constF;
+  std::unordered_map<U256, uint32_t, U256Hash> fpool_mont, fpool_plain, constU, constF, constZ;
 
   // signals & constraints
   std::vector<uint32_t> sig_val;  // per signal index -> value id (0 = unassigned)
@@ -198,6 +207,7 @@ struct Compiler::Impl {
     uint32_t id = (uint32_t)v_cls.size();
     v_cls.push_back((uint8_t)cls); v_lo.push_back(lo); v_hi.push_back(hi); v_tbl.push_back(tbl);
     v_convF.push_back(0); v_convN.push_back(0); v_def.push_back((uint32_t)ops.size()); v_const.push_back(0);
+    v_convZ.push_back(0); v_zb.push_back(0); v_zneg.push_back(0);
     return id;
   }
   // ---- batched inversion (Montgomery's trick), decided at compile time ----------------------
@@ -221,7 +231,7 @@ struct Compiler::Impl {
     op0 = o.a + 3; nop = k + m + k; def0 = op0 + nop; ndef = m + 1 + k;
   }
   bool op_reads_values(int opc) {
-    switch (opc) { case PZK_NOP: case PZK_U_CONST: case PZK_F_CONST: case PZK_IN_U: case PZK_IN_F: case PZK_BIGDIV: case PZK_MODINV: case PZK_BJJ_MUL8: return false; }
+    switch (opc) { case PZK_NOP: case PZK_U_CONST: case PZK_F_CONST: case PZK_Z_CONST: case PZK_IN_U: case PZK_IN_F: case PZK_BIGDIV: case PZK_MODINV: case PZK_BJJ_MUL8: return false; }
     return true;
   }
   bool is_pending(uint32_t v) { return v != PZK_OPERAND_NONE && v < v_pending.size() && v_pending[v]; }
@@ -392,6 +402,7 @@ struct Compiler::Impl {
     uint32_t r = new_value(CLS_F);
     if (c == CLS_U) emit(PZK_F_FROM_U, r, id);
     else if (c == CLS_I) emit(PZK_F_FROM_I, r, id);
+    else if (c == CLS_Z) emit(PZK_F_FROM_N, r, id, 0, PZK_FLAG_ZSRC);
     else emit(PZK_F_FROM_N, r, id);
     v_convF[id] = r;
     return r;
@@ -409,11 +420,91 @@ struct Compiler::Impl {
     uint32_t r = new_value(CLS_N);
     if (c == CLS_U) emit(PZK_N_FROM_U, r, id);
     else if (c == CLS_F) emit(PZK_N_FROM_F, r, id);
+    else if (c == CLS_Z) emit(PZK_N_FROM_F, r, id, 0, PZK_FLAG_ZSRC);
     else { uint32_t f = to_F(s); emit(PZK_N_FROM_F, r, f); }
     v_convN[id] = r;
     return r;
   }
   SVal sv(uint32_t id) { return SVal::ssa(id); }
+
+  // ================================================================== Z class: exact wide integers
+  // A value is "integral" when the compiler knows it as an integer v (not just a residue): narrow values, Z values
+  // and constants of small magnitude.  bits: |v| < 2^bits; neg: v may be negative.
+  static const int ZMAX = 250;
+  bool int_bits(const SVal& s, int& bits, bool& neg) {
+    if (s.kind == 0) {
+      int bl = s.c.bitlen();
+      if (bl <= ZMAX) { bits = bl; neg = false; return true; }
+      U256 n = sub(FR_P, s.c);
+      if (n.bitlen() <= ZMAX) { bits = n.bitlen(); neg = true; return true; }
+      return false;
+    }
+    if (s.kind != 1) return false;
+    int c = v_cls[s.id];
+    if (c == CLS_U || c == CLS_I) {
+      i128 a = v_lo[s.id] < 0 ? -v_lo[s.id] : v_lo[s.id], b = v_hi[s.id] < 0 ? -v_hi[s.id] : v_hi[s.id];
+      bits = bitlen128(a > b ? a : b); neg = v_lo[s.id] < 0;
+      return true;
+    }
+    if (c == CLS_Z) { bits = v_zb[s.id]; neg = v_zneg[s.id] != 0; return true; }
+    return false;
+  }
+  // two's complement 256-bit pattern of a constant of small magnitude (as the field represents it)
+  U256 z_pattern(const U256& c) {
+    if (c.bitlen() <= ZMAX) return c;
+    U256 n = sub(FR_P, c);          // c = -n
+    U256 zero;
+    return sub(zero, n);            // 2^256 - n
+  }
+  uint32_t to_Z(const SVal& s) {
+    if (s.kind == 0) {
+      auto it = constZ.find(s.c);
+      if (it != constZ.end()) return it->second;
+      uint32_t id = new_value(CLS_Z);
+      int b; bool ng; int_bits(s, b, ng);
+      v_zb[id] = (uint16_t)b; v_zneg[id] = ng;
+      emit(PZK_Z_CONST, id, pool_plain(z_pattern(s.c)));
+      v_const[id] = 1; const_of[id] = s.c; constZ[s.c] = id;
+      return id;
+    }
+    uint32_t id = s.id;
+    int c = v_cls[id];
+    if (c == CLS_Z) return id;
+    if (v_convZ[id]) return v_convZ[id];
+    uint32_t r = new_value(CLS_Z);
+    int b; bool ng; int_bits(s, b, ng);
+    v_zb[r] = (uint16_t)b; v_zneg[r] = ng;
+    emit(c == CLS_U ? PZK_Z_FROM_U : PZK_Z_FROM_I, r, id);
+    v_convZ[id] = r;
+    stats->z_ops++;
+    return r;
+  }
+  SVal emit_z(int op, const SVal& a, const SVal& b, int rbits, bool rneg) {
+    int ba = 0, bb = 0; bool na = false, nb = false;
+    int_bits(a, ba, na); int_bits(b, bb, nb);
+    uint32_t ia = to_Z(a);
+    uint32_t id;
+    int imm = 0;
+    if (op == O_MUL && !na && !nb) {
+      int la = (ba + 31) / 32, lb = (bb + 31) / 32;
+      if (la < 1) la = 1;
+      if (lb < 1) lb = 1;
+      if (la <= 8 && lb <= 8 && la + lb <= 8) imm = la | (lb << 4);
+    }
+    const int opc = op == O_ADD ? PZK_Z_ADD : op == O_SUB ? PZK_Z_SUB : PZK_Z_MUL;
+    if (b.kind == 0) {
+      uint32_t pi = pool_plain(z_pattern(b.c));
+      id = new_value(CLS_Z);
+      emit(opc, id, ia, pi, PZK_FLAG_B_POOL, imm);
+    } else {
+      uint32_t ib = to_Z(b);
+      id = new_value(CLS_Z);
+      emit(opc, id, ia, ib, 0, imm);
+    }
+    v_zb[id] = (uint16_t)rbits; v_zneg[id] = rneg;
+    if (op == O_MUL) stats->z_mul++; else stats->z_ops++;
+    return sv(id);
+  }
 
   // ================================================================== tables
   bool table_of(const SVal& s, Table& t, bool root_only) {
@@ -526,6 +617,8 @@ struct Compiler::Impl {
     if (x == y) return true;
     if (x < v_convF.size() && v_convF[x] && v_convF[x] == y) return true;
     if (y < v_convF.size() && v_convF[y] && v_convF[y] == x) return true;
+    if (x < v_convZ.size() && v_convZ[x] && v_convZ[x] == y) return true;
+    if (y < v_convZ.size() && v_convZ[y] && v_convZ[y] == x) return true;
     return false;
   }
   bool try_inverse_product(const SVal& p, const SVal& q, SVal& out, const Stmt* at) {
@@ -688,6 +781,19 @@ struct Compiler::Impl {
             if (cls >= 0) {
               if ((op == O_ADD || op == O_MUL) && a.kind == 0) return emit_u(op == O_ADD ? PZK_U_ADD : PZK_U_MUL, b, a, cls, lo, hi);
               return emit_u(op == O_ADD ? PZK_U_ADD : op == O_SUB ? PZK_U_SUB : PZK_U_MUL, a, b, cls, lo, hi);
+            }
+          }
+        }
+        if (opt.zclass) {
+          // both operands are integers of bounded magnitude and so is the result: exact integer arithmetic in the Z
+          // class (sound in the field because |result| < 2^250 < p / 2: the integer determines the residue)
+          int ba, bb; bool na, nb;
+          if (int_bits(a, ba, na) && int_bits(b, bb, nb)) {
+            int rb = op == O_MUL ? ba + bb : (ba > bb ? ba : bb) + 1;
+            bool rn = op == O_SUB ? true : (na || nb);
+            if (rb <= ZMAX) {
+              if ((op == O_ADD || op == O_MUL) && a.kind == 0) return emit_z(op, b, a, rb, rn);
+              return emit_z(op, a, b, rb, rn);
             }
           }
         }
@@ -2024,11 +2130,22 @@ struct Compiler::Impl {
         d.k = (uint8_t)(d.k + r);
         return true;
       }
-      case PZK_U_ADD: case PZK_F_ADD: {
+      case PZK_U_ADD: case PZK_F_ADD: case PZK_Z_ADD: {
         if (o.flags & (PZK_FLAG_B_IMM | PZK_FLAG_B_POOL)) return false;
         ViewD x, y;
         if (!src_view(o.a, x) || !src_view(o.b, y)) return false;
-        return view_merge(x, y, o.opc == PZK_U_ADD ? 64 : 253, d);
+        return view_merge(x, y, o.opc == PZK_U_ADD ? 64 : (o.opc == PZK_Z_ADD ? 250 : 253), d);
+      }
+      case PZK_Z_MUL: {
+        if (!(o.flags & PZK_FLAG_B_POOL)) {
+          if (o.a == o.b && src_view(o.a, d)) return d.n == 1 && d.k == 0;
+          return false;
+        }
+        c = fpool[o.b];   // raw pattern: a power of two is non-negative
+        if ((c.w[3] >> 63) || !pow2_of(c, r) || !src_view(o.a, d)) return false;
+        if (d.k + d.n + r > 250) return false;
+        d.k = (uint8_t)(d.k + r);
+        return true;
       }
       case PZK_F_MUL: {
         if (!(o.flags & PZK_FLAG_B_POOL)) {
@@ -2051,7 +2168,7 @@ struct Compiler::Impl {
       case PZK_N_LOW:
         if (!src_view(o.a, d)) return false;
         return view_window(d, 0, 64);
-      case PZK_N_FROM_U: case PZK_F_FROM_U: return src_view(o.a, d);
+      case PZK_N_FROM_U: case PZK_F_FROM_U: case PZK_Z_FROM_U: return src_view(o.a, d);
       case PZK_F_FROM_N: case PZK_N_FROM_F:
         if (!vw[o.a].base) return false;  // only views pass through; a real F value is the base of its own bits
         d = vw[o.a];
@@ -2122,7 +2239,8 @@ struct Compiler::Impl {
         case PZK_U_AND: case PZK_U_SHR: case PZK_U_SHL: case PZK_N_SHR: return (o.flags & PZK_FLAG_B_IMM) != 0;
         case PZK_U_MUL: { U256 c; int r; return const_operand(o, c) && pow2_of(c, r); }
         case PZK_F_MUL: { int r; return (o.flags & PZK_FLAG_B_POOL) && pow2_of(fr_from_mont(fpool[o.b]), r); }
-        case PZK_N_BIT: case PZK_N_LOW: case PZK_N_FROM_U: case PZK_F_FROM_U: return true;
+        case PZK_Z_MUL: { int r; return (o.flags & PZK_FLAG_B_POOL) && !(fpool[o.b].w[3] >> 63) && pow2_of(fpool[o.b], r); }
+        case PZK_N_BIT: case PZK_N_LOW: case PZK_N_FROM_U: case PZK_F_FROM_U: case PZK_Z_FROM_U: return true;
       }
       return false;
     };
@@ -2221,6 +2339,9 @@ struct Compiler::Impl {
         else extract(PZK_U_EXTRACT, v);
       } else if (cls == CLS_N) {
         if (!nbase && d.s == 0 && d.k == 0 && d.n >= bw) { o.opc = PZK_N_FROM_U; push(o); }
+        else extract(PZK_N_EXTRACT, v);
+      } else if (cls == CLS_Z) {  // a non-negative plain integer is its own two's complement pattern
+        if (!nbase && d.s == 0 && d.k == 0 && d.n >= bw) { o.opc = PZK_Z_FROM_U; push(o); }
         else extract(PZK_N_EXTRACT, v);
       } else {  // CLS_F: Montgomery form of the integer
         if (!nbase && d.s == 0 && d.k == 0 && d.n >= bw) { o.opc = PZK_F_FROM_U; push(o); }
@@ -2382,7 +2503,7 @@ struct Compiler::Impl {
             o.a = real_of(o.a);
             if (!(o.flags & (PZK_FLAG_B_IMM | PZK_FLAG_B_POOL))) {
               switch (o.opc) {
-                case PZK_F_NEG: case PZK_F_INV: case PZK_F_FROM_U: case PZK_F_FROM_I: case PZK_N_FROM_F:
+                case PZK_F_NEG: case PZK_F_INV: case PZK_F_FROM_U: case PZK_F_FROM_I: case PZK_N_FROM_F: case PZK_Z_FROM_U: case PZK_Z_FROM_I:
                 case PZK_F_FROM_N: case PZK_N_FROM_U: case PZK_N_LOW: case PZK_N_FITS: break;
                 default: o.b = real_of(o.b);
               }
@@ -2454,7 +2575,7 @@ void Compiler::Impl::backend() {
   // ---- operand enumeration helper
   std::function<void(const OpRec&, const std::function<void(uint32_t)>&)> for_operands = [&](const OpRec& o, const std::function<void(uint32_t)>& f) {
     switch (o.opc) {
-      case PZK_NOP: case PZK_U_CONST: case PZK_F_CONST: case PZK_IN_U: case PZK_IN_F: return;
+      case PZK_NOP: case PZK_U_CONST: case PZK_F_CONST: case PZK_Z_CONST: case PZK_IN_U: case PZK_IN_F: return;
       case PZK_BIGDIV: case PZK_MODINV: case PZK_BJJ_MUL8: {
         uint32_t op0, nop, def0, ndef; macro_layout(o, op0, nop, def0, ndef);
         for (uint32_t i = 0; i < nop; i++) f(list_pool[op0 + i]);
@@ -2474,7 +2595,7 @@ void Compiler::Impl::backend() {
         f(o.a);
         if (!(o.flags & (PZK_FLAG_B_IMM | PZK_FLAG_B_POOL))) {
           switch (o.opc) {  // unary ops have no b
-            case PZK_F_NEG: case PZK_F_INV: case PZK_F_FROM_U: case PZK_F_FROM_I: case PZK_N_FROM_F:
+            case PZK_F_NEG: case PZK_F_INV: case PZK_F_FROM_U: case PZK_F_FROM_I: case PZK_N_FROM_F: case PZK_Z_FROM_U: case PZK_Z_FROM_I:
             case PZK_F_FROM_N: case PZK_N_FROM_U: case PZK_N_LOW: case PZK_N_FITS: break;
             default: f(o.b);
           }
@@ -2570,6 +2691,7 @@ void Compiler::Impl::backend() {
         return true;
       }
       if (o.opc == PZK_F_CONST) { out = fr_from_mont(fpool[o.a]); return true; }
+      if (o.opc == PZK_Z_CONST) { out = z_field(fpool[o.a]); return true; }
       return false;
     };
     auto prove_by_tables = [&](const std::vector<MT>* parts) -> bool {
@@ -2663,19 +2785,20 @@ void Compiler::Impl::backend() {
         lin.erase(pick);
         const bool imm = (o.flags & PZK_FLAG_B_IMM) != 0, pool = (o.flags & PZK_FLAG_B_POOL) != 0;
         switch (o.opc) {
-          case PZK_U_ADD: case PZK_U_SUB: case PZK_F_ADD: case PZK_F_SUB: {
-            const bool sub_ = (o.opc == PZK_U_SUB || o.opc == PZK_F_SUB);
+          case PZK_U_ADD: case PZK_U_SUB: case PZK_F_ADD: case PZK_F_SUB: case PZK_Z_ADD: case PZK_Z_SUB: {
+            const bool sub_ = (o.opc == PZK_U_SUB || o.opc == PZK_F_SUB || o.opc == PZK_Z_SUB);
+            const bool zop = (o.opc == PZK_Z_ADD || o.opc == PZK_Z_SUB);
             add(o.a, c);
             U256 cb = sub_ ? fr_neg(c) : c;
             if (imm) add(0xFFFFFFFFu, fr_mul(cb, U256((uint64_t)o.b)));
-            else if (pool) add(0xFFFFFFFFu, fr_mul(cb, fr_from_mont(fpool[o.b])));
+            else if (pool) add(0xFFFFFFFFu, fr_mul(cb, zop ? z_field(fpool[o.b]) : fr_from_mont(fpool[o.b])));
             else add(o.b, cb);
             break;
           }
-          case PZK_U_MUL: case PZK_F_MUL: {
+          case PZK_U_MUL: case PZK_F_MUL: case PZK_Z_MUL: {
             U256 k;
             if (imm) { add(o.a, fr_mul(c, U256((uint64_t)o.b))); break; }
-            if (pool) { add(o.a, fr_mul(c, fr_from_mont(fpool[o.b]))); break; }
+            if (pool) { add(o.a, fr_mul(c, o.opc == PZK_Z_MUL ? z_field(fpool[o.b]) : fr_from_mont(fpool[o.b]))); break; }
             if (const_of(o.b, k)) { add(o.a, fr_mul(c, k)); break; }
             if (const_of(o.a, k)) { add(o.b, fr_mul(c, k)); break; }
             // a genuine product: it must be the row's own A * B, with exactly the opposite coefficient
@@ -2686,7 +2809,8 @@ void Compiler::Impl::backend() {
             break;
           }
           case PZK_F_NEG: add(o.a, fr_neg(c)); break;
-          case PZK_F_FROM_U: case PZK_F_FROM_I: add(o.a, c); break;
+          case PZK_F_FROM_U: case PZK_F_FROM_I: case PZK_Z_FROM_U: case PZK_Z_FROM_I: add(o.a, c); break;
+          case PZK_F_FROM_N: if (o.flags & PZK_FLAG_ZSRC) { add(o.a, c); break; } return false;
           default: return false;
         }
       }
@@ -2711,7 +2835,7 @@ void Compiler::Impl::backend() {
         if (const_of(val, k)) { konst = fr_add(konst, fr_mul(c, k)); return true; }
         ViewD d;
         if (!src_view(val, d)) {
-          if (v_cls[val] != CLS_F || !v_convN[val]) return false;
+          if ((v_cls[val] != CLS_F && v_cls[val] != CLS_Z) || !v_convN[val]) return false;
           uint32_t nf = v_convN[val];
           if (v_def[nf] >= nops || !keep[v_def[nf]] || ops[v_def[nf]].opc != PZK_N_FROM_F || ops[v_def[nf]].dst != nf) return false;
           d.base = nf; d.s = 0; d.n = 254; d.k = 0;
@@ -3005,7 +3129,7 @@ void Compiler::Impl::backend() {
     if (sig == 0xFFFFFFFFu) return PZK_REF_ONE;
     uint32_t v = sig_val[sig];
     if (!v) return PZK_REF_ZERO;
-    uint32_t cls = v_cls[v] == CLS_U ? 0u : (v_cls[v] == CLS_I ? 1u : 2u);
+    uint32_t cls = v_cls[v] == CLS_U ? 0u : (v_cls[v] == CLS_I ? 1u : (v_cls[v] == CLS_Z ? 3u : 2u));
     return (cls << 30) | v_slot[v];
   };
   std::unordered_map<uint64_t, uint32_t> icoef_off;  // int64 coefficient -> list offset
@@ -3083,7 +3207,7 @@ void Compiler::Impl::backend() {
       out_ops.push_back(raw);
     }
     if (is_i64) n_i64_rows++; else if (is_int) n_int_rows++; else n_field_rows++;
-    for (auto& t : ts) if (t.ref < PZK_REF_ONE_LIST) check_bytes += (PZK_REF_CLS(t.ref) == 2) ? 32 : 8;
+    for (auto& t : ts) if (t.ref < PZK_REF_ONE_LIST) check_bytes += (PZK_REF_CLS(t.ref) >= 2) ? 32 : 8;
   };
   out_list = list_pool;
   out_ops.clear();
@@ -3220,7 +3344,7 @@ void Compiler::Impl::backend() {
     return slot_of(v);
   };
   auto tref = [&](uint32_t v) -> uint32_t {
-    uint32_t cls = v_cls[v] == CLS_U ? 0u : (v_cls[v] == CLS_I ? 1u : 2u);
+    uint32_t cls = v_cls[v] == CLS_U ? 0u : (v_cls[v] == CLS_I ? 1u : (v_cls[v] == CLS_Z ? 3u : 2u));
     if (cell_of[v] >= 0) { cache_hits++; return (cls << 30) | PZK_TERM_CELL | (uint32_t)cell_of[v]; }
     cache_miss++;
     needs_global[v] = 1;
@@ -3253,7 +3377,7 @@ void Compiler::Impl::backend() {
       bool has_dst = false;
       switch (o.opc) {
         case PZK_NOP: break;
-        case PZK_U_CONST: case PZK_F_CONST: case PZK_IN_U: case PZK_IN_F: has_dst = true; break;
+        case PZK_U_CONST: case PZK_F_CONST: case PZK_Z_CONST: case PZK_IN_U: case PZK_IN_F: has_dst = true; break;
         case PZK_ASSERT_NZ: r.a = opnd(o.a); break;
         case PZK_BIGDIV: case PZK_MODINV: case PZK_BJJ_MUL8: {
           uint32_t op0, nop, def0, ndef; macro_layout(o, op0, nop, def0, ndef);
@@ -3267,7 +3391,7 @@ void Compiler::Impl::backend() {
           has_dst = true; r.a = opnd(o.a);
           if (!(o.flags & (PZK_FLAG_B_IMM | PZK_FLAG_B_POOL))) {
             switch (o.opc) {
-              case PZK_F_NEG: case PZK_F_INV: case PZK_F_FROM_U: case PZK_F_FROM_I: case PZK_N_FROM_F:
+              case PZK_F_NEG: case PZK_F_INV: case PZK_F_FROM_U: case PZK_F_FROM_I: case PZK_N_FROM_F: case PZK_Z_FROM_U: case PZK_Z_FROM_I:
               case PZK_F_FROM_N: case PZK_N_FROM_U: case PZK_N_LOW: case PZK_N_FITS: r.b = 0; break;
               default: r.b = opnd(o.b);
             }
@@ -3337,7 +3461,7 @@ void Compiler::Impl::backend() {
       } else {
         uint32_t cv = canon(v);
         uint32_t cls = v_cls[cv] == CLS_U ? 0u : (v_cls[cv] == CLS_I ? 1u : 2u);
-        e.ref = (cls << 30) | slot_of(cv);
+        e.ref = (cls << 30) | (v_cls[cv] == CLS_Z ? PZK_REF_Z : 0u) | slot_of(cv);
       }
       by_seg[sig_seg[sig]].push_back(e);
     }
@@ -3388,7 +3512,7 @@ void Compiler::Impl::build_meta() {
        ",\"n_prv_in\":" + std::to_string(n_prv_in);
   s += ",\"stats\":{\"u_ops\":" + std::to_string(stats->u_ops) + ",\"f_mul\":" + std::to_string(stats->f_mul) +
        ",\"f_inv\":" + std::to_string(stats->f_inv) + ",\"f_inv_real\":" + std::to_string(stats->f_inv_real) + ",\"f_other\":" + std::to_string(stats->f_other) +
-       ",\"bigdiv\":" + std::to_string(stats->bigdiv) + ",\"modinv\":" + std::to_string(stats->modinv) + ",\"lut\":" + std::to_string(stats->lut) +
+       ",\"bigdiv\":" + std::to_string(stats->bigdiv) + ",\"modinv\":" + std::to_string(stats->modinv) + ",\"z_ops\":" + std::to_string(stats->z_ops) + ",\"z_mul\":" + std::to_string(stats->z_mul) + ",\"lut\":" + std::to_string(stats->lut) +
        ",\"op_records\":" + std::to_string(out_ops.size()) + ",\"segments\":" + std::to_string(segs.size()) +
        ",\"static_rows\":" + std::to_string(n_static_rows) + ",\"def_rows\":" + std::to_string(n_def_rows) + ",\"table_rows\":" + std::to_string(n_table_rows) + ",\"symbolic_rows\":" + std::to_string(n_symbolic_rows) + ",\"view_rows\":" + std::to_string(n_view_rows) + ",\"range_rows\":" + std::to_string(n_range_rows) + ",\"vlut\":" + std::to_string(n_vlut) + ",\"vlut_lanes\":" + std::to_string(n_vlut_lanes) + ",\"view_signals\":" + std::to_string(n_view_sigs) + ",\"tabview_signals\":" + std::to_string(n_tabview_sigs) + ",\"extracts\":" + std::to_string(n_extracts) + ",\"fused_shladd\":" + std::to_string(n_fused) + ",\"i64_rows\":" + std::to_string(n_i64_rows) +
        ",\"int_rows\":" + std::to_string(n_int_rows) + ",\"field_rows\":" + std::to_string(n_field_rows) +

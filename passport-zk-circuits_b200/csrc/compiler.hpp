@@ -104,7 +104,7 @@ struct ViewD {
   uint8_t s = 0, n = 0, k = 0;
 };
 
-enum { CLS_U = 0, CLS_I = 1, CLS_F = 2, CLS_N = 3 };
+enum { CLS_U = 0, CLS_I = 1, CLS_F = 2, CLS_N = 3, CLS_Z = 4 };
 
 struct CompileOptions {
   std::map<std::string, int> input_bits;  // main input name -> declared width (bits)
@@ -118,11 +118,12 @@ struct CompileOptions {
   bool def_rows_static = false;  // discharge the rows of `x <== e` (they hold by construction) at compile time
   bool views = true;     // bit-field views + bit-view row proofs (Num2Bits / GetLastNBits / running sums cost no ops)
   bool vectorize = true; // pack one-bit truth-table ops over rotated words into V_LUT records (needs views)
+  bool zclass = true;    // exact wide integers (limb products, Karatsuba sums) as Z-class integer ops instead of Fr ops
 };
 
 struct CompileStats {
   uint64_t n_signals = 0, n_constraints = 0, n_ops = 0, n_values = 0;
-  uint64_t u_ops = 0, f_mul = 0, f_inv = 0, f_inv_real = 0, f_other = 0, bigdiv = 0, lut = 0, modinv = 0, bjj = 0;
+  uint64_t u_ops = 0, f_mul = 0, f_inv = 0, f_inv_real = 0, f_other = 0, bigdiv = 0, lut = 0, modinv = 0, bjj = 0, z_ops = 0, z_mul = 0;
   uint32_t n_u_slots = 0, n_f_slots = 0, n_segments = 0;
   double seconds = 0;
 };

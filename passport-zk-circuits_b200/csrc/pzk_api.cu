@@ -243,7 +243,7 @@ static void build_digest_program(pzk_circuit* c, std::vector<DigRec>& recs, std:
         } else if (n_ != 0 && s_ < width) { r.type_nbits = DIG_GENERIC; r.slot = 0; r.a = (uint32_t)e; r.b = cw; recs.push_back(r); }
         continue;
       }
-      r.type_nbits = cls == 0 ? DIG_PLAIN_U : cls == 1 ? DIG_PLAIN_I : DIG_PLAIN_F;
+      r.type_nbits = cls == 0 ? DIG_PLAIN_U : cls == 1 ? DIG_PLAIN_I : ((x.ref & PZK_REF_Z) ? DIG_PLAIN_Z : DIG_PLAIN_F);
       recs.push_back(r);
     }
     for (auto& kv : words) {

@@ -431,6 +431,17 @@ __device__ __forceinline__ void lin_field(const StreamCoefs sc, const uint2* ter
       continue;
     }
     const u32 cls = PZK_REF_CLS(ref);
+    if (cls == 3) {
+      // Z wire: |v| * (c R^2) -> one Montgomery product, sign applied after
+      u64 z[4], m[4], c[4], r[4];
+      ldFo(Fl, L, cells, 0, (ref & PZK_TERM_CELL) ? (PZK_OPERAND_CELL | (ref & 0xffffu)) : PZK_REF_SLOT(ref), z);
+      const bool vneg = (long long)z[3] < 0;
+      if (vneg) { const u64 zero[4] = {0, 0, 0, 0}; sub256(m, zero, z); } else { m[0] = z[0]; m[1] = z[1]; m[2] = z[2]; m[3] = z[3]; }
+      ldPool(cbase, ci * 3 + 2, c);  // c * R^2
+      fr_mul(r, c, m);
+      if (vneg) fr_sub(acc, acc, r); else fr_add(acc, acc, r);
+      continue;
+    }
     if (cls < 2) {
       u64 v = TERM_U(ref);
       const bool vneg = (cls == 1) && ((long long)v < 0);
@@ -523,6 +534,72 @@ __device__ __forceinline__ void field256(u64* r, const u64* v, unsigned s, unsig
     }
   }
   shl256(r, t, k);
+}
+
+// ---- Z class: exact wide integers in 256-bit two's complement (pzk_program.h) -----------------------------
+// canonical residue of a Z value: v < 0 ? p + v : v
+__device__ __forceinline__ void z_canonical(u64* r, const u64* z) {
+  r[0] = z[0]; r[1] = z[1]; r[2] = z[2]; r[3] = z[3];
+  if ((long long)z[3] < 0) { const u64 pp[4] = {P0, P1, P2, P3}; add256(r, r, pp); }
+}
+// Montgomery form of a Z value (|v| < 2^250 < p)
+__device__ __forceinline__ void z_to_mont(u64* r, const u64* z) {
+  const bool neg = (long long)z[3] < 0;
+  u64 m[4] = {z[0], z[1], z[2], z[3]};
+  if (neg) { const u64 zero[4] = {0, 0, 0, 0}; sub256(m, zero, z); }
+  fr_to_mont(r, m);
+  if (neg) fr_neg(r, r);
+}
+// schoolbook LA x LB product of 32-bit limbs (non-negative operands that fit LA / LB limbs, LA + LB <= 8)
+template <int LA, int LB>
+__device__ __forceinline__ void z_mul_nn(u64* r64, const u64* a64, const u64* b64) {
+  u32 a[8], b[8], r[8];
+#pragma unroll
+  for (int i = 0; i < 4; i++) { a[2 * i] = (u32)a64[i]; a[2 * i + 1] = (u32)(a64[i] >> 32); b[2 * i] = (u32)b64[i]; b[2 * i + 1] = (u32)(b64[i] >> 32); }
+#pragma unroll
+  for (int i = 0; i < 8; i++) r[i] = 0;
+#pragma unroll
+  for (int i = 0; i < LA; i++) {
+    u32 carry = 0;
+#pragma unroll
+    for (int j = 0; j < LB; j++) {
+      const u64 t = (u64)a[i] * b[j] + r[i + j] + carry;
+      r[i + j] = (u32)t; carry = (u32)(t >> 32);
+    }
+    r[i + LB] = carry;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) r64[i] = (u64)r[2 * i] | ((u64)r[2 * i + 1] << 32);
+}
+// a * b mod 2^256: exact for two's complement operands whenever the true product fits
+__device__ __noinline__ void z_mul_full(u64* r64, const u64* a64, const u64* b64) {
+  u32 a[8], b[8], r[8];
+#pragma unroll
+  for (int i = 0; i < 4; i++) { a[2 * i] = (u32)a64[i]; a[2 * i + 1] = (u32)(a64[i] >> 32); b[2 * i] = (u32)b64[i]; b[2 * i + 1] = (u32)(b64[i] >> 32); }
+#pragma unroll
+  for (int i = 0; i < 8; i++) r[i] = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    u32 carry = 0;
+#pragma unroll
+    for (int j = 0; j < 8 - i; j++) {
+      const u64 t = (u64)a[i] * b[j] + r[i + j] + carry;
+      r[i + j] = (u32)t; carry = (u32)(t >> 32);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) r64[i] = (u64)r[2 * i] | ((u64)r[2 * i + 1] << 32);
+}
+__device__ __forceinline__ void z_mul(u64* r, const u64* a, const u64* b, u32 imm) {
+  const u32 la = imm & 15u, lb = imm >> 4;
+  if (imm == 0) { z_mul_full(r, a, b); return; }
+  // the common shapes of the big-integer multipliers: 64 x 64, (64 + carry bits) x (64 + carry bits), 128 x 64 ...
+  if (la <= 2 && lb <= 2) z_mul_nn<2, 2>(r, a, b);
+  else if (la <= 3 && lb <= 3) z_mul_nn<3, 3>(r, a, b);
+  else if (la <= 4 && lb <= 4) z_mul_nn<4, 4>(r, a, b);
+  else if (la <= 6 && lb <= 2) z_mul_nn<6, 2>(r, a, b);
+  else if (la <= 2 && lb <= 6) z_mul_nn<2, 6>(r, a, b);
+  else z_mul_full(r, a, b);
 }
 
 __global__ void __launch_bounds__(128, 8) eval_kernel(EvalParams p) {
@@ -677,8 +754,28 @@ __global__ void __launch_bounds__(128, 8) eval_kernel(EvalParams p) {
         break;
       }
       case PZK_F_CSEL: { u64 v[4]; ldPool(fpool, b + (u32)LDO(a), v); STFD(v); break; }
-      case PZK_N_FROM_F: { u64 va[4], r[4]; LDFA(va); fr_from_mont(r, va); STFD(r); break; }
-      case PZK_F_FROM_N: { u64 va[4], r[4]; LDFA(va); reduce_p(va); fr_to_mont(r, va); STFD(r); break; }
+      case PZK_N_FROM_F: {
+        u64 va[4], r[4]; LDFA(va);
+        if (flags & PZK_FLAG_ZSRC) z_canonical(r, va); else fr_from_mont(r, va);
+        STFD(r); break;
+      }
+      case PZK_F_FROM_N: {
+        u64 va[4], r[4]; LDFA(va);
+        if (flags & PZK_FLAG_ZSRC) z_to_mont(r, va); else { reduce_p(va); fr_to_mont(r, va); }
+        STFD(r); break;
+      }
+      case PZK_Z_ADD: case PZK_Z_SUB: case PZK_Z_MUL: {
+        u64 va[4], vb[4], r[4];
+        LDFA(va); LDFB(vb);
+        if (opc == PZK_Z_ADD) add256(r, va, vb);
+        else if (opc == PZK_Z_SUB) sub256(r, va, vb);
+        else z_mul(r, va, vb, imm16);
+        STFD(r);
+        break;
+      }
+      case PZK_Z_FROM_U: { u64 v[4] = {LDO(a), 0, 0, 0}; STFD(v); break; }
+      case PZK_Z_FROM_I: { const u64 x_ = LDO(a); const u64 sx = (u64)((long long)x_ >> 63); u64 v[4] = {x_, sx, sx, sx}; STFD(v); break; }
+      case PZK_Z_CONST: { u64 v[4]; ldPool(fpool, a, v); STFD(v); break; }
       case PZK_N_FROM_U: { u64 v[4] = {LDO(a), 0, 0, 0}; STFD(v); break; }
       case PZK_N_BIT: {
         u64 limb = 0;
@@ -849,7 +946,10 @@ __device__ __forceinline__ void export_value(const ExportParams& p, const uint4 
     u64 t[4] = {0, 0, 0, 0};
     if (ref & PZK_REF_VIEW_N) ldF(Fb, PZK_LANE_BLOCK, slot, t); else t[0] = Ub[(u64)slot * PZK_LANE_BLOCK];
     field256(w, t, s_, n_, k_);
-  } else if (cls == 2) { u64 m[4]; ldF(Fb, PZK_LANE_BLOCK, slot, m); fr_from_mont(w, m); }
+  } else if (cls == 2) {
+    u64 m[4]; ldF(Fb, PZK_LANE_BLOCK, slot, m);
+    if (ref & PZK_REF_Z) z_canonical(w, m); else fr_from_mont(w, m);
+  }
   else {
     const u64 v = Ub[(u64)slot * PZK_LANE_BLOCK];
     if (cls == 1 && (long long)v < 0) { const u64 pp[4] = {P0, P1, P2, P3}; u64 m[4] = {(u64)(-(long long)v), 0, 0, 0}; sub256(w, pp, m); }
@@ -908,7 +1008,7 @@ __host__ __device__ __forceinline__ u32 pzk_digest_weight(u32 wire) {
   return (u32)((z ^ (z >> 31)) >> 32) | 1u;
 }
 
-enum { DIG_WORD_U = 1, DIG_WORD_N = 2, DIG_PLAIN_U = 3, DIG_PLAIN_I = 4, DIG_PLAIN_F = 5, DIG_GENERIC = 6, DIG_CONST = 7 };
+enum { DIG_WORD_U = 1, DIG_WORD_N = 2, DIG_PLAIN_U = 3, DIG_PLAIN_I = 4, DIG_PLAIN_F = 5, DIG_GENERIC = 6, DIG_CONST = 7, DIG_PLAIN_Z = 8 };
 struct DigRec { u32 type_nbits; u32 slot; u32 a; u32 b; };  // type in bits 0..7, nbits in bits 8..31
 #define DIG_STATE_PIECES 28  // accN 4, accNeg 4, accM 10, accP 10 (32-bit pieces, carry-save)
 
@@ -995,6 +1095,13 @@ __global__ void __launch_bounds__(128) digest_kernel(DigestParams p) {
         u64 w[4];
         ldF(Fb, PZK_LANE_BLOCK, rw.y, w);
         mac320(accM, rw.z, w);
+        break;
+      }
+      case DIG_PLAIN_Z: {
+        u64 z[4], w[4];
+        ldF(Fb, PZK_LANE_BLOCK, rw.y, z);
+        z_canonical(w, z);
+        mac320(accP, rw.z, w);
         break;
       }
       case DIG_GENERIC: {

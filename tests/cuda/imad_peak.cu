@@ -28,6 +28,21 @@ __global__ void __launch_bounds__(256) imad_kernel(u32* out, u32 a, u32 b, int i
   if (s == 0x12345678u) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// mad.hi.u32: the other half of every 32 x 32 product in a mad.lo.cc / madc.hi.cc Montgomery chain
+__global__ void __launch_bounds__(256) imad_hi_kernel(u32* out, u32 a, u32 b, int iters) {
+  u32 x[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) x[k] = threadIdx.x + k;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int k = 0; k < 16; k++) asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(x[k]) : "r"(a), "r"(b));
+  }
+  u32 s = 0;
+#pragma unroll
+  for (int k = 0; k < 16; k++) s ^= x[k];
+  if (s == 0x12345678u) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 __global__ void __launch_bounds__(256) imad_wide_kernel(u64* out, u32 a, u32 b, int iters) {
   u64 x[8];
   u32 y[8];
@@ -92,14 +107,15 @@ int main() {
   double ms1 = best_ms([&] { imad_kernel<<<grid, 256>>>((u32*)buf, 0x9e3779b1u, 0x7f4a7c15u, it1); });
   double ms2 = best_ms([&] { imad_wide_kernel<<<grid, 256>>>(buf, 0x9e3779b1u, 0x7f4a7c15u, it2); });
   double ms3 = best_ms([&] { frmul_kernel<<<grid, 128>>>(buf, din, it3); });
+  double ms4 = best_ms([&] { imad_hi_kernel<<<grid, 256>>>((u32*)buf, 0x9e3779b1u, 0x7f4a7c15u, it1); });
   cudaError_t e = cudaDeviceSynchronize();
   double imad = (double)grid * 256 * it1 * 16 / (ms1 * 1e-3);
   double wide = (double)grid * 256 * it2 * 16 / (ms2 * 1e-3);
   double frm = (double)grid * 128 * it3 * 2 / (ms3 * 1e-3);
-  printf("{\"imad_per_s\": %.6e, \"imad_wide_per_s\": %.6e, \"fr_mul_per_s\": %.6e, \"fr_mul_imad_per_s\": %.6e, "
+  printf("{\"imad_hi_per_s\": %.6e, \"imad_per_s\": %.6e, \"imad_wide_per_s\": %.6e, \"fr_mul_per_s\": %.6e, \"fr_mul_imad_per_s\": %.6e, "
          "\"n_sm\": %d, \"sm_clock_mhz_attr\": %.1f, \"imad_per_clk_per_sm\": %.2f, \"imad_wide_per_clk_per_sm\": %.2f, "
          "\"ms\": [%.3f, %.3f, %.3f], \"cuda\": \"%s\"}\n",
-         imad, wide, frm, frm * 136.0, n_sm, clk_khz / 1e3, imad / n_sm / (clk_khz * 1e3), wide / n_sm / (clk_khz * 1e3),
+         (double)grid * 256 * it1 * 16 / (ms4 * 1e-3), imad, wide, frm, frm * 136.0, n_sm, clk_khz / 1e3, imad / n_sm / (clk_khz * 1e3), wide / n_sm / (clk_khz * 1e3),
          ms1, ms2, ms3, cudaGetErrorString(e));
   return e != cudaSuccess;
 }
