@@ -22,6 +22,7 @@ section 8(d).
 from __future__ import annotations
 
 import hashlib
+import math
 import random
 from dataclasses import dataclass
 
@@ -93,7 +94,7 @@ def _is_probable_prime(n, rng, rounds=24):
 def _gen_prime(bits, rng, e=65537):
     while True:
         p = rng.getrandbits(bits) | (3 << (bits - 2)) | 1
-        if p % e == 1:
+        if math.gcd(p - 1, e) != 1:     # e need not be prime (37187 = 41 * 907, SIGNATURE_TYPE 4)
             continue
         if _is_probable_prime(p, rng):
             return p
