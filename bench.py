@@ -368,8 +368,9 @@ def main():
                     "algorithmic_imad_per_witness": hist["algorithmic_imad"],
                     "fr_products_per_witness": hist["fr_products"], "narrow_records_per_witness": hist["narrow_records"],
                     "definition": "136 IMAD per Fr product (explicit F_MUL records + products inside the hint intrinsics + 1 per "
-                                  "quadratic field row) + 1 per narrow record; Montgomery conversions, address arithmetic and the "
-                                  "digest are NOT counted",
+                                  "quadratic field row) + 4 la lb per Z-class integer product of la x lb 64-bit limbs + 1 per narrow "
+                                  "record; Montgomery conversions, address arithmetic and the digest are NOT counted",
+                    "z_mul_records_per_witness": hist["z_mul_records"], "z_mul_imad_per_witness": hist["z_mul_imad"],
                     "imad_per_launch": imad_per_launch, "avg_launch_ms": 1e3 * avg_launch_s, "launches": eval_launches,
                     "share_of_step": eval_ms / max(1e-9, prof["run"][0]),
                     "fr_mul_microbenchmark": {"fr_mul_per_s": ipk.get("fr_mul_per_s"),

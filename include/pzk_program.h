@@ -132,7 +132,7 @@ enum PzkOpcode {
   PZK_Z_ADD = 64,    /* dst = a + b                (b may be a pool constant: PZK_FLAG_B_POOL, raw two's complement) */
   PZK_Z_SUB = 65,
   PZK_Z_MUL = 66,    /* dst = a * b mod 2^256; imm16 = la | lb << 4: when non-zero both operands are non-negative and
-                        fit la / lb 32-bit limbs (schoolbook la x lb instead of the truncated 8 x 8)            */
+                        fit la / lb 64-bit limbs with la + lb <= 4 (schoolbook la x lb instead of the truncated 4 x 4) */
   PZK_Z_FROM_U = 67, /* dst(Z) = a(U)                                                                          */
   PZK_Z_FROM_I = 68, /* dst(Z) = a(I), sign extended                                                            */
   PZK_Z_CONST = 69,  /* dst(Z) = fpool[a] (raw two's complement)                                                */

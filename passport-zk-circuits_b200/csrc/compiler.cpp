@@ -486,10 +486,10 @@ struct Compiler::Impl {
     uint32_t id;
     int imm = 0;
     if (op == O_MUL && !na && !nb) {
-      int la = (ba + 31) / 32, lb = (bb + 31) / 32;
+      int la = (ba + 63) / 64, lb = (bb + 63) / 64;   // 64-bit limbs the (non-negative) operands fit
       if (la < 1) la = 1;
       if (lb < 1) lb = 1;
-      if (la <= 8 && lb <= 8 && la + lb <= 8) imm = la | (lb << 4);
+      if (la + lb <= 4) imm = la | (lb << 4);
     }
     const int opc = op == O_ADD ? PZK_Z_ADD : op == O_SUB ? PZK_Z_SUB : PZK_Z_MUL;
     if (b.kind == 0) {
@@ -3037,12 +3037,16 @@ void Compiler::Impl::backend() {
   {
     uint64_t rec = 0; uint32_t seg = 0;
     size_t rp = 0;
+    bool after_solo = false;
     for (size_t i = 0; i < nops; i++) {
       if (!keep[i]) continue;
       uint64_t need = ((ops[i].flags & PZK_FLAG_EXT) ? 2 : 1) + ((ops[i].opc == PZK_V_LUT && (ops[i].flags & PZK_FLAG_W64)) ? 1 : 0);
       size_t q = rp;
       while (q < nrows && row_trigger[row_order[q]] == i) { if (!row_static[row_order[q]]) need += row_recs[row_order[q]]; q++; }
-      if (rec && rec + need > opt.seg_ops) { seg++; rec = 0; }
+      // the BabyJubjub ladder gets a segment of its own: the runtime runs it as a dedicated kernel
+      const bool solo = ops[i].opc == PZK_BJJ_MUL8 && need == 1;
+      if (rec && (rec + need > opt.seg_ops || solo || after_solo)) { seg++; rec = 0; }
+      after_solo = solo;
       rec += need;
       op_seg[i] = seg;
       rp = q;

@@ -608,7 +608,16 @@ static int run_batch(pzk_circuit* c, const RunOpts& o) {
     for (uint32_t s = 0; s < c->h.n_segments; s++) {
       const PzkSegment& sg = c->segs[s];
       cudaEvent_t ea, eb;
-      if (sg.n_ops) {
+      if (sg.n_ops == 1 && c->ops[sg.op_off].opc == PZK_BJJ_MUL8) {
+        // the BabyJubjub ladder alone in its segment: the dedicated kernel (pzk_kernels.cuh)
+        BjjParams bp;
+        bp.list = c->d_list + c->ops[sg.op_off].a; bp.fpool = c->d_fpool; bp.F = c->d_F; bp.n_lanes = n;
+        bp.n_f_slots = c->h.n_f_slots; bp.status = c->d_status + base;
+        prof_begin(c, 0, ea, eb);
+        bjj_kernel<<<grid, 128, 0, c->stream>>>(bp);
+        prof_end(c, 0, ea, eb);
+        if (c->prof) c->pending_seg.push_back((int)s);
+      } else if (sg.n_ops) {
         EvalParams p;
         p.ops = c->d_ops + sg.op_off; p.n_rec = sg.n_ops; p.U = c->d_U; p.F = c->d_F; p.L = L; p.n_lanes = n;
         p.fpool = c->d_fpool; p.list = c->d_list;

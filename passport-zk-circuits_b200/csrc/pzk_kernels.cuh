@@ -550,59 +550,51 @@ __device__ __forceinline__ void z_to_mont(u64* r, const u64* z) {
   fr_to_mont(r, m);
   if (neg) fr_neg(r, r);
 }
-// schoolbook LA x LB product of 32-bit limbs (non-negative operands that fit LA / LB limbs, LA + LB <= 8)
-template <int LA, int LB>
-__device__ __forceinline__ void z_mul_nn(u64* r64, const u64* a64, const u64* b64) {
-  u32 a[8], b[8], r[8];
-#pragma unroll
-  for (int i = 0; i < 4; i++) { a[2 * i] = (u32)a64[i]; a[2 * i + 1] = (u32)(a64[i] >> 32); b[2 * i] = (u32)b64[i]; b[2 * i + 1] = (u32)(b64[i] >> 32); }
-#pragma unroll
-  for (int i = 0; i < 8; i++) r[i] = 0;
-#pragma unroll
-  for (int i = 0; i < LA; i++) {
-    u32 carry = 0;
-#pragma unroll
-    for (int j = 0; j < LB; j++) {
-      const u64 t = (u64)a[i] * b[j] + r[i + j] + carry;
-      r[i + j] = (u32)t; carry = (u32)(t >> 32);
-    }
-    r[i + LB] = carry;
-  }
-#pragma unroll
-  for (int i = 0; i < 4; i++) r64[i] = (u64)r[2 * i] | ((u64)r[2 * i + 1] << 32);
-}
-// a * b mod 2^256: exact for two's complement operands whenever the true product fits
-__device__ __noinline__ void z_mul_full(u64* r64, const u64* a64, const u64* b64) {
-  u32 a[8], b[8], r[8];
-#pragma unroll
-  for (int i = 0; i < 4; i++) { a[2 * i] = (u32)a64[i]; a[2 * i + 1] = (u32)(a64[i] >> 32); b[2 * i] = (u32)b64[i]; b[2 * i + 1] = (u32)(b64[i] >> 32); }
-#pragma unroll
-  for (int i = 0; i < 8; i++) r[i] = 0;
-#pragma unroll
-  for (int i = 0; i < 8; i++) {
-    u32 carry = 0;
-#pragma unroll
-    for (int j = 0; j < 8 - i; j++) {
-      const u64 t = (u64)a[i] * b[j] + r[i + j] + carry;
-      r[i + j] = (u32)t; carry = (u32)(t >> 32);
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < 4; i++) r64[i] = (u64)r[2 * i] | ((u64)r[2 * i + 1] << 32);
-}
-__device__ __forceinline__ void z_mul(u64* r, const u64* a, const u64* b, u32 imm) {
+// a * b mod 2^256 on 64-bit limbs, everything in registers (no arrays whose address escapes: a __noinline__ helper with
+// pointer arguments demoted the operand arrays of every Z op to local memory - 30 % of the stall samples of the
+// big-integer segments, profiles/README.md).  LA / LB: 64-bit limbs the NON-NEGATIVE operands fit (0 = unknown or
+// possibly negative: truncated 4 x 4, exact in two's complement whenever the true product fits).
+#define Z_MAC(acc_lo, acc_hi, carry, x, y)                         \
+  do {                                                             \
+    const u64 pl__ = (x) * (y), ph__ = __umul64hi((x), (y));       \
+    const u64 s__ = (acc_lo) + pl__;                               \
+    const u64 c__ = s__ < pl__;                                    \
+    (acc_lo) = s__;                                                \
+    const u64 t__ = (acc_hi) + ph__;                               \
+    const u64 c2__ = t__ < ph__;                                   \
+    const u64 u__ = t__ + c__;                                     \
+    (carry) += c2__ + (u__ < c__);                                 \
+    (acc_hi) = u__;                                                \
+  } while (0)
+__device__ __forceinline__ void z_mul(u64& r0, u64& r1, u64& r2, u64& r3, u64 a0, u64 a1, u64 a2, u64 a3, u64 b0, u64 b1,
+                                      u64 b2, u64 b3, u32 imm) {
   const u32 la = imm & 15u, lb = imm >> 4;
-  if (imm == 0) { z_mul_full(r, a, b); return; }
-  // the common shapes of the big-integer multipliers: 64 x 64, (64 + carry bits) x (64 + carry bits), 128 x 64 ...
-  if (la <= 2 && lb <= 2) z_mul_nn<2, 2>(r, a, b);
-  else if (la <= 3 && lb <= 3) z_mul_nn<3, 3>(r, a, b);
-  else if (la <= 4 && lb <= 4) z_mul_nn<4, 4>(r, a, b);
-  else if (la <= 6 && lb <= 2) z_mul_nn<6, 2>(r, a, b);
-  else if (la <= 2 && lb <= 6) z_mul_nn<2, 6>(r, a, b);
-  else z_mul_full(r, a, b);
+  if (la == 1 && lb == 1) {  // 64 x 64: the limb products of the multipliers
+    r0 = a0 * b0; r1 = __umul64hi(a0, b0); r2 = 0; r3 = 0;
+    return;
+  }
+  if (la != 0 && la <= 2 && lb <= 2) {  // (64 + carry bits) x (64 + carry bits): Karatsuba leaves
+    u64 c0 = a0 * b0, c1 = __umul64hi(a0, b0), c2 = 0, c3 = 0, k = 0;
+    Z_MAC(c1, c2, c3, a0, b1);
+    Z_MAC(c1, c2, c3, a1, b0);
+    Z_MAC(c2, c3, k, a1, b1);
+    r0 = c0; r1 = c1; r2 = c2; r3 = c3;
+    return;
+  }
+  // truncated 4 x 4
+  u64 c0 = a0 * b0, c1 = __umul64hi(a0, b0), c2 = 0, c3 = 0, k = 0;
+  Z_MAC(c1, c2, c3, a0, b1);
+  Z_MAC(c1, c2, c3, a1, b0);
+  Z_MAC(c2, c3, k, a0, b2);
+  Z_MAC(c2, c3, k, a1, b1);
+  Z_MAC(c2, c3, k, a2, b0);
+  c3 += a0 * b3 + a1 * b2 + a2 * b1 + a3 * b0;
+  r0 = c0; r1 = c1; r2 = c2; r3 = c3;
 }
 
-__global__ void __launch_bounds__(128, 8) eval_kernel(EvalParams p) {
+// 7 CTAs of 128 lanes per SM (72 registers): measured best of 8 / 7 / 6 / 5 on the round-2 program (284 / 298 / 295 /
+// 280 k witnesses/s): one more warp-quartet of latency hiding is worth less than the spills of a 64-register budget
+__global__ void __launch_bounds__(128, 7) eval_kernel(EvalParams p) {
   extern __shared__ u64 cell_mem[];
   const u64 lane = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   if (lane >= p.n_lanes) return;
@@ -769,7 +761,7 @@ __global__ void __launch_bounds__(128, 8) eval_kernel(EvalParams p) {
         LDFA(va); LDFB(vb);
         if (opc == PZK_Z_ADD) add256(r, va, vb);
         else if (opc == PZK_Z_SUB) sub256(r, va, vb);
-        else z_mul(r, va, vb, imm16);
+        else z_mul(r[0], r[1], r[2], r[3], va[0], va[1], va[2], va[3], vb[0], vb[1], vb[2], vb[3], imm16);
         STFD(r);
         break;
       }
@@ -982,6 +974,96 @@ __global__ void __launch_bounds__(128) export_rows_kernel(ExportParams p) {
     export_value(p, ew, lane, w);
     export_store(p, row_out, ew.x, w);
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// The BabyJubjub ladder as a kernel of its own.  Inside eval_kernel (72 registers, points behind references of
+// __noinline__ helpers) the 8 600 serial Montgomery products of PZK_BJJ_MUL8 ran at IPC 0.2 - 114 ms of a 1 065 ms
+// step for ONE record.  The compiler gives the record a segment of its own; the runtime launches this kernel for it:
+// same algorithm (bjj_mul8_device), everything inlined, the three points in registers, no register cap.
+// ------------------------------------------------------------------------------------------
+struct BjjParams {
+  const u32* list;   // list pool at the record's operand list
+  const u64* fpool;
+  u64* F;
+  u64 n_lanes;
+  u32 n_f_slots;
+  u32* status;
+};
+
+__device__ __forceinline__ void bjj_padd_reg(u64* oX, u64* oY, u64* oZ, const u64* pX, const u64* pY, const u64* pZ,
+                                             const u64* qX, const u64* qY, const u64* qZ, const u64* ca, const u64* cd) {
+  u64 A[4], B[4], C[4], D[4], E[4], F[4], G[4], t[4], u[4];
+  fr_mul(A, pZ, qZ); fr_mul(B, A, A);
+  fr_mul(C, pX, qX); fr_mul(D, pY, qY);
+  fr_mul(E, C, D); fr_mul(E, E, cd);
+  fr_sub(F, B, E); fr_add(G, B, E);
+  fr_add(t, pX, pY); fr_add(u, qX, qY); fr_mul(t, t, u); fr_sub(t, t, C); fr_sub(t, t, D);
+  fr_mul(u, A, F); fr_mul(oX, u, t);
+  fr_mul(t, C, ca); fr_sub(t, D, t);
+  fr_mul(u, A, G); fr_mul(oY, u, t);
+  fr_mul(oZ, F, G);
+}
+
+__global__ void __launch_bounds__(128) bjj_kernel(BjjParams p) {
+  const u64 lane = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (lane >= p.n_lanes) return;
+  const u64 L = PZK_LANE_BLOCK;
+  u64* Fl = p.F + (u64)blockIdx.x * p.n_f_slots * 4 * PZK_LANE_BLOCK + threadIdx.x;
+  const u32* Lst = p.list;
+  const u32 n = Lst[0], nadd = 2 * n - 1;
+  u64 ca[4], cd[4], bx[4], by[4], one[4], sc[4];
+  ldPool(p.fpool, Lst[1], ca); ldPool(p.fpool, Lst[2], cd); ldPool(p.fpool, Lst[3], bx); ldPool(p.fpool, Lst[4], by);
+  { const u64 o1[4] = {1, 0, 0, 0}; fr_to_mont(one, o1); }
+  { u64 m[4]; ldF(Fl, L, Lst[5], m); fr_from_mont(sc, m); }
+  const u32* out = Lst + 6;
+  const u32* scr = out + 2 * nadd;
+  u64 SX[4] = {0, 0, 0, 0}, SY[4] = {0, 0, 0, 0}, SZ[4] = {one[0], one[1], one[2], one[3]};
+  u64 pre[4] = {one[0], one[1], one[2], one[3]};
+  u32 k = 0;
+  for (u32 i = 0; i < n; i++) {
+    u64 DX[4], DY[4], DZ[4];
+    if (i > 0) {
+      bjj_padd_reg(DX, DY, DZ, SX, SY, SZ, SX, SY, SZ, ca, cd);
+      stF(Fl, L, out[2 * k], DX); stF(Fl, L, out[2 * k + 1], DY); stF(Fl, L, scr[2 * k], DZ);
+      fr_mul(pre, pre, DZ); stF(Fl, L, scr[2 * k + 1], pre);
+      k++;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; j++) { DX[j] = DY[j] = 0; DZ[j] = one[j]; }
+    }
+    const u32 bi = n - 1 - i;
+    const bool bit = (sc[bi >> 6] >> (bi & 63)) & 1;
+    u64 QX[4], QY[4], AX[4], AY[4], AZ[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) { QX[j] = bit ? bx[j] : 0; QY[j] = bit ? by[j] : 0; }
+    bjj_padd_reg(AX, AY, AZ, DX, DY, DZ, QX, QY, one, ca, cd);
+    stF(Fl, L, out[2 * k], AX); stF(Fl, L, out[2 * k + 1], AY); stF(Fl, L, scr[2 * k], AZ);
+    fr_mul(pre, pre, AZ); stF(Fl, L, scr[2 * k + 1], pre);
+    k++;
+    // addZeroBabyjub: in1 "zero" -> in2, else in2 "zero" -> in1, else the sum (zero = x coordinate 0)
+    const bool zd = fr_is_zero(DX), zq = !bit;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      SX[j] = zd ? QX[j] : (zq ? DX[j] : AX[j]);
+      SY[j] = zd ? QY[j] : (zq ? DY[j] : AY[j]);
+      SZ[j] = zd ? one[j] : (zq ? DZ[j] : AZ[j]);
+    }
+  }
+  u32 st = fr_is_zero(pre) ? PZK_LANE_HINT : 0;
+  u64 inv[4];
+  fr_inv(inv, pre);
+  for (u32 kk = nadd; kk-- > 0;) {
+    u64 z[4], zi[4], x[4], y[4];
+    ldF(Fl, L, scr[2 * kk], z);
+    if (kk > 0) { u64 pp[4]; ldF(Fl, L, scr[2 * kk - 1], pp); fr_mul(zi, inv, pp); }
+    else { zi[0] = inv[0]; zi[1] = inv[1]; zi[2] = inv[2]; zi[3] = inv[3]; }
+    fr_mul(inv, inv, z);
+    ldF(Fl, L, out[2 * kk], x); ldF(Fl, L, out[2 * kk + 1], y);
+    fr_mul(x, x, zi); fr_mul(y, y, zi);
+    stF(Fl, L, out[2 * kk], x); stF(Fl, L, out[2 * kk + 1], y);
+  }
+  if (st) p.status[lane] |= st;
 }
 
 // ------------------------------------------------------------------------------------------
