@@ -3044,9 +3044,9 @@ void Compiler::Impl::backend() {
       size_t q = rp;
       while (q < nrows && row_trigger[row_order[q]] == i) { if (!row_static[row_order[q]]) need += row_recs[row_order[q]]; q++; }
       // the BabyJubjub ladder gets a segment of its own: the runtime runs it as a dedicated kernel
-      const bool solo = ops[i].opc == PZK_BJJ_MUL8 && need == 1;
-      if (rec && (rec + need > opt.seg_ops || solo || after_solo)) { seg++; rec = 0; }
-      after_solo = solo;
+      const bool solo = ops[i].opc == PZK_BJJ_MUL8;   // first record of its segment (the rows it completes follow it)
+      if (rec && (rec + need > opt.seg_ops || solo)) { seg++; rec = 0; }
+      (void)after_solo;
       rec += need;
       op_seg[i] = seg;
       rp = q;

@@ -608,8 +608,10 @@ static int run_batch(pzk_circuit* c, const RunOpts& o) {
     for (uint32_t s = 0; s < c->h.n_segments; s++) {
       const PzkSegment& sg = c->segs[s];
       cudaEvent_t ea, eb;
-      if (sg.n_ops == 1 && c->ops[sg.op_off].opc == PZK_BJJ_MUL8) {
-        // the BabyJubjub ladder alone in its segment: the dedicated kernel (pzk_kernels.cuh)
+      uint64_t skip = 0;
+      if (sg.n_ops >= 1 && c->ops[sg.op_off].opc == PZK_BJJ_MUL8) {
+        // the BabyJubjub ladder is the first record of its segment: the dedicated kernel (pzk_kernels.cuh), then the
+        // rest of the segment (the rows the ladder completes) in the evaluator
         BjjParams bp;
         bp.list = c->d_list + c->ops[sg.op_off].a; bp.fpool = c->d_fpool; bp.F = c->d_F; bp.n_lanes = n;
         bp.n_f_slots = c->h.n_f_slots; bp.status = c->d_status + base;
@@ -617,9 +619,11 @@ static int run_batch(pzk_circuit* c, const RunOpts& o) {
         bjj_kernel<<<grid, 128, 0, c->stream>>>(bp);
         prof_end(c, 0, ea, eb);
         if (c->prof) c->pending_seg.push_back((int)s);
-      } else if (sg.n_ops) {
+        skip = 1;
+      }
+      if (sg.n_ops > skip) {
         EvalParams p;
-        p.ops = c->d_ops + sg.op_off; p.n_rec = sg.n_ops; p.U = c->d_U; p.F = c->d_F; p.L = L; p.n_lanes = n;
+        p.ops = c->d_ops + sg.op_off + skip; p.n_rec = sg.n_ops - skip; p.U = c->d_U; p.F = c->d_F; p.L = L; p.n_lanes = n;
         p.fpool = c->d_fpool; p.list = c->d_list;
         if (c->packed) {
           p.inputs = reinterpret_cast<const u64*>(reinterpret_cast<const unsigned char*>(c->d_inputs) + base * c->packed_stride);
