@@ -34,7 +34,7 @@ extern "C" {
 #endif
 
 #define PZK_MAGIC 0x314b5a50u /* "PZK1" */
-#define PZK_VERSION 11u
+#define PZK_VERSION 12u
 
 /* ---- opcodes ------------------------------------------------------------ */
 enum PzkOpcode {
@@ -147,6 +147,11 @@ enum PzkOpcode {
                               evaluator takes them on a two-compare path in front of its opcode dispatch      */
 #define PZK_FLAG_NBASE 16u /* U_EXTRACT / N_EXTRACT / CHECK_RANGE: operand a is a plain 256-bit value (F plane) */
 #define PZK_FLAG_W64 32u   /* V_LUT: 64 lanes, a second extension record follows                              */
+#define PZK_FLAG_DIG 128u  /* the op's result is a wire (or the word behind bit-field views that are wires): one 16-byte
+                              digest descriptor follows the op's own records.  On disk {0, plane (0 = U, 1 = F), slot, 0};
+                              the runtime rewrites it when the program is loaded to {rep | table << 4 | nbits << 8,
+                              weight low, weight high, table offset} (pzk_kernels.cuh "fused digest"); an evaluator
+                              that does not compute the digest skips it                                          */
 #define PZK_FLAG_ZSRC 64u  /* N_FROM_F / F_FROM_N: operand a is a Z value: dst(N) = canonical(a) = a < 0 ? p + a : a,
                               dst(F) = Montgomery(a)                                                           */
 

@@ -596,6 +596,7 @@ uint32_t pzk_ref_witness(const PzkRefProgram* p, const uint8_t* inputs, uint8_t*
         }
         default: fprintf(stderr, "ssa_ref: bad opcode %d\n", o->opc); abort();
       }
+      if (o->flags & PZK_FLAG_DIG) pc++; /* digest descriptor of the device's fused witness digest: not an op */
     }
     if (check_rows) {
       for (uint64_t r = sg->row_off; r < sg->row_off + sg->n_rows; r++) {

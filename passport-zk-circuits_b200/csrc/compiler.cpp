@@ -3032,6 +3032,26 @@ void Compiler::Impl::backend() {
     }
     f(canon(v));
   };
+  // Fused witness digest (pzk_program.h, PZK_FLAG_DIG): an op whose result is a wire, or the word behind bit-field
+  // views that are wires, is followed by a digest descriptor so that the evaluator can fold the value when it is
+  // defined instead of storing and re-reading it.  Export entries the descriptor cannot carry (truth-table views
+  // over several words, views wider than 64 bits) are folded after the segment from the global slots of their
+  // words: those words must always be stored.
+  std::vector<uint8_t> dig_work(nv, 0), dig_global(nv, 0);
+  if (opt.fused_digest) {
+    for (uint32_t sgi = 0; sgi < sig_val.size(); sgi++) {
+      uint32_t v = sig_val[sgi];
+      if (!v) continue;
+      if (v < vw.size() && vw[v].base) {
+        const ViewD& d = vw[v];
+        uint32_t b = canon(d.base);
+        const uint32_t width = (v_cls[b] == CLS_U) ? 64 : 256;
+        if ((uint32_t)d.n + d.k <= 64 && d.s < width) dig_work[b] = 1; else dig_global[b] = 1;
+      } else if (v < v_tabview.size() && v_tabview[v]) {
+        sig_words(v, [&](uint32_t w) { dig_global[w] = 1; });
+      } else dig_work[canon(v)] = 1;
+    }
+  }
   // ---- segments over kept ops (+ their rows)
   std::vector<uint32_t> def_seg(nv, 0), last_seg(nv, 0), op_seg(nops, 0);
   {
@@ -3040,7 +3060,7 @@ void Compiler::Impl::backend() {
     bool after_solo = false;
     for (size_t i = 0; i < nops; i++) {
       if (!keep[i]) continue;
-      uint64_t need = ((ops[i].flags & PZK_FLAG_EXT) ? 2 : 1) + ((ops[i].opc == PZK_V_LUT && (ops[i].flags & PZK_FLAG_W64)) ? 1 : 0);
+      uint64_t need = ((ops[i].flags & PZK_FLAG_EXT) ? 2 : 1) + ((ops[i].opc == PZK_V_LUT && (ops[i].flags & PZK_FLAG_W64)) ? 1 : 0) + ((opt.fused_digest && !is_macro(ops[i].opc) && ops[i].dst && ops[i].dst < dig_work.size() && dig_work[ops[i].dst]) ? 1 : 0);
       size_t q = rp;
       while (q < nrows && row_trigger[row_order[q]] == i) { if (!row_static[row_order[q]]) need += row_recs[row_order[q]]; q++; }
       // the BabyJubjub ladder gets a segment of its own: the runtime runs it as a dedicated kernel
@@ -3358,6 +3378,7 @@ void Compiler::Impl::backend() {
   row_opnd = opnd;
   // values that must always reach their global slot: public wires (read by the export kernel)
   for (uint32_t sg = 0; sg < sig_val.size(); sg++) if (sig_val[sg] && sig2wire[sg] <= n_pub_out + n_pub_in) sig_words(sig_val[sg], [&](uint32_t w) { needs_global[w] = 1; });
+  for (size_t v = 0; v < nv; v++) if (dig_global[v]) needs_global[v] = 1;
   for (pass = 0; pass < 2; pass++) {
     // pass 0 learns which values are ever read from their global slot; pass 1 emits
     out_list = list_pool; out_ops.clear(); icoef_off.clear();
@@ -3411,6 +3432,8 @@ void Compiler::Impl::backend() {
         r.dst = slot | (cell >= 0 ? ((uint32_t)cell + 1) << 22 : 0);
         if (pass == 1 && cell >= 0 && !needs_global[o.dst]) r.dst |= PZK_DST_OPTIONAL;
       }
+      const bool with_dig = has_dst && !is_macro(o.opc) && o.dst < dig_work.size() && dig_work[o.dst];
+      if (with_dig) r.flags |= PZK_FLAG_DIG;
       out_ops.push_back(r);
       if (o.flags & PZK_FLAG_EXT) {
         PzkOpExt x; x.c = ext_c; x.d = ext_d; x.e = o.e; x.f = o.f;
@@ -3422,6 +3445,13 @@ void Compiler::Impl::backend() {
           memcpy(&raw, &y, sizeof raw);
           out_ops.push_back(raw);
         }
+      }
+      if (with_dig) {
+        // descriptor: {0, plane (0 = U, 1 = F), slot, 0}; the runtime fills in weights / table when it loads the program
+        const bool narrow_d = (v_cls[o.dst] == CLS_U || v_cls[o.dst] == CLS_I);
+        uint32_t wds[4] = {0u, narrow_d ? 0u : 1u, slot_of(o.dst), 0u};
+        PzkOp raw; memcpy(&raw, wds, 16);
+        out_ops.push_back(raw);
       }
       pos++;
       while (rp < nrows && row_trigger[row_order[rp]] == i) {

@@ -118,6 +118,7 @@ struct CompileOptions {
   bool def_rows_static = false;  // discharge the rows of `x <== e` (they hold by construction) at compile time
   bool views = true;     // bit-field views + bit-view row proofs (Num2Bits / GetLastNBits / running sums cost no ops)
   bool vectorize = true; // pack one-bit truth-table ops over rotated words into V_LUT records (needs views)
+  bool fused_digest = true;  // digest descriptors behind the ops that define wires (PZK_FLAG_DIG)
   bool zclass = true;    // exact wide integers (limb products, Karatsuba sums) as Z-class integer ops instead of Fr ops
 };
 

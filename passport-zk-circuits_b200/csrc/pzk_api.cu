@@ -92,6 +92,8 @@ struct pzk_circuit {
   DigRec* d_dig_recs = nullptr;        // digest program: records per segment
   ulonglong2* d_dig_tab = nullptr;     // per-bit coefficient tables
   std::vector<std::pair<uint64_t, uint64_t>> dig_seg;  // (offset, count) of each segment's digest records
+  bool dig_fused = false;              // the program carries digest descriptors (PZK_FLAG_DIG): fold in the evaluator
+  uint64_t dig_fused_entries = 0, dig_kernel_entries = 0;
   // profiling
   bool prof = false;
   double prof_ms[5] = {0, 0, 0, 0, 0};
@@ -215,46 +217,104 @@ static void classify_coefs(const PzkCoef* coefs, uint32_t n, std::vector<unsigne
 }
 
 // The digest program: the export entries of every segment compiled into digest records (pzk_kernels.cuh).
-// All bit-field views of one word collapse into one table of per-bit 128-bit coefficients.
+// All bit-field views of one word collapse into one table of per-bit 128-bit coefficients.  When the program carries
+// digest descriptors (PZK_FLAG_DIG, written by the compiler behind the op that defines a wire or a word with views),
+// the records of that value are moved INTO the descriptor - the evaluator folds the value when it is defined - and
+// only the rest (outputs of the hint intrinsics, truth-table views over several words, wide views) stays in the
+// per-segment list of digest_kernel.
 static void build_digest_program(pzk_circuit* c, std::vector<DigRec>& recs, std::vector<ulonglong2>& tab) {
   typedef unsigned __int128 u128;
   c->dig_seg.assign(c->h.n_segments, {0, 0});
+  c->dig_fused = false; c->dig_fused_entries = c->dig_kernel_entries = 0;
+  PzkOp* ops = const_cast<PzkOp*>(c->ops);
   for (uint32_t s = 0; s < c->h.n_segments; s++) {
     const PzkSegment& sg = c->segs[s];
     c->dig_seg[s].first = recs.size();
-    std::map<uint64_t, std::vector<u128>> words;  // (is_N << 32 | slot) -> coefficient per bit
+    struct Work { u128 plain = 0; uint32_t plain_rep = 0; std::vector<u128> T; uint64_t n_entries = 0; };
+    std::map<uint64_t, Work> work;  // (plane << 32 | slot) -> what the wires behind this value contribute
+    std::vector<DigRec> generic;
     u128 konst = 0;
     for (uint64_t e = sg.exp_off; e < sg.exp_off + sg.n_exp; e++) {
       const PzkExport& x = c->exports[e];
       const uint32_t cw = pzk_digest_weight(x.wire);
       if (x.ref == PZK_REF_ZERO) continue;
       if (x.ref == PZK_REF_ONE) { konst += cw; continue; }
-      DigRec r; r.type_nbits = 0; r.slot = PZK_REF_SLOT(x.ref); r.a = cw; r.b = 0;
-      if (x.ref == PZK_REF_TABVIEW) { r.type_nbits = DIG_GENERIC; r.slot = 0; r.a = (uint32_t)e; r.b = cw; recs.push_back(r); continue; }
-      const uint32_t cls = PZK_REF_CLS(x.ref);
+      DigRec g; g.type_nbits = DIG_GENERIC; g.slot = 0; g.a = (uint32_t)e; g.b = cw;
+      if (x.ref == PZK_REF_TABVIEW) { generic.push_back(g); continue; }
+      const uint32_t cls = PZK_REF_CLS(x.ref), slot = PZK_REF_SLOT(x.ref);
       if (cls == 3) {
         const uint32_t s_ = x.aux & 255u, n_ = (x.aux >> 8) & 255u, k_ = (x.aux >> 16) & 255u;
         const bool isn = (x.ref & PZK_REF_VIEW_N) != 0;
         const uint32_t width = isn ? 256 : 64;
         if (n_ + k_ <= 64 && s_ < width) {
-          std::vector<u128>& T = words[((uint64_t)isn << 32) | r.slot];
-          if (T.empty()) T.assign(width, 0);
-          for (uint32_t b = s_; b < s_ + n_ && b < width; b++) T[b] += (u128)cw << (b - s_ + k_);
-        } else if (n_ != 0 && s_ < width) { r.type_nbits = DIG_GENERIC; r.slot = 0; r.a = (uint32_t)e; r.b = cw; recs.push_back(r); }
+          Work& w = work[((uint64_t)isn << 32) | slot];
+          if (w.T.empty()) w.T.assign(width, 0);
+          for (uint32_t b = s_; b < s_ + n_ && b < width; b++) w.T[b] += (u128)cw << (b - s_ + k_);
+          w.n_entries++;
+        } else if (n_ != 0 && s_ < width) generic.push_back(g);
         continue;
       }
-      r.type_nbits = cls == 0 ? DIG_PLAIN_U : cls == 1 ? DIG_PLAIN_I : ((x.ref & PZK_REF_Z) ? DIG_PLAIN_Z : DIG_PLAIN_F);
-      recs.push_back(r);
+      Work& w = work[((uint64_t)(cls == 2) << 32) | slot];
+      w.plain += cw; w.n_entries++;
+      w.plain_rep = cls == 0 ? 1u : cls == 1 ? 2u : ((x.ref & PZK_REF_Z) ? 4u : 3u);
     }
-    for (auto& kv : words) {
+    // descriptors of this segment's op stream claim the work of the value they follow
+    for (uint64_t pc = sg.op_off; pc < sg.op_off + sg.n_ops; pc++) {
+      const PzkOp& o = ops[pc];
+      const bool dig = (o.flags & PZK_FLAG_DIG) != 0;
+      if (o.opc == PZK_CHECK_INT || o.opc == PZK_CHECK_F || o.opc == PZK_CHECK_I64) { pc += o.b; continue; }
+      if (o.flags & PZK_FLAG_EXT) pc++;
+      if (o.opc == PZK_V_LUT && (o.flags & PZK_FLAG_W64)) pc++;
+      if (!dig) continue;
+      pc++;
+      c->dig_fused = true;
+      uint32_t wds[4];
+      memcpy(wds, &ops[pc], 16);
+      const uint64_t key = ((uint64_t)(wds[1] != 0) << 32) | wds[2];
+      uint32_t out[4] = {0, 0, 0, 0};
+      auto it = work.find(key);
+      if (it != work.end()) {
+        Work& w = it->second;
+        uint32_t nbits = 0;
+        for (uint32_t b = 0; b < w.T.size(); b++) if (w.T[b]) nbits = b + 1;
+        uint32_t repk = w.plain_rep;
+        if (!repk) repk = wds[1] ? 5u : 1u;  // a word that is only the base of views: U word or plain N value
+        if ((uint64_t)(w.plain >> 64)) { set_err(c, "digest: weight overflow"); }
+        out[0] = repk | (nbits ? 16u : 0u) | (nbits << 8);
+        out[1] = (uint32_t)(uint64_t)w.plain; out[2] = (uint32_t)((uint64_t)w.plain >> 32);
+        out[3] = (uint32_t)tab.size();
+        for (uint32_t b = 0; b < nbits; b++) tab.push_back(make_ulonglong2((u64)w.T[b], (u64)(w.T[b] >> 64)));
+        c->dig_fused_entries += w.n_entries;
+        work.erase(it);
+      }
+      memcpy(&ops[pc], out, 16);
+    }
+    // what no descriptor claimed: records for digest_kernel
+    for (auto& kv : work) {
+      Work& w = kv.second;
+      const bool fplane = (kv.first >> 32) != 0;
+      c->dig_kernel_entries += w.n_entries;
+      if (w.plain) {
+        u128 pl = w.plain;
+        while (pl) {  // 32-bit weights per record
+          DigRec r; r.slot = (uint32_t)kv.first; r.b = 0;
+          r.type_nbits = w.plain_rep == 1 ? DIG_PLAIN_U : w.plain_rep == 2 ? DIG_PLAIN_I : w.plain_rep == 4 ? DIG_PLAIN_Z : DIG_PLAIN_F;
+          r.a = (uint32_t)std::min<u128>(pl, (u128)0xffffffffu);
+          pl -= r.a;
+          recs.push_back(r);
+        }
+      }
       uint32_t nbits = 0;
-      for (uint32_t b = 0; b < kv.second.size(); b++) if (kv.second[b]) nbits = b + 1;
-      if (!nbits) continue;
-      DigRec r; r.type_nbits = ((kv.first >> 32) ? DIG_WORD_N : DIG_WORD_U) | (nbits << 8);
-      r.slot = (uint32_t)kv.first; r.a = (uint32_t)tab.size(); r.b = 0;
-      for (uint32_t b = 0; b < nbits; b++) tab.push_back(make_ulonglong2((u64)kv.second[b], (u64)(kv.second[b] >> 64)));
-      recs.push_back(r);
+      for (uint32_t b = 0; b < w.T.size(); b++) if (w.T[b]) nbits = b + 1;
+      if (nbits) {
+        DigRec r; r.type_nbits = (fplane ? DIG_WORD_N : DIG_WORD_U) | (nbits << 8);
+        r.slot = (uint32_t)kv.first; r.a = (uint32_t)tab.size(); r.b = 0;
+        for (uint32_t b = 0; b < nbits; b++) tab.push_back(make_ulonglong2((u64)w.T[b], (u64)(w.T[b] >> 64)));
+        recs.push_back(r);
+      }
     }
+    c->dig_kernel_entries += generic.size();
+    recs.insert(recs.end(), generic.begin(), generic.end());
     while (konst) {  // constant wires (value 1): 64 bits at a time
       DigRec r; r.type_nbits = DIG_CONST; r.slot = 0; r.a = (uint32_t)konst; r.b = (uint32_t)(konst >> 32);
       recs.push_back(r);
@@ -388,7 +448,7 @@ static int open_impl(const char* program_path, const char* own_sym, const char* 
     c->packed_stride = (offf + 15) / 16 * 16;
   }
   c->bytes_per_lane = (uint64_t)c->h.n_u_slots * 8 + (uint64_t)c->h.n_f_slots * 32;
-  c->smem_bytes = (size_t)c->h.reserved[1] * 8 * 128;
+  c->smem_bytes = ((size_t)c->h.reserved[1] + DIG_ACC_WORDS) * 8 * 128;  // operand cache + digest accumulators
 
   CK(cudaSetDevice(cuda_device));
   CK(cudaStreamCreate(&c->stream));
@@ -399,6 +459,13 @@ static int open_impl(const char* program_path, const char* own_sym, const char* 
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, eval_kernel, 128, c->smem_bytes));
     CK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, cuda_device));
     c->wave_lanes = (uint64_t)per_sm * n_sm * 128;
+  }
+  {
+    // the digest program first: it fills in the digest descriptors of the op stream before that is uploaded
+    std::vector<DigRec> recs; std::vector<ulonglong2> tab;
+    build_digest_program(c, recs, tab);
+    CK(upload(&c->d_dig_recs, recs.data(), recs.size() * sizeof(DigRec)));
+    CK(upload(&c->d_dig_tab, tab.data(), tab.size() * sizeof(ulonglong2)));
   }
   CK(upload(&c->d_ops, c->ops, c->h.n_op_records * sizeof(PzkOp)));
   CK(upload(&c->d_fpool, c->fpool, (size_t)c->h.n_fpool * 32));
@@ -425,12 +492,6 @@ static int open_impl(const char* program_path, const char* own_sym, const char* 
       if (c->exports[e].wire >= 1 && c->exports[e].wire <= n_pub) { c->seg[s].pub.push_back(c->exports[e]); all_pub.push_back(c->exports[e]); }
   }
   CK(upload(&c->d_pub_entries, all_pub.data(), all_pub.size() * sizeof(PzkExport)));
-  {
-    std::vector<DigRec> recs; std::vector<ulonglong2> tab;
-    build_digest_program(c, recs, tab);
-    CK(upload(&c->d_dig_recs, recs.data(), recs.size() * sizeof(DigRec)));
-    CK(upload(&c->d_dig_tab, tab.data(), tab.size() * sizeof(ulonglong2)));
-  }
   return PZK_OK;
 }
 
@@ -565,7 +626,8 @@ static int run_batch(pzk_circuit* c, const RunOpts& o) {
   const uint64_t L = std::min<uint64_t>(c->L, (want + 127) / 128 * 128);
   const uint32_t n_pub = c->h.n_pub_out + c->h.n_pub_in;
   const bool digest = c->digest_on;
-  const int store_all = (o.n_export > 0 || digest) ? 1 : 0;
+  const bool fused = digest && c->dig_fused;   // values are folded when they are defined: nothing extra to store
+  const int store_all = (o.n_export > 0 || (digest && !fused)) ? 1 : 0;
   const uint64_t n_tiles = (c->batch + L - 1) / L;
   c->in_flight = true;
   auto new_event = [&]() { cudaEvent_t e; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); c->run_events.push_back(e); return e; };
@@ -632,6 +694,8 @@ static int run_batch(pzk_circuit* c, const RunOpts& o) {
         p.n_inputs = c->h.n_inputs; p.status = c->d_status + base; p.n_u_slots = c->h.n_u_slots; p.n_f_slots = c->h.n_f_slots;
         p.check_rows = o.check_rows; p.store_all = store_all; p.sc.coefs = c->d_coefs; p.sc.coef_kind = c->d_coef_kind; p.sc.coef_mag = c->d_coef_mag;
         p.first_bad = c->d_first_bad + base;
+        p.digest = fused ? 1 : 0; p.dig_tab = c->d_dig_tab; p.dig_state = c->d_dig_state; p.dig_stride = c->batch_cap;
+        p.dig_lane_base = base; p.dig_smem_off = (u32)((size_t)c->h.reserved[1] * 8 * 128);
         prof_begin(c, 0, ea, eb);
         eval_kernel<<<grid, 128, c->smem_bytes, c->stream>>>(p);
         prof_end(c, 0, ea, eb);

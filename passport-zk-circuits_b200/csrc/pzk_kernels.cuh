@@ -45,6 +45,13 @@ struct EvalParams {
   int store_all;  // 1: every value reaches its global slot (witness export requested)
   StreamCoefs sc;
   unsigned long long* first_bad;
+  // fused witness digest (see "fused digest" below): 0 = off (descriptors are skipped)
+  int digest;
+  const ulonglong2* dig_tab;  // per-bit coefficient tables
+  u64* dig_state;             // [DIG_STATE_PIECES][dig_stride] carry-save accumulators
+  u64 dig_stride;
+  u64 dig_lane_base;
+  u32 dig_smem_off;           // byte offset of the accumulators behind the operand cache
 };
 
 // Slot planes are private to a lane and far larger than any cache, but their accesses still go through
@@ -536,6 +543,101 @@ __device__ __forceinline__ void field256(u64* r, const u64* v, unsigned s, unsig
   shl256(r, t, k);
 }
 
+// ---- fused witness digest --------------------------------------------------------------------------------
+// The digest of pzk.h (sum over wires of c(i) w_i mod p) folded WHEN A VALUE IS DEFINED instead of after the
+// segment from HBM (digest_kernel below keeps the entries that cannot be attached to one defining op: outputs of
+// the hint intrinsics, truth-table views over several words, views wider than 64 bits).  An op with PZK_FLAG_DIG is
+// followed by a descriptor the runtime filled in when it loaded the program:
+//   x = rep | has_table << 4 | nbits << 8    rep: 1 = U word, 2 = signed I word, 3 = F (Montgomery), 4 = Z, 5 = N (plain)
+//   y, z = 64-bit weight of the value itself (sum of c(i) over the wires that ARE this value; 0 = none)
+//   w = offset of the per-bit coefficient table (all bit-field views of this word)
+// Accumulators live in shared memory behind the operand cache (12 x 8 bytes per lane): accN 128-bit (narrow words,
+// view tables), accM 320-bit (sum of weight x Montgomery value), accP 320-bit (sum of weight x canonical value);
+// they are flushed to the per-lane carry-save state at the end of the launch, digest_finalize_kernel normalises.
+#define DIG_ACC_WORDS 12
+__device__ __forceinline__ void dig_acc_add128(u32 acc, u64 lo, u64 hi) {  // acc: shared address of {lo, hi}
+  u64 a0 = lds64(acc), a1 = lds64(acc + 1024);
+  asm("add.cc.u64 %0, %0, %2; addc.u64 %1, %1, %3;" : "+l"(a0), "+l"(a1) : "l"(lo), "l"(hi));
+  sts64(acc, a0); sts64(acc + 1024, a1);
+}
+// acc (5 x 64 in shared memory) += c * w (4 x 64), c < 2^64, total < 2^320.  Almost every weight is the 32-bit c(i)
+// of a single wire: 32 x 32 products on the halves of the limbs (8 IMAD.WIDE) instead of 64 x 64 ones.
+__device__ __noinline__ void dig_acc_mac320(u32 acc, u64 c, u64 w0, u64 w1, u64 w2, u64 w3) {
+  const u64 w[4] = {w0, w1, w2, w3};
+  u64 carry = 0;
+  if ((c >> 32) == 0) {
+    const u32 c32 = (u32)c;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const u64 pl = (u64)c32 * (u32)w[j], ph = (u64)c32 * (u32)(w[j] >> 32);  // c w = pl + ph 2^32
+      const u64 lo = pl + (ph << 32);
+      const u64 hi = (ph >> 32) + (lo < pl);
+      const u64 a = lds64(acc + 1024 * j);
+      u64 t = a + lo;
+      const u64 c1 = t < lo;
+      const u64 t2 = t + carry;
+      const u64 c2 = t2 < carry;
+      sts64(acc + 1024 * j, t2);
+      carry = hi + c1 + c2;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const u64 lo = c * w[j], hi = __umul64hi(c, w[j]);
+      const u64 a = lds64(acc + 1024 * j);
+      u64 t = a + lo;
+      const u64 c1 = t < lo;
+      const u64 t2 = t + carry;
+      const u64 c2 = t2 < carry;
+      sts64(acc + 1024 * j, t2);
+      carry = hi + c1 + c2;  // hi <= 2^64 - 2: no overflow
+    }
+  }
+  sts64(acc + 4096, lds64(acc + 4096) + carry);
+}
+__device__ __noinline__ void dig_fold_table(u32 accN, const ulonglong2* T, u32 nbits, u64 W0, u64 W1, u64 W2, u64 W3) {
+  u64 a0 = lds64(accN), a1 = lds64(accN + 1024);
+  const u64 Wv[4] = {W0, W1, W2, W3};
+  for (u32 j = 0; j * 64 < nbits; j++) {
+    u64 W = Wv[j];
+    const u32 nb = min(64u, nbits - j * 64);
+    const ulonglong2* Tj = T + j * 64;
+#pragma unroll 8
+    for (u32 b = 0; b < nb; b++) {
+      const ulonglong2 t = __ldg(Tj + b);
+      if (W & 1ull) asm("add.cc.u64 %0, %0, %2; addc.u64 %1, %1, %3;" : "+l"(a0), "+l"(a1) : "l"(t.x), "l"(t.y));
+      W >>= 1;
+    }
+  }
+  sts64(accN, a0); sts64(accN + 1024, a1);
+}
+
+// one descriptor: v0..v3 = the value just defined (a U / I word in v0, or the 4 limbs of an F / Z / N value)
+__device__ __noinline__ void dig_fold(u32 dacc, const ulonglong2* tab, uint4 dg, u64 v0, u64 v1, u64 v2, u64 v3) {
+  const u32 repk = dg.x & 15u, nbits = dg.x >> 8;
+  const u64 c = (u64)dg.y | ((u64)dg.z << 32);
+  const u32 accN = dacc, accM = dacc + 2 * 1024, accP = dacc + 7 * 1024;
+  if (repk == 1 || (repk == 2 && (long long)v0 >= 0)) {
+    if (c) dig_acc_add128(accN, c * v0, __umul64hi(c, v0));
+    if (dg.x & 16u) dig_fold_table(accN, tab + dg.w, nbits, v0, 0, 0, 0);
+  } else if (repk == 2) {  // negative signed word: its canonical value is p - |v|
+    const u64 pp[4] = {P0, P1, P2, P3}; u64 m[4] = {(u64)(-(long long)v0), 0, 0, 0}, w[4];
+    sub256(w, pp, m);
+    if (c) dig_acc_mac320(accP, c, w[0], w[1], w[2], w[3]);
+  } else if (repk == 3) {
+    if (c) dig_acc_mac320(accM, c, v0, v1, v2, v3);
+  } else if (repk == 4) {
+    if (c) {
+      u64 w[4] = {v0, v1, v2, v3};
+      if ((long long)v3 < 0) { const u64 pp[4] = {P0, P1, P2, P3}; add256(w, w, pp); }
+      dig_acc_mac320(accP, c, w[0], w[1], w[2], w[3]);
+    }
+  } else if (repk == 5) {
+    if (c) dig_acc_mac320(accP, c, v0, v1, v2, v3);
+    if (dg.x & 16u) dig_fold_table(accN, tab + dg.w, nbits, v0, v1, v2, v3);
+  }
+}
+
 // ---- Z class: exact wide integers in 256-bit two's complement (pzk_program.h) -----------------------------
 // canonical residue of a Z value: v < 0 ? p + v : v
 __device__ __forceinline__ void z_canonical(u64* r, const u64* z) {
@@ -617,6 +719,13 @@ __global__ void __launch_bounds__(128, 7) eval_kernel(EvalParams p) {
   const u32* __restrict__ list = p.list;
   const StreamCoefs sc = p.sc;
   const u32 n_rec = (u32)p.n_rec;
+  const bool digest = p.digest != 0;
+  const ulonglong2* __restrict__ dig_tab = p.dig_tab;
+  const u32 dacc = (u32)__cvta_generic_to_shared(cell_mem) + p.dig_smem_off + threadIdx.x * 8;
+  if (digest) {
+#pragma unroll
+    for (int k = 0; k < DIG_ACC_WORDS; k++) sts64(dacc + 1024 * k, 0);
+  }
   for (u32 pc = 0; pc < n_rec; pc++) {
     const uint4 w = __ldg(ops + pc);
     const u32 opc = w.x & 0xffu, flags = (w.x >> 8) & 0xffu, imm16 = w.x >> 16;
@@ -636,6 +745,10 @@ __global__ void __launch_bounds__(128, 7) eval_kernel(EvalParams p) {
       const u64 r_ = opc == PZK_U_ADD ? x_ + y_ : opc == PZK_U_MUL ? x_ * y_ : opc == PZK_U_AND ? (x_ & y_)
                    : opc == PZK_U_SHLADD ? x_ + (y_ << imm16) : sh_;
       STD(dst, r_);
+      if (flags & PZK_FLAG_DIG) {
+        const uint4 dg = __ldg(ops + (++pc));
+        if (digest) dig_fold(dacc, dig_tab, dg, r_, 0, 0, 0);
+      }
       continue;
     }
     switch (opc) {
@@ -873,6 +986,31 @@ __global__ void __launch_bounds__(128, 7) eval_kernel(EvalParams p) {
         break;
       }
       default: st |= 0x80000000u; break;
+    }
+    if (flags & PZK_FLAG_DIG) {
+      // the value this op just defined, from its cache cell or its slot, folded into the digest
+      const uint4 dg = __ldg(ops + (++pc));
+      if (digest && (dg.x & 15u)) {
+        const u32 cell = PZK_DST_CELL(dst);
+        u64 v[4] = {0, 0, 0, 0};
+        if ((dg.x & 15u) <= 2) v[0] = cell ? lds64(cells + ((cell - 1) << 10)) : PLD(Ul + (u64)PZK_DST_SLOT(dst) * L);
+        else if (cell) { const u32 c0 = cells + ((cell - 1) << 10); v[0] = lds64(c0); v[1] = lds64(c0 + 1024); v[2] = lds64(c0 + 2048); v[3] = lds64(c0 + 3072); }
+        else ldF(Fl, L, PZK_DST_SLOT(dst), v);
+        dig_fold(dacc, dig_tab, dg, v[0], v[1], v[2], v[3]);
+      }
+    }
+  }
+  if (digest) {
+    // flush the accumulators to the per-lane carry-save state (pieces of 32 bits, see digest_kernel)
+    unsigned long long* stt = reinterpret_cast<unsigned long long*>(p.dig_state) + p.dig_lane_base + lane;
+    const u64 S = p.dig_stride;
+    const int piece0[DIG_ACC_WORDS] = {0, 2, 8, 10, 12, 14, 16, 18, 20, 22, 24, 26};
+#pragma unroll
+    for (int k = 0; k < DIG_ACC_WORDS; k++) {
+      const u64 a = lds64(dacc + 1024 * k);
+      const u64 lo = a & 0xffffffffull, hi = a >> 32;
+      if (lo) atomicAdd(stt + (u64)piece0[k] * S, (unsigned long long)lo);
+      if (hi) atomicAdd(stt + (u64)(piece0[k] + 1) * S, (unsigned long long)hi);
     }
   }
   if (bad != ~0ull) {

@@ -565,6 +565,7 @@ def program_histogram(program_path: str) -> dict:
     quad_field_rows = 0
     bjj_products = 0
     z_imad = 0
+    n_dig = 0
     pc = 0
     w0 = ops[:, 0]
     while pc < n_rec:
@@ -586,13 +587,16 @@ def program_histogram(program_path: str) -> dict:
             pc += 1
         if opc == 23 and fl & 32:
             pc += 1
+        if fl & 128 and opc not in (56, 57, 58):      # digest descriptor behind the op (PZK_FLAG_DIG)
+            pc += 1
+            n_dig += 1
         pc += 1
     narrow = sum(v for k, v in hist.items() if k.startswith(("U_", "I_", "V_")) or k in ("N_BIT", "N_LOW", "N_FITS", "IN_U", "CHECK_I64", "CHECK_INT", "CHECK_RANGE",
                                                                                           "Z_ADD", "Z_SUB", "Z_FROM_U", "Z_FROM_I"))
     fr_products = hist.get("F_MUL", 0) + bjj_products + quad_field_rows
     return {"records": hist, "fr_products": fr_products, "explicit_f_mul": hist.get("F_MUL", 0),
             "intrinsic_products": bjj_products, "quadratic_field_rows": quad_field_rows, "narrow_records": narrow,
-            "z_mul_records": hist.get("Z_MUL", 0), "z_mul_imad": z_imad,
+            "z_mul_records": hist.get("Z_MUL", 0), "z_mul_imad": z_imad, "digest_descriptors": n_dig,
             "algorithmic_imad": 136 * fr_products + z_imad + narrow}
 
 
