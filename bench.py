@@ -350,10 +350,11 @@ def main():
         rows = rows_of(stats, calc.n_constraints)
         eval_ms, eval_launches = prof["eval"]
         lanes_per_launch = min(B, calc.tile_lanes())
-        n_seg = stats["segments"]
-        imad_per_launch = hist["algorithmic_imad"] * lanes_per_launch / n_seg
+        # algorithmic IMAD of the whole timed region / CUDA-event time of its evaluator launches (eval_kernel + bjj_kernel;
+        # with the fused digest the folds are inside those launches and inside that time, but not in the numerator)
         avg_launch_s = eval_ms / 1e3 / max(1, eval_launches)
-        achieved = imad_per_launch / avg_launch_s
+        achieved = hist["algorithmic_imad"] * B * a.steps / (eval_ms / 1e3)
+        imad_per_launch = achieved * avg_launch_s
         imad_peak = ipk.get("imad_per_s")
         dram = ncu_dram_bytes()
         traffic = None
