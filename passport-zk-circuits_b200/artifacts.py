@@ -76,6 +76,13 @@ def reference_circuits():
                     "timestampLowerbound, timestampUpperbound, identityCounterLowerbound, identityCounterUpperbound, "
                     "birthDateLowerbound, birthDateUpperbound, expirationDateLowerbound, expirationDateUpperbound, "
                     "citizenshipMask] } = QueryIdentity(80);\n", {"dg1": 1}),
+        # config 2 for TD1 identity cards (760-bit DG1, 190-bit commitment chunks, hashed document / personal numbers)
+        "query80_td1": (f'pragma circom 2.1.6;\ninclude "{W._ROOT}/tests/circuits/shims/babypbk.circom";\n'
+                        f'include "{REFERENCE}/circuits/identityManagement/queryIdentityTD1.circom";\n'
+                        "component main { public [eventID, eventData, idStateRoot, selector, currentDate, "
+                        "timestampLowerbound, timestampUpperbound, identityCounterLowerbound, identityCounterUpperbound, "
+                        "birthDateLowerbound, birthDateUpperbound, expirationDateLowerbound, expirationDateUpperbound, "
+                        "citizenshipMask] } = QueryIdentity(80);\n", {"dg1": 1}),
         # one P-256 point doubling of the ECDSA verifier (lib/circuits/ec/curve.circom:281-313): mod_inv, long_div,
         # long_div2 / short_div with their data-dependent returns, PointOnTangent / PointOnCurve constraints
         "p256dbl": (f'pragma circom 2.1.6;\ninclude "{lib}/ec/curve.circom";\n'

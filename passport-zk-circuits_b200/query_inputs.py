@@ -51,14 +51,30 @@ def td3_dg1(rng) -> bytes:
     return bytes([0x61, 0x5B, 0x5F, 0x1F, 0x58]) + (line1 + line2).encode()
 
 
-def make_query_input(index: int, seed: int = 1, selector: int = 39) -> dict:
+def td1_dg1(rng) -> bytes:
+    """95-byte DG1 of a TD1 identity card: tag/len 61 5D 5F 1F 5A + three 30-character MRZ lines
+    (ICAO 9303 part 5; /root/reference/circuits/identityManagement/queryIdentityTD1.circom:75 reads 760 bits)."""
+    nat = rng.choice(_NAT)
+    docnum = "".join(rng.choice(_AL + "0123456789") for _ in range(9))
+    line1 = ("ID" + nat + docnum + "0").ljust(30, "<")[:30]
+    dob = "%02d%02d%02d" % (rng.randint(50, 99), rng.randint(1, 12), rng.randint(1, 28))
+    exp = "%02d%02d%02d" % (rng.randint(27, 35), rng.randint(1, 12), rng.randint(1, 28))
+    line2 = (dob + "0" + rng.choice("MF") + exp + "0" + nat).ljust(29, "<")[:29] + "0"
+    name = ("".join(rng.choice(_AL) for _ in range(rng.randint(3, 9))) + "<<" +
+            "".join(rng.choice(_AL) for _ in range(rng.randint(3, 9))))
+    line3 = name.ljust(30, "<")[:30]
+    return bytes([0x61, 0x5D, 0x5F, 0x1F, 0x5A]) + (line1 + line2 + line3).encode()
+
+
+def make_query_input(index: int, seed: int = 1, selector: int = 39, td1: bool = False) -> dict:
     rng = random.Random((seed << 20) ^ index)
-    dg1 = td3_dg1(rng)
+    dg1 = td1_dg1(rng) if td1 else td3_dg1(rng)
     bits = [(b >> (7 - i)) & 1 for b in dg1 for i in range(8)]
     sk = rng.getrandbits(248)
     pk_passport_hash = rng.getrandbits(250)
     timestamp, counter = 1713436475 + index, 1
-    chunks = [sum(bits[i * 186 + j] << j for j in range(186)) for i in range(4)]
+    cs = 190 if td1 else 186      # DG1 commitment chunk size (queryIdentityTD1.circom:203-212)
+    chunks = [sum(bits[i * cs + j] << j for j in range(cs)) for i in range(4)]
     dg_commit = poseidon(chunks + [poseidon([sk])])
     value = poseidon([dg_commit, counter, timestamp])
     pk_hash = poseidon(list(ed_mul(sk, BASE8)))

@@ -56,7 +56,7 @@ def golden(name, sym_path, inputs_list, n_pub, n_samples=4096):
 
 def main():
     from passport_zk_circuits_b200.artifacts import C4_VARIANTS as _ALL_C4
-    which = sys.argv[1:] or (["poseidon2", "sha256_1", "smt80", "query80", "c3"] + list(_ALL_C4))
+    which = sys.argv[1:] or (["poseidon2", "sha256_1", "smt80", "query80", "query80_td1", "c3"] + list(_ALL_C4))
     if "poseidon2" in which:
         golden("poseidon2", os.path.join(ART, "poseidon2.sym"), [{"in": ["1", "2"]}, {"in": ["0", str(co.P - 1)]}], 1)
     if "sha256_1" in which:
@@ -83,6 +83,10 @@ def main():
         from passport_zk_circuits_b200.query_inputs import make_query_input
         golden("query80", os.path.join(ART, "query80.sym"),
                [make_query_input(0, seed=7, selector=39), make_query_input(1, seed=7, selector=255)], 23)
+    if "query80_td1" in which:
+        from passport_zk_circuits_b200.query_inputs import make_query_input
+        golden("query80_td1", os.path.join(ART, "query80_td1.sym"),
+               [make_query_input(0, seed=7, selector=39, td1=True), make_query_input(1, seed=7, selector=255, td1=True)], 24)
     if "c3" in which:
         fac = PassportFactory(C3, seed=42, n_sig_keys=2, n_aa_keys=2)
         sym = os.path.join(ART, "c3.sym")

@@ -112,7 +112,7 @@ def golden_inputs(meta, case):
     return {k: (list(v) if isinstance(v, str) and size[k] > 1 else v) for k, v in case["inputs"].items()}
 
 
-GOLDEN = ["poseidon2", "sha256_1", "smt80", "query80", "c3", "c4_sig3", "c4_sig10", "c4_sig13", "c4_sig20",
+GOLDEN = ["poseidon2", "sha256_1", "smt80", "query80", "query80_td1", "c3", "c4_sig3", "c4_sig10", "c4_sig13", "c4_sig20",
           "c4_sig2", "c4_sig4", "c4_sig11", "c4_sig12", "c4_sig14", "c4_sig21", "c4_sig24", "c4_na", "c4_ecaa", "c4_td1"]
 
 

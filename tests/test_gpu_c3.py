@@ -125,20 +125,22 @@ def test_config4_variants(name):
     calc.close()
 
 
-def test_config2_query_identity():
-    """queryIdentity(80): golden public signals / .wtns bytes, all selectors, enforced SMT inclusion."""
+@pytest.mark.parametrize("name,td1", [("query80", False), ("query80_td1", True)])
+def test_config2_query_identity(name, td1):
+    """queryIdentity(80) for TD3 passports and queryIdentityTD1 for identity cards (760-bit DG1, hashed document /
+    personal numbers): golden public signals / .wtns bytes, all selectors, enforced SMT inclusion."""
     import hashlib
     from passport_zk_circuits_b200.query_inputs import make_query_input
-    prog = W.artifact("query80")
+    prog = W.artifact(name)
     calc = W.WitnessCalculator(prog, device=0)
-    g, ins = _golden_inputs(calc, "query80")
+    g, ins = _golden_inputs(calc, name)
     res = calc.calculateWitnessBatch(ins, export_lanes=range(len(ins)))
     for j, case in enumerate(g["cases"]):
         assert res.status[j] == 0
         assert hashlib.sha256(res.witnesses[j].tobytes()).hexdigest() == case["wtns_data_sha256"]
         assert [str(v) for v in res.public_ints(j)] == case["public"]
     B = 150
-    objs = [make_query_input(i, seed=3, selector=(i * 37) & 0xFF) for i in range(B)]
+    objs = [make_query_input(i, seed=3, selector=(i * 37) & 0xFF, td1=td1) for i in range(B)]
     objs[17]["idStateRoot"] = str(int(objs[17]["idStateRoot"]) ^ 1)        # not in the tree any more
     inp = W.pack_inputs_fast(calc.meta, objs)
     out = calc.calculateWitnessBatch(inp, export_lanes=[0, 17, B - 1])
