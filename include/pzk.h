@@ -78,6 +78,13 @@ int pzk_compile(const char* main_circom_path, const char* out_prefix, const char
  * verdicts; these flags switch the rewrite off (validation; PZK_COMPILE_NO_TABLE_PROOFS implies NO_VIEWS). */
 #define PZK_COMPILE_NO_VIEWS 8u
 #define PZK_COMPILE_NO_VECTORIZE 16u
+/* Also write <prefix>.O1.r1cs and <prefix>.O1.sym: the constraint system after an O1-style simplification (the
+ * reference's library circuits are compiled with `circom --O1`): linear constraints "signal = signal" and "signal =
+ * constant" are removed by substitution, repeatedly; the signals they eliminate leave the witness and carry witness
+ * index -1 in the .sym; main inputs and outputs always stay.  pzk_circuit_open_ex(program, <prefix>.sym,
+ * <prefix>.O1.sym) then produces the witness of that system.  Not calibrated against circom's own numbering (circom is
+ * not available in this environment): self-consistent, every surviving constraint holds on the renumbered witness. */
+#define PZK_COMPILE_EMIT_O1 32u
 int pzk_compile_ex(const char* main_circom_path, const char* out_prefix, const char* const* bits_names,
                    const int* bits_widths, int n_bits, uint32_t segment_ops, uint32_t flags, char* err,
                    size_t err_len);

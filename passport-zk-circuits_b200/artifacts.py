@@ -113,7 +113,10 @@ OWN_CIRCUITS = {"t_mix": ("mix.circom", {"u": 16, "bits": 1}),
                 "t_modinv": ("modinv.circom", {"a": 64})}
 
 COMPILE_OPTS = {"c3_lean": {"static_def_rows": True},
-                "c3_allrows": {"table_proofs": False, "segment_ops": 16384}}
+                "c3_allrows": {"table_proofs": False, "segment_ops": 16384},
+                # the small circuits also get the O1-simplified system (<name>.O1.r1cs / .O1.sym, pzk.h PZK_COMPILE_EMIT_O1)
+                "smt80": {"emit_o1": True}, "sha256_1": {"emit_o1": True}, "poseidon2": {"emit_o1": True},
+                "query80": {"emit_o1": True}}
 
 BIG = {"c3", "c3_lean", "c3_allrows", "c3_cms"} | set(C4_VARIANTS)  # ship only the xz-packed program for these
 
@@ -137,7 +140,7 @@ def build_all(verbose=True, only=None):
         if _stale(prefix + ".pzkp", deps + [src]):
             if verbose:
                 print("compiling", name)
-            W.compile_circuit(src, prefix, bits)
+            W.compile_circuit(src, prefix, bits, emit_o1=True)
     if not os.path.isdir(REFERENCE):
         return
     for name, (body, bits) in reference_circuits().items():

@@ -195,6 +195,7 @@ struct Compiler::Impl {
   std::vector<uint32_t> seg_quads;
   uint32_t n_pub_out = 0, n_pub_in = 0, n_prv_in = 0;
   std::string meta_json;
+  std::string o1_stats;
 
   const std::string& nm(int id) { return unit.names.str(id); }
   [[noreturn]] void fail(const Stmt* s, const std::string& m) {
@@ -3672,6 +3673,163 @@ void Compiler::write_r1cs(const std::string& path) {
   for (uint32_t i = 0; i < n_wires; i++) u64(i);
   fclose(f);
 }
+
+// ---------------------------------------------------------------------------------------
+// O1-style simplification of the emitted constraint system (the reference's library circuits are compiled with
+// `circom --O1`, /root/reference/circuits/lib/circuits/scripts/compile-circuit.sh:34): linear constraints that say
+// "signal = signal" or "signal = constant" are removed by substitution, repeatedly, and the signals they eliminate
+// leave the witness.  Main inputs and outputs are never eliminated.  Writes <r1cs_path> with the surviving wires
+// renumbered in their original order and <sym_path> in which eliminated signals carry witness index -1 - the shape of
+// the .sym circom writes - so that pzk_circuit_open_ex(program, program.sym, this .sym) produces the matching witness.
+// circom itself is not available here: the result is self-consistent (every surviving constraint holds on the
+// renumbered witness, tests/) but its numbering is not calibrated against a circom-built file.
+// ---------------------------------------------------------------------------------------
+void Compiler::write_o1(const std::string& r1cs_path, const std::string& sym_path) {
+  Impl& m = *im;
+  const uint32_t n_wires = (uint32_t)m.sig_val.size() + 1;
+  const uint32_t n_keep = 1 + m.n_pub_out + m.n_pub_in + m.n_prv_in;  // wire 0 and the main IO: never eliminated
+  typedef std::vector<std::pair<uint32_t, U256>> LC;  // (wire, coefficient), sorted by wire, no zero coefficients
+  struct Con { LC a, b, c; bool dead = false; };
+  std::vector<Con> cons(m.rows.size());
+  for (size_t r = 0; r < m.rows.size(); r++) {
+    const RowRec& rr = m.rows[r];
+    uint64_t off = rr.off;
+    LC* parts[3] = {&cons[r].a, &cons[r].b, &cons[r].c};
+    uint32_t lens[3] = {rr.na, rr.nb, rr.nc};
+    for (int part = 0; part < 3; part++)
+      for (uint32_t t = 0; t < lens[part]; t++, off++) {
+        uint32_t sig = m.terms[off].first;
+        parts[part]->emplace_back(sig == 0xFFFFFFFFu ? 0u : m.sig2wire[sig], m.coefs[m.terms[off].second]);
+      }
+  }
+  std::vector<uint32_t> parent(n_wires);
+  for (uint32_t i = 0; i < n_wires; i++) parent[i] = i;
+  std::vector<uint8_t> is_const(n_wires, 0);
+  std::vector<U256> const_val(n_wires);
+  std::function<uint32_t(uint32_t)> find = [&](uint32_t x) { while (parent[x] != x) { parent[x] = parent[parent[x]]; x = parent[x]; } return x; };
+  auto normalise = [&](LC& lc) {
+    std::map<uint32_t, U256> acc;
+    for (auto& t : lc) {
+      uint32_t w = find(t.first);
+      if (w != 0 && is_const[w]) { acc[0] = fr_add(acc[0], fr_mul(t.second, const_val[w])); continue; }
+      acc[w] = fr_add(acc[w], t.second);
+    }
+    lc.clear();
+    for (auto& kv : acc) if (!kv.second.is_zero()) lc.emplace_back(kv.first, kv.second);
+  };
+  auto const_only = [](const LC& lc, U256& k) { if (lc.empty()) { k = U256(); return true; } if (lc.size() == 1 && lc[0].first == 0) { k = lc[0].second; return true; } return false; };
+  uint64_t n_alias = 0, n_constant = 0, n_trivial = 0;
+  for (int pass = 0; pass < 64; pass++) {
+    bool changed = false;
+    for (Con& cn : cons) {
+      if (cn.dead) continue;
+      normalise(cn.a); normalise(cn.b); normalise(cn.c);
+      // the linear form L = C - k B (A = k constant) or C - k A (B = k constant)
+      U256 k;
+      LC lin;
+      bool linear = false;
+      if (const_only(cn.a, k)) { linear = true; lin = cn.c; for (auto& t : cn.b) lin.emplace_back(t.first, fr_neg(fr_mul(k, t.second))); }
+      else if (const_only(cn.b, k)) { linear = true; lin = cn.c; for (auto& t : cn.a) lin.emplace_back(t.first, fr_neg(fr_mul(k, t.second))); }
+      if (!linear) continue;
+      normalise(lin);
+      if (lin.empty()) { cn.dead = true; n_trivial++; changed = true; continue; }
+      U256 c0;
+      size_t first = 0;
+      if (lin[0].first == 0) { c0 = lin[0].second; first = 1; }
+      const size_t nsig = lin.size() - first;
+      if (nsig == 1) {
+        // cx * x + c0 = 0  ->  x = -c0 / cx
+        uint32_t x = lin[first].first;
+        if (x < n_keep) continue;
+        is_const[x] = 1; const_val[x] = fr_mul(fr_neg(c0), fr_inv(lin[first].second));
+        cn.dead = true; n_constant++; changed = true;
+      } else if (nsig == 2 && c0.is_zero() && fr_add(lin[first].second, lin[first + 1].second).is_zero()) {
+        // cx * (x - y) = 0  ->  x = y: the signal that is not main IO (else the later one) is eliminated
+        uint32_t x = lin[first].first, y = lin[first + 1].first;   // x < y
+        if (y < n_keep) continue;                                  // both are main IO: the constraint stays
+        parent[y] = x;
+        cn.dead = true; n_alias++; changed = true;
+      }
+    }
+    if (!changed) break;
+  }
+  for (Con& cn : cons) if (!cn.dead) { normalise(cn.a); normalise(cn.b); normalise(cn.c); }
+  // surviving wires, renumbered in their original order
+  std::vector<int64_t> renum(n_wires, -1);
+  uint32_t n_new = 0;
+  for (uint32_t wv = 0; wv < n_wires; wv++)
+    if (wv < n_keep || (find(wv) == wv && !is_const[wv])) renum[wv] = n_new++;
+  uint32_t n_cons = 0;
+  for (Con& cn : cons) if (!cn.dead) n_cons++;
+  {
+    FILE* f = fopen(r1cs_path.c_str(), "wb");
+    if (!f) throw CompileError("cannot write " + r1cs_path);
+    auto u32 = [&](uint32_t v) { wr(f, &v, 4); };
+    auto u64 = [&](uint64_t v) { wr(f, &v, 8); };
+    wr(f, "r1cs", 4); u32(1); u32(3);
+    u32(1); u64(4 + 32 + 4 * 4 + 8 + 4);
+    u32(32); wr(f, FR_P.w, 32);
+    u32(n_new); u32(m.n_pub_out); u32(m.n_pub_in); u32(m.n_prv_in);
+    u64(n_wires); u32(n_cons);
+    uint64_t size = 0;
+    for (Con& cn : cons) if (!cn.dead) size += 12 + (uint64_t)(cn.a.size() + cn.b.size() + cn.c.size()) * 36;
+    u32(2); u64(size);
+    for (Con& cn : cons) {
+      if (cn.dead) continue;
+      const LC* parts[3] = {&cn.a, &cn.b, &cn.c};
+      for (int part = 0; part < 3; part++) {
+        u32((uint32_t)parts[part]->size());
+        for (auto& t : *parts[part]) { u32((uint32_t)renum[t.first]); wr(f, t.second.w, 32); }
+      }
+    }
+    // wire -> label map: the original (O0) wire of every surviving one
+    u32(3); u64((uint64_t)n_new * 8);
+    for (uint32_t wv = 0; wv < n_wires; wv++) if (renum[wv] >= 0) u64(wv);
+    fclose(f);
+  }
+  {
+    FILE* f = fopen(sym_path.c_str(), "w");
+    if (!f) throw CompileError("cannot write " + sym_path);
+    uint32_t comp_counter = 0;
+    std::function<void(Layout*, uint32_t, const std::string&)> walk = [&](Layout* lay, uint32_t base, const std::string& prefix) {
+      uint32_t cid = comp_counter++;
+      std::vector<std::pair<uint32_t, std::string>> lines;
+      for (int n : lay->order) {
+        SigInfo& s = lay->sigs[n];
+        uint32_t cnt = Impl::prod(s.dims);
+        std::vector<int> idx(s.dims.size(), 0);
+        for (uint32_t k = 0; k < cnt; k++) {
+          std::string name = prefix + "." + m.nm(n);
+          for (size_t d = 0; d < idx.size(); d++) name += "[" + std::to_string(idx[d]) + "]";
+          lines.emplace_back(base + s.off + k, name);
+          for (int d = (int)idx.size() - 1; d >= 0; d--) { if (++idx[d] < s.dims[d]) break; idx[d] = 0; }
+        }
+      }
+      std::sort(lines.begin(), lines.end());
+      for (auto& l : lines) {
+        uint32_t wv = m.sig2wire[l.first];
+        fprintf(f, "%u,%lld,%u,%s\n", wv, (long long)renum[wv], cid, l.second.c_str());
+      }
+      for (auto& ck : lay->child_order) {
+        Child& ch = lay->children[ck];
+        std::string nm2 = prefix + "." + m.nm(ck.first);
+        auto cd = lay->comp_dims.find(ck.first);
+        if (cd != lay->comp_dims.end() && !cd->second.empty()) {
+          std::vector<int> idx(cd->second.size());
+          int rem = ck.second;
+          for (int d = (int)cd->second.size() - 1; d >= 0; d--) { idx[d] = rem % cd->second[d]; rem /= cd->second[d]; }
+          for (int v : idx) nm2 += "[" + std::to_string(v) + "]";
+        }
+        walk(ch.lay, base + ch.rel_base, nm2);
+      }
+    };
+    walk(m.main_lay, 0, "main");
+    fclose(f);
+  }
+  m.o1_stats = fmt("{\"wires\":%u,\"constraints\":%u,\"wires_o0\":%u,\"constraints_o0\":%zu,\"aliases\":%llu,\"constants\":%llu,\"trivial\":%llu}",
+                   n_new, n_cons, n_wires, m.rows.size(), (unsigned long long)n_alias, (unsigned long long)n_constant, (unsigned long long)n_trivial);
+}
+std::string Compiler::o1_stats() const { return im->o1_stats; }
 
 void Compiler::write_sym(const std::string& path) {
   Impl& m = *im;

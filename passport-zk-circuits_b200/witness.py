@@ -150,12 +150,14 @@ REGISTER_IDENTITY_BITS = {"dg1": 1, "dg15": 1, "encapsulatedContent": 1, "signed
 
 
 COMPILE_STATIC_DEF_ROWS, COMPILE_NO_INTRINSICS, COMPILE_NO_TABLE_PROOFS, COMPILE_NO_VIEWS, COMPILE_NO_VECTORIZE = 1, 2, 4, 8, 16
+COMPILE_EMIT_O1 = 32
 
 
 def compile_circuit(main_path, out_prefix, input_bits=None, segment_ops=0, static_def_rows=False, intrinsics=True,
-                    table_proofs=True, views=True, vectorize=True):
+                    table_proofs=True, views=True, vectorize=True, emit_o1=False):
     """circom -> program (.pzkp) + .r1cs + .sym; the role of
-    `circom <file> --r1cs --wasm --sym` (/root/reference/circuits/scripts/compile-circuit.sh:34)."""
+    `circom <file> --r1cs --wasm --sym` (/root/reference/circuits/scripts/compile-circuit.sh:34).
+    emit_o1: also <prefix>.O1.r1cs / .O1.sym, the system after an O1-style simplification (pzk.h)."""
     L = lib()
     input_bits = input_bits or {}
     names = (ctypes.c_char_p * max(1, len(input_bits)))(*[k.encode() for k in input_bits])
@@ -164,7 +166,7 @@ def compile_circuit(main_path, out_prefix, input_bits=None, segment_ops=0, stati
     os.makedirs(os.path.dirname(os.path.abspath(out_prefix)), exist_ok=True)
     flags = ((COMPILE_STATIC_DEF_ROWS if static_def_rows else 0) | (0 if intrinsics else COMPILE_NO_INTRINSICS) |
              (0 if table_proofs else COMPILE_NO_TABLE_PROOFS) | (0 if views else COMPILE_NO_VIEWS) |
-             (0 if vectorize else COMPILE_NO_VECTORIZE))
+             (0 if vectorize else COMPILE_NO_VECTORIZE) | (COMPILE_EMIT_O1 if emit_o1 else 0))
     rc = L.pzk_compile_ex(os.fsencode(main_path), os.fsencode(out_prefix), names, widths, len(input_bits),
                           segment_ops, flags, err, len(err))
     if rc != 0:

@@ -587,3 +587,58 @@ def test_napi_shim_binds_only_exported_symbols(artifacts_dir):
                         "-I" + os.path.join(ROOT, "include"), "-DNODE_GYP_MODULE_NAME=pzk",
                         os.path.join(ROOT, "native", "pzk_napi.cc")], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+@pytest.mark.parametrize("name", ["t_mix", "smt80", "sha256_1", "query80"])
+def test_o1_simplified_system_is_consistent(artifacts_dir, name):
+    """PZK_COMPILE_EMIT_O1: `signal = signal` / `signal = constant` constraints removed by substitution, eliminated
+    signals dropped from the witness (the reference compiles its library circuits with `circom --O1`).  The witness of
+    the compiled program, re-indexed BY NAME through <name>.O1.sym, must satisfy every constraint of <name>.O1.r1cs;
+    main inputs and outputs keep their places; a corrupted surviving wire is caught by both systems."""
+    pre = os.path.join(artifacts_dir, name)
+    if not os.path.exists(pre + ".O1.r1cs"):
+        pytest.skip("O1 artefacts are built from the reference sources")
+    r0, r1 = formats.read_r1cs(pre + ".r1cs"), formats.read_r1cs(pre + ".O1.r1cs")
+    own, o1 = formats.read_sym(pre + ".sym"), formats.read_sym(pre + ".O1.sym")
+    assert r1["n_wires"] < r0["n_wires"] and len(r1["constraints"]) < len(r0["constraints"])
+    assert set(own) == set(o1)
+    n_io = 1 + r0["n_pub_out"] + r0["n_pub_in"] + r0["n_prv_in"]
+    for nm, w in own.items():
+        if w < n_io:
+            assert o1[nm] == w                                   # main IO is never eliminated or moved
+    kept = sorted(v for v in o1.values() if v >= 0)
+    assert kept == list(range(1, r1["n_wires"]))                 # a bijection onto the surviving wires
+    prog = oracle_ref.RefProgram(pre + ".pzkp")
+    from util import random_inputs
+    if name == "smt80":
+        keys = [5, 77]
+        rows = []
+        for key in keys:
+            vals = {"root": poseidon([key, key, 1]), "leaf": key, "key": key, "siblings": [0] * 80}
+            flat = []
+            for d in prog.meta["inputs"]:
+                v = vals[d["name"]]
+                flat += v if isinstance(v, list) else [v]
+            rows.append(ints_to_u64(flat))
+        inp = np.stack(rows)
+    elif name == "query80":
+        from passport_zk_circuits_b200.query_inputs import make_query_input
+        inp = W.pack_inputs_fast(prog.meta, [make_query_input(i, seed=5, selector=39) for i in range(2)])
+    else:
+        inp = random_inputs(prog.meta, 2, 5)
+    rng = np.random.default_rng(1)
+    for b in range(len(inp)):
+        st, fb, wit = prog.witness(inp[b])
+        w = u64_to_ints(wit)
+        w1 = [0] * r1["n_wires"]
+        w1[0] = 1
+        for nm, wi in o1.items():
+            if wi >= 0:
+                w1[wi] = w[own[nm]]
+        assert formats.wtns_check(r0, w)[0] == (st == 0)
+        assert formats.wtns_check(r1, w1)[0] == (st == 0)
+        if st == 0:
+            used = sorted({t[0] for c in r1["constraints"] for lc in c for t in lc} - {0})
+            victim = used[int(rng.integers(len(used)))]
+            w1[victim] = (w1[victim] + 1) % W.P
+            assert not formats.wtns_check(r1, w1)[0]

@@ -224,3 +224,46 @@ def test_external_sym_renumbers_the_witness(tmp_path):
         W.WitnessCalculator(prefix + ".pzkp", 0, external_sym=str(sym_path))
     calc.close()
     calc0.close()
+
+
+@pytest.mark.parametrize("name", ["t_mix", "smt80", "query80"])
+def test_o1_layout_on_the_device(name):
+    """The O1-simplified system (pzk.h PZK_COMPILE_EMIT_O1) end to end on the device: the program opened with
+    <name>.O1.sym produces witnesses in the O1 numbering, every row of <name>.O1.r1cs holds on them - through explicit
+    witnesses, a .wtns image and the device-resident hand-off - and tampered lanes fail in both systems."""
+    prefix = os.path.join(ROOT, "artifacts", name)
+    ref = oracle_ref.RefProgram(prefix + ".pzkp")
+    if name == "smt80":
+        from test_gpu_parity import smt_inputs
+        inp = smt_inputs(ref.meta, [31 + 5 * i for i in range(40)])
+        d = {x["name"]: x for x in ref.meta["inputs"]}
+        inp[9, d["siblings"]["offset"] + 79, 0] = 5                 # last sibling must be zero
+    elif name == "query80":
+        from passport_zk_circuits_b200.query_inputs import make_query_input
+        objs = [make_query_input(i, seed=9, selector=39) for i in range(40)]
+        objs[9]["idStateRoot"] = str(int(objs[9]["idStateRoot"]) ^ 1)
+        inp = W.pack_inputs_fast(ref.meta, objs)
+    else:
+        inp = random_inputs(ref.meta, 40, 3)
+        d = {x["name"]: x for x in ref.meta["inputs"]}
+        inp[9, d["x"]["offset"], 0] ^= np.uint64(1)
+    own = W.WitnessCalculator(prefix + ".pzkp", 0)
+    o1 = W.WitnessCalculator(prefix + ".pzkp", 0, external_sym=prefix + ".O1.sym", program_sym=prefix + ".sym")
+    r1 = W.R1cs(prefix + ".O1.r1cs", 0)
+    assert o1.n_wires == r1.n_wires < own.n_wires
+    a = own.calculateWitnessBatch(inp)
+    b = o1.calculateWitnessBatch(inp, export_lanes=range(40))
+    assert np.array_equal(a.status, b.status) and np.array_equal(a.public, b.public)
+    ok, first, _ = r1.check(b.witnesses)
+    assert np.array_equal(ok, (a.status & W.STATUS_CONSTRAINT) == 0)
+    o1.upload(inp)
+    ok2, _, _, _ = r1.check_circuit(o1, range(40))
+    assert np.array_equal(ok2, ok)
+    o1.set_digest(True)
+    o1.run(True)
+    dg = o1.download_digest()
+    for lane in (0, 9, 39):
+        assert np.array_equal(dg[lane], W.witness_digest(b.witnesses[lane]))
+    for c in (own, o1):
+        c.close()
+    r1.close()
