@@ -5,7 +5,9 @@ from passport_zk_circuits_b200 import witness as W
 from passport_zk_circuits_b200.passports import C3, PassportFactory
 name = sys.argv[1]; B = int(sys.argv[2])
 WAVES = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+DIGEST = len(sys.argv) > 4 and sys.argv[4] == 'digest'
 calc = W.WitnessCalculator(W.artifact(name), 0)
+if DIGEST: calc.set_digest(True)
 name = "c3" if name.startswith("c3") else name
 if WAVES: B = WAVES * calc.wave_lanes()
 print(name, 'wave', calc.wave_lanes(), 'B', B, 'wires', calc.n_wires, 'constraints', calc.n_constraints, calc.stats())
