@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <unordered_map>
@@ -128,6 +129,7 @@ int pzk_compile_ex(const char* main_circom_path, const char* out_prefix, const c
     pzk::CompileOptions opt;
     for (int i = 0; i < n_bits; i++) opt.input_bits[bits_names[i]] = bits_widths[i];
     if (segment_ops) opt.seg_ops = segment_ops;
+    if (const char* e = getenv("PZK_CELLS")) { int v = atoi(e); if (v >= 0 && v <= 128 && v % 4 == 0) opt.cells = (uint32_t)v; }  // tuning knob
     opt.def_rows_static = (flags & PZK_COMPILE_STATIC_DEF_ROWS) != 0;
     opt.intrinsics = (flags & PZK_COMPILE_NO_INTRINSICS) == 0;
     opt.table_rows_static = (flags & PZK_COMPILE_NO_TABLE_PROOFS) == 0;
@@ -697,8 +699,10 @@ static int run_batch(pzk_circuit* c, const RunOpts& o) {
         p.first_bad = c->d_first_bad + base;
         p.digest = fused ? 1 : 0; p.dig_tab = c->d_dig_tab; p.dig_state = c->d_dig_state; p.dig_stride = c->batch_cap;
         p.dig_lane_base = base; p.dig_smem_off = (u32)((size_t)c->h.reserved[1] * 8 * 128);
+        // the digest accumulators only take shared memory when they are used: the rest stays L1
+        const size_t smem = fused ? c->smem_bytes : (size_t)c->h.reserved[1] * 8 * 128;
         prof_begin(c, 0, ea, eb);
-        eval_kernel<<<grid, 128, c->smem_bytes, c->stream>>>(p);
+        eval_kernel<<<grid, 128, smem, c->stream>>>(p);
         prof_end(c, 0, ea, eb);
         if (c->prof) c->pending_seg.push_back((int)s);
       }
