@@ -9,7 +9,7 @@ The reference ships the constants as a 25k-line table
 (test/poseidon_constants.js).  They are not copied here: the round constants
 and the MDS matrix are re-derived from the Poseidon paper's Grain-LFSR
 parameter generator (field=1, sbox=0, n=254, t, RF, RP), which is how circomlib
-produced them.  tests/test_poseidon_host.py checks the derived tables against
+produced them.  tests/test_cpu_host.py::test_poseidon_constants_match_reference_tables checks the derived tables against
 the reference's tables when /root/reference is present.  The un-optimised
 permutation below yields the same digests as the reference's optimised one.
 """
