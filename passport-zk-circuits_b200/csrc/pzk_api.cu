@@ -367,6 +367,7 @@ static int remap_wires(pzk_circuit* c, const char* own_sym, const char* ext_sym)
     to[it->second] = kv.second;
     if (kv.second > max_w) max_w = kv.second;
   }
+  if (max_w >= (int64_t)c->h.n_wires) { set_err(c, "external .sym: witness index " + std::to_string(max_w) + " exceeds the program's " + std::to_string(c->h.n_wires) + " wires"); return PZK_EFORMAT; }
   const uint32_t n_new = (uint32_t)max_w + 1;
   std::vector<uint8_t> taken(n_new, 0);
   taken[0] = 1;
