@@ -34,7 +34,7 @@ extern "C" {
 #endif
 
 #define PZK_MAGIC 0x314b5a50u /* "PZK1" */
-#define PZK_VERSION 12u
+#define PZK_VERSION 13u
 
 /* ---- opcodes ------------------------------------------------------------ */
 enum PzkOpcode {
@@ -136,6 +136,12 @@ enum PzkOpcode {
   PZK_Z_FROM_U = 67, /* dst(Z) = a(U)                                                                          */
   PZK_Z_FROM_I = 68, /* dst(Z) = a(I), sign extended                                                            */
   PZK_Z_CONST = 69,  /* dst(Z) = fpool[a] (raw two's complement)                                                */
+  /* fused multiply-add: a product whose only reader is a sum and that is not a wire is computed inside the sum's record
+     (Poseidon's mix rows, the column sums of the RSA limb products).  Extension record {c, -, -, -}.                 */
+  PZK_F_MULADD = 70, /* dst = +-(a * b) +- c in Fr; b may be a pool constant (PZK_FLAG_B_POOL); imm16 bit 8 negates the
+                        product, bit 9 negates c                                                                     */
+  PZK_Z_MULADD = 71, /* dst = +-(a * b) +- c mod 2^256; imm16 = la | lb << 4 (as Z_MUL) | negate product << 8 |
+                        negate c << 9                                                                                */
   PZK_OPCODE_MAX = 80
 };
 

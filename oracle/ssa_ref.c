@@ -431,6 +431,18 @@ uint32_t pzk_ref_witness(const PzkRefProgram* p, const uint8_t* inputs, uint8_t*
         case PZK_Z_ADD: { uint64_t r[4]; add4(r, FA, FB); WRF(o->dst, r); break; }
         case PZK_Z_SUB: { uint64_t r[4]; sub4(r, FA, FB); WRF(o->dst, r); break; }
         case PZK_Z_MUL: { uint64_t r[4]; z_mul(r, FA, FB); WRF(o->dst, r); break; }
+        case PZK_F_MULADD: { /* +-(a b) +- c: imm16 bit 8 negates the product, bit 9 negates c */
+          uint64_t m[4], r[4];
+          fmul(m, FA, FB);
+          if (o->imm16 & 0x100) fsub(r, RDF(x->c), m); else if (o->imm16 & 0x200) fsub(r, m, RDF(x->c)); else fadd(r, m, RDF(x->c));
+          WRF(o->dst, r); break;
+        }
+        case PZK_Z_MULADD: {
+          uint64_t m[4], r[4];
+          z_mul(m, FA, FB);
+          if (o->imm16 & 0x100) sub4(r, RDF(x->c), m); else if (o->imm16 & 0x200) sub4(r, m, RDF(x->c)); else add4(r, m, RDF(x->c));
+          WRF(o->dst, r); break;
+        }
         case PZK_Z_FROM_U: { uint64_t w[4] = {UA, 0, 0, 0}; WRF(o->dst, w); break; }
         case PZK_Z_FROM_I: { uint64_t x_ = UA, sx = (uint64_t)((int64_t)x_ >> 63); uint64_t w[4] = {x_, sx, sx, sx}; WRF(o->dst, w); break; }
         case PZK_Z_CONST: WRF(o->dst, p->fpool + 4 * (uint64_t)o->a); break;

@@ -191,7 +191,7 @@ struct Compiler::Impl {
   std::vector<uint32_t> out_list;
   uint32_t n_u_slots = 0, n_f_slots = 0;
   std::vector<uint8_t> row_kind;  // per constraint: 0 run-time check, 1 alias, 2 table proof, 3 symbolic proof, 4 definitional
-  uint64_t n_static_rows = 0, n_def_rows = 0, n_table_rows = 0, n_symbolic_rows = 0, n_fused = 0, n_i64_rows = 0, n_int_rows = 0, n_field_rows = 0, eval_bytes = 0, check_bytes = 0, cache_hit_refs = 0, cache_miss_refs = 0;
+  uint64_t n_static_rows = 0, n_def_rows = 0, n_table_rows = 0, n_symbolic_rows = 0, n_fused = 0, n_fused_mac = 0, n_i64_rows = 0, n_int_rows = 0, n_field_rows = 0, eval_bytes = 0, check_bytes = 0, cache_hit_refs = 0, cache_miss_refs = 0;
   std::vector<uint32_t> seg_quads;
   uint32_t n_pub_out = 0, n_pub_in = 0, n_prv_in = 0;
   std::string meta_json;
@@ -2592,6 +2592,7 @@ void Compiler::Impl::backend() {
       case PZK_U_SEL: case PZK_F_SEL: f(o.a); f(o.b); f(o.c); return;
       case PZK_N_BIT: f(o.a); return;
       case PZK_F_CSEL: f(o.a); return;
+      case PZK_F_MULADD: case PZK_Z_MULADD: f(o.a); if (!(o.flags & PZK_FLAG_B_POOL)) f(o.b); f(o.c); return;
       default:
         f(o.a);
         if (!(o.flags & (PZK_FLAG_B_IMM | PZK_FLAG_B_POOL))) {
@@ -3033,6 +3034,44 @@ void Compiler::Impl::backend() {
     }
     f(canon(v));
   };
+  // ---- peephole: x +- (p * q) with a single-use product that is not a wire -> one F_MULADD / Z_MULADD record (the
+  // linear combinations of Poseidon's mix layers, the column sums of the big-integer products).  The product's
+  // dispatch, its store and the sum's re-load go away; the value of the sum is the same field / integer element.
+  if (opt.fuse_muladd) {
+    std::vector<uint32_t> uses(nv, 0), def_op(nv, 0xFFFFFFFFu);
+    std::vector<uint8_t> is_sig(nv, 0);
+    for (uint32_t v : sig_val) if (v) { is_sig[canon(v)] = 1; if (v < nv) is_sig[v] = 1; sig_words(v, [&](uint32_t w) { is_sig[w] = 1; }); }
+    for (size_t i = 0; i < nops; i++) if (keep[i]) {
+      for_operands(ops[i], [&](uint32_t v) { if (v != PZK_OPERAND_NONE) uses[v]++; });
+      for_defs(ops[i], [&](uint32_t d) { def_op[d] = (uint32_t)i; });
+    }
+    for (size_t r = 0; r < nrows; r++) if (!row_static[r]) row_values((uint32_t)r, [&](uint32_t v) { uses[v]++; });
+    auto product_of = [&](uint32_t v, int mul_opc) -> int64_t {
+      if (v >= nv || def_op[v] == 0xFFFFFFFFu || is_sig[v] || uses[v] != 1) return -1;
+      const OpRec& d = ops[def_op[v]];
+      if (d.opc != mul_opc || d.dst != v || (d.flags & (PZK_FLAG_EXT | PZK_FLAG_B_IMM))) return -1;
+      return (int64_t)def_op[v];
+    };
+    for (size_t i = 0; i < nops; i++) {
+      if (!keep[i]) continue;
+      OpRec& o = ops[i];
+      const bool fop = (o.opc == PZK_F_ADD || o.opc == PZK_F_SUB), zop = (o.opc == PZK_Z_ADD || o.opc == PZK_Z_SUB);
+      if ((!fop && !zop) || (o.flags & (PZK_FLAG_B_POOL | PZK_FLAG_B_IMM | PZK_FLAG_EXT))) continue;
+      const int mul_opc = fop ? PZK_F_MUL : PZK_Z_MUL;
+      const bool sub = (o.opc == PZK_F_SUB || o.opc == PZK_Z_SUB);
+      int64_t di; uint32_t c; bool neg_prod, neg_c;
+      if ((di = product_of(o.b, mul_opc)) >= 0) { c = o.a; neg_prod = sub; neg_c = false; }
+      else if ((di = product_of(o.a, mul_opc)) >= 0) { c = o.b; neg_prod = false; neg_c = sub; }
+      else continue;
+      const OpRec d = ops[(size_t)di];
+      keep[(size_t)di] = 0;
+      o.opc = fop ? PZK_F_MULADD : PZK_Z_MULADD;
+      o.flags = (uint8_t)(PZK_FLAG_EXT | (d.flags & PZK_FLAG_B_POOL));
+      o.imm16 = (uint16_t)((zop ? (d.imm16 & 0xff) : 0) | (neg_prod ? 0x100 : 0) | (neg_c ? 0x200 : 0));
+      o.a = d.a; o.b = d.b; o.c = c; o.d = PZK_OPERAND_NONE; o.e = 0; o.f = 0;
+      n_fused_mac++;
+    }
+  }
   // Fused witness digest (pzk_program.h, PZK_FLAG_DIG): an op whose result is a wire, or the word behind bit-field
   // views that are wires, is followed by a digest descriptor so that the evaluator can fold the value when it is
   // defined instead of storing and re-reading it.  Export entries the descriptor cannot carry (truth-table views
@@ -3413,6 +3452,8 @@ void Compiler::Impl::backend() {
         case PZK_N_BIT: case PZK_F_CSEL: case PZK_U_EXTRACT: case PZK_N_EXTRACT: has_dst = true; r.a = opnd(o.a); break;
         case PZK_U_LUT: case PZK_U_LUTV: case PZK_V_LUT: has_dst = true; r.a = opnd(o.a); r.b = opnd(o.b); ext_c = opnd(o.c); ext_d = opnd(o.d); break;
         case PZK_U_SEL: case PZK_F_SEL: has_dst = true; r.a = opnd(o.a); r.b = opnd(o.b); ext_c = opnd(o.c); break;
+        case PZK_F_MULADD: case PZK_Z_MULADD:
+          has_dst = true; r.a = opnd(o.a); if (!(o.flags & PZK_FLAG_B_POOL)) r.b = opnd(o.b); ext_c = opnd(o.c); break;
         default:
           has_dst = true; r.a = opnd(o.a);
           if (!(o.flags & (PZK_FLAG_B_IMM | PZK_FLAG_B_POOL))) {
@@ -3549,7 +3590,7 @@ void Compiler::Impl::build_meta() {
        ",\"f_inv\":" + std::to_string(stats->f_inv) + ",\"f_inv_real\":" + std::to_string(stats->f_inv_real) + ",\"f_other\":" + std::to_string(stats->f_other) +
        ",\"bigdiv\":" + std::to_string(stats->bigdiv) + ",\"modinv\":" + std::to_string(stats->modinv) + ",\"z_ops\":" + std::to_string(stats->z_ops) + ",\"z_mul\":" + std::to_string(stats->z_mul) + ",\"lut\":" + std::to_string(stats->lut) +
        ",\"op_records\":" + std::to_string(out_ops.size()) + ",\"segments\":" + std::to_string(segs.size()) +
-       ",\"static_rows\":" + std::to_string(n_static_rows) + ",\"def_rows\":" + std::to_string(n_def_rows) + ",\"table_rows\":" + std::to_string(n_table_rows) + ",\"symbolic_rows\":" + std::to_string(n_symbolic_rows) + ",\"view_rows\":" + std::to_string(n_view_rows) + ",\"range_rows\":" + std::to_string(n_range_rows) + ",\"vlut\":" + std::to_string(n_vlut) + ",\"vlut_lanes\":" + std::to_string(n_vlut_lanes) + ",\"view_signals\":" + std::to_string(n_view_sigs) + ",\"tabview_signals\":" + std::to_string(n_tabview_sigs) + ",\"extracts\":" + std::to_string(n_extracts) + ",\"fused_shladd\":" + std::to_string(n_fused) + ",\"i64_rows\":" + std::to_string(n_i64_rows) +
+       ",\"static_rows\":" + std::to_string(n_static_rows) + ",\"def_rows\":" + std::to_string(n_def_rows) + ",\"table_rows\":" + std::to_string(n_table_rows) + ",\"symbolic_rows\":" + std::to_string(n_symbolic_rows) + ",\"view_rows\":" + std::to_string(n_view_rows) + ",\"range_rows\":" + std::to_string(n_range_rows) + ",\"vlut\":" + std::to_string(n_vlut) + ",\"vlut_lanes\":" + std::to_string(n_vlut_lanes) + ",\"view_signals\":" + std::to_string(n_view_sigs) + ",\"tabview_signals\":" + std::to_string(n_tabview_sigs) + ",\"extracts\":" + std::to_string(n_extracts) + ",\"fused_shladd\":" + std::to_string(n_fused) + ",\"fused_muladd\":" + std::to_string(n_fused_mac) + ",\"i64_rows\":" + std::to_string(n_i64_rows) +
        ",\"int_rows\":" + std::to_string(n_int_rows) + ",\"field_rows\":" + std::to_string(n_field_rows) +
        ",\"eval_bytes\":" + std::to_string(eval_bytes) + ",\"check_bytes\":" + std::to_string(check_bytes) +
        ",\"cells\":" + std::to_string(opt.cells) + ",\"cache_hit_refs\":" + std::to_string(cache_hit_refs) +

@@ -63,16 +63,26 @@ __device__ __forceinline__ void sub_p(u64* a) {
   const u64 p[4] = {P0, P1, P2, P3};
   sub256(a, a, p);
 }
+// t < 2p (with `carry` the bit above the 256) -> t mod p.  Straight-line: neighbouring lanes almost never agree on
+// whether the subtraction is needed, so a branch would run both sides anyway and pay for the reconvergence.
+__device__ __forceinline__ void cond_sub_p(u64* t, u32 carry = 0) {
+  const u64 p[4] = {P0, P1, P2, P3};
+  u64 u[4];
+  const u32 br = sub256(u, t, p);
+  const bool take = carry || !br;
+  t[0] = take ? u[0] : t[0]; t[1] = take ? u[1] : t[1]; t[2] = take ? u[2] : t[2]; t[3] = take ? u[3] : t[3];
+}
 __device__ __forceinline__ void fr_add(u64* r, const u64* a, const u64* b) {
   u64 t[4];
   u32 c = add256(t, a, b);
-  if (c || geq_p(t)) sub_p(t);
+  cond_sub_p(t, c);
   r[0] = t[0]; r[1] = t[1]; r[2] = t[2]; r[3] = t[3];
 }
 __device__ __forceinline__ void fr_sub(u64* r, const u64* a, const u64* b) {
   u64 t[4];
-  u32 br = sub256(t, a, b);
-  if (br) { const u64 p[4] = {P0, P1, P2, P3}; add256(t, t, p); }
+  const u32 br = sub256(t, a, b);
+  const u64 p[4] = {br ? P0 : 0, br ? P1 : 0, br ? P2 : 0, br ? P3 : 0};
+  add256(t, t, p);
   r[0] = t[0]; r[1] = t[1]; r[2] = t[2]; r[3] = t[3];
 }
 __device__ __forceinline__ bool fr_is_zero(const u64* a) { return (a[0] | a[1] | a[2] | a[3]) == 0; }
@@ -144,7 +154,7 @@ __device__ __forceinline__ void fr_mul(u64* r64, const u64* a64, const u64* b64)
   u64 r[4];
 #pragma unroll
   for (int i = 0; i < 4; i++) r[i] = (u64)even[2 * i] | ((u64)even[2 * i + 1] << 32);
-  if (geq_p(r)) sub_p(r);  // operands < p < 2^254: the result is < 2p and fits 256 bits
+  cond_sub_p(r);  // operands < p < 2^254: the result is < 2p and fits 256 bits
   r64[0] = r[0]; r64[1] = r[1]; r64[2] = r[2]; r64[3] = r[3];
 }
 
@@ -190,7 +200,7 @@ __device__ __forceinline__ void fr_mul_plain(u64* r64, const u64* a64, const u64
   u64 r[4];
 #pragma unroll
   for (int i = 0; i < 4; i++) r[i] = (u64)t[2 * i] | ((u64)t[2 * i + 1] << 32);
-  if (t[8] || geq_p(r)) sub_p(r);
+  cond_sub_p(r, t[8]);
   r64[0] = r[0]; r64[1] = r[1]; r64[2] = r[2]; r64[3] = r[3];
 }
 

@@ -77,8 +77,10 @@ __device__ __forceinline__ void sts64(u32 addr, u64 v) { asm volatile("st.shared
 #define STD(d, v)                                                        \
   do {                                                                   \
     const u64 v__ = (v);                                                 \
-    if (!((d) & PZK_DST_OPTIONAL) || store_all) PST(Ul + (u64)PZK_DST_SLOT(d) * L, v__); \
-    if (PZK_DST_CELL(d)) sts64(cells + ((PZK_DST_CELL(d) - 1) << 10), v__); \
+    u32 d__ = (d);                                                       \
+    asm volatile("" : "+r"(d__));                                        \
+    if (!(d__ & PZK_DST_OPTIONAL) || store_all) PST(Ul + (u64)PZK_DST_SLOT(d__) * L, v__); \
+    if (PZK_DST_CELL(d__)) sts64(cells + ((PZK_DST_CELL(d__) - 1) << 10), v__); \
   } while (0)
 
 __device__ __forceinline__ void ldF(const u64* Fl, u64 L, u32 slot, u64* v) {
@@ -670,7 +672,7 @@ __device__ __forceinline__ void z_to_mont(u64* r, const u64* z) {
   } while (0)
 __device__ __forceinline__ void z_mul(u64& r0, u64& r1, u64& r2, u64& r3, u64 a0, u64 a1, u64 a2, u64 a3, u64 b0, u64 b1,
                                       u64 b2, u64 b3, u32 imm) {
-  const u32 la = imm & 15u, lb = imm >> 4;
+  const u32 la = imm & 15u, lb = (imm >> 4) & 15u;
   if (la == 1 && lb == 1) {  // 64 x 64: the limb products of the multipliers
     r0 = a0 * b0; r1 = __umul64hi(a0, b0); r2 = 0; r3 = 0;
     return;
@@ -696,10 +698,18 @@ __device__ __forceinline__ void z_mul(u64& r0, u64& r1, u64& r2, u64& r3, u64 a0
 
 // 7 CTAs of 128 lanes per SM (72 registers): measured best of 8 / 7 / 6 / 5 on the round-2 program (284 / 298 / 295 /
 // 280 k witnesses/s): one more warp-quartet of latency hiding is worth less than the spills of a 64-register budget
+// the lane index, read from the special registers at each use: kept as a loop-invariant variable the compiler
+// re-derives it at the top of every record
+__device__ __forceinline__ u64 lane_now() {
+  u32 c, n, t;
+  asm volatile("mov.u32 %0, %%ctaid.x;" : "=r"(c));
+  asm volatile("mov.u32 %0, %%ntid.x;" : "=r"(n));
+  asm volatile("mov.u32 %0, %%tid.x;" : "=r"(t));
+  return (u64)c * n + t;
+}
 __global__ void __launch_bounds__(128, 7) eval_kernel(EvalParams p) {
   extern __shared__ u64 cell_mem[];
-  const u64 lane = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (lane >= p.n_lanes) return;
+  if ((u64)blockIdx.x * blockDim.x + threadIdx.x >= p.n_lanes) return;
   // Blocked planes: the 128 lanes of a CTA own one contiguous region per plane, so the hot slots of
   // a CTA span a few 2 MB pages instead of one page per slot (the flat [slot][lane] layout was
   // page-walk bound: consecutive ops touch slots that are megabytes apart).
@@ -709,7 +719,7 @@ __global__ void __launch_bounds__(128, 7) eval_kernel(EvalParams p) {
   u64* Ul = p.U + (u64)blockIdx.x * p.n_u_slots * PZK_LANE_BLOCK + threadIdx.x;
   u64* Fl = p.F + (u64)blockIdx.x * p.n_f_slots * 4 * PZK_LANE_BLOCK + threadIdx.x;
   u32 st = 0;
-  unsigned long long bad = ~0ull;
+  u32 bad = 0xffffffffu;  // first failing row (row ids are 32-bit record words)
   // kernel parameters are copied into registers once: taking references to the parameter block
   // would push it to local memory and turn every use into an LDL
   const bool store_all = p.store_all != 0;
@@ -721,7 +731,8 @@ __global__ void __launch_bounds__(128, 7) eval_kernel(EvalParams p) {
   const u32 n_rec = (u32)p.n_rec;
   const bool digest = p.digest != 0;
   const ulonglong2* __restrict__ dig_tab = p.dig_tab;
-  const u32 dacc = (u32)__cvta_generic_to_shared(cell_mem) + p.dig_smem_off + threadIdx.x * 8;
+  const u32 dig_off = p.dig_smem_off;  // uniform: the accumulators sit behind the operand cache
+#define dacc (cells + dig_off)
   if (digest) {
 #pragma unroll
     for (int k = 0; k < DIG_ACC_WORDS; k++) sts64(dacc + 1024 * k, 0);
@@ -751,7 +762,22 @@ __global__ void __launch_bounds__(128, 7) eval_kernel(EvalParams p) {
       }
       continue;
     }
-    switch (opc) {
+    // the two groups that make up two thirds of the remaining records leave before the compare tree of the switch
+    if (opc - PZK_F_ADD <= 2u) {
+      u64 va[4], vb[4], r[4];
+      LDFA(va); LDFB(vb);
+      if (opc == PZK_F_ADD) fr_add(r, va, vb);
+      else if (opc == PZK_F_SUB) fr_sub(r, va, vb);
+      else fr_mul(r, va, vb);
+      STFD(r);
+    } else if (opc - PZK_Z_ADD <= 2u) {
+      u64 va[4], vb[4], r[4];
+      LDFA(va); LDFB(vb);
+      if (opc == PZK_Z_ADD) add256(r, va, vb);
+      else if (opc == PZK_Z_SUB) sub256(r, va, vb);
+      else z_mul(r[0], r[1], r[2], r[3], va[0], va[1], va[2], va[3], vb[0], vb[1], vb[2], vb[3], imm16);
+      STFD(r);
+    } else switch (opc) {
       case PZK_NOP: break;
       case PZK_U_CONST: STD(dst, ((u64)b << 32) | a); break;
       case PZK_U_ADD: STD(dst, LDO(a) + UBV); break;
@@ -825,20 +851,11 @@ __global__ void __launch_bounds__(128, 7) eval_kernel(EvalParams p) {
           bool ok;
           if (flags & PZK_FLAG_NBASE) { u64 t[4], r[4]; LDFA(t); shr256(r, t, imm16); ok = (r[0] | r[1] | r[2] | r[3]) == 0; }
           else ok = imm16 >= 64 || (LDO(a) >> imm16) == 0;
-          if (!ok && (unsigned long long)dst < bad) bad = dst;
+          if (!ok && dst < bad) bad = dst;
         }
         break;
       }
       case PZK_F_CONST: { u64 v[4]; ldPool(fpool, a, v); STFD(v); break; }
-      case PZK_F_ADD: case PZK_F_SUB: case PZK_F_MUL: {
-        u64 va[4], vb[4], r[4];
-        LDFA(va); LDFB(vb);
-        if (opc == PZK_F_ADD) fr_add(r, va, vb);
-        else if (opc == PZK_F_SUB) fr_sub(r, va, vb);
-        else fr_mul(r, va, vb);
-        STFD(r);
-        break;
-      }
       case PZK_F_NEG: { u64 va[4], r[4]; LDFA(va); fr_neg(r, va); STFD(r); break; }
       case PZK_F_INV: { u64 va[4], r[4]; LDFA(va); fr_inv(r, va); STFD(r); break; }
       case PZK_F_FROM_U: { u64 va[4] = {LDO(a), 0, 0, 0}, r[4]; fr_to_mont(r, va); STFD(r); break; }
@@ -869,12 +886,27 @@ __global__ void __launch_bounds__(128, 7) eval_kernel(EvalParams p) {
         if (flags & PZK_FLAG_ZSRC) z_to_mont(r, va); else { reduce_p(va); fr_to_mont(r, va); }
         STFD(r); break;
       }
-      case PZK_Z_ADD: case PZK_Z_SUB: case PZK_Z_MUL: {
+      case PZK_F_MULADD: {
+        FETCH_EXT();
         u64 va[4], vb[4], r[4];
         LDFA(va); LDFB(vb);
-        if (opc == PZK_Z_ADD) add256(r, va, vb);
-        else if (opc == PZK_Z_SUB) sub256(r, va, vb);
-        else z_mul(r[0], r[1], r[2], r[3], va[0], va[1], va[2], va[3], vb[0], vb[1], vb[2], vb[3], imm16);
+        fr_mul(r, va, vb);
+        ldFo(Fl, L, cells, NT, x.x, va);
+        if (imm16 & 0x100u) fr_sub(r, va, r);          // c - a b
+        else if (imm16 & 0x200u) fr_sub(r, r, va);     // a b - c
+        else fr_add(r, r, va);
+        STFD(r);
+        break;
+      }
+      case PZK_Z_MULADD: {
+        FETCH_EXT();
+        u64 va[4], vb[4], r[4];
+        LDFA(va); LDFB(vb);
+        z_mul(r[0], r[1], r[2], r[3], va[0], va[1], va[2], va[3], vb[0], vb[1], vb[2], vb[3], imm16);
+        ldFo(Fl, L, cells, NT, x.x, va);
+        if (imm16 & 0x100u) sub256(r, va, r);
+        else if (imm16 & 0x200u) sub256(r, r, va);
+        else add256(r, r, va);
         STFD(r);
         break;
       }
@@ -938,7 +970,7 @@ __global__ void __launch_bounds__(128, 7) eval_kernel(EvalParams p) {
           for (; k < tot; k++) I64_TERM(C)
 #undef I64_TERM
           const bool ok = (na == 0 || nab == na) ? (C == 0) : (A * B == C);
-          if (!ok && (unsigned long long)dst < bad) bad = dst;
+          if (!ok && dst < bad) bad = dst;
         }
         pc += b;
         break;
@@ -950,7 +982,7 @@ __global__ void __launch_bounds__(128, 7) eval_kernel(EvalParams p) {
           const u32 na = imm16, nb = a & 0xffffu, nc = a >> 16;
           bool ok = (opc == PZK_CHECK_INT) ? check_row_int(recs, na, nb, nc, list, Ul, L, cells, NT)
                                            : check_row_field(sc, recs, na, nb, nc, Ul, Fl, L, cells, NT);
-          if (!ok && (unsigned long long)dst < bad) bad = dst;
+          if (!ok && dst < bad) bad = dst;
         }
         pc += row_recs;
         break;
@@ -962,13 +994,13 @@ __global__ void __launch_bounds__(128, 7) eval_kernel(EvalParams p) {
       case PZK_IN_U: {
         if (p.in_table) {
           const uint2 e = __ldg(p.in_table + a);
-          const unsigned char* base = reinterpret_cast<const unsigned char*>(p.inputs) + (u64)lane * p.in_stride + e.y;
+          const unsigned char* base = reinterpret_cast<const unsigned char*>(p.inputs) + lane_now() * p.in_stride + e.y;
           u64 v = (e.x == 0) ? (u64)*base : *reinterpret_cast<const u64*>(base);
           if (imm16 < 64 && (v >> imm16) != 0) st |= PZK_LANE_INPUT_RANGE;
           STD(dst, v);
           break;
         }
-        const ulonglong2* ip = reinterpret_cast<const ulonglong2*>(p.inputs + ((u64)lane * p.n_inputs + a) * 4);
+        const ulonglong2* ip = reinterpret_cast<const ulonglong2*>(p.inputs + (lane_now() * p.n_inputs + a) * 4);
         ulonglong2 lo = ip[0], hi = ip[1];
         if ((lo.y | hi.x | hi.y) != 0 || (imm16 < 64 && (lo.x >> imm16) != 0)) st |= PZK_LANE_INPUT_RANGE;
         STD(dst, lo.x);
@@ -976,8 +1008,8 @@ __global__ void __launch_bounds__(128, 7) eval_kernel(EvalParams p) {
       }
       case PZK_IN_F: {
         const ulonglong2* ip = p.in_table
-            ? reinterpret_cast<const ulonglong2*>(reinterpret_cast<const unsigned char*>(p.inputs) + (u64)lane * p.in_stride + __ldg(p.in_table + a).y)
-            : reinterpret_cast<const ulonglong2*>(p.inputs + ((u64)lane * p.n_inputs + a) * 4);
+            ? reinterpret_cast<const ulonglong2*>(reinterpret_cast<const unsigned char*>(p.inputs) + lane_now() * p.in_stride + __ldg(p.in_table + a).y)
+            : reinterpret_cast<const ulonglong2*>(p.inputs + (lane_now() * p.n_inputs + a) * 4);
         ulonglong2 lo = ip[0], hi = ip[1];
         u64 v[4] = {lo.x, lo.y, hi.x, hi.y}, r[4];
         if (geq_p(v)) { st |= PZK_LANE_INPUT_RANGE; reduce_p(v); }
@@ -1002,7 +1034,7 @@ __global__ void __launch_bounds__(128, 7) eval_kernel(EvalParams p) {
   }
   if (digest) {
     // flush the accumulators to the per-lane carry-save state (pieces of 32 bits, see digest_kernel)
-    unsigned long long* stt = reinterpret_cast<unsigned long long*>(p.dig_state) + p.dig_lane_base + lane;
+    unsigned long long* stt = reinterpret_cast<unsigned long long*>(p.dig_state) + p.dig_lane_base + lane_now();
     const u64 S = p.dig_stride;
     const int piece0[DIG_ACC_WORDS] = {0, 2, 8, 10, 12, 14, 16, 18, 20, 22, 24, 26};
 #pragma unroll
@@ -1013,15 +1045,17 @@ __global__ void __launch_bounds__(128, 7) eval_kernel(EvalParams p) {
       if (hi) atomicAdd(stt + (u64)(piece0[k] + 1) * S, (unsigned long long)hi);
     }
   }
-  if (bad != ~0ull) {
+  if (bad != 0xffffffffu) {
     st |= PZK_LANE_CONSTRAINT;
+    const u64 lane = lane_now();
     if (bad < p.first_bad[lane]) p.first_bad[lane] = bad;
   }
-  if (st) p.status[lane] |= st;
+  if (st) p.status[lane_now()] |= st;
 }
 
 // ------------------------------------------------------------------------------------------
 // Export: entries (wire <- slot) of one segment for a list of lanes -> canonical 32-byte wires.
+#undef dacc
 // grid.x covers lanes (fast, coalesced plane reads), grid.y strides over entries.
 // ------------------------------------------------------------------------------------------
 struct ExportParams {

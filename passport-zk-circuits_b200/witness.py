@@ -582,7 +582,7 @@ def program_histogram(program_path: str) -> dict:
         elif opc == 37:
             n = int(lst[int(ops[pc, 2])])
             bjj_products += (2 * n - 1) * (13 + 4)      # 13 per projective addition, 1 prefix + 3 to normalise
-        elif opc == 66:                                 # Z_MUL: la x lb 64-bit limbs = 4 la lb 32-bit multiply-adds
+        elif opc in (66, 71):                           # Z_MUL / Z_MULADD: la x lb 64-bit limbs = 4 la lb 32-bit multiply-adds
             la, lb = (w >> 16) & 15, (w >> 20) & 15
             z_imad += 4 * la * lb if la and lb else 40
         if fl & 4:
@@ -595,10 +595,11 @@ def program_histogram(program_path: str) -> dict:
         pc += 1
     narrow = sum(v for k, v in hist.items() if k.startswith(("U_", "I_", "V_")) or k in ("N_BIT", "N_LOW", "N_FITS", "IN_U", "CHECK_I64", "CHECK_INT", "CHECK_RANGE",
                                                                                           "Z_ADD", "Z_SUB", "Z_FROM_U", "Z_FROM_I"))
-    fr_products = hist.get("F_MUL", 0) + bjj_products + quad_field_rows
-    return {"records": hist, "fr_products": fr_products, "explicit_f_mul": hist.get("F_MUL", 0),
+    explicit = hist.get("F_MUL", 0) + hist.get("F_MULADD", 0)
+    fr_products = explicit + bjj_products + quad_field_rows
+    return {"records": hist, "fr_products": fr_products, "explicit_f_mul": explicit,
             "intrinsic_products": bjj_products, "quadratic_field_rows": quad_field_rows, "narrow_records": narrow,
-            "z_mul_records": hist.get("Z_MUL", 0), "z_mul_imad": z_imad, "digest_descriptors": n_dig,
+            "z_mul_records": hist.get("Z_MUL", 0) + hist.get("Z_MULADD", 0), "z_mul_imad": z_imad, "digest_descriptors": n_dig,
             "algorithmic_imad": 136 * fr_products + z_imad + narrow}
 
 
