@@ -191,7 +191,7 @@ struct Compiler::Impl {
   std::vector<uint32_t> out_list;
   uint32_t n_u_slots = 0, n_f_slots = 0;
   std::vector<uint8_t> row_kind;  // per constraint: 0 run-time check, 1 alias, 2 table proof, 3 symbolic proof, 4 definitional
-  uint64_t n_static_rows = 0, n_def_rows = 0, n_table_rows = 0, n_symbolic_rows = 0, n_fused = 0, n_fused_mac = 0, n_i64_rows = 0, n_int_rows = 0, n_field_rows = 0, eval_bytes = 0, check_bytes = 0, cache_hit_refs = 0, cache_miss_refs = 0;
+  uint64_t n_static_rows = 0, n_def_rows = 0, n_table_rows = 0, n_symbolic_rows = 0, n_fused = 0, n_fused_mac = 0, n_dig_wide = 0, n_dig_macro = 0, n_i64_rows = 0, n_int_rows = 0, n_field_rows = 0, eval_bytes = 0, check_bytes = 0, cache_hit_refs = 0, cache_miss_refs = 0;
   std::vector<uint32_t> seg_quads;
   uint32_t n_pub_out = 0, n_pub_in = 0, n_prv_in = 0;
   std::string meta_json;
@@ -3086,10 +3086,14 @@ void Compiler::Impl::backend() {
         const ViewD& d = vw[v];
         uint32_t b = canon(d.base);
         const uint32_t width = (v_cls[b] == CLS_U) ? 64 : 256;
-        if ((uint32_t)d.n + d.k <= 64 && d.s < width) dig_work[b] = 1; else dig_global[b] = 1;
+        if ((uint32_t)d.n + d.k <= 64 && d.s < width) dig_work[b] = 1; else { dig_global[b] = 1; n_dig_wide++; }
       } else if (v < v_tabview.size() && v_tabview[v]) {
         sig_words(v, [&](uint32_t w) { dig_global[w] = 1; });
-      } else dig_work[canon(v)] = 1;
+      } else {
+        dig_work[canon(v)] = 1;
+        uint32_t dv = v_def[canon(v)];
+        if (dv < ops.size() && is_macro(ops[dv].opc)) n_dig_macro++;
+      }
     }
   }
   // ---- segments over kept ops (+ their rows)
@@ -3590,7 +3594,7 @@ void Compiler::Impl::build_meta() {
        ",\"f_inv\":" + std::to_string(stats->f_inv) + ",\"f_inv_real\":" + std::to_string(stats->f_inv_real) + ",\"f_other\":" + std::to_string(stats->f_other) +
        ",\"bigdiv\":" + std::to_string(stats->bigdiv) + ",\"modinv\":" + std::to_string(stats->modinv) + ",\"z_ops\":" + std::to_string(stats->z_ops) + ",\"z_mul\":" + std::to_string(stats->z_mul) + ",\"lut\":" + std::to_string(stats->lut) +
        ",\"op_records\":" + std::to_string(out_ops.size()) + ",\"segments\":" + std::to_string(segs.size()) +
-       ",\"static_rows\":" + std::to_string(n_static_rows) + ",\"def_rows\":" + std::to_string(n_def_rows) + ",\"table_rows\":" + std::to_string(n_table_rows) + ",\"symbolic_rows\":" + std::to_string(n_symbolic_rows) + ",\"view_rows\":" + std::to_string(n_view_rows) + ",\"range_rows\":" + std::to_string(n_range_rows) + ",\"vlut\":" + std::to_string(n_vlut) + ",\"vlut_lanes\":" + std::to_string(n_vlut_lanes) + ",\"view_signals\":" + std::to_string(n_view_sigs) + ",\"tabview_signals\":" + std::to_string(n_tabview_sigs) + ",\"extracts\":" + std::to_string(n_extracts) + ",\"fused_shladd\":" + std::to_string(n_fused) + ",\"fused_muladd\":" + std::to_string(n_fused_mac) + ",\"i64_rows\":" + std::to_string(n_i64_rows) +
+       ",\"static_rows\":" + std::to_string(n_static_rows) + ",\"def_rows\":" + std::to_string(n_def_rows) + ",\"table_rows\":" + std::to_string(n_table_rows) + ",\"symbolic_rows\":" + std::to_string(n_symbolic_rows) + ",\"view_rows\":" + std::to_string(n_view_rows) + ",\"range_rows\":" + std::to_string(n_range_rows) + ",\"vlut\":" + std::to_string(n_vlut) + ",\"vlut_lanes\":" + std::to_string(n_vlut_lanes) + ",\"view_signals\":" + std::to_string(n_view_sigs) + ",\"tabview_signals\":" + std::to_string(n_tabview_sigs) + ",\"extracts\":" + std::to_string(n_extracts) + ",\"fused_shladd\":" + std::to_string(n_fused) + ",\"fused_muladd\":" + std::to_string(n_fused_mac) + ",\"digest_wide_views\":" + std::to_string(n_dig_wide) + ",\"digest_macro_defs\":" + std::to_string(n_dig_macro) + ",\"i64_rows\":" + std::to_string(n_i64_rows) +
        ",\"int_rows\":" + std::to_string(n_int_rows) + ",\"field_rows\":" + std::to_string(n_field_rows) +
        ",\"eval_bytes\":" + std::to_string(eval_bytes) + ",\"check_bytes\":" + std::to_string(check_bytes) +
        ",\"cells\":" + std::to_string(opt.cells) + ",\"cache_hit_refs\":" + std::to_string(cache_hit_refs) +

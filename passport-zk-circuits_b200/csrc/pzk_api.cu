@@ -286,7 +286,14 @@ static void build_digest_program(pzk_circuit* c, std::vector<DigRec>& recs, std:
         out[0] = repk | (nbits ? 16u : 0u) | (nbits << 8);
         out[1] = (uint32_t)(uint64_t)w.plain; out[2] = (uint32_t)((uint64_t)w.plain >> 32);
         out[3] = (uint32_t)tab.size();
-        for (uint32_t b = 0; b < nbits; b++) tab.push_back(make_ulonglong2((u64)w.T[b], (u64)(w.T[b] >> 64)));
+        // nibble tables for the in-stream fold (dig_fold_table): 16 subset sums per four bits
+        for (uint32_t g = 0; 4 * g < nbits; g++)
+          for (uint32_t v = 0; v < 16; v++) {
+            u128 sum = 0;
+            for (uint32_t j = 0; j < 4; j++) if (((v >> j) & 1u) && 4 * g + j < nbits) sum += w.T[4 * g + j];
+            tab.push_back(make_ulonglong2((u64)sum, (u64)(sum >> 64)));
+          }
+        if (tab.size() > 0xffffffffull) set_err(c, "digest: table pool overflow");
         c->dig_fused_entries += w.n_entries;
         work.erase(it);
       }

@@ -597,20 +597,33 @@ __device__ __noinline__ void dig_acc_mac320(u32 acc, u64 c, u64 w0, u64 w1, u64 
   }
   sts64(acc + 4096, lds64(acc + 4096) + carry);
 }
+// Bit-field views of a word, folded four bits at a time: the table of a word holds, per nibble, the 16 sums of
+// the per-bit weights (pzk_api.cu, build_digest_program), so a nibble costs one indexed 16-byte load and one 128-bit
+// add instead of four loads and four predicated adds.  The lanes of a warp read up to 16 neighbouring entries (256 B).
 __device__ __noinline__ void dig_fold_table(u32 accN, const ulonglong2* T, u32 nbits, u64 W0, u64 W1, u64 W2, u64 W3) {
   u64 a0 = lds64(accN), a1 = lds64(accN + 1024);
-  const u64 Wv[4] = {W0, W1, W2, W3};
-  for (u32 j = 0; j * 64 < nbits; j++) {
-    u64 W = Wv[j];
-    const u32 nb = min(64u, nbits - j * 64);
-    const ulonglong2* Tj = T + j * 64;
-#pragma unroll 8
-    for (u32 b = 0; b < nb; b++) {
-      const ulonglong2 t = __ldg(Tj + b);
-      if (W & 1ull) asm("add.cc.u64 %0, %0, %2; addc.u64 %1, %1, %3;" : "+l"(a0), "+l"(a1) : "l"(t.x), "l"(t.y));
-      W >>= 1;
+  const u32 ng = (nbits + 3) >> 2;  // nibbles with a table
+#define DIG_NIBBLE(g)                                                                                        \
+  do {                                                                                                       \
+    const u32 off = (g) == 0 ? (w << 4) & 0xf0u : (g) == 1 ? w & 0xf0u : (w >> (4 * (g) - 4)) & 0xf0u;         \
+    const ulonglong2 t = __ldg(reinterpret_cast<const ulonglong2*>(Tb + off + 256 * (g)));                   \
+    asm("add.cc.u64 %0, %0, %2; addc.u64 %1, %1, %3;" : "+l"(a0), "+l"(a1) : "l"(t.x), "l"(t.y));            \
+  } while (0)
+  const unsigned char* Tb = reinterpret_cast<const unsigned char*>(T);
+  for (u32 h = 0; h * 8 < ng; h++, Tb += 8 * 256) {  // 32 bits of the word at a time
+    const u64 W = h < 2 ? W0 : h < 4 ? W1 : h < 6 ? W2 : W3;
+    const u32 w = (h & 1u) ? (u32)(W >> 32) : (u32)W;
+    const u32 n = ng - h * 8;
+    if (n >= 8) {
+      DIG_NIBBLE(0); DIG_NIBBLE(1); DIG_NIBBLE(2); DIG_NIBBLE(3); DIG_NIBBLE(4); DIG_NIBBLE(5); DIG_NIBBLE(6); DIG_NIBBLE(7);
+    } else {
+      for (u32 g = 0; g < n; g++) {
+        const ulonglong2 t = __ldg(reinterpret_cast<const ulonglong2*>(Tb + (((w >> (4 * g)) & 15u) << 4) + 256 * g));
+        asm("add.cc.u64 %0, %0, %2; addc.u64 %1, %1, %3;" : "+l"(a0), "+l"(a1) : "l"(t.x), "l"(t.y));
+      }
     }
   }
+#undef DIG_NIBBLE
   sts64(accN, a0); sts64(accN + 1024, a1);
 }
 
