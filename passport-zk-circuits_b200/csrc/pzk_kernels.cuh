@@ -79,6 +79,7 @@ __device__ __forceinline__ void sts64(u32 addr, u64 v) { asm volatile("st.shared
     const u64 v__ = (v);                                                 \
     u32 d__ = (d);                                                       \
     asm volatile("" : "+r"(d__));                                        \
+    rv0 = v__;                                                           \
     if (!(d__ & PZK_DST_OPTIONAL) || store_all) PST(Ul + (u64)PZK_DST_SLOT(d__) * L, v__); \
     if (PZK_DST_CELL(d__)) sts64(cells + ((PZK_DST_CELL(d__) - 1) << 10), v__); \
   } while (0)
@@ -568,20 +569,37 @@ __device__ __noinline__ void dig_acc_mac320(u32 acc, u64 c, u64 w0, u64 w1, u64 
   const u64 w[4] = {w0, w1, w2, w3};
   u64 carry = 0;
   if ((c >> 32) == 0) {
+    // 32-bit weight: one mad.lo carry chain over the eight 32-bit limbs, one mad.hi chain a limb higher
     const u32 c32 = (u32)c;
+    u32 a[10], v[8];
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-      const u64 pl = (u64)c32 * (u32)w[j], ph = (u64)c32 * (u32)(w[j] >> 32);  // c w = pl + ph 2^32
-      const u64 lo = pl + (ph << 32);
-      const u64 hi = (ph >> 32) + (lo < pl);
-      const u64 a = lds64(acc + 1024 * j);
-      u64 t = a + lo;
-      const u64 c1 = t < lo;
-      const u64 t2 = t + carry;
-      const u64 c2 = t2 < carry;
-      sts64(acc + 1024 * j, t2);
-      carry = hi + c1 + c2;
-    }
+    for (int j = 0; j < 5; j++) { const u64 t = lds64(acc + 1024 * j); a[2 * j] = (u32)t; a[2 * j + 1] = (u32)(t >> 32); }
+#pragma unroll
+    for (int j = 0; j < 4; j++) { v[2 * j] = (u32)w[j]; v[2 * j + 1] = (u32)(w[j] >> 32); }
+    asm("mad.lo.cc.u32 %0, %10, %11, %0;\n\t"
+        "madc.lo.cc.u32 %1, %10, %12, %1;\n\t"
+        "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
+        "madc.lo.cc.u32 %3, %10, %14, %3;\n\t"
+        "madc.lo.cc.u32 %4, %10, %15, %4;\n\t"
+        "madc.lo.cc.u32 %5, %10, %16, %5;\n\t"
+        "madc.lo.cc.u32 %6, %10, %17, %6;\n\t"
+        "madc.lo.cc.u32 %7, %10, %18, %7;\n\t"
+        "addc.cc.u32 %8, %8, 0;\n\t"
+        "addc.u32 %9, %9, 0;\n\t"
+        "mad.hi.cc.u32 %1, %10, %11, %1;\n\t"
+        "madc.hi.cc.u32 %2, %10, %12, %2;\n\t"
+        "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+        "madc.hi.cc.u32 %4, %10, %14, %4;\n\t"
+        "madc.hi.cc.u32 %5, %10, %15, %5;\n\t"
+        "madc.hi.cc.u32 %6, %10, %16, %6;\n\t"
+        "madc.hi.cc.u32 %7, %10, %17, %7;\n\t"
+        "madc.hi.cc.u32 %8, %10, %18, %8;\n\t"
+        "addc.u32 %9, %9, 0;"
+        : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]), "+r"(a[8]), "+r"(a[9])
+        : "r"(c32), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]));
+#pragma unroll
+    for (int j = 0; j < 5; j++) sts64(acc + 1024 * j, (u64)a[2 * j] | ((u64)a[2 * j + 1] << 32));
+    return;
   } else {
 #pragma unroll
     for (int j = 0; j < 4; j++) {
@@ -754,11 +772,12 @@ __global__ void __launch_bounds__(128, 7) eval_kernel(EvalParams p) {
     const uint4 w = __ldg(ops + pc);
     const u32 opc = w.x & 0xffu, flags = (w.x >> 8) & 0xffu, imm16 = w.x >> 16;
     const u32 dst = w.y, a = w.z, b = w.w;
+    u64 rv0 = 0, rv1 = 0, rv2 = 0, rv3 = 0;  // the value this record defines, for the digest fold behind it
 #define FETCH_EXT() const uint4 x = __ldg(ops + (++pc))
 #define UBV ((flags & PZK_FLAG_B_IMM) ? (u64)b : LDO(b))
 #define LDFA(v) ldFo(Fl, L, cells, NT, a, v)
 #define LDFB(v) do { if (flags & PZK_FLAG_B_POOL) ldPool(fpool, b, v); else ldFo(Fl, L, cells, NT, b, v); } while (0)
-#define STFD(v) stFd(Fl, L, cells, NT, dst, v, store_all)
+#define STFD(v) do { stFd(Fl, L, cells, NT, dst, v, store_all); rv0 = (v)[0]; rv1 = (v)[1]; rv2 = (v)[2]; rv3 = (v)[3]; } while (0)
     // U_ADD / U_MUL / U_AND / U_SHR / U_SHLADD are 57 % of the ops of the passport circuits (weighted bit sums, bit
     // extraction).  The compiler marks them with PZK_FLAG_FAST; testing the flag instead of the opcode keeps this
     // exit in front of the six-level compare tree the switch compiles to, and the four results are selected,
@@ -1035,14 +1054,7 @@ __global__ void __launch_bounds__(128, 7) eval_kernel(EvalParams p) {
     if (flags & PZK_FLAG_DIG) {
       // the value this op just defined, from its cache cell or its slot, folded into the digest
       const uint4 dg = __ldg(ops + (++pc));
-      if (digest && (dg.x & 15u)) {
-        const u32 cell = PZK_DST_CELL(dst);
-        u64 v[4] = {0, 0, 0, 0};
-        if ((dg.x & 15u) <= 2) v[0] = cell ? lds64(cells + ((cell - 1) << 10)) : PLD(Ul + (u64)PZK_DST_SLOT(dst) * L);
-        else if (cell) { const u32 c0 = cells + ((cell - 1) << 10); v[0] = lds64(c0); v[1] = lds64(c0 + 1024); v[2] = lds64(c0 + 2048); v[3] = lds64(c0 + 3072); }
-        else ldF(Fl, L, PZK_DST_SLOT(dst), v);
-        dig_fold(dacc, dig_tab, dg, v[0], v[1], v[2], v[3]);
-      }
+      if (digest && (dg.x & 15u)) dig_fold(dacc, dig_tab, dg, rv0, rv1, rv2, rv3);
     }
   }
   if (digest) {
