@@ -294,27 +294,35 @@ __device__ __forceinline__ int cmp256(const u64* a, const u64* b) {
   for (int i = 3; i >= 0; i--) { if (a[i] < b[i]) return -1; if (a[i] > b[i]) return 1; }
   return 0;
 }
+// 256-bit shifts by a run-time amount, on registers only: the limb move is two conditional swaps, not an indexed
+// array (which the compiler would put in local memory)
 __device__ __forceinline__ void shr256(u64* r, const u64* a, unsigned s) {
-  u64 t[4] = {0, 0, 0, 0};
-  if (s < 256) {
-    unsigned ws = s >> 6, bs = s & 63;
-    for (unsigned i = 0; i + ws < 4; i++) {
-      t[i] = a[i + ws] >> bs;
-      if (bs && i + ws + 1 < 4) t[i] |= a[i + ws + 1] << (64 - bs);
-    }
+  u64 x0 = a[0], x1 = a[1], x2 = a[2], x3 = a[3];
+  if (s >= 256) { x0 = x1 = x2 = x3 = 0; s = 0; }
+  if (s & 64) { x0 = x1; x1 = x2; x2 = x3; x3 = 0; }
+  if (s & 128) { x0 = x2; x1 = x3; x2 = 0; x3 = 0; }
+  const unsigned bs = s & 63;
+  if (bs) {
+    x0 = (x0 >> bs) | (x1 << (64 - bs));
+    x1 = (x1 >> bs) | (x2 << (64 - bs));
+    x2 = (x2 >> bs) | (x3 << (64 - bs));
+    x3 >>= bs;
   }
-  r[0] = t[0]; r[1] = t[1]; r[2] = t[2]; r[3] = t[3];
+  r[0] = x0; r[1] = x1; r[2] = x2; r[3] = x3;
 }
 __device__ __forceinline__ void shl256(u64* r, const u64* a, unsigned s) {
-  u64 t[4] = {0, 0, 0, 0};
-  if (s < 256) {
-    unsigned ws = s >> 6, bs = s & 63;
-    for (int i = 3; i >= (int)ws; i--) {
-      t[i] = a[i - ws] << bs;
-      if (bs && i - (int)ws - 1 >= 0) t[i] |= a[i - ws - 1] >> (64 - bs);
-    }
+  u64 x0 = a[0], x1 = a[1], x2 = a[2], x3 = a[3];
+  if (s >= 256) { x0 = x1 = x2 = x3 = 0; s = 0; }
+  if (s & 64) { x3 = x2; x2 = x1; x1 = x0; x0 = 0; }
+  if (s & 128) { x3 = x1; x2 = x0; x1 = 0; x0 = 0; }
+  const unsigned bs = s & 63;
+  if (bs) {
+    x3 = (x3 << bs) | (x2 >> (64 - bs));
+    x2 = (x2 << bs) | (x1 >> (64 - bs));
+    x1 = (x1 << bs) | (x0 >> (64 - bs));
+    x0 <<= bs;
   }
-  r[0] = t[0]; r[1] = t[1]; r[2] = t[2]; r[3] = t[3];
+  r[0] = x0; r[1] = x1; r[2] = x2; r[3] = x3;
 }
 __device__ __noinline__ void divmod256(const u64* a, const u64* b, u64* q, u64* m) {
   u64 qq[4] = {0, 0, 0, 0}, rr[4] = {0, 0, 0, 0};

@@ -563,20 +563,9 @@ __device__ __forceinline__ void dig_acc_add128(u32 acc, u64 lo, u64 hi) {  // ac
   asm("add.cc.u64 %0, %0, %2; addc.u64 %1, %1, %3;" : "+l"(a0), "+l"(a1) : "l"(lo), "l"(hi));
   sts64(acc, a0); sts64(acc + 1024, a1);
 }
-// acc (5 x 64 in shared memory) += c * w (4 x 64), c < 2^64, total < 2^320.  Almost every weight is the 32-bit c(i)
-// of a single wire: 32 x 32 products on the halves of the limbs (8 IMAD.WIDE) instead of 64 x 64 ones.
-__device__ __noinline__ void dig_acc_mac320(u32 acc, u64 c, u64 w0, u64 w1, u64 w2, u64 w3) {
-  const u64 w[4] = {w0, w1, w2, w3};
-  u64 carry = 0;
-  if ((c >> 32) == 0) {
-    // 32-bit weight: one mad.lo carry chain over the eight 32-bit limbs, one mad.hi chain a limb higher
-    const u32 c32 = (u32)c;
-    u32 a[10], v[8];
-#pragma unroll
-    for (int j = 0; j < 5; j++) { const u64 t = lds64(acc + 1024 * j); a[2 * j] = (u32)t; a[2 * j + 1] = (u32)(t >> 32); }
-#pragma unroll
-    for (int j = 0; j < 4; j++) { v[2 * j] = (u32)w[j]; v[2 * j + 1] = (u32)(w[j] >> 32); }
-    asm("mad.lo.cc.u32 %0, %10, %11, %0;\n\t"
+// a (10 x 32 bits) += c * v (8 x 32 bits): one mad.lo carry chain over the limbs, one mad.hi chain a limb higher
+__device__ __forceinline__ void mad320_chain(u32* a, u32 c32, const u32* v) {
+  asm("mad.lo.cc.u32 %0, %10, %11, %0;\n\t"
         "madc.lo.cc.u32 %1, %10, %12, %1;\n\t"
         "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
         "madc.lo.cc.u32 %3, %10, %14, %3;\n\t"
@@ -597,6 +586,21 @@ __device__ __noinline__ void dig_acc_mac320(u32 acc, u64 c, u64 w0, u64 w1, u64 
         "addc.u32 %9, %9, 0;"
         : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]), "+r"(a[8]), "+r"(a[9])
         : "r"(c32), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]));
+}
+// acc (5 x 64 in shared memory) += c * w (4 x 64), c < 2^64, total < 2^320.  Almost every weight is the 32-bit c(i)
+// of a single wire: 32 x 32 products on the halves of the limbs (8 IMAD.WIDE) instead of 64 x 64 ones.
+__device__ __noinline__ void dig_acc_mac320(u32 acc, u64 c, u64 w0, u64 w1, u64 w2, u64 w3) {
+  const u64 w[4] = {w0, w1, w2, w3};
+  u64 carry = 0;
+  if ((c >> 32) == 0) {
+    // 32-bit weight: one mad.lo carry chain over the eight 32-bit limbs, one mad.hi chain a limb higher
+    const u32 c32 = (u32)c;
+    u32 a[10], v[8];
+#pragma unroll
+    for (int j = 0; j < 5; j++) { const u64 t = lds64(acc + 1024 * j); a[2 * j] = (u32)t; a[2 * j + 1] = (u32)(t >> 32); }
+#pragma unroll
+    for (int j = 0; j < 4; j++) { v[2 * j] = (u32)w[j]; v[2 * j + 1] = (u32)(w[j] >> 32); }
+    mad320_chain(a, c32, v);
 #pragma unroll
     for (int j = 0; j < 5; j++) sts64(acc + 1024 * j, (u64)a[2 * j] | ((u64)a[2 * j + 1] << 32));
     return;
@@ -1308,18 +1312,14 @@ __device__ __forceinline__ void add128(u64* acc, u64 lo, u64 hi) {
 }
 // acc (5 x 64) += c * w (4 x 64), c < 2^32
 __device__ __forceinline__ void mac320(u64* acc, u32 c, const u64* w) {
-  u64 carry = 0;
+  u32 a[10], v[8];
 #pragma unroll
-  for (int j = 0; j < 4; j++) {
-    const u64 lo = (u64)c * w[j], hi = __umul64hi((u64)c, w[j]);
-    u64 t = acc[j] + lo;
-    u64 c1 = t < lo;
-    u64 t2 = t + carry;
-    u64 c2 = t2 < carry;
-    acc[j] = t2;
-    carry = hi + c1 + c2;  // hi < 2^32: no overflow
-  }
-  acc[4] += carry;
+  for (int j = 0; j < 5; j++) { a[2 * j] = (u32)acc[j]; a[2 * j + 1] = (u32)(acc[j] >> 32); }
+#pragma unroll
+  for (int j = 0; j < 4; j++) { v[2 * j] = (u32)w[j]; v[2 * j + 1] = (u32)(w[j] >> 32); }
+  mad320_chain(a, c, v);
+#pragma unroll
+  for (int j = 0; j < 5; j++) acc[j] = (u64)a[2 * j] | ((u64)a[2 * j + 1] << 32);
 }
 
 __global__ void __launch_bounds__(128) digest_kernel(DigestParams p) {
@@ -1367,7 +1367,7 @@ __global__ void __launch_bounds__(128) digest_kernel(DigestParams p) {
       case DIG_PLAIN_I: {
         const long long v = (long long)Ub[(u64)rw.y * PZK_LANE_BLOCK];
         const u64 mag = v < 0 ? (u64)(-v) : (u64)v;
-        add128(v < 0 ? accNeg : accN, (u64)rw.z * mag, __umul64hi((u64)rw.z, mag));
+        if (v < 0) add128(accNeg, (u64)rw.z * mag, __umul64hi((u64)rw.z, mag)); else add128(accN, (u64)rw.z * mag, __umul64hi((u64)rw.z, mag));
         break;
       }
       case DIG_PLAIN_F: {
@@ -1385,6 +1385,16 @@ __global__ void __launch_bounds__(128) digest_kernel(DigestParams p) {
       }
       case DIG_GENERIC: {
         const uint4 ew = __ldg(reinterpret_cast<const uint4*>(p.exports + rw.z));
+        if (ew.y == PZK_REF_TABVIEW) {  // a truth-table entry: a small signed integer, no 256-bit arithmetic
+          const u32* Lp = p.ex.list + ew.z;
+          const u32 n = __ldg(Lp);
+          u32 idx = 0;
+          for (u32 j = 0; j < n; j++) idx |= (u32)((Ub[(u64)__ldg(Lp + 1 + 2 * j) * PZK_LANE_BLOCK] >> __ldg(Lp + 2 + 2 * j)) & 1) << j;
+          const long long v = (long long)((u64)__ldg(Lp + 1 + 2 * n + 2 * idx) | ((u64)__ldg(Lp + 2 + 2 * n + 2 * idx) << 32));
+          const u64 mag = v < 0 ? (u64)(-v) : (u64)v;
+          if (v < 0) add128(accNeg, (u64)rw.w * mag, __umul64hi((u64)rw.w, mag)); else add128(accN, (u64)rw.w * mag, __umul64hi((u64)rw.w, mag));
+          break;
+        }
         u64 w[4];
         export_value(p.ex, ew, lane, w);
         mac320(accP, rw.w, w);
