@@ -110,7 +110,8 @@ def reference_circuits():
 OWN_CIRCUITS = {"t_mix": ("mix.circom", {"u": 16, "bits": 1}),
                 "t_bigdiv": ("bigdiv.circom", {"a": 64, "b": 64}),
                 "t_earlyret": ("earlyret.circom", {"v": 16, "a": 64, "b": 64, "c": 1}),
-                "t_modinv": ("modinv.circom", {"a": 64})}
+                "t_modinv": ("modinv.circom", {"a": 64}),
+                "t_muladd": ("muladd.circom", {"a": 64, "b": 64, "c": 64})}
 
 COMPILE_OPTS = {"c3_lean": {"static_def_rows": True},
                 "c3_allrows": {"table_proofs": False, "segment_ops": 16384},

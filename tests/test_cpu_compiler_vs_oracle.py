@@ -13,7 +13,8 @@ from conftest import REFERENCE, has_reference
 from util import ROOT, input_dict, ints_to_u64, random_inputs, u64_to_ints
 
 OWN = {"t_mix": "tests/circuits/mix.circom", "t_bigdiv": "tests/circuits/bigdiv.circom",
-       "t_earlyret": "tests/circuits/earlyret.circom", "t_modinv": "tests/circuits/modinv.circom"}
+       "t_earlyret": "tests/circuits/earlyret.circom", "t_modinv": "tests/circuits/modinv.circom",
+       "t_muladd": "tests/circuits/muladd.circom"}
 REF_SMALL = ["poseidon2", "sha256_1", "smt80", "babyjub"]
 
 
@@ -87,6 +88,24 @@ def test_own_early_returns_under_data_dependent_conditions(artifacts_dir):
     assert st & 1
 
 
+def test_own_fused_multiply_add_records(artifacts_dir):
+    """A product whose only reader is a sum and that is no signal is computed inside the sum's record
+    (pzk_program.h, PZK_F_MULADD / PZK_Z_MULADD): every sign combination, field and wide-integer class."""
+    from passport_zk_circuits_b200 import witness as W
+    prefix = os.path.join(artifacts_dir, "t_muladd")
+    hist = W.program_histogram(prefix + ".pzkp")["records"]
+    assert hist.get("F_MULADD", 0) >= 4 and hist.get("Z_MULADD", 0) >= 4, hist
+    prog = oracle_ref.RefProgram(prefix + ".pzkp")
+    inp = random_inputs(prog.meta, 12, 21)
+    d = {x["name"]: x for x in prog.meta["inputs"]}
+    inp[0, d["c"]["offset"], 0] = 0                                   # c - a b < 0 with c = 0
+    inp[1, d["a"]["offset"], 0] = np.uint64(0xFFFFFFFFFFFFFFFF)       # the largest 64 x 64 product
+    inp[1, d["b"]["offset"], 0] = np.uint64(0xFFFFFFFFFFFFFFFF)
+    inp[2, d["a"]["offset"], 0] = 0                                   # a b = 0
+    inp[3, d["x"]["offset"]] = 0                                      # x y = 0 in the field
+    compare(prefix, os.path.join(ROOT, OWN["t_muladd"]), inp)
+
+
 def modinv_inputs(meta, B, seed):
     inp = random_inputs(meta, B, seed)
     inp[0, :, 0] = 0                                                                # a == 0
@@ -155,7 +174,7 @@ def _failing_rows(r1cs, witness):
     return bad
 
 
-PROOF_CASES = ["t_mix", "t_earlyret", "t_bigdiv", "t_modinv", "poseidon2", "sha256_1", "babyjub", "smt80"]
+PROOF_CASES = ["t_mix", "t_earlyret", "t_bigdiv", "t_modinv", "t_muladd", "poseidon2", "sha256_1", "babyjub", "smt80"]
 
 
 @pytest.mark.parametrize("name", PROOF_CASES)

@@ -117,6 +117,20 @@ def test_early_returns_and_narrowed_limb():
     assert (np.delete(res.status, 9) == 0).all()
 
 
+def test_fused_multiply_add_records():
+    """PZK_F_MULADD / PZK_Z_MULADD in every sign combination against the C oracle evaluator, wire by wire."""
+    prog = oracle_ref.RefProgram(W.artifact("t_muladd"))
+    inp = random_inputs(prog.meta, 300, 21)
+    d = {x["name"]: x for x in prog.meta["inputs"]}
+    inp[0, d["c"]["offset"], 0] = 0
+    inp[1, d["a"]["offset"], 0] = np.uint64(0xFFFFFFFFFFFFFFFF)
+    inp[1, d["b"]["offset"], 0] = np.uint64(0xFFFFFFFFFFFFFFFF)
+    inp[2, d["a"]["offset"], 0] = 0
+    inp[3, d["x"]["offset"]] = 0
+    res = run_and_compare("t_muladd", inp)
+    assert (res.status == 0).all()
+
+
 def test_modinv_intrinsic():
     prog = oracle_ref.RefProgram(W.artifact("t_modinv"))
     inp = random_inputs(prog.meta, 300, 9)
