@@ -1275,7 +1275,8 @@ __global__ void __launch_bounds__(128) bjj_kernel(BjjParams p) {
 //   * a bit-field view ((W >> s) & (2^n - 1)) << k is a sum of bits of W times powers of two, so ALL the views of
 //     one word (110 per word on average in registerIdentity) collapse into one table of per-bit coefficients
 //     C_b = sum over views containing bit b of c(i) 2^(b - s + k), built when the program is loaded:
-//     one conditional 128-bit add per bit of the word instead of a shift / mask / multiply per wire;
+//     one conditional 128-bit add per bit of the word instead of a shift / mask / multiply per wire (this kernel),
+//     one indexed load + add per nibble from 16-entry subset-sum tables in the evaluator's fused fold (dig_fold_table);
 //   * a Montgomery value w R is accumulated as the 320-bit integer sum of c(i) * (w R) and reduced and converted
 //     ONCE per lane at the end (no from_mont per wire);
 //   * narrow words are 64 x 32 -> 96-bit products in a 128-bit accumulator (negative I-class values in a second).
