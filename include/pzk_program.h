@@ -34,7 +34,7 @@ extern "C" {
 #endif
 
 #define PZK_MAGIC 0x314b5a50u /* "PZK1" */
-#define PZK_VERSION 13u
+#define PZK_VERSION 14u
 
 /* ---- opcodes ------------------------------------------------------------ */
 enum PzkOpcode {
@@ -136,8 +136,9 @@ enum PzkOpcode {
   PZK_Z_FROM_U = 67, /* dst(Z) = a(U)                                                                          */
   PZK_Z_FROM_I = 68, /* dst(Z) = a(I), sign extended                                                            */
   PZK_Z_CONST = 69,  /* dst(Z) = fpool[a] (raw two's complement)                                                */
-  /* fused multiply-add: a product whose only reader is a sum and that is not a wire is computed inside the sum's record
-     (Poseidon's mix rows, the column sums of the RSA limb products).  Extension record {c, -, -, -}.                 */
+  /* fused multiply-add: a product whose only reader is a sum is computed inside the sum's record (Poseidon's mix rows,
+     the column sums of the RSA limb products).  Extension record {c, d, -, -}; a product that is a wire is a second
+     result of the record (PZK_FLAG_DST2 / PZK_FLAG_DIG2): neither stored for nor re-read by the sum.               */
   PZK_F_MULADD = 70, /* dst = +-(a * b) +- c in Fr; b may be a pool constant (PZK_FLAG_B_POOL); imm16 bit 8 negates the
                         product, bit 9 negates c                                                                     */
   PZK_Z_MULADD = 71, /* dst = +-(a * b) +- c mod 2^256; imm16 = la | lb << 4 (as Z_MUL) | negate product << 8 |
@@ -160,6 +161,11 @@ enum PzkOpcode {
                               that does not compute the digest skips it                                          */
 #define PZK_FLAG_ZSRC 64u  /* N_FROM_F / F_FROM_N: operand a is a Z value: dst(N) = canonical(a) = a < 0 ? p + a : a,
                               dst(F) = Montgomery(a)                                                           */
+
+#define PZK_FLAG_DST2 64u  /* F_MULADD / Z_MULADD: the product a * b is itself a wire whose only reader is this sum: it is a
+                              second result of the record, extension word .d = its destination (encoded like .dst)    */
+#define PZK_FLAG_DIG2 32u  /* F_MULADD / Z_MULADD with DST2: the digest descriptor of the product follows the extension
+                              record, in front of the descriptor of the sum (PZK_FLAG_DIG) if there is one             */
 
 typedef struct PzkOp {
   uint8_t opc;

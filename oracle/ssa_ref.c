@@ -434,12 +434,14 @@ uint32_t pzk_ref_witness(const PzkRefProgram* p, const uint8_t* inputs, uint8_t*
         case PZK_F_MULADD: { /* +-(a b) +- c: imm16 bit 8 negates the product, bit 9 negates c */
           uint64_t m[4], r[4];
           fmul(m, FA, FB);
+          if (o->flags & PZK_FLAG_DST2) memcpy(F + 4 * (uint64_t)PZK_DST_SLOT(x->d), m, 32); /* the product is a wire */
           if (o->imm16 & 0x100) fsub(r, RDF(x->c), m); else if (o->imm16 & 0x200) fsub(r, m, RDF(x->c)); else fadd(r, m, RDF(x->c));
           WRF(o->dst, r); break;
         }
         case PZK_Z_MULADD: {
           uint64_t m[4], r[4];
           z_mul(m, FA, FB);
+          if (o->flags & PZK_FLAG_DST2) memcpy(F + 4 * (uint64_t)PZK_DST_SLOT(x->d), m, 32);
           if (o->imm16 & 0x100) sub4(r, RDF(x->c), m); else if (o->imm16 & 0x200) sub4(r, m, RDF(x->c)); else add4(r, m, RDF(x->c));
           WRF(o->dst, r); break;
         }
@@ -609,6 +611,7 @@ uint32_t pzk_ref_witness(const PzkRefProgram* p, const uint8_t* inputs, uint8_t*
         default: fprintf(stderr, "ssa_ref: bad opcode %d\n", o->opc); abort();
       }
       if (o->flags & PZK_FLAG_DIG) pc++; /* digest descriptor of the device's fused witness digest: not an op */
+      if ((o->opc == PZK_F_MULADD || o->opc == PZK_Z_MULADD) && (o->flags & PZK_FLAG_DIG2)) pc++; /* the product's */
     }
     if (check_rows) {
       for (uint64_t r = sg->row_off; r < sg->row_off + sg->n_rows; r++) {

@@ -191,7 +191,7 @@ struct Compiler::Impl {
   std::vector<uint32_t> out_list;
   uint32_t n_u_slots = 0, n_f_slots = 0;
   std::vector<uint8_t> row_kind;  // per constraint: 0 run-time check, 1 alias, 2 table proof, 3 symbolic proof, 4 definitional
-  uint64_t n_static_rows = 0, n_def_rows = 0, n_table_rows = 0, n_symbolic_rows = 0, n_fused = 0, n_fused_mac = 0, n_dig_wide = 0, n_dig_macro = 0, n_i64_rows = 0, n_int_rows = 0, n_field_rows = 0, eval_bytes = 0, check_bytes = 0, cache_hit_refs = 0, cache_miss_refs = 0;
+  uint64_t n_static_rows = 0, n_def_rows = 0, n_table_rows = 0, n_symbolic_rows = 0, n_fused = 0, n_fused_mac = 0, n_fused_mac_wire = 0, n_dig_wide = 0, n_dig_macro = 0, n_i64_rows = 0, n_int_rows = 0, n_field_rows = 0, eval_bytes = 0, check_bytes = 0, cache_hit_refs = 0, cache_miss_refs = 0;
   std::vector<uint32_t> seg_quads;
   uint32_t n_pub_out = 0, n_pub_in = 0, n_prv_in = 0;
   std::string meta_json;
@@ -2612,6 +2612,7 @@ void Compiler::Impl::backend() {
       return;
     }
     f(o.dst);
+    if ((o.opc == PZK_F_MULADD || o.opc == PZK_Z_MULADD) && (o.flags & PZK_FLAG_DST2)) f(o.d);  // the product, a wire
   };
   // ---- sanity: every operand is defined by an earlier op (catches scheduling bugs of deferred ops)
   {
@@ -3046,8 +3047,15 @@ void Compiler::Impl::backend() {
       for_defs(ops[i], [&](uint32_t d) { def_op[d] = (uint32_t)i; });
     }
     for (size_t r = 0; r < nrows; r++) if (!row_static[r]) row_values((uint32_t)r, [&](uint32_t v) { uses[v]++; });
+    // words other signals are views of keep their own record (their descriptor carries the view table)
+    std::vector<uint8_t> is_view_base(nv, 0);
+    for (uint32_t v : sig_val) if (v) sig_words(v, [&](uint32_t w) { if (w != canon(v)) is_view_base[w] = 1; });
+    // a product that IS a wire (every limb product of the RSA multiplier, the S-box products of Poseidon) can move
+    // into the sum as well when the sum is its only reader - no other op, no run-time row: it becomes a second result
+    // of the record (PZK_FLAG_DST2), digested there, stored only when witnesses are exported
     auto product_of = [&](uint32_t v, int mul_opc) -> int64_t {
-      if (v >= nv || def_op[v] == 0xFFFFFFFFu || is_sig[v] || uses[v] != 1) return -1;
+      if (v >= nv || def_op[v] == 0xFFFFFFFFu || uses[v] != 1) return -1;
+      if (is_sig[v] && (!opt.fuse_muladd_wires || (v < vw.size() && (vw[v].base || v_tabview[v])) || is_view_base[v])) return -1;
       const OpRec& d = ops[def_op[v]];
       if (d.opc != mul_opc || d.dst != v || (d.flags & (PZK_FLAG_EXT | PZK_FLAG_B_IMM))) return -1;
       return (int64_t)def_op[v];
@@ -3065,11 +3073,13 @@ void Compiler::Impl::backend() {
       else continue;
       const OpRec d = ops[(size_t)di];
       keep[(size_t)di] = 0;
+      const bool wire = is_sig[d.dst] != 0;
       o.opc = fop ? PZK_F_MULADD : PZK_Z_MULADD;
-      o.flags = (uint8_t)(PZK_FLAG_EXT | (d.flags & PZK_FLAG_B_POOL));
+      o.flags = (uint8_t)(PZK_FLAG_EXT | (d.flags & PZK_FLAG_B_POOL) | (wire ? PZK_FLAG_DST2 : 0));
       o.imm16 = (uint16_t)((zop ? (d.imm16 & 0xff) : 0) | (neg_prod ? 0x100 : 0) | (neg_c ? 0x200 : 0));
-      o.a = d.a; o.b = d.b; o.c = c; o.d = PZK_OPERAND_NONE; o.e = 0; o.f = 0;
+      o.a = d.a; o.b = d.b; o.c = c; o.d = wire ? d.dst : PZK_OPERAND_NONE; o.e = 0; o.f = 0;
       n_fused_mac++;
+      if (wire) n_fused_mac_wire++;
     }
   }
   // Fused witness digest (pzk_program.h, PZK_FLAG_DIG): an op whose result is a wire, or the word behind bit-field
@@ -3104,7 +3114,7 @@ void Compiler::Impl::backend() {
     bool after_solo = false;
     for (size_t i = 0; i < nops; i++) {
       if (!keep[i]) continue;
-      uint64_t need = ((ops[i].flags & PZK_FLAG_EXT) ? 2 : 1) + ((ops[i].opc == PZK_V_LUT && (ops[i].flags & PZK_FLAG_W64)) ? 1 : 0) + ((opt.fused_digest && !is_macro(ops[i].opc) && ops[i].dst && ops[i].dst < dig_work.size() && dig_work[ops[i].dst]) ? 1 : 0);
+      uint64_t need = ((ops[i].flags & PZK_FLAG_EXT) ? 2 : 1) + ((ops[i].opc == PZK_V_LUT && (ops[i].flags & PZK_FLAG_W64)) ? 1 : 0) + ((opt.fused_digest && !is_macro(ops[i].opc) && ops[i].dst && ops[i].dst < dig_work.size() && dig_work[ops[i].dst]) ? 1 : 0) + ((opt.fused_digest && (ops[i].flags & PZK_FLAG_DST2) && (ops[i].opc == PZK_F_MULADD || ops[i].opc == PZK_Z_MULADD) && dig_work[ops[i].d]) ? 1 : 0);
       size_t q = rp;
       while (q < nrows && row_trigger[row_order[q]] == i) { if (!row_static[row_order[q]]) need += row_recs[row_order[q]]; q++; }
       // the BabyJubjub ladder gets a segment of its own: the runtime runs it as a dedicated kernel
@@ -3457,7 +3467,14 @@ void Compiler::Impl::backend() {
         case PZK_U_LUT: case PZK_U_LUTV: case PZK_V_LUT: has_dst = true; r.a = opnd(o.a); r.b = opnd(o.b); ext_c = opnd(o.c); ext_d = opnd(o.d); break;
         case PZK_U_SEL: case PZK_F_SEL: has_dst = true; r.a = opnd(o.a); r.b = opnd(o.b); ext_c = opnd(o.c); break;
         case PZK_F_MULADD: case PZK_Z_MULADD:
-          has_dst = true; r.a = opnd(o.a); if (!(o.flags & PZK_FLAG_B_POOL)) r.b = opnd(o.b); ext_c = opnd(o.c); break;
+          has_dst = true; r.a = opnd(o.a); if (!(o.flags & PZK_FLAG_B_POOL)) r.b = opnd(o.b); ext_c = opnd(o.c);
+          if (o.flags & PZK_FLAG_DST2) {
+            // the product: nobody reads it but the export / digest; stored only on request
+            ext_d = slot_of(o.d);
+            if (ext_d > 0x3fffffu) throw CompileError("too many live slots for the dst encoding");
+            if (pass == 1 && !needs_global[o.d]) ext_d |= PZK_DST_OPTIONAL;
+          }
+          break;
         default:
           has_dst = true; r.a = opnd(o.a);
           if (!(o.flags & (PZK_FLAG_B_IMM | PZK_FLAG_B_POOL))) {
@@ -3480,6 +3497,8 @@ void Compiler::Impl::backend() {
       }
       const bool with_dig = has_dst && !is_macro(o.opc) && o.dst < dig_work.size() && dig_work[o.dst];
       if (with_dig) r.flags |= PZK_FLAG_DIG;
+      const bool with_dig2 = (o.opc == PZK_F_MULADD || o.opc == PZK_Z_MULADD) && (o.flags & PZK_FLAG_DST2) && opt.fused_digest && dig_work[o.d];
+      if (with_dig2) r.flags |= PZK_FLAG_DIG2;
       out_ops.push_back(r);
       if (o.flags & PZK_FLAG_EXT) {
         PzkOpExt x; x.c = ext_c; x.d = ext_d; x.e = o.e; x.f = o.f;
@@ -3491,6 +3510,11 @@ void Compiler::Impl::backend() {
           memcpy(&raw, &y, sizeof raw);
           out_ops.push_back(raw);
         }
+      }
+      if (with_dig2) {  // the product's descriptor comes first: the evaluator folds it before it forms the sum
+        uint32_t wds[4] = {0u, 1u, slot_of(o.d), 0u};
+        PzkOp raw; memcpy(&raw, wds, 16);
+        out_ops.push_back(raw);
       }
       if (with_dig) {
         // descriptor: {0, plane (0 = U, 1 = F), slot, 0}; the runtime fills in weights / table when it loads the program
@@ -3594,7 +3618,7 @@ void Compiler::Impl::build_meta() {
        ",\"f_inv\":" + std::to_string(stats->f_inv) + ",\"f_inv_real\":" + std::to_string(stats->f_inv_real) + ",\"f_other\":" + std::to_string(stats->f_other) +
        ",\"bigdiv\":" + std::to_string(stats->bigdiv) + ",\"modinv\":" + std::to_string(stats->modinv) + ",\"z_ops\":" + std::to_string(stats->z_ops) + ",\"z_mul\":" + std::to_string(stats->z_mul) + ",\"lut\":" + std::to_string(stats->lut) +
        ",\"op_records\":" + std::to_string(out_ops.size()) + ",\"segments\":" + std::to_string(segs.size()) +
-       ",\"static_rows\":" + std::to_string(n_static_rows) + ",\"def_rows\":" + std::to_string(n_def_rows) + ",\"table_rows\":" + std::to_string(n_table_rows) + ",\"symbolic_rows\":" + std::to_string(n_symbolic_rows) + ",\"view_rows\":" + std::to_string(n_view_rows) + ",\"range_rows\":" + std::to_string(n_range_rows) + ",\"vlut\":" + std::to_string(n_vlut) + ",\"vlut_lanes\":" + std::to_string(n_vlut_lanes) + ",\"view_signals\":" + std::to_string(n_view_sigs) + ",\"tabview_signals\":" + std::to_string(n_tabview_sigs) + ",\"extracts\":" + std::to_string(n_extracts) + ",\"fused_shladd\":" + std::to_string(n_fused) + ",\"fused_muladd\":" + std::to_string(n_fused_mac) + ",\"digest_wide_views\":" + std::to_string(n_dig_wide) + ",\"digest_macro_defs\":" + std::to_string(n_dig_macro) + ",\"i64_rows\":" + std::to_string(n_i64_rows) +
+       ",\"static_rows\":" + std::to_string(n_static_rows) + ",\"def_rows\":" + std::to_string(n_def_rows) + ",\"table_rows\":" + std::to_string(n_table_rows) + ",\"symbolic_rows\":" + std::to_string(n_symbolic_rows) + ",\"view_rows\":" + std::to_string(n_view_rows) + ",\"range_rows\":" + std::to_string(n_range_rows) + ",\"vlut\":" + std::to_string(n_vlut) + ",\"vlut_lanes\":" + std::to_string(n_vlut_lanes) + ",\"view_signals\":" + std::to_string(n_view_sigs) + ",\"tabview_signals\":" + std::to_string(n_tabview_sigs) + ",\"extracts\":" + std::to_string(n_extracts) + ",\"fused_shladd\":" + std::to_string(n_fused) + ",\"fused_muladd\":" + std::to_string(n_fused_mac) + ",\"fused_muladd_wire_products\":" + std::to_string(n_fused_mac_wire) + ",\"digest_wide_views\":" + std::to_string(n_dig_wide) + ",\"digest_macro_defs\":" + std::to_string(n_dig_macro) + ",\"i64_rows\":" + std::to_string(n_i64_rows) +
        ",\"int_rows\":" + std::to_string(n_int_rows) + ",\"field_rows\":" + std::to_string(n_field_rows) +
        ",\"eval_bytes\":" + std::to_string(eval_bytes) + ",\"check_bytes\":" + std::to_string(check_bytes) +
        ",\"cells\":" + std::to_string(opt.cells) + ",\"cache_hit_refs\":" + std::to_string(cache_hit_refs) +

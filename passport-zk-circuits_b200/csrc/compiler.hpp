@@ -115,7 +115,8 @@ struct CompileOptions {
   bool table_rows_static = true;  // prove rows over table-valued wires by exhaustive evaluation
   bool symbolic_rows_static = true;  // prove rows by expanding their wires through the defining ops
   bool fuse_shladd = true;  // x + z * 2^k with a single-use product -> one U_SHLADD record
-  bool fuse_muladd = true;  // x +- p * q with a single-use product that is not a wire -> one F_MULADD / Z_MULADD record
+  bool fuse_muladd = true;  // x +- p * q with a single-use product -> one F_MULADD / Z_MULADD record
+  bool fuse_muladd_wires = true;  // ... also when the product is a wire (second result of the record, PZK_FLAG_DST2)
   bool def_rows_static = false;  // discharge the rows of `x <== e` (they hold by construction) at compile time
   bool views = true;     // bit-field views + bit-view row proofs (Num2Bits / GetLastNBits / running sums cost no ops)
   bool vectorize = true; // pack one-bit truth-table ops over rotated words into V_LUT records (needs views)

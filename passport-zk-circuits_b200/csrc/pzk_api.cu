@@ -262,17 +262,10 @@ static void build_digest_program(pzk_circuit* c, std::vector<DigRec>& recs, std:
       w.plain_rep = cls == 0 ? 1u : cls == 1 ? 2u : ((x.ref & PZK_REF_Z) ? 4u : 3u);
     }
     // descriptors of this segment's op stream claim the work of the value they follow
-    for (uint64_t pc = sg.op_off; pc < sg.op_off + sg.n_ops; pc++) {
-      const PzkOp& o = ops[pc];
-      const bool dig = (o.flags & PZK_FLAG_DIG) != 0;
-      if (o.opc == PZK_CHECK_INT || o.opc == PZK_CHECK_F || o.opc == PZK_CHECK_I64) { pc += o.b; continue; }
-      if (o.flags & PZK_FLAG_EXT) pc++;
-      if (o.opc == PZK_V_LUT && (o.flags & PZK_FLAG_W64)) pc++;
-      if (!dig) continue;
-      pc++;
+    auto claim = [&](uint64_t at) {
       c->dig_fused = true;
       uint32_t wds[4];
-      memcpy(wds, &ops[pc], 16);
+      memcpy(wds, &ops[at], 16);
       const uint64_t key = ((uint64_t)(wds[1] != 0) << 32) | wds[2];
       uint32_t out[4] = {0, 0, 0, 0};
       auto it = work.find(key);
@@ -297,7 +290,17 @@ static void build_digest_program(pzk_circuit* c, std::vector<DigRec>& recs, std:
         c->dig_fused_entries += w.n_entries;
         work.erase(it);
       }
-      memcpy(&ops[pc], out, 16);
+      memcpy(&ops[at], out, 16);
+    };
+    for (uint64_t pc = sg.op_off; pc < sg.op_off + sg.n_ops; pc++) {
+      const PzkOp& o = ops[pc];
+      const bool dig = (o.flags & PZK_FLAG_DIG) != 0;
+      const bool dig2 = (o.opc == PZK_F_MULADD || o.opc == PZK_Z_MULADD) && (o.flags & PZK_FLAG_DIG2);
+      if (o.opc == PZK_CHECK_INT || o.opc == PZK_CHECK_F || o.opc == PZK_CHECK_I64) { pc += o.b; continue; }
+      if (o.flags & PZK_FLAG_EXT) pc++;
+      if (o.opc == PZK_V_LUT && (o.flags & PZK_FLAG_W64)) pc++;
+      if (dig2) claim(++pc);  // the product of a fused multiply-add that is a wire: its descriptor comes first
+      if (dig) claim(++pc);
     }
     // what no descriptor claimed: records for digest_kernel
     for (auto& kv : work) {

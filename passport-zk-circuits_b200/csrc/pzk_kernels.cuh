@@ -781,6 +781,16 @@ __global__ void __launch_bounds__(128, 7) eval_kernel(EvalParams p) {
 #define UBV ((flags & PZK_FLAG_B_IMM) ? (u64)b : LDO(b))
 #define LDFA(v) ldFo(Fl, L, cells, NT, a, v)
 #define LDFB(v) do { if (flags & PZK_FLAG_B_POOL) ldPool(fpool, b, v); else ldFo(Fl, L, cells, NT, b, v); } while (0)
+// the product of a fused multiply-add that is itself a wire (PZK_FLAG_DST2): stored when witnesses are exported,
+// folded into the digest through its own descriptor (in front of the sum's)
+#define MULADD_PRODUCT(v)                                                                   \
+  do {                                                                                      \
+    if (!(x.y & PZK_DST_OPTIONAL) || store_all) stF(Fl, L, PZK_DST_SLOT(x.y), v);            \
+    if (flags & PZK_FLAG_DIG2) {                                                            \
+      const uint4 dg2 = __ldg(ops + (++pc));                                                \
+      if (digest && (dg2.x & 15u)) dig_fold(dacc, dig_tab, dg2, (v)[0], (v)[1], (v)[2], (v)[3]); \
+    }                                                                                       \
+  } while (0)
 #define STFD(v) do { stFd(Fl, L, cells, NT, dst, v, store_all); rv0 = (v)[0]; rv1 = (v)[1]; rv2 = (v)[2]; rv3 = (v)[3]; } while (0)
     // U_ADD / U_MUL / U_AND / U_SHR / U_SHLADD are 57 % of the ops of the passport circuits (weighted bit sums, bit
     // extraction).  The compiler marks them with PZK_FLAG_FAST; testing the flag instead of the opcode keeps this
@@ -927,6 +937,7 @@ __global__ void __launch_bounds__(128, 7) eval_kernel(EvalParams p) {
         u64 va[4], vb[4], r[4];
         LDFA(va); LDFB(vb);
         fr_mul(r, va, vb);
+        if (flags & PZK_FLAG_DST2) MULADD_PRODUCT(r);
         ldFo(Fl, L, cells, NT, x.x, va);
         if (imm16 & 0x100u) fr_sub(r, va, r);          // c - a b
         else if (imm16 & 0x200u) fr_sub(r, r, va);     // a b - c
@@ -939,6 +950,7 @@ __global__ void __launch_bounds__(128, 7) eval_kernel(EvalParams p) {
         u64 va[4], vb[4], r[4];
         LDFA(va); LDFB(vb);
         z_mul(r[0], r[1], r[2], r[3], va[0], va[1], va[2], va[3], vb[0], vb[1], vb[2], vb[3], imm16);
+        if (flags & PZK_FLAG_DST2) MULADD_PRODUCT(r);
         ldFo(Fl, L, cells, NT, x.x, va);
         if (imm16 & 0x100u) sub256(r, va, r);
         else if (imm16 & 0x200u) sub256(r, r, va);

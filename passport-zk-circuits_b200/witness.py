@@ -592,6 +592,9 @@ def program_histogram(program_path: str) -> dict:
         if fl & 128 and opc not in (56, 57, 58):      # digest descriptor behind the op (PZK_FLAG_DIG)
             pc += 1
             n_dig += 1
+        if opc in (70, 71) and fl & 32:               # fused multiply-add whose product is a wire (PZK_FLAG_DIG2)
+            pc += 1
+            n_dig += 1
         pc += 1
     narrow = sum(v for k, v in hist.items() if k.startswith(("U_", "I_", "V_")) or k in ("N_BIT", "N_LOW", "N_FITS", "IN_U", "CHECK_I64", "CHECK_INT", "CHECK_RANGE",
                                                                                           "Z_ADD", "Z_SUB", "Z_FROM_U", "Z_FROM_I"))
