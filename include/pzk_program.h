@@ -34,7 +34,7 @@ extern "C" {
 #endif
 
 #define PZK_MAGIC 0x314b5a50u /* "PZK1" */
-#define PZK_VERSION 14u
+#define PZK_VERSION 15u
 
 /* ---- opcodes ------------------------------------------------------------ */
 enum PzkOpcode {
@@ -162,6 +162,8 @@ enum PzkOpcode {
 #define PZK_FLAG_ZSRC 64u  /* N_FROM_F / F_FROM_N: operand a is a Z value: dst(N) = canonical(a) = a < 0 ? p + a : a,
                               dst(F) = Montgomery(a)                                                           */
 
+#define PZK_FLAG_A_U 16u   /* Z_MUL / Z_MULADD: operand a is a U word (zero-extended), read where it is instead of    */
+#define PZK_FLAG_B_U 1u    /* through a 256-bit Z_FROM_U copy; likewise operand b                                      */
 #define PZK_FLAG_DST2 64u  /* F_MULADD / Z_MULADD: the product a * b is itself a wire whose only reader is this sum: it is a
                               second result of the record, extension word .d = its destination (encoded like .dst)    */
 #define PZK_FLAG_DIG2 32u  /* F_MULADD / Z_MULADD with DST2: the digest descriptor of the product follows the extension

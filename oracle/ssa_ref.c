@@ -329,6 +329,10 @@ uint32_t pzk_ref_witness(const PzkRefProgram* p, const uint8_t* inputs, uint8_t*
 #define UB ((o->flags & PZK_FLAG_B_IMM) ? (uint64_t)o->b : RDU(o->b))
 #define FA RDF(o->a)
 #define FB ((o->flags & PZK_FLAG_B_POOL) ? (p->fpool + 4 * (uint64_t)o->b) : RDF(o->b))
+      /* Z_MUL / Z_MULADD: a factor may be a U word read in place (PZK_FLAG_A_U / PZK_FLAG_B_U) */
+      uint64_t zt_a[4] = {0, 0, 0, 0}, zt_b[4] = {0, 0, 0, 0};
+#define ZFA ((o->flags & PZK_FLAG_A_U) ? (zt_a[0] = RDU(o->a), (const uint64_t*)zt_a) : (const uint64_t*)FA)
+#define ZFB ((o->flags & PZK_FLAG_B_U) ? (zt_b[0] = RDU(o->b), (const uint64_t*)zt_b) : (const uint64_t*)FB)
       switch (o->opc) {
         case PZK_NOP: break;
         case PZK_U_CONST: WRU(o->dst, ((uint64_t)o->b << 32) | o->a); break;
@@ -430,7 +434,7 @@ uint32_t pzk_ref_witness(const PzkRefProgram* p, const uint8_t* inputs, uint8_t*
         }
         case PZK_Z_ADD: { uint64_t r[4]; add4(r, FA, FB); WRF(o->dst, r); break; }
         case PZK_Z_SUB: { uint64_t r[4]; sub4(r, FA, FB); WRF(o->dst, r); break; }
-        case PZK_Z_MUL: { uint64_t r[4]; z_mul(r, FA, FB); WRF(o->dst, r); break; }
+        case PZK_Z_MUL: { uint64_t r[4]; z_mul(r, ZFA, ZFB); WRF(o->dst, r); break; }
         case PZK_F_MULADD: { /* +-(a b) +- c: imm16 bit 8 negates the product, bit 9 negates c */
           uint64_t m[4], r[4];
           fmul(m, FA, FB);
@@ -440,7 +444,7 @@ uint32_t pzk_ref_witness(const PzkRefProgram* p, const uint8_t* inputs, uint8_t*
         }
         case PZK_Z_MULADD: {
           uint64_t m[4], r[4];
-          z_mul(m, FA, FB);
+          z_mul(m, ZFA, ZFB);
           if (o->flags & PZK_FLAG_DST2) memcpy(F + 4 * (uint64_t)PZK_DST_SLOT(x->d), m, 32);
           if (o->imm16 & 0x100) sub4(r, RDF(x->c), m); else if (o->imm16 & 0x200) sub4(r, m, RDF(x->c)); else add4(r, m, RDF(x->c));
           WRF(o->dst, r); break;

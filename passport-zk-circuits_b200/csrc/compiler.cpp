@@ -191,7 +191,7 @@ struct Compiler::Impl {
   std::vector<uint32_t> out_list;
   uint32_t n_u_slots = 0, n_f_slots = 0;
   std::vector<uint8_t> row_kind;  // per constraint: 0 run-time check, 1 alias, 2 table proof, 3 symbolic proof, 4 definitional
-  uint64_t n_static_rows = 0, n_def_rows = 0, n_table_rows = 0, n_symbolic_rows = 0, n_fused = 0, n_fused_mac = 0, n_fused_mac_wire = 0, n_dig_wide = 0, n_dig_macro = 0, n_i64_rows = 0, n_int_rows = 0, n_field_rows = 0, eval_bytes = 0, check_bytes = 0, cache_hit_refs = 0, cache_miss_refs = 0;
+  uint64_t n_static_rows = 0, n_def_rows = 0, n_table_rows = 0, n_symbolic_rows = 0, n_fused = 0, n_fused_mac = 0, n_fused_mac_wire = 0, n_z_u_operands = 0, n_dig_wide = 0, n_dig_macro = 0, n_i64_rows = 0, n_int_rows = 0, n_field_rows = 0, eval_bytes = 0, check_bytes = 0, cache_hit_refs = 0, cache_miss_refs = 0;
   std::vector<uint32_t> seg_quads;
   uint32_t n_pub_out = 0, n_pub_in = 0, n_prv_in = 0;
   std::string meta_json;
@@ -2593,6 +2593,7 @@ void Compiler::Impl::backend() {
       case PZK_N_BIT: f(o.a); return;
       case PZK_F_CSEL: f(o.a); return;
       case PZK_F_MULADD: case PZK_Z_MULADD: f(o.a); if (!(o.flags & PZK_FLAG_B_POOL)) f(o.b); f(o.c); return;
+      case PZK_Z_MUL: f(o.a); if (!(o.flags & PZK_FLAG_B_POOL)) f(o.b); return;  // bit 0 is PZK_FLAG_B_U here, not B_IMM
       default:
         f(o.a);
         if (!(o.flags & (PZK_FLAG_B_IMM | PZK_FLAG_B_POOL))) {
@@ -3081,6 +3082,31 @@ void Compiler::Impl::backend() {
       n_fused_mac++;
       if (wire) n_fused_mac_wire++;
     }
+    // Z products read 64-bit factors where they are - a U word in the narrow plane or its cache cell - instead of
+    // through the 256-bit copy Z_FROM_U makes (the limbs of the RSA operands: 32 bytes per read became 8)
+    for (size_t i = 0; i < nops; i++) {
+      if (!keep[i]) continue;
+      OpRec& o = ops[i];
+      if (o.opc != PZK_Z_MUL && o.opc != PZK_Z_MULADD) continue;
+      auto narrow_src = [&](uint32_t v, uint32_t& src) -> bool {
+        if (v >= nv || def_op[v] == 0xFFFFFFFFu || !keep[def_op[v]] || is_sig[v]) return false;
+        const OpRec& d = ops[def_op[v]];
+        if (d.opc != PZK_Z_FROM_U || d.dst != v) return false;
+        src = d.a;
+        return true;
+      };
+      uint32_t src;
+      if (narrow_src(o.a, src)) {
+        const uint32_t old = o.a;
+        o.a = src; o.flags |= PZK_FLAG_A_U; uses[src]++; n_z_u_operands++;
+        if (--uses[old] == 0) keep[def_op[old]] = 0;
+      }
+      if (!(o.flags & PZK_FLAG_B_POOL) && narrow_src(o.b, src)) {
+        const uint32_t old = o.b;
+        o.b = src; o.flags |= PZK_FLAG_B_U; uses[src]++; n_z_u_operands++;
+        if (--uses[old] == 0) keep[def_op[old]] = 0;
+      }
+    }
   }
   // Fused witness digest (pzk_program.h, PZK_FLAG_DIG): an op whose result is a wire, or the word behind bit-field
   // views that are wires, is followed by a digest descriptor so that the evaluator can fold the value when it is
@@ -3466,6 +3492,7 @@ void Compiler::Impl::backend() {
         case PZK_N_BIT: case PZK_F_CSEL: case PZK_U_EXTRACT: case PZK_N_EXTRACT: has_dst = true; r.a = opnd(o.a); break;
         case PZK_U_LUT: case PZK_U_LUTV: case PZK_V_LUT: has_dst = true; r.a = opnd(o.a); r.b = opnd(o.b); ext_c = opnd(o.c); ext_d = opnd(o.d); break;
         case PZK_U_SEL: case PZK_F_SEL: has_dst = true; r.a = opnd(o.a); r.b = opnd(o.b); ext_c = opnd(o.c); break;
+        case PZK_Z_MUL: has_dst = true; r.a = opnd(o.a); if (!(o.flags & PZK_FLAG_B_POOL)) r.b = opnd(o.b); break;
         case PZK_F_MULADD: case PZK_Z_MULADD:
           has_dst = true; r.a = opnd(o.a); if (!(o.flags & PZK_FLAG_B_POOL)) r.b = opnd(o.b); ext_c = opnd(o.c);
           if (o.flags & PZK_FLAG_DST2) {
@@ -3618,7 +3645,7 @@ void Compiler::Impl::build_meta() {
        ",\"f_inv\":" + std::to_string(stats->f_inv) + ",\"f_inv_real\":" + std::to_string(stats->f_inv_real) + ",\"f_other\":" + std::to_string(stats->f_other) +
        ",\"bigdiv\":" + std::to_string(stats->bigdiv) + ",\"modinv\":" + std::to_string(stats->modinv) + ",\"z_ops\":" + std::to_string(stats->z_ops) + ",\"z_mul\":" + std::to_string(stats->z_mul) + ",\"lut\":" + std::to_string(stats->lut) +
        ",\"op_records\":" + std::to_string(out_ops.size()) + ",\"segments\":" + std::to_string(segs.size()) +
-       ",\"static_rows\":" + std::to_string(n_static_rows) + ",\"def_rows\":" + std::to_string(n_def_rows) + ",\"table_rows\":" + std::to_string(n_table_rows) + ",\"symbolic_rows\":" + std::to_string(n_symbolic_rows) + ",\"view_rows\":" + std::to_string(n_view_rows) + ",\"range_rows\":" + std::to_string(n_range_rows) + ",\"vlut\":" + std::to_string(n_vlut) + ",\"vlut_lanes\":" + std::to_string(n_vlut_lanes) + ",\"view_signals\":" + std::to_string(n_view_sigs) + ",\"tabview_signals\":" + std::to_string(n_tabview_sigs) + ",\"extracts\":" + std::to_string(n_extracts) + ",\"fused_shladd\":" + std::to_string(n_fused) + ",\"fused_muladd\":" + std::to_string(n_fused_mac) + ",\"fused_muladd_wire_products\":" + std::to_string(n_fused_mac_wire) + ",\"digest_wide_views\":" + std::to_string(n_dig_wide) + ",\"digest_macro_defs\":" + std::to_string(n_dig_macro) + ",\"i64_rows\":" + std::to_string(n_i64_rows) +
+       ",\"static_rows\":" + std::to_string(n_static_rows) + ",\"def_rows\":" + std::to_string(n_def_rows) + ",\"table_rows\":" + std::to_string(n_table_rows) + ",\"symbolic_rows\":" + std::to_string(n_symbolic_rows) + ",\"view_rows\":" + std::to_string(n_view_rows) + ",\"range_rows\":" + std::to_string(n_range_rows) + ",\"vlut\":" + std::to_string(n_vlut) + ",\"vlut_lanes\":" + std::to_string(n_vlut_lanes) + ",\"view_signals\":" + std::to_string(n_view_sigs) + ",\"tabview_signals\":" + std::to_string(n_tabview_sigs) + ",\"extracts\":" + std::to_string(n_extracts) + ",\"fused_shladd\":" + std::to_string(n_fused) + ",\"fused_muladd\":" + std::to_string(n_fused_mac) + ",\"fused_muladd_wire_products\":" + std::to_string(n_fused_mac_wire) + ",\"z_u_operands\":" + std::to_string(n_z_u_operands) + ",\"digest_wide_views\":" + std::to_string(n_dig_wide) + ",\"digest_macro_defs\":" + std::to_string(n_dig_macro) + ",\"i64_rows\":" + std::to_string(n_i64_rows) +
        ",\"int_rows\":" + std::to_string(n_int_rows) + ",\"field_rows\":" + std::to_string(n_field_rows) +
        ",\"eval_bytes\":" + std::to_string(eval_bytes) + ",\"check_bytes\":" + std::to_string(check_bytes) +
        ",\"cells\":" + std::to_string(opt.cells) + ",\"cache_hit_refs\":" + std::to_string(cache_hit_refs) +

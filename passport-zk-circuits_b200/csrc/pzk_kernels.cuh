@@ -818,7 +818,9 @@ __global__ void __launch_bounds__(128, 7) eval_kernel(EvalParams p) {
       STFD(r);
     } else if (opc - PZK_Z_ADD <= 2u) {
       u64 va[4], vb[4], r[4];
-      LDFA(va); LDFB(vb);
+      // Z_MUL: a factor may be a U word read in place (PZK_FLAG_A_U / PZK_FLAG_B_U; never set on Z_ADD / Z_SUB)
+      if (flags & PZK_FLAG_A_U) { va[0] = LDO(a); va[1] = va[2] = va[3] = 0; } else LDFA(va);
+      if (flags & PZK_FLAG_B_U) { vb[0] = LDO(b); vb[1] = vb[2] = vb[3] = 0; } else LDFB(vb);
       if (opc == PZK_Z_ADD) add256(r, va, vb);
       else if (opc == PZK_Z_SUB) sub256(r, va, vb);
       else z_mul(r[0], r[1], r[2], r[3], va[0], va[1], va[2], va[3], vb[0], vb[1], vb[2], vb[3], imm16);
@@ -948,7 +950,8 @@ __global__ void __launch_bounds__(128, 7) eval_kernel(EvalParams p) {
       case PZK_Z_MULADD: {
         FETCH_EXT();
         u64 va[4], vb[4], r[4];
-        LDFA(va); LDFB(vb);
+        if (flags & PZK_FLAG_A_U) { va[0] = LDO(a); va[1] = va[2] = va[3] = 0; } else LDFA(va);
+        if (flags & PZK_FLAG_B_U) { vb[0] = LDO(b); vb[1] = vb[2] = vb[3] = 0; } else LDFB(vb);
         z_mul(r[0], r[1], r[2], r[3], va[0], va[1], va[2], va[3], vb[0], vb[1], vb[2], vb[3], imm16);
         if (flags & PZK_FLAG_DST2) MULADD_PRODUCT(r);
         ldFo(Fl, L, cells, NT, x.x, va);
