@@ -94,8 +94,10 @@ def test_own_fused_multiply_add_records(artifacts_dir):
     from passport_zk_circuits_b200 import witness as W
     prefix = os.path.join(artifacts_dir, "t_muladd")
     hist = W.program_histogram(prefix + ".pzkp")["records"]
-    assert hist.get("F_MULADD", 0) >= 4 and hist.get("Z_MULADD", 0) >= 4, hist
+    assert hist.get("F_MULADD", 0) >= 5 and hist.get("Z_MULADD", 0) >= 6, hist
     prog = oracle_ref.RefProgram(prefix + ".pzkp")
+    assert prog.meta["stats"]["fused_muladd_wire_products"] >= 3     # fp, zp, zq: second results (PZK_FLAG_DST2)
+    assert prog.meta["stats"]["z_u_operands"] >= 6                   # 64-bit factors read as U words in place
     inp = random_inputs(prog.meta, 12, 21)
     d = {x["name"]: x for x in prog.meta["inputs"]}
     inp[0, d["c"]["offset"], 0] = 0                                   # c - a b < 0 with c = 0
