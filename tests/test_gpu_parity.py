@@ -117,6 +117,18 @@ def test_early_returns_and_narrowed_limb():
     assert (np.delete(res.status, 9) == 0).all()
 
 
+def test_program_of_another_format_version_is_refused(tmp_path):
+    """The record semantics change with the format version (pzk_program.h PZK_VERSION): a stale program must be
+    refused when it is opened, not mis-executed."""
+    import struct
+    blob = bytearray(open(W.artifact("t_mix"), "rb").read())
+    struct.pack_into("<I", blob, 4, struct.unpack_from("<I", blob, 4)[0] - 1)
+    stale = tmp_path / "stale.pzkp"
+    stale.write_bytes(bytes(blob))
+    with pytest.raises(W.PzkError, match="magic/version"):
+        W.WitnessCalculator(str(stale), device=0)
+
+
 def test_fused_multiply_add_records():
     """PZK_F_MULADD / PZK_Z_MULADD in every sign combination against the C oracle evaluator, wire by wire."""
     prog = oracle_ref.RefProgram(W.artifact("t_muladd"))
