@@ -596,6 +596,8 @@ def program_histogram(program_path: str) -> dict:
             pc += 1
             n_dig += 1
         pc += 1
+    if pc != n_rec:
+        raise PzkError(f"{program_path}: the record walk ends at {pc}, the program has {n_rec} records")
     narrow = sum(v for k, v in hist.items() if k.startswith(("U_", "I_", "V_")) or k in ("N_BIT", "N_LOW", "N_FITS", "IN_U", "CHECK_I64", "CHECK_INT", "CHECK_RANGE",
                                                                                           "Z_ADD", "Z_SUB", "Z_FROM_U", "Z_FROM_I"))
     explicit = hist.get("F_MUL", 0) + hist.get("F_MULADD", 0)

@@ -561,6 +561,18 @@ def test_malformed_r1cs_and_wtns_are_format_errors_not_wild_reads(artifacts_dir,
     assert L.pzk_wtns_check(r1, bytes(bad), len(bad), 0, ctypes.byref(v), ctypes.byref(fb), err, len(err)) == -7
 
 
+def test_every_program_walks_to_its_last_record(artifacts_dir):
+    """Extension records, digest descriptors (of the result and of a fused product) and the term records of the
+    rows are all counted in the headers they follow (pzk_program.h): a walk over the op stream of every built
+    program must end exactly on the last record, and its descriptors must be as many as the compiler counted."""
+    names = [f[:-5] for f in sorted(os.listdir(artifacts_dir)) if f.endswith(".pzkp")]
+    assert "t_mix" in names and "t_muladd" in names
+    for name in names:
+        h = W.program_histogram(os.path.join(artifacts_dir, name + ".pzkp"))    # raises when the walk overruns
+        assert h["digest_descriptors"] > 0, name
+        assert "PZK_OPCODE_MAX" not in h["records"] and not any(k.isdigit() for k in h["records"]), (name, h["records"].keys())
+
+
 def test_witness_digest_host_restatement_matches_the_c_weights():
     L = W.lib()
     k = W.digest_weights(1000)
