@@ -133,7 +133,7 @@ struct Ctx {  // one template instance being executed (or nullptr inside functio
   Comp* comp = nullptr;
 };
 
-struct RowRec { uint64_t off; uint32_t na, nb, nc; bool by_def = false; };
+struct RowRec { uint64_t off; uint32_t na, nb, nc; bool by_def = false; int32_t line = 0, file = -1, tname = -1; };
 
 struct Compiler::Impl {
   SourceUnit unit;
@@ -1076,6 +1076,8 @@ struct Compiler::Impl {
     else { r.na = r.nb = 0; }
     push_lin(negc, r.nc);
     r.by_def = by_def;
+    if (at) { r.line = at->line; r.file = at->file; }
+    r.tname = cur_tname;
     rows.push_back(r);
   }
 
@@ -3728,6 +3730,40 @@ void Compiler::write_rowkinds(const std::string& path) {
   FILE* f = fopen(path.c_str(), "wb");
   if (!f) throw CompileError("cannot write " + path);
   wr(f, im->row_kind.data(), im->row_kind.size());
+  fclose(f);
+}
+
+// <prefix>.rowsrc: where the constraints that are checked at run time come from (template, file, line) - what the
+// circom runtime prints behind "Assert Failed." ("Error in template X line: N").  Binary, little endian:
+//   "PZKS" u32 n_files {u32 len, bytes}* u32 n_templates {u32 len, bytes}* u32 n_entries {u32 row, u32 line, u16 file, u16 template}*
+// Rows discharged at compile time cannot fail and are left out.
+void Compiler::write_rowsrc(const std::string& path) {
+  FILE* f = fopen(path.c_str(), "wb");
+  if (!f) throw CompileError("cannot write " + path);
+  auto u32w = [&](uint32_t v) { wr(f, &v, 4); };
+  auto strw = [&](const std::string& t) { u32w((uint32_t)t.size()); wr(f, t.data(), t.size()); };
+  wr(f, "PZKS", 4);
+  u32w((uint32_t)im->unit.files.size());
+  for (auto& t : im->unit.files) strw(t);
+  std::vector<int32_t> tids; std::unordered_map<int32_t, uint16_t> tix;
+  for (size_t r = 0; r < im->rows.size(); r++) {
+    if (r < im->row_kind.size() && im->row_kind[r]) continue;
+    int32_t t = im->rows[r].tname;
+    if (!tix.count(t)) { tix[t] = (uint16_t)tids.size(); tids.push_back(t); }
+  }
+  if (tids.size() > 0xffff) throw CompileError("too many templates for the .rowsrc encoding");
+  u32w((uint32_t)tids.size());
+  for (int32_t t : tids) strw(t >= 0 ? im->unit.names.str(t) : std::string("?"));
+  uint32_t n = 0;
+  for (size_t r = 0; r < im->rows.size(); r++) if (!(r < im->row_kind.size() && im->row_kind[r])) n++;
+  u32w(n);
+  for (size_t r = 0; r < im->rows.size(); r++) {
+    if (r < im->row_kind.size() && im->row_kind[r]) continue;
+    const RowRec& rr = im->rows[r];
+    u32w((uint32_t)r); u32w((uint32_t)rr.line);
+    uint16_t fi = (uint16_t)(rr.file >= 0 ? rr.file : 0xffff), ti = tix[rr.tname];
+    wr(f, &fi, 2); wr(f, &ti, 2);
+  }
   fclose(f);
 }
 

@@ -140,6 +140,7 @@ class Compiler {
   void write_r1cs(const std::string& path);
   void write_sym(const std::string& path);
   void write_rowkinds(const std::string& path);
+  void write_rowsrc(const std::string& path);  // source location of every run-time constraint
   void write_o1(const std::string& r1cs_path, const std::string& sym_path);  // O1-simplified constraint system + .sym
   std::string o1_stats() const;
   CompileStats stats;

@@ -143,6 +143,7 @@ int pzk_compile_ex(const char* main_circom_path, const char* out_prefix, const c
     cc.write_r1cs(p + ".r1cs");
     cc.write_sym(p + ".sym");
     cc.write_rowkinds(p + ".rowkind");
+    cc.write_rowsrc(p + ".rowsrc");
     if (flags & PZK_COMPILE_EMIT_O1) cc.write_o1(p + ".O1.r1cs", p + ".O1.sym");
   } catch (std::exception& e) {
     set_err(err, err_len, e.what());

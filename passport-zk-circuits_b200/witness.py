@@ -19,6 +19,7 @@ import json
 import lzma
 import os
 import subprocess
+from struct import error as struct_error
 from dataclasses import dataclass
 
 import numpy as np
@@ -174,6 +175,44 @@ def compile_circuit(main_path, out_prefix, input_bits=None, segment_ops=0, stati
     return out_prefix + ".pzkp"
 
 
+def constraint_source(program_path, index):
+    """(template, file, line) of a constraint that is checked at run time, from <prefix>.rowsrc written by
+    pzk_compile - what the circom runtime prints behind "Assert Failed." (witness_calculator.js: "Error in template
+    X line: N").  None when the file is missing or the row is one the compiler discharged (those cannot fail)."""
+    import struct
+    program_path = os.fsdecode(program_path)
+    base = program_path[:-5] if program_path.endswith(".pzkp") else program_path
+    path = base + ".rowsrc"
+    if index is None or index < 0 or not os.path.exists(path):
+        return None
+    blob = open(path, "rb").read()
+    if blob[:4] != b"PZKS":
+        return None
+    pos = 4
+
+    def strings(pos):
+        n = struct.unpack_from("<I", blob, pos)[0]
+        pos += 4
+        out = []
+        for _ in range(n):
+            ln = struct.unpack_from("<I", blob, pos)[0]
+            out.append(blob[pos + 4:pos + 4 + ln].decode(errors="replace"))
+            pos += 4 + ln
+        return out, pos
+    files, pos = strings(pos)
+    templates, pos = strings(pos)
+    n = struct.unpack_from("<I", blob, pos)[0]
+    pos += 4
+    ent = np.frombuffer(blob, dtype=np.dtype([("row", "<u4"), ("line", "<u4"), ("file", "<u2"), ("tmpl", "<u2")]),
+                        count=n, offset=pos)
+    k = int(np.searchsorted(ent["row"], index))
+    if k >= n or int(ent["row"][k]) != index:
+        return None
+    e = ent[k]
+    fname = files[int(e["file"])] if int(e["file"]) < len(files) else "?"
+    return templates[int(e["tmpl"])], fname, int(e["line"])
+
+
 def pack_artifact(program_path):
     """xz-compress a program for transport (artifacts/ travels with the repo snapshot)."""
     with open(program_path, "rb") as f, lzma.open(program_path + ".xz", "wb", preset=1) as g:
@@ -308,6 +347,7 @@ class WitnessCalculator:
         are then numbered after it (pzk_circuit_open_ex); program_sym defaults to the .sym next to the program."""
         self._L = lib()
         self._h = ctypes.c_void_p()
+        self._program_path = program_path
         if external_sym is not None:
             if program_sym is None:
                 base = program_path[:-5] if program_path.endswith(".pzkp") else program_path
@@ -378,7 +418,12 @@ class WitnessCalculator:
         if st & STATUS_BIGDIV:
             raise PzkError("Assert Failed. long division precondition violated (status 8)")
         if st & (STATUS_ASSERT | STATUS_CONSTRAINT):
-            raise PzkError(f"Assert Failed. (status {st}, first failing constraint {fb})")
+            try:
+                src = constraint_source(self._program_path, fb) if st & STATUS_CONSTRAINT else None
+            except (OSError, ValueError, IndexError, struct_error):
+                src = None   # a damaged side file must not hide the verdict
+            where = f"\nError in template {src[0]} line: {src[2]} ({os.path.basename(src[1])})" if src else ""
+            raise PzkError(f"Assert Failed. (status {st}, first failing constraint {fb}){where}")
 
     # ---- batched product path
     def calculateWitnessBatch(self, inputs, export_lanes=()) -> BatchResult:

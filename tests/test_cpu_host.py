@@ -561,6 +561,39 @@ def test_malformed_r1cs_and_wtns_are_format_errors_not_wild_reads(artifacts_dir,
     assert L.pzk_wtns_check(r1, bytes(bad), len(bad), 0, ctypes.byref(v), ctypes.byref(fb), err, len(err)) == -7
 
 
+def test_failing_constraint_maps_to_template_and_line(artifacts_dir):
+    """witness_calculator.js reports "Assert Failed." with "Error in template X line: N" (SURVEY.md 8b): pzk_compile
+    writes <prefix>.rowsrc, the source location of every constraint that is checked at run time; rows the compiler
+    discharged cannot fail and have no entry."""
+    prefix = os.path.join(artifacts_dir, "t_mix")
+    lines = open(os.path.join(ROOT, "tests", "circuits", "mix.circom")).read().split("\n")
+    kinds = np.fromfile(prefix + ".rowkind", dtype=np.uint8)
+    seen = set()
+    for r in range(len(kinds)):
+        src = W.constraint_source(prefix + ".pzkp", r)
+        if kinds[r]:
+            assert src is None, (r, src)
+            continue
+        tmpl, fname, line = src
+        assert os.path.basename(fname) == "mix.circom" and tmpl in ("Mix", "Bits", "NonZeroInv", "Less")
+        assert "===" in lines[line - 1] or "<==" in lines[line - 1], (r, lines[line - 1])
+        seen.add(tmpl)
+    assert {"Mix", "Bits", "NonZeroInv"} <= seen
+    assert W.constraint_source(prefix + ".pzkp", -1) is None and W.constraint_source(prefix + ".pzkp", 10 ** 9) is None
+    # registerIdentity: a flipped signature limb fails inside the RSA verifier of the reference
+    if os.path.exists(os.path.join(artifacts_dir, "c3.rowsrc")):
+        prog = oracle_ref.RefProgram(W.artifact("c3"))
+        fac = PassportFactory(C3, seed=3, n_sig_keys=1, n_aa_keys=1)
+        inp = W.pack_inputs_fast(prog.meta, [fac.make(0).inputs])
+        d = {x["name"]: x for x in prog.meta["inputs"]}
+        inp[0, d["signature"]["offset"] + 3, 0] ^= np.uint64(1 << 17)
+        st, fb, _ = prog.witness(inp[0], want_witness=False)
+        assert st & W.STATUS_CONSTRAINT and fb >= 0
+        tmpl, fname, line = W.constraint_source(W.artifact("c3"), fb)
+        assert fname.endswith(".circom") and line > 0 and tmpl
+        assert "bigInt" in fname or "rsa" in fname.lower() or "signature" in fname.lower(), (tmpl, fname, line)
+
+
 def test_every_program_walks_to_its_last_record(artifacts_dir):
     """Extension records, digest descriptors (of the result and of a fused product) and the term records of the
     rows are all counted in the headers they follow (pzk_program.h): a walk over the op stream of every built
