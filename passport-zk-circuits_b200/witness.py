@@ -411,8 +411,7 @@ class WitnessCalculator:
         self._raise_status(st.value, fb.value, sanityCheck)
         return out.raw
 
-    @staticmethod
-    def _raise_status(st, fb, sanity):
+    def _raise_status(self, st, fb, sanity):
         if st & STATUS_INPUT_RANGE:
             raise PzkError("Input out of its declared range (status 4)")
         if st & STATUS_BIGDIV:

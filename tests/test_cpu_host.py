@@ -594,6 +594,25 @@ def test_failing_constraint_maps_to_template_and_line(artifacts_dir):
         assert "bigInt" in fname or "rsa" in fname.lower() or "signature" in fname.lower(), (tmpl, fname, line)
 
 
+def test_assert_failed_message_carries_the_trace(artifacts_dir):
+    """The status -> exception mapping of the host mirror, exercised without a device (a bare instance with the one
+    attribute the method reads): the strings of witness_calculator.js, the trace where the side file has the row."""
+    c = W.WitnessCalculator.__new__(W.WitnessCalculator)
+    c._program_path = os.path.join(artifacts_dir, "t_mix.pzkp")
+    c._raise_status(0, -1, True)                                             # a valid lane raises nothing
+    with pytest.raises(W.PzkError, match=r"Assert Failed\. .*\nError in template Mix line: 58 \(mix\.circom\)"):
+        c._raise_status(W.STATUS_CONSTRAINT, 6, True)
+    with pytest.raises(W.PzkError, match=r"Assert Failed\. \(status 1, first failing constraint -1\)$"):
+        c._raise_status(W.STATUS_ASSERT, -1, True)
+    with pytest.raises(W.PzkError, match="declared range"):
+        c._raise_status(W.STATUS_INPUT_RANGE, -1, True)
+    with pytest.raises(W.PzkError, match="long division precondition"):
+        c._raise_status(W.STATUS_BIGDIV, -1, True)
+    c._program_path = os.path.join(artifacts_dir, "no_such_program.pzkp")     # no side file: the verdict alone
+    with pytest.raises(W.PzkError, match=r"first failing constraint 6\)$"):
+        c._raise_status(W.STATUS_CONSTRAINT, 6, True)
+
+
 def test_every_program_walks_to_its_last_record(artifacts_dir):
     """Extension records, digest descriptors (of the result and of a fused product) and the term records of the
     rows are all counted in the headers they follow (pzk_program.h): a walk over the op stream of every built
